@@ -1,0 +1,27 @@
+"""CPU oracle for the pairwise-ranking hot path -- TEST INFRASTRUCTURE ONLY.
+
+This package restates, on the CPU, the arithmetic of the reference's hot path
+(BinFuPKU/CollaborativeFilteringUsingTensorflow: src/models/pl/models/{bprmf,cml,gbprmf}.py,
+src/models/basic/models/wrmf.py, src/samplers/sampler_*.py, src/metrics/ranking.py).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import it, and only as the checker or the timed CPU
+baseline.  The product package ``collaborativefilteringusingtensorflow_b200`` never
+imports it and has no CPU fallback.
+
+Pinning status
+--------------
+* ``oracle.ranking``  -- PINNED: checked against the reference's own ``ranking.py`` run
+  live in the build container and against the golden vectors captured from its
+  ``__main__`` toy inputs (tests/golden/ranking_golden.json, made by oracle/gen_golden.py).
+* ``oracle.samplers`` -- PINNED on invariants/dtypes/shapes against the reference samplers
+  run live (tests/golden/sampler_golden.json); streams are unseeded in the reference so no
+  stream-level golden vectors exist.
+* ``oracle.steps`` / ``oracle.scoring`` -- **PARITY UNPINNED against TensorFlow itself**: the
+  arithmetic lives in third-party TensorFlow (>=1.13, unpinned, README.md:20-22), which is
+  not installable here and for which the reference ships no tests or golden vectors.  The
+  restatement follows the reference call sites line by line and TF1's published semantics
+   and is cross-checked against an independent torch-autograd
+  restatement of the same TF graph with ``torch.optim.Adagrad(initial_accumulator_value=0.1,
+  eps=0)`` (tests/golden/step_golden.npz, made by oracle/gen_golden.py).
+"""

@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""Generate tests/golden/* by RUNNING THE REFERENCE where it runs.  TEST INFRASTRUCTURE.
+
+Run in the build container (needs /root/reference; the GPU box does not have it):
+
+    python oracle/gen_golden.py            # writes tests/golden/*.json|*.npz
+
+What comes from where
+---------------------
+* ranking_golden.json  -- outputs of the reference's own /root/reference/src/metrics/ranking.py
+  (imported as-is) on its ``__main__`` toy inputs (ranking.py:125,131) and on seeded random inputs.
+* sampler_golden.json  -- shapes / dtypes / invariant checks of the reference's own samplers
+  (/root/reference/src/samplers/sampler_{ranking,uij_ranking,gbpr,rating}.py imported as-is) on ml-100k fold 1.
+* ml100k_fold1.npz     -- the bundled /root/reference/data/movielens/ml-100k/ratings__1_{tra,tst}.txt parsed by the
+  reference's own loadSparseR + matBinarize (utils/IOUtil.py:7-16, Util.py:15-16), stored as int16/int8 triplets.
+* step_golden.npz      -- TensorFlow is not installable, so the TF graphs of bprmf.py:52-88, cml.py:55-129,
+  gbprmf.py:58-106, wrmf.py:52-88 are restated with torch autograd + torch.optim.Adagrad(lr,
+  initial_accumulator_value=0.1, eps=0) (== TF1 AdagradOptimizer on summed sparse grads).  This is an
+  INDEPENDENT restatement (autodiff, not the hand-derived gradients of oracle/steps.py).
+* e2e_golden.json      -- oracle-trained ml-100k fold-1 metrics (reference hyper-parameters of testbprmf.py:21-30).
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+REF = '/root/reference/src'
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+OUT = os.path.join(ROOT, 'tests', 'golden')
+sys.path.insert(0, ROOT)
+
+
+def ref_import():
+    for sub in ('metrics', 'samplers', 'utils'):
+        sys.path.insert(0, os.path.join(REF, sub))
+    import ranking as ref_ranking          # noqa
+    import IOUtil                           # noqa
+    import Util                             # noqa
+    return ref_ranking, IOUtil, Util
+
+
+def gen_ranking(ref_ranking):
+    cases = []
+    toyA = dict(yss_true=[[4, 2], [3, 1], [1]], yss_pred=[[3, 1, 2], [1, 2], [2, 3, 1]], k=3)
+    toyB = [dict(yss_true=[[0, 1, 3, 4, 5, 8, 10, 12, 16, 18]], yss_pred=[list(range(20))], k=k) for k in (5, 10, 20)]
+    rng = np.random.default_rng(2026)
+    rnd = []
+    for n_users, n_items, k in ((7, 30, 5), (40, 200, 10), (25, 60, 20), (10, 15, 12)):
+        yt = [sorted(rng.choice(n_items, size=int(rng.integers(1, 12)), replace=False).tolist()) for _ in range(n_users)]
+        yp = [rng.permutation(n_items)[:int(rng.integers(max(1, k - 3), k + 4))].tolist() for _ in range(n_users)]
+        rnd.append(dict(yss_true=yt, yss_pred=yp, k=k))
+    names = ['pre', 'recall', 'ndcg', 'map', 'mrr']
+    for c in [toyA] + toyB + rnd:
+        yt = [set(x) for x in c['yss_true']]
+        c['cv'] = dict(zip(names, ref_ranking.evaluateCV(yt, c['yss_pred'], names, c['k'])))
+        cases.append(c)
+    loov = [dict(ys_true=[1, 5], yss_pred=[[3, 1, 2], [1, 2, 3]], k=3)]
+    for n_users, n_items, k in ((30, 50, 5), (12, 20, 10)):
+        loov.append(dict(ys_true=rng.integers(0, n_items, n_users).tolist(),
+                         yss_pred=[rng.permutation(n_items)[:k + 2].tolist() for _ in range(n_users)], k=k))
+    for c in loov:
+        c['loov'] = dict(zip(['hr', 'arhr'], ref_ranking.evaluateLOOV(c['ys_true'], c['yss_pred'], ['hr', 'arhr'], c['k'])))
+    unknown = ref_ranking.evaluateCV([{1}], [[1]], ['auc', 'pre'], 1)
+    json.dump(dict(cv=cases, loov=loov, unknown_metric=unknown), open(os.path.join(OUT, 'ranking_golden.json'), 'w'))
+    print('ranking_golden.json:', len(cases), 'cv cases,', len(loov), 'loov cases')
+
+
+def load_ml100k(IOUtil, Util):
+    from scipy.sparse import lil_matrix
+    d = '/root/reference/data/movielens/ml-100k/'
+    nu, ni = 943, 1682
+    raw, bins = {}, {}
+    for part in ('tra', 'tst'):
+        sR = IOUtil.loadSparseR(nu, ni, d + 'ratings__1_%s.txt' % part)
+        raw[part] = sR
+        bins[part] = lil_matrix(Util.matBinarize(sR, 3))
+    return nu, ni, raw, bins
+
+
+def gen_ml100k(IOUtil, Util):
+    nu, ni, raw, bins = load_ml100k(IOUtil, Util)
+    arrs = {}
+    for part in ('tra', 'tst'):
+        coo = raw[part].tocoo()
+        order = np.lexsort((coo.col, coo.row))
+        arrs[part + '_u'] = coo.row[order].astype(np.int16)
+        arrs[part + '_i'] = coo.col[order].astype(np.int16)
+        arrs[part + '_r'] = coo.data[order].astype(np.int8)
+    tst_users = sorted(set(np.asarray(bins['tst'].nonzero()[0]).tolist()))
+    stats = dict(n_users=nu, n_items=ni, tra_rows=int(raw['tra'].nnz), tst_rows=int(raw['tst'].nnz),
+                 tra_pos=int(bins['tra'].nnz), tst_pos=int(bins['tst'].nnz), n_test_users=len(tst_users),
+                 max_train_size=int(max(len(r) for r in bins['tra'].rows)))
+    np.savez_compressed(os.path.join(OUT, 'ml100k_fold1.npz'), **arrs)
+    json.dump(stats, open(os.path.join(OUT, 'ml100k_fold1_stats.json'), 'w'))
+    print('ml100k_fold1:', stats)
+    return nu, ni, bins
+
+
+def gen_sampler(bins):
+    """Run the reference's own samplers (threads never stop -> caller must os._exit)."""
+    import sampler_ranking, sampler_uij_ranking, sampler_gbpr, sampler_rating   # noqa
+    from oracle import samplers as chk
+    tra = bins['tra']
+    out = {}
+    s = sampler_ranking.Sampler(trasR=tra, n_neg=5, batch_size=100)
+    nb = int(tra.nnz / 100)
+    batches = [s.next_batch() for _ in range(nb)]
+    # The reference queues a VIEW of its pair array (sampler_ranking.py:27,37) which the next epoch's in-place
+    # shuffle (:24) can mutate before the queue's feeder thread pickles it: the last batch of an epoch can come out
+    # with pairs that no longer match its negatives.  Record which batches are hit; everything else must be valid.
+    invalid = [k for k, b in enumerate(batches) if not chk.negatives_are_valid(tra, np.array(b[0])[:, 0], b[1])]
+    batches_ok = [b for k, b in enumerate(batches) if k not in invalid]
+    pairs = np.concatenate([np.array(b[0]) for b in batches_ok])
+    negs = np.concatenate([b[1] for b in batches_ok])
+    out['ranking'] = dict(pairs_dtype=str(batches[0][0].dtype), negs_dtype=str(batches[0][1].dtype),
+                          pairs_shape=list(batches[0][0].shape), negs_shape=list(batches[0][1].shape),
+                          batches_per_epoch=nb, race_hit_batches=invalid,
+                          negatives_valid=chk.negatives_are_valid(tra, pairs[:, 0], negs),
+                          pairs_positive=chk.pairs_are_positives(tra, pairs),
+                          neg_mean=float(negs.mean()), n_items=int(tra.shape[1]))
+    s = sampler_uij_ranking.Sampler(trasR=tra, batch_size=100)
+    b = s.next_batch()
+    out['uij'] = dict(dtype=str(b.dtype), shape=list(b.shape),
+                      negatives_valid=chk.negatives_are_valid(tra, b[:, 0], b[:, 2:3]))
+    s = sampler_gbpr.Sampler(tra, 3, 5, 100)
+    p, n, g = s.next_batch()
+    out['gbpr'] = dict(pairs_dtype=str(p.dtype), negs_dtype=str(n.dtype), group_dtype=str(g.dtype),
+                       group_shape=list(g.shape), group_valid=chk.group_members_are_valid(tra, p[:, 1], g),
+                       negatives_valid=chk.negatives_are_valid(tra, p[:, 0], n))
+    s = sampler_rating.Sampler(tra, 1, 100)
+    b0, b1 = s.next_batch(), s.next_batch()
+    pos0 = b0[b0[:, 2] > 0]
+    first100 = chk._pairs_of(tra)[:100]
+    out['rating'] = dict(dtype=str(b0.dtype), shape=list(b0.shape), n_pos=int((b0[:, 2] > 0).sum()),
+                         positives_in_file_order=bool(set(map(tuple, pos0[:, :2].astype(int).tolist())) ==
+                                                      set(map(tuple, first100.tolist()))),
+                         neg_valid=chk.negatives_are_valid(tra, b0[b0[:, 2] == 0][:, 0].astype(int),
+                                                           b0[b0[:, 2] == 0][:, 1:2].astype(int)),
+                         second_batch_differs=bool(not np.array_equal(np.sort(b0, 0), np.sort(b1, 0))))
+    json.dump(out, open(os.path.join(OUT, 'sampler_golden.json'), 'w'), indent=1)
+    print('sampler_golden.json:', json.dumps(out)[:400], '...')
+
+
+# ---------------------------------------------------------------- torch-autograd restatement of the TF graphs
+def _torch_models():
+    import torch
+
+    def l2(t):
+        return (t * t).sum() / 2                                   # tf.nn.l2_loss
+
+    def bpr_loss(P, pairs, negs, h):                               # bprmf.py:52-75
+        U, V = P['U'], P['V']
+        u, i, j = U[pairs[:, 0]], V[pairs[:, 1]], V[negs]
+        ui = (u * i).sum(1)
+        uj = (u[:, None, :] * j).sum(-1)
+        emb = (-torch.log(torch.sigmoid(ui[:, None] - uj))).sum()
+        return emb + h['reg'] * (l2(u) + l2(i) + l2(j))
+
+    def cml_loss(P, pairs, negs, h):                               # cml.py:55-109
+        U, V = P['U'], P['V']
+        u, i, j = U[pairs[:, 0]], V[pairs[:, 1]], V[negs]
+        dp = ((u - i) ** 2).sum(1)
+        dn = ((u[:, None, :] - j) ** 2).sum(-1)
+        closest = torch.amin(dn, 1)                                # reduce_min: grad split evenly among ties
+        lp = torch.relu(dp - closest + h['margin'])
+        if h['use_rank_weight']:
+            imp = ((dp[:, None] - dn + h['margin']) > 0).float()
+            lp = lp * torch.log(imp.mean(1) * V.shape[0] + 1.0)
+        loss = lp.sum()
+        if h['reg_cov'] > 0:
+            loss = loss + h['reg_cov'] * (l2(u) + l2(i) + l2(j))
+        return loss
+
+    def gbpr_loss(P, pairs, negs, group, h):                       # gbprmf.py:58-93
+        U, V, b = P['U'], P['V'], P['b']
+        u, i, js, g = U[pairs[:, 0]], V[pairs[:, 1]], V[negs], U[group]
+        ib, jb = b[pairs[:, 1]], b[negs]
+        ui_u = (u * i).sum(-1)
+        ui_g = (g * i[:, None, :]).sum((1, 2)) / float(group.shape[1])
+        ui = h['rho'] * ui_g + (1 - h['rho']) * ui_u + ib
+        uj = (u[:, None, :] * js).sum(-1) + jb
+        emb = (-torch.log(torch.sigmoid(ui[:, None] - uj))).sum()
+        return emb + h['reg'] * (l2(u) + l2(g) + l2(i) + l2(jb))
+
+    def wrmf_loss(P, ui, r, h):                                    # wrmf.py:52-75
+        U, V = P['U'], P['V']
+        u, i = U[ui[:, 0]], V[ui[:, 1]]
+        pred = (u * i).sum(1)
+        return l2((pred - r) * float(np.sqrt(h['weight']))) + h['reg'] * (l2(u) + l2(i))
+
+    return torch, bpr_loss, cml_loss, gbpr_loss, wrmf_loss
+
+
+def gen_steps():
+    torch, bpr_loss, cml_loss, gbpr_loss, wrmf_loss = _torch_models()
+    from oracle.steps import truncated_normal
+    torch.set_num_threads(1)
+    rng = np.random.default_rng(7)
+    out = {}
+
+    def run(name, params, loss_fn, batches, h, clip=None, n_steps=2):
+        P = {k: torch.tensor(v, requires_grad=True) for k, v in params.items()}
+        opt = torch.optim.Adagrad(list(P.values()), lr=h['lr'], initial_accumulator_value=0.1, eps=0)
+        for k, v in params.items():
+            out['%s/init/%s' % (name, k)] = v
+        for s in range(n_steps):
+            opt.zero_grad()
+            loss = loss_fn(P, *[torch.tensor(x) for x in batches[s]], h)
+            loss.backward()
+            opt.step()
+            if clip is not None:                                   # cml.py:119-129: whole tables, every step
+                with torch.no_grad():
+                    for k in ('U', 'V'):
+                        n = P[k].norm(dim=1, keepdim=True)
+                        P[k].mul_(clip / torch.maximum(n, torch.tensor(clip)))
+            out['%s/loss%d' % (name, s)] = np.float64(loss.item())
+            for k in P:
+                out['%s/step%d/%s' % (name, s, k)] = P[k].detach().numpy().copy()
+                out['%s/step%d/acc%s' % (name, s, k)] = opt.state[P[k]]['sum'].numpy().copy()
+            for bi, x in enumerate(batches[s]):
+                out['%s/batch%d/%d' % (name, s, bi)] = x
+        out[name + '/hyper'] = np.array(json.dumps(h))
+
+    nu, ni = 60, 90      # small tables so duplicate rows (and u in its own group) are the norm at B=100
+    for name, d, W in (('bpr', 100, 1), ('bpr_w3', 20, 3)):
+        U, V = truncated_normal(rng, (nu, d)), truncated_normal(rng, (ni, d))
+        bt = [(np.stack([rng.integers(0, nu, 100), rng.integers(0, ni, 100)], 1), rng.integers(0, ni, (100, W)))
+              for _ in range(2)]
+        run(name, dict(U=U, V=V), bpr_loss, bt, dict(lr=0.1, reg=0.1))
+    for name, d, W, rw, rc in (('cml', 50, 5, True, 1.0), ('cml_norank_noreg', 12, 4, False, 0.0)):
+        U = (0.1 * rng.standard_normal((nu, d))).astype(np.float32)
+        V = (0.1 * rng.standard_normal((ni, d))).astype(np.float32)
+        if name == 'cml_norank_noreg':
+            U *= 4
+            V *= 4
+        bt = [(np.stack([rng.integers(0, nu, 50), rng.integers(0, ni, 50)], 1), rng.integers(0, ni, (50, W)))
+              for _ in range(2)]
+        run(name, dict(U=U, V=V), cml_loss, bt,
+            dict(lr=0.1, reg_cov=rc, margin=1.0 if rw else 0.5, use_rank_weight=rw, clip_norm=1.0), clip=1.0)
+    for name, d, W, G in (('gbpr', 64, 5, 3), ('gbpr_g1', 100, 5, 1)):
+        U, V = truncated_normal(rng, (nu, d)), truncated_normal(rng, (ni, d))
+        b = truncated_normal(rng, (ni,))
+        bt = [(np.stack([rng.integers(0, nu, 100), rng.integers(0, ni, 100)], 1), rng.integers(0, ni, (100, W)),
+               rng.integers(0, nu, (100, G))) for _ in range(2)]
+        run(name, dict(U=U, V=V, b=b), gbpr_loss, bt, dict(lr=0.1, reg=0.01, rho=0.4))
+    U, V = truncated_normal(rng, (nu, 100)), truncated_normal(rng, (ni, 100))
+    bt = [(np.stack([rng.integers(0, nu, 200), rng.integers(0, ni, 200)], 1),
+           (rng.random(200) < 0.5).astype(np.float32)) for _ in range(2)]
+    run('wrmf', dict(U=U, V=V), wrmf_loss, bt, dict(lr=0.1, reg=0.1, weight=2.0))
+    np.savez_compressed(os.path.join(OUT, 'step_golden.npz'), **out)
+    print('step_golden.npz:', len(out), 'arrays')
+
+
+def gen_e2e(nu, ni, bins, ref_ranking):
+    """ml-100k fold 1, BPRMF with the reference driver's hyper-parameters (testbprmf.py:21-30), trained by the
+    numpy oracle; evaluated with the reference's own ranking.py."""
+    from oracle import steps, samplers, scoring
+    tra, tst = bins['tra'], bins['tst']
+    rng = np.random.default_rng(2026)
+    d, B, W, reg, lr, epochs, topn = 100, 100, 1, 0.1, 0.1, 20, 10
+    U, V = steps.truncated_normal(rng, (nu, d)), steps.truncated_normal(rng, (ni, d))
+    aU, aV = np.full_like(U, 0.1), np.full_like(V, 0.1)
+    gen = samplers.ranking_batches(tra, W, B, seed=2026)
+    nb = int(tra.nnz / B)
+    test_users = sorted(set(np.asarray(tst.nonzero()[0]).tolist()))
+    yss_true = [set(tst.rows[u]) for u in test_users]
+    train_sets = [set(tra.rows[u]) for u in test_users]
+    names = ['pre', 'recall', 'map', 'mrr', 'ndcg']
+    hist = []
+    for ep in range(epochs):
+        for _ in range(nb):
+            p, n = next(gen)
+            steps.bpr_step(U, V, aU, aV, p, n, lr, reg)
+        if ep in (9, 19):
+            top = scoring.topn_masked(scoring.scores_f64(U[test_users], V), train_sets, topn)
+            sc = ref_ranking.evaluateCV(yss_true, [r.tolist() for r in top], names, topn)
+            hist.append(dict(epoch=ep + 1, **dict(zip(names, sc))))
+            print('e2e oracle BPRMF epoch', ep + 1, hist[-1])
+    json.dump(dict(model='BPRMF', hyper=dict(n_factors=d, batch_size=B, n_neg=W, reg=reg, lr=lr, topN=topn),
+                   history=hist), open(os.path.join(OUT, 'e2e_golden.json'), 'w'), indent=1)
+
+
+if __name__ == '__main__':
+    os.makedirs(OUT, exist_ok=True)
+    what = set(sys.argv[1:]) or {'ranking', 'ml100k', 'steps', 'sampler', 'e2e'}
+    ref_ranking, IOUtil, Util = ref_import()
+    if 'ranking' in what:
+        gen_ranking(ref_ranking)
+    if 'steps' in what:
+        gen_steps()
+    if what & {'ml100k', 'sampler', 'e2e'}:
+        nu, ni, bins = gen_ml100k(IOUtil, Util)
+        if 'e2e' in what:
+            gen_e2e(nu, ni, bins, ref_ranking)
+        if 'sampler' in what:
+            gen_sampler(bins)
+    sys.stdout.flush()
+    os._exit(0)      # the reference's sampler threads never stop (sampler_ranking.py:23)

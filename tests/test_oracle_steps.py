@@ -1,0 +1,108 @@
+"""The numpy oracle (hand-derived gradients) vs the independent torch-autograd restatement of the TF graphs
+(tests/golden/step_golden.npz, made by oracle/gen_golden.py).  CPU only."""
+import json
+
+import numpy as np
+import pytest
+
+from oracle import steps
+
+RTOL = 1e-5   # north_star: 'within 1e-5 relative (fp32)'; atol 1e-6 covers elements near zero (|x| ~ 0.1 scale)
+
+
+def _load(g, name, k):
+    return {p: g['%s/init/%s' % (name, p)].copy() for p in k}
+
+
+def _close(a, b, rtol=RTOL):
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=1e-6)
+
+
+@pytest.mark.parametrize('name', ['bpr', 'bpr_w3'])
+def test_bpr_oracle_matches_autograd(step_golden, name):
+    g = step_golden
+    h = json.loads(str(g[name + '/hyper']))
+    P = _load(g, name, 'UV')
+    aU, aV = np.full_like(P['U'], 0.1), np.full_like(P['V'], 0.1)
+    for s in range(2):
+        pairs, negs = g['%s/batch%d/0' % (name, s)], g['%s/batch%d/1' % (name, s)]
+        loss = steps.bpr_step(P['U'], P['V'], aU, aV, pairs, negs, h['lr'], h['reg'])
+        assert abs(loss - float(g['%s/loss%d' % (name, s)])) < 1e-4 * abs(loss)
+        _close(P['U'], g['%s/step%d/U' % (name, s)])
+        _close(P['V'], g['%s/step%d/V' % (name, s)])
+        _close(aU, g['%s/step%d/accU' % (name, s)])
+        _close(aV, g['%s/step%d/accV' % (name, s)])
+
+
+@pytest.mark.parametrize('name', ['cml', 'cml_norank_noreg'])
+def test_cml_oracle_matches_autograd(step_golden, name):
+    g = step_golden
+    h = json.loads(str(g[name + '/hyper']))
+    P = _load(g, name, 'UV')
+    aU, aV = np.full_like(P['U'], 0.1), np.full_like(P['V'], 0.1)
+    for s in range(2):
+        pairs, negs = g['%s/batch%d/0' % (name, s)], g['%s/batch%d/1' % (name, s)]
+        f = steps.cml_forward(P['U'], P['V'], pairs, negs, h['margin'], h['use_rank_weight'], P['V'].shape[0])
+        assert f['kink'] > 1e-5, 'golden inputs sit on a relu/indicator kink'
+        loss = steps.cml_step(P['U'], P['V'], aU, aV, pairs, negs, h['lr'], h['reg_cov'], h['margin'],
+                              h['use_rank_weight'], h['clip_norm'])
+        assert abs(loss - float(g['%s/loss%d' % (name, s)])) < 1e-4 * max(1.0, abs(loss))
+        _close(P['U'], g['%s/step%d/U' % (name, s)])
+        _close(P['V'], g['%s/step%d/V' % (name, s)])
+        _close(aU, g['%s/step%d/accU' % (name, s)])
+        _close(aV, g['%s/step%d/accV' % (name, s)])
+
+
+def test_cml_touched_row_clip_equals_whole_table_clip_after_first_step(step_golden):
+    """once every row has norm <= clip, clipping only the touched rows == the reference's whole-table clip."""
+    g = step_golden
+    name = 'cml'
+    h = json.loads(str(g[name + '/hyper']))
+    A = _load(g, name, 'UV')
+    B = {k: v.copy() for k, v in A.items()}
+    accA = [np.full_like(A['U'], 0.1), np.full_like(A['V'], 0.1)]
+    accB = [x.copy() for x in accA]
+    for s in range(2):
+        pairs, negs = g['%s/batch%d/0' % (name, s)], g['%s/batch%d/1' % (name, s)]
+        steps.cml_step(A['U'], A['V'], accA[0], accA[1], pairs, negs, h['lr'], h['reg_cov'], h['margin'], True, 1.0)
+        steps.cml_step(B['U'], B['V'], accB[0], accB[1], pairs, negs, h['lr'], h['reg_cov'], h['margin'], True, 1.0,
+                       clip_whole_table=(s == 0))
+        _close(A['U'], B['U'], 1e-6)
+        _close(A['V'], B['V'], 1e-6)
+
+
+@pytest.mark.parametrize('name', ['gbpr', 'gbpr_g1'])
+def test_gbpr_oracle_matches_autograd(step_golden, name):
+    g = step_golden
+    h = json.loads(str(g[name + '/hyper']))
+    P = _load(g, name, 'UVb')
+    acc = {k: np.full_like(v, 0.1) for k, v in P.items()}
+    for s in range(2):
+        pairs, negs, group = (g['%s/batch%d/%d' % (name, s, k)] for k in range(3))
+        loss = steps.gbpr_step(P['U'], P['V'], P['b'], acc['U'], acc['V'], acc['b'], pairs, negs, group,
+                               h['lr'], h['reg'], h['rho'])
+        assert abs(loss - float(g['%s/loss%d' % (name, s)])) < 1e-4 * abs(loss)
+        for k in 'UVb':
+            _close(P[k], g['%s/step%d/%s' % (name, s, k)])
+            _close(acc[k], g['%s/step%d/acc%s' % (name, s, k)])
+
+
+def test_wrmf_oracle_matches_autograd(step_golden):
+    g = step_golden
+    name = 'wrmf'
+    h = json.loads(str(g[name + '/hyper']))
+    P = _load(g, name, 'UV')
+    aU, aV = np.full_like(P['U'], 0.1), np.full_like(P['V'], 0.1)
+    for s in range(2):
+        ui, r = g['%s/batch%d/0' % (name, s)], g['%s/batch%d/1' % (name, s)]
+        uir = np.concatenate([ui.astype(np.float64), r[:, None].astype(np.float64)], axis=1)
+        loss = steps.wrmf_step(P['U'], P['V'], aU, aV, uir, h['lr'], h['reg'], h['weight'])
+        assert abs(loss - float(g['%s/loss%d' % (name, s)])) < 1e-4 * abs(loss)
+        _close(P['U'], g['%s/step%d/U' % (name, s)])
+        _close(P['V'], g['%s/step%d/V' % (name, s)])
+        _close(aU, g['%s/step%d/accU' % (name, s)])
+
+
+def test_truncated_normal_bounds():
+    x = steps.truncated_normal(np.random.default_rng(0), (1000, 8), 0.0, 0.1)
+    assert x.dtype == np.float32 and np.abs(x).max() <= 0.2 + 1e-7 and 0.07 < x.std() < 0.1
