@@ -1,0 +1,23 @@
+"""B200-native pairwise-ranking training + full-catalog top-K evaluation behind the API of
+BinFuPKU/CollaborativeFilteringUsingTensorflow (models/pl/models/{bprmf,cml,gbprmf}.py, models/basic/models/wrmf.py,
+samplers/sampler_{ranking,uij_ranking,gbpr,rating}.py, metrics/ranking.py, utils/{IOUtil,Util}.py).
+
+All arithmetic runs in hand-written sm_100a CUDA (libcf_b200.so, C ABI in include/cf_b200.h); there is no CPU fallback.
+"""
+__version__ = '0.1.0'
+
+
+def __getattr__(name):   # lazy: importing the package must work on a box without a GPU (build / symbol checks)
+    if name == 'BPRMF':
+        from .models.pl.models.bprmf import BPRMF
+        return BPRMF
+    if name == 'CML':
+        from .models.pl.models.cml import CML
+        return CML
+    if name == 'GBPRMF':
+        from .models.pl.models.gbprmf import GBPRMF
+        return GBPRMF
+    if name == 'WRMF':
+        from .models.basic.models.wrmf import WRMF
+        return WRMF
+    raise AttributeError(name)

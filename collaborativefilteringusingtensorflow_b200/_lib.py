@@ -1,0 +1,126 @@
+"""ctypes binding of libcf_b200.so (C ABI declared in include/cf_b200.h).
+
+There is NO CPU fallback: if the CUDA library is missing or the ABI version differs this raises, and every
+product entry point goes through :func:`lib`.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libcf_b200.so')
+ABI_VERSION = 3
+
+# enums of cf_b200.h
+MODEL_BPR, MODEL_CML, MODEL_GBPR, MODEL_WRMF = 0, 1, 2, 3
+OPT_ADAGRAD, OPT_SGD = 0, 1
+UPDATE_SYNC, UPDATE_HOGWILD = 1, 0
+SCORE_DOT, SCORE_DOT_BIAS, SCORE_NEG_SQDIST = 0, 1, 2
+FLAG_INDEX_RANGE, FLAG_STAGING_FULL, FLAG_SAMPLER_GAVEUP, FLAG_TOPK_OVERFLOW = 1, 2, 4, 8
+
+_p = C.c_void_p
+
+
+class StepArgs(C.Structure):
+    _fields_ = [
+        ('U', _p), ('V', _p), ('b', _p), ('accU', _p), ('accV', _p), ('accb', _p),
+        ('n_users', C.c_int64), ('n_items', C.c_int64), ('d', C.c_int32), ('ld', C.c_int32),
+        ('pairs', _p), ('negs', _p), ('group', _p), ('ratings', _p),
+        ('B', C.c_int32), ('W', C.c_int32), ('G', C.c_int32), ('n_batches', C.c_int32),
+        ('model', C.c_int32), ('optimizer', C.c_int32), ('update', C.c_int32), ('use_rank_weight', C.c_int32),
+        ('lr', C.c_float), ('reg', C.c_float), ('margin', C.c_float), ('clip_norm', C.c_float),
+        ('rho', C.c_float), ('weight', C.c_float),
+        ('metaU', _p), ('metaV', _p), ('slotU', _p), ('slotV', _p), ('staging', _p),
+        ('staging_rows', C.c_int64), ('counters', _p), ('loss', _p),
+    ]
+
+
+class Csr(C.Structure):
+    _fields_ = [('indptr', _p), ('indices', _p), ('rows', _p), ('values', _p),
+                ('n_rows', C.c_int64), ('n_cols', C.c_int64), ('nnz', C.c_int64)]
+
+
+class SampleArgs(C.Structure):
+    _fields_ = [
+        ('train', Csr), ('train_t', Csr), ('seed', C.c_uint64), ('epoch', C.c_int64), ('batch0', C.c_int64),
+        ('n_batches', C.c_int32), ('B', C.c_int32), ('W', C.c_int32), ('G', C.c_int32),
+        ('n_neg_rows', C.c_int32), ('shuffle', C.c_int32),
+        ('out_pairs', _p), ('out_negs', _p), ('out_group', _p), ('out_ratings', _p), ('flags', _p),
+    ]
+
+
+class TopkArgs(C.Structure):
+    _fields_ = [
+        ('U', _p), ('V', _p), ('b', _p), ('n_users', C.c_int64), ('n_items', C.c_int64),
+        ('d', C.c_int32), ('ld', C.c_int32), ('users', _p), ('T', C.c_int32), ('K', C.c_int32), ('kind', C.c_int32),
+        ('train', Csr), ('out_idx', _p), ('out_val', _p), ('flags', _p),
+        ('item_lo', C.c_int64), ('item_hi', C.c_int64),
+    ]
+
+
+_SIGNATURES = {
+    'cf_last_error': (C.c_char_p, []),
+    'cf_abi_version': (C.c_int, []),
+    'cf_build_arch': (C.c_char_p, []),
+    'cf_train_steps': (C.c_int, [C.POINTER(StepArgs), _p]),
+    'cf_step_staging_rows': (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    'cf_step_launches_per_batch': (C.c_int32, []),
+    'cf_clip_rows': (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, _p]),
+    'cf_sample_ranking': (C.c_int, [C.POINTER(SampleArgs), _p]),
+    'cf_sample_rating': (C.c_int, [C.POINTER(SampleArgs), _p]),
+    'cf_topk_exact': (C.c_int, [C.POINTER(TopkArgs), _p]),
+    'cf_scores': (C.c_int, [C.POINTER(TopkArgs), _p, _p]),
+    'cf_topk_merge': (C.c_int, [_p, _p, C.c_int32, C.c_int32, C.c_int32, _p, _p, _p]),
+    'cf_rank_metrics': (C.c_int, [_p, C.c_int32, C.c_int32, C.c_int32, _p, _p, _p, _p]),
+}
+
+_lib = None
+
+
+class CudaLibraryError(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded CUDA library; raises CudaLibraryError (never falls back) if it cannot be used."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CudaLibraryError(
+            '%s is missing: build it with `python -m collaborativefilteringusingtensorflow_b200.build` '
+            '(needs nvcc, targets sm_100a). There is no CPU fallback.' % LIB_PATH)
+    try:
+        h = C.CDLL(LIB_PATH)
+    except OSError as e:
+        raise CudaLibraryError('cannot load %s: %s' % (LIB_PATH, e))
+    for name, (res, args) in _SIGNATURES.items():
+        try:
+            fn = getattr(h, name)
+        except AttributeError:
+            raise CudaLibraryError('%s does not export %s (stale build?)' % (LIB_PATH, name))
+        fn.restype, fn.argtypes = res, args
+    if h.cf_abi_version() != ABI_VERSION:
+        raise CudaLibraryError('ABI mismatch: library %d, binding %d; rebuild' % (h.cf_abi_version(), ABI_VERSION))
+    _lib = h
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError('%s failed (%d): %s' % (what, rc, lib().cf_last_error().decode()))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise CudaLibraryError('no CUDA device: this package runs on a B200 only (no CPU fallback)')
+    return torch

@@ -1,0 +1,280 @@
+"""Device state + kernel launches shared by the four model classes (host side of the C ABI).
+
+Holds what the reference keeps in TF variables and Adagrad slots (bprmf.py:29-34,86): the embedding tables,
+their accumulators and -- new here -- the per-row occurrence workspace of the fused step kernel.
+torch is used for device memory and streams only; all arithmetic is in libcf_b200.so.
+"""
+import numpy as np
+
+from . import _lib
+from .sparse import DeviceCSR, null_csr
+
+_MODEL_IDS = {'bpr': _lib.MODEL_BPR, 'cml': _lib.MODEL_CML, 'gbpr': _lib.MODEL_GBPR, 'wrmf': _lib.MODEL_WRMF}
+_SCORE_KIND = {'bpr': _lib.SCORE_DOT, 'cml': _lib.SCORE_NEG_SQDIST, 'gbpr': _lib.SCORE_DOT_BIAS, 'wrmf': _lib.SCORE_DOT}
+_OPT = {'adagrad': _lib.OPT_ADAGRAD, 'sgd': _lib.OPT_SGD}
+_UPD = {'sync': _lib.UPDATE_SYNC, 'hogwild': _lib.UPDATE_HOGWILD}
+
+ADAGRAD_ACC0 = 0.1   # tf.train.AdagradOptimizer initial_accumulator_value
+
+
+def resolve_device(device):
+    """The reference's ``device='CPU'|'GPU'`` (bprmf.py:26-27) picks a TF device; here everything runs on CUDA."""
+    torch = _lib.require_cuda()
+    if isinstance(device, torch.device):
+        return device
+    s = str(device)
+    if s.upper() in ('CPU', 'GPU'):
+        return torch.device('cuda', torch.cuda.current_device())
+    return torch.device(s)
+
+
+def pad_ld(d):
+    return (int(d) + 3) // 4 * 4
+
+
+class FactorEngine(object):
+    def __init__(self, kind, n_users, n_items, n_factors, device='GPU', init_mean=0.0, init_stddev=0.1,
+                 optimizer='adagrad', update='sync', seed=None, **hyper):
+        torch = _lib.require_cuda()
+        self.torch = torch
+        self.lib = _lib.lib()
+        self.kind = kind
+        self.model_id = _MODEL_IDS[kind]
+        self.device = resolve_device(device)
+        self.n_users, self.n_items, self.d = int(n_users), int(n_items), int(n_factors)
+        self.ld = pad_ld(n_factors)
+        if self.ld > 512:
+            raise ValueError('n_factors up to 512 are supported')
+        self.optimizer, self.update = optimizer, update
+        self.hyper = dict(lr=0.1, reg=0.0, margin=0.0, clip_norm=1.0, rho=0.0, weight=1.0, use_rank_weight=False)
+        self.hyper.update(hyper)
+        gen = torch.Generator(device=self.device)
+        gen.manual_seed(int(seed) if seed is not None else int(np.random.SeedSequence().generate_state(1)[0]))
+        self.U = self._init_table(self.n_users, init_mean, init_stddev, gen, truncated=(kind != 'cml'))
+        self.V = self._init_table(self.n_items, init_mean, init_stddev, gen, truncated=(kind != 'cml'))
+        self.b = None
+        if kind == 'gbpr':   # gbprmf.py:36-38
+            self.b = torch.empty(self.n_items, device=self.device)
+            torch.nn.init.trunc_normal_(self.b, init_mean, init_stddev, init_mean - 2 * init_stddev,
+                                        init_mean + 2 * init_stddev, generator=gen)
+        self.accU = torch.full_like(self.U, ADAGRAD_ACC0)
+        self.accV = torch.full_like(self.V, ADAGRAD_ACC0)
+        self.accb = torch.full_like(self.b, ADAGRAD_ACC0) if self.b is not None else None
+        self.counters = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self._ws = None
+        self._ws_rows = 0
+        self._needs_full_clip = (kind == 'cml')
+        self.launches = 0
+
+    # ------------------------------------------------------------------ state
+    def _init_table(self, n, mean, std, gen, truncated):
+        torch = self.torch
+        t = torch.zeros(n, self.ld, device=self.device)
+        view = t[:, :self.d]
+        if truncated:   # tf.truncated_normal_initializer (bprmf.py:30): resample beyond 2 sigma
+            torch.nn.init.trunc_normal_(view, mean, std, mean - 2 * std, mean + 2 * std, generator=gen)
+        else:           # tf.random_normal_initializer (cml.py:33)
+            view.normal_(mean, std, generator=gen)
+        return t
+
+    def state_dict(self):
+        out = {'U': self.U[:, :self.d].clone(), 'V': self.V[:, :self.d].clone(),
+               'accU': self.accU[:, :self.d].clone(), 'accV': self.accV[:, :self.d].clone()}
+        if self.b is not None:
+            out['b'], out['accb'] = self.b.clone(), self.accb.clone()
+        return out
+
+    def load_state_dict(self, sd):
+        torch = self.torch
+        for name in ('U', 'V', 'accU', 'accV'):
+            if name in sd:
+                dst = getattr(self, name)
+                src = torch.as_tensor(np.asarray(sd[name]) if not torch.is_tensor(sd[name]) else sd[name],
+                                      dtype=torch.float32, device=self.device)
+                if tuple(src.shape) != (dst.shape[0], self.d):
+                    raise ValueError('%s: expected shape %s, got %s' % (name, (dst.shape[0], self.d), tuple(src.shape)))
+                dst[:, :self.d].copy_(src)
+        for name in ('b', 'accb'):
+            if name in sd and getattr(self, name) is not None:
+                getattr(self, name).copy_(torch.as_tensor(np.asarray(sd[name]) if not torch.is_tensor(sd[name])
+                                                          else sd[name], dtype=torch.float32, device=self.device))
+        self._needs_full_clip = (self.kind == 'cml')
+
+    # ------------------------------------------------------------------ workspace
+    def _workspace(self, B, W, G):
+        torch = self.torch
+        rows = int(self.lib.cf_step_staging_rows(self.model_id, B, W, G))
+        if self._ws is None or self._ws_rows < rows:
+            self._ws = dict(
+                metaU=torch.zeros(self.n_users, dtype=torch.int64, device=self.device),
+                metaV=torch.zeros(self.n_items, dtype=torch.int64, device=self.device),
+                slotU=torch.zeros(self.n_users, dtype=torch.int32, device=self.device),
+                slotV=torch.zeros(self.n_items, dtype=torch.int32, device=self.device),
+                staging=torch.zeros(rows, self.ld + 4, device=self.device))
+            self._ws_rows = rows
+        return self._ws
+
+    def reset_workspace(self):
+        if self._ws is not None:
+            for k in ('metaU', 'metaV', 'staging'):
+                self._ws[k].zero_()
+        self.counters.zero_()
+
+    def check_flags(self):
+        """Synchronises; raises on a device-side condition recorded by a previous launch."""
+        f = int(self.counters[1].item())
+        if f:
+            self.reset_workspace()
+            msgs = []
+            if f & _lib.FLAG_INDEX_RANGE:
+                msgs.append('batch index out of range (TF would raise InvalidArgumentError in the gather)')
+            if f & _lib.FLAG_STAGING_FULL:
+                msgs.append('gradient staging overflow')
+            if f & _lib.FLAG_SAMPLER_GAVEUP:
+                msgs.append('a user has (almost) every item as a positive: no negative found '
+                            '(the reference sampler would spin forever, sampler_ranking.py:35)')
+            raise RuntimeError('; '.join(msgs) or 'device flag %d' % f)
+
+    # ------------------------------------------------------------------ training
+    def _as_i32(self, x, cols=None):
+        torch = self.torch
+        if x is None:
+            return None
+        if not torch.is_tensor(x):
+            x = torch.from_numpy(np.ascontiguousarray(np.asarray(x)))
+        x = x.to(device=self.device, dtype=torch.int32, non_blocking=True).contiguous()
+        return x
+
+    def train_batches(self, pairs, negs=None, group=None, ratings=None, batch_size=None, want_loss=True):
+        """Run ``n = rows / batch_size`` consecutive minibatches (the inner loop of bprmf.py:143-148).
+        Index arrays may be numpy or torch (any int dtype); returns the per-minibatch loss as a CUDA float64
+        tensor (or None)."""
+        torch = self.torch
+        pairs = self._as_i32(pairs)
+        rows = int(pairs.shape[0])
+        B = int(batch_size or rows)
+        if rows == 0 or rows % B:
+            raise ValueError('rows (%d) must be a positive multiple of batch_size (%d)' % (rows, B))
+        nb = rows // B
+        W = G = 0
+        if self.kind != 'wrmf':
+            negs = self._as_i32(negs)
+            if negs is None or negs.dim() != 2 or negs.shape[0] != rows:
+                raise ValueError('negs must be [rows, W]')
+            W = int(negs.shape[1])
+        if self.kind == 'gbpr':
+            group = self._as_i32(group)
+            if group is None or group.dim() != 2 or group.shape[0] != rows:
+                raise ValueError('group must be [rows, G]')
+            G = int(group.shape[1])
+        if self.kind == 'wrmf':
+            if ratings is None:
+                raise ValueError('WRMF needs ratings')
+            if not torch.is_tensor(ratings):
+                ratings = torch.from_numpy(np.ascontiguousarray(np.asarray(ratings, dtype=np.float32)))
+            ratings = ratings.to(device=self.device, dtype=torch.float32).contiguous()
+        a = _lib.StepArgs()
+        a.U, a.V, a.b = _lib.ptr(self.U), _lib.ptr(self.V), _lib.ptr(self.b)
+        a.accU, a.accV, a.accb = _lib.ptr(self.accU), _lib.ptr(self.accV), _lib.ptr(self.accb)
+        a.n_users, a.n_items, a.d, a.ld = self.n_users, self.n_items, self.d, self.ld
+        a.pairs, a.negs, a.group = _lib.ptr(pairs), _lib.ptr(negs), _lib.ptr(group)
+        a.ratings = _lib.ptr(ratings) if self.kind == 'wrmf' else None
+        a.B, a.W, a.G, a.n_batches = B, W, G, nb
+        a.model, a.optimizer, a.update = self.model_id, _OPT[self.optimizer], _UPD[self.update]
+        h = self.hyper
+        a.use_rank_weight = int(bool(h['use_rank_weight']))
+        a.lr, a.reg, a.margin, a.clip_norm = h['lr'], h['reg'], h['margin'], h['clip_norm']
+        a.rho, a.weight = h['rho'], h['weight']
+        if self.update == 'sync':
+            ws = self._workspace(B, W, G)
+            a.metaU, a.metaV = _lib.ptr(ws['metaU']), _lib.ptr(ws['metaV'])
+            a.slotU, a.slotV = _lib.ptr(ws['slotU']), _lib.ptr(ws['slotV'])
+            a.staging, a.staging_rows = _lib.ptr(ws['staging']), ws['staging'].shape[0]
+        a.counters = _lib.ptr(self.counters)
+        loss = torch.zeros(nb, dtype=torch.float64, device=self.device) if want_loss else None
+        a.loss = _lib.ptr(loss)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        if self._needs_full_clip and nb > 1:
+            # the reference clips BOTH WHOLE tables after every step (cml.py:119-129); after the first such clip
+            # every row has norm <= clip_norm and clipping only the touched rows (fused) is the same thing
+            a.n_batches = 1
+            _lib.check(self.lib.cf_train_steps(a, stream), 'cf_train_steps')
+            self._full_clip(stream)
+            a.n_batches = nb - 1
+            a.pairs = pairs.data_ptr() + 4 * 2 * B
+            a.negs = negs.data_ptr() + 4 * W * B
+            a.loss = (loss.data_ptr() + 8) if want_loss else None
+            _lib.check(self.lib.cf_train_steps(a, stream), 'cf_train_steps')
+        else:
+            _lib.check(self.lib.cf_train_steps(a, stream), 'cf_train_steps')
+            if self._needs_full_clip:
+                self._full_clip(stream)
+        self.launches += nb * (2 if self.update == 'sync' else 1)
+        return loss
+
+    def _full_clip(self, stream):
+        c = float(self.hyper['clip_norm'])
+        _lib.check(self.lib.cf_clip_rows(_lib.ptr(self.U), self.n_users, self.d, self.ld, c, stream), 'cf_clip_rows')
+        _lib.check(self.lib.cf_clip_rows(_lib.ptr(self.V), self.n_items, self.d, self.ld, c, stream), 'cf_clip_rows')
+        self._needs_full_clip = False
+        self.launches += 2
+
+    # ------------------------------------------------------------------ evaluation
+    def _topk_args(self, users, K, train_csr, item_range=None):
+        torch = self.torch
+        a = _lib.TopkArgs()
+        a.U, a.V, a.b = _lib.ptr(self.U), _lib.ptr(self.V), _lib.ptr(self.b)
+        a.n_users, a.n_items, a.d, a.ld = self.n_users, self.n_items, self.d, self.ld
+        if users is None:
+            users_t, T = None, self.n_users
+        else:
+            users_t = self._as_i32(users)
+            T = int(users_t.numel())
+            if T and (int(users_t.min()) < 0 or int(users_t.max()) >= self.n_users):
+                raise ValueError('user id out of range')
+        a.users, a.T, a.K, a.kind = _lib.ptr(users_t), T, int(K), _SCORE_KIND[self.kind]
+        a.train = train_csr.as_c(False) if train_csr is not None else null_csr()
+        a.flags = _lib.ptr(self.counters[1:2])
+        a.item_lo, a.item_hi = item_range if item_range is not None else (0, 0)
+        return a, users_t, T
+
+    def topk(self, users, K, train_csr=None, return_values=False, item_range=None):
+        """Masked top-K item ids [T, K] int32 (and fp64 scores): bprmf.py:90-103 in one pass."""
+        torch = self.torch
+        if K <= 0:
+            raise ValueError('K must be positive')
+        a, users_t, T = self._topk_args(users, K, train_csr, item_range)
+        if T == 0:
+            raise ValueError('no query users')
+        out_idx = torch.empty(T, K, dtype=torch.int32, device=self.device)
+        out_val = torch.empty(T, K, dtype=torch.float64, device=self.device) if return_values else None
+        a.out_idx, a.out_val = _lib.ptr(out_idx), _lib.ptr(out_val)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.cf_topk_exact(a, stream), 'cf_topk_exact')
+        self.launches += 1
+        return (out_idx, out_val) if return_values else out_idx
+
+    def scores(self, users):
+        """Dense [T, n_items] fp64 score matrix of ``__predict__`` (small inputs only)."""
+        torch = self.torch
+        a, users_t, T = self._topk_args(users, 1, None)
+        out = torch.empty(T, self.n_items, dtype=torch.float64, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.cf_scores(a, _lib.ptr(out), stream), 'cf_scores')
+        self.launches += 1
+        return out
+
+
+def rank_metrics_device(pred_idx, truth_csr, k):
+    """Per-user metric values [T, 8] (float64, CUDA) = {pre, recall, ndcg, map, mrr, hit, rr, n_pred}."""
+    torch = _lib.require_cuda()
+    lib = _lib.lib()
+    pred_idx = pred_idx.contiguous()
+    T, ldp = int(pred_idx.shape[0]), int(pred_idx.shape[1])
+    if truth_csr.shape[0] != T or T == 0 or k <= 0:
+        raise ValueError('len(yss_true) != len(yss_pred) or len(yss_true)==0 or k<=0!')
+    out = torch.empty(T, 8, dtype=torch.float64, device=pred_idx.device)
+    stream = torch.cuda.current_stream(pred_idx.device).cuda_stream
+    _lib.check(lib.cf_rank_metrics(_lib.ptr(pred_idx), T, ldp, int(k), _lib.ptr(truth_csr.indptr),
+                                   _lib.ptr(truth_csr.indices), _lib.ptr(out), stream), 'cf_rank_metrics')
+    return out

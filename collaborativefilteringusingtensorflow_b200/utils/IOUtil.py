@@ -1,0 +1,37 @@
+"""reference src/utils/IOUtil.py:7-25: ``u<sep>i[<sep>r]`` text -> scipy lil_matrix, and the inverse writer.
+
+The reference inserts one element at a time into a lil_matrix; here the file is parsed in one pass into COO arrays
+(later entries for the same cell overwrite earlier ones, like the reference's repeated ``sR[u, i] = r``)."""
+import numpy as np
+from scipy.sparse import coo_matrix, lil_matrix
+
+from .Util import split_row
+
+
+def loadTriplets(inFilePath):
+    us, is_, rs = [], [], []
+    with open(inFilePath, 'r') as infile:
+        for line in infile:
+            phs = split_row(line)
+            if len(phs) == 2:
+                us.append(int(phs[0])); is_.append(int(phs[1])); rs.append(1.0)
+            elif len(phs) == 3:
+                us.append(int(phs[0])); is_.append(int(phs[1])); rs.append(float(phs[2]))
+    return np.asarray(us, dtype=np.int64), np.asarray(is_, dtype=np.int64), np.asarray(rs, dtype=np.float64)
+
+
+def loadSparseR(usernum, itemnum, inFilePath):
+    u, i, r = loadTriplets(inFilePath)
+    if len(u) and (u.min() < 0 or u.max() >= usernum or i.min() < 0 or i.max() >= itemnum):
+        raise IndexError('row/column index out of bounds')
+    key = u * itemnum + i
+    _, last = np.unique(key[::-1], return_index=True)        # last write wins
+    keep = len(key) - 1 - last
+    sR = coo_matrix((r[keep], (u[keep], i[keep])), shape=(usernum, itemnum)).tolil()
+    return lil_matrix(sR)
+
+
+def saveTriads(triads, outFilePath, isRatingInt=False):
+    with open(outFilePath, 'w') as outfile:
+        for user, item, rating in triads:
+            outfile.write(str(int(user)) + '\t' + str(int(item)) + ('\t%d\n' % rating if isRatingInt else '\t%.1f\n' % rating))

@@ -1,0 +1,209 @@
+/*
+ * cf_b200.h -- C ABI of libcf_b200.so: the B200 (sm_100a) implementation of the pairwise-ranking
+ * training + full-catalog top-K evaluation hot path of BinFuPKU/CollaborativeFilteringUsingTensorflow.
+ *
+ * The reference has no FFI/plugin boundary of its own (it is pure Python over TensorFlow 1.x); the
+ * boundary it does have is "numpy batch in -> sess.run(...) -> numpy out".  Every entry point below
+ * replaces one such sess.run / numpy-loop call site; the citation beside each names it
+ * (paths relative to the reference checkout, src/...).
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers unless the name ends in _host.  Nothing is owned or freed here:
+ *    tables, batches and workspaces are borrowed from the caller (torch tensors on the Python side).
+ *  - Every call is asynchronous on the cudaStream_t passed as `stream` (a void* holding the handle).
+ *  - Return value: 0 = launched; <0 = rejected on the host (cf_last_error() has the reason).  Device-side
+ *    conditions (index out of range, staging overflow, sampler gave up) are reported through the int32
+ *    `flags` word of the workspace (CF_FLAG_*), which the caller reads back when it synchronises.
+ *  - Embedding tables are fp32, row-major with a leading dimension `ld` (floats) that is a multiple of 4
+ *    and >= d; columns d..ld-1 must be zero and stay zero.  Base pointers are 16-byte aligned.
+ */
+#ifndef CF_B200_H
+#define CF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CF_ABI_VERSION 3
+
+/* models */
+enum { CF_MODEL_BPR = 0, CF_MODEL_CML = 1, CF_MODEL_GBPR = 2, CF_MODEL_WRMF = 3 };
+/* optimizers: ADAGRAD = TF1 AdagradOptimizer (acc0 = 0.1, no eps; bprmf.py:86, cml.py:127, gbprmf.py:104, wrmf.py:86) */
+enum { CF_OPT_ADAGRAD = 0, CF_OPT_SGD = 1 };
+/* update discipline: SYNC = the reference's minibatch-synchronous semantics (all gradients at pre-update
+ * parameters, duplicate rows summed, one apply per unique row); HOGWILD = per-occurrence racy apply. */
+enum { CF_UPDATE_SYNC = 1, CF_UPDATE_HOGWILD = 0 };
+/* scoring kinds: bprmf.py:80 / wrmf.py:80 ; gbprmf.py:98 ; cml.py:116 */
+enum { CF_SCORE_DOT = 0, CF_SCORE_DOT_BIAS = 1, CF_SCORE_NEG_SQDIST = 2 };
+/* device-side condition flags (bitwise OR into workspace flags word) */
+enum {
+  CF_FLAG_INDEX_RANGE = 1,      /* a batch index was outside its table */
+  CF_FLAG_STAGING_FULL = 2,     /* more duplicated rows than staging_rows */
+  CF_FLAG_SAMPLER_GAVEUP = 4,   /* rejection sampling found no negative in CF_SAMPLER_MAX_TRIES draws */
+  CF_FLAG_TOPK_OVERFLOW = 8     /* candidate buffer overflow in the tensor-core top-K path */
+};
+#define CF_SAMPLER_MAX_TRIES 256
+
+const char* cf_last_error(void);
+int cf_abi_version(void);
+/* compiled SASS target, e.g. "sm_100a" */
+const char* cf_build_arch(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Training step.  Replaces `sess.run(train_op, feed_dict)` of
+ *   bprmf.py:145  (BPRMF),  cml.py:184 (CML, incl. the clip of cml.py:119-129),
+ *   gbprmf.py:163 (GBPRMF), wrmf.py:145 (WRMF)
+ * for `n_batches` consecutive minibatches of `B` rows each (the reference's inner loop bprmf.py:143-148).
+ * Per minibatch it launches a row-occurrence counting kernel and ONE fused gather/gradient/update kernel.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct cf_step_args {
+  /* parameters */
+  float* U;          /* [n_users, ld] */
+  float* V;          /* [n_items, ld] */
+  float* b;          /* [n_items] item bias (GBPR) or NULL */
+  float* accU;       /* Adagrad accumulators, same shapes; may be NULL for CF_OPT_SGD */
+  float* accV;
+  float* accb;
+  int64_t n_users;
+  int64_t n_items;
+  int32_t d;
+  int32_t ld;
+  /* batches: int32 ids, n_batches*B rows */
+  const int32_t* pairs;   /* [n_batches*B, 2] (user, item)                     (useritem_placeholder) */
+  const int32_t* negs;    /* [n_batches*B, W] negative items; NULL for WRMF    (negItems_placeholder) */
+  const int32_t* group;   /* [n_batches*B, G] group users (GBPR) or NULL       (group_placeholder)    */
+  const float* ratings;   /* [n_batches*B] (WRMF) or NULL                      (rating_placeholder)   */
+  int32_t B;
+  int32_t W;
+  int32_t G;
+  int32_t n_batches;
+  /* hyper-parameters (constructor arguments of the reference classes) */
+  int32_t model;           /* CF_MODEL_* */
+  int32_t optimizer;       /* CF_OPT_* */
+  int32_t update;          /* CF_UPDATE_* */
+  int32_t use_rank_weight; /* CML */
+  float lr;
+  float reg;               /* reg (BPR/GBPR/WRMF) or reg_cov (CML; <=0 disables, cml.py:109) */
+  float margin;            /* CML */
+  float clip_norm;         /* CML */
+  float rho;               /* GBPR */
+  float weight;            /* WRMF */
+  /* workspace (see cf_step_workspace_sizes); metaU/metaV/slots/staging must be zero before the first
+   * call and are returned to zero by every successful call */
+  uint64_t* metaU;         /* [n_users]  (occurrences | done<<32) */
+  uint64_t* metaV;         /* [n_items] */
+  int32_t* slotU;          /* [n_users]  staging slot of a duplicated row */
+  int32_t* slotV;          /* [n_items] */
+  float* staging;          /* [staging_rows, ld + 4] gradient staging for rows that occur more than once */
+  int64_t staging_rows;
+  int32_t* counters;       /* [4]: {n_slots, flags, ticket, reserved}, zero-initialised */
+  double* loss;            /* [n_batches] summed minibatch loss, or NULL to skip the loss */
+} cf_step_args;
+
+int cf_train_steps(const cf_step_args* args, void* stream);
+/* rows of staging needed so that no batch of B rows can overflow it */
+int64_t cf_step_staging_rows(int32_t model, int32_t B, int32_t W, int32_t G);
+/* number of kernels cf_train_steps launches per minibatch (for gpu_launches accounting) */
+int32_t cf_step_launches_per_batch(void);
+
+/* row <- row * c / max(||row||_2, c) over a whole table: cml.py:119-122 (used once, after the first step) */
+int cf_clip_rows(float* table, int64_t n_rows, int32_t d, int32_t ld, float clip_norm, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * On-device samplers.  Replace the producer threads of
+ *   samplers/sampler_ranking.py:22-37, sampler_uij_ranking.py:22-38, sampler_gbpr.py:25-43,
+ *   sampler_rating.py:22-39.
+ * Stream position is the counter (seed, epoch, batch): identical arguments give identical batches.
+ * Positives: position p of epoch e is training pair perm_{seed,e}(p) (a keyed Feistel bijection on
+ * [0,nnz) with cycle walking = the reference's per-epoch shuffle without materialising it); the tail
+ * nnz mod B is dropped like sampler_ranking.py:25.  Negatives: Philox4x32-10 uniform draws re-drawn while
+ * they hit the user's CSR row (sampler_ranking.py:35-36).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct cf_csr {
+  const int64_t* indptr;   /* [n_rows + 1] */
+  const int32_t* indices;  /* [nnz] sorted within a row */
+  const int32_t* rows;     /* [nnz] row id of every entry (COO expansion), or NULL */
+  const float* values;     /* [nnz] ratings (sampler_rating) or NULL = all 1.0 */
+  int64_t n_rows;
+  int64_t n_cols;
+  int64_t nnz;
+} cf_csr;
+
+typedef struct cf_sample_args {
+  cf_csr train;            /* user -> items; rows[] required */
+  cf_csr train_t;          /* item -> users (GBPR group sampling); indptr NULL when G == 0 */
+  uint64_t seed;
+  int64_t epoch;
+  int64_t batch0;          /* first minibatch of the epoch to generate */
+  int32_t n_batches;
+  int32_t B;               /* positives per minibatch */
+  int32_t W;               /* negatives per positive (ranking/gbpr/uij) */
+  int32_t G;               /* group size (gbpr) */
+  int32_t n_neg_rows;      /* rating sampler: int(B*negRatio) extra (user, negative, 0) rows per minibatch */
+  int32_t shuffle;         /* ranking: 1 = per-epoch permutation (reference), 0 = file order */
+  int32_t* out_pairs;      /* [n_batches*B, 2]            (rating: [n_batches*(B+n_neg_rows), 2]) */
+  int32_t* out_negs;       /* [n_batches*B, W] or NULL */
+  int32_t* out_group;      /* [n_batches*B, G] or NULL */
+  float* out_ratings;      /* rating sampler: [n_batches*(B+n_neg_rows)] or NULL */
+  int32_t* flags;          /* device int32, CF_FLAG_* OR-ed in */
+} cf_sample_args;
+
+int cf_sample_ranking(const cf_sample_args* args, void* stream);   /* ranking / uij / gbpr */
+int cf_sample_rating(const cf_sample_args* args, void* stream);    /* sampler_rating */
+
+/* ------------------------------------------------------------------------------------------------
+ * Full-catalog scoring + masked top-K.  Replaces
+ *   sess.run(tf.nn.top_k(self.__predict__, maxsz + topN)) + the Python filter loop of
+ *   bprmf.py:90-103 (same in cml.py:131-144, gbprmf.py:108-121, wrmf.py:98-111).
+ * out_idx[t, 0..K) = the K best items of user users[t] that are not in its training row, ordered by
+ * (score desc, item id asc); scores are fp32 inputs accumulated in fp64 sequentially over k (the
+ * oracle's definition, oracle/scoring.py).  Short rows are padded with -1 / -inf.
+ * cf_topk_exact runs entirely on CUDA cores in fp64 (reference-quality path, any K <= 1024).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct cf_topk_args {
+  const float* U;
+  const float* V;
+  const float* b;          /* item bias for CF_SCORE_DOT_BIAS or NULL */
+  int64_t n_users;
+  int64_t n_items;
+  int32_t d;
+  int32_t ld;
+  const int32_t* users;    /* [T] query users (test_users), or NULL = 0..T-1 */
+  int32_t T;
+  int32_t K;
+  int32_t kind;            /* CF_SCORE_* */
+  cf_csr train;            /* rows to mask; indptr NULL = no masking */
+  int32_t* out_idx;        /* [T, K] */
+  double* out_val;         /* [T, K] or NULL */
+  int32_t* flags;
+  /* restrict scoring to items [item_lo, item_hi) (item-sharded multi-GPU evaluation); 0,0 = all */
+  int64_t item_lo;
+  int64_t item_hi;
+} cf_topk_args;
+
+int cf_topk_exact(const cf_topk_args* args, void* stream);
+
+/* the dense score matrix of `__predict__` (bprmf.py:77-81, cml.py:111-117, gbprmf.py:95-99, wrmf.py:77-81) as
+ * out_scores[T, n_items] fp64; for small inputs only -- the top-K path never materialises it */
+int cf_scores(const cf_topk_args* args, double* out_scores, void* stream);
+
+/* merge P per-shard top-K lists ([P, T, K] idx/val, e.g. after an all-gather) into the global top-K */
+int cf_topk_merge(const int32_t* idx, const double* val, int32_t P, int32_t T, int32_t K,
+                  int32_t* out_idx, double* out_val, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Ranking metrics.  Replaces metrics/ranking.py:11-67 (pre/recall/ndcg/map/mrr) and :75-91 (hr/arhr):
+ * per-user values are written to out[T, 8] = {pre, recall, ndcg, map, mrr, hit, rr_of_truth0, n_pred};
+ * the mean (CV) or sum (LOOV) over users is taken by the caller, as ranking.py does.
+ * pred[T, ldp] holds each user's list (-1 terminated / padded), truth is the test CSR restricted to the
+ * same T users (row t = user t).
+ * ------------------------------------------------------------------------------------------------ */
+int cf_rank_metrics(const int32_t* pred, int32_t T, int32_t ldp, int32_t k, const int64_t* truth_indptr,
+                    const int32_t* truth_indices, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CF_B200_H */

@@ -1,0 +1,70 @@
+"""CPU-side checks of the C-ABI boundary: the library loads, exports every symbol include/cf_b200.h declares,
+the ctypes structs match the header, and host-side argument validation rejects bad calls without touching a GPU."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from collaborativefilteringusingtensorflow_b200 import _lib
+
+HEADER = os.path.join(ROOT, 'include', 'cf_b200.h')
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(cf_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.lib()
+    names = _declared_functions()
+    assert 'cf_train_steps' in names and 'cf_topk_exact' in names and len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), 'libcf_b200.so does not export %s' % n
+    assert sorted(_lib.exported_symbols()) == names, 'ctypes binding and header disagree'
+    assert lib.cf_abi_version() == _lib.ABI_VERSION
+    assert lib.cf_build_arch() == b'sm_100a'
+
+
+def test_struct_layouts_match_header():
+    # field order/types are mirrored by hand; sizes follow from the C layout rules (natural alignment)
+    assert C.sizeof(_lib.Csr) == 4 * 8 + 3 * 8
+    assert C.sizeof(_lib.StepArgs) == 6 * 8 + 2 * 8 + 2 * 4 + 4 * 8 + 4 * 4 + 4 * 4 + 6 * 4 + 5 * 8 + 8 + 2 * 8
+    assert C.sizeof(_lib.SampleArgs) == 2 * C.sizeof(_lib.Csr) + 3 * 8 + 6 * 4 + 5 * 8
+    assert C.sizeof(_lib.TopkArgs) == 3 * 8 + 2 * 8 + 2 * 4 + 8 + 3 * 4 + 4 + C.sizeof(_lib.Csr) + 3 * 8 + 2 * 8
+
+
+def test_host_side_validation_needs_no_gpu():
+    lib = _lib.lib()
+    a = _lib.StepArgs()
+    assert lib.cf_train_steps(C.byref(a), None) < 0 and b'U, V and pairs' in lib.cf_last_error() or b'model' in lib.cf_last_error()
+    a.model, a.optimizer, a.update = 0, 0, 1
+    a.U, a.V, a.pairs = 16, 32, 64
+    a.d, a.ld = 10, 10
+    assert lib.cf_train_steps(C.byref(a), None) < 0 and b'ld' in lib.cf_last_error()
+    t = _lib.TopkArgs()
+    assert lib.cf_topk_exact(C.byref(t), None) < 0
+    t.U, t.V, t.out_idx, t.d, t.ld, t.T, t.K, t.n_items = 16, 32, 48, 8, 8, 4, 5000, 100
+    assert lib.cf_topk_exact(C.byref(t), None) < 0 and b'K must be' in lib.cf_last_error()
+    assert lib.cf_step_staging_rows(_lib.MODEL_CML, 100, 5, 0) == 351
+    assert lib.cf_step_staging_rows(_lib.MODEL_WRMF, 200, 7, 3) == 201
+
+
+def test_product_refuses_to_run_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    from collaborativefilteringusingtensorflow_b200 import BPRMF
+    with pytest.raises(_lib.CudaLibraryError):
+        BPRMF(10, 10)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'collaborativefilteringusingtensorflow_b200')
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh')):
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', open(os.path.join(d, f)).read(), flags=re.M), f

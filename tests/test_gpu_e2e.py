@@ -1,0 +1,74 @@
+"""End to end on ml-100k fold 1 with the reference driver's hyper-parameters (testbprmf.py:21-30): NDCG@10 (the
+reference's own definition) within +-0.02 of the CPU oracle run (tests/golden/e2e_golden.json),
+and the other three models reach their BASELINE.md ballparks."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+NAMES = ['pre', 'recall', 'map', 'mrr', 'ndcg']
+
+
+def test_bprmf_ml100k_ndcg_matches_oracle_run(ml100k, capsys):
+    from collaborativefilteringusingtensorflow_b200.models.pl.models.bprmf import BPRMF
+    from collaborativefilteringusingtensorflow_b200.samplers.sampler_ranking import Sampler
+    gold = json.load(open(os.path.join(GOLDEN, 'e2e_golden.json')))
+    h = gold['hyper']
+    tra, tst = ml100k['tra'], ml100k['tst']
+    sampler = Sampler(trasR=tra, n_neg=h['n_neg'], batch_size=h['batch_size'], seed=2026)
+    m = BPRMF(943, 1682, h['topN'], 'cv', NAMES, h['reg'], h['n_factors'], h['batch_size'], 20, seed=2026)
+    scores = m.train(1, tra, tst, sampler)
+    out = capsys.readouterr().out
+    assert out.count('cv_fold=1 iter=') == 20 and 'TraLoss=' in out and 'Tst@10:pre=' in out
+    want = gold['history'][-1]
+    got = dict(zip(NAMES, scores))
+    assert abs(got['ndcg'] - want['ndcg']) < 0.02, (got, want)
+    assert abs(got['pre'] - want['pre']) < 0.02 and abs(got['mrr'] - want['mrr']) < 0.04
+    m.close()
+
+
+def test_cml_gbpr_wrmf_train_on_ml100k(ml100k):
+    from collaborativefilteringusingtensorflow_b200 import CML, GBPRMF, WRMF
+    from collaborativefilteringusingtensorflow_b200.samplers import sampler_gbpr, sampler_ranking, sampler_rating
+    tra, tst = ml100k['tra'], ml100k['tst']
+    cml = CML(943, 1682, 10, 'cv', NAMES, 1., 1., True, 1.0, 50, 50, 10, verbose=False, seed=1)      # testcml.py:22-34
+    s = cml.train(1, tra, tst, sampler_ranking.Sampler(tra, n_neg=5, batch_size=50, seed=1))
+    assert s[NAMES.index('ndcg')] > 0.40, s          # 0.53 after 50 epochs
+    g = GBPRMF(943, 1682, 100, .4, 1, 'cv', NAMES, .01, 100, 100, 8, verbose=False, seed=1)           # testgbprmf.py:23-32
+    s = g.train(1, tra, tst, sampler_gbpr.Sampler(tra, 1, 5, 100, seed=1))
+    assert s[NAMES.index('recall')] > 0.5, s         # recall@100 0.665 after 30 epochs
+    w = WRMF(943, 1682, 10, 'cv', NAMES, 2., .1, 100, 100, 10, verbose=False, seed=1)                 # testwrmf.py:22-30
+    s = w.train(1, tra, tst, sampler_rating.Sampler(tra, 1, 100, seed=1))
+    assert s[NAMES.index('ndcg')] > 0.40, s          # 0.51 after 50 epochs
+
+
+def test_reference_style_sampler_object_is_accepted(ml100k):
+    """train() also takes any object with the reference's next_batch() -> numpy arrays (here the CPU oracle's
+    restatement of sampler_ranking), uploading batch by batch."""
+    from collaborativefilteringusingtensorflow_b200 import BPRMF
+    from oracle import samplers
+
+    class RefLike(object):
+        def __init__(self, gen):
+            self.gen = gen
+
+        def next_batch(self):
+            return next(self.gen)
+
+    tra, tst = ml100k['tra'], ml100k['tst']
+    m = BPRMF(943, 1682, 10, 'cv', NAMES, .1, 32, 100, 2, verbose=False, seed=1)
+    s = m.train(1, tra, tst, RefLike(samplers.ranking_batches(tra, 1, 100, seed=3)))
+    assert len(s) == 5 and all(np.isfinite(s))
+
+
+def test_loov_split(ml100k):
+    from collaborativefilteringusingtensorflow_b200 import BPRMF
+    from collaborativefilteringusingtensorflow_b200.samplers.sampler_ranking import Sampler
+    tra, tst = ml100k['tra'], ml100k['tst']
+    m = BPRMF(943, 1682, 10, 'loov', ['hr', 'arhr'], .1, 32, 100, 2, verbose=False, seed=1)
+    s = m.train(1, tra, tst, Sampler(tra, 1, 100, seed=1))
+    assert 0 <= s[1] <= s[0] <= 919
