@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libcf_b200.so')
-ABI_VERSION = 3
+ABI_VERSION = 5
 
 # enums of cf_b200.h
 MODEL_BPR, MODEL_CML, MODEL_GBPR, MODEL_WRMF = 0, 1, 2, 3
@@ -29,7 +29,7 @@ class StepArgs(C.Structure):
         ('model', C.c_int32), ('optimizer', C.c_int32), ('update', C.c_int32), ('use_rank_weight', C.c_int32),
         ('lr', C.c_float), ('reg', C.c_float), ('margin', C.c_float), ('clip_norm', C.c_float),
         ('rho', C.c_float), ('weight', C.c_float),
-        ('metaU', _p), ('metaV', _p), ('slotU', _p), ('slotV', _p), ('staging', _p),
+        ('metaU', _p), ('metaV', _p), ('slotU', _p), ('slotV', _p), ('slot_row', _p), ('staging', _p),
         ('staging_rows', C.c_int64), ('counters', _p), ('loss', _p),
     ]
 
@@ -62,6 +62,8 @@ _SIGNATURES = {
     'cf_abi_version': (C.c_int, []),
     'cf_build_arch': (C.c_char_p, []),
     'cf_train_steps': (C.c_int, [C.POINTER(StepArgs), _p]),
+    'cf_train_steps_profiled': (C.c_int, [C.POINTER(StepArgs), _p, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                        C.POINTER(C.c_float)]),
     'cf_step_staging_rows': (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     'cf_step_launches_per_batch': (C.c_int32, []),
     'cf_clip_rows': (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, _p]),

@@ -25,6 +25,7 @@ using namespace cfstep;
 // shapes: 0: LPG 8 (ld <= 32)  1: LPG 16 (ld <= 64)  2: LPG 32 (ld <= 128)  3: LPG 32 x2 (ld <= 256)  4: LPG 32 x4 (ld <= 512)
 #define CF_DECL_MODEL(M) CF_STEP_PICK_DECL(M, 0); CF_STEP_PICK_DECL(M, 1); CF_STEP_PICK_DECL(M, 2); CF_STEP_PICK_DECL(M, 3); CF_STEP_PICK_DECL(M, 4);
 CF_DECL_MODEL(0) CF_DECL_MODEL(1) CF_DECL_MODEL(2) CF_DECL_MODEL(3)
+CF_APPLY_PICK_DECL(0); CF_APPLY_PICK_DECL(1); CF_APPLY_PICK_DECL(2); CF_APPLY_PICK_DECL(3); CF_APPLY_PICK_DECL(4);
 
 namespace {
 
@@ -32,24 +33,28 @@ namespace {
 __global__ void __launch_bounds__(256) k_count(const __grid_constant__ StepDev P) {
   const int R = (P.model == CF_MODEL_WRMF) ? 2 : 2 + P.W + P.G;
   const long long total = (long long)P.B * R;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const long long b = t / R;
-    const int k = (int)(t - b * R);
-    int tab;
-    long long r;
-    if (k == 0) { tab = 0; r = __ldg(P.pairs + 2 * b); }
-    else if (k == 1) { tab = 1; r = __ldg(P.pairs + 2 * b + 1); }
-    else if (k < 2 + P.W) { tab = 1; r = __ldg(P.negs + b * P.W + (k - 2)); }
-    else { tab = 0; r = __ldg(P.group + b * P.G + (k - 2 - P.W)); }
-    if (!in_range(r, tab ? P.n_items : P.n_users)) {
-      atomicOr(P.counters + 1, CF_FLAG_INDEX_RANGE);
-      continue;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t0 = (long long)blockIdx.x * blockDim.x; t0 < total; t0 += stride) {
+    const long long t = t0 + threadIdx.x;
+    bool need = false;
+    int tab = 0;
+    long long r = 0;
+    if (t < total) {
+      const long long b = t / R;
+      const int k = (int)(t - b * R);
+      if (k == 0) { tab = 0; r = __ldg(P.pairs + 2 * b); }
+      else if (k == 1) { tab = 1; r = __ldg(P.pairs + 2 * b + 1); }
+      else if (k < 2 + P.W) { tab = 1; r = __ldg(P.negs + b * P.W + (k - 2)); }
+      else { tab = 0; r = __ldg(P.group + b * P.G + (k - 2 - P.W)); }
+      if (!in_range(r, tab ? P.n_items : P.n_users)) atomicOr(P.counters + 1, CF_FLAG_INDEX_RANGE);
+      else need = atomicAdd((tab ? P.metaV : P.metaU) + r, 1u) == 1u;   // second occurrence: the row needs a staging slot
     }
-    const unsigned long long old = atomicAdd((tab ? P.metaV : P.metaU) + r, 1ull);
-    if ((unsigned)old == 1u) {  // second occurrence: this row needs a staging slot
-      const int s = atomicAdd(P.counters, 1);
-      if (s < P.staging_rows) (tab ? P.slotV : P.slotU)[r] = s;
-      else atomicOr(P.counters + 1, CF_FLAG_STAGING_FULL);
+    if (need) {
+      // The staging slot of a duplicated row is the index t of its SECOND occurrence: unique per row, needs no shared
+      // allocation counter (a same-address atomic per duplicated row serialised this kernel), at the price of a
+      // staging buffer with one (mostly untouched) slot per occurrence.
+      (tab ? P.slotV : P.slotU)[r] = (int)t;
+      P.slot_row[t] = (uint32_t)r | (tab ? 0x80000000u : 0u);
     }
   }
 }
@@ -77,17 +82,28 @@ __global__ void __launch_bounds__(256) k_clip(float* tab, long long n_rows, int 
 }
 
 
-step_kernel_t pick_kernel(int model, int nvec, int W, int* lpg) {
+step_kernel_t pick_apply(int nvec) {
+  const int shape = nvec <= 8 ? 0 : nvec <= 16 ? 1 : nvec <= 32 ? 2 : nvec <= 64 ? 3 : 4;
+  switch (shape) {
+    case 0: return cf_apply_pick_0();
+    case 1: return cf_apply_pick_1();
+    case 2: return cf_apply_pick_2();
+    case 3: return cf_apply_pick_3();
+    default: return cf_apply_pick_4();
+  }
+}
+
+step_kernel_t pick_kernel(int model, int nvec, int* lpg) {
   const int shape = nvec <= 8 ? 0 : nvec <= 16 ? 1 : nvec <= 32 ? 2 : nvec <= 64 ? 3 : 4;
   *lpg = shape == 0 ? 8 : shape == 1 ? 16 : 32;
 #define CF_CASE(M)                                   \
   case M:                                            \
     switch (shape) {                                 \
-      case 0: return cf_step_pick_##M##_0(W);        \
-      case 1: return cf_step_pick_##M##_1(W);        \
-      case 2: return cf_step_pick_##M##_2(W);        \
-      case 3: return cf_step_pick_##M##_3(W);        \
-      default: return cf_step_pick_##M##_4(W);       \
+      case 0: return cf_step_pick_##M##_0();        \
+      case 1: return cf_step_pick_##M##_1();        \
+      case 2: return cf_step_pick_##M##_2();        \
+      case 3: return cf_step_pick_##M##_3();        \
+      default: return cf_step_pick_##M##_4();       \
     }
   switch (model) {
     CF_CASE(0)
@@ -104,13 +120,12 @@ step_kernel_t pick_kernel(int model, int nvec, int W, int* lpg) {
 
 extern "C" int64_t cf_step_staging_rows(int32_t model, int32_t B, int32_t W, int32_t G) {
   const int64_t R = (model == CF_MODEL_WRMF) ? 2 : 2 + (int64_t)W + G;
-  return (int64_t)B * R / 2 + 1;  // a row needs a slot only if it occurs at least twice
+  return (int64_t)B * R;  // slot id = occurrence index of a duplicated row's second occurrence
 }
 
-extern "C" int32_t cf_step_launches_per_batch(void) { return 2; }
+extern "C" int32_t cf_step_launches_per_batch(void) { return 3; }
 
-extern "C" int cf_train_steps(const cf_step_args* a, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+static int train_steps_impl(const cf_step_args* a, cudaStream_t stream, cudaEvent_t* ev) {
   CF_CHECK_ARG(a != nullptr, "cf_train_steps: args is NULL");
   CF_CHECK_ARG(a->model >= CF_MODEL_BPR && a->model <= CF_MODEL_WRMF, "cf_train_steps: unknown model %d", a->model);
   CF_CHECK_ARG(a->optimizer == CF_OPT_ADAGRAD || a->optimizer == CF_OPT_SGD, "cf_train_steps: unknown optimizer %d", a->optimizer);
@@ -136,7 +151,7 @@ extern "C" int cf_train_steps(const cf_step_args* a, void* stream_) {
   }
   if (a->model == CF_MODEL_CML) CF_CHECK_ARG(a->clip_norm > 0.f, "cf_train_steps: CML needs clip_norm > 0");
   if (a->update == CF_UPDATE_SYNC) {
-    CF_CHECK_ARG(a->metaU && a->metaV && a->slotU && a->slotV && a->staging && a->counters, "cf_train_steps: SYNC mode needs the workspace");
+    CF_CHECK_ARG(a->metaU && a->metaV && a->slotU && a->slotV && a->slot_row && a->staging && a->counters, "cf_train_steps: SYNC mode needs the workspace");
     CF_CHECK_ARG(a->staging_rows >= cf_step_staging_rows(a->model, a->B, W, G), "cf_train_steps: staging_rows %lld < required %lld",
                  (long long)a->staging_rows, (long long)cf_step_staging_rows(a->model, a->B, W, G));
   } else {
@@ -151,22 +166,41 @@ extern "C" int cf_train_steps(const cf_step_args* a, void* stream_) {
   P.B = a->B; P.W = W; P.G = G;
   P.model = a->model; P.optimizer = a->optimizer; P.update = a->update; P.use_rank_weight = a->use_rank_weight;
   P.lr = a->lr; P.reg = a->reg; P.margin = a->margin; P.clip = a->clip_norm; P.rho = a->rho; P.weight = a->weight;
-  P.metaU = (unsigned long long*)a->metaU; P.metaV = (unsigned long long*)a->metaV;
+  P.metaU = a->metaU; P.metaV = a->metaV; P.slot_row = a->slot_row;
   P.slotU = a->slotU; P.slotV = a->slotV; P.staging = a->staging; P.staging_rows = a->staging_rows;
   P.lds = a->ld + 4; P.counters = a->counters;
 
   int lpg = 32;
-  step_kernel_t kern = pick_kernel(a->model, P.nvec, W, &lpg);
+  step_kernel_t kern = pick_kernel(a->model, P.nvec, &lpg);
   static int sms = 0;
   if (!sms) sms = cf_num_sms();
-  int occ = 0;
-  CF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
-  if (occ < 1) occ = 1;
+  // entries (negatives + group users) staged per tile: all of them if the lanes (one per slot) and the shared
+  // memory (two rows per slot per group) allow, else the largest tile that still fits two blocks per SM
+  const int E = W + G;
   const long long groups_per_block = 256 / lpg;
+  const long long slot_bytes = groups_per_block * 2ll * a->ld * 4ll;   // one more slot costs this much smem per block
+  int T = E < lpg - 2 ? E : lpg - 2;
+  const long long budget2 = 112 * 1024, budget1 = 224 * 1024;
+  if ((2 + T) * slot_bytes > budget2) {
+    int t2 = (int)(budget2 / slot_bytes) - 2;
+    if (t2 >= 4 || t2 >= E) T = t2 < T ? t2 : T;
+    else { int t1 = (int)(budget1 / slot_bytes) - 2; T = t1 < T ? t1 : T; }
+  }
+  if (E > 0 && T < 1) T = 1;
+  CF_CHECK_ARG((2 + T) * slot_bytes <= budget1, "cf_train_steps: rows too wide for the shared-memory staging (ld=%d)", a->ld);
+  P.T = T;
+  const size_t smem = (size_t)((2 + T) * slot_bytes);
+  CF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+  if (occ < 1) occ = 1;
   long long grid = (a->B + groups_per_block - 1) / groups_per_block;
   const long long cap = (long long)sms * occ;
   if (grid > cap) grid = cap;
+  step_kernel_t kapply = pick_apply(P.nvec);
   const long long R = (a->model == CF_MODEL_WRMF) ? 2 : 2 + W + G;
+  long long agrid = ((long long)a->B * R + 255) / 256;   // every thread scans one slot code per iteration
+  if (agrid > (long long)sms * 16) agrid = (long long)sms * 16;
   long long cgrid = ((long long)a->B * R + 255) / 256;
   if (cgrid > (long long)sms * 8) cgrid = (long long)sms * 8;
 
@@ -177,11 +211,50 @@ extern "C" int cf_train_steps(const cf_step_args* a, void* stream_) {
     P.group = (G && a->group) ? a->group + off * G : nullptr;
     P.ratings = a->ratings ? a->ratings + off : nullptr;
     P.loss = a->loss ? a->loss + nb : nullptr;
+    if (ev) CF_CUDA_OK(cudaEventRecord(ev[4 * nb + 0], stream));
     if (a->update == CF_UPDATE_SYNC) k_count<<<(unsigned)cgrid, 256, 0, stream>>>(P);
-    kern<<<(unsigned)grid, 256, 0, stream>>>(P);
+    if (ev) CF_CUDA_OK(cudaEventRecord(ev[4 * nb + 1], stream));
+    kern<<<(unsigned)grid, 256, smem, stream>>>(P);
+    if (ev) CF_CUDA_OK(cudaEventRecord(ev[4 * nb + 2], stream));
+    if (a->update == CF_UPDATE_SYNC) kapply<<<(unsigned)agrid, 256, 0, stream>>>(P);
+    if (ev) CF_CUDA_OK(cudaEventRecord(ev[4 * nb + 3], stream));
   }
   CF_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+extern "C" int cf_train_steps(const cf_step_args* a, void* stream_) {
+  return train_steps_impl(a, (cudaStream_t)stream_, nullptr);
+}
+
+extern "C" int cf_train_steps_profiled(const cf_step_args* a, void* stream_, float* ms_count_host, float* ms_step_host,
+                                       float* ms_apply_host) {
+  CF_CHECK_ARG(a != nullptr && ms_count_host && ms_step_host && ms_apply_host, "cf_train_steps_profiled: NULL argument");
+  CF_CHECK_ARG(a->n_batches > 0 && a->n_batches <= 4096, "cf_train_steps_profiled: n_batches must be in [1, 4096]");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int n = 4 * a->n_batches;
+  cudaEvent_t* ev = new cudaEvent_t[n];
+  for (int k = 0; k < n; ++k) CF_CUDA_OK(cudaEventCreate(&ev[k]));
+  int rc = train_steps_impl(a, stream, ev);
+  if (rc == 0) {
+    CF_CUDA_OK(cudaStreamSynchronize(stream));
+    double tc = 0.0, ts = 0.0, ta = 0.0;
+    for (int nb = 0; nb < a->n_batches; ++nb) {
+      float x = 0.f, y = 0.f, z = 0.f;
+      CF_CUDA_OK(cudaEventElapsedTime(&x, ev[4 * nb], ev[4 * nb + 1]));
+      CF_CUDA_OK(cudaEventElapsedTime(&y, ev[4 * nb + 1], ev[4 * nb + 2]));
+      CF_CUDA_OK(cudaEventElapsedTime(&z, ev[4 * nb + 2], ev[4 * nb + 3]));
+      tc += x;
+      ts += y;
+      ta += z;
+    }
+    *ms_count_host = (float)tc;
+    *ms_step_host = (float)ts;
+    *ms_apply_host = (float)ta;
+  }
+  for (int k = 0; k < n; ++k) cudaEventDestroy(ev[k]);
+  delete[] ev;
+  return rc;
 }
 
 extern "C" int cf_clip_rows(float* table, int64_t n_rows, int32_t d, int32_t ld, float clip_norm, void* stream_) {

@@ -1,5 +1,20 @@
-// Device templates of the fused minibatch step (included by the generated instantiation units and by cf_step.cu).
-// See cf_step.cu for the design notes.
+// Device side of the fused minibatch step (included by the generated instantiation units and by cf_step.cu).
+//
+// One GROUP of LPG lanes (8 / 16 / 32, by row width) owns one (user, item) pair at a time.  Lane s of the group is
+// the book-keeper of row SLOT s of the pair: slot 0 = the user row, slot 1 = the positive item row, slots 2.. = a
+// tile of up to T "entries" (the W negatives first, then the G group users of GBPR).  Per pair:
+//   1. every lane loads its slot's row id and (SYNC mode) the row's occurrence word            -- parallel 4/8-byte loads
+//   2. the group issues cp.async.cg (16 B per lane, L2-coherent, no registers) for every slot's parameter row and,
+//      when the row will be applied by this group (unique row or HOGWILD), its Adagrad accumulator row, straight
+//      into the group's shared-memory staging: all 2(2+T) rows of the pair are in flight together
+//   3. scores / distances from shared memory (warp-shuffle reductions), per-slot gradient coefficients kept by the
+//      slot's lane
+//   4. a rolled loop over the slots forms each row gradient and either applies it from registers (unique row: read
+//      param + acc, write param + acc -- the algorithmic minimum) or red.adds it into the row's staging slot
+//   5. rows that occur more than once in the minibatch: ONE fence, then each such slot's lane bumps the row's done
+//      counter; whoever completes a row (last arriver) applies the summed gradient.
+// All loops over slots are rolled (the slot's data lives in shared memory / its lane), so the kernel is a few KB of
+// SASS instead of the 80-250 KB of the first, fully unrolled version (which stalled on instruction fetch).
 #pragma once
 #include <math.h>
 
@@ -7,18 +22,18 @@
 
 namespace cfstep {
 
-
 struct StepDev {
   float *U, *V, *b, *accU, *accV, *accb;
   long long n_users, n_items;
   int d, ld, nvec;
   const int32_t *pairs, *negs, *group;
   const float* ratings;
-  int B, W, G;
+  int B, W, G, T;  // T = entries (negatives + group users) staged per tile
   int model, optimizer, update, use_rank_weight;
   float lr, reg, margin, clip, rho, weight;
-  unsigned long long *metaU, *metaV;
-  int32_t *slotU, *slotV;
+  unsigned int *metaU, *metaV;     // occurrences of each row in the current minibatch (0 between minibatches)
+  int32_t *slotU, *slotV;          // staging slot of a row that occurs more than once
+  uint32_t* slot_row;              // inverse map: slot -> row id | (item table ? 1u << 31 : 0)
   float* staging;
   long long staging_rows;
   int lds;
@@ -49,7 +64,6 @@ __device__ __forceinline__ Row<NV> load_row(const float* tab, long long r, int l
   }
   return x;
 }
-
 template <int LPG, int NV>
 __device__ __forceinline__ void store_row(float* tab, long long r, int ld, int nvec, int gl, const Row<NV>& x) {
   float* p = tab + r * (long long)ld;
@@ -59,7 +73,17 @@ __device__ __forceinline__ void store_row(float* tab, long long r, int ld, int n
     if (v < nvec) stcg4(p + 4 * v, x.v[k]);
   }
 }
-
+// shared-memory row (stride ld floats); lanes past the row read zeros / `fill`
+template <int LPG, int NV>
+__device__ __forceinline__ Row<NV> smem_row(const float* s, int nvec, int gl, float fill = 0.f) {
+  Row<NV> x;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int v = gl + k * LPG;
+    x.v[k] = (v < nvec) ? *reinterpret_cast<const float4*>(s + 4 * v) : make_float4(fill, fill, fill, fill);
+  }
+  return x;
+}
 template <int NV>
 __device__ __forceinline__ float dotp(const Row<NV>& a, const Row<NV>& b) {
   float s = 0.f;
@@ -74,9 +98,8 @@ __device__ __forceinline__ float sqdp(const Row<NV>& a, const Row<NV>& b) {
   for (int k = 0; k < NV; ++k) s += sqd4(a.v[k], b.v[k]);
   return s;
 }
-// y += s * x
 template <int NV>
-__device__ __forceinline__ void axpy(Row<NV>& y, float s, const Row<NV>& x) {
+__device__ __forceinline__ void axpy(Row<NV>& y, float s, const Row<NV>& x) {  // y += s * x
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     y.v[k].x = fmaf(s, x.v[k].x, y.v[k].x);
@@ -85,9 +108,8 @@ __device__ __forceinline__ void axpy(Row<NV>& y, float s, const Row<NV>& x) {
     y.v[k].w = fmaf(s, x.v[k].w, y.v[k].w);
   }
 }
-// a*x + b*y
 template <int NV>
-__device__ __forceinline__ Row<NV> lin2(float a, const Row<NV>& x, float b, const Row<NV>& y) {
+__device__ __forceinline__ Row<NV> lin2(float a, const Row<NV>& x, float b, const Row<NV>& y) {  // a*x + b*y
   Row<NV> r;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
@@ -105,40 +127,58 @@ __device__ __forceinline__ Row<NV> zero_row() {
   for (int k = 0; k < NV; ++k) r.v[k] = f4zero();
   return r;
 }
-
 template <int LPG>
 __device__ __forceinline__ float group_sum(float x, unsigned gmask) {
 #pragma unroll
   for (int o = LPG / 2; o > 0; o >>= 1) x += __shfl_xor_sync(gmask, x, o);
   return x;
 }
-
+template <int LPG>
+__device__ __forceinline__ float group_min(float x, unsigned gmask) {
+#pragma unroll
+  for (int o = LPG / 2; o > 0; o >>= 1) x = fminf(x, __shfl_xor_sync(gmask, x, o));
+  return x;
+}
 __device__ __forceinline__ float softplus_neg(float x) {  // -log(sigmoid(x)), bprmf.py:70
-  return x > 0.f ? log1pf(expf(-x)) : (-x + log1pf(expf(x)));
+  return x > 0.f ? log1pf(__expf(-x)) : (-x + log1pf(__expf(x)));
 }
-__device__ __forceinline__ float sigm1(float x) {  // sigmoid(x) - 1
-  return -1.f / (1.f + expf(x));
+__device__ __forceinline__ float sigm1(float x) { return -1.f / (1.f + expf(x)); }  // sigmoid(x) - 1
+__device__ __forceinline__ bool in_range(long long r, long long n) { return r >= 0 && r < n; }
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+template <int LPG, int NV>
+__device__ __forceinline__ void stage_row(float* smem_dst, const float* tab, long long r, int ld, int nvec, int gl) {
+  const float* p = tab + r * (long long)ld;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int v = gl + k * LPG;
+    if (v < nvec) cp_async16(smem_dst + 4 * v, p + 4 * v);
+  }
 }
 
-// ---- one Adagrad / SGD apply of a (summed) row gradient; optional CML unit-norm clip (cml.py:119-122) fused in
+// new parameter row (and accumulator row) from the current row, its accumulator and the summed gradient;
+// the CML unit-norm clip (cml.py:119-122) of the updated row is fused in
 template <int LPG, int NV>
-__device__ __forceinline__ void apply_row(const StepDev& P, float* tab, float* acc, long long r, const Row<NV>& cur,
-                                          const Row<NV>& g, int gl, unsigned gmask) {
-  Row<NV> p;
+__device__ __forceinline__ void apply_math(const StepDev& P, const Row<NV>& cur, Row<NV>& acc, const Row<NV>& g, Row<NV>& p,
+                                           unsigned gmask) {
   if (P.optimizer == CF_OPT_ADAGRAD) {
-    Row<NV> a = load_row<LPG, NV>(acc, r, P.ld, P.nvec, gl, 1.f);
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      a.v[k].x = fmaf(g.v[k].x, g.v[k].x, a.v[k].x);
-      a.v[k].y = fmaf(g.v[k].y, g.v[k].y, a.v[k].y);
-      a.v[k].z = fmaf(g.v[k].z, g.v[k].z, a.v[k].z);
-      a.v[k].w = fmaf(g.v[k].w, g.v[k].w, a.v[k].w);
-      p.v[k].x = cur.v[k].x - (P.lr * g.v[k].x) / sqrtf(a.v[k].x);
-      p.v[k].y = cur.v[k].y - (P.lr * g.v[k].y) / sqrtf(a.v[k].y);
-      p.v[k].z = cur.v[k].z - (P.lr * g.v[k].z) / sqrtf(a.v[k].z);
-      p.v[k].w = cur.v[k].w - (P.lr * g.v[k].w) / sqrtf(a.v[k].w);
+      acc.v[k].x = fmaf(g.v[k].x, g.v[k].x, acc.v[k].x);
+      acc.v[k].y = fmaf(g.v[k].y, g.v[k].y, acc.v[k].y);
+      acc.v[k].z = fmaf(g.v[k].z, g.v[k].z, acc.v[k].z);
+      acc.v[k].w = fmaf(g.v[k].w, g.v[k].w, acc.v[k].w);
+      p.v[k].x = fmaf(-P.lr * g.v[k].x, rsqrtf(acc.v[k].x), cur.v[k].x);
+      p.v[k].y = fmaf(-P.lr * g.v[k].y, rsqrtf(acc.v[k].y), cur.v[k].y);
+      p.v[k].z = fmaf(-P.lr * g.v[k].z, rsqrtf(acc.v[k].z), cur.v[k].z);
+      p.v[k].w = fmaf(-P.lr * g.v[k].w, rsqrtf(acc.v[k].w), cur.v[k].w);
     }
-    store_row<LPG, NV>(acc, r, P.ld, P.nvec, gl, a);
   } else {
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
@@ -149,100 +189,32 @@ __device__ __forceinline__ void apply_row(const StepDev& P, float* tab, float* a
     }
   }
   if (P.model == CF_MODEL_CML) {
-    const float nrm = sqrtf(group_sum<LPG>(dotp<NV>(p, p), gmask));
-    const float den = fmaxf(nrm, P.clip);
-    if (nrm > P.clip) {
+    const float n2 = group_sum<LPG>(dotp<NV>(p, p), gmask);
+    if (n2 > P.clip * P.clip) {
+      const float sc = P.clip * rsqrtf(n2);
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
-        p.v[k].x = (p.v[k].x * P.clip) / den;
-        p.v[k].y = (p.v[k].y * P.clip) / den;
-        p.v[k].z = (p.v[k].z * P.clip) / den;
-        p.v[k].w = (p.v[k].w * P.clip) / den;
+        p.v[k].x *= sc; p.v[k].y *= sc; p.v[k].z *= sc; p.v[k].w *= sc;
       }
     }
   }
-  store_row<LPG, NV>(tab, r, P.ld, P.nvec, gl, p);
 }
 
 __device__ __forceinline__ void apply_bias(const StepDev& P, long long r, float cur, float g) {
   if (P.optimizer == CF_OPT_ADAGRAD) {
     const float a = fmaf(g, g, __ldcg(P.accb + r));
     __stcg(P.accb + r, a);
-    __stcg(P.b + r, cur - (P.lr * g) / sqrtf(a));
+    __stcg(P.b + r, fmaf(-P.lr * g, rsqrtf(a), cur));
   } else {
     __stcg(P.b + r, fmaf(-P.lr, g, cur));
   }
 }
 
-// ---- commit one occurrence of row r of table `tab` (0 = U, 1 = V[+bias]) with gradient g (bias gradient gb)
-template <int LPG, int NV>
-__device__ __forceinline__ void commit(const StepDev& P, int tab, long long r, unsigned long long meta_word,
-                                       const Row<NV>& cur, const Row<NV>& g, float bcur, float gb, int gl,
-                                       unsigned gmask, int leader) {
-  float* T = tab ? P.V : P.U;
-  float* A = tab ? P.accV : P.accU;
-  const bool bias = tab && P.b != nullptr;
-  if (P.update == CF_UPDATE_HOGWILD) {
-    apply_row<LPG, NV>(P, T, A, r, cur, g, gl, gmask);
-    if (bias && gl == 0) apply_bias(P, r, bcur, gb);
-    return;
-  }
-  unsigned long long* meta = tab ? P.metaV : P.metaU;
-  const unsigned occ = (unsigned)__shfl_sync(gmask, meta_word, leader);
-  if (occ <= 1u) {  // the only occurrence in this minibatch: update from registers
-    apply_row<LPG, NV>(P, T, A, r, cur, g, gl, gmask);
-    if (gl == 0) {
-      if (bias) apply_bias(P, r, bcur, gb);
-      __stcg(meta + r, 0ull);
-    }
-    return;
-  }
-  int slot = 0;
-  if (gl == 0) slot = __ldcg((tab ? P.slotV : P.slotU) + r);
-  slot = __shfl_sync(gmask, slot, leader);
-  float* st = P.staging + (long long)slot * P.lds;
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int v = gl + k * LPG;
-    if (v < P.nvec) atomicAdd(reinterpret_cast<float4*>(st + 4 * v), g.v[k]);
-  }
-  if (bias && gl == 0) atomicAdd(st + P.ld, gb);
-  __threadfence();
-  __syncwarp(gmask);
-  unsigned long long old = 0;
-  if (gl == 0) old = atomicAdd(meta + r, 1ull << 32);
-  old = __shfl_sync(gmask, old, leader);
-  if ((unsigned)(old >> 32) + 1u == occ) {  // last arriver: every gradient of this row is in the slot
-    __threadfence();
-    Row<NV> gt;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int v = gl + k * LPG;
-      if (v < P.nvec) {
-        gt.v[k] = ldcg4(st + 4 * v);
-        stcg4(st + 4 * v, f4zero());
-      } else {
-        gt.v[k] = f4zero();
-      }
-    }
-    apply_row<LPG, NV>(P, T, A, r, cur, gt, gl, gmask);
-    if (gl == 0) {
-      if (bias) {
-        const float gbt = __ldcg(st + P.ld);
-        __stcg(st + P.ld, 0.f);
-        apply_bias(P, r, bcur, gbt);
-      }
-      __stcg(meta + r, 0ull);
-    }
-  }
-}
+enum { ROLE_NONE = 0, ROLE_USER = 1, ROLE_ITEM = 2, ROLE_NEG = 3, ROLE_GROUP = 4 };
 
-__device__ __forceinline__ bool in_range(long long r, long long n) { return r >= 0 && r < n; }
-
-constexpr int GT = 4;  // group rows kept in registers (GBPR)
-
-template <int MODEL, int LPG, int NV, int WT>
+template <int MODEL, int LPG, int NV>
 __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepDev P) {
+  extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31;
   const int gl = lane & (LPG - 1);
   const int leader = lane & ~(LPG - 1);
@@ -250,243 +222,239 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepDev P)
   const long long ngroups = (long long)gridDim.x * blockDim.x / LPG;
   const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPG;
   const bool sync = P.update == CF_UPDATE_SYNC;
+  const bool adagrad = P.optimizer == CF_OPT_ADAGRAD;
   const bool want_loss = P.loss != nullptr;
+  const int nslot = 2 + P.T;
+  float* sp = smem + (size_t)(threadIdx.x / LPG) * (2 * nslot) * P.ld;  // parameter rows of this group's slots
+  float* sa = sp + (size_t)nslot * P.ld;                                // accumulator rows
+  const int E = (MODEL == CF_MODEL_WRMF) ? 0 : P.W + ((MODEL == CF_MODEL_GBPR) ? P.G : 0);
+  const bool single = E <= P.T;
+  const float creg = (MODEL == CF_MODEL_CML) ? (P.reg > 0.f ? P.reg : 0.f) : P.reg;
   if (sync && (__ldcg(P.counters + 1) & (CF_FLAG_INDEX_RANGE | CF_FLAG_STAGING_FULL))) return;
 
   double loss_acc = 0.0;
   const long long iters = (P.B + ngroups - 1) / ngroups;
   for (long long it = 0; it < iters; ++it) {
     const long long b0 = gid + it * ngroups;
-    bool active = b0 < P.B;
-    const long long bb = active ? b0 : (long long)P.B - 1;
-    const int u = __ldg(P.pairs + 2 * bb), i = __ldg(P.pairs + 2 * bb + 1);
-    if (!in_range(u, P.n_users) || !in_range(i, P.n_items)) {
-      if (active && gl == 0) atomicOr(P.counters + 1, CF_FLAG_INDEX_RANGE);
-      active = false;
-    }
-    // negatives / group ids are validated below; an invalid id deactivates the whole pair
-    if (MODEL != CF_MODEL_WRMF) {
-      for (int w = 0; w < P.W; ++w)
-        if (!in_range(__ldg(P.negs + bb * P.W + w), P.n_items)) {
-          if (active && gl == 0) atomicOr(P.counters + 1, CF_FLAG_INDEX_RANGE);
-          active = false;
-        }
-    }
-    if (MODEL == CF_MODEL_GBPR) {
-      for (int g = 0; g < P.G; ++g)
-        if (!in_range(__ldg(P.group + bb * P.G + g), P.n_users)) {
-          if (active && gl == 0) atomicOr(P.counters + 1, CF_FLAG_INDEX_RANGE);
-          active = false;
-        }
-    }
-    if (!active) continue;  // group-uniform; every shuffle below uses the group's own mask
+    if (b0 >= P.B) continue;  // group-uniform
+    const long long bb = b0;
 
-    unsigned long long mu = 0, mi = 0;
-    if (sync && gl == 0) {
-      mu = __ldcg(P.metaU + u);
-      mi = __ldcg(P.metaV + i);
+    // ---------------------------------------------------------------- slots 0 (user) and 1 (positive item)
+    int my_row = -1, my_role = ROLE_NONE;
+    if (gl == 0) { my_row = __ldg(P.pairs + 2 * bb); my_role = ROLE_USER; }
+    if (gl == 1) { my_row = __ldg(P.pairs + 2 * bb + 1); my_role = ROLE_ITEM; }
+    bool ok = my_role == ROLE_NONE || in_range(my_row, my_role == ROLE_USER ? P.n_users : P.n_items);
+    // every entry id of the pair is validated up front (an invalid id skips the whole pair, nothing is written)
+    for (int e = gl; e < E; e += LPG) {
+      const bool isneg = e < P.W;
+      const int r = isneg ? __ldg(P.negs + bb * P.W + e) : __ldg(P.group + bb * P.G + (e - P.W));
+      ok = ok && in_range(r, isneg ? P.n_items : P.n_users);
     }
-    const Row<NV> Uu = load_row<LPG, NV>(P.U, u, P.ld, P.nvec, gl);
-    const Row<NV> Vi = load_row<LPG, NV>(P.V, i, P.ld, P.nvec, gl);
-    float lossv = 0.f, sq = 0.f;
+    if (!__all_sync(gmask, ok)) {
+      if (gl == 0) atomicOr(P.counters + 1, CF_FLAG_INDEX_RANGE);
+      continue;
+    }
+    const int u = __shfl_sync(gmask, my_row, leader), i = __shfl_sync(gmask, my_row, leader + 1);
 
-    if constexpr (MODEL == CF_MODEL_BPR) {
-      // bprmf.py:52-75: x_bw = <U_u,V_i> - <U_u,V_jw>; s = sigmoid(x) - 1
-      const float dui = group_sum<LPG>(dotp<NV>(Uu, Vi), gmask);
-      Row<NV> gU = zero_row<NV>();
-      float S = 0.f;
-      if (want_loss) sq = dotp<NV>(Uu, Uu) + dotp<NV>(Vi, Vi);
-      for (int w0 = 0; w0 < P.W; w0 += WT) {
-        Row<NV> Vj[WT];
-        int j[WT];
-        unsigned long long mj[WT];
-#pragma unroll
-        for (int t = 0; t < WT; ++t)
-          if (w0 + t < P.W) {
-            j[t] = __ldg(P.negs + bb * P.W + w0 + t);
-            mj[t] = (sync && gl == 0) ? __ldcg(P.metaV + j[t]) : 0ull;
-            Vj[t] = load_row<LPG, NV>(P.V, j[t], P.ld, P.nvec, gl);
+    // pair-level quantities carried across tiles
+    float S = 0.f;                 // sum_w s_bw (BPR / GBPR)
+    float dmin = INFINITY;         // CML: closest negative distance, its entry index, impostor count
+    int wmin = -1, imp = 0;
+    Row<NV> XA = zero_row<NV>();   // BPR/GBPR: -sum_w s_w V_jw ; CML: V_j*  (pieces of the user-row gradient)
+    Row<NV> XB = zero_row<NV>();   // GBPR: sum_g U_g
+    float lossv = 0.f, sq = 0.f, bsq = 0.f;
+    Row<NV> Uu, Vi;
+    float dui = 0.f, dp = 0.f, bi = 0.f, ui = 0.f, coef = 0.f, omega = 1.f, we = 0.f;
+
+    // ---------------------------------------------------------------- tiles of entries
+    // pass 0 (only when the entries do not fit one tile): CML needs min_w / impostors over ALL negatives and GBPR
+    // needs sum_g U_g before any gradient can be formed; pass 1: gradients + commits.
+    const int first_pass = (!single && (MODEL == CF_MODEL_CML || MODEL == CF_MODEL_GBPR)) ? 0 : 1;
+    unsigned occ_lo = 0u;          // occurrences of MY slot's row in this minibatch (lanes 0 / 1 keep theirs across tiles)
+    for (int pass = first_pass; pass < 2; ++pass) {
+      const bool commit_pass = pass == 1;
+      for (int e0 = 0; e0 < max(E, 1); e0 += max(P.T, 1)) {
+        const int ne = min(P.T, E - e0);           // entries in this tile (0 for WRMF)
+        const bool first_tile = e0 == 0, last_tile = e0 + P.T >= E;
+        // ---- my slot in this tile
+        if (gl >= 2) {
+          my_role = ROLE_NONE;
+          my_row = -1;
+          const int e = e0 + gl - 2;
+          if (gl - 2 < ne) {
+            if (e < P.W) { my_row = __ldg(P.negs + bb * P.W + e); my_role = ROLE_NEG; }
+            else { my_row = __ldg(P.group + bb * P.G + (e - P.W)); my_role = ROLE_GROUP; }
           }
-#pragma unroll
-        for (int t = 0; t < WT; ++t)
-          if (w0 + t < P.W) {
-            const float x = dui - group_sum<LPG>(dotp<NV>(Uu, Vj[t]), gmask);
-            const float s = sigm1(x);
-            S += s;
-            if (want_loss) {
-              lossv += softplus_neg(x);
-              sq += dotp<NV>(Vj[t], Vj[t]);
-            }
-            axpy<NV>(gU, s, Vi);
-            axpy<NV>(gU, -s, Vj[t]);
-            const Row<NV> g = lin2<NV>(-s, Uu, P.reg, Vj[t]);
-            commit<LPG, NV>(P, 1, j[t], mj[t], Vj[t], g, 0.f, 0.f, gl, gmask, leader);
-          }
-      }
-      axpy<NV>(gU, P.reg, Uu);
-      commit<LPG, NV>(P, 0, u, mu, Uu, gU, 0.f, 0.f, gl, gmask, leader);
-      const Row<NV> gV = lin2<NV>(S, Uu, P.reg, Vi);
-      commit<LPG, NV>(P, 1, i, mi, Vi, gV, 0.f, 0.f, gl, gmask, leader);
-      if (want_loss) lossv += 0.5f * P.reg * group_sum<LPG>(sq, gmask);
-    } else if constexpr (MODEL == CF_MODEL_CML) {
-      // cml.py:55-109: hinge on squared distances vs the closest of W negatives, WARP-style rank weight
-      const float c = P.reg > 0.f ? P.reg : 0.f;
-      const float dp = group_sum<LPG>(sqdp<NV>(Uu, Vi), gmask);
-      const bool single = P.W <= WT;
-      Row<NV> Vj[WT];
-      int j[WT];
-      unsigned long long mj[WT];
-      float dmin = INFINITY;
-      int wmin = -1, imp = 0;
-      if (want_loss) sq = dotp<NV>(Uu, Uu) + dotp<NV>(Vi, Vi);
-      for (int w0 = 0; w0 < P.W; w0 += WT) {
-#pragma unroll
-        for (int t = 0; t < WT; ++t)
-          if (w0 + t < P.W) {
-            j[t] = __ldg(P.negs + bb * P.W + w0 + t);
-            mj[t] = (sync && gl == 0) ? __ldcg(P.metaV + j[t]) : 0ull;
-            Vj[t] = load_row<LPG, NV>(P.V, j[t], P.ld, P.nvec, gl);
-          }
-#pragma unroll
-        for (int t = 0; t < WT; ++t)
-          if (w0 + t < P.W) {
-            const float dn = group_sum<LPG>(sqdp<NV>(Uu, Vj[t]), gmask);
-            if (dn < dmin) {
-              dmin = dn;
-              wmin = w0 + t;
-            }
-            imp += ((dp - dn) + P.margin) > 0.f;
-            if (want_loss) sq += dotp<NV>(Vj[t], Vj[t]);
-          }
-      }
-      const float h = (dp - dmin) + P.margin;
-      const float omega = P.use_rank_weight ? logf(((float)imp / (float)P.W) * (float)P.n_items + 1.f) : 1.f;
-      const float coef = h > 0.f ? 2.f * omega : 0.f;
-      if (want_loss) lossv = fmaxf(h, 0.f) * omega + 0.5f * c * group_sum<LPG>(sq, gmask);
-      Row<NV> dUi = lin2<NV>(1.f, Uu, -1.f, Vi);
-      Row<NV> gU = lin2<NV>(coef, dUi, c, Uu);
-      for (int w0 = 0; w0 < P.W; w0 += WT) {
-        if (!single) {
-#pragma unroll
-          for (int t = 0; t < WT; ++t)
-            if (w0 + t < P.W) {
-              j[t] = __ldg(P.negs + bb * P.W + w0 + t);
-              mj[t] = (sync && gl == 0) ? __ldcg(P.metaV + j[t]) : 0ull;
-              Vj[t] = load_row<LPG, NV>(P.V, j[t], P.ld, P.nvec, gl);
-            }
         }
-#pragma unroll
-        for (int t = 0; t < WT; ++t)
-          if (w0 + t < P.W) {
-            const float tie = (w0 + t == wmin) ? coef : 0.f;  // reduce_min grad -> the (first) closest negative
-            const Row<NV> dUj = lin2<NV>(1.f, Uu, -1.f, Vj[t]);
-            axpy<NV>(gU, -tie, dUj);
-            const Row<NV> g = lin2<NV>(tie, dUj, c, Vj[t]);
-            commit<LPG, NV>(P, 1, j[t], mj[t], Vj[t], g, 0.f, 0.f, gl, gmask, leader);
-          }
-      }
-      commit<LPG, NV>(P, 0, u, mu, Uu, gU, 0.f, 0.f, gl, gmask, leader);
-      const Row<NV> gV = lin2<NV>(-coef, dUi, c, Vi);
-      commit<LPG, NV>(P, 1, i, mi, Vi, gV, 0.f, 0.f, gl, gmask, leader);
-    } else if constexpr (MODEL == CF_MODEL_GBPR) {
-      // gbprmf.py:58-93: r_ui = rho * mean_g <U_g,V_i> + (1-rho) <U_u,V_i> + b_i ; r_uj = <U_u,V_j> + b_j
-      const float invG = 1.f / (float)P.G;
-      float bi = 0.f;
-      if (gl == 0) bi = __ldcg(P.b + i);
-      bi = __shfl_sync(gmask, bi, leader);
-      Row<NV> Ug[GT];
-      int gi[GT];
-      unsigned long long mg[GT];
-      Row<NV> Ugs = zero_row<NV>();
-      const bool gsingle = P.G <= GT;
-      if (want_loss) sq = dotp<NV>(Uu, Uu) + dotp<NV>(Vi, Vi);
-      for (int g0 = 0; g0 < P.G; g0 += GT) {
-#pragma unroll
-        for (int t = 0; t < GT; ++t)
-          if (g0 + t < P.G) {
-            gi[t] = __ldg(P.group + bb * P.G + g0 + t);
-            mg[t] = (sync && gl == 0) ? __ldcg(P.metaU + gi[t]) : 0ull;
-            Ug[t] = load_row<LPG, NV>(P.U, gi[t], P.ld, P.nvec, gl);
-          }
-#pragma unroll
-        for (int t = 0; t < GT; ++t)
-          if (g0 + t < P.G) {
-            axpy<NV>(Ugs, 1.f, Ug[t]);
-            if (want_loss) sq += dotp<NV>(Ug[t], Ug[t]);
-          }
-      }
-      const float ui_u = group_sum<LPG>(dotp<NV>(Uu, Vi), gmask);
-      const float ui_g = group_sum<LPG>(dotp<NV>(Ugs, Vi), gmask) * invG;
-      const float ui = P.rho * ui_g + (1.f - P.rho) * ui_u + bi;
-      Row<NV> gU = zero_row<NV>();
-      float S = 0.f, bsq = 0.f;
-      for (int w0 = 0; w0 < P.W; w0 += WT) {
-        Row<NV> Vj[WT];
-        int j[WT];
-        unsigned long long mj[WT];
-        float bj[WT];
-#pragma unroll
-        for (int t = 0; t < WT; ++t)
-          if (w0 + t < P.W) {
-            j[t] = __ldg(P.negs + bb * P.W + w0 + t);
-            mj[t] = (sync && gl == 0) ? __ldcg(P.metaV + j[t]) : 0ull;
-            bj[t] = (gl == 0) ? __ldcg(P.b + j[t]) : 0.f;
-            Vj[t] = load_row<LPG, NV>(P.V, j[t], P.ld, P.nvec, gl);
-          }
-#pragma unroll
-        for (int t = 0; t < WT; ++t)
-          if (w0 + t < P.W) {
-            const float bjt = __shfl_sync(gmask, bj[t], leader);
-            const float x = ui - (group_sum<LPG>(dotp<NV>(Uu, Vj[t]), gmask) + bjt);
-            const float s = sigm1(x);
-            S += s;
-            if (want_loss) {
-              lossv += softplus_neg(x);
-              bsq += bjt * bjt;
-            }
-            axpy<NV>(gU, -s, Vj[t]);
-            const Row<NV> g = lin2<NV>(-s, Uu, 0.f, Vj[t]);  // no L2 on V_j (gbprmf.py:60-64)
-            commit<LPG, NV>(P, 1, j[t], mj[t], Vj[t], g, bjt, fmaf(P.reg, bjt, -s), gl, gmask, leader);
-          }
-      }
-      axpy<NV>(gU, (1.f - P.rho) * S, Vi);
-      axpy<NV>(gU, P.reg, Uu);
-      commit<LPG, NV>(P, 0, u, mu, Uu, gU, 0.f, 0.f, gl, gmask, leader);
-      const float cg = P.rho * invG * S;
-      for (int g0 = 0; g0 < P.G; g0 += GT) {
-        if (!gsingle) {
-#pragma unroll
-          for (int t = 0; t < GT; ++t)
-            if (g0 + t < P.G) {
-              gi[t] = __ldg(P.group + bb * P.G + g0 + t);
-              mg[t] = (sync && gl == 0) ? __ldcg(P.metaU + gi[t]) : 0ull;
-              Ug[t] = load_row<LPG, NV>(P.U, gi[t], P.ld, P.nvec, gl);
-            }
+        const bool is_user_tab = my_role == ROLE_USER || my_role == ROLE_GROUP;
+        const bool stage_ui = first_tile && pass == first_pass;      // u / i parameter rows: once per pair
+        const bool meta_ui = first_tile && commit_pass;              // u / i occurrence words + accumulators: once
+        if (sync && commit_pass && my_role != ROLE_NONE && (gl >= 2 || meta_ui))
+          occ_lo = __ldcg((is_user_tab ? P.metaU : P.metaV) + my_row);
+        // ---- stage parameter rows (and the accumulators of rows this group will apply itself) into shared memory
+        __syncwarp(gmask);   // the previous tile's shared-memory reads are done
+        int my_slot = 0;     // staging slot of my row when it is a duplicated one (loaded while the rows are in flight)
+        for (int s = stage_ui ? 0 : 2; s < 2 + ne; ++s) {
+          const int r = __shfl_sync(gmask, my_row, leader + s);
+          const int role = __shfl_sync(gmask, my_role, leader + s);
+          stage_row<LPG, NV>(sp + (size_t)s * P.ld, (role == ROLE_USER || role == ROLE_GROUP) ? P.U : P.V, r, P.ld, P.nvec, gl);
         }
-#pragma unroll
-        for (int t = 0; t < GT; ++t)
-          if (g0 + t < P.G) {
-            const Row<NV> g = lin2<NV>(cg, Vi, P.reg, Ug[t]);
-            commit<LPG, NV>(P, 0, gi[t], mg[t], Ug[t], g, 0.f, 0.f, gl, gmask, leader);
+        if (adagrad && commit_pass) {
+          for (int s = meta_ui ? 0 : 2; s < 2 + ne; ++s) {
+            const unsigned occ = __shfl_sync(gmask, occ_lo, leader + s);
+            const int r = __shfl_sync(gmask, my_row, leader + s);
+            const int role = __shfl_sync(gmask, my_role, leader + s);
+            if (!sync || occ <= 1u)
+              stage_row<LPG, NV>(sa + (size_t)s * P.ld, (role == ROLE_USER || role == ROLE_GROUP) ? P.accU : P.accV, r, P.ld, P.nvec, gl);
           }
-      }
-      Row<NV> gV = lin2<NV>(P.rho * invG * S, Ugs, (1.f - P.rho) * S, Uu);
-      axpy<NV>(gV, P.reg, Vi);
-      commit<LPG, NV>(P, 1, i, mi, Vi, gV, bi, S, gl, gmask, leader);
-      if (want_loss) lossv += 0.5f * P.reg * (group_sum<LPG>(sq, gmask) + bsq);
-    } else {
-      // wrmf.py:52-75: e = <U_u,V_i> - r ; L = weight/2 e^2 + reg/2 (|U_u|^2 + |V_i|^2)
-      const float r = __ldg(P.ratings + bb);
-      const float e = group_sum<LPG>(dotp<NV>(Uu, Vi), gmask) - r;
-      const float we = P.weight * e;
-      if (want_loss)
-        lossv = 0.5f * P.weight * e * e + 0.5f * P.reg * group_sum<LPG>(dotp<NV>(Uu, Uu) + dotp<NV>(Vi, Vi), gmask);
-      const Row<NV> gU = lin2<NV>(we, Vi, P.reg, Uu);
-      const Row<NV> gV = lin2<NV>(we, Uu, P.reg, Vi);
-      commit<LPG, NV>(P, 0, u, mu, Uu, gU, 0.f, 0.f, gl, gmask, leader);
-      commit<LPG, NV>(P, 1, i, mi, Vi, gV, 0.f, 0.f, gl, gmask, leader);
+        }
+        if (sync && commit_pass && my_role != ROLE_NONE && (gl >= 2 || last_tile) && occ_lo > 1u)
+          my_slot = __ldcg((is_user_tab ? P.slotU : P.slotV) + my_row);
+        cp_async_wait_all();
+        __syncwarp(gmask);
+
+        // ---- pair-level forward quantities (first tile of the first pass)
+        if (first_tile && pass == first_pass) {
+          Uu = smem_row<LPG, NV>(sp, P.nvec, gl);
+          Vi = smem_row<LPG, NV>(sp + P.ld, P.nvec, gl);
+          if (want_loss) sq = dotp<NV>(Uu, Uu) + dotp<NV>(Vi, Vi);
+          if constexpr (MODEL == CF_MODEL_BPR) dui = group_sum<LPG>(dotp<NV>(Uu, Vi), gmask);
+          if constexpr (MODEL == CF_MODEL_CML) dp = group_sum<LPG>(sqdp<NV>(Uu, Vi), gmask);
+          if constexpr (MODEL == CF_MODEL_GBPR) {
+            dui = group_sum<LPG>(dotp<NV>(Uu, Vi), gmask);
+            bi = __ldcg(P.b + i);
+          }
+          if constexpr (MODEL == CF_MODEL_WRMF) {
+            const float e = group_sum<LPG>(dotp<NV>(Uu, Vi), gmask) - __ldg(P.ratings + bb);
+            we = P.weight * e;
+            if (want_loss) lossv = 0.5f * P.weight * e * e;
+          }
+        }
+
+        // ---- per-entry forward: scores / distances; the entry's lane keeps its coefficient
+        float my_alpha = 0.f, my_b = 0.f, my_gb = 0.f;
+        if constexpr (MODEL == CF_MODEL_GBPR) {
+          if (my_role == ROLE_NEG) my_b = __ldcg(P.b + my_row);
+          if (gl == 1) my_b = bi;
+          // group rows first: sum_g U_g (pass 0, or the single tile)
+          if (pass == first_pass) {
+            for (int s = 2; s < 2 + ne; ++s) {
+              if (__shfl_sync(gmask, my_role, leader + s) != ROLE_GROUP) continue;
+              const Row<NV> Ug = smem_row<LPG, NV>(sp + (size_t)s * P.ld, P.nvec, gl);
+              axpy<NV>(XB, 1.f, Ug);
+              if (want_loss) sq += dotp<NV>(Ug, Ug);
+            }
+          }
+          if (commit_pass && first_tile) {  // sum_g U_g is complete here (pass 0 covered every tile, or single tile)
+            const float ui_g = group_sum<LPG>(dotp<NV>(XB, Vi), gmask) / (float)P.G;
+            ui = P.rho * ui_g + (1.f - P.rho) * dui + bi;
+          }
+        }
+        if (MODEL != CF_MODEL_WRMF && (commit_pass || MODEL == CF_MODEL_CML)) {
+          for (int s = 2; s < 2 + ne; ++s) {
+            if (__shfl_sync(gmask, my_role, leader + s) != ROLE_NEG) continue;
+            const Row<NV> Vj = smem_row<LPG, NV>(sp + (size_t)s * P.ld, P.nvec, gl);
+            if constexpr (MODEL == CF_MODEL_BPR) {
+              const float x = dui - group_sum<LPG>(dotp<NV>(Uu, Vj), gmask);   // bprmf.py:68-70
+              const float sw = sigm1(x);
+              S += sw;
+              axpy<NV>(XA, -sw, Vj);
+              if (gl == s) my_alpha = -sw;
+              if (want_loss) { lossv += softplus_neg(x); sq += dotp<NV>(Vj, Vj); }
+            } else if constexpr (MODEL == CF_MODEL_CML) {
+              if (pass == first_pass) {                                            // cml.py:63-82
+                const float dn = group_sum<LPG>(sqdp<NV>(Uu, Vj), gmask);
+                if (dn < dmin) { dmin = dn; wmin = e0 + s - 2; }
+                imp += ((dp - dn) + P.margin) > 0.f;
+                if (want_loss) sq += dotp<NV>(Vj, Vj);
+              }
+            } else if constexpr (MODEL == CF_MODEL_GBPR) {
+              const float bj = __shfl_sync(gmask, my_b, leader + s);
+              const float x = ui - (group_sum<LPG>(dotp<NV>(Uu, Vj), gmask) + bj);  // gbprmf.py:83-88
+              const float sw = sigm1(x);
+              S += sw;
+              axpy<NV>(XA, -sw, Vj);
+              if (gl == s) { my_alpha = -sw; my_gb = fmaf(P.reg, bj, -sw); }
+              if (want_loss) { lossv += softplus_neg(x); bsq += bj * bj; }
+            }
+          }
+        }
+        if (!commit_pass) continue;
+
+        if constexpr (MODEL == CF_MODEL_CML) {
+          if (first_tile) {  // min / impostors are complete (pass 0 or single tile): hinge, rank weight (cml.py:73-85)
+            const float h = (dp - dmin) + P.margin;
+            omega = P.use_rank_weight ? __logf(((float)imp / (float)P.W) * (float)P.n_items + 1.f) : 1.f;
+            coef = h > 0.f ? 2.f * omega : 0.f;
+            if (want_loss) lossv = fmaxf(h, 0.f) * omega;
+          }
+          if (my_role == ROLE_NEG && e0 + gl - 2 == wmin) my_alpha = coef;   // reduce_min grad -> the closest negative
+          if (wmin >= e0 && wmin < e0 + ne) XA = smem_row<LPG, NV>(sp + (size_t)(2 + wmin - e0) * P.ld, P.nvec, gl);
+        }
+
+        // ---- commit loop over the slots of this tile (u and i ride with the last tile)
+        for (int s = last_tile ? 0 : 2; s < 2 + ne; ++s) {
+          const int role = __shfl_sync(gmask, my_role, leader + s);
+          if (role == ROLE_NONE) continue;
+          const int r = __shfl_sync(gmask, my_row, leader + s);
+          const float alpha = __shfl_sync(gmask, my_alpha, leader + s);
+          const unsigned occ = __shfl_sync(gmask, occ_lo, leader + s);
+          const bool utab = role == ROLE_USER || role == ROLE_GROUP;
+          const Row<NV> cur = smem_row<LPG, NV>(sp + (size_t)s * P.ld, P.nvec, gl);
+          Row<NV> g;
+          if constexpr (MODEL == CF_MODEL_BPR) {
+            if (role == ROLE_NEG) g = lin2<NV>(alpha, Uu, creg, cur);                     // -s U + reg V_j
+            else if (role == ROLE_ITEM) g = lin2<NV>(S, Uu, creg, cur);                    // S U + reg V_i
+            else { g = lin2<NV>(S, Vi, creg, cur); axpy<NV>(g, 1.f, XA); }                 // S V_i - sum s V_j + reg U
+          } else if constexpr (MODEL == CF_MODEL_CML) {
+            if (role == ROLE_NEG) g = lin2<NV>(alpha, Uu, creg - alpha, cur);              // tie (U - V_j) + c V_j
+            else if (role == ROLE_ITEM) g = lin2<NV>(-coef, Uu, creg + coef, cur);          // -coef (U - V_i) + c V_i
+            else { g = lin2<NV>(coef, XA, creg, cur); axpy<NV>(g, -coef, Vi); }            // coef (V_j* - V_i) + c U
+          } else if constexpr (MODEL == CF_MODEL_GBPR) {
+            const float cg = P.rho * S / (float)P.G;
+            if (role == ROLE_NEG) g = lin2<NV>(alpha, Uu, 0.f, cur);                       // -s U          (no L2 on V_j)
+            else if (role == ROLE_GROUP) g = lin2<NV>(cg, Vi, creg, cur);                  // rho/G S V_i + reg U_g
+            else if (role == ROLE_ITEM) { g = lin2<NV>((1.f - P.rho) * S, Uu, creg, cur); axpy<NV>(g, cg, XB); }
+            else { g = lin2<NV>((1.f - P.rho) * S, Vi, creg, cur); axpy<NV>(g, 1.f, XA); }
+          } else {
+            g = role == ROLE_ITEM ? lin2<NV>(we, Uu, creg, cur) : lin2<NV>(we, Vi, creg, cur);
+          }
+          float* Tb = utab ? P.U : P.V;
+          float* Ab = utab ? P.accU : P.accV;
+          if (!sync || occ <= 1u) {  // unique row (or racy mode): update straight from registers / shared memory
+            Row<NV> acc = smem_row<LPG, NV>(sa + (size_t)s * P.ld, P.nvec, gl, 1.f), p;
+            apply_math<LPG, NV>(P, cur, acc, g, p, gmask);
+            if (adagrad) store_row<LPG, NV>(Ab, r, P.ld, P.nvec, gl, acc);
+            store_row<LPG, NV>(Tb, r, P.ld, P.nvec, gl, p);
+          } else {
+            // the row occurs more than once in this minibatch: stage the gradient; k_apply_staged applies the sum
+            const int slot = __shfl_sync(gmask, my_slot, leader + s);
+            float* st = P.staging + (long long)slot * P.lds;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+              const int v = gl + k * LPG;
+              if (v < P.nvec) atomicAdd(reinterpret_cast<float4*>(st + 4 * v), g.v[k]);
+            }
+          }
+        }
+        // ---- item bias (GBPR): one lane per item slot
+        if constexpr (MODEL == CF_MODEL_GBPR) {
+          if (gl == 1) my_gb = S;
+          const bool item_slot = (my_role == ROLE_NEG) || (gl == 1 && last_tile);
+          if (item_slot) {
+            if (!sync || occ_lo <= 1u) apply_bias(P, my_row, my_b, my_gb);
+            else atomicAdd(P.staging + (long long)my_slot * P.lds + P.ld, my_gb);
+          }
+        }
+        // ---- unique rows are done: return their occurrence word to zero (duplicated rows: k_apply_staged does it)
+        if (sync && my_role != ROLE_NONE && (gl >= 2 || last_tile) && occ_lo <= 1u)
+          __stcg((is_user_tab ? P.metaU : P.metaV) + my_row, 0u);
+      }  // tiles
+    }    // passes
+    if (want_loss) {
+      const float regsq = group_sum<LPG>(sq, gmask) + bsq;
+      if (gl == 0) loss_acc += (double)(lossv + 0.5f * creg * regsq);
     }
-    if (want_loss && gl == 0) loss_acc += (double)lossv;
   }
 
   if (want_loss) {
@@ -494,37 +462,60 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepDev P)
     for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
     if (lane == 0 && loss_acc != 0.0) atomicAdd(P.loss, loss_acc);
   }
-  if (sync) {  // last block out resets the slot counter for the next minibatch
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      const int t = atomicAdd(P.counters + 2, 1);
-      if (t == (int)gridDim.x - 1) {
-        P.counters[0] = 0;
-        P.counters[2] = 0;
-        __threadfence();
+}
+
+// Applies the summed gradient of every row that occurred more than once in the minibatch (one group per staging slot):
+// param + acc + staged gradient in, param + acc out, slot and occurrence word back to zero.  The parameter row is still
+// the pre-update one (k_step never writes a duplicated row), so this is exactly TF's "sum duplicates, apply once".
+#define CF_SLOT_EMPTY 0xffffffffu
+
+template <int LPG, int NV>
+__global__ void __launch_bounds__(256) k_apply_staged(const __grid_constant__ StepDev P) {
+  const int lane = threadIdx.x & 31, gl = lane & (LPG - 1), leader = lane & ~(LPG - 1);
+  const unsigned gmask = LPG == 32 ? 0xffffffffu : (((1u << LPG) - 1u) << leader);
+  const long long ngroups = (long long)gridDim.x * blockDim.x / LPG;
+  const int R = (P.model == CF_MODEL_WRMF) ? 2 : 2 + P.W + P.G;
+  const long long n = (long long)P.B * R;     // one potential slot per row occurrence of the minibatch
+  const bool adagrad = P.optimizer == CF_OPT_ADAGRAD;
+  // each group scans LPG consecutive slot codes at a time (one coalesced load) and walks the occupied ones together
+  for (long long t0 = (((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPG) * LPG; t0 < n; t0 += ngroups * LPG) {
+    uint32_t code = CF_SLOT_EMPTY;
+    if (t0 + gl < n) code = __ldcg(P.slot_row + t0 + gl);
+    unsigned occupied = (__ballot_sync(gmask, code != CF_SLOT_EMPTY) & gmask) >> leader;
+    if (code != CF_SLOT_EMPTY) __stcg(P.slot_row + t0 + gl, CF_SLOT_EMPTY);
+    while (occupied) {
+      const int k = __ffs(occupied) - 1;
+      occupied &= occupied - 1;
+      const uint32_t c = __shfl_sync(gmask, code, leader + k);
+      const bool vtab = c >> 31;
+      const long long r = c & 0x7fffffffu;
+      float* st = P.staging + (t0 + k) * P.lds;
+      const Row<NV> g = load_row<LPG, NV>(st, 0, 0, P.nvec, gl);
+      const Row<NV> cur = load_row<LPG, NV>(vtab ? P.V : P.U, r, P.ld, P.nvec, gl);
+      Row<NV> acc, p;
+      if (adagrad) acc = load_row<LPG, NV>(vtab ? P.accV : P.accU, r, P.ld, P.nvec, gl, 1.f);
+      apply_math<LPG, NV>(P, cur, acc, g, p, gmask);
+      if (adagrad) store_row<LPG, NV>(vtab ? P.accV : P.accU, r, P.ld, P.nvec, gl, acc);
+      store_row<LPG, NV>(vtab ? P.V : P.U, r, P.ld, P.nvec, gl, p);
+      // The slot is zeroed only AFTER its gradient has been consumed: a store issued while a load of the same line is
+      // still outstanding is ~4x slower on B200 (measured, tests/micro/apply_micro.cu: 264 us vs 61 us per 100k rows).
+      store_row<LPG, NV>(st, 0, 0, P.nvec, gl, zero_row<NV>());
+      if (gl == 0) {
+        if (vtab && P.b != nullptr) {
+          const float gb = __ldcg(st + P.ld);
+          apply_bias(P, r, __ldcg(P.b + r), gb);
+          __stcg(st + P.ld, 0.f);
+        }
+        __stcg((vtab ? P.metaV : P.metaU) + r, 0u);
       }
     }
   }
 }
 
-
 typedef void (*step_kernel_t)(const StepDev);
-
-template <int MODEL, int LPG, int NV>
-inline step_kernel_t pick_wt(int W) {
-  if (MODEL == CF_MODEL_WRMF) return k_step<MODEL, LPG, NV, 1>;
-  if (W <= 1) return k_step<MODEL, LPG, NV, 1>;
-  if constexpr (NV >= 4) {  // very wide rows (ld > 256): fewer register-resident negatives, longer tile loops
-    return k_step<MODEL, LPG, NV, 4>;
-  } else {
-    if (W <= 2) return k_step<MODEL, LPG, NV, 2>;
-    if (W <= 4) return k_step<MODEL, LPG, NV, 4>;
-    return k_step<MODEL, LPG, NV, 8>;
-  }
-}
 
 }  // namespace cfstep
 
 // one instantiation unit per (model, row shape): build.py generates build/gen/cf_step_inst_<m>_<s>.cu defining these
-#define CF_STEP_PICK_DECL(M, S) cfstep::step_kernel_t cf_step_pick_##M##_##S(int W)
+#define CF_STEP_PICK_DECL(M, S) cfstep::step_kernel_t cf_step_pick_##M##_##S()
+#define CF_APPLY_PICK_DECL(S) cfstep::step_kernel_t cf_apply_pick_##S()

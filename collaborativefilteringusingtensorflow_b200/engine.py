@@ -106,8 +106,9 @@ class FactorEngine(object):
         rows = int(self.lib.cf_step_staging_rows(self.model_id, B, W, G))
         if self._ws is None or self._ws_rows < rows:
             self._ws = dict(
-                metaU=torch.zeros(self.n_users, dtype=torch.int64, device=self.device),
-                metaV=torch.zeros(self.n_items, dtype=torch.int64, device=self.device),
+                metaU=torch.zeros(self.n_users, dtype=torch.int32, device=self.device),
+                metaV=torch.zeros(self.n_items, dtype=torch.int32, device=self.device),
+                slot_row=torch.full((rows,), -1, dtype=torch.int32, device=self.device),   # CF_SLOT_EMPTY
                 slotU=torch.zeros(self.n_users, dtype=torch.int32, device=self.device),
                 slotV=torch.zeros(self.n_items, dtype=torch.int32, device=self.device),
                 staging=torch.zeros(rows, self.ld + 4, device=self.device))
@@ -118,6 +119,7 @@ class FactorEngine(object):
         if self._ws is not None:
             for k in ('metaU', 'metaV', 'staging'):
                 self._ws[k].zero_()
+            self._ws['slot_row'].fill_(-1)
         self.counters.zero_()
 
     def check_flags(self):
@@ -145,7 +147,7 @@ class FactorEngine(object):
         x = x.to(device=self.device, dtype=torch.int32, non_blocking=True).contiguous()
         return x
 
-    def train_batches(self, pairs, negs=None, group=None, ratings=None, batch_size=None, want_loss=True):
+    def train_batches(self, pairs, negs=None, group=None, ratings=None, batch_size=None, want_loss=True, profile=None):
         """Run ``n = rows / batch_size`` consecutive minibatches (the inner loop of bprmf.py:143-148).
         Index arrays may be numpy or torch (any int dtype); returns the per-minibatch loss as a CUDA float64
         tensor (or None)."""
@@ -188,7 +190,7 @@ class FactorEngine(object):
         if self.update == 'sync':
             ws = self._workspace(B, W, G)
             a.metaU, a.metaV = _lib.ptr(ws['metaU']), _lib.ptr(ws['metaV'])
-            a.slotU, a.slotV = _lib.ptr(ws['slotU']), _lib.ptr(ws['slotV'])
+            a.slotU, a.slotV, a.slot_row = _lib.ptr(ws['slotU']), _lib.ptr(ws['slotV']), _lib.ptr(ws['slot_row'])
             a.staging, a.staging_rows = _lib.ptr(ws['staging']), ws['staging'].shape[0]
         a.counters = _lib.ptr(self.counters)
         loss = torch.zeros(nb, dtype=torch.float64, device=self.device) if want_loss else None
@@ -205,11 +207,20 @@ class FactorEngine(object):
             a.negs = negs.data_ptr() + 4 * W * B
             a.loss = (loss.data_ptr() + 8) if want_loss else None
             _lib.check(self.lib.cf_train_steps(a, stream), 'cf_train_steps')
+        elif profile is not None:   # bench.py: per-kernel CUDA-event times (synchronises)
+            import ctypes as C
+            mc, ms, ma = C.c_float(0), C.c_float(0), C.c_float(0)
+            _lib.check(self.lib.cf_train_steps_profiled(a, stream, C.byref(mc), C.byref(ms), C.byref(ma)),
+                       'cf_train_steps_profiled')
+            profile['count_ms'] = profile.get('count_ms', 0.0) + mc.value
+            profile['step_ms'] = profile.get('step_ms', 0.0) + ms.value
+            profile['apply_ms'] = profile.get('apply_ms', 0.0) + ma.value
+            profile['n_batches'] = profile.get('n_batches', 0) + nb
         else:
             _lib.check(self.lib.cf_train_steps(a, stream), 'cf_train_steps')
             if self._needs_full_clip:
                 self._full_clip(stream)
-        self.launches += nb * (2 if self.update == 'sync' else 1)
+        self.launches += nb * (3 if self.update == 'sync' else 1)
         return loss
 
     def _full_clip(self, stream):

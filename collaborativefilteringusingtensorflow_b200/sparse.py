@@ -16,6 +16,9 @@ class DeviceCSR(object):
         self._t = None
         self._host = None
 
+    def __len__(self):
+        return self.shape[0]
+
     @classmethod
     def from_scipy(cls, m, device, with_values=False):
         torch = _lib.require_cuda()

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CF_ABI_VERSION 3
+#define CF_ABI_VERSION 5
 
 /* models */
 enum { CF_MODEL_BPR = 0, CF_MODEL_CML = 1, CF_MODEL_GBPR = 2, CF_MODEL_WRMF = 3 };
@@ -56,7 +56,8 @@ const char* cf_build_arch(void);
  *   bprmf.py:145  (BPRMF),  cml.py:184 (CML, incl. the clip of cml.py:119-129),
  *   gbprmf.py:163 (GBPRMF), wrmf.py:145 (WRMF)
  * for `n_batches` consecutive minibatches of `B` rows each (the reference's inner loop bprmf.py:143-148).
- * Per minibatch it launches a row-occurrence counting kernel and ONE fused gather/gradient/update kernel.
+ * Per minibatch it launches a row-occurrence counting kernel, ONE fused gather/gradient/update kernel and a
+ * kernel that applies the summed gradient of the rows that occurred more than once.
  * ------------------------------------------------------------------------------------------------ */
 typedef struct cf_step_args {
   /* parameters */
@@ -92,18 +93,24 @@ typedef struct cf_step_args {
   float weight;            /* WRMF */
   /* workspace (see cf_step_workspace_sizes); metaU/metaV/slots/staging must be zero before the first
    * call and are returned to zero by every successful call */
-  uint64_t* metaU;         /* [n_users]  (occurrences | done<<32) */
-  uint64_t* metaV;         /* [n_items] */
-  int32_t* slotU;          /* [n_users]  staging slot of a duplicated row */
+  uint32_t* metaU;         /* [n_users]  occurrences of the row in the current minibatch */
+  uint32_t* metaV;         /* [n_items] */
+  int32_t* slotU;          /* [n_users]  staging slot of a row that occurs more than once */
   int32_t* slotV;          /* [n_items] */
+  uint32_t* slot_row;      /* [staging_rows] inverse map: slot -> row id | (item table ? 1u<<31 : 0); 0xffffffff = empty,
+                            * must be all-empty before the first call and is returned all-empty */
   float* staging;          /* [staging_rows, ld + 4] gradient staging for rows that occur more than once */
   int64_t staging_rows;
-  int32_t* counters;       /* [4]: {n_slots, flags, ticket, reserved}, zero-initialised */
+  int32_t* counters;       /* [4]: {reserved, flags, reserved, reserved}, zero-initialised */
   double* loss;            /* [n_batches] summed minibatch loss, or NULL to skip the loss */
 } cf_step_args;
 
 int cf_train_steps(const cf_step_args* args, void* stream);
-/* rows of staging needed so that no batch of B rows can overflow it */
+/* same work, but brackets every kernel with CUDA events on `stream`, synchronises, and returns the summed device
+ * time (ms) of the counting, fused-step and staged-apply kernels (bench.py's per-kernel roofline numbers) */
+int cf_train_steps_profiled(const cf_step_args* args, void* stream, float* ms_count_host, float* ms_step_host,
+                            float* ms_apply_host);
+/* rows of staging (and entries of slot_row) needed for minibatches of B rows: one per row occurrence */
 int64_t cf_step_staging_rows(int32_t model, int32_t B, int32_t W, int32_t G);
 /* number of kernels cf_train_steps launches per minibatch (for gpu_launches accounting) */
 int32_t cf_step_launches_per_batch(void);

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     # field order/types are mirrored by hand; sizes follow from the C layout rules (natural alignment)
     assert C.sizeof(_lib.Csr) == 4 * 8 + 3 * 8
-    assert C.sizeof(_lib.StepArgs) == 6 * 8 + 2 * 8 + 2 * 4 + 4 * 8 + 4 * 4 + 4 * 4 + 6 * 4 + 5 * 8 + 8 + 2 * 8
+    assert C.sizeof(_lib.StepArgs) == 6 * 8 + 2 * 8 + 2 * 4 + 4 * 8 + 4 * 4 + 4 * 4 + 6 * 4 + 6 * 8 + 8 + 2 * 8
     assert C.sizeof(_lib.SampleArgs) == 2 * C.sizeof(_lib.Csr) + 3 * 8 + 6 * 4 + 5 * 8
     assert C.sizeof(_lib.TopkArgs) == 3 * 8 + 2 * 8 + 2 * 4 + 8 + 3 * 4 + 4 + C.sizeof(_lib.Csr) + 3 * 8 + 2 * 8
 
@@ -49,8 +49,8 @@ def test_host_side_validation_needs_no_gpu():
     assert lib.cf_topk_exact(C.byref(t), None) < 0
     t.U, t.V, t.out_idx, t.d, t.ld, t.T, t.K, t.n_items = 16, 32, 48, 8, 8, 4, 5000, 100
     assert lib.cf_topk_exact(C.byref(t), None) < 0 and b'K must be' in lib.cf_last_error()
-    assert lib.cf_step_staging_rows(_lib.MODEL_CML, 100, 5, 0) == 351
-    assert lib.cf_step_staging_rows(_lib.MODEL_WRMF, 200, 7, 3) == 201
+    assert lib.cf_step_staging_rows(_lib.MODEL_CML, 100, 5, 0) == 700
+    assert lib.cf_step_staging_rows(_lib.MODEL_WRMF, 200, 7, 3) == 400
 
 
 def test_product_refuses_to_run_without_cuda():
