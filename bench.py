@@ -378,6 +378,7 @@ def main():
     ap.add_argument('--topk-users', type=int, default=1024)
     ap.add_argument('--cpu-budget', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--phases', action='store_true', help='N > 1: also report per-phase times of the sharded step')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -1,0 +1,95 @@
+"""bench.py's N > 1 arm: weak scaling of the N=1 workload per GPU (same users, interactions and minibatch per rank; the item
+catalogue grows with N so every rank owns the same number of item rows), users range-sharded, items sharded by item % N,
+per-minibatch NCCL all-to-all of requested item rows and their gradients."""
+import json
+import os
+import time
+
+import torch
+import torch.distributed as dist
+
+
+def run_distributed(args, rank, world, device):
+    import bench as B_
+    from collaborativefilteringusingtensorflow_b200.dist import DistributedTrainer, item_shard_rows
+    wl = dict(B_.WORKLOADS[args.workload])
+    if wl['model'] not in ('cml', 'bpr'):
+        raise SystemExit('the sharded path supports the cml / bpr workloads')
+    n_items_global = wl['n_items'] * world
+    B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
+    pk = B_.peaks()
+    csr = B_.synth_interactions(wl['n_users'], n_items_global, wl['nnz'], 2026 + rank, device)
+    local_wl = dict(wl, n_items=item_shard_rows(n_items_global, world, rank))
+    model = B_.make_model(local_wl, device, seed=2026 + rank, optimizer=args.optimizer, update='sync')
+    sampler = B_.make_sampler(wl, csr, B, 2026 + rank, device)
+    tr = DistributedTrainer(model, sampler, n_items_global, world, rank)
+    tr.step(Wm)
+    model.engine.check_flags()
+    torch.cuda.synchronize()
+    dist.barrier()
+
+    clk = B_.ClockSampler(device.index)
+    if rank == 0:
+        clk.start()
+        time.sleep(0.3)
+    l0, s0, b0 = tr.launches, sampler.launches, tr.bytes_sent
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.time()
+    e0.record()
+    losses = tr.step(K)
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    launches = (tr.launches - l0) + (sampler.launches - s0)
+    sent = (tr.bytes_sent - b0) / K
+    model.engine.check_flags()
+
+    # e2e: host index buffers -> H2D -> sharded step -> D2H loss, every step
+    host = [t.cpu().pin_memory() for t in sampler.next_chunk(K)]
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for k in range(K):
+        dev = [t[k * B:(k + 1) * B].to(device, non_blocking=True) for t in host]
+        _ = tr.step_chunk(dev[0], dev[1], B).cpu()
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=device)
+    dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    ms2 = float(ms2.item())
+    phases = None
+    if args.phases:
+        tr.phase_ms = {}
+        tr.step(5)
+        phases = {k: v / 5 for k, v in tr.phase_ms.items()}
+        tr.phase_ms = None
+    if rank != 0:
+        return
+    clocks = clk.stop(t0, t1)
+    units = world * B * wl['W'] * K
+    bpp = B_.bytes_per_pair(wl['model'], wl['d'], wl['W'], wl['G'], args.optimizer)
+    achieved = bpp * B / (ms / K * 1e-3) / 1e9            # per GPU, whole sharded step (exchange included)
+    out = dict(metric='triple updates/s (fused pairwise-ranking step incl. on-device sampling) @d=%d' % wl['d'],
+               value=units / (ms * 1e-3), unit='triple updates/s', n_gpus=world, steps=K, warmup=Wm, ms_per_step=ms / K,
+               higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+               config=dict(workload=wl['desc'] + ' PER GPU; items = %d x %d GPUs, users range-sharded, items by item %% N, '
+                           'NCCL all-to-all of item rows + gradients per minibatch' % (wl['n_items'], world),
+                           batch_pairs_per_gpu=B, negatives=wl['W'], optimizer=args.optimizer, update='sync',
+                           l2='inputs larger than L2 (random rows of GB-sized tables)'),
+               gpu_launches=launches,
+               e2e=dict(value=units / (ms2 * 1e-3), unit='triple updates/s', ms_per_step=ms2 / K,
+                        h2d_bytes_per_step=sum(int(t[:B].numel()) * t.element_size() for t in host), d2h_bytes_per_step=8),
+               roofline=dict(bound='hbm', kernel='whole sharded step per GPU (k_count + k_step + k_apply_staged + exchange + owner apply)',
+                             achieved=achieved, peak=pk['hbm'], unit='GB/s', frac=achieved / pk['hbm'], traffic=None,
+                             peak_source=pk['source']),
+               nvlink=dict(bytes_sent_per_step_per_gpu=sent, achieved_GBs=sent / (ms / K * 1e-3) / 1e9,
+                           peak_GBs_per_direction=770.0, note='rows out + gradients back + ids; measured peer copy 770 GB/s/dir'),
+               phases_ms_per_step=phases, cpu_baseline=None, clocks=clocks, loss_first_last=[float(losses[0]), float(losses[-1])])
+    print(json.dumps(out))

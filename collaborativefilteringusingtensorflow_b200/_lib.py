@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libcf_b200.so')
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # enums of cf_b200.h
 MODEL_BPR, MODEL_CML, MODEL_GBPR, MODEL_WRMF = 0, 1, 2, 3
@@ -30,7 +30,16 @@ class StepArgs(C.Structure):
         ('lr', C.c_float), ('reg', C.c_float), ('margin', C.c_float), ('clip_norm', C.c_float),
         ('rho', C.c_float), ('weight', C.c_float),
         ('metaU', _p), ('metaV', _p), ('slotU', _p), ('slotV', _p), ('slot_row', _p), ('staging', _p),
-        ('staging_rows', C.c_int64), ('counters', _p), ('loss', _p),
+        ('staging_rows', C.c_int64), ('counters', _p), ('loss', _p), ('gradV', _p), ('rank_items', C.c_int64),
+    ]
+
+
+class ApplyArgs(C.Structure):
+    _fields_ = [
+        ('table', _p), ('acc', _p), ('n_rows', C.c_int64), ('d', C.c_int32), ('ld', C.c_int32),
+        ('rows', _p), ('grads', _p), ('n', C.c_int64), ('ldg', C.c_int32), ('model', C.c_int32),
+        ('optimizer', C.c_int32), ('lr', C.c_float), ('clip_norm', C.c_float),
+        ('meta', _p), ('slot', _p), ('slot_row', _p), ('staging', _p), ('staging_rows', C.c_int64), ('counters', _p),
     ]
 
 
@@ -66,6 +75,7 @@ _SIGNATURES = {
                                         C.POINTER(C.c_float)]),
     'cf_step_staging_rows': (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     'cf_step_launches_per_batch': (C.c_int32, []),
+    'cf_apply_rows': (C.c_int, [C.POINTER(ApplyArgs), _p]),
     'cf_clip_rows': (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, _p]),
     'cf_sample_ranking': (C.c_int, [C.POINTER(SampleArgs), _p]),
     'cf_sample_rating': (C.c_int, [C.POINTER(SampleArgs), _p]),

@@ -26,6 +26,7 @@ using namespace cfstep;
 #define CF_DECL_MODEL(M) CF_STEP_PICK_DECL(M, 0); CF_STEP_PICK_DECL(M, 1); CF_STEP_PICK_DECL(M, 2); CF_STEP_PICK_DECL(M, 3); CF_STEP_PICK_DECL(M, 4);
 CF_DECL_MODEL(0) CF_DECL_MODEL(1) CF_DECL_MODEL(2) CF_DECL_MODEL(3)
 CF_APPLY_PICK_DECL(0); CF_APPLY_PICK_DECL(1); CF_APPLY_PICK_DECL(2); CF_APPLY_PICK_DECL(3); CF_APPLY_PICK_DECL(4);
+CF_SCATTER_PICK_DECL(0); CF_SCATTER_PICK_DECL(1); CF_SCATTER_PICK_DECL(2); CF_SCATTER_PICK_DECL(3); CF_SCATTER_PICK_DECL(4);
 
 namespace {
 
@@ -46,7 +47,8 @@ __global__ void __launch_bounds__(256) k_count(const __grid_constant__ StepDev P
       else if (k == 1) { tab = 1; r = __ldg(P.pairs + 2 * b + 1); }
       else if (k < 2 + P.W) { tab = 1; r = __ldg(P.negs + b * P.W + (k - 2)); }
       else { tab = 0; r = __ldg(P.group + b * P.G + (k - 2 - P.W)); }
-      if (!in_range(r, tab ? P.n_items : P.n_users)) atomicOr(P.counters + 1, CF_FLAG_INDEX_RANGE);
+      if (tab && P.gradV) { /* fetched item rows are not applied here */ }
+      else if (!in_range(r, tab ? P.n_items : P.n_users)) atomicOr(P.counters + 1, CF_FLAG_INDEX_RANGE);
       else need = atomicAdd((tab ? P.metaV : P.metaU) + r, 1u) == 1u;   // second occurrence: the row needs a staging slot
     }
     if (need) {
@@ -90,6 +92,29 @@ step_kernel_t pick_apply(int nvec) {
     case 2: return cf_apply_pick_2();
     case 3: return cf_apply_pick_3();
     default: return cf_apply_pick_4();
+  }
+}
+
+scatter_kernel_t pick_scatter(int nvec) {
+  const int shape = nvec <= 8 ? 0 : nvec <= 16 ? 1 : nvec <= 32 ? 2 : nvec <= 64 ? 3 : 4;
+  switch (shape) {
+    case 0: return cf_scatter_pick_0();
+    case 1: return cf_scatter_pick_1();
+    case 2: return cf_scatter_pick_2();
+    case 3: return cf_scatter_pick_3();
+    default: return cf_scatter_pick_4();
+  }
+}
+
+// owner-side counting: one thread per received gradient row
+__global__ void __launch_bounds__(256) k_count_rows(const __grid_constant__ StepDev P, const int32_t* __restrict__ rows, long long n) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const long long r = __ldg(rows + t);
+    if (!in_range(r, P.n_users)) { atomicOr(P.counters + 1, CF_FLAG_INDEX_RANGE); continue; }
+    if (atomicAdd(P.metaU + r, 1u) == 1u) {
+      P.slotU[r] = (int)t;
+      P.slot_row[t] = (uint32_t)r;
+    }
   }
 }
 
@@ -169,6 +194,8 @@ static int train_steps_impl(const cf_step_args* a, cudaStream_t stream, cudaEven
   P.metaU = a->metaU; P.metaV = a->metaV; P.slot_row = a->slot_row;
   P.slotU = a->slotU; P.slotV = a->slotV; P.staging = a->staging; P.staging_rows = a->staging_rows;
   P.lds = a->ld + 4; P.counters = a->counters;
+  P.gradV = a->gradV; P.rank_items = a->rank_items > 0 ? a->rank_items : a->n_items;
+  if (a->gradV) CF_CHECK_ARG(a->model != CF_MODEL_GBPR && a->update == CF_UPDATE_SYNC, "cf_train_steps: exchange mode (gradV) supports BPR/CML/WRMF in SYNC mode");
 
   int lpg = 32;
   step_kernel_t kern = pick_kernel(a->model, P.nvec, &lpg);
@@ -199,6 +226,7 @@ static int train_steps_impl(const cf_step_args* a, cudaStream_t stream, cudaEven
   if (grid > cap) grid = cap;
   step_kernel_t kapply = pick_apply(P.nvec);
   const long long R = (a->model == CF_MODEL_WRMF) ? 2 : 2 + W + G;
+  P.n_occ = (long long)a->B * R;
   long long agrid = ((long long)a->B * R + 255) / 256;   // every thread scans one slot code per iteration
   if (agrid > (long long)sms * 16) agrid = (long long)sms * 16;
   long long cgrid = ((long long)a->B * R + 255) / 256;
@@ -255,6 +283,36 @@ extern "C" int cf_train_steps_profiled(const cf_step_args* a, void* stream_, flo
   for (int k = 0; k < n; ++k) cudaEventDestroy(ev[k]);
   delete[] ev;
   return rc;
+}
+
+extern "C" int cf_apply_rows(const cf_apply_args* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CF_CHECK_ARG(a != nullptr, "cf_apply_rows: args is NULL");
+  CF_CHECK_ARG(a->table && a->rows && a->grads && a->meta && a->slot && a->slot_row && a->staging && a->counters, "cf_apply_rows: NULL pointer");
+  CF_CHECK_ARG(a->d > 0 && a->ld >= a->d && a->ld % 4 == 0 && a->ld <= 512 && a->ldg >= a->ld && a->ldg % 4 == 0, "cf_apply_rows: bad d/ld/ldg");
+  CF_CHECK_ARG(a->optimizer == CF_OPT_SGD || a->acc, "cf_apply_rows: Adagrad needs the accumulator table");
+  CF_CHECK_ARG(a->n >= 0 && a->staging_rows >= a->n, "cf_apply_rows: staging_rows %lld < n %lld", (long long)a->staging_rows, (long long)a->n);
+  if (a->n == 0) return 0;
+  StepDev P = {};
+  P.U = a->table; P.accU = a->acc; P.V = nullptr; P.accV = nullptr; P.b = nullptr; P.accb = nullptr;
+  P.n_users = a->n_rows; P.n_items = 0; P.d = a->d; P.ld = a->ld; P.nvec = a->ld / 4;
+  P.model = a->model; P.optimizer = a->optimizer; P.update = CF_UPDATE_SYNC;
+  P.lr = a->lr; P.clip = a->clip_norm;
+  P.metaU = a->meta; P.slotU = a->slot; P.slot_row = a->slot_row; P.staging = a->staging; P.staging_rows = a->staging_rows;
+  P.lds = a->ld + 4; P.counters = a->counters; P.n_occ = a->n;
+  static int sms = 0;
+  if (!sms) sms = cf_num_sms();
+  const int lpg = P.nvec <= 8 ? 8 : (P.nvec <= 16 ? 16 : 32);
+  long long cgrid = (a->n + 255) / 256, sgrid = (a->n + (256 / lpg) - 1) / (256 / lpg), agrid = (a->n + 255) / 256;
+  const long long cap = (long long)sms * 16;
+  if (cgrid > cap) cgrid = cap;
+  if (sgrid > cap) sgrid = cap;
+  if (agrid > cap) agrid = cap;
+  k_count_rows<<<(unsigned)cgrid, 256, 0, stream>>>(P, a->rows, a->n);
+  pick_scatter(P.nvec)<<<(unsigned)sgrid, 256, 0, stream>>>(P, a->rows, a->grads, a->n, a->ldg);
+  pick_apply(P.nvec)<<<(unsigned)agrid, 256, 0, stream>>>(P);
+  CF_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 extern "C" int cf_clip_rows(float* table, int64_t n_rows, int32_t d, int32_t ld, float clip_norm, void* stream_) {

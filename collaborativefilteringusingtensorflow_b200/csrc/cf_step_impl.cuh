@@ -39,6 +39,10 @@ struct StepDev {
   int lds;
   int32_t* counters;
   double* loss;
+  float* gradV;          // exchange mode (multi-GPU): V/n_items describe FETCHED item rows; item-row gradients are
+                         // red.added into gradV[row] (stride ld) instead of being applied here
+  long long rank_items;  // CML rank weight uses the GLOBAL item count
+  long long n_occ;       // slots scanned by k_apply_staged
 };
 
 template <int NV>
@@ -224,6 +228,7 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepDev P)
   const bool sync = P.update == CF_UPDATE_SYNC;
   const bool adagrad = P.optimizer == CF_OPT_ADAGRAD;
   const bool want_loss = P.loss != nullptr;
+  const bool item_ext = P.gradV != nullptr;
   const int nslot = 2 + P.T;
   float* sp = smem + (size_t)(threadIdx.x / LPG) * (2 * nslot) * P.ld;  // parameter rows of this group's slots
   float* sa = sp + (size_t)nslot * P.ld;                                // accumulator rows
@@ -289,7 +294,8 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepDev P)
         const bool is_user_tab = my_role == ROLE_USER || my_role == ROLE_GROUP;
         const bool stage_ui = first_tile && pass == first_pass;      // u / i parameter rows: once per pair
         const bool meta_ui = first_tile && commit_pass;              // u / i occurrence words + accumulators: once
-        if (sync && commit_pass && my_role != ROLE_NONE && (gl >= 2 || meta_ui))
+        const bool my_local = my_role != ROLE_NONE && (is_user_tab || !item_ext);   // rows this GPU owns and applies
+        if (sync && commit_pass && my_local && (gl >= 2 || meta_ui))
           occ_lo = __ldcg((is_user_tab ? P.metaU : P.metaV) + my_row);
         // ---- stage parameter rows (and the accumulators of rows this group will apply itself) into shared memory
         __syncwarp(gmask);   // the previous tile's shared-memory reads are done
@@ -304,11 +310,12 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepDev P)
             const unsigned occ = __shfl_sync(gmask, occ_lo, leader + s);
             const int r = __shfl_sync(gmask, my_row, leader + s);
             const int role = __shfl_sync(gmask, my_role, leader + s);
-            if (!sync || occ <= 1u)
-              stage_row<LPG, NV>(sa + (size_t)s * P.ld, (role == ROLE_USER || role == ROLE_GROUP) ? P.accU : P.accV, r, P.ld, P.nvec, gl);
+            const bool utab = role == ROLE_USER || role == ROLE_GROUP;
+            if ((utab || !item_ext) && (!sync || occ <= 1u))
+              stage_row<LPG, NV>(sa + (size_t)s * P.ld, utab ? P.accU : P.accV, r, P.ld, P.nvec, gl);
           }
         }
-        if (sync && commit_pass && my_role != ROLE_NONE && (gl >= 2 || last_tile) && occ_lo > 1u)
+        if (sync && commit_pass && my_local && (gl >= 2 || last_tile) && occ_lo > 1u)
           my_slot = __ldcg((is_user_tab ? P.slotU : P.slotV) + my_row);
         cp_async_wait_all();
         __syncwarp(gmask);
@@ -384,7 +391,7 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepDev P)
         if constexpr (MODEL == CF_MODEL_CML) {
           if (first_tile) {  // min / impostors are complete (pass 0 or single tile): hinge, rank weight (cml.py:73-85)
             const float h = (dp - dmin) + P.margin;
-            omega = P.use_rank_weight ? __logf(((float)imp / (float)P.W) * (float)P.n_items + 1.f) : 1.f;
+            omega = P.use_rank_weight ? __logf(((float)imp / (float)P.W) * (float)P.rank_items + 1.f) : 1.f;
             coef = h > 0.f ? 2.f * omega : 0.f;
             if (want_loss) lossv = fmaxf(h, 0.f) * omega;
           }
@@ -421,7 +428,14 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepDev P)
           }
           float* Tb = utab ? P.U : P.V;
           float* Ab = utab ? P.accU : P.accV;
-          if (!sync || occ <= 1u) {  // unique row (or racy mode): update straight from registers / shared memory
+          if (item_ext && !utab) {   // a fetched (remote) item row: its gradient goes back to the owner
+            float* gr = P.gradV + (long long)r * P.ld;
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+              const int v = gl + k * LPG;
+              if (v < P.nvec) atomicAdd(reinterpret_cast<float4*>(gr + 4 * v), g.v[k]);
+            }
+          } else if (!sync || occ <= 1u) {  // unique row (or racy mode): update straight from registers / shared memory
             Row<NV> acc = smem_row<LPG, NV>(sa + (size_t)s * P.ld, P.nvec, gl, 1.f), p;
             apply_math<LPG, NV>(P, cur, acc, g, p, gmask);
             if (adagrad) store_row<LPG, NV>(Ab, r, P.ld, P.nvec, gl, acc);
@@ -447,7 +461,7 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepDev P)
           }
         }
         // ---- unique rows are done: return their occurrence word to zero (duplicated rows: k_apply_staged does it)
-        if (sync && my_role != ROLE_NONE && (gl >= 2 || last_tile) && occ_lo <= 1u)
+        if (sync && my_local && (gl >= 2 || last_tile) && occ_lo <= 1u)
           __stcg((is_user_tab ? P.metaU : P.metaV) + my_row, 0u);
       }  // tiles
     }    // passes
@@ -474,8 +488,7 @@ __global__ void __launch_bounds__(256) k_apply_staged(const __grid_constant__ St
   const int lane = threadIdx.x & 31, gl = lane & (LPG - 1), leader = lane & ~(LPG - 1);
   const unsigned gmask = LPG == 32 ? 0xffffffffu : (((1u << LPG) - 1u) << leader);
   const long long ngroups = (long long)gridDim.x * blockDim.x / LPG;
-  const int R = (P.model == CF_MODEL_WRMF) ? 2 : 2 + P.W + P.G;
-  const long long n = (long long)P.B * R;     // one potential slot per row occurrence of the minibatch
+  const long long n = P.n_occ;                 // one potential slot per row occurrence of the minibatch
   const bool adagrad = P.optimizer == CF_OPT_ADAGRAD;
   // each group scans LPG consecutive slot codes at a time (one coalesced load) and walks the occupied ones together
   for (long long t0 = (((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPG) * LPG; t0 < n; t0 += ngroups * LPG) {
@@ -512,10 +525,46 @@ __global__ void __launch_bounds__(256) k_apply_staged(const __grid_constant__ St
   }
 }
 
+// Owner side of the multi-GPU exchange: n gradient rows (grads[k], stride ldg) for table rows rows[k] of THIS GPU's shard
+// (described as the "U" table of P).  A row received once is applied straight away; a row requested by several GPUs is
+// summed in its staging slot and applied by k_apply_staged -- the same "sum duplicates, apply once" rule.
+template <int LPG, int NV>
+__global__ void __launch_bounds__(256) k_scatter_rows(const __grid_constant__ StepDev P, const int32_t* __restrict__ rows,
+                                                      const float* __restrict__ grads, long long n, int ldg) {
+  const int lane = threadIdx.x & 31, gl = lane & (LPG - 1), leader = lane & ~(LPG - 1);
+  const unsigned gmask = LPG == 32 ? 0xffffffffu : (((1u << LPG) - 1u) << leader);
+  const long long ngroups = (long long)gridDim.x * blockDim.x / LPG;
+  const bool adagrad = P.optimizer == CF_OPT_ADAGRAD;
+  for (long long k = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPG; k < n; k += ngroups) {
+    const long long r = __ldg(rows + k);
+    if (!in_range(r, P.n_users)) continue;   // flagged by the counting kernel
+    const unsigned occ = __ldcg(P.metaU + r);
+    const Row<NV> g = load_row<LPG, NV>(grads, k, ldg, P.nvec, gl);
+    if (occ <= 1u) {
+      const Row<NV> cur = load_row<LPG, NV>(P.U, r, P.ld, P.nvec, gl);
+      Row<NV> acc, p;
+      if (adagrad) acc = load_row<LPG, NV>(P.accU, r, P.ld, P.nvec, gl, 1.f);
+      apply_math<LPG, NV>(P, cur, acc, g, p, gmask);
+      if (adagrad) store_row<LPG, NV>(P.accU, r, P.ld, P.nvec, gl, acc);
+      store_row<LPG, NV>(P.U, r, P.ld, P.nvec, gl, p);
+      if (gl == 0) __stcg(P.metaU + r, 0u);
+    } else {
+      float* st = P.staging + (long long)__ldcg(P.slotU + r) * P.lds;
+#pragma unroll
+      for (int q = 0; q < NV; ++q) {
+        const int v = gl + q * LPG;
+        if (v < P.nvec) atomicAdd(reinterpret_cast<float4*>(st + 4 * v), g.v[q]);
+      }
+    }
+  }
+}
+
 typedef void (*step_kernel_t)(const StepDev);
+typedef void (*scatter_kernel_t)(const StepDev, const int32_t*, const float*, long long, int);
 
 }  // namespace cfstep
 
 // one instantiation unit per (model, row shape): build.py generates build/gen/cf_step_inst_<m>_<s>.cu defining these
 #define CF_STEP_PICK_DECL(M, S) cfstep::step_kernel_t cf_step_pick_##M##_##S()
 #define CF_APPLY_PICK_DECL(S) cfstep::step_kernel_t cf_apply_pick_##S()
+#define CF_SCATTER_PICK_DECL(S) cfstep::scatter_kernel_t cf_scatter_pick_##S()

@@ -1,0 +1,225 @@
+"""Multi-GPU (one process per GPU, torch.distributed) sharding of the hot path -- SURVEY.md section 8(e).
+
+The reference is single-device (bprmf.py:131 uses DEVICES[0] only); this is new.
+
+Training: users are range-sharded with their CSR rows (sampling and the user-row update are local), the item table is
+row-sharded by ``item % P`` (local row ``item // P``).  Per minibatch every rank
+  1. samples B local pairs + negatives (global item ids),
+  2. dedupes the item ids it needs and asks their owners for the rows       (all_to_all: counts, ids, rows),
+  3. runs the fused step kernel in exchange mode: user rows are updated in place, item-row gradients are summed into a
+     compact buffer aligned with the fetched rows,
+  4. returns the gradient rows to the owners                                (all_to_all: rows),
+  5. owners sum what they received per row and apply it once (cf_apply_rows), i.e. exactly the single-GPU
+     minibatch-synchronous semantics with global batch P*B.
+Evaluation: every rank scores its item shard for all query users (their embeddings are all-gathered), keeps a local
+top-K, and the [T, K] lists are all-gathered and merged (cf_topk_merge).
+
+``ItemExchange`` is pure index bookkeeping + collectives on whatever device its tensors live on, so it is tested on CPU
+with the gloo backend (tests/test_dist_gloo.py); the kernels plug in at steps 3 and 5.
+"""
+import numpy as np
+
+from . import _lib
+
+
+class ExchangePlan(object):
+    __slots__ = ('n_req', 'occ_local', 'send_counts', 'recv_counts', 'recv_local_rows', 'req_global')
+
+
+class ItemExchange(object):
+    """Routes item-row requests between ranks. Owner of item i is ``i % world``; its local row is ``i // world``."""
+
+    def __init__(self, world, rank, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world, self.rank, self.group = int(world), int(rank), group
+
+    def _a2a(self, out, inp, out_split, in_split):
+        if self.world == 1:
+            out.copy_(inp)
+        else:
+            self.dist.all_to_all_single(out, inp, out_split, in_split, group=self.group)
+
+    def plan(self, item_ids):
+        """item_ids: int tensor (any shape) of GLOBAL item ids needed by this rank's minibatch."""
+        torch = self.torch
+        flat = item_ids.reshape(-1).to(torch.int64)
+        uniq, inv = torch.unique(flat, return_inverse=True)                 # sorted unique ids + occurrence -> unique
+        owner = uniq % self.world
+        order = torch.sort(owner, stable=True).indices                      # group the requests by owner
+        pos = torch.empty_like(order)
+        pos[order] = torch.arange(order.numel(), device=order.device)
+        send_counts = torch.bincount(owner, minlength=self.world)
+        recv_counts = torch.empty_like(send_counts)
+        self._a2a(recv_counts, send_counts, None, None)
+        sc, rc = send_counts.tolist(), recv_counts.tolist()
+        send_rows = (uniq[order] // self.world).to(torch.int32)             # local row ids at the owners
+        recv_rows = torch.empty(sum(rc), dtype=torch.int32, device=flat.device)
+        self._a2a(recv_rows, send_rows, rc, sc)
+        p = ExchangePlan()
+        p.n_req = int(uniq.numel())
+        p.occ_local = pos[inv].reshape(item_ids.shape).to(torch.int32)      # occurrence -> row of the fetched buffer
+        p.send_counts, p.recv_counts = sc, rc
+        p.recv_local_rows = recv_rows                                       # rows of MY shard that others (and I) asked for
+        p.req_global = uniq[order]
+        return p
+
+    def fetch(self, plan, table_shard):
+        """Returns the requested rows [n_req, ld], ordered like plan.occ_local indexes them."""
+        torch = self.torch
+        send = table_shard.index_select(0, plan.recv_local_rows.to(torch.int64))
+        out = torch.empty(plan.n_req, table_shard.shape[1], dtype=table_shard.dtype, device=table_shard.device)
+        self._a2a(out, send, plan.send_counts, plan.recv_counts)
+        return out
+
+    def push(self, plan, grad_rows):
+        """Sends one gradient row per fetched row back to its owner; returns [n_recv, ld] aligned with
+        plan.recv_local_rows (a row requested by several ranks appears once per requester)."""
+        torch = self.torch
+        out = torch.empty(int(plan.recv_local_rows.numel()), grad_rows.shape[1], dtype=grad_rows.dtype,
+                          device=grad_rows.device)
+        self._a2a(out, grad_rows.contiguous(), plan.recv_counts, plan.send_counts)
+        return out
+
+
+def item_shard_rows(n_items_global, world, rank):
+    return (int(n_items_global) - rank + world - 1) // world
+
+
+class DistributedTrainer(object):
+    """Row-sharded BPRMF / CML training over ``world`` GPUs.  ``model`` is a model object built with
+    n_users = this rank's users and n_items = this rank's item-shard rows; ``sampler`` samples this rank's CSR (columns =
+    GLOBAL item ids)."""
+
+    def __init__(self, model, sampler, n_items_global, world, rank, group=None):
+        self.torch = _lib.require_cuda()
+        self.lib = _lib.lib()
+        self.model, self.eng, self.sampler = model, model.engine, sampler
+        if self.eng.kind not in ('bpr', 'cml'):
+            raise ValueError('sharded training supports BPRMF and CML')
+        self.n_items_global = int(n_items_global)
+        self.world, self.rank = int(world), int(rank)
+        if self.eng.n_items != item_shard_rows(n_items_global, world, rank):
+            raise ValueError('model.n_items must be the item-shard size %d' % item_shard_rows(n_items_global, world, rank))
+        self.ex = ItemExchange(world, rank, group)
+        self._ows = None
+        self._ows_rows = 0
+        self.launches = 0
+        self.bytes_sent = 0
+        self.phase_ms = None          # set to {} to collect per-phase CUDA-event times (synchronises every phase)
+        if self.eng.kind == 'cml':   # one-time whole-table clip, then touched-row clips suffice
+            self.eng._full_clip(self.torch.cuda.current_stream(self.eng.device).cuda_stream)
+
+    def _owner_workspace(self, n):
+        torch, eng = self.torch, self.eng
+        if self._ows is None or self._ows_rows < n:
+            rows = int(n * 1.25) + 1024
+            self._ows = dict(meta=torch.zeros(eng.n_items, dtype=torch.int32, device=eng.device),
+                             slot=torch.zeros(eng.n_items, dtype=torch.int32, device=eng.device),
+                             slot_row=torch.full((rows,), -1, dtype=torch.int32, device=eng.device),
+                             staging=torch.zeros(rows, eng.ld + 4, device=eng.device))
+            self._ows_rows = rows
+        return self._ows
+
+    def _tick(self, name, ev0):
+        if self.phase_ms is None:
+            return None
+        torch = self.torch
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record()
+        ev1.synchronize()
+        if ev0 is not None:
+            self.phase_ms[name] = self.phase_ms.get(name, 0.0) + ev0.elapsed_time(ev1)
+        return ev1
+
+    def step_chunk(self, pairs, negs, batch_size, want_loss=True):
+        """One minibatch (rows == batch_size) of the sharded step on explicit local batches."""
+        torch, eng = self.torch, self.eng
+        B = int(batch_size)
+        ev = self._tick('', None)
+        if int(pairs.shape[0]) != B:
+            raise ValueError('the sharded step takes one minibatch per call')
+        items = torch.cat([pairs[:, 1:2].to(torch.int64), negs.to(torch.int64)], dim=1)       # [B, 1 + W] global ids
+        plan = self.ex.plan(items)
+        ev = self._tick('plan (unique + route ids)', ev)
+        Vbuf = self.ex.fetch(plan, eng.V)                                                    # [n_req, ld]
+        ev = self._tick('fetch rows (gather + all_to_all)', ev)
+        Gbuf = torch.zeros_like(Vbuf)
+        lp = torch.stack([pairs[:, 0].to(torch.int32), plan.occ_local[:, 0]], dim=1).contiguous()
+        ln = plan.occ_local[:, 1:].contiguous()
+        a = _lib.StepArgs()
+        a.U, a.V, a.accU, a.accV = _lib.ptr(eng.U), _lib.ptr(Vbuf), _lib.ptr(eng.accU), _lib.ptr(eng.accV)
+        a.n_users, a.n_items, a.d, a.ld = eng.n_users, plan.n_req, eng.d, eng.ld
+        a.pairs, a.negs = _lib.ptr(lp), _lib.ptr(ln)
+        a.B, a.W, a.G, a.n_batches = B, int(negs.shape[1]), 0, 1
+        a.model, a.optimizer, a.update = eng.model_id, 0 if eng.optimizer == 'adagrad' else 1, _lib.UPDATE_SYNC
+        h = eng.hyper
+        a.use_rank_weight = int(bool(h['use_rank_weight']))
+        a.lr, a.reg, a.margin, a.clip_norm, a.rho, a.weight = h['lr'], h['reg'], h['margin'], h['clip_norm'], h['rho'], h['weight']
+        ws = eng._workspace(B, int(negs.shape[1]), 0)
+        a.metaU, a.metaV = _lib.ptr(ws['metaU']), _lib.ptr(ws['metaV'])
+        a.slotU, a.slotV, a.slot_row = _lib.ptr(ws['slotU']), _lib.ptr(ws['slotV']), _lib.ptr(ws['slot_row'])
+        a.staging, a.staging_rows = _lib.ptr(ws['staging']), ws['staging'].shape[0]
+        a.counters = _lib.ptr(eng.counters)
+        loss = torch.zeros(1, dtype=torch.float64, device=eng.device) if want_loss else None
+        a.loss = _lib.ptr(loss)
+        a.gradV, a.rank_items = _lib.ptr(Gbuf), self.n_items_global
+        stream = torch.cuda.current_stream(eng.device).cuda_stream
+        ev = self._tick('prep (remap ids, zero grads)', ev)
+        _lib.check(self.lib.cf_train_steps(a, stream), 'cf_train_steps')
+        ev = self._tick('k_count + k_step + k_apply_staged', ev)
+        recv = self.ex.push(plan, Gbuf)
+        ev = self._tick('push grads (all_to_all)', ev)                                                      # [n_recv, ld]
+        n = int(recv.shape[0])
+        if n:
+            ows = self._owner_workspace(n)
+            ap = _lib.ApplyArgs()
+            ap.table, ap.acc, ap.n_rows, ap.d, ap.ld = _lib.ptr(eng.V), _lib.ptr(eng.accV), eng.n_items, eng.d, eng.ld
+            ap.rows, ap.grads, ap.n, ap.ldg = _lib.ptr(plan.recv_local_rows), _lib.ptr(recv), n, eng.ld
+            ap.model, ap.optimizer, ap.lr, ap.clip_norm = eng.model_id, a.optimizer, h['lr'], h['clip_norm']
+            ap.meta, ap.slot, ap.slot_row = _lib.ptr(ows['meta']), _lib.ptr(ows['slot']), _lib.ptr(ows['slot_row'])
+            ap.staging, ap.staging_rows, ap.counters = _lib.ptr(ows['staging']), ows['staging'].shape[0], _lib.ptr(eng.counters)
+            _lib.check(self.lib.cf_apply_rows(ap, stream), 'cf_apply_rows')
+        ev = self._tick('owner apply (cf_apply_rows)', ev)
+        self.launches += 3 + 3
+        self.bytes_sent += (plan.n_req + n) * eng.ld * 4 + plan.n_req * 4
+        return loss
+
+    def step(self, n_minibatches=1, want_loss=True):
+        """Sample + run n minibatches; returns their losses (CUDA float64)."""
+        torch = self.torch
+        B = self.sampler.batch_size
+        chunk = self.sampler.next_chunk(n_minibatches)
+        out = []
+        for k in range(n_minibatches):
+            out.append(self.step_chunk(chunk[0][k * B:(k + 1) * B], chunk[1][k * B:(k + 1) * B], B, want_loss))
+        return torch.cat(out) if want_loss else None
+
+
+def distributed_topk(engine, query_rows, K, train_local_csr, world, rank, group=None):
+    """query_rows: [T, ld] embeddings of the query users (already all-gathered / replicated on every rank).
+    engine.V is this rank's item shard (local row j = global item j * world + rank); train_local_csr masks in LOCAL item
+    ids (row t = query t).  Returns the merged global top-K ids [T, K] (int32) and scores on every rank."""
+    torch = _lib.require_cuda()
+    import torch.distributed as dist
+    lib = _lib.lib()
+    T = int(query_rows.shape[0])
+    saved_U, saved_n = engine.U, engine.n_users
+    engine.U, engine.n_users = query_rows.contiguous(), T
+    try:
+        idx, val = engine.topk(None, K, train_local_csr, return_values=True)
+    finally:
+        engine.U, engine.n_users = saved_U, saved_n
+    gidx = torch.where(idx >= 0, idx * world + rank, idx)
+    if world == 1:
+        return gidx, val
+    all_i = torch.empty(world, T, K, dtype=torch.int32, device=idx.device)
+    all_v = torch.empty(world, T, K, dtype=torch.float64, device=idx.device)
+    dist.all_gather_into_tensor(all_i, gidx.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_v, val.contiguous(), group=group)
+    out_i = torch.empty(T, K, dtype=torch.int32, device=idx.device)
+    out_v = torch.empty(T, K, dtype=torch.float64, device=idx.device)
+    _lib.check(lib.cf_topk_merge(all_i.data_ptr(), all_v.data_ptr(), world, T, K, out_i.data_ptr(), out_v.data_ptr(),
+                                 torch.cuda.current_stream(idx.device).cuda_stream), 'cf_topk_merge')
+    return out_i, out_v

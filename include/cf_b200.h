@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CF_ABI_VERSION 5
+#define CF_ABI_VERSION 6
 
 /* models */
 enum { CF_MODEL_BPR = 0, CF_MODEL_CML = 1, CF_MODEL_GBPR = 2, CF_MODEL_WRMF = 3 };
@@ -103,6 +103,11 @@ typedef struct cf_step_args {
   int64_t staging_rows;
   int32_t* counters;       /* [4]: {reserved, flags, reserved, reserved}, zero-initialised */
   double* loss;            /* [n_batches] summed minibatch loss, or NULL to skip the loss */
+  /* multi-GPU exchange mode (NULL / 0 on a single GPU): V, n_items then describe the FETCHED item rows of this
+   * minibatch (ids in pairs[:,1] / negs index into them), item rows are not applied locally; their summed gradients
+   * are red.added into gradV[n_items, ld] (zeroed by the caller) and travel back to the rows' owners (cf_apply_rows) */
+  float* gradV;
+  int64_t rank_items;      /* CML rank weight: global number of items (0 = n_items) */
 } cf_step_args;
 
 int cf_train_steps(const cf_step_args* args, void* stream);
@@ -114,6 +119,32 @@ int cf_train_steps_profiled(const cf_step_args* args, void* stream, float* ms_co
 int64_t cf_step_staging_rows(int32_t model, int32_t B, int32_t W, int32_t G);
 /* number of kernels cf_train_steps launches per minibatch (for gpu_launches accounting) */
 int32_t cf_step_launches_per_batch(void);
+
+/* Owner side of the multi-GPU exchange: apply n gradient rows (grads[k], stride ldg floats) to rows[k] of this GPU's
+ * table shard with the same rule as the fused step (rows received from several GPUs are summed, then applied once;
+ * model == CF_MODEL_CML also clips the updated row).  Replaces nothing in the reference (it is single-device). */
+typedef struct cf_apply_args {
+  float* table;            /* [n_rows, ld] */
+  float* acc;              /* Adagrad accumulators or NULL (SGD) */
+  int64_t n_rows;
+  int32_t d;
+  int32_t ld;
+  const int32_t* rows;     /* [n] local row ids */
+  const float* grads;      /* [n, ldg] */
+  int64_t n;
+  int32_t ldg;
+  int32_t model;
+  int32_t optimizer;
+  float lr;
+  float clip_norm;
+  uint32_t* meta;          /* [n_rows] zero */
+  int32_t* slot;           /* [n_rows] */
+  uint32_t* slot_row;      /* [staging_rows] all 0xffffffff */
+  float* staging;          /* [staging_rows, ld + 4] zero */
+  int64_t staging_rows;    /* >= n */
+  int32_t* counters;       /* [4] */
+} cf_apply_args;
+int cf_apply_rows(const cf_apply_args* args, void* stream);
 
 /* row <- row * c / max(||row||_2, c) over a whole table: cml.py:119-122 (used once, after the first step) */
 int cf_clip_rows(float* table, int64_t n_rows, int32_t d, int32_t ld, float clip_norm, void* stream);

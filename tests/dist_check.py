@@ -1,0 +1,108 @@
+#!/usr/bin/env python
+"""Multi-GPU parity script (run under torchrun on N GPUs of one box):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_check.py
+
+Sharded training (users range-sharded, items by item % P, all-to-all of rows and gradients) must equal ONE GPU running the
+same global minibatch (P * B pairs) with the plain fused step; sharded top-K + all-gather merge must equal single-GPU
+top-K.  Rank 0 prints 'DIST_CHECK OK'."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist.init_process_group('nccl', device_id=dev)
+    from collaborativefilteringusingtensorflow_b200 import BPRMF, CML
+    from collaborativefilteringusingtensorflow_b200.dist import DistributedTrainer, distributed_topk, item_shard_rows
+    from collaborativefilteringusingtensorflow_b200.sparse import DeviceCSR
+    from scipy.sparse import lil_matrix
+    ok = True
+    for kind in ('bpr', 'cml'):
+        nu_l, ni, d, B, W = 500, 1203, 128, 1024, 3
+        nu = nu_l * world
+        rng = np.random.default_rng(7)                                  # same stream on every rank
+        U0 = (0.05 * rng.standard_normal((nu, d))).astype(np.float32)   # row norms < clip: the sharded trainer clips at start
+        V0 = (0.05 * rng.standard_normal((ni, d))).astype(np.float32)
+        mk = (lambda n_u, n_i: BPRMF(n_u, n_i, n_factors=d, reg=0.05, verbose=False, seed=1, device=dev)) if kind == 'bpr' else \
+             (lambda n_u, n_i: CML(n_u, n_i, n_factors=d, reg_cov=1.0, margin=1.0, verbose=False, seed=1, device=dev))
+        local_m = mk(nu_l, item_shard_rows(ni, world, rank))
+        local_m.load_state_dict(dict(U=U0[rank * nu_l:(rank + 1) * nu_l], V=V0[rank::world]))
+
+        class NoSampler(object):
+            batch_size = B
+        tr = DistributedTrainer(local_m, NoSampler(), ni, world, rank)
+        ref = None
+        if rank == 0:
+            ref = mk(nu, ni)
+            ref.load_state_dict(dict(U=U0, V=V0))
+        for step in range(3):
+            pairs = np.stack([rng.integers(0, nu_l, (world, B)), rng.integers(0, ni, (world, B))], 2).astype(np.int32)
+            negs = rng.integers(0, ni, (world, B, W)).astype(np.int32)
+            tr.step_chunk(torch.from_numpy(pairs[rank]).to(dev), torch.from_numpy(negs[rank]).to(dev), B)
+            local_m.engine.check_flags()
+            if rank == 0:
+                gp = pairs.copy()
+                gp[:, :, 0] += (np.arange(world) * nu_l)[:, None]        # local -> global user ids
+                ref.step(gp.reshape(-1, 2), negs.reshape(-1, W))
+        # gather the shards on rank 0 and compare
+        st = local_m.state_dict()
+        Us = [torch.empty_like(st['U']) for _ in range(world)]
+        dist.all_gather(Us, st['U'].contiguous())
+        n_max = item_shard_rows(ni, world, 0)
+        Vpad = torch.zeros(n_max, d, device=dev)
+        Vpad[:st['V'].shape[0]] = st['V']
+        Vs = [torch.empty_like(Vpad) for _ in range(world)]
+        dist.all_gather(Vs, Vpad)
+        if rank == 0:
+            r = ref.state_dict()
+            Ug = torch.cat(Us).cpu().numpy()
+            Vg = np.zeros((ni, d), np.float32)
+            for p in range(world):
+                Vg[p::world] = Vs[p][:item_shard_rows(ni, world, p)].cpu().numpy()
+            for name, got, want in (('U', Ug, r['U'].cpu().numpy()), ('V', Vg, r['V'].cpu().numpy())):
+                err = np.abs(got - want).max()
+                good = np.allclose(got, want, rtol=5e-5, atol=2e-6 if kind == 'bpr' else 1e-5)   # CML: fp32 sums regrouped per rank
+                print('%s %s max|diff| = %.3g %s' % (kind, name, err, 'ok' if good else 'MISMATCH'))
+                ok &= bool(good)
+        # ---- evaluation: item-sharded top-K + all-gather merge vs single GPU
+        T, K = 64, 100
+        users = np.arange(T)
+        tra = lil_matrix((T, ni), dtype=np.float32)
+        for t in range(T):
+            tra[t, rng.choice(ni, 30, replace=False)] = 1
+        # query embeddings live on their owner rank: all-gather the tile (here: users of rank 0's shard, replicated)
+        q = local_m.engine.U[:T].clone() if rank == 0 else torch.empty(T, local_m.engine.ld, device=dev)
+        dist.broadcast(q, 0)
+        local_mask = lil_matrix((T, item_shard_rows(ni, world, rank)), dtype=np.float32)
+        for t in range(T):
+            cols = [c // world for c in tra.rows[t] if c % world == rank]
+            if cols:
+                local_mask[t, cols] = 1
+        gi, gv = distributed_topk(local_m.engine, q, K, DeviceCSR.from_scipy(local_mask, dev), world, rank)
+        if rank == 0:
+            # reference: a single engine holding the gathered tables
+            full = mk(nu_l, ni)
+            full.load_state_dict(dict(U=local_m.state_dict()['U'], V=torch.from_numpy(Vg)))
+            wi, wv = full.engine.topk(torch.arange(T), K, DeviceCSR.from_scipy(tra, dev), return_values=True)
+            same = bool(torch.equal(wi, gi) and torch.equal(wv, gv))
+            print('%s sharded top-%d == single GPU: %s' % (kind, K, same))
+            ok &= same
+    if rank == 0:
+        print('DIST_CHECK OK' if ok else 'DIST_CHECK FAILED')
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0 and not ok:
+        sys.exit(1)
+
+
+if __name__ == '__main__':
+    main()
