@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libcf_b200.so')
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 # enums of cf_b200.h
 MODEL_BPR, MODEL_CML, MODEL_GBPR, MODEL_WRMF = 0, 1, 2, 3
@@ -80,6 +80,8 @@ _SIGNATURES = {
     'cf_sample_ranking': (C.c_int, [C.POINTER(SampleArgs), _p]),
     'cf_sample_rating': (C.c_int, [C.POINTER(SampleArgs), _p]),
     'cf_topk_exact': (C.c_int, [C.POINTER(TopkArgs), _p]),
+    'cf_topk_tc_workspace_bytes': (C.c_int64, [C.POINTER(TopkArgs)]),
+    'cf_topk_tc': (C.c_int, [C.POINTER(TopkArgs), _p, C.c_int64, _p, _p]),
     'cf_scores': (C.c_int, [C.POINTER(TopkArgs), _p, _p]),
     'cf_topk_merge': (C.c_int, [_p, _p, C.c_int32, C.c_int32, C.c_int32, _p, _p, _p]),
     'cf_rank_metrics': (C.c_int, [_p, C.c_int32, C.c_int32, C.c_int32, _p, _p, _p, _p]),

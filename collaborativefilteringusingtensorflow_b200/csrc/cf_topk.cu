@@ -55,6 +55,7 @@ struct TopkDev {
   int32_t* out_idx;
   double* out_val;
   long long item_lo, item_hi;
+  const int32_t* only_if_flag;   // when set, only query rows t with only_if_flag[t] != 0 are computed
 };
 
 
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(TK_THREADS) k_topk_exact(const __grid_constant
   __shared__ int s_thi;
 
   for (int t = blockIdx.x; t < P.T; t += gridDim.x) {
+    if (P.only_if_flag && !P.only_if_flag[t]) continue;   // block-uniform
     const long long u = P.users ? P.users[t] : t;
     for (int k = threadIdx.x; k < P.ld; k += blockDim.x) s_u[k] = P.U[u * P.ld + k];
     if (threadIdx.x == 0) {
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(128) k_rank_metrics(const int32_t* __restrict_
 
 }  // namespace
 
-extern "C" int cf_topk_exact(const cf_topk_args* a, void* stream_) {
+int cf_topk_exact_flagged(const cf_topk_args* a, const int32_t* only_if_flag, cudaStream_t stream) {
   CF_CHECK_ARG(a != nullptr, "cf_topk_exact: args is NULL");
   CF_CHECK_ARG(a->U && a->V && a->out_idx, "cf_topk_exact: U, V and out_idx are required");
   CF_CHECK_ARG(a->d > 0 && a->ld >= a->d && a->ld % 4 == 0 && a->ld <= 512, "cf_topk_exact: need 0 < d <= ld <= 512, ld %% 4 == 0");
@@ -276,15 +278,19 @@ extern "C" int cf_topk_exact(const cf_topk_args* a, void* stream_) {
   P.users = a->users; P.T = a->T; P.K = a->K; P.kind = a->kind;
   P.tr_indptr = (const long long*)a->train.indptr; P.tr_indices = a->train.indices;
   P.out_idx = a->out_idx; P.out_val = a->out_val;
-  P.item_lo = a->item_lo; P.item_hi = a->item_hi;
+  P.item_lo = a->item_lo; P.item_hi = a->item_hi; P.only_if_flag = only_if_flag;
   if (P.item_lo == 0 && P.item_hi == 0) P.item_hi = a->n_items;
   CF_CHECK_ARG(P.item_lo >= 0 && P.item_hi <= a->n_items && P.item_lo <= P.item_hi, "cf_topk_exact: bad item range");
   int grid = a->T;
   const int cap = cf_num_sms() * 4;
   if (grid > cap) grid = cap;
-  k_topk_exact<<<grid, TK_THREADS, 0, (cudaStream_t)stream_>>>(P);
+  k_topk_exact<<<grid, TK_THREADS, 0, stream>>>(P);
   CF_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+extern "C" int cf_topk_exact(const cf_topk_args* a, void* stream_) {
+  return cf_topk_exact_flagged(a, nullptr, (cudaStream_t)stream_);
 }
 
 extern "C" int cf_scores(const cf_topk_args* a, double* out_scores, void* stream_) {
@@ -298,7 +304,7 @@ extern "C" int cf_scores(const cf_topk_args* a, double* out_scores, void* stream
   P.U = a->U; P.V = a->V; P.b = a->b; P.n_items = a->n_items; P.ld = a->ld; P.nvec = a->ld / 4;
   P.users = a->users; P.T = a->T; P.K = 0; P.kind = a->kind;
   P.tr_indptr = nullptr; P.tr_indices = nullptr; P.out_idx = nullptr; P.out_val = nullptr;
-  P.item_lo = 0; P.item_hi = a->n_items;
+  P.item_lo = 0; P.item_hi = a->n_items; P.only_if_flag = nullptr;
   int grid = a->T;
   const int cap = cf_num_sms() * 4;
   if (grid > cap) grid = cap;

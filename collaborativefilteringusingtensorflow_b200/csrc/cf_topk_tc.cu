@@ -1,0 +1,671 @@
+// Tensor-core full-catalog top-K for sm_100a: tcgen05.mma (bf16 -> fp32 in TMEM) fed by TMA, with an epilogue that keeps a
+// per-row candidate superset instead of writing scores, followed by an exact fp64 re-rank of the candidates.
+//
+// Replaces `sess.run(tf.nn.top_k(matmul(U[test_users], V^T) (+b | cml distance), K'))` + the Python filter loop
+// (reference src/models/pl/models/bprmf.py:77-103, cml.py:111-144, gbprmf.py:95-121, basic/models/wrmf.py:77-111).
+//
+// Stage 0 (k_prep_items / k_prep_queries): fp32 tables -> bf16 operand matrices with K padded to a multiple of 64.  The
+//   three scoring kinds all become plain dot products a'.b':   DOT       a' = u            b' = v
+//                                                               DOT_BIAS  a' = [u, 1, 1]    b' = [v, hi(b_i), lo(b_i)]
+//                                                               NEG_SQDIST a' = [2u, 1, 1]  b' = [v, hi(-|v|^2), lo(-|v|^2)]
+//   (per-user constants such as -|u|^2 do not change a user's ranking).  eps_row = 2^-7.9 |a'| max_i|b'_i| bounds the bf16
+//   rounding + fp32 accumulation error of every score of the row.
+// Stage 1 (k_topk_tc): one CTA per (256 query rows, item split): A = 2 x (128 x Kp) resident in smem, B tiles of 128 items
+//   streamed by TMA through a ring, 2 x tcgen05.mma (M=128, N=128) per k-step into a double-buffered TMEM accumulator,
+//   8 epilogue warps (one thread per row) read the accumulators with tcgen05.ld and append (score, item) to the row's
+//   candidate buffer iff score >= theta_row - 2 eps_row, where theta_row is the running K-th best approximate score of
+//   unmasked items.  Any item of the exact top-K satisfies that test (proof in DESIGN.md), so the buffer is a superset.
+//   Training items are masked by a binary search of the user's CSR row -- only for the rare candidates.  A full buffer is
+//   compacted warp-cooperatively (radix select of the K-th key, drop everything below theta - 2 eps).
+// Stage 2 (k_rerank): exact scores (fp32 inputs, fp64 sequential-k accumulation, identical to cf_topk_exact) of the
+//   candidates, bitonic sort by (score desc, id asc), top K.  Rows whose buffer overflowed (degenerate score
+//   distributions) are recomputed by the exact streaming kernel.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TC_M = 128;        // rows per MMA
+constexpr int TC_MT = 2;         // M tiles per CTA (256 query rows)
+constexpr int TC_N = 128;        // items per B tile
+constexpr int TC_KCH = 64;       // bf16 elements per 128-byte swizzle chunk
+constexpr int TC_CHUNK_BYTES = TC_M * TC_KCH * 2;   // 16 KB: one TMA box {64, 128}
+constexpr int TC_CAP = 256;      // candidate buffer entries per (row, split)
+constexpr int TC_KMAX = 112;     // largest K served by the tensor path (CAP - 32 >= 2K)
+constexpr int TC_THREADS = 384;  // warp 0: TMA, 1: MMA, 2: TMEM alloc, 3: idle, 4..11: epilogue
+constexpr int TC_MAX_STAGES = 6;
+
+struct TcParams {
+  int T, N, KC, n_tiles, S, stages, K;
+  const int32_t* users;            // [T] user id of every query row (for the training-row mask), or NULL = row index
+  const long long* tr_indptr;      // training CSR (NULL = no mask)
+  const int32_t* tr_indices;
+  const float* eps2;               // [T_pad] 2 * eps_row
+  float* cand_val;                 // [T_pad, S, CAP]
+  int32_t* cand_idx;
+  int32_t* cand_cnt;               // [T_pad, S]
+  int32_t* overflow;               // [T_pad]
+  float* dbg_scores;               // optional [T_pad, dbg_ld] dump of the raw accumulators
+  long long dbg_ld;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(dst)),
+               "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
+      "%25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format: version 1, layout type 2, SBO = 1024 B)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                               // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                               // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M x N
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ unsigned ord_key(float f) {  // monotone float -> uint map
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord_unkey(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+
+// Warp-cooperative compaction of ONE row's candidate buffer (n entries): theta <- K-th largest value, keep >= theta - eps2.
+__device__ __forceinline__ void compact_row(float* cv, int32_t* ci, int n, int K, float eps2, int lane, float& theta_out,
+                                            int& cnt_out) {
+  constexpr int EPL = TC_CAP / 32;
+  float v[EPL];
+  int32_t id[EPL];
+  unsigned key[EPL];
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) {
+    const int e = lane + 32 * i;
+    v[i] = e < n ? __ldcg(cv + e) : -INFINITY;
+    id[i] = e < n ? __ldcg(ci + e) : -1;
+    key[i] = e < n ? ord_key(v[i]) : 0u;
+  }
+  unsigned prefix = 0u;
+  for (int bit = 31; bit >= 0; --bit) {
+    const unsigned cand = prefix | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) c += key[i] >= cand;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (c >= K) prefix = cand;
+  }
+  const float theta = ord_unkey(prefix);
+  const float cut = theta - eps2;
+  int pos = 0;
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) {
+    const bool keep = (lane + 32 * i < n) && v[i] >= cut;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const int p = pos + __popc(m & ((1u << lane) - 1u));
+      cv[p] = v[i];
+      ci[p] = id[i];
+    }
+    pos += __popc(m);
+  }
+  __syncwarp();
+  theta_out = theta;
+  cnt_out = pos;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmV, const __grid_constant__ TcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KC = P.KC;
+  const int a_bytes = TC_MT * KC * TC_CHUNK_BYTES, b_stage_bytes = KC * TC_CHUNK_BYTES;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)P.stages * b_stage_bytes);
+  uint64_t* full = bars;                       // [stages]
+  uint64_t* empty = bars + TC_MAX_STAGES;      // [stages]
+  uint64_t* a_full = bars + 2 * TC_MAX_STAGES;
+  uint64_t* tfull = a_full + 1;                // [2]
+  uint64_t* tempty = tfull + 2;                // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int row0 = blockIdx.x * (TC_MT * TC_M);
+  const int split = blockIdx.y;
+  const int tiles_per_split = (P.n_tiles + P.S - 1) / P.S;
+  const int tile_lo = split * tiles_per_split;
+  const int tile_hi = min(P.n_tiles, tile_lo + tiles_per_split);
+  const int nt = max(0, tile_hi - tile_lo);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P.stages; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(a_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull + s, 1);
+      mbar_init(tempty + s, 8 * 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================== TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(a_full, (uint32_t)a_bytes);
+      for (int mt = 0; mt < TC_MT; ++mt)
+        for (int kc = 0; kc < KC; ++kc)
+          tma_load_2d(&tmQ, a_full, sA + (size_t)(mt * KC + kc) * TC_CHUNK_BYTES, kc * TC_KCH, row0 + mt * TC_M);
+      for (int t = 0; t < nt; ++t) {
+        const int st = t % P.stages;
+        const uint32_t ph = (uint32_t)(t / P.stages) & 1u;
+        mbar_wait(empty + st, ph ^ 1u);
+        mbar_arrive_expect_tx(full + st, (uint32_t)b_stage_bytes);
+        for (int kc = 0; kc < KC; ++kc)
+          tma_load_2d(&tmV, full + st, sB + (size_t)st * b_stage_bytes + (size_t)kc * TC_CHUNK_BYTES, kc * TC_KCH,
+                      (tile_lo + t) * TC_N);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(TC_M, TC_N);
+      mbar_wait(a_full, 0u);
+      for (int t = 0; t < nt; ++t) {
+        const int st = t % P.stages;
+        const uint32_t ph = (uint32_t)(t / P.stages) & 1u;
+        const int acc = t & 1;
+        mbar_wait(tempty + acc, ((uint32_t)(t >> 1) & 1u) ^ 1u);
+        mbar_wait(full + st, ph);
+        tc_fence_after();
+        for (int mt = 0; mt < TC_MT; ++mt) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * (TC_MT * TC_N) + mt * TC_N);
+          for (int kc = 0; kc < KC; ++kc) {
+            const uint32_t a_addr = smem_u32(sA + (size_t)(mt * KC + kc) * TC_CHUNK_BYTES);
+            const uint32_t b_addr = smem_u32(sB + (size_t)st * b_stage_bytes + (size_t)kc * TC_CHUNK_BYTES);
+#pragma unroll
+            for (int k = 0; k < TC_KCH / 16; ++k)   // UMMA_K = 16 bf16 = 32 bytes inside the 128-byte swizzle atom
+              tc_mma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (kc | k) ? 1u : 0u);
+          }
+        }
+        tc_commit(empty + st);     // smem stage free once these MMAs have read it
+        tc_commit(tfull + acc);    // accumulator ready for the epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================================== epilogue: one thread per query row
+    const int ew = warp - 4;
+    const int mt = ew >> 2, q = warp & 3;
+    const int row = row0 + mt * TC_M + q * 32 + lane;
+    const bool valid = row < P.T;
+    float theta = valid ? -INFINITY : INFINITY;
+    int cnt = 0;
+    const float eps2 = valid ? P.eps2[row] : 0.f;
+    long long tlo = 0, thi = 0;
+    if (valid && P.tr_indptr) {
+      const long long u = P.users ? P.users[row] : row;
+      tlo = P.tr_indptr[u];
+      thi = P.tr_indptr[u + 1];
+    }
+    float* cv = P.cand_val + ((long long)row * P.S + split) * TC_CAP;
+    int32_t* ci = P.cand_idx + ((long long)row * P.S + split) * TC_CAP;
+    bool overflowed = false;
+
+    for (int t = 0; t < nt; ++t) {
+      const int acc = t & 1;
+      mbar_wait(tfull + acc, (uint32_t)(t >> 1) & 1u);
+      tc_fence_after();
+      const int n0 = (tile_lo + t) * TC_N;
+#pragma unroll 1
+      for (int c = 0; c < TC_N / 32; ++c) {
+        uint32_t r[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * (TC_MT * TC_N) + mt * TC_N + c * 32), r);
+        tc_wait_ld();
+        if (P.dbg_scores && valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) P.dbg_scores[(long long)row * P.dbg_ld + n0 + c * 32 + j] = __uint_as_float(r[j]);
+        }
+        // make room: a chunk can append at most 32 entries
+        unsigned need = __ballot_sync(0xffffffffu, cnt > TC_CAP - 32);
+        while (need) {
+          const int l = __ffs(need) - 1;
+          need &= need - 1;
+          float* rcv = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(cv), l));
+          int32_t* rci = reinterpret_cast<int32_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(ci), l));
+          const int rn = __shfl_sync(0xffffffffu, cnt, l);
+          const float re = __shfl_sync(0xffffffffu, eps2, l);
+          float nth;
+          int ncnt;
+          compact_row(rcv, rci, rn, P.K, re, lane, nth, ncnt);
+          if (lane == l) {
+            theta = nth;
+            cnt = ncnt;
+            if (ncnt > TC_CAP - 32) {  // too many items within 2 eps of the K-th best: give this row to the exact kernel
+              overflowed = true;
+              theta = INFINITY;
+              cnt = 0;
+            }
+          }
+        }
+        const float thr = theta - eps2;
+        float m = __uint_as_float(r[0]);
+#pragma unroll
+        for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
+        if (m >= thr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float s = __uint_as_float(r[j]);
+            if (s >= thr) {
+              const int item = n0 + c * 32 + j;
+              if (item < P.N && !csr_contains(P.tr_indices, tlo, thi, item)) {
+                cv[cnt] = s;
+                ci[cnt] = item;
+                ++cnt;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty + acc);
+    }
+    if (valid) {
+      P.cand_cnt[(long long)row * P.S + split] = cnt;
+      if (overflowed) P.overflow[row] = 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ stage 0: operands
+struct PrepParams {
+  const float* src;      // fp32 table [rows, ld]
+  const float* bias;     // item bias (DOT_BIAS) or NULL
+  const int32_t* ids;    // optional row gather (query users)
+  long long n_valid, n_pad;
+  int d, ld, Kp, kind, is_query;
+  __nv_bfloat16* dst;    // [n_pad, Kp]
+  float* bmax;           // items: atomicMax of |b'|; queries: read
+  float* eps2;           // queries: [n_pad]
+};
+
+__global__ void __launch_bounds__(256) k_prep(const __grid_constant__ PrepParams P) {
+  const int lane = threadIdx.x & 31;
+  const long long nw = (long long)gridDim.x * blockDim.x / 32;
+  for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 32; r < P.n_pad; r += nw) {
+    __nv_bfloat16* out = P.dst + r * P.Kp;
+    float nrm2 = 0.f;
+    const bool valid = r < P.n_valid;
+    const long long src_row = valid ? (P.ids ? (long long)P.ids[r] : r) : 0;
+    const float scale = (P.is_query && P.kind == CF_SCORE_NEG_SQDIST) ? 2.f : 1.f;
+    float vsq = 0.f;
+    for (int k = lane; k < P.Kp; k += 32) {
+      float x = 0.f;
+      if (valid && k < P.d) {
+        x = P.src[src_row * P.ld + k];
+        vsq += x * x;
+        x *= scale;
+      }
+      if (k < P.d) {
+        out[k] = __float2bfloat16_rn(x);
+        nrm2 += x * x;
+      } else if (k >= P.d + 2 || P.kind == CF_SCORE_DOT) {
+        out[k] = __float2bfloat16_rn(0.f);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      nrm2 += __shfl_xor_sync(0xffffffffu, nrm2, o);
+      vsq += __shfl_xor_sync(0xffffffffu, vsq, o);
+    }
+    if (P.kind != CF_SCORE_DOT && lane == 0) {   // the two augmentation columns
+      float c_hi = 0.f, c_lo = 0.f;
+      if (valid) {
+        if (P.is_query) {
+          c_hi = 1.f;
+          c_lo = 1.f;
+        } else {
+          const float c = P.kind == CF_SCORE_DOT_BIAS ? P.bias[src_row] : -vsq;
+          c_hi = __bfloat162float(__float2bfloat16_rn(c));
+          c_lo = c - c_hi;
+          nrm2 += c * c;
+        }
+      }
+      if (P.is_query && valid) nrm2 += 2.f;
+      out[P.d] = __float2bfloat16_rn(c_hi);
+      out[P.d + 1] = __float2bfloat16_rn(c_lo);
+    }
+    if (lane == 0) {
+      const float nrm = sqrtf(nrm2);
+      if (!P.is_query) {
+        if (valid) atomicMax(reinterpret_cast<int*>(P.bmax), __float_as_int(nrm));   // non-negative floats order like ints
+      } else {
+        // |a'.b' - bf16(a').bf16(b')| <= (2^-8 + 2^-18) |a'||b'| ; + fp32 accumulation slack
+        P.eps2[r] = valid ? 2.f * (0.00395f * nrm * (*P.bmax) * 1.02f + 1e-6f) : 0.f;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ stage 2: exact re-rank
+constexpr int RR_CAP = 2048;
+
+struct RerankParams {
+  const float *U, *V, *b;
+  int ld, nvec, kind, T, S, K;
+  const int32_t* users;
+  const float* cand_val;
+  const int32_t* cand_idx;
+  const int32_t* cand_cnt;
+  const int32_t* overflow;
+  int32_t* out_idx;
+  double* out_val;
+};
+
+__device__ __forceinline__ bool rr_before(double va, int ia, double vb, int ib) { return va > vb || (va == vb && ia < ib); }
+
+__global__ void __launch_bounds__(256) k_rerank(const __grid_constant__ RerankParams P) {
+  __shared__ double s_val[RR_CAP];
+  __shared__ int s_idx[RR_CAP];
+  __shared__ __align__(16) float s_u[512];
+  for (int t = blockIdx.x; t < P.T; t += gridDim.x) {
+    if (P.overflow[t]) continue;   // recomputed by the exact streaming kernel
+    const long long u = P.users ? P.users[t] : t;
+    for (int k = threadIdx.x; k < P.ld; k += blockDim.x) s_u[k] = P.U[u * P.ld + k];
+    int total = 0;
+    for (int s = 0; s < P.S; ++s) total += P.cand_cnt[(long long)t * P.S + s];
+    int n2 = 32;
+    while (n2 < total) n2 <<= 1;
+    __syncthreads();
+    // gather + exact score
+    int base = 0;
+    for (int s = 0; s < P.S; ++s) {
+      const int c = P.cand_cnt[(long long)t * P.S + s];
+      const int32_t* ci = P.cand_idx + ((long long)t * P.S + s) * TC_CAP;
+      for (int e = threadIdx.x; e < c; e += blockDim.x) {
+        const long long item = ci[e];
+        const float4* vp = reinterpret_cast<const float4*>(P.V + item * P.ld);
+        double sc = 0.0;
+        if (P.kind == CF_SCORE_NEG_SQDIST) {
+          for (int k4 = 0; k4 < P.nvec; ++k4) {
+            const float4 v = __ldg(vp + k4);
+            const float4 qv = *reinterpret_cast<const float4*>(s_u + 4 * k4);
+            double df = (double)qv.x - (double)v.x; sc = __dadd_rn(sc, __dmul_rn(df, df));
+            df = (double)qv.y - (double)v.y; sc = __dadd_rn(sc, __dmul_rn(df, df));
+            df = (double)qv.z - (double)v.z; sc = __dadd_rn(sc, __dmul_rn(df, df));
+            df = (double)qv.w - (double)v.w; sc = __dadd_rn(sc, __dmul_rn(df, df));
+          }
+          sc = -sc;
+        } else {
+          for (int k4 = 0; k4 < P.nvec; ++k4) {
+            const float4 v = __ldg(vp + k4);
+            const float4 qv = *reinterpret_cast<const float4*>(s_u + 4 * k4);
+            sc = fma((double)qv.x, (double)v.x, sc);
+            sc = fma((double)qv.y, (double)v.y, sc);
+            sc = fma((double)qv.z, (double)v.z, sc);
+            sc = fma((double)qv.w, (double)v.w, sc);
+          }
+          if (P.kind == CF_SCORE_DOT_BIAS) sc = __dadd_rn(sc, (double)__ldg(P.b + item));
+        }
+        s_val[base + e] = sc;
+        s_idx[base + e] = (int)item;
+      }
+      base += c;
+    }
+    for (int e = total + threadIdx.x; e < n2; e += blockDim.x) {
+      s_val[e] = -INFINITY;
+      s_idx[e] = 0x7fffffff;
+    }
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int x = threadIdx.x; x < n2; x += blockDim.x) {
+          const int p = x ^ j;
+          if (p > x) {
+            const bool up = (x & k) == 0;
+            const double va = s_val[x], vb = s_val[p];
+            const int ia = s_idx[x], ib = s_idx[p];
+            const bool sw = up ? rr_before(vb, ib, va, ia) : rr_before(va, ia, vb, ib);
+            if (sw) { s_val[x] = vb; s_idx[x] = ib; s_val[p] = va; s_idx[p] = ia; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    for (int k = threadIdx.x; k < P.K; k += blockDim.x) {
+      const bool ok = k < total;
+      P.out_idx[(long long)t * P.K + k] = ok ? s_idx[k] : -1;
+      if (P.out_val) P.out_val[(long long)t * P.K + k] = ok ? s_val[k] : -INFINITY;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*encode_tiled_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+encode_tiled_t get_encode() {
+  static encode_tiled_t fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<encode_tiled_t>(p);
+  }
+  return fn;
+}
+
+int make_map(CUtensorMap* tm, void* base, long long rows, int Kp) {
+  encode_tiled_t enc = get_encode();
+  CF_CHECK_ARG(enc != nullptr, "cf_topk_tc: cuTensorMapEncodeTiled is not available from the driver");
+  const cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
+  const cuuint32_t box[2] = {TC_KCH, TC_M};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CF_CHECK_ARG(r == CUDA_SUCCESS, "cf_topk_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+struct TcPlan {
+  int Kp, KC, S, stages;
+  long long T_pad, N_pad;
+  size_t off_vb, off_qb, off_eps, off_cval, off_cidx, off_ccnt, off_ovf, off_bmax, total;
+  size_t smem;
+};
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int plan_tc(const cf_topk_args* a, TcPlan* p) {
+  const int aug = a->kind == CF_SCORE_DOT ? 0 : 2;
+  p->Kp = (int)align_up((size_t)a->d + aug, TC_KCH);
+  p->KC = p->Kp / TC_KCH;
+  CF_CHECK_ARG(p->KC >= 1 && p->KC <= 4, "cf_topk_tc: n_factors up to 254 are served by the tensor path (d=%d)", a->d);
+  p->T_pad = (long long)align_up((size_t)a->T, TC_MT * TC_M);
+  p->N_pad = (long long)align_up((size_t)a->n_items, TC_N);
+  const long long row_tiles = p->T_pad / (TC_MT * TC_M), n_tiles = p->N_pad / TC_N;
+  int S = (int)((2ll * cf_num_sms() + row_tiles - 1) / row_tiles);   // aim for >= 2 CTAs per SM's worth of work
+  if (S < 1) S = 1;
+  if (S > 8) S = 8;
+  if (S > n_tiles) S = (int)n_tiles;
+  p->S = S;
+  const size_t a_bytes = (size_t)TC_MT * p->KC * TC_CHUNK_BYTES, b_bytes = (size_t)p->KC * TC_CHUNK_BYTES;
+  int stages = (int)((200 * 1024 - a_bytes) / b_bytes);
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  CF_CHECK_ARG(stages >= 2, "cf_topk_tc: not enough shared memory for a 2-stage ring");
+  p->stages = stages;
+  p->smem = a_bytes + stages * b_bytes + 256 + 1024;
+  size_t off = 0;
+  p->off_vb = off; off = align_up(off + (size_t)p->N_pad * p->Kp * 2, 1024);
+  p->off_qb = off; off = align_up(off + (size_t)p->T_pad * p->Kp * 2, 1024);
+  p->off_eps = off; off = align_up(off + (size_t)p->T_pad * 4, 256);
+  p->off_cval = off; off = align_up(off + (size_t)p->T_pad * S * TC_CAP * 4, 256);
+  p->off_cidx = off; off = align_up(off + (size_t)p->T_pad * S * TC_CAP * 4, 256);
+  p->off_ccnt = off; off = align_up(off + (size_t)p->T_pad * S * 4, 256);
+  p->off_ovf = off; off = align_up(off + (size_t)p->T_pad * 4, 256);
+  p->off_bmax = off; off = align_up(off + 256, 256);
+  p->total = off;
+  return 0;
+}
+
+int validate_tc(const cf_topk_args* a, const char* who) {
+  CF_CHECK_ARG(a != nullptr, "%s: args is NULL", who);
+  CF_CHECK_ARG(a->d > 0 && a->ld >= a->d && a->ld % 4 == 0 && a->ld <= 512, "%s: need 0 < d <= ld <= 512, ld %% 4 == 0", who);
+  CF_CHECK_ARG(a->T > 0 && a->n_items > 0 && a->n_items < (1ll << 31), "%s: T and n_items must be positive", who);
+  CF_CHECK_ARG(a->K > 0 && a->K <= TC_KMAX, "%s: K must be in [1, %d] for the tensor path (got %d)", who, TC_KMAX, a->K);
+  CF_CHECK_ARG(a->kind >= CF_SCORE_DOT && a->kind <= CF_SCORE_NEG_SQDIST, "%s: unknown scoring kind %d", who, a->kind);
+  CF_CHECK_ARG(a->item_lo == 0 && (a->item_hi == 0 || a->item_hi == a->n_items), "%s: item ranges are not supported here (shard V instead)", who);
+  return 0;
+}
+
+}  // namespace
+
+int cf_topk_exact_flagged(const cf_topk_args* a, const int32_t* only_if_flag, cudaStream_t stream);
+
+extern "C" int64_t cf_topk_tc_workspace_bytes(const cf_topk_args* a) {
+  if (validate_tc(a, "cf_topk_tc_workspace_bytes")) return -1;
+  TcPlan p;
+  if (plan_tc(a, &p)) return -1;
+  return (int64_t)p.total;
+}
+
+extern "C" int cf_topk_tc(const cf_topk_args* a, void* workspace, int64_t workspace_bytes, float* dbg_scores, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int rc = validate_tc(a, "cf_topk_tc")) return rc;
+  CF_CHECK_ARG(a->U && a->V && a->out_idx && workspace, "cf_topk_tc: U, V, out_idx and workspace are required");
+  CF_CHECK_ARG(a->kind != CF_SCORE_DOT_BIAS || a->b, "cf_topk_tc: DOT_BIAS needs the bias vector");
+  CF_CHECK_ARG(((uintptr_t)workspace % 1024) == 0, "cf_topk_tc: workspace must be 1024-byte aligned");
+  TcPlan p;
+  if (int rc = plan_tc(a, &p)) return rc;
+  CF_CHECK_ARG(workspace_bytes >= (int64_t)p.total, "cf_topk_tc: workspace %lld < required %lld bytes", (long long)workspace_bytes, (long long)p.total);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  __nv_bfloat16* Vb = reinterpret_cast<__nv_bfloat16*>(ws + p.off_vb);
+  __nv_bfloat16* Qb = reinterpret_cast<__nv_bfloat16*>(ws + p.off_qb);
+  float* eps2 = reinterpret_cast<float*>(ws + p.off_eps);
+  float* cval = reinterpret_cast<float*>(ws + p.off_cval);
+  int32_t* cidx = reinterpret_cast<int32_t*>(ws + p.off_cidx);
+  int32_t* ccnt = reinterpret_cast<int32_t*>(ws + p.off_ccnt);
+  int32_t* ovf = reinterpret_cast<int32_t*>(ws + p.off_ovf);
+  float* bmax = reinterpret_cast<float*>(ws + p.off_bmax);
+  CF_CUDA_OK(cudaMemsetAsync(bmax, 0, 256, stream));
+  CF_CUDA_OK(cudaMemsetAsync(ovf, 0, (size_t)p.T_pad * 4, stream));
+  CF_CUDA_OK(cudaMemsetAsync(ccnt, 0, (size_t)p.T_pad * p.S * 4, stream));
+  const int sms = cf_num_sms();
+
+  PrepParams pi = {};
+  pi.src = a->V; pi.bias = a->b; pi.ids = nullptr; pi.n_valid = a->n_items; pi.n_pad = p.N_pad;
+  pi.d = a->d; pi.ld = a->ld; pi.Kp = p.Kp; pi.kind = a->kind; pi.is_query = 0; pi.dst = Vb; pi.bmax = bmax; pi.eps2 = nullptr;
+  long long g = (p.N_pad + 7) / 8;
+  if (g > (long long)sms * 16) g = (long long)sms * 16;
+  k_prep<<<(unsigned)g, 256, 0, stream>>>(pi);
+  PrepParams pq = pi;
+  pq.src = a->U; pq.bias = nullptr; pq.ids = a->users; pq.n_valid = a->T; pq.n_pad = p.T_pad; pq.is_query = 1; pq.dst = Qb; pq.eps2 = eps2;
+  g = (p.T_pad + 7) / 8;
+  if (g > (long long)sms * 16) g = (long long)sms * 16;
+  k_prep<<<(unsigned)g, 256, 0, stream>>>(pq);
+
+  CUtensorMap tmQ, tmV;
+  if (int rc = make_map(&tmQ, Qb, p.T_pad, p.Kp)) return rc;
+  if (int rc = make_map(&tmV, Vb, p.N_pad, p.Kp)) return rc;
+  TcParams P = {};
+  P.T = a->T; P.N = (int)a->n_items; P.KC = p.KC; P.n_tiles = (int)(p.N_pad / TC_N); P.S = p.S; P.stages = p.stages; P.K = a->K;
+  P.users = a->users; P.tr_indptr = (const long long*)a->train.indptr; P.tr_indices = a->train.indices;
+  P.eps2 = eps2; P.cand_val = cval; P.cand_idx = cidx; P.cand_cnt = ccnt; P.overflow = ovf;
+  P.dbg_scores = dbg_scores; P.dbg_ld = p.N_pad;
+  CF_CUDA_OK(cudaFuncSetAttribute(k_topk_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  dim3 grid((unsigned)(p.T_pad / (TC_MT * TC_M)), (unsigned)p.S);
+  k_topk_tc<<<grid, TC_THREADS, p.smem, stream>>>(tmQ, tmV, P);
+
+  RerankParams R = {};
+  R.U = a->U; R.V = a->V; R.b = a->b; R.ld = a->ld; R.nvec = a->ld / 4; R.kind = a->kind; R.T = a->T; R.S = p.S; R.K = a->K;
+  R.users = a->users; R.cand_val = cval; R.cand_idx = cidx; R.cand_cnt = ccnt; R.overflow = ovf;
+  R.out_idx = a->out_idx; R.out_val = a->out_val;
+  int rg = a->T;
+  if (rg > sms * 8) rg = sms * 8;
+  k_rerank<<<rg, 256, 0, stream>>>(R);
+  CF_CUDA_OK(cudaGetLastError());
+  return cf_topk_exact_flagged(a, ovf, stream);
+}

@@ -249,20 +249,44 @@ class FactorEngine(object):
         a.item_lo, a.item_hi = item_range if item_range is not None else (0, 0)
         return a, users_t, T
 
-    def topk(self, users, K, train_csr=None, return_values=False, item_range=None):
-        """Masked top-K item ids [T, K] int32 (and fp64 scores): bprmf.py:90-103 in one pass."""
+    TENSOR_MIN_WORK = 1 << 31      # T * n_items above which method='auto' takes the tensor-core path
+
+    def topk(self, users, K, train_csr=None, return_values=False, item_range=None, method='auto', debug_scores=False):
+        """Masked top-K item ids [T, K] int32 (and fp64 scores): bprmf.py:90-103 in one pass.
+        method: 'exact' (fp64 CUDA cores), 'tensor' (tcgen05 bf16 candidate pass + exact re-rank; identical results,
+        K <= 112, d <= 254) or 'auto' (tensor for large problems)."""
         torch = self.torch
         if K <= 0:
             raise ValueError('K must be positive')
         a, users_t, T = self._topk_args(users, K, train_csr, item_range)
         if T == 0:
             raise ValueError('no query users')
+        tensor_ok = K <= 112 and self.d <= 254 and item_range is None
+        if method == 'auto':
+            method = 'tensor' if tensor_ok and T * self.n_items >= self.TENSOR_MIN_WORK else 'exact'
+        if method == 'tensor' and not tensor_ok:
+            raise ValueError('the tensor-core top-K path needs K <= 112, n_factors <= 254 and no item range')
         out_idx = torch.empty(T, K, dtype=torch.int32, device=self.device)
         out_val = torch.empty(T, K, dtype=torch.float64, device=self.device) if return_values else None
         a.out_idx, a.out_val = _lib.ptr(out_idx), _lib.ptr(out_val)
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        _lib.check(self.lib.cf_topk_exact(a, stream), 'cf_topk_exact')
-        self.launches += 1
+        if method == 'tensor':
+            need = int(self.lib.cf_topk_tc_workspace_bytes(a))
+            if need < 0:
+                raise RuntimeError(self.lib.cf_last_error().decode())
+            if getattr(self, '_tc_ws', None) is None or self._tc_ws.numel() < need + 1024:
+                self._tc_ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+            base = (self._tc_ws.data_ptr() + 1023) // 1024 * 1024
+            dbg = None
+            if debug_scores:
+                dbg = torch.zeros(T, (self.n_items + 127) // 128 * 128, dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.cf_topk_tc(a, base, need, _lib.ptr(dbg), stream), 'cf_topk_tc')
+            self.launches += 5
+            if debug_scores:
+                return out_idx, out_val, dbg
+        else:
+            _lib.check(self.lib.cf_topk_exact(a, stream), 'cf_topk_exact')
+            self.launches += 1
         return (out_idx, out_val) if return_values else out_idx
 
     def scores(self, users):
