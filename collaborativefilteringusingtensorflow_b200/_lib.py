@@ -81,7 +81,7 @@ _SIGNATURES = {
     'cf_sample_rating': (C.c_int, [C.POINTER(SampleArgs), _p]),
     'cf_topk_exact': (C.c_int, [C.POINTER(TopkArgs), _p]),
     'cf_topk_tc_workspace_bytes': (C.c_int64, [C.POINTER(TopkArgs)]),
-    'cf_topk_tc': (C.c_int, [C.POINTER(TopkArgs), _p, C.c_int64, _p, _p]),
+    'cf_topk_tc': (C.c_int, [C.POINTER(TopkArgs), _p, C.c_int64, _p, _p, _p]),
     'cf_scores': (C.c_int, [C.POINTER(TopkArgs), _p, _p]),
     'cf_topk_merge': (C.c_int, [_p, _p, C.c_int32, C.c_int32, C.c_int32, _p, _p, _p]),
     'cf_rank_metrics': (C.c_int, [_p, C.c_int32, C.c_int32, C.c_int32, _p, _p, _p, _p]),

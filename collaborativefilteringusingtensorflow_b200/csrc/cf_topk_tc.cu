@@ -33,8 +33,8 @@ constexpr int TC_MT = 2;         // M tiles per CTA (256 query rows)
 constexpr int TC_N = 128;        // items per B tile
 constexpr int TC_KCH = 64;       // bf16 elements per 128-byte swizzle chunk
 constexpr int TC_CHUNK_BYTES = TC_M * TC_KCH * 2;   // 16 KB: one TMA box {64, 128}
-constexpr int TC_CAP = 256;      // candidate buffer entries per (row, split)
-constexpr int TC_KMAX = 112;     // largest K served by the tensor path (CAP - 32 >= 2K)
+constexpr int TC_CAP = 512;      // candidate buffer entries per (row, split)
+constexpr int TC_KMAX = 200;     // largest K served by the tensor path (CAP - 32 >= 2K with room for the 2-eps band)
 constexpr int TC_THREADS = 384;  // warp 0: TMA, 1: MMA, 2: TMEM alloc, 3: idle, 4..11: epilogue
 constexpr int TC_MAX_STAGES = 6;
 
@@ -139,20 +139,18 @@ __device__ __forceinline__ void compact_row(float* cv, int32_t* ci, int n, int K
   constexpr int EPL = TC_CAP / 32;
   float v[EPL];
   int32_t id[EPL];
-  unsigned key[EPL];
 #pragma unroll
   for (int i = 0; i < EPL; ++i) {
     const int e = lane + 32 * i;
-    v[i] = e < n ? __ldcg(cv + e) : -INFINITY;
+    v[i] = e < n ? __ldcg(cv + e) : __uint_as_float(0xffffffffu);   // padding: key 0 (below every real score)
     id[i] = e < n ? __ldcg(ci + e) : -1;
-    key[i] = e < n ? ord_key(v[i]) : 0u;
   }
   unsigned prefix = 0u;
   for (int bit = 31; bit >= 0; --bit) {
     const unsigned cand = prefix | (1u << bit);
     int c = 0;
 #pragma unroll
-    for (int i = 0; i < EPL; ++i) c += key[i] >= cand;
+    for (int i = 0; i < EPL; ++i) c += ord_key(v[i]) >= cand;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if (c >= K) prefix = cand;
@@ -163,7 +161,7 @@ __device__ __forceinline__ void compact_row(float* cv, int32_t* ci, int n, int K
   __syncwarp();
 #pragma unroll
   for (int i = 0; i < EPL; ++i) {
-    const bool keep = (lane + 32 * i < n) && v[i] >= cut;
+    const bool keep = (lane + 32 * i < n) && v[i] >= cut;   // (padding is NaN: compares false)
     const unsigned m = __ballot_sync(0xffffffffu, keep);
     if (keep) {
       const int p = pos + __popc(m & ((1u << lane) - 1u));
@@ -367,6 +365,7 @@ struct PrepParams {
   __nv_bfloat16* dst;    // [n_pad, Kp]
   float* bmax;           // items: atomicMax of |b'|; queries: read
   float* eps2;           // queries: [n_pad]
+  int32_t* stats;        // optional [4]: {overflow rows, candidates, max eps2 bits, bmax bits}
 };
 
 __global__ void __launch_bounds__(256) k_prep(const __grid_constant__ PrepParams P) {
@@ -398,6 +397,7 @@ __global__ void __launch_bounds__(256) k_prep(const __grid_constant__ PrepParams
       nrm2 += __shfl_xor_sync(0xffffffffu, nrm2, o);
       vsq += __shfl_xor_sync(0xffffffffu, vsq, o);
     }
+    float cabs = 0.f;
     if (P.kind != CF_SCORE_DOT && lane == 0) {   // the two augmentation columns
       float c_hi = 0.f, c_lo = 0.f;
       if (valid) {
@@ -408,20 +408,30 @@ __global__ void __launch_bounds__(256) k_prep(const __grid_constant__ PrepParams
           const float c = P.kind == CF_SCORE_DOT_BIAS ? P.bias[src_row] : -vsq;
           c_hi = __bfloat162float(__float2bfloat16_rn(c));
           c_lo = c - c_hi;
-          nrm2 += c * c;
+          cabs = fabsf(c);
         }
       }
-      if (P.is_query && valid) nrm2 += 2.f;
       out[P.d] = __float2bfloat16_rn(c_hi);
       out[P.d + 1] = __float2bfloat16_rn(c_lo);
     }
     if (lane == 0) {
-      const float nrm = sqrtf(nrm2);
+      const float nrm = sqrtf(nrm2);   // norm of the d "main" columns (query: after the x2 of the CML form)
       if (!P.is_query) {
-        if (valid) atomicMax(reinterpret_cast<int*>(P.bmax), __float_as_int(nrm));   // non-negative floats order like ints
+        if (valid) {   // non-negative floats order like ints
+          atomicMax(reinterpret_cast<int*>(P.bmax), __float_as_int(nrm));
+          atomicMax(reinterpret_cast<int*>(P.bmax) + 1, __float_as_int(cabs));
+        }
       } else {
-        // |a'.b' - bf16(a').bf16(b')| <= (2^-8 + 2^-18) |a'||b'| ; + fp32 accumulation slack
-        P.eps2[r] = valid ? 2.f * (0.00395f * nrm * (*P.bmax) * 1.02f + 1e-6f) : 0.f;
+        // main columns: both operands rounded to bf16 (rel. 2^-9 each): |err| <= (2^-8 + 2^-18) sum|a_k b_k| <= .. |a||b|;
+        // augmentation: c = hi + lo with lo rounded to bf16: |err| <= 2^-18 |c| (charged 2^-16); x1.02 + 1e-6 covers the
+        // fp32 accumulation of <= 256 products in the tensor core.
+        const float e = 0.0039102f * nrm * P.bmax[0] * 1.02f + 1.53e-5f * P.bmax[1] + 1e-6f;
+        const float e2 = valid ? 2.f * e : 0.f;
+        P.eps2[r] = e2;
+        if (P.stats && valid) {
+          atomicMax(P.stats + 2, __float_as_int(e2));
+          P.stats[3] = __float_as_int(P.bmax[0]);
+        }
       }
     }
   }
@@ -440,6 +450,7 @@ struct RerankParams {
   const int32_t* overflow;
   int32_t* out_idx;
   double* out_val;
+  int32_t* stats;
 };
 
 __device__ __forceinline__ bool rr_before(double va, int ia, double vb, int ib) { return va > vb || (va == vb && ia < ib); }
@@ -449,13 +460,17 @@ __global__ void __launch_bounds__(256) k_rerank(const __grid_constant__ RerankPa
   __shared__ int s_idx[RR_CAP];
   __shared__ __align__(16) float s_u[512];
   for (int t = blockIdx.x; t < P.T; t += gridDim.x) {
-    if (P.overflow[t]) continue;   // recomputed by the exact streaming kernel
+    if (P.overflow[t]) {            // recomputed by the exact streaming kernel
+      if (P.stats && threadIdx.x == 0) atomicAdd(P.stats, 1);
+      continue;
+    }
     const long long u = P.users ? P.users[t] : t;
     for (int k = threadIdx.x; k < P.ld; k += blockDim.x) s_u[k] = P.U[u * P.ld + k];
     int total = 0;
     for (int s = 0; s < P.S; ++s) total += P.cand_cnt[(long long)t * P.S + s];
     int n2 = 32;
     while (n2 < total) n2 <<= 1;
+    if (P.stats && threadIdx.x == 0) atomicAdd(P.stats + 1, total);
     __syncthreads();
     // gather + exact score
     int base = 0;
@@ -569,7 +584,7 @@ int plan_tc(const cf_topk_args* a, TcPlan* p) {
   const long long row_tiles = p->T_pad / (TC_MT * TC_M), n_tiles = p->N_pad / TC_N;
   int S = (int)((2ll * cf_num_sms() + row_tiles - 1) / row_tiles);   // aim for >= 2 CTAs per SM's worth of work
   if (S < 1) S = 1;
-  if (S > 8) S = 8;
+  if (S > RR_CAP / TC_CAP) S = RR_CAP / TC_CAP;
   if (S > n_tiles) S = (int)n_tiles;
   p->S = S;
   const size_t a_bytes = (size_t)TC_MT * p->KC * TC_CHUNK_BYTES, b_bytes = (size_t)p->KC * TC_CHUNK_BYTES;
@@ -612,7 +627,8 @@ extern "C" int64_t cf_topk_tc_workspace_bytes(const cf_topk_args* a) {
   return (int64_t)p.total;
 }
 
-extern "C" int cf_topk_tc(const cf_topk_args* a, void* workspace, int64_t workspace_bytes, float* dbg_scores, void* stream_) {
+extern "C" int cf_topk_tc(const cf_topk_args* a, void* workspace, int64_t workspace_bytes, float* dbg_scores, int32_t* stats,
+                          void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int rc = validate_tc(a, "cf_topk_tc")) return rc;
   CF_CHECK_ARG(a->U && a->V && a->out_idx && workspace, "cf_topk_tc: U, V, out_idx and workspace are required");
@@ -637,7 +653,8 @@ extern "C" int cf_topk_tc(const cf_topk_args* a, void* workspace, int64_t worksp
 
   PrepParams pi = {};
   pi.src = a->V; pi.bias = a->b; pi.ids = nullptr; pi.n_valid = a->n_items; pi.n_pad = p.N_pad;
-  pi.d = a->d; pi.ld = a->ld; pi.Kp = p.Kp; pi.kind = a->kind; pi.is_query = 0; pi.dst = Vb; pi.bmax = bmax; pi.eps2 = nullptr;
+  pi.d = a->d; pi.ld = a->ld; pi.Kp = p.Kp; pi.kind = a->kind; pi.is_query = 0; pi.dst = Vb; pi.bmax = bmax; pi.eps2 = nullptr; pi.stats = stats;
+  if (stats) CF_CUDA_OK(cudaMemsetAsync(stats, 0, 16, stream));
   long long g = (p.N_pad + 7) / 8;
   if (g > (long long)sms * 16) g = (long long)sms * 16;
   k_prep<<<(unsigned)g, 256, 0, stream>>>(pi);
@@ -662,7 +679,7 @@ extern "C" int cf_topk_tc(const cf_topk_args* a, void* workspace, int64_t worksp
   RerankParams R = {};
   R.U = a->U; R.V = a->V; R.b = a->b; R.ld = a->ld; R.nvec = a->ld / 4; R.kind = a->kind; R.T = a->T; R.S = p.S; R.K = a->K;
   R.users = a->users; R.cand_val = cval; R.cand_idx = cidx; R.cand_cnt = ccnt; R.overflow = ovf;
-  R.out_idx = a->out_idx; R.out_val = a->out_val;
+  R.out_idx = a->out_idx; R.out_val = a->out_val; R.stats = stats;
   int rg = a->T;
   if (rg > sms * 8) rg = sms * 8;
   k_rerank<<<rg, 256, 0, stream>>>(R);

@@ -226,10 +226,13 @@ int cf_topk_exact(const cf_topk_args* args, void* stream);
 /* Same result as cf_topk_exact (bit-identical indices and fp64 scores), computed by the tensor-core path: bf16
  * tcgen05.mma/TMA scoring with a candidate-superset epilogue (the score matrix never leaves the SM), then an exact fp64
  * re-rank of the candidates; rows whose candidate buffer overflows fall back to the exact kernel inside the same call.
- * K <= 112, d <= 254.  `workspace` (device, 1024-byte aligned) must hold cf_topk_tc_workspace_bytes(args) bytes.
- * dbg_scores: NULL, or [T, round_up(n_items,128)] to receive the raw bf16-GEMM scores (tests). */
+ * K <= 200, d <= 254.  `workspace` (device, 1024-byte aligned) must hold cf_topk_tc_workspace_bytes(args) bytes.
+ * dbg_scores: NULL, or [T, round_up(n_items,128)] to receive the raw bf16-GEMM scores (tests).
+ * stats: NULL, or device int32[4] = {rows that fell back to the exact kernel, total candidates re-ranked,
+ * float bits of the largest 2*eps, float bits of max_i |b'_i|}. */
 int64_t cf_topk_tc_workspace_bytes(const cf_topk_args* args);
-int cf_topk_tc(const cf_topk_args* args, void* workspace, int64_t workspace_bytes, float* dbg_scores, void* stream);
+int cf_topk_tc(const cf_topk_args* args, void* workspace, int64_t workspace_bytes, float* dbg_scores, int32_t* stats,
+               void* stream);
 
 /* the dense score matrix of `__predict__` (bprmf.py:77-81, cml.py:111-117, gbprmf.py:95-99, wrmf.py:77-81) as
  * out_scores[T, n_items] fp64; for small inputs only -- the top-K path never materialises it */

@@ -39,7 +39,7 @@ def test_raw_gemm_scores_match_torch_bf16(d):
 
 @pytest.mark.parametrize('kind', ['bpr', 'gbpr', 'cml'])
 @pytest.mark.parametrize('nu,ni,d,K,T', [(900, 5000, 128, 100, 700), (300, 70001, 100, 10, 300), (2100, 1300, 64, 50, 2100),
-                                        (64, 20000, 20, 112, 40)])
+                                        (64, 20000, 20, 200, 40)])
 def test_tensor_topk_is_bit_identical_to_exact(kind, nu, ni, d, K, T):
     import torch
     rng = np.random.default_rng(nu + ni)
@@ -55,6 +55,8 @@ def test_tensor_topk_is_bit_identical_to_exact(kind, nu, ni, d, K, T):
     ti, tv = m.engine.topk(users, K, csr, return_values=True, method='tensor')
     assert torch.equal(ei, ti), 'first mismatch at %s' % (torch.nonzero(ei != ti)[:3].tolist(),)
     assert torch.equal(ev, tv)
+    st = m.engine.tc_stats.cpu().numpy()
+    assert st[0] <= max(2, T // 50), 'the tensor path handed %d of %d rows to the exact fallback' % (st[0], T)
 
 
 def test_degenerate_scores_fall_back_to_exact_rows():
