@@ -110,6 +110,15 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format: version 1, layout type 2, SBO = 1024 B)
@@ -288,17 +297,21 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
       mbar_wait(tfull + acc, (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
       const int n0 = (tile_lo + t) * TC_N;
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * (TC_MT * TC_N) + mt * TC_N);
 #pragma unroll 1
       for (int c = 0; c < TC_N / 32; ++c) {
         uint32_t r[32];
-        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * (TC_MT * TC_N) + mt * TC_N + c * 32), r);
+        tc_ld32(tbase + (uint32_t)(c * 32), r);
         tc_wait_ld();
+        if (c == TC_N / 32 - 1) {   // every column of this accumulator stage is in registers: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(tempty + acc);
+        }
         if (P.dbg_scores && valid) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) P.dbg_scores[(long long)row * P.dbg_ld + n0 + c * 32 + j] = __uint_as_float(r[j]);
         }
-        // make room: a chunk can append at most 32 entries
-        unsigned need = __ballot_sync(0xffffffffu, cnt > TC_CAP - 32);
+        unsigned need = __ballot_sync(0xffffffffu, cnt > TC_CAP - 32);   // make room: a chunk appends at most 32 entries
         while (need) {
           const int l = __ffs(need) - 1;
           need &= need - 1;
@@ -312,34 +325,44 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
           if (lane == l) {
             theta = nth;
             cnt = ncnt;
-            if (ncnt > TC_CAP - 32) {  // too many items within 2 eps of the K-th best: give this row to the exact kernel
+            if (ncnt > TC_CAP - 64) {  // too many items within 2 eps of the K-th best: give this row to the exact kernel
               overflowed = true;
               theta = INFINITY;
               cnt = 0;
             }
           }
         }
+        // Four groups of 8 columns: group maxima first (FMNMX3 trees); only a group whose maximum reaches the row's
+        // threshold is scanned value by value.  Late in the sweep hits are rare, so a chunk costs ~20 instructions.
         const float thr = theta - eps2;
-        float m = __uint_as_float(r[0]);
+        float g[4];
 #pragma unroll
-        for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
+        for (int gq = 0; gq < 4; ++gq) {
+          const float a0 = fmaxf(fmaxf(__uint_as_float(r[8 * gq]), __uint_as_float(r[8 * gq + 1])), __uint_as_float(r[8 * gq + 2]));
+          const float a1 = fmaxf(fmaxf(__uint_as_float(r[8 * gq + 3]), __uint_as_float(r[8 * gq + 4])), __uint_as_float(r[8 * gq + 5]));
+          g[gq] = fmaxf(fmaxf(a0, a1), fmaxf(__uint_as_float(r[8 * gq + 6]), __uint_as_float(r[8 * gq + 7])));
+        }
+        const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
         if (m >= thr) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float s = __uint_as_float(r[j]);
-            if (s >= thr) {
-              const int item = n0 + c * 32 + j;
-              if (item < P.N && !csr_contains(P.tr_indices, tlo, thi, item)) {
-                cv[cnt] = s;
-                ci[cnt] = item;
-                ++cnt;
+          for (int gq = 0; gq < 4; ++gq) {
+            if (g[gq] >= thr) {
+#pragma unroll
+              for (int j = 8 * gq; j < 8 * gq + 8; ++j) {
+                const float sv = __uint_as_float(r[j]);
+                if (sv >= thr) {
+                  const int item = n0 + c * 32 + j;
+                  if (item < P.N && !csr_contains(P.tr_indices, tlo, thi, item)) {
+                    cv[cnt] = sv;
+                    ci[cnt] = item;
+                    ++cnt;
+                  }
+                }
               }
             }
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(tempty + acc);
     }
     if (valid) {
       P.cand_cnt[(long long)row * P.S + split] = cnt;
