@@ -292,21 +292,43 @@ def run_ours(args):
     e2e = dict(value=units / (ms_e2e * 1e-3), unit='triple updates/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=8,
                ms_per_step=ms_e2e / K)
 
-    # ---- secondary metric: users/s of full-catalog masked top-100 (exact fp64 kernel)
+    # ---- secondary metric: users/s of full-catalog masked top-100 (tcgen05/TMA candidate pass + exact fp64 re-rank)
     topk = None
     if args.topk_users > 0:
-        users = torch.randperm(wl['n_users'], device=device)[:args.topk_users].to(torch.int32)
-        model.recommend_device(users[:64], 100, csr)
-        torch.cuda.synchronize()
-        e0.record()
-        model.recommend_device(users, 100, csr)
-        e1.record()
-        torch.cuda.synchronize()
-        tk_ms = e0.elapsed_time(e1)
-        flops = 2.0 * wl['n_items'] * wl['d'] * args.topk_users
-        topk = dict(metric='users/s full-catalog top-100 (mask train items)', value=args.topk_users / (tk_ms * 1e-3),
-                    users=args.topk_users, n_items=wl['n_items'], ms=tk_ms, kernel='k_topk_exact (fp64 CUDA cores)',
-                    tflops=flops / (tk_ms * 1e-3) / 1e12)
+        def time_topk(engine, users, mask, reps=2):
+            engine.topk(users[:1024], 100, mask, method='tensor')
+            torch.cuda.synchronize()
+            best = None
+            for _ in range(reps):
+                e0.record()
+                engine.topk(users, 100, mask, method='tensor')
+                e1.record()
+                torch.cuda.synchronize()
+                best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
+            st = engine.tc_stats.cpu().numpy()
+            return best, int(st[0]), float(st[1]) / max(1, len(users) - int(st[0]))
+
+        Tq = args.topk_users
+        users = torch.randperm(wl['n_users'], device=device)[:Tq].to(torch.int32)
+        tk_ms, fb, cand = time_topk(eng, users, csr)
+        flops = 2.0 * wl['n_items'] * wl['d'] * Tq
+        topk = dict(metric='users/s full-catalog top-100 (mask train items), exact result via tensor-core candidate pass',
+                    value=Tq / (tk_ms * 1e-3), users=Tq, n_items=wl['n_items'], ms=tk_ms,
+                    kernels='k_prep x2 + k_topk_tc (tcgen05.mma bf16 + TMA) + k_rerank (fp64) + k_topk_exact (fallback rows)',
+                    tflops=flops / (tk_ms * 1e-3) / 1e12, frac_of_bf16_peak=flops / (tk_ms * 1e-3) / 1e12 / pk['bf16'],
+                    peak_tflops=pk['bf16'], fallback_rows=fb, candidates_per_row=cand)
+        if args.topk_c5_items > 0:
+            # configs[4]'s catalogue size on one GPU (item-sharded over P GPUs: x P): BPRMF scoring, 10M items, d=128
+            from collaborativefilteringusingtensorflow_b200.engine import FactorEngine
+            big = FactorEngine('bpr', Tq, args.topk_c5_items, 128, device, seed=7)
+            uq = torch.arange(Tq, dtype=torch.int32, device=device)
+            ms5, fb5, cand5 = time_topk(big, uq, None, reps=1)
+            fl5 = 2.0 * args.topk_c5_items * 128 * Tq
+            topk['c5_catalogue'] = dict(n_items=args.topk_c5_items, d=128, users=Tq, ms=ms5, value=Tq / (ms5 * 1e-3),
+                                        tflops=fl5 / (ms5 * 1e-3) / 1e12, frac_of_bf16_peak=fl5 / (ms5 * 1e-3) / 1e12 / pk['bf16'],
+                                        fallback_rows=fb5, candidates_per_row=cand5)
+            del big
+            torch.cuda.empty_cache()
 
     # ---- CPU baseline: the oracle port on this box's cores, bounded sample
     cpub = None
@@ -375,7 +397,8 @@ def main():
     ap.add_argument('--cpu-batch', type=int, default=65536, help='minibatch of the bounded CPU-baseline sample')
     ap.add_argument('--optimizer', default='adagrad', choices=['adagrad', 'sgd'])
     ap.add_argument('--update', default='sync', choices=['sync', 'hogwild'])
-    ap.add_argument('--topk-users', type=int, default=1024)
+    ap.add_argument('--topk-users', type=int, default=37888, help='query users of the top-K measurement (148 SMs x 256 rows)')
+    ap.add_argument('--topk-c5-items', type=int, default=10_000_000, help='also time top-100 over a configs[4]-sized catalogue (0 = skip)')
     ap.add_argument('--cpu-budget', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--phases', action='store_true', help='N > 1: also report per-phase times of the sharded step')
