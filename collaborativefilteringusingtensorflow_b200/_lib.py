@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libcf_b200.so')
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 # enums of cf_b200.h
 MODEL_BPR, MODEL_CML, MODEL_GBPR, MODEL_WRMF = 0, 1, 2, 3
@@ -40,6 +40,14 @@ class ApplyArgs(C.Structure):
         ('rows', _p), ('grads', _p), ('n', C.c_int64), ('ldg', C.c_int32), ('model', C.c_int32),
         ('optimizer', C.c_int32), ('lr', C.c_float), ('clip_norm', C.c_float),
         ('meta', _p), ('slot', _p), ('slot_row', _p), ('staging', _p), ('staging_rows', C.c_int64), ('counters', _p),
+    ]
+
+
+class AlsArgs(C.Structure):
+    _fields_ = [
+        ('X', _p), ('Y', _p), ('n_x', C.c_int64), ('n_y', C.c_int64), ('d', C.c_int32), ('ldx', C.c_int32),
+        ('ldy', C.c_int32), ('reserved', C.c_int32), ('indptr', _p), ('indices', _p), ('weight', C.c_float),
+        ('reg', C.c_float), ('workspace', _p), ('workspace_bytes', C.c_int64),
     ]
 
 
@@ -84,6 +92,8 @@ _SIGNATURES = {
     'cf_topk_tc': (C.c_int, [C.POINTER(TopkArgs), _p, C.c_int64, _p, _p, _p]),
     'cf_scores': (C.c_int, [C.POINTER(TopkArgs), _p, _p]),
     'cf_topk_merge': (C.c_int, [_p, _p, C.c_int32, C.c_int32, C.c_int32, _p, _p, _p]),
+    'cf_als_workspace_bytes': (C.c_int64, [C.c_int64]),
+    'cf_als_half_sweep': (C.c_int, [C.POINTER(AlsArgs), _p]),
     'cf_rank_metrics': (C.c_int, [_p, C.c_int32, C.c_int32, C.c_int32, _p, _p, _p, _p]),
 }
 

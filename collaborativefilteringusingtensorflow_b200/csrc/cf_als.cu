@@ -1,0 +1,285 @@
+// Weighted ALS half-sweep for WRMF (sm_100a): tensor-core Gram G = Y^T Y + batched per-row d x d Cholesky solves.
+//
+// The reference's wrmf.py is minibatch Adagrad on sampled (u, i, r) rows (reference src/models/basic/models/wrmf.py:52-88;
+// that path is cf_train_steps with CF_MODEL_WRMF).  This is the solver of the model the reference's README cites for WRMF
+// (README.md:29, Pan et al. / Hu-Koren-Volinsky wALS; the pos/neg-differentiated weighting wrmf.py:61-62 has commented
+// out): minimise  sum_{u,i} c_ui (r_ui - x_u.y_i)^2 + reg (|X|^2 + |Y|^2),  c_ui = weight on observed pairs (r = 1), 1
+// elsewhere (r = 0).  One half-sweep solves, for every row u of X with observed columns P_u,
+//     (Y^T Y + (weight - 1) sum_{i in P_u} y_i y_i^T + reg I) x_u = weight * sum_{i in P_u} y_i          
+//   k_als_split    Y fp32 -> transposed bf16 hi / lo planes  Yt[128, n]   (y = hi + lo up to 2^-17: fp32-grade Gram)
+//   k_gram_tc      G = Yt Yt^T with tcgen05.mma (hi.hi + hi.lo + lo.hi into one TMEM accumulator), TMA-fed, split over
+//                  the item range across CTAs, fp32 atomics into G[128,128]
+//   k_als_solve    one CTA per row: A = G + reg I + (weight-1) sum y y^T in shared memory (fp32), in-place Cholesky,
+//                  forward/back substitution, x_u written to X.
+#include <math.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+using namespace tc;
+
+namespace {
+
+constexpr int ALS_D = 128;   // padded factor dimension handled by the tensor-core Gram (d <= 128)
+
+// ---- Y [n, ld] fp32  ->  hi / lo bf16 planes, transposed: plane[a, i], a < 128 (zero rows for a >= d), i < n_pad
+__global__ void __launch_bounds__(256) k_als_split(const float* __restrict__ Y, long long n, long long n_pad, int d, int ld,
+                                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  const long long i0 = (long long)blockIdx.x * 32;
+  const int a0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const long long i = i0 + r;
+    const int a = a0 + tx;
+    tile[r][tx] = (i < n && a < d) ? Y[i * ld + a] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int a = a0 + r;
+    const long long i = i0 + tx;
+    if (i < n_pad) {
+      const float v = tile[tx][r];
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      hi[(long long)a * n_pad + i] = h;
+      lo[(long long)a * n_pad + i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+
+// ---- G += Yt[:, chunk range] Yt[:, chunk range]^T on the tensor cores
+__global__ void __launch_bounds__(192, 1)
+k_gram_tc(const __grid_constant__ CUtensorMap tmHi, const __grid_constant__ CUtensorMap tmLo, int n_chunks, float* __restrict__ G) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sHi = smem;
+  uint8_t* sLo = smem + CHUNK_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * CHUNK_BYTES);
+  uint64_t* full = bars;
+  uint64_t* mma_done = bars + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per = (n_chunks + gridDim.x - 1) / gridDim.x;
+  const int c_lo = blockIdx.x * per, c_hi = min(n_chunks, c_lo + per);
+
+  if (threadIdx.x == 0) {
+    mbar_init(full, 1);
+    mbar_init(mma_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {   // one thread drives TMA + MMA (the Gram is a tiny share of a half-sweep)
+    const uint32_t idesc = umma_idesc_bf16(ROWS, ALS_D);
+    uint32_t first = 1u;
+    for (int c = c_lo; c < c_hi; ++c) {
+      const uint32_t ph = (uint32_t)(c - c_lo) & 1u;
+      if (c > c_lo) mbar_wait(mma_done, ph ^ 1u);   // the previous chunk's MMAs have finished reading shared memory
+      mbar_arrive_expect_tx(full, 2u * CHUNK_BYTES);
+      tma_load_2d(&tmHi, full, sHi, c * KCH, 0);
+      tma_load_2d(&tmLo, full, sLo, c * KCH, 0);
+      mbar_wait(full, ph);
+      tc_fence_after();
+      const uint32_t h = smem_u32(sHi), l = smem_u32(sLo);
+#pragma unroll
+      for (int k = 0; k < KCH / 16; ++k) {
+        const uint64_t dh = umma_desc_sw128(h + k * 32), dl = umma_desc_sw128(l + k * 32);
+        tc_mma_bf16(tmem_base, dh, dh, idesc, first ? 0u : 1u);   // hi . hi
+        first = 0u;
+        tc_mma_bf16(tmem_base, dh, dl, idesc, 1u);                // hi . lo
+        tc_mma_bf16(tmem_base, dl, dh, idesc, 1u);                // lo . hi
+      }
+      tc_commit(mma_done);
+    }
+    if (c_hi > c_lo) mbar_wait(mma_done, (uint32_t)(c_hi - c_lo - 1) & 1u);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp >= 2 && c_hi > c_lo) {   // warps 2..5: TMEM lane quadrant = warp % 4; one thread per row of G
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < ALS_D / 32; ++c) {
+      uint32_t r[32];
+      tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+      tc_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) atomicAdd(G + row * ALS_D + c * 32 + j, __uint_as_float(r[j]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+  }
+}
+
+struct SolveParams {
+  float* X;             // [n_x, ldx] rows to solve
+  const float* Y;       // [n_y, ldy]
+  const float* G;       // [128, 128] = Y^T Y
+  const long long* indptr;
+  const int32_t* indices;
+  long long n_x;
+  int d, ldx, ldy;
+  float weight, reg;
+};
+
+// one CTA per row of X; A (d x d, fp32, leading dimension d + 1) lives in shared memory
+__global__ void __launch_bounds__(256) k_als_solve(const __grid_constant__ SolveParams P) {
+  extern __shared__ float sm[];
+  const int d = P.d, lda = d + 1;
+  float* A = sm;                    // [d, lda]
+  float* b = A + d * lda;           // [d]
+  float* rows = b + d;              // [8, d] gathered y rows
+  const int tid = threadIdx.x;
+  for (long long u = blockIdx.x; u < P.n_x; u += gridDim.x) {
+    // A = G + reg I (lower triangle is what Cholesky reads; fill all for simplicity), b = 0
+    for (int e = tid; e < d * d; e += blockDim.x) {
+      const int i = e / d, j = e - i * d;
+      A[i * lda + j] = P.G[i * ALS_D + j] + (i == j ? P.reg : 0.f);
+    }
+    for (int e = tid; e < d; e += blockDim.x) b[e] = 0.f;
+    const long long lo = P.indptr[u], hi = P.indptr[u + 1];
+    const float wm1 = P.weight - 1.f;
+    for (long long e0 = lo; e0 < hi; e0 += 8) {
+      const int nb = (int)min(8ll, hi - e0);
+      __syncthreads();
+      for (int e = tid; e < nb * d; e += blockDim.x) {
+        const int r = e / d, k = e - r * d;
+        rows[r * d + k] = P.Y[(long long)P.indices[e0 + r] * P.ldy + k];
+      }
+      __syncthreads();
+      if (wm1 != 0.f) {   // A += (weight - 1) sum_r y_r y_r^T   (lower triangle)
+        for (int e = tid; e < d * d; e += blockDim.x) {
+          const int i = e / d, j = e - i * d;
+          if (j <= i) {
+            float acc = 0.f;
+            for (int r = 0; r < nb; ++r) acc = fmaf(rows[r * d + i], rows[r * d + j], acc);
+            A[i * lda + j] = fmaf(wm1, acc, A[i * lda + j]);
+          }
+        }
+      }
+      for (int k = tid; k < d; k += blockDim.x) {   // b += weight * sum_r y_r   (r_ui = 1 on observed pairs)
+        float acc = 0.f;
+        for (int r = 0; r < nb; ++r) acc += rows[r * d + k];
+        b[k] = fmaf(P.weight, acc, b[k]);
+      }
+    }
+    __syncthreads();
+    // in-place Cholesky A = L L^T (lower), right-looking
+    for (int k = 0; k < d; ++k) {
+      if (tid == 0) A[k * lda + k] = sqrtf(fmaxf(A[k * lda + k], 1e-30f));
+      __syncthreads();
+      const float inv = 1.f / A[k * lda + k];
+      for (int i = k + 1 + tid; i < d; i += blockDim.x) A[i * lda + k] *= inv;
+      __syncthreads();
+      const int m = d - k - 1;
+      for (int e = tid; e < m * m; e += blockDim.x) {
+        const int i = k + 1 + e / m, j = k + 1 + e % m;
+        if (j <= i) A[i * lda + j] = fmaf(-A[i * lda + k], A[j * lda + k], A[i * lda + j]);
+      }
+      __syncthreads();
+    }
+    // L z = b, L^T x = z (one warp; dot products by shuffle reduction)
+    if (tid < 32) {
+      for (int k = 0; k < d; ++k) {
+        float acc = 0.f;
+        for (int j = tid; j < k; j += 32) acc = fmaf(A[k * lda + j], b[j], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (tid == 0) b[k] = (b[k] - acc) / A[k * lda + k];
+        __syncwarp();
+      }
+      for (int k = d - 1; k >= 0; --k) {
+        float acc = 0.f;
+        for (int j = k + 1 + tid; j < d; j += 32) acc = fmaf(A[j * lda + k], b[j], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (tid == 0) b[k] = (b[k] - acc) / A[k * lda + k];
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    for (int k = tid; k < d; k += blockDim.x) P.X[u * P.ldx + k] = b[k];
+    __syncthreads();
+  }
+}
+
+typedef CUresult (*encode_tiled_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_plane_map(CUtensorMap* tm, void* base, long long n_pad) {
+  static encode_tiled_t enc = nullptr;
+  if (!enc) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      enc = reinterpret_cast<encode_tiled_t>(p);
+  }
+  CF_CHECK_ARG(enc != nullptr, "cf_als_half_sweep: cuTensorMapEncodeTiled is not available from the driver");
+  const cuuint64_t dims[2] = {(cuuint64_t)n_pad, (cuuint64_t)ALS_D};
+  const cuuint64_t strides[1] = {(cuuint64_t)n_pad * 2};
+  const cuuint32_t box[2] = {KCH, ROWS};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CF_CHECK_ARG(r == CUDA_SUCCESS, "cf_als_half_sweep: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int64_t cf_als_workspace_bytes(int64_t n_y) {
+  const long long n_pad = (n_y + KCH - 1) / KCH * KCH;
+  return 2ll * ALS_D * n_pad * 2 + ALS_D * ALS_D * 4 + 2048;
+}
+
+extern "C" int cf_als_half_sweep(const cf_als_args* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CF_CHECK_ARG(a != nullptr, "cf_als_half_sweep: args is NULL");
+  CF_CHECK_ARG(a->X && a->Y && a->indptr && a->indices && a->workspace, "cf_als_half_sweep: NULL pointer");
+  CF_CHECK_ARG(a->d > 0 && a->d <= ALS_D && a->ldx >= a->d && a->ldy >= a->d, "cf_als_half_sweep: n_factors up to %d are supported (d=%d)", ALS_D, a->d);
+  CF_CHECK_ARG(a->n_x > 0 && a->n_y > 0, "cf_als_half_sweep: empty factor matrix");
+  CF_CHECK_ARG(a->reg > 0.f, "cf_als_half_sweep: reg must be positive (it keeps the normal equations SPD)");
+  CF_CHECK_ARG(((uintptr_t)a->workspace % 1024) == 0 && a->workspace_bytes >= cf_als_workspace_bytes(a->n_y), "cf_als_half_sweep: workspace too small or not 1024-byte aligned");
+  const long long n_pad = (a->n_y + KCH - 1) / KCH * KCH;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(ws);
+  __nv_bfloat16* lo = hi + (size_t)ALS_D * n_pad;
+  float* G = reinterpret_cast<float*>(ws + (((size_t)2 * ALS_D * n_pad * 2 + 1023) / 1024) * 1024);
+  CF_CUDA_OK(cudaMemsetAsync(G, 0, ALS_D * ALS_D * 4, stream));
+  dim3 sgrid((unsigned)((n_pad + 31) / 32), ALS_D / 32);
+  k_als_split<<<sgrid, 256, 0, stream>>>(a->Y, a->n_y, n_pad, a->d, a->ldy, hi, lo);
+  CUtensorMap tmHi, tmLo;
+  if (int rc = make_plane_map(&tmHi, hi, n_pad)) return rc;
+  if (int rc = make_plane_map(&tmLo, lo, n_pad)) return rc;
+  const int n_chunks = (int)(n_pad / KCH);
+  int ggrid = cf_num_sms();
+  if (ggrid > n_chunks) ggrid = n_chunks;
+  const size_t gsmem = 2 * CHUNK_BYTES + 64 + 1024;
+  CF_CUDA_OK(cudaFuncSetAttribute(k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+  k_gram_tc<<<ggrid, 192, gsmem, stream>>>(tmHi, tmLo, n_chunks, G);
+  SolveParams S;
+  S.X = a->X; S.Y = a->Y; S.G = G; S.indptr = (const long long*)a->indptr; S.indices = a->indices;
+  S.n_x = a->n_x; S.d = a->d; S.ldx = a->ldx; S.ldy = a->ldy; S.weight = a->weight; S.reg = a->reg;
+  const size_t ssmem = ((size_t)a->d * (a->d + 1) + a->d + 8 * a->d) * 4;
+  CF_CUDA_OK(cudaFuncSetAttribute(k_als_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
+  long long sg = a->n_x;
+  const long long cap = (long long)cf_num_sms() * 8;
+  if (sg > cap) sg = cap;
+  k_als_solve<<<(unsigned)sg, 256, ssmem, stream>>>(S);
+  CF_CUDA_OK(cudaGetLastError());
+  return 0;
+}

@@ -291,6 +291,28 @@ class FactorEngine(object):
             self.launches += 1
         return (out_idx, out_val) if return_values else out_idx
 
+    def als_half_sweep(self, side, csr):
+        """Solve all user rows (side='users', csr = user -> items) or all item rows (side='items', csr = item -> users)
+        of the weighted-ALS normal equations (cf_als_half_sweep); hyper: weight, reg."""
+        torch = self.torch
+        if self.d > 128:
+            raise ValueError('the ALS solver supports n_factors <= 128')
+        X, Y = (self.U, self.V) if side == 'users' else (self.V, self.U)
+        n_x, n_y = X.shape[0], Y.shape[0]
+        if csr.shape != (n_x, n_y):
+            raise ValueError('CSR shape %s does not match (%d, %d)' % (csr.shape, n_x, n_y))
+        need = int(self.lib.cf_als_workspace_bytes(n_y))
+        if getattr(self, '_als_ws', None) is None or self._als_ws.numel() < need + 1024:
+            self._als_ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+        a = _lib.AlsArgs()
+        a.X, a.Y, a.n_x, a.n_y, a.d, a.ldx, a.ldy = _lib.ptr(X), _lib.ptr(Y), n_x, n_y, self.d, self.ld, self.ld
+        a.indptr, a.indices = _lib.ptr(csr.indptr), _lib.ptr(csr.indices)
+        a.weight, a.reg = float(self.hyper['weight']), float(self.hyper['reg'])
+        a.workspace = (self._als_ws.data_ptr() + 1023) // 1024 * 1024
+        a.workspace_bytes = need
+        _lib.check(self.lib.cf_als_half_sweep(a, torch.cuda.current_stream(self.device).cuda_stream), 'cf_als_half_sweep')
+        self.launches += 3
+
     def scores(self, users):
         """Dense [T, n_items] fp64 score matrix of ``__predict__`` (small inputs only)."""
         torch = self.torch

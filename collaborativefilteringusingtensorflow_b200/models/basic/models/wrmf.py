@@ -1,7 +1,10 @@
 """WRMF with the reference's constructor and train/close entry points (reference src/models/basic/models/wrmf.py:11-163).
 
 ``solver='sgd'`` (default) is what the reference implements: minibatch Adagrad on sampled (user, item, rating) rows with a
-uniform weight (wrmf.py:58-62), fed by sampler_rating."""
+uniform weight (wrmf.py:58-62), fed by sampler_rating.  ``solver='als'`` is the weighted-ALS solver of the
+model the reference's README cites (README.md:29): confidence ``weight`` on observed pairs, 1 elsewhere, L2 ``reg``; one
+epoch = a user half-sweep + an item half-sweep (tensor-core Gram + per-row Cholesky, csrc/cf_als.cu); the sampler is not
+used.  It cannot be step-compared with the reference (different algorithm); tests compare it with a dense fp64 solve."""
 import numpy as np
 
 from ..._base import RankingModelBase
@@ -15,8 +18,10 @@ class WRMF(RankingModelBase):
                  weight=1, reg=0.02, n_factors=10, batch_size=500,
                  max_iter=50, lr=.1,
                  init_mean=0.0, init_stddev=0.1,
-                 device='CPU', *, optimizer='adagrad', update='sync', seed=None, verbose=True):
-        self.weight, self.reg = weight, reg
+                 device='CPU', *, optimizer='adagrad', update='sync', seed=None, verbose=True, solver='sgd'):
+        if solver not in ('sgd', 'als'):
+            raise ValueError("solver must be 'sgd' or 'als'")
+        self.weight, self.reg, self.solver = weight, reg, solver
         self._setup(n_users, n_items, topN, split_method, eval_metrics, n_factors, batch_size, max_iter, lr,
                     init_mean, init_stddev, device, optimizer, update, seed, verbose, reg=float(reg), weight=float(weight))
 
@@ -32,6 +37,14 @@ class WRMF(RankingModelBase):
         else:                      # device sampler chunk: (ids int32 [rows, 2], ratings float32 [rows])
             ids, ratings = batch
         return self.engine.train_batches(ids, ratings=ratings, batch_size=rows_per_batch)
+
+    def _epoch(self, sampler, n_batches):
+        if self.solver == 'sgd':
+            return super(WRMF, self)._epoch(sampler, n_batches)
+        tra = self._train_csr
+        self.engine.als_half_sweep('users', tra)
+        self.engine.als_half_sweep('items', tra.transpose())
+        return self.engine.torch.full((1,), float('nan'), dtype=self.engine.torch.float64, device=self.device)
 
     def _log_line(self, fold, it, aveloss, scores):
         # wrmf.py:153-156

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CF_ABI_VERSION 7
+#define CF_ABI_VERSION 8
 
 /* models */
 enum { CF_MODEL_BPR = 0, CF_MODEL_CML = 1, CF_MODEL_GBPR = 2, CF_MODEL_WRMF = 3 };
@@ -241,6 +241,32 @@ int cf_scores(const cf_topk_args* args, double* out_scores, void* stream);
 /* merge P per-shard top-K lists ([P, T, K] idx/val, e.g. after an all-gather) into the global top-K */
 int cf_topk_merge(const int32_t* idx, const double* val, int32_t P, int32_t T, int32_t K,
                   int32_t* out_idx, double* out_val, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * WRMF by weighted alternating least squares (new solver; the reference's wrmf.py is minibatch Adagrad, which is
+ * cf_train_steps with CF_MODEL_WRMF).  One half-sweep solves every row x_u of X:
+ *   (Y^T Y + (weight-1) sum_{i in P_u} y_i y_i^T + reg I) x_u = weight * sum_{i in P_u} y_i
+ * with a tensor-core Gram (tcgen05, bf16 hi/lo split = fp32-grade) and one shared-memory Cholesky per row.  d <= 128.
+ * The item half-sweep is the same call with X <-> Y and the transposed CSR.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct cf_als_args {
+  float* X;                /* [n_x, ldx] rows to solve (overwritten) */
+  const float* Y;          /* [n_y, ldy] fixed factors */
+  int64_t n_x;
+  int64_t n_y;
+  int32_t d;
+  int32_t ldx;
+  int32_t ldy;
+  int32_t reserved;
+  const int64_t* indptr;   /* CSR of X's rows: [n_x + 1] */
+  const int32_t* indices;  /* observed columns = row ids of Y */
+  float weight;            /* confidence of observed pairs (1 elsewhere) */
+  float reg;
+  void* workspace;         /* device, 1024-byte aligned, cf_als_workspace_bytes(n_y) bytes */
+  int64_t workspace_bytes;
+} cf_als_args;
+int64_t cf_als_workspace_bytes(int64_t n_y);
+int cf_als_half_sweep(const cf_als_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Ranking metrics.  Replaces metrics/ranking.py:11-67 (pre/recall/ndcg/map/mrr) and :75-91 (hr/arhr):
