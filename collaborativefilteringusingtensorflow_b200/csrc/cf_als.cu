@@ -143,32 +143,29 @@ __global__ void __launch_bounds__(256) k_als_solve(const __grid_constant__ Solve
   float* b = A + d * lda;           // [d]
   float* rows = b + d;              // [8, d] gathered y rows
   const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;   // 16 x 16 thread grid over (row i, column j): no integer divisions in the loops
   for (long long u = blockIdx.x; u < P.n_x; u += gridDim.x) {
-    // A = G + reg I (lower triangle is what Cholesky reads; fill all for simplicity), b = 0
-    for (int e = tid; e < d * d; e += blockDim.x) {
-      const int i = e / d, j = e - i * d;
-      A[i * lda + j] = P.G[i * ALS_D + j] + (i == j ? P.reg : 0.f);
-    }
+    // A = G + reg I (lower triangle), b = 0
+    for (int i = ty; i < d; i += 16)
+      for (int j = tx; j <= i; j += 16) A[i * lda + j] = P.G[i * ALS_D + j] + (i == j ? P.reg : 0.f);
     for (int e = tid; e < d; e += blockDim.x) b[e] = 0.f;
     const long long lo = P.indptr[u], hi = P.indptr[u + 1];
     const float wm1 = P.weight - 1.f;
     for (long long e0 = lo; e0 < hi; e0 += 8) {
       const int nb = (int)min(8ll, hi - e0);
       __syncthreads();
-      for (int e = tid; e < nb * d; e += blockDim.x) {
-        const int r = e / d, k = e - r * d;
-        rows[r * d + k] = P.Y[(long long)P.indices[e0 + r] * P.ldy + k];
+      for (int r = 0; r < nb; ++r) {
+        const float* yr = P.Y + (long long)P.indices[e0 + r] * P.ldy;
+        for (int k = tid; k < d; k += blockDim.x) rows[r * d + k] = yr[k];
       }
       __syncthreads();
       if (wm1 != 0.f) {   // A += (weight - 1) sum_r y_r y_r^T   (lower triangle)
-        for (int e = tid; e < d * d; e += blockDim.x) {
-          const int i = e / d, j = e - i * d;
-          if (j <= i) {
+        for (int i = ty; i < d; i += 16)
+          for (int j = tx; j <= i; j += 16) {
             float acc = 0.f;
             for (int r = 0; r < nb; ++r) acc = fmaf(rows[r * d + i], rows[r * d + j], acc);
             A[i * lda + j] = fmaf(wm1, acc, A[i * lda + j]);
           }
-        }
       }
       for (int k = tid; k < d; k += blockDim.x) {   // b += weight * sum_r y_r   (r_ui = 1 on observed pairs)
         float acc = 0.f;
@@ -184,10 +181,9 @@ __global__ void __launch_bounds__(256) k_als_solve(const __grid_constant__ Solve
       const float inv = 1.f / A[k * lda + k];
       for (int i = k + 1 + tid; i < d; i += blockDim.x) A[i * lda + k] *= inv;
       __syncthreads();
-      const int m = d - k - 1;
-      for (int e = tid; e < m * m; e += blockDim.x) {
-        const int i = k + 1 + e / m, j = k + 1 + e % m;
-        if (j <= i) A[i * lda + j] = fmaf(-A[i * lda + k], A[j * lda + k], A[i * lda + j]);
+      for (int i = k + 1 + ty; i < d; i += 16) {
+        const float lik = A[i * lda + k];
+        for (int j = k + 1 + tx; j <= i; j += 16) A[i * lda + j] = fmaf(-lik, A[j * lda + k], A[i * lda + j]);
       }
       __syncthreads();
     }
