@@ -23,7 +23,7 @@ from . import _lib
 
 
 class ExchangePlan(object):
-    __slots__ = ('n_req', 'occ_local', 'send_counts', 'recv_counts', 'recv_local_rows', 'req_global')
+    __slots__ = ('n_req', 'occ_local', 'send_counts', 'recv_counts', 'recv_local_rows', 'req_global', 'send_rows')
 
 
 class ItemExchange(object):
@@ -41,28 +41,56 @@ class ItemExchange(object):
         else:
             self.dist.all_to_all_single(out, inp, out_split, in_split, group=self.group)
 
-    def plan(self, item_ids):
-        """item_ids: int tensor (any shape) of GLOBAL item ids needed by this rank's minibatch."""
+    def plan(self, item_ids, n_items_global=None):
+        return self.plan_exchange(self.plan_local(item_ids, n_items_global))
+
+    def plan_local(self, item_ids, n_items_global=None):
+        """Collective-free half of the plan (dedupe + grouping by owner).  item_ids: int tensor (any shape) of GLOBAL item ids needed by this rank's minibatch.
+        With ``n_items_global`` the dedupe is sort-free (flag array laid out [owner][local row] + prefix sum: O(items +
+        occurrences)); without it falls back to torch.unique."""
         torch = self.torch
         flat = item_ids.reshape(-1).to(torch.int64)
-        uniq, inv = torch.unique(flat, return_inverse=True)                 # sorted unique ids + occurrence -> unique
-        owner = uniq % self.world
-        order = torch.sort(owner, stable=True).indices                      # group the requests by owner
-        pos = torch.empty_like(order)
-        pos[order] = torch.arange(order.numel(), device=order.device)
-        send_counts = torch.bincount(owner, minlength=self.world)
-        recv_counts = torch.empty_like(send_counts)
-        self._a2a(recv_counts, send_counts, None, None)
-        sc, rc = send_counts.tolist(), recv_counts.tolist()
-        send_rows = (uniq[order] // self.world).to(torch.int32)             # local row ids at the owners
-        recv_rows = torch.empty(sum(rc), dtype=torch.int32, device=flat.device)
-        self._a2a(recv_rows, send_rows, rc, sc)
+        P = self.world
+        if n_items_global is not None:
+            L = (int(n_items_global) + P - 1) // P                         # rows per owner (padded)
+            key = (flat % P) * L + flat // P                                # position in the owner-major layout
+            flag = torch.zeros(P * L, dtype=torch.int32, device=flat.device)
+            flag[key] = 1
+            csum = torch.cumsum(flag, 0, dtype=torch.int32)
+            occ = (csum[key] - 1).to(torch.int32)                           # occurrence -> row of the fetched buffer
+            upos = torch.nonzero(flag).reshape(-1)                          # owner-major, ascending local row
+            send_rows = (upos % L).to(torch.int32)
+            ends = csum[torch.arange(1, P + 1, device=flat.device) * L - 1].to(torch.int64)
+            send_counts = torch.diff(ends, prepend=torch.zeros(1, dtype=torch.int64, device=flat.device))
+            req_global = (upos % L) * P + upos // L
+        else:
+            uniq, inv = torch.unique(flat, return_inverse=True)             # sorted unique ids + occurrence -> unique
+            owner = uniq % P
+            order = torch.sort(owner, stable=True).indices                  # group the requests by owner
+            pos = torch.empty_like(order)
+            pos[order] = torch.arange(order.numel(), device=order.device)
+            send_counts = torch.bincount(owner, minlength=P)
+            send_rows = (uniq[order] // P).to(torch.int32)                  # local row ids at the owners
+            occ = pos[inv].to(torch.int32)
+            req_global = uniq[order]
         p = ExchangePlan()
-        p.n_req = int(uniq.numel())
-        p.occ_local = pos[inv].reshape(item_ids.shape).to(torch.int32)      # occurrence -> row of the fetched buffer
+        p.n_req = int(send_rows.numel())
+        p.occ_local = occ.reshape(item_ids.shape)
+        p.send_counts = send_counts
+        p.send_rows = send_rows
+        p.req_global = req_global
+        return p
+
+    def plan_exchange(self, p):
+        """Collective half: tell every owner how many and which of its rows this rank needs."""
+        torch = self.torch
+        recv_counts = torch.empty_like(p.send_counts)
+        self._a2a(recv_counts, p.send_counts, None, None)
+        sc, rc = p.send_counts.tolist(), recv_counts.tolist()
+        recv_rows = torch.empty(sum(rc), dtype=torch.int32, device=p.send_rows.device)
+        self._a2a(recv_rows, p.send_rows, rc, sc)
         p.send_counts, p.recv_counts = sc, rc
         p.recv_local_rows = recv_rows                                       # rows of MY shard that others (and I) asked for
-        p.req_global = uniq[order]
         return p
 
     def fetch(self, plan, table_shard):
@@ -103,6 +131,10 @@ class DistributedTrainer(object):
         if self.eng.n_items != item_shard_rows(n_items_global, world, rank):
             raise ValueError('model.n_items must be the item-shard size %d' % item_shard_rows(n_items_global, world, rank))
         self.ex = ItemExchange(world, rank, group)
+        # the collective-free half of the plan of minibatch k+1 (dedupe, grouping by owner) runs on a side stream while
+        # minibatch k computes and exchanges rows
+        self.side = self.torch.cuda.Stream(device=self.eng.device)
+        self._keep = []
         self._ows = None
         self._ows_rows = 0
         self.launches = 0
@@ -133,16 +165,24 @@ class DistributedTrainer(object):
             self.phase_ms[name] = self.phase_ms.get(name, 0.0) + ev0.elapsed_time(ev1)
         return ev1
 
-    def step_chunk(self, pairs, negs, batch_size, want_loss=True):
+    def make_plan(self, pairs, negs, local_only=False):
+        torch = self.torch
+        items = torch.cat([pairs[:, 1:2].to(torch.int64), negs.to(torch.int64)], dim=1)       # [B, 1 + W] global ids
+        p = self.ex.plan_local(items, self.n_items_global)
+        return p if local_only else self.ex.plan_exchange(p)
+
+    def step_chunk(self, pairs, negs, batch_size, want_loss=True, plan=None):
         """One minibatch (rows == batch_size) of the sharded step on explicit local batches."""
         torch, eng = self.torch, self.eng
         B = int(batch_size)
         ev = self._tick('', None)
         if int(pairs.shape[0]) != B:
             raise ValueError('the sharded step takes one minibatch per call')
-        items = torch.cat([pairs[:, 1:2].to(torch.int64), negs.to(torch.int64)], dim=1)       # [B, 1 + W] global ids
-        plan = self.ex.plan(items)
-        ev = self._tick('plan (unique + route ids)', ev)
+        if plan is None:
+            plan = self.make_plan(pairs, negs)
+        elif getattr(plan, 'recv_local_rows', None) is None:
+            plan = self.ex.plan_exchange(plan)
+        ev = self._tick('plan (dedupe + route ids)', ev)
         Vbuf = self.ex.fetch(plan, eng.V)                                                    # [n_req, ld]
         ev = self._tick('fetch rows (gather + all_to_all)', ev)
         Gbuf = torch.zeros_like(Vbuf)
@@ -187,13 +227,37 @@ class DistributedTrainer(object):
         return loss
 
     def step(self, n_minibatches=1, want_loss=True):
-        """Sample + run n minibatches; returns their losses (CUDA float64)."""
+        """Sample + run n minibatches; returns their losses (CUDA float64).  The plan (dedupe + id routing) of minibatch
+        k+1 is built on a side stream while minibatch k computes and exchanges rows."""
         torch = self.torch
         B = self.sampler.batch_size
         chunk = self.sampler.next_chunk(n_minibatches)
+        main = torch.cuda.current_stream(self.eng.device)
+        overlap = self.phase_ms is None and self.world > 1
+
+        def batch(k):
+            return chunk[0][k * B:(k + 1) * B], chunk[1][k * B:(k + 1) * B]
+
+        sampled = torch.cuda.Event()
+        sampled.record(main)
+        self.side.wait_event(sampled)      # the side stream only depends on the sampled indices, not on the steps
+
+        def plan_async(k):
+            with torch.cuda.stream(self.side):
+                return self.make_plan(*batch(k), local_only=True)
+
         out = []
+        nxt = plan_async(0) if overlap else None
         for k in range(n_minibatches):
-            out.append(self.step_chunk(chunk[0][k * B:(k + 1) * B], chunk[1][k * B:(k + 1) * B], B, want_loss))
+            plan = None
+            if overlap:
+                plan = nxt
+                main.wait_stream(self.side)
+                self._keep = (self._keep + [plan])[-3:]     # plans were allocated on the side stream: keep them alive
+            p, n = batch(k)
+            out.append(self.step_chunk(p, n, B, want_loss, plan))
+            if overlap and k + 1 < n_minibatches:
+                nxt = plan_async(k + 1)
         return torch.cat(out) if want_loss else None
 
 

@@ -36,7 +36,7 @@ def _worker(rank, world, port, n_items, ld, q):
             ids = torch.randint(0, n_items, (64, 4), generator=g)
             if trial == 2:
                 ids = torch.full((5, 2), int(rank), dtype=torch.int64)      # every occurrence the same item
-            plan = ex.plan(ids)
+            plan = ex.plan(ids, n_items if trial != 1 else None)      # sort-free dedupe and the torch.unique fallback
             rows = ex.fetch(plan, shard)
             assert rows.shape == (plan.n_req, ld) and plan.n_req == len(torch.unique(ids))
             got = rows[plan.occ_local.to(torch.int64).reshape(-1)]
