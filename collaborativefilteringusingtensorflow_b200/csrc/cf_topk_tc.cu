@@ -1,10 +1,10 @@
-// Tensor-core full-catalog top-K for sm_100a: tcgen05.mma (bf16 -> fp32 in TMEM) fed by TMA, with an epilogue that keeps a
+// Tensor-core full-catalog top-K for sm_100a: tcgen05.mma (fp16 -> fp32 in TMEM) fed by TMA, with an epilogue that keeps a
 // per-row candidate superset instead of writing scores, followed by an exact fp64 re-rank of the candidates.
 //
 // Replaces `sess.run(tf.nn.top_k(matmul(U[test_users], V^T) (+b | cml distance), K'))` + the Python filter loop
 // (reference src/models/pl/models/bprmf.py:77-103, cml.py:111-144, gbprmf.py:95-121, basic/models/wrmf.py:77-111).
 //
-// Stage 0 (k_prep_items / k_prep_queries): fp32 tables -> bf16 operand matrices with K padded to a multiple of 64.  The
+// Stage 0 (k_prep): fp32 tables -> fp16 operand matrices (fp16, not bf16: 8x tighter error band for the same MMA rate) with K padded to a multiple of 64.  The
 //   three scoring kinds all become plain dot products a'.b':   DOT       a' = u            b' = v
 //                                                               DOT_BIAS  a' = [u, 1, 1]    b' = [v, hi(b_i), lo(b_i)]
 //                                                               NEG_SQDIST a' = [2u, 1, 1]  b' = [v, hi(-|v|^2), lo(-|v|^2)]
@@ -169,7 +169,7 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
   } else if (warp == 1) {
     // ================================================================== MMA issuer (one thread)
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(TC_M, TC_N);
+      const uint32_t idesc = umma_idesc_fp16(TC_M, TC_N);
       mbar_wait(a_full, 0u);
       for (int t = 0; t < nt; ++t) {
         const int st = t % P.stages;
@@ -304,7 +304,7 @@ struct PrepParams {
   const int32_t* ids;    // optional row gather (query users)
   long long n_valid, n_pad;
   int d, ld, Kp, kind, is_query;
-  __nv_bfloat16* dst;    // [n_pad, Kp]
+  __half* dst;    // [n_pad, Kp]
   float* bmax;           // items: atomicMax of |b'|; queries: read
   float* eps2;           // queries: [n_pad]
   int32_t* stats;        // optional [4]: {overflow rows, candidates, max eps2 bits, bmax bits}
@@ -314,8 +314,9 @@ __global__ void __launch_bounds__(256) k_prep(const __grid_constant__ PrepParams
   const int lane = threadIdx.x & 31;
   const long long nw = (long long)gridDim.x * blockDim.x / 32;
   for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 32; r < P.n_pad; r += nw) {
-    __nv_bfloat16* out = P.dst + r * P.Kp;
+    __half* out = P.dst + r * P.Kp;
     float nrm2 = 0.f;
+    bool big = false;
     const bool valid = r < P.n_valid;
     const long long src_row = valid ? (P.ids ? (long long)P.ids[r] : r) : 0;
     const float scale = (P.is_query && P.kind == CF_SCORE_NEG_SQDIST) ? 2.f : 1.f;
@@ -326,12 +327,13 @@ __global__ void __launch_bounds__(256) k_prep(const __grid_constant__ PrepParams
         x = P.src[src_row * P.ld + k];
         vsq += x * x;
         x *= scale;
+        big = big || !(fabsf(x) < 65000.f);   // outside fp16 range (or NaN): this row / table cannot use the fp16 pass
       }
       if (k < P.d) {
-        out[k] = __float2bfloat16_rn(x);
+        out[k] = __float2half_rn(x);
         nrm2 += x * x;
       } else if (k >= P.d + 2 || P.kind == CF_SCORE_DOT) {
-        out[k] = __float2bfloat16_rn(0.f);
+        out[k] = __float2half_rn(0.f);
       }
     }
 #pragma unroll
@@ -339,6 +341,7 @@ __global__ void __launch_bounds__(256) k_prep(const __grid_constant__ PrepParams
       nrm2 += __shfl_xor_sync(0xffffffffu, nrm2, o);
       vsq += __shfl_xor_sync(0xffffffffu, vsq, o);
     }
+    big = __any_sync(0xffffffffu, big);
     float cabs = 0.f;
     if (P.kind != CF_SCORE_DOT && lane == 0) {   // the two augmentation columns
       float c_hi = 0.f, c_lo = 0.f;
@@ -348,13 +351,13 @@ __global__ void __launch_bounds__(256) k_prep(const __grid_constant__ PrepParams
           c_lo = 1.f;
         } else {
           const float c = P.kind == CF_SCORE_DOT_BIAS ? P.bias[src_row] : -vsq;
-          c_hi = __bfloat162float(__float2bfloat16_rn(c));
+          c_hi = __half2float(__float2half_rn(c));
           c_lo = c - c_hi;
           cabs = fabsf(c);
         }
       }
-      out[P.d] = __float2bfloat16_rn(c_hi);
-      out[P.d + 1] = __float2bfloat16_rn(c_lo);
+      out[P.d] = __float2half_rn(c_hi);
+      out[P.d + 1] = __float2half_rn(c_lo);
     }
     if (lane == 0) {
       const float nrm = sqrtf(nrm2);   // norm of the d "main" columns (query: after the x2 of the CML form)
@@ -362,13 +365,15 @@ __global__ void __launch_bounds__(256) k_prep(const __grid_constant__ PrepParams
         if (valid) {   // non-negative floats order like ints
           atomicMax(reinterpret_cast<int*>(P.bmax), __float_as_int(nrm));
           atomicMax(reinterpret_cast<int*>(P.bmax) + 1, __float_as_int(cabs));
+          if (big || !(cabs < 65000.f)) atomicMax(reinterpret_cast<int*>(P.bmax) + 2, __float_as_int(1.f));
         }
       } else {
-        // main columns: both operands rounded to bf16 (rel. 2^-9 each): |err| <= (2^-8 + 2^-18) sum|a_k b_k| <= .. |a||b|;
-        // augmentation: c = hi + lo with lo rounded to bf16: |err| <= 2^-18 |c| (charged 2^-16); x1.02 + 1e-6 covers the
-        // fp32 accumulation of <= 256 products in the tensor core.
-        const float e = 0.0039102f * nrm * P.bmax[0] * 1.02f + 1.53e-5f * P.bmax[1] + 1e-6f;
-        const float e2 = valid ? 2.f * e : 0.f;
+        // Operands are rounded to fp16 (11-bit significand): |dx| <= 2^-11 |x| in the normal range, <= 2^-25 below it.
+        // main columns: |err| <= (2^-10 + 2^-22) |a||b| + 2^-25 sqrt(Kp) (|a| + |b|); augmentation: c = hi + lo with lo
+        // rounded to fp16: |err| <= 2^-22 |c| (charged 2^-20); x1.02 + 1e-6 covers the fp32 accumulation in the tensor core.
+        const float e = 0.00097680f * nrm * P.bmax[0] * 1.02f + 2.98e-8f * sqrtf((float)P.Kp) * (nrm + P.bmax[0]) +
+                        9.6e-7f * P.bmax[1] + 1e-6f;
+        const float e2 = valid ? ((big || P.bmax[2] > 0.f) ? INFINITY : 2.f * e) : 0.f;   // inf -> row goes to the exact kernel
         P.eps2[r] = e2;
         if (P.stats && valid) {
           atomicMax(P.stats + 2, __float_as_int(e2));
@@ -501,7 +506,7 @@ int make_map(CUtensorMap* tm, void* base, long long rows, int Kp) {
   const cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
   const cuuint32_t box[2] = {TC_KCH, TC_M};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CF_CHECK_ARG(r == CUDA_SUCCESS, "cf_topk_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
   return 0;
@@ -580,8 +585,8 @@ extern "C" int cf_topk_tc(const cf_topk_args* a, void* workspace, int64_t worksp
   if (int rc = plan_tc(a, &p)) return rc;
   CF_CHECK_ARG(workspace_bytes >= (int64_t)p.total, "cf_topk_tc: workspace %lld < required %lld bytes", (long long)workspace_bytes, (long long)p.total);
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
-  __nv_bfloat16* Vb = reinterpret_cast<__nv_bfloat16*>(ws + p.off_vb);
-  __nv_bfloat16* Qb = reinterpret_cast<__nv_bfloat16*>(ws + p.off_qb);
+  __half* Vb = reinterpret_cast<__half*>(ws + p.off_vb);
+  __half* Qb = reinterpret_cast<__half*>(ws + p.off_qb);
   float* eps2 = reinterpret_cast<float*>(ws + p.off_eps);
   float* cval = reinterpret_cast<float*>(ws + p.off_cval);
   int32_t* cidx = reinterpret_cast<int32_t*>(ws + p.off_cidx);

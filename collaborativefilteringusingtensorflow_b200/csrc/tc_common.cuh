@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace tc {
@@ -88,7 +89,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                               // SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M x N
+// kind::f16 instruction descriptors: D = f32, A = B = bf16 (format 1) or fp16 (format 0), both K-major, M x N
+__device__ __forceinline__ uint32_t umma_idesc_fp16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }

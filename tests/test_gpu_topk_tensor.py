@@ -1,5 +1,5 @@
 """Tensor-core top-K (tcgen05 / TMA candidate pass + exact re-rank) == the exact fp64 kernel, bit for bit, and its raw
-bf16 GEMM scores match a torch matmul of the bf16-rounded operands."""
+fp16 GEMM scores match a torch matmul of the fp16-rounded operands."""
 import numpy as np
 import pytest
 
@@ -24,14 +24,14 @@ def _train_csr(rng, nu, ni, deg, device):
 
 
 @pytest.mark.parametrize('d', [128, 100, 64])
-def test_raw_gemm_scores_match_torch_bf16(d):
+def test_raw_gemm_scores_match_torch_fp16(d):
     import torch
     nu, ni = 300, 1000
     m = _model('bpr', nu, ni, d)
     users = torch.arange(0, nu, dtype=torch.int32, device=m.device)
     _, _, dbg = m.engine.topk(users, 10, None, return_values=True, method='tensor', debug_scores=True)
-    U = m.engine.U[:, :d].to(torch.bfloat16).float()
-    V = m.engine.V[:, :d].to(torch.bfloat16).float()
+    U = m.engine.U[:, :d].to(torch.float16).float()
+    V = m.engine.V[:, :d].to(torch.float16).float()
     want = U @ V.T
     got = dbg[:, :ni]
     assert torch.allclose(got, want, rtol=1e-4, atol=1e-5), float((got - want).abs().max())
@@ -69,3 +69,15 @@ def test_degenerate_scores_fall_back_to_exact_rows():
     users = torch.arange(nu, dtype=torch.int32, device=m.device)
     ti = m.engine.topk(users, K, None, method='tensor')
     assert torch.equal(ti, torch.arange(K, dtype=torch.int32, device=m.device).expand(nu, K))
+
+
+def test_values_outside_fp16_range_fall_back_to_exact():
+    import torch
+    nu, ni, d, K = 300, 3000, 64, 10
+    m = _model('bpr', nu, ni, d)
+    with torch.no_grad():
+        m.engine.V[7, 3] = 1e6          # not representable in fp16
+    users = torch.arange(nu, dtype=torch.int32, device=m.device)
+    ei = m.engine.topk(users, K, None, method='exact')
+    ti = m.engine.topk(users, K, None, method='tensor')
+    assert torch.equal(ei, ti) and int(m.engine.tc_stats[0].item()) == nu
