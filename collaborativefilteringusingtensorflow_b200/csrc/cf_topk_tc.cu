@@ -23,6 +23,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -529,8 +530,10 @@ int plan_tc(const cf_topk_args* a, TcPlan* p) {
   p->T_pad = (long long)align_up((size_t)a->T, TC_MT * TC_M);
   p->N_pad = (long long)align_up((size_t)a->n_items, TC_N);
   const long long row_tiles = p->T_pad / (TC_MT * TC_M), n_tiles = p->N_pad / TC_N;
-  int S = (int)((2ll * cf_num_sms() + row_tiles - 1) / row_tiles);   // aim for >= 2 CTAs per SM's worth of work
+  int S = (int)((cf_num_sms() + row_tiles - 1) / row_tiles);   // just enough item splits to give every SM a CTA: each
+                                                               // split restarts its rows' thresholds from -inf
   if (S < 1) S = 1;
+  if (const char* e = getenv("CF_TC_SPLITS")) S = atoi(e) > 0 ? atoi(e) : S;   // tuning knob
   if (S > RR_CAP / TC_CAP) S = RR_CAP / TC_CAP;
   if (S > n_tiles) S = (int)n_tiles;
   p->S = S;

@@ -34,6 +34,9 @@ def run(kind, T, N, d, K=100, method='tensor', reps=3):
 
 
 if __name__ == '__main__':
+    if len(sys.argv) > 1:
+        run(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), reps=int(sys.argv[5]) if len(sys.argv) > 5 else 2)
+        sys.exit(0)
     run('cml', 2048, 500_000, 128)
     run('cml', 37888, 500_000, 128)
     run('bpr', 37888, 500_000, 128)
