@@ -314,6 +314,8 @@ struct PrepParams {
 __global__ void __launch_bounds__(256) k_prep(const __grid_constant__ PrepParams P) {
   const int lane = threadIdx.x & 31;
   const long long nw = (long long)gridDim.x * blockDim.x / 32;
+  float w_nrm = 0.f, w_cabs = 0.f, w_big = 0.f;   // per-warp maxima: one atomic per warp, not one per row (a same-address
+                                                  // atomic per row serialised this kernel)
   for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 32; r < P.n_pad; r += nw) {
     __half* out = P.dst + r * P.Kp;
     float nrm2 = 0.f;
@@ -363,10 +365,10 @@ __global__ void __launch_bounds__(256) k_prep(const __grid_constant__ PrepParams
     if (lane == 0) {
       const float nrm = sqrtf(nrm2);   // norm of the d "main" columns (query: after the x2 of the CML form)
       if (!P.is_query) {
-        if (valid) {   // non-negative floats order like ints
-          atomicMax(reinterpret_cast<int*>(P.bmax), __float_as_int(nrm));
-          atomicMax(reinterpret_cast<int*>(P.bmax) + 1, __float_as_int(cabs));
-          if (big || !(cabs < 65000.f)) atomicMax(reinterpret_cast<int*>(P.bmax) + 2, __float_as_int(1.f));
+        if (valid) {
+          w_nrm = fmaxf(w_nrm, nrm);
+          w_cabs = fmaxf(w_cabs, cabs);
+          if (big || !(cabs < 65000.f)) w_big = 1.f;
         }
       } else {
         // Operands are rounded to fp16 (11-bit significand): |dx| <= 2^-11 |x| in the normal range, <= 2^-25 below it.
@@ -382,6 +384,11 @@ __global__ void __launch_bounds__(256) k_prep(const __grid_constant__ PrepParams
         }
       }
     }
+  }
+  if (!P.is_query && lane == 0) {   // non-negative floats order like ints
+    atomicMax(reinterpret_cast<int*>(P.bmax), __float_as_int(w_nrm));
+    atomicMax(reinterpret_cast<int*>(P.bmax) + 1, __float_as_int(w_cabs));
+    if (w_big > 0.f) atomicMax(reinterpret_cast<int*>(P.bmax) + 2, __float_as_int(1.f));
   }
 }
 
