@@ -141,10 +141,16 @@ class ClockSampler(object):
 
 
 # ---------------------------------------------------------------------------------------------- CPU baseline (oracle)
-def cpu_baseline(wl, B, csr_host, budget_s=20.0, max_steps=8, seed=2026):
-    """Times the numpy restatement of the reference's TF1 step (oracle/steps.py) + its sampler (oracle/samplers.py
-    logic) on this box's host cores: same tables, same B, same W; whole-table clip every step as cml.py:119-129."""
+def cpu_baseline(wl, B, csr_host, budget_s=20.0, max_steps=8, seed=2026, threads=None):
+    """Times the CPU restatement of the reference's TF1 step + its sampler on this box's host cores: same tables, same
+    B, same W; whole-table clip every step as cml.py:119-129.  BPR / CML use the torch port (oracle/steps_torch.py) on
+    all host cores; the numpy restatement (oracle/steps.py, one core) serves GBPR."""
     from oracle import steps
+    import torch
+    use_torch = wl['model'] in ('cml', 'bpr')
+    if use_torch:
+        from oracle import steps_torch
+        torch.set_num_threads(threads or os.cpu_count())
     rng = np.random.default_rng(seed)
     nu, ni, d, W, G = wl['n_users'], wl['n_items'], wl['d'], wl['W'], wl['G']
     indptr, indices, rows = csr_host
@@ -171,16 +177,19 @@ def cpu_baseline(wl, B, csr_host, budget_s=20.0, max_steps=8, seed=2026):
                 break
             negs[bad] = rng.integers(0, ni, int(bad.sum()))
         h_ = wl['hyper']
+        if use_torch and done == 0:
+            tU, tV, taU, taV = (torch.from_numpy(x) for x in (U, V, aU, aV))   # share memory with the numpy tables
         if wl['model'] == 'cml':
-            steps.cml_step(U, V, aU, aV, pairs, negs, h_['lr'], h_['reg_cov'], h_['margin'], h_['use_rank_weight'], h_['clip_norm'])
+            steps_torch.cml_step(tU, tV, taU, taV, torch.from_numpy(pairs), torch.from_numpy(negs), h_['lr'], h_['reg_cov'],
+                                 h_['margin'], h_['use_rank_weight'], h_['clip_norm'])
         elif wl['model'] == 'bpr':
-            steps.bpr_step(U, V, aU, aV, pairs, negs, h_['lr'], h_['reg'])
+            steps_torch.bpr_step(tU, tV, taU, taV, torch.from_numpy(pairs), torch.from_numpy(negs), h_['lr'], h_['reg'])
         elif wl['model'] == 'gbpr':
             group = rng.integers(0, nu, (B, G))
             steps.gbpr_step(U, V, b, aU, aV, ab, pairs, negs, group, h_['lr'], h_['reg'], h_['rho'])
         t_total += time.perf_counter() - t0
         done += 1
-    return done, t_total
+    return done, t_total, (torch.get_num_threads() if use_torch else 1)
 
 
 # ---------------------------------------------------------------------------------------------- main
@@ -335,9 +344,9 @@ def run_ours(args):
     if not args.no_cpu_baseline:
         csr_host = (csr.indptr.cpu().numpy(), csr.indices.cpu().numpy(), csr.rows.cpu().numpy())
         Bc = min(B, args.cpu_batch)
-        n_cpu, t_cpu = cpu_baseline(wl, Bc, csr_host, budget_s=args.cpu_budget)
-        cpub = dict(value=n_cpu * Bc * wl['W'] / t_cpu, unit='triple updates/s', cores=1, kind='port',
-                    sample='%d minibatches of B=%d pairs x W=%d (numpy oracle restatement of the TF1 step incl. '
+        n_cpu, t_cpu, cores = cpu_baseline(wl, Bc, csr_host, budget_s=args.cpu_budget)
+        cpub = dict(value=n_cpu * Bc * wl['W'] / t_cpu, unit='triple updates/s', cores=cores, kind='port',
+                    sample='%d minibatches of B=%d pairs x W=%d (torch-CPU oracle port of the TF1 step incl. '
                            'whole-table clip + numpy rejection sampler), %.1f s; host has %d cores'
                            % (n_cpu, Bc, wl['W'], t_cpu, os.cpu_count()))
 
@@ -372,11 +381,11 @@ def run_reference(args):
     indices = rng.integers(0, ni, len(rows)).astype(np.int32)
     order = np.lexsort((indices, rows))
     indices = indices[order]
-    steps_done, t = cpu_baseline(wl, B, (indptr, indices, rows), budget_s=max(20.0, args.cpu_budget),
-                                 max_steps=max(1, args.steps))
+    steps_done, t, cores = cpu_baseline(wl, B, (indptr, indices, rows), budget_s=max(20.0, args.cpu_budget),
+                                        max_steps=max(1, args.steps))
     value = steps_done * B * wl['W'] / t
-    cb = dict(value=value, unit='triple updates/s', cores=1, kind='port',
-              sample='%d minibatches of B=%d pairs x W=%d, numpy oracle port of the TF1 step (TensorFlow not installable)'
+    cb = dict(value=value, unit='triple updates/s', cores=cores, kind='port',
+              sample='%d minibatches of B=%d pairs x W=%d, torch-CPU oracle port of the TF1 step on all host cores (TensorFlow not installable)'
                      % (steps_done, B, wl['W']))
     print(json.dumps(dict(impl='reference', metric='triple updates/s (fused pairwise-ranking step incl. sampling) @d=%d' % wl['d'],
                           value=value, unit='triple updates/s', n_gpus=args.gpus, steps=steps_done, warmup=0,

@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libcf_b200.so')
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 # enums of cf_b200.h
 MODEL_BPR, MODEL_CML, MODEL_GBPR, MODEL_WRMF = 0, 1, 2, 3
@@ -94,6 +94,9 @@ _SIGNATURES = {
     'cf_topk_merge': (C.c_int, [_p, _p, C.c_int32, C.c_int32, C.c_int32, _p, _p, _p]),
     'cf_als_workspace_bytes': (C.c_int64, [C.c_int64]),
     'cf_als_half_sweep': (C.c_int, [C.POINTER(AlsArgs), _p]),
+    'cf_parse_triplets': (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.POINTER(C.c_int64)),
+                                  C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.POINTER(C.c_double))]),
+    'cf_free_host': (None, [_p]),
     'cf_rank_metrics': (C.c_int, [_p, C.c_int32, C.c_int32, C.c_int32, _p, _p, _p, _p]),
 }
 

@@ -9,6 +9,27 @@ from .Util import split_row
 
 
 def loadTriplets(inFilePath):
+    """(users, items, ratings) of every 2- or 3-field line, parsed by the native one-pass parser (cf_parse_triplets)."""
+    import ctypes as C
+    from .. import _lib
+    lib = _lib.lib()
+    n = C.c_int64(0)
+    pu, pi, pr = C.POINTER(C.c_int64)(), C.POINTER(C.c_int64)(), C.POINTER(C.c_double)()
+    _lib.check(lib.cf_parse_triplets(str(inFilePath).encode(), C.byref(n), C.byref(pu), C.byref(pi), C.byref(pr)),
+               'cf_parse_triplets')
+    try:
+        k = n.value
+        u = np.ctypeslib.as_array(pu, shape=(k,)).copy() if k else np.zeros(0, np.int64)
+        i = np.ctypeslib.as_array(pi, shape=(k,)).copy() if k else np.zeros(0, np.int64)
+        r = np.ctypeslib.as_array(pr, shape=(k,)).copy() if k else np.zeros(0, np.float64)
+    finally:
+        for p in (pu, pi, pr):
+            lib.cf_free_host(C.cast(p, C.c_void_p))
+    return u, i, r
+
+
+def _loadTriplets_python(inFilePath):
+    """The reference's per-line loop, kept for the parser's own test."""
     us, is_, rs = [], [], []
     with open(inFilePath, 'r') as infile:
         for line in infile:

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CF_ABI_VERSION 8
+#define CF_ABI_VERSION 9
 
 /* models */
 enum { CF_MODEL_BPR = 0, CF_MODEL_CML = 1, CF_MODEL_GBPR = 2, CF_MODEL_WRMF = 3 };
@@ -277,6 +277,15 @@ int cf_als_half_sweep(const cf_als_args* args, void* stream);
  * ------------------------------------------------------------------------------------------------ */
 int cf_rank_metrics(const int32_t* pred, int32_t T, int32_t ldp, int32_t k, const int64_t* truth_indptr,
                     const int32_t* truth_indices, double* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-side loader.  Replaces the per-line Python loop of utils/IOUtil.py:7-16 (`loadSparseR`): parses
+ * "u<sep>i[<sep>rating]" lines (separators ',' ';' or whitespace, Util.py:5-11) into host arrays allocated with malloc
+ * (release each with cf_free_host).  Lines with another number of fields are skipped, like the reference.
+ * ------------------------------------------------------------------------------------------------ */
+int cf_parse_triplets(const char* path_host, int64_t* n_out_host, int64_t** users_out_host, int64_t** items_out_host,
+                      double** ratings_out_host);
+void cf_free_host(void* p_host);
 
 #ifdef __cplusplus
 }

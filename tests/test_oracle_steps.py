@@ -106,3 +106,26 @@ def test_wrmf_oracle_matches_autograd(step_golden):
 def test_truncated_normal_bounds():
     x = steps.truncated_normal(np.random.default_rng(0), (1000, 8), 0.0, 0.1)
     assert x.dtype == np.float32 and np.abs(x).max() <= 0.2 + 1e-7 and 0.07 < x.std() < 0.1
+
+
+def test_torch_multithreaded_port_matches_numpy_oracle():
+    """oracle/steps_torch.py (bench.py's all-cores CPU baseline) == oracle/steps.py."""
+    import torch
+    from oracle import steps_torch
+    rng = np.random.default_rng(3)
+    nu, ni, d, B, W = 200, 300, 32, 256, 4
+    U0 = (0.05 * rng.standard_normal((nu, d))).astype(np.float32)
+    V0 = (0.05 * rng.standard_normal((ni, d))).astype(np.float32)
+    pairs = np.stack([rng.integers(0, nu, B), rng.integers(0, ni, B)], 1)
+    negs = rng.integers(0, ni, (B, W))
+    for kind in ('bpr', 'cml'):
+        a = [U0.copy(), V0.copy(), np.full_like(U0, 0.1), np.full_like(V0, 0.1)]
+        b = [torch.from_numpy(x.copy()) for x in a]
+        if kind == 'bpr':
+            steps.bpr_step(a[0], a[1], a[2], a[3], pairs, negs, 0.1, 0.05)
+            steps_torch.bpr_step(b[0], b[1], b[2], b[3], torch.from_numpy(pairs), torch.from_numpy(negs), 0.1, 0.05)
+        else:
+            steps.cml_step(a[0], a[1], a[2], a[3], pairs, negs, 0.1, 1.0, 1.0, True, 1.0)
+            steps_torch.cml_step(b[0], b[1], b[2], b[3], torch.from_numpy(pairs), torch.from_numpy(negs), 0.1, 1.0, 1.0, True, 1.0)
+        for x, y in zip(a, b):
+            np.testing.assert_allclose(y.numpy(), x, rtol=2e-5, atol=2e-6)
