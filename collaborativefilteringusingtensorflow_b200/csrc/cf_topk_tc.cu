@@ -171,6 +171,14 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     // ================================================================== MMA issuer (one thread)
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_fp16(TC_M, TC_N);
+      // Descriptors are precomputed: the single issuing thread must spend only a few instructions per MMA (building two
+      // 64-bit descriptors from scratch took ~30 dependent instructions = ~3x the 64-cycle MMA itself and starved the
+      // tensor pipe).  Within the 256 KB shared window the 14-bit address field never carries, so an offset is one add.
+      uint64_t a0[TC_MT];
+#pragma unroll
+      for (int mt = 0; mt < TC_MT; ++mt) a0[mt] = umma_desc_sw128(smem_u32(sA + (size_t)mt * KC * TC_CHUNK_BYTES));
+      const uint64_t b00 = umma_desc_sw128(smem_u32(sB));
+      const uint64_t b_stage_step = (uint64_t)(b_stage_bytes >> 4);
       mbar_wait(a_full, 0u);
       for (int t = 0; t < nt; ++t) {
         const int st = t % P.stages;
@@ -179,14 +187,19 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
         mbar_wait(tempty + acc, ((uint32_t)(t >> 1) & 1u) ^ 1u);
         mbar_wait(full + st, ph);
         tc_fence_after();
+        const uint64_t b0 = b00 + (uint64_t)st * b_stage_step;
+#pragma unroll
         for (int mt = 0; mt < TC_MT; ++mt) {
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * (TC_MT * TC_N) + mt * TC_N);
-          for (int kc = 0; kc < KC; ++kc) {
-            const uint32_t a_addr = smem_u32(sA + (size_t)(mt * KC + kc) * TC_CHUNK_BYTES);
-            const uint32_t b_addr = smem_u32(sB + (size_t)st * b_stage_bytes + (size_t)kc * TC_CHUNK_BYTES);
 #pragma unroll
-            for (int k = 0; k < TC_KCH / 16; ++k)   // UMMA_K = 16 bf16 = 32 bytes inside the 128-byte swizzle atom
-              tc_mma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc, (kc | k) ? 1u : 0u);
+          for (int kc = 0; kc < 4; ++kc) {
+            if (kc < KC) {
+#pragma unroll
+              for (int k = 0; k < TC_KCH / 16; ++k) {   // UMMA_K = 16 halfs = 32 bytes inside the 128-byte swizzle atom
+                const uint64_t off = (uint64_t)((kc * TC_CHUNK_BYTES + k * 32) >> 4);
+                tc_mma_bf16(d_tmem, a0[mt] + off, b0 + off, idesc, (kc | k) ? 1u : 0u);
+              }
+            }
           }
         }
         tc_commit(empty + st);     // smem stage free once these MMAs have read it
