@@ -157,14 +157,15 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
       for (int mt = 0; mt < TC_MT; ++mt)
         for (int kc = 0; kc < KC; ++kc)
           tma_load_2d(&tmQ, a_full, sA + (size_t)(mt * KC + kc) * TC_CHUNK_BYTES, kc * TC_KCH, row0 + mt * TC_M);
+      int st = 0;
+      uint32_t ph = 0u;
       for (int t = 0; t < nt; ++t) {
-        const int st = t % P.stages;
-        const uint32_t ph = (uint32_t)(t / P.stages) & 1u;
         mbar_wait(empty + st, ph ^ 1u);
         mbar_arrive_expect_tx(full + st, (uint32_t)b_stage_bytes);
         for (int kc = 0; kc < KC; ++kc)
           tma_load_2d(&tmV, full + st, sB + (size_t)st * b_stage_bytes + (size_t)kc * TC_CHUNK_BYTES, kc * TC_KCH,
                       (tile_lo + t) * TC_N);
+        if (++st == P.stages) { st = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -180,14 +181,14 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
       const uint64_t b00 = umma_desc_sw128(smem_u32(sB));
       const uint64_t b_stage_step = (uint64_t)(b_stage_bytes >> 4);
       mbar_wait(a_full, 0u);
+      int st = 0;
+      uint32_t ph = 0u;
+      uint64_t b0 = b00;
       for (int t = 0; t < nt; ++t) {
-        const int st = t % P.stages;
-        const uint32_t ph = (uint32_t)(t / P.stages) & 1u;
         const int acc = t & 1;
         mbar_wait(tempty + acc, ((uint32_t)(t >> 1) & 1u) ^ 1u);
         mbar_wait(full + st, ph);
         tc_fence_after();
-        const uint64_t b0 = b00 + (uint64_t)st * b_stage_step;
 #pragma unroll
         for (int mt = 0; mt < TC_MT; ++mt) {
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * (TC_MT * TC_N) + mt * TC_N);
@@ -204,6 +205,8 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
         }
         tc_commit(empty + st);     // smem stage free once these MMAs have read it
         tc_commit(tfull + acc);    // accumulator ready for the epilogue
+        b0 += b_stage_step;
+        if (++st == P.stages) { st = 0; ph ^= 1u; b0 = b00; }
       }
     }
   } else if (warp >= 4) {
