@@ -410,6 +410,7 @@ def main():
     ap.add_argument('--topk-c5-items', type=int, default=10_000_000, help='also time top-100 over a configs[4]-sized catalogue (0 = skip)')
     ap.add_argument('--cpu-budget', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--grow-catalogue', action='store_true', help='N > 1: n_items x N items in total instead of a fixed catalogue')
     ap.add_argument('--phases', action='store_true', help='N > 1: also report per-phase times of the sharded step')
     args = ap.parse_args()
     if args.impl == 'reference':

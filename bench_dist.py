@@ -1,6 +1,7 @@
-"""bench.py's N > 1 arm: weak scaling of the N=1 workload per GPU (same users, interactions and minibatch per rank; the item
-catalogue grows with N so every rank owns the same number of item rows), users range-sharded, items sharded by item % N,
-per-minibatch NCCL all-to-all of requested item rows and their gradients."""
+"""bench.py's N > 1 arm: weak scaling of the N=1 workload (same users, interactions and minibatch PER GPU; the item
+catalogue keeps its global size and is row-sharded, like BASELINE.json configs[4] keeps 10 M items for 8 x 12.5 M users):
+users range-sharded, items sharded by item % N, per-minibatch NCCL all-to-all of requested item rows and their gradients
+(SURVEY.md 8e).  `--grow-catalogue` instead multiplies the catalogue by N (every rank owns n_items rows)."""
 import json
 import os
 import time
@@ -15,7 +16,7 @@ def run_distributed(args, rank, world, device):
     wl = dict(B_.WORKLOADS[args.workload])
     if wl['model'] not in ('cml', 'bpr'):
         raise SystemExit('the sharded path supports the cml / bpr workloads')
-    n_items_global = wl['n_items'] * world
+    n_items_global = wl['n_items'] * (world if getattr(args, 'grow_catalogue', False) else 1)
     B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
     pk = B_.peaks()
     csr = B_.synth_interactions(wl['n_users'], n_items_global, wl['nnz'], 2026 + rank, device)
@@ -79,8 +80,9 @@ def run_distributed(args, rank, world, device):
     out = dict(metric='triple updates/s (fused pairwise-ranking step incl. on-device sampling) @d=%d' % wl['d'],
                value=units / (ms * 1e-3), unit='triple updates/s', n_gpus=world, steps=K, warmup=Wm, ms_per_step=ms / K,
                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
-               config=dict(workload=wl['desc'] + ' PER GPU; items = %d x %d GPUs, users range-sharded, items by item %% N, '
-                           'NCCL all-to-all of item rows + gradients per minibatch' % (wl['n_items'], world),
+               config=dict(workload=wl['desc'] + ' -- users, interactions and minibatch PER GPU; %d items in total, row-sharded by '
+                           'item %% N; users range-sharded; NCCL all-to-all of item rows + gradients per minibatch'
+                           % n_items_global,
                            batch_pairs_per_gpu=B, negatives=wl['W'], optimizer=args.optimizer, update='sync',
                            l2='inputs larger than L2 (random rows of GB-sized tables)'),
                gpu_launches=launches,
