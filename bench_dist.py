@@ -65,6 +65,42 @@ def run_distributed(args, rank, world, device):
     ms2 = torch.tensor([e0.elapsed_time(e1)], device=device)
     dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     ms2 = float(ms2.item())
+    # ---- evaluation: item-sharded full-catalogue top-100 of rank 0's users, merged with an all-gather
+    topk = None
+    if args.topk_users > 0:
+        from collaborativefilteringusingtensorflow_b200.dist import distributed_topk, shard_mask_csr
+        from collaborativefilteringusingtensorflow_b200.sparse import DeviceCSR
+        Tq = min(args.topk_users, wl['n_users'])
+        eng = model.engine
+        # the query users live on rank 0: broadcast their embeddings and their training rows (global item ids)
+        q = eng.U[:Tq].clone() if rank == 0 else torch.empty(Tq, eng.ld, device=device)
+        dist.broadcast(q, 0)
+        sub = csr.select_rows(torch.arange(Tq, device=device)) if rank == 0 else None
+        meta = torch.tensor([sub.nnz if rank == 0 else 0], device=device)
+        dist.broadcast(meta, 0)
+        nnz = int(meta.item())
+        ind = sub.indices if rank == 0 else torch.empty(nnz, dtype=torch.int32, device=device)
+        rws = sub.rows if rank == 0 else torch.empty(nnz, dtype=torch.int32, device=device)
+        ptr = sub.indptr if rank == 0 else torch.empty(Tq + 1, dtype=torch.int64, device=device)
+        for t in (ind, rws, ptr):
+            dist.broadcast(t, 0)
+        mask = shard_mask_csr(DeviceCSR(ptr, ind, rws, None, (Tq, n_items_global)), world, rank)
+        distributed_topk(eng, q[:1024], 100, shard_mask_csr(DeviceCSR(ptr[:1025].clone(), ind[:int(ptr[1024])], rws[:int(ptr[1024])],
+                                                                      None, (1024, n_items_global)), world, rank), world, rank, method='tensor')
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        gi, gv = distributed_topk(eng, q, 100, mask, world, rank, method='tensor')
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        tms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        tms = float(tms.item())
+        fl = 2.0 * n_items_global * wl['d'] * Tq
+        topk = dict(metric='users/s full-catalog top-100 (mask train items), items sharded over %d GPUs, all-gather merge' % world,
+                    value=Tq / (tms * 1e-3), users=Tq, n_items=n_items_global, ms=tms, tflops_aggregate=fl / (tms * 1e-3) / 1e12,
+                    fallback_rows_rank0=int(eng.tc_stats[0].item()))
     phases = None
     if args.phases:
         tr.phase_ms = {}
@@ -93,5 +129,5 @@ def run_distributed(args, rank, world, device):
                              peak_source=pk['source']),
                nvlink=dict(bytes_sent_per_step_per_gpu=sent, achieved_GBs=sent / (ms / K * 1e-3) / 1e9,
                            peak_GBs_per_direction=770.0, note='rows out + gradients back + ids; measured peer copy 770 GB/s/dir'),
-               phases_ms_per_step=phases, cpu_baseline=None, clocks=clocks, loss_first_last=[float(losses[0]), float(losses[-1])])
+               phases_ms_per_step=phases, topk=topk, cpu_baseline=None, clocks=clocks, loss_first_last=[float(losses[0]), float(losses[-1])])
     print(json.dumps(out))

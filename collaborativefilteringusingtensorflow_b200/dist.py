@@ -261,7 +261,20 @@ class DistributedTrainer(object):
         return torch.cat(out) if want_loss else None
 
 
-def distributed_topk(engine, query_rows, K, train_local_csr, world, rank, group=None):
+def shard_mask_csr(sub_csr, world, rank):
+    """Rows of ``sub_csr`` (global item ids) restricted to the items this rank owns, in LOCAL ids (item // world)."""
+    torch = _lib.require_cuda()
+    from .sparse import DeviceCSR
+    keep = (sub_csr.indices % world) == rank
+    rows = sub_csr.rows[keep]
+    cols = (sub_csr.indices[keep] // world).to(torch.int32)
+    counts = torch.bincount(rows.to(torch.int64), minlength=sub_csr.shape[0])
+    indptr = torch.zeros(sub_csr.shape[0] + 1, dtype=torch.int64, device=rows.device)
+    indptr[1:] = torch.cumsum(counts, 0)
+    return DeviceCSR(indptr, cols.contiguous(), rows.contiguous(), None, (sub_csr.shape[0], item_shard_rows(sub_csr.shape[1], world, rank)))
+
+
+def distributed_topk(engine, query_rows, K, train_local_csr, world, rank, group=None, method='auto'):
     """query_rows: [T, ld] embeddings of the query users (already all-gathered / replicated on every rank).
     engine.V is this rank's item shard (local row j = global item j * world + rank); train_local_csr masks in LOCAL item
     ids (row t = query t).  Returns the merged global top-K ids [T, K] (int32) and scores on every rank."""
@@ -272,7 +285,7 @@ def distributed_topk(engine, query_rows, K, train_local_csr, world, rank, group=
     saved_U, saved_n = engine.U, engine.n_users
     engine.U, engine.n_users = query_rows.contiguous(), T
     try:
-        idx, val = engine.topk(None, K, train_local_csr, return_values=True)
+        idx, val = engine.topk(None, K, train_local_csr, return_values=True, method=method)
     finally:
         engine.U, engine.n_users = saved_U, saved_n
     gidx = torch.where(idx >= 0, idx * world + rank, idx)
