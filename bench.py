@@ -278,8 +278,15 @@ def run_ours(args):
     # The algorithmic bytes of a minibatch (4 * R * 4d per pair) are moved by the fused step kernel and, for
     # rows that occur more than once, by the staged-apply kernel that follows it: the roofline is quoted on their sum.
     achieved = bpp * B / ((step_ms + apply_ms) * 1e-3) / 1e9
+    # DRAM bytes per launch (k_step + k_apply_staged) from the committed `ncu --set full` capture of this exact configuration
+    traffic = None
+    if args.workload == 'c2' and B == (1 << 20) and args.optimizer == 'adagrad' and args.update == 'sync':
+        traffic = (6.952 + 3.395 + 1.177 + 1.058) * 1e9     # profiles/r1_ncu_full_c2_cml_B1M.txt
     roofline = dict(bound='hbm', kernel='cfstep::k_step<%s> + cfstep::k_apply_staged' % wl['model'], achieved=achieved,
-                    peak=pk['hbm'], unit='GB/s', frac=achieved / pk['hbm'], traffic=None, peak_source=pk['source'],
+                    peak=pk['hbm'], unit='GB/s', frac=achieved / pk['hbm'], traffic=traffic,
+                    traffic_source='profiles/r1_ncu_full_c2_cml_B1M.txt (dram__bytes_read + write; below the algorithmic bytes '
+                                   'because rows that occur more than once in a minibatch share their traffic)' if traffic else None,
+                    peak_source=pk['source'],
                     k_step_only_GBs=bpp * B / (step_ms * 1e-3) / 1e9,
                     algorithmic_bytes_per_launch=bpp * B, kernel_ms_per_launch=step_ms,
                     count_kernel_ms_per_launch=prof['count_ms'] / prof['n_batches'],

@@ -12,6 +12,7 @@
 //   k_als_solve    one CTA per row: A = G + reg I + (weight-1) sum y y^T in shared memory (fp32), in-place Cholesky,
 //                  forward/back substitution, x_u written to X.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -212,6 +213,174 @@ __global__ void __launch_bounds__(256) k_als_solve(const __grid_constant__ Solve
   }
 }
 
+// ---- register-blocked variant (the one that is launched): the 128 x 128 system is tiled 16 x 16, thread (ty, tx) owns the
+// 8 x 8 block (rows 8ty.., columns 8tx..) of the lower triangle in REGISTERS.  Building A costs 64 FMAs per 16 shared
+// loads per gathered row (vs 1 FMA per 2 loads element-wise), and the right-looking blocked Cholesky needs 3 barriers
+// per block column (48 per matrix, vs 384 column-wise).  Dimensions d < 128 are padded: the padding block of A is reg * I,
+// which decouples and yields zeros.
+constexpr int BS = 8, NBK = ALS_D / BS;
+
+__global__ void __launch_bounds__(256, 2) k_als_solve_blocked(const __grid_constant__ SolveParams P) {
+  extern __shared__ float sm[];
+  constexpr int lda = ALS_D + 1;
+  float* L = sm;                          // [128, 129] the factor, written once for the triangular solves
+  float* panel = L + ALS_D * lda;         // [16][64] current block column  L_ik (row-major 8 x 8 each)
+  float* rows = panel + NBK * 64;         // [8][128] gathered y rows
+  float* b = rows + 8 * ALS_D;            // [128]
+  float* diag = b + ALS_D;                // [64] factored diagonal block
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const bool lower = ty >= tx;
+  const int d = P.d;
+  for (long long u = blockIdx.x; u < P.n_x; u += gridDim.x) {
+    float a[BS][BS];
+    if (lower) {
+#pragma unroll
+      for (int i = 0; i < BS; ++i)
+#pragma unroll
+        for (int j = 0; j < BS; ++j) {
+          const int gi = BS * ty + i, gj = BS * tx + j;
+          a[i][j] = ((gi < d && gj < d) ? __ldg(P.G + gi * ALS_D + gj) : 0.f) + (gi == gj ? P.reg : 0.f);
+        }
+    }
+    if (tid < ALS_D) b[tid] = 0.f;
+    const long long lo = P.indptr[u], hi = P.indptr[u + 1];
+    const float wm1 = P.weight - 1.f;
+    for (long long e0 = lo; e0 < hi; e0 += 8) {
+      const int nb = (int)min(8ll, hi - e0);
+      __syncthreads();
+      for (int r = 0; r < nb; ++r) {
+        const float* yr = P.Y + (long long)P.indices[e0 + r] * P.ldy;
+        if (tid < ALS_D) rows[r * ALS_D + tid] = tid < d ? yr[tid] : 0.f;
+      }
+      __syncthreads();
+      if (lower && wm1 != 0.f) {
+        for (int r = 0; r < nb; ++r) {
+          float yi[BS], yj[BS];
+#pragma unroll
+          for (int i = 0; i < BS; ++i) {
+            yi[i] = wm1 * rows[r * ALS_D + BS * ty + i];
+            yj[i] = rows[r * ALS_D + BS * tx + i];
+          }
+#pragma unroll
+          for (int i = 0; i < BS; ++i)
+#pragma unroll
+            for (int j = 0; j < BS; ++j) a[i][j] = fmaf(yi[i], yj[j], a[i][j]);
+        }
+      }
+      if (tid < ALS_D) {
+        float acc = 0.f;
+        for (int r = 0; r < nb; ++r) acc += rows[r * ALS_D + tid];
+        b[tid] = fmaf(P.weight, acc, b[tid]);
+      }
+    }
+    // ---- blocked right-looking Cholesky
+    for (int kb = 0; kb < NBK; ++kb) {
+      if (ty == kb && tx == kb) {   // factor the diagonal block in registers
+#pragma unroll
+        for (int k = 0; k < BS; ++k) {
+          a[k][k] = sqrtf(fmaxf(a[k][k], 1e-30f));
+          const float inv = 1.f / a[k][k];
+#pragma unroll
+          for (int i = k + 1; i < BS; ++i) a[i][k] *= inv;
+#pragma unroll
+          for (int i = k + 1; i < BS; ++i)
+#pragma unroll
+            for (int j = k + 1; j <= i; ++j) a[i][j] = fmaf(-a[i][k], a[j][k], a[i][j]);
+        }
+#pragma unroll
+        for (int i = 0; i < BS; ++i)
+#pragma unroll
+          for (int j = 0; j < BS; ++j) {
+            diag[i * BS + j] = j <= i ? a[i][j] : 0.f;
+            L[(BS * kb + i) * lda + BS * kb + j] = j <= i ? a[i][j] : 0.f;
+          }
+      }
+      __syncthreads();
+      if (tx == kb && ty > kb) {    // L_ik = A_ik L_kk^-T  (each row of the block: forward substitution with L_kk)
+#pragma unroll
+        for (int i = 0; i < BS; ++i) {
+#pragma unroll
+          for (int j = 0; j < BS; ++j) {
+            float v = a[i][j];
+#pragma unroll
+            for (int q = 0; q < j; ++q) v = fmaf(-a[i][q], diag[j * BS + q], v);
+            a[i][j] = v / diag[j * BS + j];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < BS; ++i)
+#pragma unroll
+          for (int j = 0; j < BS; ++j) {
+            panel[ty * 64 + i * BS + j] = a[i][j];
+            L[(BS * ty + i) * lda + BS * kb + j] = a[i][j];
+          }
+      }
+      __syncthreads();
+      if (lower && tx > kb) {       // A_ij -= L_ik L_jk^T
+        const float* li = panel + ty * 64;
+        const float* lj = panel + tx * 64;
+#pragma unroll
+        for (int q = 0; q < BS; ++q) {
+          float ci[BS], cj[BS];
+#pragma unroll
+          for (int i = 0; i < BS; ++i) {
+            ci[i] = li[i * BS + q];
+            cj[i] = lj[i * BS + q];
+          }
+#pragma unroll
+          for (int i = 0; i < BS; ++i)
+#pragma unroll
+            for (int j = 0; j < BS; ++j) a[i][j] = fmaf(-ci[i], cj[j], a[i][j]);
+        }
+      }
+      __syncthreads();
+    }
+    // ---- blocked substitutions: L z = b then L^T x = z.  Per block: thread 0 solves the 8 x 8 triangle, then 128
+    // threads (one per row) eliminate the solved block from the remaining right-hand side.
+    for (int kb = 0; kb < NBK; ++kb) {
+      if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < BS; ++k) {
+          float v = b[BS * kb + k];
+#pragma unroll
+          for (int q = 0; q < k; ++q) v = fmaf(-L[(BS * kb + k) * lda + BS * kb + q], b[BS * kb + q], v);
+          b[BS * kb + k] = v / L[(BS * kb + k) * lda + BS * kb + k];
+        }
+      }
+      __syncthreads();
+      if (tid < ALS_D && tid >= BS * (kb + 1)) {
+        float v = b[tid];
+#pragma unroll
+        for (int q = 0; q < BS; ++q) v = fmaf(-L[tid * lda + BS * kb + q], b[BS * kb + q], v);
+        b[tid] = v;
+      }
+      __syncthreads();
+    }
+    for (int kb = NBK - 1; kb >= 0; --kb) {
+      if (tid == 0) {
+#pragma unroll
+        for (int k = BS - 1; k >= 0; --k) {
+          float v = b[BS * kb + k];
+#pragma unroll
+          for (int q = k + 1; q < BS; ++q) v = fmaf(-L[(BS * kb + q) * lda + BS * kb + k], b[BS * kb + q], v);
+          b[BS * kb + k] = v / L[(BS * kb + k) * lda + BS * kb + k];
+        }
+      }
+      __syncthreads();
+      if (tid < BS * kb) {       // x_tid -= sum_q L[kb-block row q][tid] * x_q   (L^T)
+        float v = b[tid];
+#pragma unroll
+        for (int q = 0; q < BS; ++q) v = fmaf(-L[(BS * kb + q) * lda + tid], b[BS * kb + q], v);
+        b[tid] = v;
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+    if (tid < d) P.X[u * P.ldx + tid] = b[tid];
+    __syncthreads();
+  }
+}
+
 typedef CUresult (*encode_tiled_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -270,12 +439,18 @@ extern "C" int cf_als_half_sweep(const cf_als_args* a, void* stream_) {
   SolveParams S;
   S.X = a->X; S.Y = a->Y; S.G = G; S.indptr = (const long long*)a->indptr; S.indices = a->indices;
   S.n_x = a->n_x; S.d = a->d; S.ldx = a->ldx; S.ldy = a->ldy; S.weight = a->weight; S.reg = a->reg;
-  const size_t ssmem = ((size_t)a->d * (a->d + 1) + a->d + 8 * a->d) * 4;
-  CF_CUDA_OK(cudaFuncSetAttribute(k_als_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
   long long sg = a->n_x;
   const long long cap = (long long)cf_num_sms() * 8;
   if (sg > cap) sg = cap;
-  k_als_solve<<<(unsigned)sg, 256, ssmem, stream>>>(S);
+  if (getenv("CF_ALS_COLUMNWISE")) {   // the first, column-wise kernel (kept for A/B measurements)
+    const size_t ssmem = ((size_t)a->d * (a->d + 1) + a->d + 8 * a->d) * 4;
+    CF_CUDA_OK(cudaFuncSetAttribute(k_als_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
+    k_als_solve<<<(unsigned)sg, 256, ssmem, stream>>>(S);
+  } else {
+    const size_t ssmem = ((size_t)ALS_D * (ALS_D + 1) + NBK * 64 + 8 * ALS_D + ALS_D + 64) * 4;
+    CF_CUDA_OK(cudaFuncSetAttribute(k_als_solve_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem));
+    k_als_solve_blocked<<<(unsigned)sg, 256, ssmem, stream>>>(S);
+  }
   CF_CUDA_OK(cudaGetLastError());
   return 0;
 }
