@@ -7,13 +7,14 @@
 // it gathers the u / i / j_1..W (/ g_1..G) rows with 128-bit L2-coherent loads, forms the gradients in
 // registers and commits every row exactly once per occurrence.
 //
-// Minibatch-synchronous semantics (CF_UPDATE_SYNC, the reference's): a counting kernel first records, per
-// table row, how many times it occurs in the minibatch (meta word, low 32 bits) and gives rows that occur
-// more than once a slot in an L2-resident staging buffer.  In the fused kernel a row that occurs once is
-// updated straight from registers (read param + acc, write param + acc: the algorithmic minimum); a row that
-// occurs T > 1 times gets its T gradients red.add-ed into its staging slot and the LAST arriver (meta word,
-// high 32 bits) applies the summed gradient once.  A row is only ever written after every pair that reads it
-// has finished reading, so all gradients are evaluated at pre-update parameters, like TF.
+// Minibatch-synchronous semantics (CF_UPDATE_SYNC, the reference's), three launches per minibatch:
+//   k_count         per table row, how many times it occurs in the minibatch; rows occurring more than once get a slot of an
+//                   L2-resident gradient staging buffer (slot id = occurrence index of the second occurrence: no counter)
+//   k_step          a row that occurs once is updated straight from registers (read param + acc, write param + acc: the
+//                   algorithmic minimum); a row that occurs T > 1 times gets its T gradients red.add-ed into its slot
+//   k_apply_staged  applies every staged (summed) gradient once and returns slot / occurrence word to zero
+// A row is only ever written after every pair that reads it has read it, so all gradients are evaluated at pre-update
+// parameters, like TF.
 #include <math.h>
 
 #include "common.cuh"

@@ -11,8 +11,9 @@
 //      slot's lane
 //   4. a rolled loop over the slots forms each row gradient and either applies it from registers (unique row: read
 //      param + acc, write param + acc -- the algorithmic minimum) or red.adds it into the row's staging slot
-//   5. rows that occur more than once in the minibatch: ONE fence, then each such slot's lane bumps the row's done
-//      counter; whoever completes a row (last arriver) applies the summed gradient.
+//   5. rows that occur more than once in the minibatch are NOT written here: k_apply_staged (next launch) applies each
+//      summed gradient once.  The kernel boundary is the only synchronisation (no fences, no spin, no done counters:
+//      an in-kernel last-arriver protocol with __threadfence() cost 2x at B = 16k).
 // All loops over slots are rolled (the slot's data lives in shared memory / its lane), so the kernel is a few KB of
 // SASS instead of the 80-250 KB of the first, fully unrolled version (which stalled on instruction fetch).
 #pragma once
@@ -137,12 +138,6 @@ __device__ __forceinline__ float group_sum(float x, unsigned gmask) {
   for (int o = LPG / 2; o > 0; o >>= 1) x += __shfl_xor_sync(gmask, x, o);
   return x;
 }
-template <int LPG>
-__device__ __forceinline__ float group_min(float x, unsigned gmask) {
-#pragma unroll
-  for (int o = LPG / 2; o > 0; o >>= 1) x = fminf(x, __shfl_xor_sync(gmask, x, o));
-  return x;
-}
 __device__ __forceinline__ float softplus_neg(float x) {  // -log(sigmoid(x)), bprmf.py:70
   return x > 0.f ? log1pf(__expf(-x)) : (-x + log1pf(__expf(x)));
 }
@@ -259,7 +254,7 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepDev P)
       if (gl == 0) atomicOr(P.counters + 1, CF_FLAG_INDEX_RANGE);
       continue;
     }
-    const int u = __shfl_sync(gmask, my_row, leader), i = __shfl_sync(gmask, my_row, leader + 1);
+    const int i = __shfl_sync(gmask, my_row, leader + 1);
 
     // pair-level quantities carried across tiles
     float S = 0.f;                 // sum_w s_bw (BPR / GBPR)

@@ -1,0 +1,91 @@
+"""The reference's experiment drivers for the four hot-path models, as one module.
+
+Mirrors reference src/models/pl/testbprmf.py:19-125, testcml.py:19-102, testgbprmf.py:19-113 and
+src/models/basic/testwrmf.py:19-96: the same module-level hyper-parameters, the same per-fold worker (load
+``ratings__<fold>_tra.txt`` / ``_tst.txt``, binarise with ``rating > 3``, build the sampler and the model, train, print the
+fold's scores) and the same ``ave`` / ``std`` summary.  The reference wraps every fold in a ``multiprocessing.Pool`` only
+because ``tf.get_variable`` names collide (testbprmf.py:114-117); here folds run in-process.
+
+    python -m collaborativefilteringusingtensorflow_b200.drivers bprmf <dataset_dir>/ 943 1682 [--folds 5] [--max-iter N]
+"""
+import argparse
+
+import numpy as np
+from scipy.sparse import lil_matrix
+
+from .models.basic.models.wrmf import WRMF
+from .models.pl.models.bprmf import BPRMF
+from .models.pl.models.cml import CML
+from .models.pl.models.gbprmf import GBPRMF
+from .samplers import sampler_gbpr, sampler_ranking, sampler_rating
+from .utils.IOUtil import loadSparseR
+from .utils.Util import matBinarize
+
+binarize_threshold = 3
+eval_metrics = ['pre', 'recall', 'map', 'mrr', 'ndcg']
+split_method = 'cv'
+
+# hyper-parameters exactly as the reference drivers set them
+HYPER = {
+    'bprmf': dict(reg=.1, topN=10, n_factors=100, batch_size=100, negSample=1),                                   # testbprmf.py:21-30
+    'cml': dict(margin=1., reg_cov=1., use_rank_weight=True, clip_norm=1.0, topN=10, n_factors=50, batch_size=50,
+                negSample=5),                                                                                     # testcml.py:22-34
+    'gbprmf': dict(gsize=1, rho=.4, reg=.01, topN=100, n_factors=100, batch_size=100, negSample=5),               # testgbprmf.py:23-32
+    'wrmf': dict(weight=2., reg=.1, topN=10, negRatio=1, n_factors=100, batch_size=100),                          # testwrmf.py:22-30
+}
+
+
+def worker(model_name, fold, n_users, n_items, dataset_dir, max_iter=None, seed=None, verbose=True):
+    h = HYPER[model_name]
+    trasR = lil_matrix(matBinarize(loadSparseR(n_users, n_items, dataset_dir + 'ratings__' + str(fold + 1) + '_tra.txt'),
+                                   binarize_threshold))
+    print(dataset_dir.split('/')[-2] + '@%d:' % (fold + 1), trasR.shape, trasR.nnz, '%.2f' % (trasR.nnz / float(trasR.shape[0])))
+    tstsR = lil_matrix(matBinarize(loadSparseR(n_users, n_items, dataset_dir + 'ratings__' + str(fold + 1) + '_tst.txt'),
+                                   binarize_threshold))
+    kw = dict(seed=seed, verbose=verbose)
+    it = {} if max_iter is None else dict(max_iter=max_iter)
+    if model_name == 'bprmf':
+        sampler = sampler_ranking.Sampler(trasR=trasR, n_neg=h['negSample'], batch_size=h['batch_size'], seed=seed or 0)
+        model = BPRMF(n_users, n_items, h['topN'], split_method, eval_metrics, h['reg'], h['n_factors'], h['batch_size'], **it, **kw)
+    elif model_name == 'cml':
+        sampler = sampler_ranking.Sampler(trasR, n_neg=h['negSample'], batch_size=h['batch_size'], seed=seed or 0)
+        model = CML(n_users, n_items, h['topN'], split_method, eval_metrics, h['reg_cov'], h['margin'], h['use_rank_weight'],
+                    h['clip_norm'], h['n_factors'], h['batch_size'], **it, **kw)
+    elif model_name == 'gbprmf':
+        sampler = sampler_gbpr.Sampler(trasR, h['gsize'], h['negSample'], h['batch_size'], seed=seed or 0)
+        model = GBPRMF(n_users, n_items, h['topN'], h['rho'], h['gsize'], split_method, eval_metrics, h['reg'], h['n_factors'],
+                       h['batch_size'], **it, **kw)
+    elif model_name == 'wrmf':
+        sampler = sampler_rating.Sampler(trasR, h['negRatio'], h['batch_size'], seed=seed or 0)
+        model = WRMF(n_users, n_items, h['topN'], split_method, eval_metrics, h['weight'], h['reg'], h['n_factors'],
+                     h['batch_size'], **it, **kw)
+    else:
+        raise ValueError('unknown model %r' % model_name)
+    scores = model.train(fold + 1, trasR, tstsR, sampler)
+    print(dataset_dir.split('/')[-2] + '@%d:' % (fold + 1),
+          ','.join(['%s' % m for m in eval_metrics]) + '@%d=' % h['topN'] + ','.join(['%.6f' % s for s in scores]))
+    model.close()
+    return scores
+
+
+def run(model_name, dataset_dir, n_users, n_items, folds=5, max_iter=None, seed=None, verbose=True):
+    """testbprmf.py:55-125: all folds, then ``ave`` / ``std`` over the folds."""
+    results = [worker(model_name, fold, n_users, n_items, dataset_dir, max_iter, seed, verbose) for fold in range(folds)]
+    results = np.array(results)
+    topN = HYPER[model_name]['topN']
+    print('ave:', ','.join(['%s' % m for m in eval_metrics]) + '@%d=' % topN + ','.join(['%.6f' % s for s in results.mean(0)]))
+    print('std:', ','.join(['%s' % m for m in eval_metrics]) + '@%d=' % topN + ','.join(['%.6f' % s for s in results.std(0)]))
+    return results
+
+
+if __name__ == '__main__':
+    ap = argparse.ArgumentParser()
+    ap.add_argument('model', choices=sorted(HYPER))
+    ap.add_argument('dataset_dir', help="directory with ratings__<k>_tra.txt / ratings__<k>_tst.txt (trailing '/')")
+    ap.add_argument('n_users', type=int)
+    ap.add_argument('n_items', type=int)
+    ap.add_argument('--folds', type=int, default=5)
+    ap.add_argument('--max-iter', type=int, default=None)
+    ap.add_argument('--seed', type=int, default=None)
+    a = ap.parse_args()
+    run(a.model, a.dataset_dir if a.dataset_dir.endswith('/') else a.dataset_dir + '/', a.n_users, a.n_items, a.folds, a.max_iter, a.seed)

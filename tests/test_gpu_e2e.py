@@ -72,3 +72,18 @@ def test_loov_split(ml100k):
     m = BPRMF(943, 1682, 10, 'loov', ['hr', 'arhr'], .1, 32, 100, 2, verbose=False, seed=1)
     s = m.train(1, tra, tst, Sampler(tra, 1, 100, seed=1))
     assert 0 <= s[1] <= s[0] <= 919
+
+
+def test_driver_module_runs_a_fold_from_files(ml100k, tmp_path, capsys):
+    """collaborativefilteringusingtensorflow_b200.drivers mirrors the reference's test*.py drivers (file layout, printed lines)."""
+    from collaborativefilteringusingtensorflow_b200 import drivers
+    from collaborativefilteringusingtensorflow_b200.utils import IOUtil
+    d = tmp_path / 'ml-100k'
+    d.mkdir()
+    for part in ('tra', 'tst'):
+        u, i, r = ml100k[part + '_raw']
+        IOUtil.saveTriads(list(zip(u.tolist(), i.tolist(), r.astype(float).tolist())), str(d / ('ratings__1_%s.txt' % part)))
+    res = drivers.run('bprmf', str(d) + '/', 943, 1682, folds=1, max_iter=3, seed=5)
+    out = capsys.readouterr().out
+    assert 'ml-100k@1: (943, 1682) 44243 46.92' in out and 'ave: pre,recall,map,mrr,ndcg@10=' in out and 'std:' in out
+    assert res.shape == (1, 5) and res[0, 4] > 0.3
