@@ -30,7 +30,7 @@ class WRMF(RankingModelBase):
         if len(batch) == 1:        # the reference's float64 [rows, 3] array (wrmf.py:145-147)
             uir = batch[0]
             if torch.is_tensor(uir):
-                ids, ratings = uir[:, :2].to(torch.int32), uir[:, 2].to(torch.float32)
+                ids, ratings = uir[:, :2].to(torch.int32).contiguous(), uir[:, 2].to(torch.float32).contiguous()
             else:
                 uir = np.asarray(uir)
                 ids, ratings = uir[:, :2].astype(np.int32), uir[:, 2].astype(np.float32)
