@@ -37,6 +37,10 @@ WORKLOADS = {
                    hyper=dict(reg=0.1, lr=0.1), desc='BPRMF on the configs[1] shape, d=128, W=1'),
     'c3': dict(model='gbpr', n_users=138_493, n_items=26_744, nnz=20_000_000, d=64, W=5, G=3,
                hyper=dict(reg=0.01, rho=0.4, lr=0.1), desc='configs[2]: GBPR ML-20M shape, G=3, d=64, W=5'),
+    'c5': dict(model='bpr', n_users=12_500_000, n_items=10_000_000, nnz=625_000_000, d=128, W=1, G=0,
+               hyper=dict(reg=0.1, lr=0.1),
+               desc='configs[4] per GPU: BPRMF, 12.5M users and 625M interactions per GPU (100M users / 5B interactions at 8 GPUs), '
+                    '10M items, d=128, W=1, reg 0.1, TF1-Adagrad, minibatch-synchronous'),
     'small': dict(model='cml', n_users=20_000, n_items=10_000, nnz=1_000_000, d=128, W=5, G=0,
                   hyper=dict(reg_cov=1.0, margin=1.0, use_rank_weight=True, clip_norm=1.0, lr=0.1),
                   desc='smoke-size CML'),
