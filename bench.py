@@ -422,6 +422,8 @@ def main():
     ap.add_argument('--cpu-budget', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--grow-catalogue', action='store_true', help='N > 1: n_items x N items in total instead of a fixed catalogue')
+    ap.add_argument('--item-transport', default='auto', choices=['nccl', 'peer', 'auto'],
+                    help='N > 1: how item rows reach the step (NCCL all-to-all of unique rows / NVLink peer reads in the kernel)')
     ap.add_argument('--phases', action='store_true', help='N > 1: also report per-phase times of the sharded step')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -23,7 +23,7 @@ def run_distributed(args, rank, world, device):
     local_wl = dict(wl, n_items=item_shard_rows(n_items_global, world, rank))
     model = B_.make_model(local_wl, device, seed=2026 + rank, optimizer=args.optimizer, update='sync')
     sampler = B_.make_sampler(wl, csr, B, 2026 + rank, device)
-    tr = DistributedTrainer(model, sampler, n_items_global, world, rank)
+    tr = DistributedTrainer(model, sampler, n_items_global, world, rank, item_transport=args.item_transport)
     tr.step(Wm)
     model.engine.check_flags()
     torch.cuda.synchronize()
@@ -33,7 +33,7 @@ def run_distributed(args, rank, world, device):
     if rank == 0:
         clk.start()
         time.sleep(0.3)
-    l0, s0, b0 = tr.launches, sampler.launches, tr.bytes_sent
+    l0, s0, b0, p0 = tr.launches, sampler.launches, tr.bytes_sent, tr.bytes_pulled
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dist.barrier()
     torch.cuda.synchronize()
@@ -49,6 +49,7 @@ def run_distributed(args, rank, world, device):
     ms = float(ms.item())
     launches = (tr.launches - l0) + (sampler.launches - s0)
     sent = (tr.bytes_sent - b0) / K
+    pulled = (tr.bytes_pulled - p0) / K * (world - 1) / world     # the share of the item rows that lives on other GPUs
     model.engine.check_flags()
 
     # e2e: host index buffers -> H2D -> sharded step -> D2H loss, every step
@@ -120,6 +121,7 @@ def run_distributed(args, rank, world, device):
                            'item %% N; users range-sharded; NCCL all-to-all of item rows + gradients per minibatch'
                            % n_items_global,
                            batch_pairs_per_gpu=B, negatives=wl['W'], optimizer=args.optimizer, update='sync',
+                           item_transport=('peer (fused NVLink reads in k_step)' if tr._pull else 'nccl (all-to-all of unique rows)'),
                            l2='inputs larger than L2 (random rows of GB-sized tables)'),
                gpu_launches=launches,
                e2e=dict(value=units / (ms2 * 1e-3), unit='triple updates/s', ms_per_step=ms2 / K,
@@ -127,7 +129,8 @@ def run_distributed(args, rank, world, device):
                roofline=dict(bound='hbm', kernel='whole sharded step per GPU (k_count + k_step + k_apply_staged + exchange + owner apply)',
                              achieved=achieved, peak=pk['hbm'], unit='GB/s', frac=achieved / pk['hbm'], traffic=None,
                              peak_source=pk['source']),
-               nvlink=dict(bytes_sent_per_step_per_gpu=sent, achieved_GBs=sent / (ms / K * 1e-3) / 1e9,
+               nvlink=dict(bytes_pulled_per_step_per_gpu=pulled,
+                           bytes_sent_per_step_per_gpu=sent, achieved_GBs=sent / (ms / K * 1e-3) / 1e9,
                            peak_GBs_per_direction=770.0, note='rows out + gradients back + ids; measured peer copy 770 GB/s/dir'),
                phases_ms_per_step=phases, topk=topk, cpu_baseline=None, clocks=clocks, loss_first_last=[float(losses[0]), float(losses[-1])])
     print(json.dumps(out))

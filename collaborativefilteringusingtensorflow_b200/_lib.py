@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libcf_b200.so')
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 # enums of cf_b200.h
 MODEL_BPR, MODEL_CML, MODEL_GBPR, MODEL_WRMF = 0, 1, 2, 3
@@ -18,6 +18,9 @@ SCORE_DOT, SCORE_DOT_BIAS, SCORE_NEG_SQDIST = 0, 1, 2
 FLAG_INDEX_RANGE, FLAG_STAGING_FULL, FLAG_SAMPLER_GAVEUP, FLAG_TOPK_OVERFLOW = 1, 2, 4, 8
 
 _p = C.c_void_p
+
+
+MAX_PEERS = 8
 
 
 class StepArgs(C.Structure):
@@ -31,6 +34,7 @@ class StepArgs(C.Structure):
         ('rho', C.c_float), ('weight', C.c_float),
         ('metaU', _p), ('metaV', _p), ('slotU', _p), ('slotV', _p), ('slot_row', _p), ('staging', _p),
         ('staging_rows', C.c_int64), ('counters', _p), ('loss', _p), ('gradV', _p), ('rank_items', C.c_int64),
+        ('peerV', _p * MAX_PEERS), ('gslot_pos', _p), ('gslot_neg', _p), ('n_peers', C.c_int32), ('reserved0', C.c_int32),
     ]
 
 
@@ -85,6 +89,9 @@ _SIGNATURES = {
     'cf_step_launches_per_batch': (C.c_int32, []),
     'cf_apply_rows': (C.c_int, [C.POINTER(ApplyArgs), _p]),
     'cf_clip_rows': (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, _p]),
+    'cf_ipc_export': (C.c_int, [_p, _p, C.POINTER(C.c_int64)]),
+    'cf_ipc_open': (C.c_int, [_p, C.POINTER(C.c_void_p)]),
+    'cf_ipc_close': (C.c_int, [_p]),
     'cf_sample_ranking': (C.c_int, [C.POINTER(SampleArgs), _p]),
     'cf_sample_rating': (C.c_int, [C.POINTER(SampleArgs), _p]),
     'cf_topk_exact': (C.c_int, [C.POINTER(TopkArgs), _p]),

@@ -197,6 +197,14 @@ static int train_steps_impl(const cf_step_args* a, cudaStream_t stream, cudaEven
   P.lds = a->ld + 4; P.counters = a->counters;
   P.gradV = a->gradV; P.rank_items = a->rank_items > 0 ? a->rank_items : a->n_items;
   if (a->gradV) CF_CHECK_ARG(a->model != CF_MODEL_GBPR && a->update == CF_UPDATE_SYNC, "cf_train_steps: exchange mode (gradV) supports BPR/CML/WRMF in SYNC mode");
+  P.n_peers = a->n_peers; P.gslot_pos = a->gslot_pos; P.gslot_neg = a->gslot_neg;
+  for (int k = 0; k < CF_MAX_PEERS; ++k) P.peerV[k] = k < a->n_peers ? a->peerV[k] : nullptr;
+  if (a->n_peers != 0) {
+    CF_CHECK_ARG(a->n_peers > 0 && a->n_peers <= CF_MAX_PEERS, "cf_train_steps: n_peers must be in [0, %d]", CF_MAX_PEERS);
+    CF_CHECK_ARG(a->gradV != nullptr && a->gslot_pos != nullptr && (W == 0 || a->gslot_neg != nullptr), "cf_train_steps: peer pull needs gradV and the gradient slots");
+    CF_CHECK_ARG(a->n_batches == 1, "cf_train_steps: peer pull takes one minibatch per call");
+    for (int k = 0; k < a->n_peers; ++k) CF_CHECK_ARG(a->peerV[k] != nullptr, "cf_train_steps: peerV[%d] is NULL", k);
+  }
 
   int lpg = 32;
   step_kernel_t kern = pick_kernel(a->model, P.nvec, &lpg);

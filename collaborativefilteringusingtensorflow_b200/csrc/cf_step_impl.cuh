@@ -43,6 +43,11 @@ struct StepDev {
   float* gradV;          // exchange mode (multi-GPU): V/n_items describe FETCHED item rows; item-row gradients are
                          // red.added into gradV[row] (stride ld) instead of being applied here
   long long rank_items;  // CML rank weight uses the GLOBAL item count
+  // peer-pull variant of the exchange mode: item ids are GLOBAL, row i lives at peerV[i % n_peers] + (i / n_peers) * ld
+  // (the owner's shard, mapped over NVLink), its gradient goes to gradV[gslot_*]
+  const float* peerV[CF_MAX_PEERS];
+  const int32_t *gslot_pos, *gslot_neg;
+  int n_peers;
   long long n_occ;       // slots scanned by k_apply_staged
 };
 
@@ -144,6 +149,15 @@ __device__ __forceinline__ float softplus_neg(float x) {  // -log(sigmoid(x)), b
 __device__ __forceinline__ float sigm1(float x) { return -1.f / (1.f + expf(x)); }  // sigmoid(x) - 1
 __device__ __forceinline__ bool in_range(long long r, long long n) { return r >= 0 && r < n; }
 
+// where item row r is read from: the local table, the fetched rows (exchange mode) or its owner's shard (peer pull)
+__device__ __forceinline__ const float* item_row_ptr(const StepDev& P, int r) {
+  if (P.n_peers > 0) {
+    const int q = r / P.n_peers;
+    return P.peerV[r - q * P.n_peers] + (long long)q * P.ld;
+  }
+  return P.V + (long long)r * P.ld;
+}
+
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
@@ -224,6 +238,7 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepDev P)
   const bool adagrad = P.optimizer == CF_OPT_ADAGRAD;
   const bool want_loss = P.loss != nullptr;
   const bool item_ext = P.gradV != nullptr;
+  const bool pull = P.n_peers > 0;
   const int nslot = 2 + P.T;
   float* sp = smem + (size_t)(threadIdx.x / LPG) * (2 * nslot) * P.ld;  // parameter rows of this group's slots
   float* sa = sp + (size_t)nslot * P.ld;                                // accumulator rows
@@ -241,8 +256,12 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepDev P)
 
     // ---------------------------------------------------------------- slots 0 (user) and 1 (positive item)
     int my_row = -1, my_role = ROLE_NONE;
+    int my_gslot = 0;   // peer pull: row of gradV that collects my item row's gradient
     if (gl == 0) { my_row = __ldg(P.pairs + 2 * bb); my_role = ROLE_USER; }
-    if (gl == 1) { my_row = __ldg(P.pairs + 2 * bb + 1); my_role = ROLE_ITEM; }
+    if (gl == 1) {
+      my_row = __ldg(P.pairs + 2 * bb + 1); my_role = ROLE_ITEM;
+      if (pull) my_gslot = __ldg(P.gslot_pos + bb);
+    }
     bool ok = my_role == ROLE_NONE || in_range(my_row, my_role == ROLE_USER ? P.n_users : P.n_items);
     // every entry id of the pair is validated up front (an invalid id skips the whole pair, nothing is written)
     for (int e = gl; e < E; e += LPG) {
@@ -282,7 +301,10 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepDev P)
           my_row = -1;
           const int e = e0 + gl - 2;
           if (gl - 2 < ne) {
-            if (e < P.W) { my_row = __ldg(P.negs + bb * P.W + e); my_role = ROLE_NEG; }
+            if (e < P.W) {
+              my_row = __ldg(P.negs + bb * P.W + e); my_role = ROLE_NEG;
+              if (pull) my_gslot = __ldg(P.gslot_neg + bb * P.W + e);
+            }
             else { my_row = __ldg(P.group + bb * P.G + (e - P.W)); my_role = ROLE_GROUP; }
           }
         }
@@ -298,7 +320,8 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepDev P)
         for (int s = stage_ui ? 0 : 2; s < 2 + ne; ++s) {
           const int r = __shfl_sync(gmask, my_row, leader + s);
           const int role = __shfl_sync(gmask, my_role, leader + s);
-          stage_row<LPG, NV>(sp + (size_t)s * P.ld, (role == ROLE_USER || role == ROLE_GROUP) ? P.U : P.V, r, P.ld, P.nvec, gl);
+          const float* src = (role == ROLE_USER || role == ROLE_GROUP) ? P.U + (long long)r * P.ld : item_row_ptr(P, r);
+          stage_row<LPG, NV>(sp + (size_t)s * P.ld, src, 0, P.ld, P.nvec, gl);
         }
         if (adagrad && commit_pass) {
           for (int s = meta_ui ? 0 : 2; s < 2 + ne; ++s) {
@@ -424,7 +447,8 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepDev P)
           float* Tb = utab ? P.U : P.V;
           float* Ab = utab ? P.accU : P.accV;
           if (item_ext && !utab) {   // a fetched (remote) item row: its gradient goes back to the owner
-            float* gr = P.gradV + (long long)r * P.ld;
+            const int gs = pull ? __shfl_sync(gmask, my_gslot, leader + s) : r;
+            float* gr = P.gradV + (long long)gs * P.ld;
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
               const int v = gl + k * LPG;

@@ -11,6 +11,11 @@ row-sharded by ``item % P`` (local row ``item // P``).  Per minibatch every rank
   4. returns the gradient rows to the owners                                (all_to_all: rows),
   5. owners sum what they received per row and apply it once (cf_apply_rows), i.e. exactly the single-GPU
      minibatch-synchronous semantics with global batch P*B.
+Peer-pull variant (``item_transport='peer'``; NVLink / NVSwitch, one node): step 2's row transfer disappears -- every
+rank maps the other ranks' item shards (CUDA IPC) and the fused kernel reads each item row straight from its owner's
+memory; only ids and gradient rows still travel through NCCL.  It moves one row per OCCURRENCE instead of one per
+unique id, so it wins when minibatches barely repeat items (huge catalogues: BASELINE configs[4]) and loses when they
+do (configs[1]); ``'auto'`` measures the repeat ratio on the first minibatch and picks.
 Evaluation: every rank scores its item shard for all query users (their embeddings are all-gathered), keeps a local
 top-K, and the [T, K] lists are all-gathered and merged (cf_topk_merge).
 
@@ -120,7 +125,9 @@ class DistributedTrainer(object):
     n_users = this rank's users and n_items = this rank's item-shard rows; ``sampler`` samples this rank's CSR (columns =
     GLOBAL item ids)."""
 
-    def __init__(self, model, sampler, n_items_global, world, rank, group=None):
+    def __init__(self, model, sampler, n_items_global, world, rank, group=None, item_transport='nccl'):
+        if item_transport not in ('nccl', 'peer', 'auto'):
+            raise ValueError("item_transport must be 'nccl', 'peer' or 'auto'")
         self.torch = _lib.require_cuda()
         self.lib = _lib.lib()
         self.model, self.eng, self.sampler = model, model.engine, sampler
@@ -139,9 +146,63 @@ class DistributedTrainer(object):
         self._ows_rows = 0
         self.launches = 0
         self.bytes_sent = 0
+        self.bytes_pulled = 0         # peer-pull mode: item-row bytes the fused kernel read (local + over NVLink)
         self.phase_ms = None          # set to {} to collect per-phase CUDA-event times (synchronises every phase)
+        self.item_transport = item_transport
+        self.peer_ptrs = None         # device pointers of every rank's item shard (this rank's own included)
+        self._peer_bases = []
+        self._pull = False
+        if item_transport != 'nccl':
+            self._map_peer_shards()
         if self.eng.kind == 'cml':   # one-time whole-table clip, then touched-row clips suffice
             self.eng._full_clip(self.torch.cuda.current_stream(self.eng.device).cuda_stream)
+
+    def _map_peer_shards(self):
+        """Exchanges CUDA IPC handles of the item shards and maps every peer's shard into this process."""
+        import ctypes as C
+        torch, dist = self.torch, self.ex.dist
+        if self.world > _lib.MAX_PEERS:
+            raise ValueError('peer pull supports up to %d GPUs on one node' % _lib.MAX_PEERS)
+        dev = self.eng.device
+        self._pull = True if self.item_transport == 'peer' else None    # 'auto': decided on the first minibatch
+        if self.world == 1:
+            self.peer_ptrs = [self.eng.V.data_ptr()]
+            return
+        handle = (C.c_ubyte * 64)()
+        off = C.c_int64(0)
+        _lib.check(self.lib.cf_ipc_export(_lib.ptr(self.eng.V), C.addressof(handle), C.byref(off)), 'cf_ipc_export')
+        mine = torch.tensor(list(handle) + [(off.value >> (8 * k)) & 255 for k in range(8)], dtype=torch.uint8, device=dev)
+        every = torch.empty(self.world, 72, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(every, mine, group=self.ex.group)
+        every = every.cpu().numpy()
+        ptrs = []
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs.append(self.eng.V.data_ptr())
+                continue
+            h = (C.c_ubyte * 64)(*every[r, :64].tolist())
+            base = C.c_void_p(0)
+            _lib.check(self.lib.cf_ipc_open(C.addressof(h), C.byref(base)), 'cf_ipc_open')
+            self._peer_bases.append(base.value)
+            ptrs.append(base.value + int.from_bytes(bytes(every[r, 64:72].tolist()), 'little'))
+        self.peer_ptrs = ptrs
+
+    def close(self):
+        """Unmaps the peers' shards (call on every rank before the tables are freed)."""
+        for b in self._peer_bases:
+            self.lib.cf_ipc_close(b)
+        self._peer_bases, self.peer_ptrs = [], None
+
+    def _decide_transport(self, plan, n_occ):
+        """'auto': pull when the minibatches of all ranks together repeat items so rarely that one row per occurrence
+        over NVLink is cheaper than gather + all_to_all + scatter of one row per unique id (same answer on every rank)."""
+        torch = self.torch
+        t = torch.tensor([float(plan.n_req), float(n_occ)], dtype=torch.float64, device=self.eng.device)
+        if self.world > 1:
+            self.ex.dist.all_reduce(t, group=self.ex.group)
+        uniq, occ = t.tolist()
+        self._pull = uniq > 0.5 * occ
+        return self._pull
 
     def _owner_workspace(self, n):
         torch, eng = self.torch, self.eng
@@ -182,15 +243,33 @@ class DistributedTrainer(object):
             plan = self.make_plan(pairs, negs)
         elif getattr(plan, 'recv_local_rows', None) is None:
             plan = self.ex.plan_exchange(plan)
+        elif self.peer_ptrs is not None and self.world > 1:
+            # peer pull relies on a barrier between the owners' applies of the previous minibatch and this minibatch's
+            # remote reads; the id exchange of the two branches above is one (it completes here only after every rank
+            # has enqueued it, i.e. after its previous apply), a plan exchanged earlier needs an explicit one
+            self.ex.dist.all_reduce(torch.zeros(1, device=eng.device), group=self.ex.group)
         ev = self._tick('plan (dedupe + route ids)', ev)
-        Vbuf = self.ex.fetch(plan, eng.V)                                                    # [n_req, ld]
-        ev = self._tick('fetch rows (gather + all_to_all)', ev)
-        Gbuf = torch.zeros_like(Vbuf)
-        lp = torch.stack([pairs[:, 0].to(torch.int32), plan.occ_local[:, 0]], dim=1).contiguous()
-        ln = plan.occ_local[:, 1:].contiguous()
+        pull = self.peer_ptrs is not None and (self._pull if self._pull is not None
+                                               else self._decide_transport(plan, pairs.shape[0] * (1 + negs.shape[1])))
         a = _lib.StepArgs()
-        a.U, a.V, a.accU, a.accV = _lib.ptr(eng.U), _lib.ptr(Vbuf), _lib.ptr(eng.accU), _lib.ptr(eng.accV)
-        a.n_users, a.n_items, a.d, a.ld = eng.n_users, plan.n_req, eng.d, eng.ld
+        if pull:
+            Gbuf = torch.zeros(plan.n_req, eng.ld, device=eng.device)
+            lp = pairs.to(torch.int32).contiguous()                                          # GLOBAL item ids
+            ln = negs.to(torch.int32).contiguous()
+            gp, gn = plan.occ_local[:, 0].contiguous(), plan.occ_local[:, 1:].contiguous()
+            a.V, a.n_items = _lib.ptr(eng.V), self.n_items_global
+            for r, q in enumerate(self.peer_ptrs):
+                a.peerV[r] = q
+            a.n_peers, a.gslot_pos, a.gslot_neg = self.world, _lib.ptr(gp), _lib.ptr(gn)
+        else:
+            Vbuf = self.ex.fetch(plan, eng.V)                                                # [n_req, ld]
+            ev = self._tick('fetch rows (gather + all_to_all)', ev)
+            Gbuf = torch.zeros_like(Vbuf)
+            lp = torch.stack([pairs[:, 0].to(torch.int32), plan.occ_local[:, 0]], dim=1).contiguous()
+            ln = plan.occ_local[:, 1:].contiguous()
+            a.V, a.n_items = _lib.ptr(Vbuf), plan.n_req
+        a.U, a.accU, a.accV = _lib.ptr(eng.U), _lib.ptr(eng.accU), _lib.ptr(eng.accV)
+        a.n_users, a.d, a.ld = eng.n_users, eng.d, eng.ld
         a.pairs, a.negs = _lib.ptr(lp), _lib.ptr(ln)
         a.B, a.W, a.G, a.n_batches = B, int(negs.shape[1]), 0, 1
         a.model, a.optimizer, a.update = eng.model_id, 0 if eng.optimizer == 'adagrad' else 1, _lib.UPDATE_SYNC
@@ -223,7 +302,9 @@ class DistributedTrainer(object):
             _lib.check(self.lib.cf_apply_rows(ap, stream), 'cf_apply_rows')
         ev = self._tick('owner apply (cf_apply_rows)', ev)
         self.launches += 3 + 3
-        self.bytes_sent += (plan.n_req + n) * eng.ld * 4 + plan.n_req * 4
+        self.bytes_sent += ((0 if pull else plan.n_req) + n) * eng.ld * 4 + plan.n_req * 4
+        if pull:
+            self.bytes_pulled += int(pairs.shape[0]) * (1 + int(negs.shape[1])) * eng.ld * 4
         return loss
 
     def step(self, n_minibatches=1, want_loss=True):

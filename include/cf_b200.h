@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CF_ABI_VERSION 9
+#define CF_ABI_VERSION 10
 
 /* models */
 enum { CF_MODEL_BPR = 0, CF_MODEL_CML = 1, CF_MODEL_GBPR = 2, CF_MODEL_WRMF = 3 };
@@ -59,6 +59,7 @@ const char* cf_build_arch(void);
  * Per minibatch it launches a row-occurrence counting kernel, ONE fused gather/gradient/update kernel and a
  * kernel that applies the summed gradient of the rows that occurred more than once.
  * ------------------------------------------------------------------------------------------------ */
+#define CF_MAX_PEERS 8
 typedef struct cf_step_args {
   /* parameters */
   float* U;          /* [n_users, ld] */
@@ -108,6 +109,15 @@ typedef struct cf_step_args {
    * are red.added into gradV[n_items, ld] (zeroed by the caller) and travel back to the rows' owners (cf_apply_rows) */
   float* gradV;
   int64_t rank_items;      /* CML rank weight: global number of items (0 = n_items) */
+  /* peer-pull variant of the exchange mode (NVLink peer memory, n_peers > 0; gradV is required): the item ids in
+   * pairs[:,1] / negs are GLOBAL, n_items is the global item count, item i is read straight from its owner's shard
+   * peerV[i % n_peers] at row i / n_peers (stride ld; the pointers come from cf_ipc_open / the local table), V is not
+   * used, and the gradient of the occurrence is red.added into gradV[gslot_pos[b]] / gradV[gslot_neg[b, w]] */
+  const float* peerV[CF_MAX_PEERS];
+  const int32_t* gslot_pos; /* [n_batches*B]    row of gradV of the positive item of pair b */
+  const int32_t* gslot_neg; /* [n_batches*B, W] row of gradV of negative w of pair b */
+  int32_t n_peers;
+  int32_t reserved0;
 } cf_step_args;
 
 int cf_train_steps(const cf_step_args* args, void* stream);
@@ -145,6 +155,14 @@ typedef struct cf_apply_args {
   int32_t* counters;       /* [4] */
 } cf_apply_args;
 int cf_apply_rows(const cf_apply_args* args, void* stream);
+
+/* CUDA IPC plumbing of the peer-pull mode (one process per GPU on one NVLink / NVSwitch node).  cf_ipc_export fills the
+ * 64-byte handle of the allocation that contains devptr and the byte offset of devptr inside it; cf_ipc_open maps a
+ * handle exported by another process into this one (peer access enabled lazily) and returns the allocation's base;
+ * cf_ipc_close unmaps it.  The reference is single-device: replaces nothing. */
+int cf_ipc_export(const void* devptr, void* handle64, int64_t* offset_bytes);
+int cf_ipc_open(const void* handle64, void** base);
+int cf_ipc_close(void* base);
 
 /* row <- row * c / max(||row||_2, c) over a whole table: cml.py:119-122 (used once, after the first step) */
 int cf_clip_rows(float* table, int64_t n_rows, int32_t d, int32_t ld, float clip_norm, void* stream);

@@ -26,6 +26,7 @@ def main():
     from collaborativefilteringusingtensorflow_b200.sparse import DeviceCSR
     from scipy.sparse import lil_matrix
     ok = True
+    transport = sys.argv[1] if len(sys.argv) > 1 else 'nccl'    # 'nccl' | 'peer' | 'auto'
     for kind in ('bpr', 'cml'):
         nu_l, ni, d, B, W = 500, 1203, 128, 1024, 3
         nu = nu_l * world
@@ -39,7 +40,7 @@ def main():
 
         class NoSampler(object):
             batch_size = B
-        tr = DistributedTrainer(local_m, NoSampler(), ni, world, rank)
+        tr = DistributedTrainer(local_m, NoSampler(), ni, world, rank, item_transport=transport)
         ref = None
         if rank == 0:
             ref = mk(nu, ni)

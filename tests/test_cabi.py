@@ -32,9 +32,33 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     # field order/types are mirrored by hand; sizes follow from the C layout rules (natural alignment)
     assert C.sizeof(_lib.Csr) == 4 * 8 + 3 * 8
-    assert C.sizeof(_lib.StepArgs) == 6 * 8 + 2 * 8 + 2 * 4 + 4 * 8 + 4 * 4 + 4 * 4 + 6 * 4 + 6 * 8 + 8 + 2 * 8 + 2 * 8
+    assert C.sizeof(_lib.StepArgs) == 6 * 8 + 2 * 8 + 2 * 4 + 4 * 8 + 4 * 4 + 4 * 4 + 6 * 4 + 6 * 8 + 8 + 2 * 8 + 2 * 8 + 8 * 8 + 2 * 8 + 2 * 4
     assert C.sizeof(_lib.SampleArgs) == 2 * C.sizeof(_lib.Csr) + 3 * 8 + 6 * 4 + 5 * 8
     assert C.sizeof(_lib.TopkArgs) == 3 * 8 + 2 * 8 + 2 * 4 + 8 + 3 * 4 + 4 + C.sizeof(_lib.Csr) + 3 * 8 + 2 * 8
+
+
+def test_struct_sizes_match_the_compiled_header(tmp_path):
+    """sizeof / offsetof of every argument struct as gcc lays out include/cf_b200.h against the ctypes mirrors."""
+    import shutil
+    import subprocess
+    if shutil.which('gcc') is None:
+        pytest.skip('no gcc')
+    names = dict(cf_step_args=_lib.StepArgs, cf_apply_args=_lib.ApplyArgs, cf_als_args=_lib.AlsArgs, cf_csr=_lib.Csr,
+                 cf_sample_args=_lib.SampleArgs, cf_topk_args=_lib.TopkArgs)
+    last = {n: c._fields_[-1][0] for n, c in names.items()}
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "cf_b200.h"\nint main(void) {\n'
+    for n in names:
+        src += '  printf("%s %%zu %%zu\\n", sizeof(%s), offsetof(%s, %s));\n' % (n, n, n, last[n])
+    src += '  return 0;\n}\n'
+    c = tmp_path / 'sizes.c'
+    c.write_text(src)
+    exe = tmp_path / 'sizes'
+    subprocess.run(['gcc', '-I', os.path.join(ROOT, 'include'), str(c), '-o', str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    for line in out.strip().splitlines():
+        n, size, off = line.split()
+        assert C.sizeof(names[n]) == int(size), n
+        assert getattr(names[n], last[n]).offset == int(off), n
 
 
 def test_host_side_validation_needs_no_gpu():

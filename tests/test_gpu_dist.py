@@ -10,8 +10,9 @@ def _state(m):
     return {k: v.cpu().numpy() for k, v in m.state_dict().items()}
 
 
+@pytest.mark.parametrize('transport', ['nccl', 'peer', 'auto'])
 @pytest.mark.parametrize('kind', ['bpr', 'cml'])
-def test_exchange_mode_world1_equals_fused_step(kind):
+def test_exchange_mode_world1_equals_fused_step(kind, transport):
     import torch
     from collaborativefilteringusingtensorflow_b200 import BPRMF, CML
     from collaborativefilteringusingtensorflow_b200.dist import DistributedTrainer
@@ -24,7 +25,7 @@ def test_exchange_mode_world1_equals_fused_step(kind):
 
     class NoSampler(object):
         batch_size = B
-    tr = DistributedTrainer(b, NoSampler(), ni, 1, 0)
+    tr = DistributedTrainer(b, NoSampler(), ni, 1, 0, item_transport=transport)
     for s in range(3):
         pairs = np.stack([rng.integers(0, nu, B), rng.integers(0, ni, B)], 1).astype(np.int32)
         negs = rng.integers(0, ni, (B, W)).astype(np.int32)
@@ -69,3 +70,81 @@ def test_item_mod_sharded_topk_merge_equals_single_shot():
     _lib.check(_lib.lib().cf_topk_merge(idx.data_ptr(), val.data_ptr(), P, nu, K, out_i.data_ptr(), out_v.data_ptr(),
                                         torch.cuda.current_stream().cuda_stream), 'merge')
     assert torch.equal(out_i, whole_i) and torch.equal(out_v, whole_v)
+
+
+@pytest.mark.parametrize('kind', ['bpr', 'cml'])
+def test_peer_pull_from_three_shards_equals_fetched_rows(kind):
+    """The peer-pull step (item rows read from their owners' shards by GLOBAL id: item i = row i // P of shard i % P)
+    against the fetched-rows exchange step on the same minibatch: same user update, same gradient rows.  The three
+    "peers" are three tensors of this process -- the kernel only sees pointers."""
+    import torch
+    from collaborativefilteringusingtensorflow_b200 import BPRMF, CML, _lib
+    from collaborativefilteringusingtensorflow_b200.dist import ItemExchange
+    nu, ni, d, B, W, P = 300, 1001, 128, 2048, 4, 3
+    mk = (lambda: BPRMF(nu, ni, n_factors=d, reg=0.05, verbose=False, seed=9)) if kind == 'bpr' else \
+         (lambda: CML(nu, ni, n_factors=d, reg_cov=1.0, margin=1.0, init_stddev=0.05, verbose=False, seed=9))
+    rng = np.random.default_rng(3)
+    pairs = torch.from_numpy(np.stack([rng.integers(0, nu, B), rng.integers(0, ni, B)], 1).astype(np.int32)).cuda()
+    negs = torch.from_numpy(rng.integers(0, ni, (B, W)).astype(np.int32)).cuda()
+    items = torch.cat([pairs[:, 1:2], negs], 1).to(torch.int64)
+    plan = ItemExchange(1, 0).plan_local(items, ni)                    # dedupe only: occ_local -> row of the compact buffers
+    out = {}
+    for mode in ('fetch', 'pull'):
+        m = mk()
+        eng = m.engine
+        shards = [eng.V[p::P].contiguous() for p in range(P)]
+        Gbuf = torch.zeros(plan.n_req, eng.ld, device=eng.device)
+        a = _lib.StepArgs()
+        if mode == 'pull':
+            lp, ln = pairs.contiguous(), negs.contiguous()
+            gp, gn = plan.occ_local[:, 0].contiguous(), plan.occ_local[:, 1:].contiguous()
+            a.V, a.n_items, a.n_peers = _lib.ptr(eng.V), ni, P
+            for p in range(P):
+                a.peerV[p] = shards[p].data_ptr()
+            a.gslot_pos, a.gslot_neg = _lib.ptr(gp), _lib.ptr(gn)
+        else:
+            Vbuf = eng.V.index_select(0, plan.req_global)
+            lp = torch.stack([pairs[:, 0], plan.occ_local[:, 0]], 1).contiguous()
+            ln = plan.occ_local[:, 1:].contiguous()
+            a.V, a.n_items = _lib.ptr(Vbuf), plan.n_req
+        a.U, a.accU, a.accV = _lib.ptr(eng.U), _lib.ptr(eng.accU), _lib.ptr(eng.accV)
+        a.n_users, a.d, a.ld = eng.n_users, eng.d, eng.ld
+        a.pairs, a.negs = _lib.ptr(lp), _lib.ptr(ln)
+        a.B, a.W, a.G, a.n_batches = B, W, 0, 1
+        a.model, a.optimizer, a.update = eng.model_id, 0, _lib.UPDATE_SYNC
+        h = eng.hyper
+        a.use_rank_weight = int(bool(h['use_rank_weight']))
+        a.lr, a.reg, a.margin, a.clip_norm, a.rho, a.weight = h['lr'], h['reg'], h['margin'], h['clip_norm'], h['rho'], h['weight']
+        ws = eng._workspace(B, W, 0)
+        a.metaU, a.metaV = _lib.ptr(ws['metaU']), _lib.ptr(ws['metaV'])
+        a.slotU, a.slotV, a.slot_row = _lib.ptr(ws['slotU']), _lib.ptr(ws['slotV']), _lib.ptr(ws['slot_row'])
+        a.staging, a.staging_rows = _lib.ptr(ws['staging']), ws['staging'].shape[0]
+        a.counters = _lib.ptr(eng.counters)
+        loss = torch.zeros(1, dtype=torch.float64, device=eng.device)
+        a.loss, a.gradV, a.rank_items = _lib.ptr(loss), _lib.ptr(Gbuf), ni
+        _lib.check(_lib.lib().cf_train_steps(a, torch.cuda.current_stream().cuda_stream), 'cf_train_steps')
+        eng.check_flags()
+        out[mode] = (eng.U.cpu().numpy(), Gbuf.cpu().numpy(), float(loss.item()))
+    assert np.abs(out['fetch'][1]).max() > 0
+    np.testing.assert_allclose(out['pull'][0], out['fetch'][0], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(out['pull'][1], out['fetch'][1], rtol=2e-5, atol=2e-5 if kind == 'cml' else 2e-6)   # red.add order differs
+    assert abs(out['pull'][2] - out['fetch'][2]) <= 1e-6 * abs(out['fetch'][2])
+
+
+def test_peer_pull_rejects_out_of_range_global_ids():
+    import torch
+    from collaborativefilteringusingtensorflow_b200 import BPRMF
+    from collaborativefilteringusingtensorflow_b200.dist import DistributedTrainer
+    m = BPRMF(50, 40, n_factors=32, verbose=False, seed=1)
+
+    class NoSampler(object):
+        batch_size = 8
+    tr = DistributedTrainer(m, NoSampler(), 40, 1, 0, item_transport='peer')
+    pairs = torch.tensor([[k, k] for k in range(8)], dtype=torch.int32).cuda()
+    negs = torch.full((8, 2), 3, dtype=torch.int32).cuda()
+    before = m.engine.U.clone()
+    pairs[5, 0] = 50                                                  # user id past the table
+    tr.step_chunk(pairs, negs, 8)
+    with pytest.raises(RuntimeError, match='out of range'):
+        m.engine.check_flags()
+    assert torch.equal(before, m.engine.U)
