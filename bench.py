@@ -251,6 +251,11 @@ def run_ours(args):
     run_steps(max(Wm, 3))
     eng.check_flags()
     sampler.check_flags()
+    # the timed region samples K minibatches with ONE launch into one [K * B, 2 + W] index buffer: have the caching
+    # allocator own blocks of that size already (a first-time cudaMalloc of ~3 GB inside the timed region cost up to
+    # 1.3 ms per step in some runs)
+    warm = sampler.next_chunk(K)
+    del warm
     torch.cuda.synchronize()
 
     # ---- timed: exactly K steps, CUDA events on the launching stream

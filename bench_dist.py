@@ -26,6 +26,8 @@ def run_distributed(args, rank, world, device):
     tr = DistributedTrainer(model, sampler, n_items_global, world, rank, item_transport=args.item_transport)
     tr.step(Wm)
     model.engine.check_flags()
+    warm = sampler.next_chunk(K)      # allocator blocks of the timed region's K-minibatch index buffer (see bench.py)
+    del warm
     torch.cuda.synchronize()
     dist.barrier()
 

@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libcf_b200.so')
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 # enums of cf_b200.h
 MODEL_BPR, MODEL_CML, MODEL_GBPR, MODEL_WRMF = 0, 1, 2, 3
@@ -35,6 +35,7 @@ class StepArgs(C.Structure):
         ('metaU', _p), ('metaV', _p), ('slotU', _p), ('slotV', _p), ('slot_row', _p), ('staging', _p),
         ('staging_rows', C.c_int64), ('counters', _p), ('loss', _p), ('gradV', _p), ('rank_items', C.c_int64),
         ('peerV', _p * MAX_PEERS), ('gslot_pos', _p), ('gslot_neg', _p), ('n_peers', C.c_int32), ('reserved0', C.c_int32),
+        ('gradU', _p), ('gradb', _p),
     ]
 
 
@@ -89,6 +90,7 @@ _SIGNATURES = {
     'cf_step_launches_per_batch': (C.c_int32, []),
     'cf_apply_rows': (C.c_int, [C.POINTER(ApplyArgs), _p]),
     'cf_clip_rows': (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, _p]),
+    'cf_apply_dense': (C.c_int, [C.POINTER(ApplyArgs), _p]),
     'cf_ipc_export': (C.c_int, [_p, _p, C.POINTER(C.c_int64)]),
     'cf_ipc_open': (C.c_int, [_p, C.POINTER(C.c_void_p)]),
     'cf_ipc_close': (C.c_int, [_p]),
@@ -101,6 +103,8 @@ _SIGNATURES = {
     'cf_topk_merge': (C.c_int, [_p, _p, C.c_int32, C.c_int32, C.c_int32, _p, _p, _p]),
     'cf_als_workspace_bytes': (C.c_int64, [C.c_int64]),
     'cf_als_half_sweep': (C.c_int, [C.POINTER(AlsArgs), _p]),
+    'cf_als_gram': (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int32, _p, _p, C.c_int64, _p]),
+    'cf_als_solve_rows': (C.c_int, [C.POINTER(AlsArgs), _p, _p]),
     'cf_parse_triplets': (C.c_int, [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.POINTER(C.c_int64)),
                                   C.POINTER(C.POINTER(C.c_int64)), C.POINTER(C.POINTER(C.c_double))]),
     'cf_free_host': (None, [_p]),

@@ -411,22 +411,13 @@ extern "C" int64_t cf_als_workspace_bytes(int64_t n_y) {
   return 2ll * ALS_D * n_pad * 2 + ALS_D * ALS_D * 4 + 2048;
 }
 
-extern "C" int cf_als_half_sweep(const cf_als_args* a, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  CF_CHECK_ARG(a != nullptr, "cf_als_half_sweep: args is NULL");
-  CF_CHECK_ARG(a->X && a->Y && a->indptr && a->indices && a->workspace, "cf_als_half_sweep: NULL pointer");
-  CF_CHECK_ARG(a->d > 0 && a->d <= ALS_D && a->ldx >= a->d && a->ldy >= a->d, "cf_als_half_sweep: n_factors up to %d are supported (d=%d)", ALS_D, a->d);
-  CF_CHECK_ARG(a->n_x > 0 && a->n_y > 0, "cf_als_half_sweep: empty factor matrix");
-  CF_CHECK_ARG(a->reg > 0.f, "cf_als_half_sweep: reg must be positive (it keeps the normal equations SPD)");
-  CF_CHECK_ARG(((uintptr_t)a->workspace % 1024) == 0 && a->workspace_bytes >= cf_als_workspace_bytes(a->n_y), "cf_als_half_sweep: workspace too small or not 1024-byte aligned");
-  const long long n_pad = (a->n_y + KCH - 1) / KCH * KCH;
-  uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
+// Gram stage: G += Y^T Y over the given rows (bf16 hi/lo planes + tcgen05); G is NOT zeroed here
+static int als_gram(const float* Y, long long n_y, int d, int ldy, float* G, uint8_t* ws, cudaStream_t stream) {
+  const long long n_pad = (n_y + KCH - 1) / KCH * KCH;
   __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(ws);
   __nv_bfloat16* lo = hi + (size_t)ALS_D * n_pad;
-  float* G = reinterpret_cast<float*>(ws + (((size_t)2 * ALS_D * n_pad * 2 + 1023) / 1024) * 1024);
-  CF_CUDA_OK(cudaMemsetAsync(G, 0, ALS_D * ALS_D * 4, stream));
   dim3 sgrid((unsigned)((n_pad + 31) / 32), ALS_D / 32);
-  k_als_split<<<sgrid, 256, 0, stream>>>(a->Y, a->n_y, n_pad, a->d, a->ldy, hi, lo);
+  k_als_split<<<sgrid, 256, 0, stream>>>(Y, n_y, n_pad, d, ldy, hi, lo);
   CUtensorMap tmHi, tmLo;
   if (int rc = make_plane_map(&tmHi, hi, n_pad)) return rc;
   if (int rc = make_plane_map(&tmLo, lo, n_pad)) return rc;
@@ -436,6 +427,12 @@ extern "C" int cf_als_half_sweep(const cf_als_args* a, void* stream_) {
   const size_t gsmem = 2 * CHUNK_BYTES + 64 + 1024;
   CF_CUDA_OK(cudaFuncSetAttribute(k_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
   k_gram_tc<<<ggrid, 192, gsmem, stream>>>(tmHi, tmLo, n_chunks, G);
+  CF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// Solve stage: every row of X from the (complete) Gram G and its observed rows of Y
+static int als_solve(const cf_als_args* a, const float* G, cudaStream_t stream) {
   SolveParams S;
   S.X = a->X; S.Y = a->Y; S.G = G; S.indptr = (const long long*)a->indptr; S.indices = a->indices;
   S.n_x = a->n_x; S.d = a->d; S.ldx = a->ldx; S.ldy = a->ldy; S.weight = a->weight; S.reg = a->reg;
@@ -453,4 +450,40 @@ extern "C" int cf_als_half_sweep(const cf_als_args* a, void* stream_) {
   }
   CF_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+static int als_check(const cf_als_args* a, const char* who, bool need_ws) {
+  CF_CHECK_ARG(a != nullptr, "%s: args is NULL", who);
+  CF_CHECK_ARG(a->X && a->Y && a->indptr && a->indices, "%s: NULL pointer", who);
+  CF_CHECK_ARG(a->d > 0 && a->d <= ALS_D && a->ldx >= a->d && a->ldy >= a->d, "%s: n_factors up to %d are supported (d=%d)", who, ALS_D, a->d);
+  CF_CHECK_ARG(a->n_x > 0 && a->n_y > 0, "%s: empty factor matrix", who);
+  CF_CHECK_ARG(a->reg > 0.f, "%s: reg must be positive (it keeps the normal equations SPD)", who);
+  if (need_ws)
+    CF_CHECK_ARG(a->workspace && ((uintptr_t)a->workspace % 1024) == 0 && a->workspace_bytes >= cf_als_workspace_bytes(a->n_y), "%s: workspace too small or not 1024-byte aligned", who);
+  return 0;
+}
+
+extern "C" int cf_als_half_sweep(const cf_als_args* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int rc = als_check(a, "cf_als_half_sweep", true)) return rc;
+  const long long n_pad = (a->n_y + KCH - 1) / KCH * KCH;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
+  float* G = reinterpret_cast<float*>(ws + (((size_t)2 * ALS_D * n_pad * 2 + 1023) / 1024) * 1024);
+  CF_CUDA_OK(cudaMemsetAsync(G, 0, ALS_D * ALS_D * 4, stream));
+  if (int rc = als_gram(a->Y, a->n_y, a->d, a->ldy, G, ws, stream)) return rc;
+  return als_solve(a, G, stream);
+}
+
+extern "C" int cf_als_gram(const float* Y, int64_t n_y, int32_t d, int32_t ldy, float* G, void* workspace,
+                           int64_t workspace_bytes, void* stream_) {
+  CF_CHECK_ARG(Y && G && workspace, "cf_als_gram: NULL pointer");
+  CF_CHECK_ARG(d > 0 && d <= ALS_D && ldy >= d && n_y > 0, "cf_als_gram: bad shape (d=%d, n_y=%lld)", d, (long long)n_y);
+  CF_CHECK_ARG(((uintptr_t)workspace % 1024) == 0 && workspace_bytes >= cf_als_workspace_bytes(n_y), "cf_als_gram: workspace too small or not 1024-byte aligned");
+  return als_gram(Y, n_y, d, ldy, G, reinterpret_cast<uint8_t*>(workspace), (cudaStream_t)stream_);
+}
+
+extern "C" int cf_als_solve_rows(const cf_als_args* a, const float* G, void* stream_) {
+  if (int rc = als_check(a, "cf_als_solve_rows", false)) return rc;
+  CF_CHECK_ARG(G != nullptr, "cf_als_solve_rows: G is NULL");
+  return als_solve(a, G, (cudaStream_t)stream_);
 }

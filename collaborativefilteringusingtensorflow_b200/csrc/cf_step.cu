@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) k_count(const __grid_constant__ StepDev P
       else if (k == 1) { tab = 1; r = __ldg(P.pairs + 2 * b + 1); }
       else if (k < 2 + P.W) { tab = 1; r = __ldg(P.negs + b * P.W + (k - 2)); }
       else { tab = 0; r = __ldg(P.group + b * P.G + (k - 2 - P.W)); }
-      if (tab && P.gradV) { /* fetched item rows are not applied here */ }
+      if (tab ? P.gradV != nullptr : P.gradU != nullptr) { /* fetched / replicated rows are not applied here */ }
       else if (!in_range(r, tab ? P.n_items : P.n_users)) atomicOr(P.counters + 1, CF_FLAG_INDEX_RANGE);
       else need = atomicAdd((tab ? P.metaV : P.metaU) + r, 1u) == 1u;   // second occurrence: the row needs a staging slot
     }
@@ -119,17 +119,17 @@ __global__ void __launch_bounds__(256) k_count_rows(const __grid_constant__ Step
   }
 }
 
-step_kernel_t pick_kernel(int model, int nvec, int* lpg) {
+step_kernel_t pick_kernel(int model, int nvec, int* lpg, bool ext) {
   const int shape = nvec <= 8 ? 0 : nvec <= 16 ? 1 : nvec <= 32 ? 2 : nvec <= 64 ? 3 : 4;
   *lpg = shape == 0 ? 8 : shape == 1 ? 16 : 32;
-#define CF_CASE(M)                                   \
-  case M:                                            \
-    switch (shape) {                                 \
-      case 0: return cf_step_pick_##M##_0();        \
-      case 1: return cf_step_pick_##M##_1();        \
-      case 2: return cf_step_pick_##M##_2();        \
-      case 3: return cf_step_pick_##M##_3();        \
-      default: return cf_step_pick_##M##_4();       \
+#define CF_CASE(M)                                                                   \
+  case M:                                                                            \
+    switch (shape) {                                                                 \
+      case 0: return ext ? cf_step_pick_ext_##M##_0() : cf_step_pick_##M##_0();     \
+      case 1: return ext ? cf_step_pick_ext_##M##_1() : cf_step_pick_##M##_1();     \
+      case 2: return ext ? cf_step_pick_ext_##M##_2() : cf_step_pick_##M##_2();     \
+      case 3: return ext ? cf_step_pick_ext_##M##_3() : cf_step_pick_##M##_3();     \
+      default: return ext ? cf_step_pick_ext_##M##_4() : cf_step_pick_##M##_4();    \
     }
   switch (model) {
     CF_CASE(0)
@@ -196,7 +196,11 @@ static int train_steps_impl(const cf_step_args* a, cudaStream_t stream, cudaEven
   P.slotU = a->slotU; P.slotV = a->slotV; P.staging = a->staging; P.staging_rows = a->staging_rows;
   P.lds = a->ld + 4; P.counters = a->counters;
   P.gradV = a->gradV; P.rank_items = a->rank_items > 0 ? a->rank_items : a->n_items;
-  if (a->gradV) CF_CHECK_ARG(a->model != CF_MODEL_GBPR && a->update == CF_UPDATE_SYNC, "cf_train_steps: exchange mode (gradV) supports BPR/CML/WRMF in SYNC mode");
+  P.gradU = a->gradU; P.gradb = a->gradb;
+  if (a->gradV) CF_CHECK_ARG(a->update == CF_UPDATE_SYNC, "cf_train_steps: exchange mode (gradV) needs SYNC mode");
+  if (a->gradV && a->model == CF_MODEL_GBPR)
+    CF_CHECK_ARG(a->gradU && a->gradb && a->n_peers == 0, "cf_train_steps: GBPR in exchange mode needs gradU, gradV and gradb (replicated data-parallel mode)");
+  if (a->gradU) CF_CHECK_ARG(a->gradV != nullptr && a->n_peers == 0, "cf_train_steps: gradU needs gradV (dense gradient tables of the replicated mode)");
   P.n_peers = a->n_peers; P.gslot_pos = a->gslot_pos; P.gslot_neg = a->gslot_neg;
   for (int k = 0; k < CF_MAX_PEERS; ++k) P.peerV[k] = k < a->n_peers ? a->peerV[k] : nullptr;
   if (a->n_peers != 0) {
@@ -207,7 +211,7 @@ static int train_steps_impl(const cf_step_args* a, cudaStream_t stream, cudaEven
   }
 
   int lpg = 32;
-  step_kernel_t kern = pick_kernel(a->model, P.nvec, &lpg);
+  step_kernel_t kern = pick_kernel(a->model, P.nvec, &lpg, a->gradV != nullptr);
   static int sms = 0;
   if (!sms) sms = cf_num_sms();
   // entries (negatives + group users) staged per tile: all of them if the lanes (one per slot) and the shared
@@ -249,11 +253,12 @@ static int train_steps_impl(const cf_step_args* a, cudaStream_t stream, cudaEven
     P.ratings = a->ratings ? a->ratings + off : nullptr;
     P.loss = a->loss ? a->loss + nb : nullptr;
     if (ev) CF_CUDA_OK(cudaEventRecord(ev[4 * nb + 0], stream));
-    if (a->update == CF_UPDATE_SYNC) k_count<<<(unsigned)cgrid, 256, 0, stream>>>(P);
+    const bool all_ext = a->gradU && a->gradV;   // nothing is applied locally: no occurrence counts, no staged rows
+    if (a->update == CF_UPDATE_SYNC && !all_ext) k_count<<<(unsigned)cgrid, 256, 0, stream>>>(P);
     if (ev) CF_CUDA_OK(cudaEventRecord(ev[4 * nb + 1], stream));
     kern<<<(unsigned)grid, 256, smem, stream>>>(P);
     if (ev) CF_CUDA_OK(cudaEventRecord(ev[4 * nb + 2], stream));
-    if (a->update == CF_UPDATE_SYNC) kapply<<<(unsigned)agrid, 256, 0, stream>>>(P);
+    if (a->update == CF_UPDATE_SYNC && !all_ext) kapply<<<(unsigned)agrid, 256, 0, stream>>>(P);
     if (ev) CF_CUDA_OK(cudaEventRecord(ev[4 * nb + 3], stream));
   }
   CF_CUDA_OK(cudaGetLastError());
@@ -320,6 +325,79 @@ extern "C" int cf_apply_rows(const cf_apply_args* a, void* stream_) {
   k_count_rows<<<(unsigned)cgrid, 256, 0, stream>>>(P, a->rows, a->n);
   pick_scatter(P.nvec)<<<(unsigned)sgrid, 256, 0, stream>>>(P, a->rows, a->grads, a->n, a->ldg);
   pick_apply(P.nvec)<<<(unsigned)agrid, 256, 0, stream>>>(P);
+  CF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---- replicated data-parallel mode: apply a DENSE (all-reduced) gradient table; rows with an all-zero gradient are
+// skipped (for Adagrad / SGD a zero gradient is a no-op, so this equals the sparse apply), used rows are zeroed again
+namespace {
+template <int LPG, int NV>
+__global__ void __launch_bounds__(256) k_apply_dense(const __grid_constant__ StepDev P, float* grad, int ldg) {
+  const int lane = threadIdx.x & 31, gl = lane & (LPG - 1), leader = lane & ~(LPG - 1);
+  const unsigned gmask = LPG == 32 ? 0xffffffffu : (((1u << LPG) - 1u) << leader);
+  const long long ngroups = (long long)gridDim.x * blockDim.x / LPG;
+  const bool adagrad = P.optimizer == CF_OPT_ADAGRAD;
+  for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPG; r < P.n_users; r += ngroups) {
+    const Row<NV> g = load_row<LPG, NV>(grad, r, ldg, P.nvec, gl);
+    bool nz = false;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) nz = nz || g.v[k].x != 0.f || g.v[k].y != 0.f || g.v[k].z != 0.f || g.v[k].w != 0.f;
+    if (!__any_sync(gmask, nz)) continue;
+    const Row<NV> cur = load_row<LPG, NV>(P.U, r, P.ld, P.nvec, gl);
+    Row<NV> acc = adagrad ? load_row<LPG, NV>(P.accU, r, P.ld, P.nvec, gl, 1.f) : zero_row<NV>(), p;
+    apply_math<LPG, NV>(P, cur, acc, g, p, gmask);
+    if (adagrad) store_row<LPG, NV>(P.accU, r, P.ld, P.nvec, gl, acc);
+    store_row<LPG, NV>(P.U, r, P.ld, P.nvec, gl, p);
+    store_row<LPG, NV>(grad, r, ldg, P.nvec, gl, zero_row<NV>());
+  }
+}
+
+__global__ void __launch_bounds__(256) k_apply_dense_scalar(float* b, float* accb, float* grad, long long n, int adagrad, float lr) {
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+    const float g = __ldcg(grad + r);
+    if (g == 0.f) continue;
+    if (adagrad) {
+      const float a = fmaf(g, g, __ldcg(accb + r));
+      __stcg(accb + r, a);
+      __stcg(b + r, fmaf(-lr * g, rsqrtf(a), __ldcg(b + r)));
+    } else {
+      __stcg(b + r, fmaf(-lr, g, __ldcg(b + r)));
+    }
+    __stcg(grad + r, 0.f);
+  }
+}
+}  // namespace
+
+extern "C" int cf_apply_dense(const cf_apply_args* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  CF_CHECK_ARG(a != nullptr && a->table && a->grads, "cf_apply_dense: NULL pointer");
+  CF_CHECK_ARG(a->n_rows > 0, "cf_apply_dense: empty table");
+  CF_CHECK_ARG(a->optimizer == CF_OPT_SGD || a->acc, "cf_apply_dense: Adagrad needs the accumulator table");
+  static int sms = 0;
+  if (!sms) sms = cf_num_sms();
+  if (a->ld == 1) {   // a bias vector (GBPR's b)
+    long long grid = (a->n_rows + 255) / 256;
+    if (grid > (long long)sms * 8) grid = (long long)sms * 8;
+    k_apply_dense_scalar<<<(unsigned)grid, 256, 0, stream>>>(a->table, a->acc, const_cast<float*>(a->grads), a->n_rows, a->optimizer == CF_OPT_ADAGRAD, a->lr);
+    CF_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  CF_CHECK_ARG(a->d > 0 && a->ld >= a->d && a->ld % 4 == 0 && a->ld <= 512 && a->ldg >= a->ld && a->ldg % 4 == 0, "cf_apply_dense: bad d/ld/ldg");
+  if (a->model == CF_MODEL_CML) CF_CHECK_ARG(a->clip_norm > 0.f, "cf_apply_dense: CML needs clip_norm > 0");
+  StepDev P = {};
+  P.U = a->table; P.accU = a->acc; P.n_users = a->n_rows; P.d = a->d; P.ld = a->ld; P.nvec = a->ld / 4;
+  P.model = a->model; P.optimizer = a->optimizer; P.lr = a->lr; P.clip = a->clip_norm;
+  const int nvec = P.nvec;
+  const int lpg = nvec <= 8 ? 8 : (nvec <= 16 ? 16 : 32);
+  long long grid = (a->n_rows + (256 / lpg) - 1) / (256 / lpg);
+  if (grid > (long long)sms * 8) grid = (long long)sms * 8;
+  float* g = const_cast<float*>(a->grads);
+  if (nvec <= 8) k_apply_dense<8, 1><<<(unsigned)grid, 256, 0, stream>>>(P, g, a->ldg);
+  else if (nvec <= 16) k_apply_dense<16, 1><<<(unsigned)grid, 256, 0, stream>>>(P, g, a->ldg);
+  else if (nvec <= 32) k_apply_dense<32, 1><<<(unsigned)grid, 256, 0, stream>>>(P, g, a->ldg);
+  else if (nvec <= 64) k_apply_dense<32, 2><<<(unsigned)grid, 256, 0, stream>>>(P, g, a->ldg);
+  else k_apply_dense<32, 4><<<(unsigned)grid, 256, 0, stream>>>(P, g, a->ldg);
   CF_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -43,6 +43,8 @@ struct StepDev {
   float* gradV;          // exchange mode (multi-GPU): V/n_items describe FETCHED item rows; item-row gradients are
                          // red.added into gradV[row] (stride ld) instead of being applied here
   long long rank_items;  // CML rank weight uses the GLOBAL item count
+  float *gradU, *gradb;  // replicated data-parallel mode: user-row (and GBPR bias) gradients are red.added into dense
+                         // tables as well (with gradV = [n_items, ld]); nothing is applied by the step kernels
   // peer-pull variant of the exchange mode: item ids are GLOBAL, row i lives at peerV[i % n_peers] + (i / n_peers) * ld
   // (the owner's shard, mapped over NVLink), its gradient goes to gradV[gslot_*]
   const float* peerV[CF_MAX_PEERS];
@@ -150,8 +152,9 @@ __device__ __forceinline__ float sigm1(float x) { return -1.f / (1.f + expf(x));
 __device__ __forceinline__ bool in_range(long long r, long long n) { return r >= 0 && r < n; }
 
 // where item row r is read from: the local table, the fetched rows (exchange mode) or its owner's shard (peer pull)
+template <bool EXT>
 __device__ __forceinline__ const float* item_row_ptr(const StepDev& P, int r) {
-  if (P.n_peers > 0) {
+  if (EXT && P.n_peers > 0) {
     const int q = r / P.n_peers;
     return P.peerV[r - q * P.n_peers] + (long long)q * P.ld;
   }
@@ -225,7 +228,13 @@ __device__ __forceinline__ void apply_bias(const StepDev& P, long long r, float 
 
 enum { ROLE_NONE = 0, ROLE_USER = 1, ROLE_ITEM = 2, ROLE_NEG = 3, ROLE_GROUP = 4 };
 
-template <int MODEL, int LPG, int NV>
+// EXT = false is the single-GPU kernel; EXT = true adds the multi-GPU variants (fetched rows / peer pull / dense gradient
+// tables).  They are compiled apart because the single-GPU d=128 kernels sit exactly at 64 registers without spills (4
+// blocks per SM); the extra live values of the exchange paths cost a block of occupancy (-35 % measured on configs[1]),
+// and forcing 64 registers with __launch_bounds__(256, 4) makes the compiler re-load parameters everywhere (-18 %).
+// Register allocation at that edge is fragile: re-check `cuobjdump -res-usage` (REG:64 STACK:0 for k_step<*,32,1,false>)
+// after touching this kernel.
+template <int MODEL, int LPG, int NV, bool EXT>
 __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepDev P) {
   extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31;
@@ -237,8 +246,9 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepDev P)
   const bool sync = P.update == CF_UPDATE_SYNC;
   const bool adagrad = P.optimizer == CF_OPT_ADAGRAD;
   const bool want_loss = P.loss != nullptr;
-  const bool item_ext = P.gradV != nullptr;
-  const bool pull = P.n_peers > 0;
+  const bool item_ext = P.gradV != nullptr;   // (runtime also in the single-GPU kernel: ptxas allocates this form in 64 registers without spills)
+  const bool user_ext = EXT && P.gradU != nullptr;
+  const bool pull = EXT && P.n_peers > 0;
   const int nslot = 2 + P.T;
   float* sp = smem + (size_t)(threadIdx.x / LPG) * (2 * nslot) * P.ld;  // parameter rows of this group's slots
   float* sa = sp + (size_t)nslot * P.ld;                                // accumulator rows
@@ -256,12 +266,8 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepDev P)
 
     // ---------------------------------------------------------------- slots 0 (user) and 1 (positive item)
     int my_row = -1, my_role = ROLE_NONE;
-    int my_gslot = 0;   // peer pull: row of gradV that collects my item row's gradient
     if (gl == 0) { my_row = __ldg(P.pairs + 2 * bb); my_role = ROLE_USER; }
-    if (gl == 1) {
-      my_row = __ldg(P.pairs + 2 * bb + 1); my_role = ROLE_ITEM;
-      if (pull) my_gslot = __ldg(P.gslot_pos + bb);
-    }
+    if (gl == 1) { my_row = __ldg(P.pairs + 2 * bb + 1); my_role = ROLE_ITEM; }
     bool ok = my_role == ROLE_NONE || in_range(my_row, my_role == ROLE_USER ? P.n_users : P.n_items);
     // every entry id of the pair is validated up front (an invalid id skips the whole pair, nothing is written)
     for (int e = gl; e < E; e += LPG) {
@@ -301,17 +307,14 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepDev P)
           my_row = -1;
           const int e = e0 + gl - 2;
           if (gl - 2 < ne) {
-            if (e < P.W) {
-              my_row = __ldg(P.negs + bb * P.W + e); my_role = ROLE_NEG;
-              if (pull) my_gslot = __ldg(P.gslot_neg + bb * P.W + e);
-            }
+            if (e < P.W) { my_row = __ldg(P.negs + bb * P.W + e); my_role = ROLE_NEG; }
             else { my_row = __ldg(P.group + bb * P.G + (e - P.W)); my_role = ROLE_GROUP; }
           }
         }
         const bool is_user_tab = my_role == ROLE_USER || my_role == ROLE_GROUP;
         const bool stage_ui = first_tile && pass == first_pass;      // u / i parameter rows: once per pair
         const bool meta_ui = first_tile && commit_pass;              // u / i occurrence words + accumulators: once
-        const bool my_local = my_role != ROLE_NONE && (is_user_tab || !item_ext);   // rows this GPU owns and applies
+        const bool my_local = my_role != ROLE_NONE && (is_user_tab ? !user_ext : !item_ext);   // rows this GPU owns and applies
         if (sync && commit_pass && my_local && (gl >= 2 || meta_ui))
           occ_lo = __ldcg((is_user_tab ? P.metaU : P.metaV) + my_row);
         // ---- stage parameter rows (and the accumulators of rows this group will apply itself) into shared memory
@@ -320,8 +323,10 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepDev P)
         for (int s = stage_ui ? 0 : 2; s < 2 + ne; ++s) {
           const int r = __shfl_sync(gmask, my_row, leader + s);
           const int role = __shfl_sync(gmask, my_role, leader + s);
-          const float* src = (role == ROLE_USER || role == ROLE_GROUP) ? P.U + (long long)r * P.ld : item_row_ptr(P, r);
-          stage_row<LPG, NV>(sp + (size_t)s * P.ld, src, 0, P.ld, P.nvec, gl);
+          if (EXT && pull && (role == ROLE_ITEM || role == ROLE_NEG))
+            stage_row<LPG, NV>(sp + (size_t)s * P.ld, item_row_ptr<EXT>(P, r), 0, P.ld, P.nvec, gl);
+          else
+            stage_row<LPG, NV>(sp + (size_t)s * P.ld, (role == ROLE_USER || role == ROLE_GROUP) ? P.U : P.V, r, P.ld, P.nvec, gl);
         }
         if (adagrad && commit_pass) {
           for (int s = meta_ui ? 0 : 2; s < 2 + ne; ++s) {
@@ -329,12 +334,16 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepDev P)
             const int r = __shfl_sync(gmask, my_row, leader + s);
             const int role = __shfl_sync(gmask, my_role, leader + s);
             const bool utab = role == ROLE_USER || role == ROLE_GROUP;
-            if ((utab || !item_ext) && (!sync || occ <= 1u))
+            if ((utab ? !user_ext : !item_ext) && (!sync || occ <= 1u))
               stage_row<LPG, NV>(sa + (size_t)s * P.ld, utab ? P.accU : P.accV, r, P.ld, P.nvec, gl);
           }
         }
         if (sync && commit_pass && my_local && (gl >= 2 || last_tile) && occ_lo > 1u)
           my_slot = __ldcg((is_user_tab ? P.slotU : P.slotV) + my_row);
+        if (pull && commit_pass) {   // peer pull: the row of gradV that collects my item row's gradient
+          if (my_role == ROLE_NEG) my_slot = __ldg(P.gslot_neg + bb * P.W + (e0 + gl - 2));
+          if (my_role == ROLE_ITEM && last_tile) my_slot = __ldg(P.gslot_pos + bb);
+        }
         cp_async_wait_all();
         __syncwarp(gmask);
 
@@ -446,9 +455,17 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepDev P)
           }
           float* Tb = utab ? P.U : P.V;
           float* Ab = utab ? P.accU : P.accV;
-          if (item_ext && !utab) {   // a fetched (remote) item row: its gradient goes back to the owner
-            const int gs = pull ? __shfl_sync(gmask, my_gslot, leader + s) : r;
-            float* gr = P.gradV + (long long)gs * P.ld;
+          // a fetched (remote) / replicated row: its gradient goes to the exchange buffer (row = the id, or the slot
+          // given by gslot_* in peer-pull mode).  The EXT = false form is kept exactly as ptxas likes it (see above).
+          bool to_ext;
+          if constexpr (EXT) to_ext = utab ? user_ext : item_ext;
+          else to_ext = item_ext && !utab;
+          if (to_ext) {
+            int gs = r;
+            if constexpr (EXT) {
+              if (pull && !utab) gs = __shfl_sync(gmask, my_slot, leader + s);
+            }
+            float* gr = ((EXT && utab) ? P.gradU : P.gradV) + (long long)gs * P.ld;
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
               const int v = gl + k * LPG;
@@ -475,7 +492,12 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepDev P)
           if (gl == 1) my_gb = S;
           const bool item_slot = (my_role == ROLE_NEG) || (gl == 1 && last_tile);
           if (item_slot) {
-            if (!sync || occ_lo <= 1u) apply_bias(P, my_row, my_b, my_gb);
+            bool sent = false;
+            if constexpr (EXT) {
+              if (item_ext) { atomicAdd(P.gradb + my_row, my_gb); sent = true; }
+            }
+            if (sent) {}
+            else if (!sync || occ_lo <= 1u) apply_bias(P, my_row, my_b, my_gb);
             else atomicAdd(P.staging + (long long)my_slot * P.lds + P.ld, my_gb);
           }
         }
@@ -584,6 +606,6 @@ typedef void (*scatter_kernel_t)(const StepDev, const int32_t*, const float*, lo
 }  // namespace cfstep
 
 // one instantiation unit per (model, row shape): build.py generates build/gen/cf_step_inst_<m>_<s>.cu defining these
-#define CF_STEP_PICK_DECL(M, S) cfstep::step_kernel_t cf_step_pick_##M##_##S()
+#define CF_STEP_PICK_DECL(M, S) cfstep::step_kernel_t cf_step_pick_##M##_##S(); cfstep::step_kernel_t cf_step_pick_ext_##M##_##S()
 #define CF_APPLY_PICK_DECL(S) cfstep::step_kernel_t cf_apply_pick_##S()
 #define CF_SCATTER_PICK_DECL(S) cfstep::scatter_kernel_t cf_scatter_pick_##S()

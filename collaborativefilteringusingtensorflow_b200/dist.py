@@ -16,6 +16,8 @@ rank maps the other ranks' item shards (CUDA IPC) and the fused kernel reads eac
 memory; only ids and gradient rows still travel through NCCL.  It moves one row per OCCURRENCE instead of one per
 unique id, so it wins when minibatches barely repeat items (huge catalogues: BASELINE configs[4]) and loses when they
 do (configs[1]); ``'auto'`` measures the repeat ratio on the first minibatch and picks.
+Small tables (GBPR's configs[2]: 42 MB) are not sharded at all: ``ReplicatedTrainer`` keeps every table on every GPU, each
+rank turns its B pairs into dense gradient tables, ONE all_reduce sums them and every rank applies the same update.
 Evaluation: every rank scores its item shard for all query users (their embeddings are all-gathered), keeps a local
 top-K, and the [T, K] lists are all-gathered and merged (cf_topk_merge).
 
@@ -381,3 +383,174 @@ def distributed_topk(engine, query_rows, K, train_local_csr, world, rank, group=
     _lib.check(lib.cf_topk_merge(all_i.data_ptr(), all_v.data_ptr(), world, T, K, out_i.data_ptr(), out_v.data_ptr(),
                                  torch.cuda.current_stream(idx.device).cuda_stream), 'cf_topk_merge')
     return out_i, out_v
+
+
+def _world(group=None):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def distributed_evaluate(truth_local, pred_local, eval_metrics, k=5, split_method='cv', group=None):
+    """``evaluateCV`` / ``evaluateLOOV`` (reference metrics/ranking.py:94-120) over users sharded across ranks: every rank
+    runs cf_rank_metrics on ITS users' lists, the per-metric sums and the user count are all-reduced (one
+    all_reduce of 8 doubles), and every rank returns the global values: the mean over all users for CV metrics, the sum
+    for LOOV ones, ``None`` for unknown names -- as ranking.py does on one process.  A rank may hold no users."""
+    torch = _lib.require_cuda()
+    import torch.distributed as dist
+    from .metrics import ranking as R
+    world, _ = _world(group)
+    loov = split_method == 'loov'
+    cols = R._LOOV_COL if loov else R._CV_COL
+    dev = pred_local.device if torch.is_tensor(pred_local) else torch.device('cuda', torch.cuda.current_device())
+    acc = torch.zeros(10, dtype=torch.float64, device=dev)           # 8 column sums, #users, #users with no truth
+    n_local = len(truth_local)
+    if n_local != len(pred_local) or k <= 0:
+        raise ValueError(R._ERR)
+    if n_local:
+        vals, truth = R.per_user(truth_local, pred_local, k, loov=loov, device=dev)
+        acc[:8] = vals.sum(0)
+        acc[8] = n_local
+        acc[9] = (truth.row_lengths() == 0).sum()
+    if world > 1:
+        dist.all_reduce(acc, group=group)
+    acc = acc.cpu().numpy()
+    if acc[8] == 0:
+        raise ValueError(R._ERR)
+    if not loov and 'map' in eval_metrics and acc[9] > 0:
+        raise ZeroDivisionError('float division by zero')             # ranking.py:53 divides by len(yss_true[ind])
+    den = 1.0 if loov else acc[8]
+    return [(float(acc[cols[m]] / den) if m in cols else None) for m in eval_metrics]
+
+
+class DistributedALS(object):
+    """Weighted-ALS sweeps of WRMF over ``world`` GPUs: both factor tables are replicated, the rows a
+    half-sweep solves are range-sharded (rank r solves rows [r * chunk, (r + 1) * chunk) with chunk = ceil(n / world)).
+    Per half-sweep: partial Gram of the rank's slice of the FIXED side (tcgen05) -> all_reduce of the 128 x 128 Gram (64
+    KB) -> solve the local rows (cf_als_solve_rows) -> all_gather of the solved rows.  ``engine`` holds the full U / V;
+    ``user_csr`` / ``item_csr`` are the CSRs of the rank's OWN row range (columns = global ids of the other side)."""
+
+    def __init__(self, engine, user_csr, item_csr, group=None):
+        self.torch = _lib.require_cuda()
+        self.eng, self.group = engine, group
+        self.world, self.rank = _world(group)
+        self.csr = dict(users=user_csr, items=item_csr)
+        self.G = self.torch.zeros(128, 128, device=engine.device)
+        for side, n in (('users', engine.n_users), ('items', engine.n_items)):
+            lo, hi = self.row_range(n, self.world, self.rank)
+            if self.csr[side].shape[0] != hi - lo:
+                raise ValueError('%s CSR must hold rows [%d, %d) of this rank' % (side, lo, hi))
+
+    @staticmethod
+    def row_range(n, world, rank):
+        chunk = (int(n) + world - 1) // world
+        return min(rank * chunk, int(n)), min((rank + 1) * chunk, int(n))
+
+    def half_sweep(self, side):
+        torch, eng = self.torch, self.eng
+        import torch.distributed as dist
+        X, Y = (eng.U, eng.V) if side == 'users' else (eng.V, eng.U)
+        n_x, n_y = int(X.shape[0]), int(Y.shape[0])
+        self.G.zero_()
+        ylo, yhi = self.row_range(n_y, self.world, self.rank)
+        if yhi > ylo:
+            eng.als_gram(Y[ylo:yhi], self.G)
+        if self.world > 1:
+            dist.all_reduce(self.G, group=self.group)
+        xlo, xhi = self.row_range(n_x, self.world, self.rank)
+        if xhi > xlo:
+            eng.als_solve_rows(X[xlo:xhi], Y, self.csr[side], self.G)
+        if self.world > 1:
+            chunk = (n_x + self.world - 1) // self.world
+            mine = torch.zeros(chunk, X.shape[1], device=X.device)
+            mine[:xhi - xlo] = X[xlo:xhi]
+            every = torch.empty(self.world * chunk, X.shape[1], device=X.device)
+            dist.all_gather_into_tensor(every, mine, group=self.group)
+            X.copy_(every[:n_x])
+
+    def sweep(self):
+        self.half_sweep('users')
+        self.half_sweep('items')
+
+
+class ReplicatedTrainer(object):
+    """Data-parallel training with REPLICATED tables for models whose tables are small (GBPR on BASELINE configs[2]: 138k
+    x 27k x d=64 = 42 MB; sharding it would be all overhead, and GBPR's group users would need a second exchange on U).
+    Works for all four models.  Per minibatch every rank
+      1. samples its own B pairs (give every rank's sampler a different seed),
+      2. runs the fused step in gradient-only mode: every row gradient (and GBPR's bias gradient) is red.added into
+         dense tables gU / gV / gb that live in ONE flat buffer,
+      3. all-reduces that buffer (NCCL, NVLS in-switch reduction where available),
+      4. applies it with cf_apply_dense (rows with an all-zero gradient are skipped; the applied rows are re-zeroed),
+    which is the single-GPU minibatch-synchronous step on the global batch of world * B pairs: the same summed gradient
+    per row, applied once (TF1 sparse Adagrad semantics, bprmf.py:83-88).  The tables must start identical on every
+    rank: ``__init__`` broadcasts rank 0's."""
+
+    def __init__(self, model, sampler, group=None):
+        self.torch = torch = _lib.require_cuda()
+        self.lib = _lib.lib()
+        self.model, self.eng, self.sampler, self.group = model, model.engine, sampler, group
+        self.world, self.rank = _world(group)
+        eng = self.eng
+        if eng.update != 'sync':
+            raise ValueError('replicated training needs update="sync"')
+        nu, ni, ld = eng.n_users, eng.n_items, eng.ld
+        nb = ni if eng.b is not None else 0
+        self.flat = torch.zeros((nu + ni) * ld + nb, device=eng.device)
+        self.gU = self.flat[:nu * ld].view(nu, ld)
+        self.gV = self.flat[nu * ld:(nu + ni) * ld].view(ni, ld)
+        self.gb = self.flat[(nu + ni) * ld:] if nb else None
+        self.launches = 0
+        self.bytes_reduced = 0
+        if self.world > 1:
+            import torch.distributed as dist
+            for t in (eng.U, eng.V, eng.accU, eng.accV, eng.b, eng.accb):
+                if t is not None:
+                    dist.broadcast(t, 0, group=group)
+        if eng.kind == 'cml':    # one-time whole-table clip, then the clip fused into the apply suffices (DESIGN.md section 5)
+            eng._full_clip(torch.cuda.current_stream(eng.device).cuda_stream)
+
+    def _apply(self, table, acc, grad, ld, d):
+        eng = self.eng
+        ap = _lib.ApplyArgs()
+        ap.table, ap.acc, ap.n_rows, ap.d, ap.ld = _lib.ptr(table), _lib.ptr(acc), int(table.shape[0]), d, ld
+        ap.grads, ap.ldg = _lib.ptr(grad), ld
+        ap.model, ap.optimizer = eng.model_id, 0 if eng.optimizer == 'adagrad' else 1
+        ap.lr, ap.clip_norm = eng.hyper['lr'], eng.hyper['clip_norm']
+        _lib.check(self.lib.cf_apply_dense(ap, self.torch.cuda.current_stream(eng.device).cuda_stream), 'cf_apply_dense')
+
+    def step_chunk(self, pairs, negs=None, group=None, ratings=None, want_loss=True):
+        """One minibatch on explicit local batches; returns the GLOBAL minibatch loss (CUDA float64 [1]) or None."""
+        eng = self.eng
+        loss = eng.train_batches(pairs, negs, group, ratings, batch_size=int(pairs.shape[0]), want_loss=want_loss,
+                                 grad_tables=(self.gU, self.gV, self.gb))
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat, group=self.group)
+            if want_loss:
+                dist.all_reduce(loss, group=self.group)
+            self.bytes_reduced += self.flat.numel() * 4
+        self._apply(eng.U, eng.accU, self.gU, eng.ld, eng.d)
+        self._apply(eng.V, eng.accV, self.gV, eng.ld, eng.d)
+        if self.gb is not None:
+            self._apply(eng.b, eng.accb, self.gb, 1, 1)
+        self.launches += 3 + (1 if self.gb is not None else 0)
+        return loss
+
+    def step(self, n_minibatches=1, want_loss=True):
+        """Sample + run n minibatches; returns their global losses."""
+        torch = self.torch
+        B = getattr(self.sampler, 'rows_per_batch', self.sampler.batch_size)     # the rating sampler adds negative rows
+        chunk = self.sampler.next_chunk(n_minibatches)
+        out = []
+        for k in range(n_minibatches):
+            part = [t[k * B:(k + 1) * B] for t in chunk]
+            kind = self.eng.kind
+            if kind == 'gbpr':
+                out.append(self.step_chunk(part[0], part[1], group=part[2], want_loss=want_loss))
+            elif kind == 'wrmf':
+                out.append(self.step_chunk(part[0], ratings=part[1], want_loss=want_loss))
+            else:
+                out.append(self.step_chunk(part[0], part[1], want_loss=want_loss))
+        return torch.cat(out) if want_loss else None

@@ -147,10 +147,13 @@ class FactorEngine(object):
         x = x.to(device=self.device, dtype=torch.int32, non_blocking=True).contiguous()
         return x
 
-    def train_batches(self, pairs, negs=None, group=None, ratings=None, batch_size=None, want_loss=True, profile=None):
+    def train_batches(self, pairs, negs=None, group=None, ratings=None, batch_size=None, want_loss=True, profile=None,
+                      grad_tables=None):
         """Run ``n = rows / batch_size`` consecutive minibatches (the inner loop of bprmf.py:143-148).
         Index arrays may be numpy or torch (any int dtype); returns the per-minibatch loss as a CUDA float64
-        tensor (or None)."""
+        tensor (or None).  ``grad_tables=(gU, gV, gb)`` (dense, zeroed; gb only for GBPR) switches to the replicated
+        data-parallel mode: one minibatch whose row gradients are summed into the tables, nothing is applied
+        (dist.ReplicatedTrainer all-reduces and applies them)."""
         torch = self.torch
         pairs = self._as_i32(pairs)
         rows = int(pairs.shape[0])
@@ -196,6 +199,14 @@ class FactorEngine(object):
         loss = torch.zeros(nb, dtype=torch.float64, device=self.device) if want_loss else None
         a.loss = _lib.ptr(loss)
         stream = torch.cuda.current_stream(self.device).cuda_stream
+        if grad_tables is not None:
+            if nb != 1 or self.update != 'sync':
+                raise ValueError('the replicated mode takes one minibatch per call, update="sync"')
+            gU, gV, gb = grad_tables
+            a.gradU, a.gradV, a.gradb = _lib.ptr(gU), _lib.ptr(gV), _lib.ptr(gb)
+            _lib.check(self.lib.cf_train_steps(a, stream), 'cf_train_steps')
+            self.launches += 1
+            return loss
         if self._needs_full_clip and nb > 1:
             # the reference clips BOTH WHOLE tables after every step (cml.py:119-129); after the first such clip
             # every row has norm <= clip_norm and clipping only the touched rows (fused) is the same thing
@@ -312,6 +323,33 @@ class FactorEngine(object):
         a.workspace_bytes = need
         _lib.check(self.lib.cf_als_half_sweep(a, torch.cuda.current_stream(self.device).cuda_stream), 'cf_als_half_sweep')
         self.launches += 3
+
+    def als_gram(self, Y, G):
+        """G[128, 128] += Y^T Y (cf_als_gram); the Gram stage of the half-sweep on a slice of rows."""
+        torch = self.torch
+        n_y = int(Y.shape[0])
+        need = int(self.lib.cf_als_workspace_bytes(n_y))
+        if getattr(self, '_als_ws', None) is None or self._als_ws.numel() < need + 1024:
+            self._als_ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+        ws = (self._als_ws.data_ptr() + 1023) // 1024 * 1024
+        _lib.check(self.lib.cf_als_gram(_lib.ptr(Y), n_y, self.d, int(Y.stride(0)), _lib.ptr(G), ws, need,
+                                        torch.cuda.current_stream(self.device).cuda_stream), 'cf_als_gram')
+        self.launches += 2
+
+    def als_solve_rows(self, X, Y, csr, G):
+        """Solves the rows of X (a row-range view is fine) from the complete Gram G and their observed rows of Y."""
+        torch = self.torch
+        if self.d > 128:
+            raise ValueError('the ALS solver supports n_factors <= 128')
+        if csr.shape != (X.shape[0], Y.shape[0]):
+            raise ValueError('CSR shape %s does not match (%d, %d)' % (csr.shape, X.shape[0], Y.shape[0]))
+        a = _lib.AlsArgs()
+        a.X, a.Y, a.n_x, a.n_y, a.d = _lib.ptr(X), _lib.ptr(Y), int(X.shape[0]), int(Y.shape[0]), self.d
+        a.ldx, a.ldy = int(X.stride(0)), int(Y.stride(0))
+        a.indptr, a.indices = _lib.ptr(csr.indptr), _lib.ptr(csr.indices)
+        a.weight, a.reg = float(self.hyper['weight']), float(self.hyper['reg'])
+        _lib.check(self.lib.cf_als_solve_rows(a, _lib.ptr(G), torch.cuda.current_stream(self.device).cuda_stream), 'cf_als_solve_rows')
+        self.launches += 1
 
     def scores(self, users):
         """Dense [T, n_items] fp64 score matrix of ``__predict__`` (small inputs only)."""

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CF_ABI_VERSION 10
+#define CF_ABI_VERSION 11
 
 /* models */
 enum { CF_MODEL_BPR = 0, CF_MODEL_CML = 1, CF_MODEL_GBPR = 2, CF_MODEL_WRMF = 3 };
@@ -118,6 +118,11 @@ typedef struct cf_step_args {
   const int32_t* gslot_neg; /* [n_batches*B, W] row of gradV of negative w of pair b */
   int32_t n_peers;
   int32_t reserved0;
+  /* replicated data-parallel mode (small tables, e.g. GBPR's configs[2]: every GPU holds all tables): with gradU (and
+   * gradV = [n_items, ld], gradb = [n_items] for GBPR) set, EVERY row gradient of the minibatch is red.added into the
+   * dense gradient tables and nothing is applied; the caller all-reduces them and applies them with cf_apply_dense */
+  float* gradU;             /* [n_users, ld] or NULL */
+  float* gradb;             /* [n_items] (GBPR) or NULL */
 } cf_step_args;
 
 int cf_train_steps(const cf_step_args* args, void* stream);
@@ -163,6 +168,12 @@ int cf_apply_rows(const cf_apply_args* args, void* stream);
 int cf_ipc_export(const void* devptr, void* handle64, int64_t* offset_bytes);
 int cf_ipc_open(const void* handle64, void** base);
 int cf_ipc_close(void* base);
+
+/* Replicated data-parallel mode: apply a dense, already all-reduced gradient table grads[n_rows, ldg] to table[n_rows, ld]
+ * (rows / n / meta / slot / staging of cf_apply_args are not used; ld == 1 applies a bias vector).  Rows whose gradient
+ * is all zero are skipped -- a zero gradient is a no-op for Adagrad and SGD, so this equals the sparse apply of
+ * bprmf.py:83-88 -- and the rows that were applied are zeroed in grads. */
+int cf_apply_dense(const cf_apply_args* args, void* stream);
 
 /* row <- row * c / max(||row||_2, c) over a whole table: cml.py:119-122 (used once, after the first step) */
 int cf_clip_rows(float* table, int64_t n_rows, int32_t d, int32_t ld, float clip_norm, void* stream);
@@ -285,6 +296,13 @@ typedef struct cf_als_args {
 } cf_als_args;
 int64_t cf_als_workspace_bytes(int64_t n_y);
 int cf_als_half_sweep(const cf_als_args* args, void* stream);
+/* The two stages of the half-sweep on their own, for the multi-GPU sweep (rows of X sharded, Y replicated):
+ * cf_als_gram ACCUMULATES Y^T Y of the given rows into G[128, 128] (row stride 128; the caller zeroes G, every rank
+ * passes its slice of Y and the partial Grams are all-reduced); cf_als_solve_rows solves args->X's rows from the
+ * complete Gram (args->workspace is not used). */
+int cf_als_gram(const float* Y, int64_t n_y, int32_t d, int32_t ldy, float* G, void* workspace, int64_t workspace_bytes,
+                void* stream);
+int cf_als_solve_rows(const cf_als_args* args, const float* G, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Ranking metrics.  Replaces metrics/ranking.py:11-67 (pre/recall/ndcg/map/mrr) and :75-91 (hr/arhr):

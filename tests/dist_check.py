@@ -97,6 +97,74 @@ def main():
             same = bool(torch.equal(wi, gi) and torch.equal(wv, gv))
             print('%s sharded top-%d == single GPU: %s' % (kind, K, same))
             ok &= same
+    # ---- metrics: users sharded, sums all-reduced (every rank gets the global values)
+    from collaborativefilteringusingtensorflow_b200.dist import DistributedALS, distributed_evaluate
+    from collaborativefilteringusingtensorflow_b200.metrics.ranking import evaluateCV
+    from collaborativefilteringusingtensorflow_b200 import WRMF
+    rng = np.random.default_rng(11)
+    Tm, nm, km = 101, 300, 10                                            # 101 users: uneven shards
+    truth = [set(rng.choice(nm, int(rng.integers(1, 9)), replace=False).tolist()) for _ in range(Tm)]
+    pred = [rng.choice(nm, 15, replace=False).tolist() for _ in range(Tm)]
+    lo, hi = DistributedALS.row_range(Tm, world, rank)
+    names = ['pre', 'recall', 'ndcg', 'map', 'mrr']
+    got = distributed_evaluate(truth[lo:hi], pred[lo:hi], names, km)
+    want = evaluateCV(truth, pred, names, km)
+    same = bool(np.allclose(got, want, rtol=0, atol=1e-12))
+    flag = torch.tensor([int(same)], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print('sharded metrics == evaluateCV on every rank: %s' % bool(flag.item()))
+        ok &= bool(flag.item())
+    # ---- WRMF ALS: rows range-sharded, Gram all-reduced, solved rows all-gathered, vs the single-GPU sweeps
+    nu_a, ni_a, da = 301, 515, 64
+    Ra = lil_matrix((nu_a, ni_a), dtype=np.float32)
+    for u in range(nu_a):
+        Ra[u, rng.choice(ni_a, int(rng.integers(1, 30)), replace=False)] = 1
+    one = WRMF(nu_a, ni_a, weight=4.0, reg=0.3, n_factors=da, verbose=False, seed=2, solver='als', device=dev)
+    many = WRMF(nu_a, ni_a, weight=4.0, reg=0.3, n_factors=da, verbose=False, seed=2, solver='als', device=dev)
+    many.load_state_dict(one.state_dict())
+    csr = DeviceCSR.from_scipy(Ra, dev)
+    csr_t = csr.transpose()
+    ulo, uhi = DistributedALS.row_range(nu_a, world, rank)
+    ilo, ihi = DistributedALS.row_range(ni_a, world, rank)
+    als = DistributedALS(many.engine, csr.select_rows(torch.arange(ulo, uhi, device=dev)),
+                         csr_t.select_rows(torch.arange(ilo, ihi, device=dev)))
+    for sweep in range(2):
+        one.engine.als_half_sweep('users', csr)
+        one.engine.als_half_sweep('items', csr_t)
+        als.sweep()
+    a, b = one.state_dict(), many.state_dict()
+    good = all(bool(torch.allclose(a[k], b[k], rtol=5e-4, atol=1e-5)) for k in ('U', 'V'))
+    flag = torch.tensor([int(good)], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print('sharded ALS sweeps == single GPU on every rank: %s (max|dU| %.3g)' % (bool(flag.item()), float((a['U'] - b['U']).abs().max())))
+        ok &= bool(flag.item())
+    # ---- GBPR: replicated tables, dense gradients all-reduced, vs ONE GPU on the global minibatch
+    from collaborativefilteringusingtensorflow_b200 import GBPRMF
+    from collaborativefilteringusingtensorflow_b200.dist import ReplicatedTrainer
+    nu_g, ni_g, dg, Bg, Wg, Gg = 400, 300, 64, 1024, 5, 3
+    mkg = lambda s: GBPRMF(nu_g, ni_g, rho=0.4, gsize=Gg, reg=0.01, n_factors=dg, verbose=False, seed=s, device=dev)
+    rep = mkg(100 + rank)                                                # different init per rank: the trainer broadcasts rank 0's
+
+    class NoSamplerG(object):
+        batch_size = Bg
+    trg = ReplicatedTrainer(rep, NoSamplerG())
+    refg = mkg(100)
+    rng = np.random.default_rng(13)
+    for step in range(3):
+        pairs = np.stack([rng.integers(0, nu_g, (world, Bg)), rng.integers(0, ni_g, (world, Bg))], 2).astype(np.int32)
+        negs = rng.integers(0, ni_g, (world, Bg, Wg)).astype(np.int32)
+        grp = rng.integers(0, nu_g, (world, Bg, Gg)).astype(np.int32)
+        lg = trg.step_chunk(torch.from_numpy(pairs[rank]).to(dev), torch.from_numpy(negs[rank]).to(dev), group=torch.from_numpy(grp[rank]).to(dev))
+        lr_ = refg.step(pairs.reshape(-1, 2), negs.reshape(-1, Wg), grp.reshape(-1, Gg))
+    a, b = refg.state_dict(), rep.state_dict()
+    good = all(bool(torch.allclose(a[k], b[k], rtol=5e-5, atol=2e-6)) for k in a) and abs(float(lg.item()) - lr_) < 2e-5 * abs(lr_)
+    flag = torch.tensor([int(good)], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print('replicated GBPR (all-reduced dense gradients) == single GPU on every rank: %s' % bool(flag.item()))
+        ok &= bool(flag.item())
     if rank == 0:
         print('DIST_CHECK OK' if ok else 'DIST_CHECK FAILED')
     dist.barrier()

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     # field order/types are mirrored by hand; sizes follow from the C layout rules (natural alignment)
     assert C.sizeof(_lib.Csr) == 4 * 8 + 3 * 8
-    assert C.sizeof(_lib.StepArgs) == 6 * 8 + 2 * 8 + 2 * 4 + 4 * 8 + 4 * 4 + 4 * 4 + 6 * 4 + 6 * 8 + 8 + 2 * 8 + 2 * 8 + 8 * 8 + 2 * 8 + 2 * 4
+    assert C.sizeof(_lib.StepArgs) == 6 * 8 + 2 * 8 + 2 * 4 + 4 * 8 + 4 * 4 + 4 * 4 + 6 * 4 + 6 * 8 + 8 + 2 * 8 + 2 * 8 + 8 * 8 + 2 * 8 + 2 * 4 + 2 * 8
     assert C.sizeof(_lib.SampleArgs) == 2 * C.sizeof(_lib.Csr) + 3 * 8 + 6 * 4 + 5 * 8
     assert C.sizeof(_lib.TopkArgs) == 3 * 8 + 2 * 8 + 2 * 4 + 8 + 3 * 4 + 4 + C.sizeof(_lib.Csr) + 3 * 8 + 2 * 8
 
@@ -92,3 +92,24 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith(('.py', '.cu', '.cuh')):
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', open(os.path.join(d, f)).read(), flags=re.M), f
+
+
+def test_single_gpu_step_kernels_keep_four_blocks_per_sm():
+    """The d<=128 single-GPU step kernels must stay at <= 64 registers with no spill (4 x 256 threads per SM): at 75
+    registers configs[1] ran 35 % slower, at a forced 64 with spills 18 % slower."""
+    import shutil
+    import subprocess
+    exe = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(exe):
+        pytest.skip('no cuobjdump')
+    out = subprocess.run([exe, '-res-usage', _lib.LIB_PATH], capture_output=True, text=True).stdout
+    seen = 0
+    lines = out.splitlines()
+    for i, line in enumerate(lines):
+        m = re.search(r'k_stepILi([0-3])ELi32ELi1ELb0E', line)
+        if m and i + 1 < len(lines):
+            regs = int(re.search(r'REG:(\d+)', lines[i + 1]).group(1))
+            stack = int(re.search(r'STACK:(\d+)', lines[i + 1]).group(1))
+            assert regs <= 64 and stack == 0, (line, lines[i + 1])
+            seen += 1
+    assert seen == 4

@@ -50,3 +50,37 @@ def test_wrmf_als_trains_on_ml100k(ml100k):
     w = WRMF(943, 1682, 10, 'cv', names, 20., 10., 64, 100, 8, verbose=False, seed=1, solver='als')
     s = w.train(1, ml100k['tra'], ml100k['tst'], None)
     assert s[names.index('ndcg')] > 0.45, s        # the SGD reference path reaches 0.51 after 50 epochs
+
+
+@pytest.mark.parametrize('P', [1, 3])
+def test_row_sharded_sweep_equals_whole_sweep(P):
+    """The multi-GPU sweep's stages on one device: partial Grams of P row slices summed (what the all_reduce does) and
+    the rows solved range by range (cf_als_gram / cf_als_solve_rows) against cf_als_half_sweep on the whole table."""
+    import torch
+    from collaborativefilteringusingtensorflow_b200 import WRMF
+    from collaborativefilteringusingtensorflow_b200.dist import DistributedALS
+    from collaborativefilteringusingtensorflow_b200.sparse import DeviceCSR
+    nu, ni, d = 257, 400, 64
+    rng = np.random.default_rng(5)
+    R = _rand_matrix(rng, nu, ni, 25)
+    a = WRMF(nu, ni, weight=4.0, reg=0.3, n_factors=d, verbose=False, seed=2, solver='als')
+    b = WRMF(nu, ni, weight=4.0, reg=0.3, n_factors=d, verbose=False, seed=2, solver='als')
+    b.load_state_dict(a.state_dict())
+    csr = DeviceCSR.from_scipy(R, a.device)
+    a.engine.als_half_sweep('users', csr)
+    eng = b.engine
+    G = torch.zeros(128, 128, device=eng.device)
+    for p in range(P):
+        lo, hi = DistributedALS.row_range(ni, P, p)
+        eng.als_gram(eng.V[lo:hi], G)
+    for p in range(P):
+        lo, hi = DistributedALS.row_range(nu, P, p)
+        eng.als_solve_rows(eng.U[lo:hi], eng.V, csr.select_rows(torch.arange(lo, hi, device=eng.device)), G)
+    got, want = b.state_dict()['U'].cpu().numpy(), a.state_dict()['U'].cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5 * np.abs(want).max())   # fp32 Gram summed in another order
+    if P == 1:   # the world-1 driver object runs the same stages
+        c = WRMF(nu, ni, weight=4.0, reg=0.3, n_factors=d, verbose=False, seed=2, solver='als')
+        c.load_state_dict(a.state_dict())
+        a.engine.als_half_sweep('items', csr.transpose())
+        DistributedALS(c.engine, csr, csr.transpose()).half_sweep('items')
+        np.testing.assert_allclose(c.state_dict()['V'].cpu().numpy(), a.state_dict()['V'].cpu().numpy(), rtol=1e-4, atol=1e-5)

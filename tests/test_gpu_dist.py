@@ -148,3 +148,79 @@ def test_peer_pull_rejects_out_of_range_global_ids():
     with pytest.raises(RuntimeError, match='out of range'):
         m.engine.check_flags()
     assert torch.equal(before, m.engine.U)
+
+
+def test_distributed_evaluate_world1_equals_evaluate():
+    from collaborativefilteringusingtensorflow_b200.dist import distributed_evaluate
+    from collaborativefilteringusingtensorflow_b200.metrics.ranking import evaluateCV, evaluateLOOV
+    rng = np.random.default_rng(2)
+    T, n, k = 200, 500, 10
+    truth = [set(rng.choice(n, int(rng.integers(1, 12)), replace=False).tolist()) for _ in range(T)]
+    pred = [rng.choice(n, 20, replace=False).tolist() for _ in range(T)]
+    names = ['pre', 'recall', 'ndcg', 'map', 'mrr', 'nope']
+    assert distributed_evaluate(truth, pred, names, k) == evaluateCV(truth, pred, names, k)
+    one = [int(next(iter(t))) for t in truth]
+    assert distributed_evaluate(one, pred, ['hr', 'arhr', 'pre'], k, 'loov') == evaluateLOOV(one, pred, ['hr', 'arhr', 'pre'], k)
+    with pytest.raises(ValueError):
+        distributed_evaluate([], [], names, k)
+    with pytest.raises(ZeroDivisionError):
+        distributed_evaluate(truth[:3] + [set()], pred[:4], ['map'], k)
+
+
+def _mk4(kind, nu, ni, d):
+    from collaborativefilteringusingtensorflow_b200 import BPRMF, CML, GBPRMF, WRMF
+    if kind == 'bpr':
+        return BPRMF(nu, ni, n_factors=d, reg=0.05, verbose=False, seed=6)
+    if kind == 'cml':
+        return CML(nu, ni, n_factors=d, reg_cov=1.0, margin=1.0, init_stddev=0.05, verbose=False, seed=6)
+    if kind == 'gbpr':
+        return GBPRMF(nu, ni, rho=0.4, gsize=3, reg=0.01, n_factors=d, verbose=False, seed=6)
+    return WRMF(nu, ni, weight=2.0, reg=0.1, n_factors=d, verbose=False, seed=6)
+
+
+@pytest.mark.parametrize('halves', [1, 2])
+@pytest.mark.parametrize('kind,d', [('bpr', 128), ('cml', 64), ('gbpr', 64), ('gbpr', 20), ('wrmf', 100)])
+def test_replicated_mode_equals_fused_step(kind, d, halves):
+    """Gradient-only step into dense tables + cf_apply_dense (what every rank of ReplicatedTrainer runs) against the
+    plain fused step.  halves=2 accumulates two half-batches into the same dense tables before the apply -- the sum the
+    all_reduce forms over two ranks -- and must equal ONE step on the whole batch."""
+    import torch
+    from collaborativefilteringusingtensorflow_b200.dist import ReplicatedTrainer
+    nu, ni, B, W, G = 300, 200, 1024, 4, 3
+    a, b = _mk4(kind, nu, ni, d), _mk4(kind, nu, ni, d)
+    b.load_state_dict(a.state_dict())
+    rng = np.random.default_rng(8)
+
+    class NoSampler(object):
+        batch_size = B
+    tr = ReplicatedTrainer(b, NoSampler())
+    for s in range(3):
+        pairs = np.stack([rng.integers(0, nu, B), rng.integers(0, ni, B)], 1).astype(np.int32)
+        negs = rng.integers(0, ni, (B, W)).astype(np.int32)
+        group = rng.integers(0, nu, (B, G)).astype(np.int32)
+        ratings = (rng.random(B) < 0.5).astype(np.float32)
+        if kind == 'wrmf':
+            la = a.step(np.concatenate([pairs, ratings[:, None]], 1).astype(np.float64))
+        elif kind == 'gbpr':
+            la = a.step(pairs, negs, group)
+        else:
+            la = a.step(pairs, negs)
+        lb = 0.0
+        h = B // halves
+        for k in range(halves):
+            sl = slice(k * h, (k + 1) * h)
+            kw = dict(group=group[sl]) if kind == 'gbpr' else (dict(ratings=ratings[sl]) if kind == 'wrmf' else {})
+            last = k == halves - 1
+            if last:
+                lb += float(tr.step_chunk(torch.from_numpy(pairs[sl]).cuda(), None if kind == 'wrmf' else torch.from_numpy(negs[sl]).cuda(), **kw)[0].item())
+            else:   # another rank's contribution: gradients only
+                lb += float(b.engine.train_batches(pairs[sl], None if kind == 'wrmf' else negs[sl], batch_size=h,
+                                                   grad_tables=(tr.gU, tr.gV, tr.gb), **kw)[0].item())
+        b.engine.check_flags()
+        assert abs(la - lb) < 2e-5 * abs(la), (la, lb)
+        assert float(tr.flat.abs().max().item()) == 0.0           # the applied rows were re-zeroed
+        sa, sb = _state(a), _state(b)
+        for k in sa:
+            scale = float(np.abs(sa[k]).max())
+            np.testing.assert_allclose(sb[k], sa[k], rtol=5e-5, atol=5e-5 * max(scale, 1.0) if kind == 'cml' else 2e-6 * max(scale, 1.0),   # CML: ~25 rank-weighted (x10) gradients per item row, fp32 sums regrouped
+                                       err_msg='%s step %d %s' % (kind, s, k))
