@@ -3,6 +3,7 @@ catalogue keeps its global size and is row-sharded, like BASELINE.json configs[4
 users range-sharded, items sharded by item % N, per-minibatch NCCL all-to-all of requested item rows and their gradients
 (SURVEY.md 8e).  `--grow-catalogue` instead multiplies the catalogue by N (every rank owns n_items rows)."""
 import json
+import sys
 import os
 import time
 
@@ -41,6 +42,8 @@ def run_distributed(args, rank, world, device):
     torch.cuda.synchronize()
     t0 = time.time()
     e0.record()
+    if args.phases:
+        tr.step_events = []
     losses = tr.step(K)
     e1.record()
     torch.cuda.synchronize()
@@ -50,6 +53,9 @@ def run_distributed(args, rank, world, device):
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     launches = (tr.launches - l0) + (sampler.launches - s0)
+    if args.phases and rank == 0:
+        evs, tr.step_events = [e0] + tr.step_events, None
+        print('per-minibatch ms: ' + ' '.join('%.2f' % evs[k].elapsed_time(evs[k + 1]) for k in range(len(evs) - 1)), file=sys.stderr)
     sent = (tr.bytes_sent - b0) / K
     pulled = (tr.bytes_pulled - p0) / K * (world - 1) / world     # the share of the item rows that lives on other GPUs
     model.engine.check_flags()

@@ -211,7 +211,9 @@ static int train_steps_impl(const cf_step_args* a, cudaStream_t stream, cudaEven
   }
 
   int lpg = 32;
-  step_kernel_t kern = pick_kernel(a->model, P.nvec, &lpg, a->gradV != nullptr);
+  // the fetched-rows exchange mode (gradV only) is served by the single-GPU kernel (it always carried that branch, in
+  // 64 registers); only peer pull and the dense-gradient mode need the larger variant
+  step_kernel_t kern = pick_kernel(a->model, P.nvec, &lpg, a->n_peers > 0 || a->gradU != nullptr);
   static int sms = 0;
   if (!sms) sms = cf_num_sms();
   // entries (negatives + group users) staged per tile: all of them if the lanes (one per slot) and the shared

@@ -149,6 +149,7 @@ class DistributedTrainer(object):
         self.launches = 0
         self.bytes_sent = 0
         self.bytes_pulled = 0         # peer-pull mode: item-row bytes the fused kernel read (local + over NVLink)
+        self.step_events = None       # set to [] to collect one CUDA event per minibatch of step()
         self.phase_ms = None          # set to {} to collect per-phase CUDA-event times (synchronises every phase)
         self.item_transport = item_transport
         self.peer_ptrs = None         # device pointers of every rank's item shard (this rank's own included)
@@ -339,6 +340,10 @@ class DistributedTrainer(object):
                 self._keep = (self._keep + [plan])[-3:]     # plans were allocated on the side stream: keep them alive
             p, n = batch(k)
             out.append(self.step_chunk(p, n, B, want_loss, plan))
+            if self.step_events is not None:               # per-minibatch device timeline (no synchronisation)
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(main)
+                self.step_events.append(ev)
             if overlap and k + 1 < n_minibatches:
                 nxt = plan_async(k + 1)
         return torch.cat(out) if want_loss else None

@@ -71,7 +71,9 @@ def main():
                 Vg[p::world] = Vs[p][:item_shard_rows(ni, world, p)].cpu().numpy()
             for name, got, want in (('U', Ug, r['U'].cpu().numpy()), ('V', Vg, r['V'].cpu().numpy())):
                 err = np.abs(got - want).max()
-                good = np.allclose(got, want, rtol=5e-5, atol=2e-6 if kind == 'bpr' else 1e-5)   # CML: fp32 sums regrouped per rank
+                # fp32 sums of a row's gradients are regrouped per rank: the more ranks, the more duplicates per row in the
+                # global minibatch; CML's rank-weighted coefficients (~10) amplify that
+                good = np.allclose(got, want, rtol=5e-5, atol=(2e-6 if kind == 'bpr' else 1e-5) * max(1, world // 2))
                 print('%s %s max|diff| = %.3g %s' % (kind, name, err, 'ok' if good else 'MISMATCH'))
                 ok &= bool(good)
         # ---- evaluation: item-sharded top-K + all-gather merge vs single GPU
@@ -110,6 +112,8 @@ def main():
     got = distributed_evaluate(truth[lo:hi], pred[lo:hi], names, km)
     want = evaluateCV(truth, pred, names, km)
     same = bool(np.allclose(got, want, rtol=0, atol=1e-12))
+    if not same:
+        print('rank %d metrics %r vs %r' % (rank, got, want))
     flag = torch.tensor([int(same)], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
@@ -135,6 +139,8 @@ def main():
         als.sweep()
     a, b = one.state_dict(), many.state_dict()
     good = all(bool(torch.allclose(a[k], b[k], rtol=5e-4, atol=1e-5)) for k in ('U', 'V'))
+    if not good:
+        print('rank %d ALS diffs %s' % (rank, {k: float((a[k] - b[k]).abs().max()) for k in ('U', 'V')}))
     flag = torch.tensor([int(good)], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
@@ -159,7 +165,10 @@ def main():
         lg = trg.step_chunk(torch.from_numpy(pairs[rank]).to(dev), torch.from_numpy(negs[rank]).to(dev), group=torch.from_numpy(grp[rank]).to(dev))
         lr_ = refg.step(pairs.reshape(-1, 2), negs.reshape(-1, Wg), grp.reshape(-1, Gg))
     a, b = refg.state_dict(), rep.state_dict()
-    good = all(bool(torch.allclose(a[k], b[k], rtol=5e-5, atol=2e-6)) for k in a) and abs(float(lg.item()) - lr_) < 2e-5 * abs(lr_)
+    diffs = {k: float((a[k] - b[k]).abs().max()) for k in a}
+    good = all(bool(torch.allclose(a[k], b[k], rtol=5e-5, atol=2e-6 * max(1, world // 2))) for k in a) and abs(float(lg.item()) - lr_) < 2e-5 * abs(lr_)
+    if not good:
+        print('rank %d GBPR diffs %s loss %r vs %r' % (rank, diffs, float(lg.item()), lr_))
     flag = torch.tensor([int(good)], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
