@@ -304,7 +304,19 @@ extern "C" int cf_train_steps_profiled(const cf_step_args* a, void* stream_, flo
 extern "C" int cf_apply_rows(const cf_apply_args* a, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   CF_CHECK_ARG(a != nullptr, "cf_apply_rows: args is NULL");
-  CF_CHECK_ARG(a->table && a->rows && a->grads && a->meta && a->slot && a->slot_row && a->staging && a->counters, "cf_apply_rows: NULL pointer");
+  CF_CHECK_ARG(a->table && a->rows && (a->grads || a->n_segs > 0) && a->meta && a->slot && a->slot_row && a->staging && a->counters, "cf_apply_rows: NULL pointer");
+  CF_CHECK_ARG(a->n_segs >= 0 && a->n_segs <= CF_MAX_PEERS, "cf_apply_rows: n_segs must be in [0, %d]", CF_MAX_PEERS);
+  GradSegs S = {};
+  S.n = a->n_segs;
+  for (int p = 0; p < a->n_segs; ++p) {
+    S.base[p] = a->seg_grads[p];
+    S.start[p] = a->seg_start[p];
+    CF_CHECK_ARG(a->seg_start[p] <= a->seg_start[p + 1] && (a->seg_start[p] == a->seg_start[p + 1] || a->seg_grads[p] != nullptr), "cf_apply_rows: bad segment %d", p);
+  }
+  if (a->n_segs > 0) {
+    S.start[a->n_segs] = a->seg_start[a->n_segs];
+    CF_CHECK_ARG(a->seg_start[0] == 0 && a->seg_start[a->n_segs] == a->n, "cf_apply_rows: the segments must cover the n rows");
+  }
   CF_CHECK_ARG(a->d > 0 && a->ld >= a->d && a->ld % 4 == 0 && a->ld <= 512 && a->ldg >= a->ld && a->ldg % 4 == 0, "cf_apply_rows: bad d/ld/ldg");
   CF_CHECK_ARG(a->optimizer == CF_OPT_SGD || a->acc, "cf_apply_rows: Adagrad needs the accumulator table");
   CF_CHECK_ARG(a->n >= 0 && a->staging_rows >= a->n, "cf_apply_rows: staging_rows %lld < n %lld", (long long)a->staging_rows, (long long)a->n);
@@ -325,7 +337,7 @@ extern "C" int cf_apply_rows(const cf_apply_args* a, void* stream_) {
   if (sgrid > cap) sgrid = cap;
   if (agrid > cap) agrid = cap;
   k_count_rows<<<(unsigned)cgrid, 256, 0, stream>>>(P, a->rows, a->n);
-  pick_scatter(P.nvec)<<<(unsigned)sgrid, 256, 0, stream>>>(P, a->rows, a->grads, a->n, a->ldg);
+  pick_scatter(P.nvec)<<<(unsigned)sgrid, 256, 0, stream>>>(P, a->rows, a->grads, a->n, a->ldg, S);
   pick_apply(P.nvec)<<<(unsigned)agrid, 256, 0, stream>>>(P);
   CF_CUDA_OK(cudaGetLastError());
   return 0;

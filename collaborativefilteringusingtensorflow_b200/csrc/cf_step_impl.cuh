@@ -569,9 +569,18 @@ __global__ void __launch_bounds__(256) k_apply_staged(const __grid_constant__ St
 // Owner side of the multi-GPU exchange: n gradient rows (grads[k], stride ldg) for table rows rows[k] of THIS GPU's shard
 // (described as the "U" table of P).  A row received once is applied straight away; a row requested by several GPUs is
 // summed in its staging slot and applied by k_apply_staged -- the same "sum duplicates, apply once" rule.
+// owner-pull variant: the gradient rows stay in the requesters' buffers (peer memory over NVLink); rows
+// [start[p], start[p + 1]) are read from base[p], consecutive
+struct GradSegs {
+  const float* base[CF_MAX_PEERS];
+  long long start[CF_MAX_PEERS + 1];
+  int n;
+};
+
 template <int LPG, int NV>
 __global__ void __launch_bounds__(256) k_scatter_rows(const __grid_constant__ StepDev P, const int32_t* __restrict__ rows,
-                                                      const float* __restrict__ grads, long long n, int ldg) {
+                                                      const float* __restrict__ grads, long long n, int ldg,
+                                                      const __grid_constant__ GradSegs S) {
   const int lane = threadIdx.x & 31, gl = lane & (LPG - 1), leader = lane & ~(LPG - 1);
   const unsigned gmask = LPG == 32 ? 0xffffffffu : (((1u << LPG) - 1u) << leader);
   const long long ngroups = (long long)gridDim.x * blockDim.x / LPG;
@@ -580,7 +589,15 @@ __global__ void __launch_bounds__(256) k_scatter_rows(const __grid_constant__ St
     const long long r = __ldg(rows + k);
     if (!in_range(r, P.n_users)) continue;   // flagged by the counting kernel
     const unsigned occ = __ldcg(P.metaU + r);
-    const Row<NV> g = load_row<LPG, NV>(grads, k, ldg, P.nvec, gl);
+    const float* gsrc = grads;
+    long long gk = k;
+    if (S.n > 0) {
+      int p = 0;
+      while (p + 1 < S.n && k >= S.start[p + 1]) ++p;
+      gsrc = S.base[p];
+      gk = k - S.start[p];
+    }
+    const Row<NV> g = load_row<LPG, NV>(gsrc, gk, ldg, P.nvec, gl);
     if (occ <= 1u) {
       const Row<NV> cur = load_row<LPG, NV>(P.U, r, P.ld, P.nvec, gl);
       Row<NV> acc, p;
@@ -601,7 +618,7 @@ __global__ void __launch_bounds__(256) k_scatter_rows(const __grid_constant__ St
 }
 
 typedef void (*step_kernel_t)(const StepDev);
-typedef void (*scatter_kernel_t)(const StepDev, const int32_t*, const float*, long long, int);
+typedef void (*scatter_kernel_t)(const StepDev, const int32_t*, const float*, long long, int, const GradSegs);
 
 }  // namespace cfstep
 

@@ -30,7 +30,8 @@ from . import _lib
 
 
 class ExchangePlan(object):
-    __slots__ = ('n_req', 'occ_local', 'send_counts', 'recv_counts', 'recv_local_rows', 'req_global', 'send_rows')
+    __slots__ = ('n_req', 'occ_local', 'send_counts', 'recv_counts', 'recv_local_rows', 'req_global', 'send_rows',
+                 'peer_offsets')
 
 
 class ItemExchange(object):
@@ -88,12 +89,25 @@ class ItemExchange(object):
         p.req_global = req_global
         return p
 
-    def plan_exchange(self, p):
-        """Collective half: tell every owner how many and which of its rows this rank needs."""
+    def plan_exchange(self, p, all_counts=False):
+        """Collective half: tell every owner how many and which of its rows this rank needs.  With ``all_counts`` the whole
+        P x P count matrix is all-gathered, which also tells an owner WHERE its segment starts in every requester's
+        buffers (``peer_offsets``: what the owner-pull apply needs to read the gradient rows in place)."""
         torch = self.torch
-        recv_counts = torch.empty_like(p.send_counts)
-        self._a2a(recv_counts, p.send_counts, None, None)
-        sc, rc = p.send_counts.tolist(), recv_counts.tolist()
+        p.peer_offsets = None
+        if all_counts:
+            M = torch.empty(self.world * self.world, dtype=p.send_counts.dtype, device=p.send_counts.device)
+            if self.world == 1:
+                M[:] = p.send_counts
+            else:
+                self.dist.all_gather_into_tensor(M, p.send_counts.contiguous(), group=self.group)
+            M = M.view(self.world, self.world).tolist()
+            sc, rc = M[self.rank], [M[q][self.rank] for q in range(self.world)]
+            p.peer_offsets = [sum(M[q][:self.rank]) for q in range(self.world)]
+        else:
+            recv_counts = torch.empty_like(p.send_counts)
+            self._a2a(recv_counts, p.send_counts, None, None)
+            sc, rc = p.send_counts.tolist(), recv_counts.tolist()
         recv_rows = torch.empty(sum(rc), dtype=torch.int32, device=p.send_rows.device)
         self._a2a(recv_rows, p.send_rows, rc, sc)
         p.send_counts, p.recv_counts = sc, rc
@@ -153,6 +167,7 @@ class DistributedTrainer(object):
         self.phase_ms = None          # set to {} to collect per-phase CUDA-event times (synchronises every phase)
         self.item_transport = item_transport
         self.peer_ptrs = None         # device pointers of every rank's item shard (this rank's own included)
+        self._gbuf, self.peer_gbuf = None, None
         self._peer_bases = []
         self._pull = False
         if item_transport != 'nccl':
@@ -161,19 +176,23 @@ class DistributedTrainer(object):
             self.eng._full_clip(self.torch.cuda.current_stream(self.eng.device).cuda_stream)
 
     def _map_peer_shards(self):
-        """Exchanges CUDA IPC handles of the item shards and maps every peer's shard into this process."""
-        import ctypes as C
-        torch, dist = self.torch, self.ex.dist
+        """Maps every peer's item shard into this process."""
         if self.world > _lib.MAX_PEERS:
             raise ValueError('peer pull supports up to %d GPUs on one node' % _lib.MAX_PEERS)
-        dev = self.eng.device
         self._pull = True if self.item_transport == 'peer' else None    # 'auto': decided on the first minibatch
+        self.peer_ptrs = self._share(self.eng.V)
+
+    def _share(self, t):
+        """Exchanges CUDA IPC handles of tensor ``t`` (one per rank) and maps the peers' tensors into this process;
+        returns the ``world`` device pointers (this rank's own pointer at its own index).  Collective."""
+        import ctypes as C
+        torch, dist = self.torch, self.ex.dist
+        dev = self.eng.device
         if self.world == 1:
-            self.peer_ptrs = [self.eng.V.data_ptr()]
-            return
+            return [t.data_ptr()]
         handle = (C.c_ubyte * 64)()
         off = C.c_int64(0)
-        _lib.check(self.lib.cf_ipc_export(_lib.ptr(self.eng.V), C.addressof(handle), C.byref(off)), 'cf_ipc_export')
+        _lib.check(self.lib.cf_ipc_export(_lib.ptr(t), C.addressof(handle), C.byref(off)), 'cf_ipc_export')
         mine = torch.tensor(list(handle) + [(off.value >> (8 * k)) & 255 for k in range(8)], dtype=torch.uint8, device=dev)
         every = torch.empty(self.world, 72, dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(every, mine, group=self.ex.group)
@@ -181,20 +200,30 @@ class DistributedTrainer(object):
         ptrs = []
         for r in range(self.world):
             if r == self.rank:
-                ptrs.append(self.eng.V.data_ptr())
+                ptrs.append(t.data_ptr())
                 continue
             h = (C.c_ubyte * 64)(*every[r, :64].tolist())
             base = C.c_void_p(0)
             _lib.check(self.lib.cf_ipc_open(C.addressof(h), C.byref(base)), 'cf_ipc_open')
             self._peer_bases.append(base.value)
             ptrs.append(base.value + int.from_bytes(bytes(every[r, 64:72].tolist()), 'little'))
-        self.peer_ptrs = ptrs
+        return ptrs
+
+    def _grad_buffer(self, rows):
+        """The persistent, IPC-shared buffer of this rank's item-row gradients (owner-pull mode): sized once for the
+        largest possible minibatch (one row per item occurrence).  Collective on first use."""
+        if self._gbuf is None:
+            self._gbuf = self.torch.zeros(rows, self.eng.ld, device=self.eng.device)
+            self.peer_gbuf = self._share(self._gbuf)
+        if rows > self._gbuf.shape[0]:
+            raise ValueError('minibatch larger than the first one (%d > %d item occurrences)' % (rows, self._gbuf.shape[0]))
+        return self._gbuf
 
     def close(self):
         """Unmaps the peers' shards (call on every rank before the tables are freed)."""
         for b in self._peer_bases:
             self.lib.cf_ipc_close(b)
-        self._peer_bases, self.peer_ptrs = [], None
+        self._peer_bases, self.peer_ptrs, self.peer_gbuf = [], None, None
 
     def _decide_transport(self, plan, n_occ):
         """'auto': pull when the minibatches of all ranks together repeat items so rarely that one row per occurrence
@@ -242,21 +271,24 @@ class DistributedTrainer(object):
         ev = self._tick('', None)
         if int(pairs.shape[0]) != B:
             raise ValueError('the sharded step takes one minibatch per call')
+        peer = self.peer_ptrs is not None
         if plan is None:
-            plan = self.make_plan(pairs, negs)
-        elif getattr(plan, 'recv_local_rows', None) is None:
-            plan = self.ex.plan_exchange(plan)
-        elif self.peer_ptrs is not None and self.world > 1:
-            # peer pull relies on a barrier between the owners' applies of the previous minibatch and this minibatch's
-            # remote reads; the id exchange of the two branches above is one (it completes here only after every rank
-            # has enqueued it, i.e. after its previous apply), a plan exchanged earlier needs an explicit one
-            self.ex.dist.all_reduce(torch.zeros(1, device=eng.device), group=self.ex.group)
+            plan = self.make_plan(pairs, negs, local_only=True)
+        if getattr(plan, 'recv_local_rows', None) is None:
+            # In peer mode this exchange is also the barrier between the owners' applies (and gradient reads) of the
+            # previous minibatch and this minibatch's remote reads / buffer reuse: it completes here only after every
+            # rank has enqueued it, i.e. after its previous apply.
+            plan = self.ex.plan_exchange(plan, all_counts=peer)
+        elif peer:
+            raise ValueError('peer transport needs the plan exchanged inside step_chunk (pass a plan_local plan)')
         ev = self._tick('plan (dedupe + route ids)', ev)
         pull = self.peer_ptrs is not None and (self._pull if self._pull is not None
                                                else self._decide_transport(plan, pairs.shape[0] * (1 + negs.shape[1])))
         a = _lib.StepArgs()
+        if peer:   # gradients stay in this rank's shared buffer; the owners read them in place
+            Gbuf = self._grad_buffer(int(pairs.shape[0]) * (1 + int(negs.shape[1])))[:plan.n_req]
+            Gbuf.zero_()
         if pull:
-            Gbuf = torch.zeros(plan.n_req, eng.ld, device=eng.device)
             lp = pairs.to(torch.int32).contiguous()                                          # GLOBAL item ids
             ln = negs.to(torch.int32).contiguous()
             gp, gn = plan.occ_local[:, 0].contiguous(), plan.occ_local[:, 1:].contiguous()
@@ -267,7 +299,8 @@ class DistributedTrainer(object):
         else:
             Vbuf = self.ex.fetch(plan, eng.V)                                                # [n_req, ld]
             ev = self._tick('fetch rows (gather + all_to_all)', ev)
-            Gbuf = torch.zeros_like(Vbuf)
+            if not peer:
+                Gbuf = torch.zeros_like(Vbuf)
             lp = torch.stack([pairs[:, 0].to(torch.int32), plan.occ_local[:, 0]], dim=1).contiguous()
             ln = plan.occ_local[:, 1:].contiguous()
             a.V, a.n_items = _lib.ptr(Vbuf), plan.n_req
@@ -291,21 +324,36 @@ class DistributedTrainer(object):
         ev = self._tick('prep (remap ids, zero grads)', ev)
         _lib.check(self.lib.cf_train_steps(a, stream), 'cf_train_steps')
         ev = self._tick('k_count + k_step + k_apply_staged', ev)
-        recv = self.ex.push(plan, Gbuf)
-        ev = self._tick('push grads (all_to_all)', ev)                                                      # [n_recv, ld]
-        n = int(recv.shape[0])
+        if peer:
+            if self.world > 1:   # every rank's gradient buffer is complete once all ranks are past their step kernels
+                self.ex.dist.all_reduce(torch.zeros(1, device=eng.device), group=self.ex.group)
+            ev = self._tick('barrier (gradient buffers complete)', ev)
+            recv, n = None, int(plan.recv_local_rows.numel())
+        else:
+            recv = self.ex.push(plan, Gbuf)
+            ev = self._tick('push grads (all_to_all)', ev)                                                  # [n_recv, ld]
+            n = int(recv.shape[0])
         if n:
             ows = self._owner_workspace(n)
             ap = _lib.ApplyArgs()
             ap.table, ap.acc, ap.n_rows, ap.d, ap.ld = _lib.ptr(eng.V), _lib.ptr(eng.accV), eng.n_items, eng.d, eng.ld
             ap.rows, ap.grads, ap.n, ap.ldg = _lib.ptr(plan.recv_local_rows), _lib.ptr(recv), n, eng.ld
+            if peer:   # read the gradient rows in place from the requesters' buffers (NVLink), requester by requester
+                ap.n_segs, start = self.world, 0
+                for q in range(self.world):
+                    ap.seg_start[q] = start
+                    ap.seg_grads[q] = self.peer_gbuf[q] + plan.peer_offsets[q] * eng.ld * 4
+                    start += plan.recv_counts[q]
+                ap.seg_start[self.world] = start
             ap.model, ap.optimizer, ap.lr, ap.clip_norm = eng.model_id, a.optimizer, h['lr'], h['clip_norm']
             ap.meta, ap.slot, ap.slot_row = _lib.ptr(ows['meta']), _lib.ptr(ows['slot']), _lib.ptr(ows['slot_row'])
             ap.staging, ap.staging_rows, ap.counters = _lib.ptr(ows['staging']), ows['staging'].shape[0], _lib.ptr(eng.counters)
             _lib.check(self.lib.cf_apply_rows(ap, stream), 'cf_apply_rows')
         ev = self._tick('owner apply (cf_apply_rows)', ev)
         self.launches += 3 + 3
-        self.bytes_sent += ((0 if pull else plan.n_req) + n) * eng.ld * 4 + plan.n_req * 4
+        self.bytes_sent += ((0 if pull else plan.n_req) + (0 if peer else n)) * eng.ld * 4 + plan.n_req * 4
+        if peer:
+            self.bytes_pulled += n * eng.ld * 4
         if pull:
             self.bytes_pulled += int(pairs.shape[0]) * (1 + int(negs.shape[1])) * eng.ld * 4
         return loss

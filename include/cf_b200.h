@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CF_ABI_VERSION 11
+#define CF_ABI_VERSION 12
 
 /* models */
 enum { CF_MODEL_BPR = 0, CF_MODEL_CML = 1, CF_MODEL_GBPR = 2, CF_MODEL_WRMF = 3 };
@@ -158,6 +158,13 @@ typedef struct cf_apply_args {
   float* staging;          /* [staging_rows, ld + 4] zero */
   int64_t staging_rows;    /* >= n */
   int32_t* counters;       /* [4] */
+  /* owner-pull variant (NVLink peer memory, n_segs > 0; grads is not used): the n gradient rows are read in place from
+   * the requesters' gradient buffers instead of a receive buffer -- rows [seg_start[p], seg_start[p+1]) of `rows` come
+   * from seg_grads[p] (a pointer into requester p's buffer, mapped with cf_ipc_open), consecutive, stride ldg */
+  const float* seg_grads[CF_MAX_PEERS];
+  int64_t seg_start[CF_MAX_PEERS + 1];
+  int32_t n_segs;
+  int32_t reserved0;
 } cf_apply_args;
 int cf_apply_rows(const cf_apply_args* args, void* stream);
 

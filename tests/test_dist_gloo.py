@@ -58,6 +58,19 @@ def _worker(rank, world, port, n_items, ld, q):
             dist.all_gather(allm, req_mask)
             expect_global = sum(allm) * torch.arange(n_items, dtype=torch.float32)
             assert torch.allclose(summed, expect_global[rank::world])
+            # owner-pull variant: the whole count matrix is gathered, so the owner knows where its segment starts in every
+            # requester's gradient buffer; reading those segments in place (here: from an all-gathered copy standing in
+            # for NVLink peer memory) must give exactly what the push would have delivered
+            plan2 = ex.plan_exchange(ex.plan_local(ids, n_items), all_counts=True)
+            assert plan2.send_counts == plan.send_counts and plan2.recv_counts == plan.recv_counts
+            assert torch.equal(plan2.recv_local_rows, plan.recv_local_rows)
+            cap = 64 * 4
+            mine = torch.zeros(cap, ld)
+            mine[:plan.n_req] = grads
+            every = [torch.zeros(cap, ld) for _ in range(world)]
+            dist.all_gather(every, mine)
+            pulled = torch.cat([every[r][plan2.peer_offsets[r]:plan2.peer_offsets[r] + plan2.recv_counts[r]] for r in range(world)])
+            assert torch.equal(pulled, recv), 'segments read in place differ from the pushed rows'
         q.put((rank, 'ok'))
     except Exception as e:      # surface the failure in the parent
         import traceback

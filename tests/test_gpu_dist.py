@@ -224,3 +224,47 @@ def test_replicated_mode_equals_fused_step(kind, d, halves):
             scale = float(np.abs(sa[k]).max())
             np.testing.assert_allclose(sb[k], sa[k], rtol=5e-5, atol=5e-5 * max(scale, 1.0) if kind == 'cml' else 2e-6 * max(scale, 1.0),   # CML: ~25 rank-weighted (x10) gradients per item row, fp32 sums regrouped
                                        err_msg='%s step %d %s' % (kind, s, k))
+
+
+def test_owner_apply_reads_gradient_rows_in_place_from_segments():
+    """cf_apply_rows with the gradient rows left in three "requesters'" buffers (owner-pull segments) against the same
+    rows concatenated into one receive buffer: identical tables (rows received from several requesters are summed)."""
+    import torch
+    from collaborativefilteringusingtensorflow_b200 import CML, _lib
+    n_rows, d, counts = 500, 128, [300, 0, 450]
+    rng = np.random.default_rng(4)
+    out = []
+    ids = [np.sort(rng.choice(n_rows, c, replace=False)).astype(np.int32) for c in counts]
+    grads = [(0.1 * rng.standard_normal((c + 7, d))).astype(np.float32) for c in counts]      # 7 rows of other owners first
+    for mode in ('concat', 'segments'):
+        m = CML(10, n_rows, n_factors=d, init_stddev=0.05, verbose=False, seed=3)
+        eng = m.engine
+        rows = torch.from_numpy(np.concatenate(ids)).cuda()
+        n = int(rows.numel())
+        bufs = [torch.from_numpy(g).cuda() for g in grads]
+        cat = torch.cat([b[7:] for b in bufs]).contiguous()
+        ap = _lib.ApplyArgs()
+        ap.table, ap.acc, ap.n_rows, ap.d, ap.ld = _lib.ptr(eng.V), _lib.ptr(eng.accV), n_rows, d, eng.ld
+        ap.rows, ap.n, ap.ldg = _lib.ptr(rows), n, eng.ld
+        ap.model, ap.optimizer, ap.lr, ap.clip_norm = eng.model_id, 0, 0.1, 1.0
+        meta = torch.zeros(n_rows, dtype=torch.int32, device='cuda')
+        slot = torch.zeros(n_rows, dtype=torch.int32, device='cuda')
+        slot_row = torch.full((n,), -1, dtype=torch.int32, device='cuda')
+        staging = torch.zeros(n, eng.ld + 4, device='cuda')
+        ap.meta, ap.slot, ap.slot_row, ap.staging, ap.staging_rows = _lib.ptr(meta), _lib.ptr(slot), _lib.ptr(slot_row), _lib.ptr(staging), n
+        ap.counters = _lib.ptr(eng.counters)
+        if mode == 'concat':
+            ap.grads = _lib.ptr(cat)
+        else:
+            ap.n_segs, start = 3, 0
+            for q in range(3):
+                ap.seg_start[q] = start
+                ap.seg_grads[q] = bufs[q].data_ptr() + 7 * eng.ld * 4
+                start += counts[q]
+            ap.seg_start[3] = start
+        _lib.check(_lib.lib().cf_apply_rows(ap, torch.cuda.current_stream().cuda_stream), 'cf_apply_rows')
+        eng.check_flags()
+        assert int(meta.abs().sum().item()) == 0 and float(staging.abs().max().item()) == 0.0
+        out.append((eng.V.cpu().numpy(), eng.accV.cpu().numpy()))
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_array_equal(out[0][1], out[1][1])
