@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libcf_b200.so')
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 # enums of cf_b200.h
 MODEL_BPR, MODEL_CML, MODEL_GBPR, MODEL_WRMF = 0, 1, 2, 3
@@ -45,7 +45,7 @@ class ApplyArgs(C.Structure):
         ('rows', _p), ('grads', _p), ('n', C.c_int64), ('ldg', C.c_int32), ('model', C.c_int32),
         ('optimizer', C.c_int32), ('lr', C.c_float), ('clip_norm', C.c_float),
         ('meta', _p), ('slot', _p), ('slot_row', _p), ('staging', _p), ('staging_rows', C.c_int64), ('counters', _p),
-        ('seg_grads', _p * MAX_PEERS), ('seg_start', C.c_int64 * (MAX_PEERS + 1)), ('n_segs', C.c_int32), ('reserved0', C.c_int32),
+        ('seg_grads', _p * MAX_PEERS), ('seg_start', C.c_int64 * (MAX_PEERS + 1)), ('n_segs', C.c_int32), ('first_seg', C.c_int32),
     ]
 
 

@@ -314,6 +314,8 @@ extern "C" int cf_apply_rows(const cf_apply_args* a, void* stream_) {
     CF_CHECK_ARG(a->seg_start[p] <= a->seg_start[p + 1] && (a->seg_start[p] == a->seg_start[p + 1] || a->seg_grads[p] != nullptr), "cf_apply_rows: bad segment %d", p);
   }
   if (a->n_segs > 0) {
+    CF_CHECK_ARG(a->first_seg >= 0 && a->first_seg < a->n_segs, "cf_apply_rows: first_seg out of range");
+    S.rot = a->seg_start[a->first_seg];
     S.start[a->n_segs] = a->seg_start[a->n_segs];
     CF_CHECK_ARG(a->seg_start[0] == 0 && a->seg_start[a->n_segs] == a->n, "cf_apply_rows: the segments must cover the n rows");
   }

@@ -574,6 +574,7 @@ __global__ void __launch_bounds__(256) k_apply_staged(const __grid_constant__ St
 struct GradSegs {
   const float* base[CF_MAX_PEERS];
   long long start[CF_MAX_PEERS + 1];
+  long long rot;   // the rows are processed in rotated order (k + rot) mod n: every owner starts at another requester
   int n;
 };
 
@@ -585,7 +586,9 @@ __global__ void __launch_bounds__(256) k_scatter_rows(const __grid_constant__ St
   const unsigned gmask = LPG == 32 ? 0xffffffffu : (((1u << LPG) - 1u) << leader);
   const long long ngroups = (long long)gridDim.x * blockDim.x / LPG;
   const bool adagrad = P.optimizer == CF_OPT_ADAGRAD;
-  for (long long k = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPG; k < n; k += ngroups) {
+  for (long long k0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPG; k0 < n; k0 += ngroups) {
+    long long k = k0 + S.rot;
+    if (k >= n) k -= n;
     const long long r = __ldg(rows + k);
     if (!in_range(r, P.n_users)) continue;   // flagged by the counting kernel
     const unsigned occ = __ldcg(P.metaU + r);

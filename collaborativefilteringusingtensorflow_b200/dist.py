@@ -345,6 +345,7 @@ class DistributedTrainer(object):
                     ap.seg_grads[q] = self.peer_gbuf[q] + plan.peer_offsets[q] * eng.ld * 4
                     start += plan.recv_counts[q]
                 ap.seg_start[self.world] = start
+                ap.first_seg = (self.rank + 1) % self.world     # stagger the owners over the requesters (no incast)
             ap.model, ap.optimizer, ap.lr, ap.clip_norm = eng.model_id, a.optimizer, h['lr'], h['clip_norm']
             ap.meta, ap.slot, ap.slot_row = _lib.ptr(ows['meta']), _lib.ptr(ows['slot']), _lib.ptr(ows['slot_row'])
             ap.staging, ap.staging_rows, ap.counters = _lib.ptr(ows['staging']), ows['staging'].shape[0], _lib.ptr(eng.counters)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CF_ABI_VERSION 12
+#define CF_ABI_VERSION 13
 
 /* models */
 enum { CF_MODEL_BPR = 0, CF_MODEL_CML = 1, CF_MODEL_GBPR = 2, CF_MODEL_WRMF = 3 };
@@ -164,7 +164,8 @@ typedef struct cf_apply_args {
   const float* seg_grads[CF_MAX_PEERS];
   int64_t seg_start[CF_MAX_PEERS + 1];
   int32_t n_segs;
-  int32_t reserved0;
+  int32_t first_seg;       /* segment to start with (the rows are processed in rotated order): owner r starts at requester
+                            * r + 1 so that the P owners do not all read the same requester's buffer at the same time */
 } cf_apply_args;
 int cf_apply_rows(const cf_apply_args* args, void* stream);
 

@@ -262,6 +262,7 @@ def test_owner_apply_reads_gradient_rows_in_place_from_segments():
                 ap.seg_grads[q] = bufs[q].data_ptr() + 7 * eng.ld * 4
                 start += counts[q]
             ap.seg_start[3] = start
+            ap.first_seg = 2
         _lib.check(_lib.lib().cf_apply_rows(ap, torch.cuda.current_stream().cuda_stream), 'cf_apply_rows')
         eng.check_flags()
         assert int(meta.abs().sum().item()) == 0 and float(staging.abs().max().item()) == 0.0
