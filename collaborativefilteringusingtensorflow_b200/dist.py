@@ -29,6 +29,10 @@ import numpy as np
 from . import _lib
 
 
+class PeerMappingError(RuntimeError):
+    """CUDA IPC mapping of a peer's buffer failed on some rank (raised on EVERY rank, after a collective vote)."""
+
+
 class ExchangePlan(object):
     __slots__ = ('n_req', 'occ_local', 'send_counts', 'recv_counts', 'recv_local_rows', 'req_global', 'send_rows',
                  'peer_offsets')
@@ -171,7 +175,18 @@ class DistributedTrainer(object):
         self._peer_bases = []
         self._pull = False
         if item_transport != 'nccl':
-            self._map_peer_shards()
+            try:
+                self._map_peer_shards()
+                n_neg = getattr(sampler, 'n_neg', None)
+                if n_neg is not None:     # otherwise the gradient buffer is shared on the first minibatch
+                    self._grad_buffer(int(sampler.batch_size) * (1 + int(n_neg)))
+            except PeerMappingError as e:
+                if item_transport == 'peer':
+                    raise
+                import warnings
+                warnings.warn('peer memory is not available (%s): item rows and gradients travel through NCCL' % e)
+                self.close()
+                self._gbuf, self._pull = None, False
         if self.eng.kind == 'cml':   # one-time whole-table clip, then touched-row clips suffice
             self.eng._full_clip(self.torch.cuda.current_stream(self.eng.device).cuda_stream)
 
@@ -190,23 +205,44 @@ class DistributedTrainer(object):
         dev = self.eng.device
         if self.world == 1:
             return [t.data_ptr()]
+        # every rank runs both collectives whatever happens locally; a failure anywhere is voted and raised everywhere
+        err = None
         handle = (C.c_ubyte * 64)()
         off = C.c_int64(0)
-        _lib.check(self.lib.cf_ipc_export(_lib.ptr(t), C.addressof(handle), C.byref(off)), 'cf_ipc_export')
+        try:
+            _lib.check(self.lib.cf_ipc_export(_lib.ptr(t), C.addressof(handle), C.byref(off)), 'cf_ipc_export')
+        except RuntimeError as e:
+            err = e
+        import os
+        if os.environ.get('CF_IPC_FAIL_RANK') == str(self.rank):      # test hook: exercises the vote + NCCL fallback
+            err = RuntimeError('CF_IPC_FAIL_RANK test hook')
         mine = torch.tensor(list(handle) + [(off.value >> (8 * k)) & 255 for k in range(8)], dtype=torch.uint8, device=dev)
-        every = torch.empty(self.world, 72, dtype=torch.uint8, device=dev)
+        every = torch.empty(self.world * 72, dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(every, mine, group=self.ex.group)
-        every = every.cpu().numpy()
-        ptrs = []
+        every = every.view(self.world, 72).cpu().numpy()
+        ptrs, opened = [], []
         for r in range(self.world):
             if r == self.rank:
                 ptrs.append(t.data_ptr())
                 continue
+            if err is not None:
+                continue
             h = (C.c_ubyte * 64)(*every[r, :64].tolist())
             base = C.c_void_p(0)
-            _lib.check(self.lib.cf_ipc_open(C.addressof(h), C.byref(base)), 'cf_ipc_open')
-            self._peer_bases.append(base.value)
+            try:
+                _lib.check(self.lib.cf_ipc_open(C.addressof(h), C.byref(base)), 'cf_ipc_open')
+            except RuntimeError as e:
+                err = e
+                continue
+            opened.append(base.value)
             ptrs.append(base.value + int.from_bytes(bytes(every[r, 64:72].tolist()), 'little'))
+        ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.ex.group)
+        if int(ok.item()) == 0:
+            for b in opened:
+                self.lib.cf_ipc_close(b)
+            raise PeerMappingError(str(err) if err is not None else 'another rank could not map a peer buffer')
+        self._peer_bases.extend(opened)
         return ptrs
 
     def _grad_buffer(self, rows):

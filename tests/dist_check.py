@@ -166,8 +166,11 @@ def main():
         lr_ = refg.step(pairs.reshape(-1, 2), negs.reshape(-1, Wg), grp.reshape(-1, Gg))
     a, b = refg.state_dict(), rep.state_dict()
     diffs = {k: float((a[k] - b[k]).abs().max()) for k in a}
-    # accumulators hold the SQUARED summed gradient (twice its relative error); 8 ranks = ~140 regrouped terms per bias
-    good = all(bool(torch.allclose(a[k], b[k], rtol=5e-5 * (max(1, world // 2) if k.startswith('acc') else 1),
+    # Parameters: 5e-5 relative + 2e-6 * world absolute.  Accumulators hold the SQUARED summed gradient of ~17 * world
+    # regrouped fp32 terms per row (twice its relative error, and the single-GPU run's own atomics order varies from run
+    # to run: at world = 8 the eight ranks' references differ from the same replicated result by 0.004 .. 0.013 in accb):
+    # 1e-4 * world relative.
+    good = all(bool(torch.allclose(a[k], b[k], rtol=(1e-4 * world if k.startswith('acc') else 5e-5),
                                    atol=2e-6 * world)) for k in a) and abs(float(lg.item()) - lr_) < 2e-5 * abs(lr_)
     if not good:
         print('rank %d GBPR diffs %s loss %r vs %r' % (rank, diffs, float(lg.item()), lr_))
