@@ -1,6 +1,6 @@
 """B200-native pairwise-ranking training + full-catalog top-K evaluation behind the API of
-BinFuPKU/CollaborativeFilteringUsingTensorflow (models/pl/models/{bprmf,cml,gbprmf}.py, models/basic/models/wrmf.py,
-samplers/sampler_{ranking,uij_ranking,gbpr,rating}.py, metrics/ranking.py, utils/{IOUtil,Util}.py).
+BinFuPKU/CollaborativeFilteringUsingTensorflow (models/pl/models/{bprmf,cml,gbprmf}.py, models/basic/models/{wrmf,mf}.py,
+samplers/sampler_{ranking,uij_ranking,gbpr,rating}.py, metrics/{ranking,rating}.py, utils/{IOUtil,Util}.py).
 
 All arithmetic runs in hand-written sm_100a CUDA (libcf_b200.so, C ABI in include/cf_b200.h); there is no CPU fallback.
 """
@@ -20,4 +20,7 @@ def __getattr__(name):   # lazy: importing the package must work on a box withou
     if name == 'WRMF':
         from .models.basic.models.wrmf import WRMF
         return WRMF
+    if name == 'MF':
+        from .models.basic.models.mf import MF
+        return MF
     raise AttributeError(name)

@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libcf_b200.so')
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 # enums of cf_b200.h
 MODEL_BPR, MODEL_CML, MODEL_GBPR, MODEL_WRMF = 0, 1, 2, 3
@@ -91,6 +91,8 @@ _SIGNATURES = {
     'cf_step_launches_per_batch': (C.c_int32, []),
     'cf_apply_rows': (C.c_int, [C.POINTER(ApplyArgs), _p]),
     'cf_clip_rows': (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, _p]),
+    'cf_predict_pairs': (C.c_int, [_p, _p, _p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _p, C.c_int64, _p, _p, _p]),
+    'cf_rating_metrics': (C.c_int, [_p, C.c_int32, _p, C.c_int64, C.c_double, C.c_double, _p, _p]),
     'cf_apply_dense': (C.c_int, [C.POINTER(ApplyArgs), _p]),
     'cf_ipc_export': (C.c_int, [_p, _p, C.POINTER(C.c_int64)]),
     'cf_ipc_open': (C.c_int, [_p, C.POINTER(C.c_void_p)]),

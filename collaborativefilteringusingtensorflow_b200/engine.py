@@ -351,6 +351,24 @@ class FactorEngine(object):
         _lib.check(self.lib.cf_als_solve_rows(a, _lib.ptr(G), torch.cuda.current_stream(self.device).cuda_stream), 'cf_als_solve_rows')
         self.launches += 1
 
+    def predict_pairs(self, pairs):
+        """Scores of explicit (user, item) rows (``__predict`` of mf.py:66-72 fed with ``tst_tuple[:, :-1]``): float32
+        CUDA tensor [n]; pairs is int [n, 2] (numpy or torch)."""
+        torch = self.torch
+        pairs = self._as_i32(pairs)
+        if pairs.dim() != 2 or pairs.shape[1] != 2:
+            raise ValueError('pairs must be [n, 2]')
+        n = int(pairs.shape[0])
+        out = torch.empty(n, dtype=torch.float32, device=self.device)
+        if n == 0:
+            return out
+        _lib.check(self.lib.cf_predict_pairs(_lib.ptr(self.U), _lib.ptr(self.V), _lib.ptr(self.b), self.n_users, self.n_items,
+                                             self.d, self.ld, _SCORE_KIND[self.kind], _lib.ptr(pairs), n, _lib.ptr(out),
+                                             _lib.ptr(self.counters), torch.cuda.current_stream(self.device).cuda_stream),
+                   'cf_predict_pairs')
+        self.launches += 1
+        return out
+
     def scores(self, users):
         """Dense [T, n_items] fp64 score matrix of ``__predict__`` (small inputs only)."""
         torch = self.torch

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CF_ABI_VERSION 13
+#define CF_ABI_VERSION 14
 
 /* models */
 enum { CF_MODEL_BPR = 0, CF_MODEL_CML = 1, CF_MODEL_GBPR = 2, CF_MODEL_WRMF = 3 };
@@ -321,6 +321,20 @@ int cf_als_solve_rows(const cf_als_args* args, const float* G, void* stream);
  * ------------------------------------------------------------------------------------------------ */
 int cf_rank_metrics(const int32_t* pred, int32_t T, int32_t ldp, int32_t k, const int64_t* truth_indptr,
                     const int32_t* truth_indices, double* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Rating path.  cf_predict_pairs replaces `__predict` of models/basic/models/mf.py:66-72 (the
+ * scores of the fed (user, item) rows; CF_SCORE_* as in cf_topk_args; out-of-range ids set CF_FLAG_INDEX_RANGE in
+ * counters[1] and give NaN).  cf_rating_metrics replaces metrics/rating.py:4-17: it ADDS sum |t - p| to sums[0] and
+ * sum (t - p)^2 to sums[1] (fp64; the caller zeroes sums, divides by n and takes the root where rating.py does), with
+ * p clipped to [lo, hi] first (tf.clip_by_value of mf.py:81; pass -inf / +inf for the plain metrics).
+ * pred is float32 (pred_is_f64 = 0) or float64.
+ * ------------------------------------------------------------------------------------------------ */
+int cf_predict_pairs(const float* U, const float* V, const float* b, int64_t n_users, int64_t n_items, int32_t d,
+                     int32_t ld, int32_t score, const int32_t* pairs, int64_t n, float* out, int32_t* counters,
+                     void* stream);
+int cf_rating_metrics(const void* pred, int32_t pred_is_f64, const double* truth, int64_t n, double lo, double hi,
+                      double* sums, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Host-side loader.  Replaces the per-line Python loop of utils/IOUtil.py:7-16 (`loadSparseR`): parses

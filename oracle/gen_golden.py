@@ -17,6 +17,9 @@ What comes from where
   gbprmf.py:58-106, wrmf.py:52-88 are restated with torch autograd + torch.optim.Adagrad(lr,
   initial_accumulator_value=0.1, eps=0) (== TF1 AdagradOptimizer on summed sparse grads).  This is an
   INDEPENDENT restatement (autodiff, not the hand-derived gradients of oracle/steps.py).
+* rating_golden.json   -- outputs of the reference's own /root/reference/src/metrics/rating.py (imported as-is) on its
+  ``__main__`` toy input and seeded random inputs; plus the numpy oracle's 5-epoch MF run on ml-100k fold 1 with the
+  hyper-parameters of basic/testmf.py:18-26 (scored with the reference's rating.py).
 * e2e_golden.json      -- oracle-trained ml-100k fold-1 metrics (reference hyper-parameters of testbprmf.py:21-30).
 """
 import json
@@ -65,6 +68,45 @@ def gen_ranking(ref_ranking):
     unknown = ref_ranking.evaluateCV([{1}], [[1]], ['auc', 'pre'], 1)
     json.dump(dict(cv=cases, loov=loov, unknown_metric=unknown), open(os.path.join(OUT, 'ranking_golden.json'), 'w'))
     print('ranking_golden.json:', len(cases), 'cv cases,', len(loov), 'loov cases')
+
+
+def gen_rating():
+    """metrics/rating.py run live on its __main__ toy input (rating.py:33) and on seeded random inputs; plus the
+    ml-100k fold-1 MF run of the numpy oracle (deterministic given the initial tables: sampler_rating with negRatio = 0
+    walks the training tuples in file order)."""
+    import rating as ref_rating            # /root/reference/src/metrics/rating.py, imported as-is
+    from oracle import rating as orc, steps
+    names = ['mae', 'mse', 'rmse', 'nope']
+    cases = [dict(ys_true=[2.5, 1.5, 0], ys_pred=[1, 2, 1])]
+    rng = np.random.default_rng(2026)
+    for n in (1, 7, 300, 3000):
+        t = rng.integers(1, 11, n) / 2.0
+        p = np.clip(t + rng.normal(0, 1.0, n), 0.5, 5).astype(np.float32)
+        cases.append(dict(ys_true=t.tolist(), ys_pred=[float(x) for x in p]))
+    for c in cases:
+        yt, yp = np.array(c['ys_true']), np.array(c['ys_pred'])
+        c['scores'] = dict(zip(names, ref_rating.evaluate(yt, yp, names)))
+        c['mae'], c['mse'], c['rmse'] = (float(ref_rating.mean_absolute_error(yt, yp)), float(ref_rating.mean_squared_error(yt, yp)),
+                                         float(ref_rating.root_mean_squared_error(yt, yp)))
+        mine = orc.evaluate(yt, yp, names)
+        assert mine[3] is None and np.allclose(mine[:3], [c['scores'][m] for m in names[:3]], rtol=1e-14, atol=0)
+    # MF on ml-100k fold 1, reference driver hyper-parameters (basic/testmf.py:18-26), 5 epochs, numpy oracle
+    d = np.load(os.path.join(OUT, 'ml100k_fold1.npz'))
+    tra = np.stack([d['tra_u'], d['tra_i'], d['tra_r']], 1).astype(np.float64)
+    tst = np.stack([d['tst_u'], d['tst_i'], d['tst_r']], 1).astype(np.float64)
+    nu, ni, k = 943, 1682, 100
+    init = np.random.default_rng(7)
+    U, V = steps.truncated_normal(init, (nu, k)), steps.truncated_normal(init, (ni, k))
+    accU, accV = np.full_like(U, 0.1), np.full_like(V, 0.1)
+    hist = orc.mf_train(U, V, accU, accV, tra, tst, ['rmse', 'mae', 'mse'], (1, 5), 0.1, 1000, 5)
+    # the reference's own metrics module on the oracle's final predictions
+    pred = orc.mf_predict(U, V, tst[:, :2], (1, 5))
+    ref_final = ref_rating.evaluate(tst[:, 2], pred, ['rmse', 'mae', 'mse'])
+    assert np.allclose(ref_final, hist[-1][1], rtol=1e-12)
+    out = dict(cases=cases, mf_ml100k=dict(init_seed=7, n_factors=k, reg=0.1, batch_size=1000, range_of_ratings=[1, 5],
+                                          epochs=[dict(loss=h[0], rmse=h[1][0], mae=h[1][1], mse=h[1][2]) for h in hist]))
+    json.dump(out, open(os.path.join(OUT, 'rating_golden.json'), 'w'))
+    print('rating_golden: %d metric cases; MF ml-100k epochs: %s' % (len(cases), ['%.4f' % h[1][0] for h in hist]))
 
 
 def load_ml100k(IOUtil, Util):
@@ -284,12 +326,14 @@ def gen_e2e(nu, ni, bins, ref_ranking):
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    what = set(sys.argv[1:]) or {'ranking', 'ml100k', 'steps', 'sampler', 'e2e'}
+    what = set(sys.argv[1:]) or {'ranking', 'ml100k', 'steps', 'sampler', 'e2e', 'rating'}
     ref_ranking, IOUtil, Util = ref_import()
     if 'ranking' in what:
         gen_ranking(ref_ranking)
     if 'steps' in what:
         gen_steps()
+    if 'rating' in what:
+        gen_rating()
     if what & {'ml100k', 'sampler', 'e2e'}:
         nu, ni, bins = gen_ml100k(IOUtil, Util)
         if 'e2e' in what:

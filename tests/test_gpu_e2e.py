@@ -87,3 +87,19 @@ def test_driver_module_runs_a_fold_from_files(ml100k, tmp_path, capsys):
     out = capsys.readouterr().out
     assert 'ml-100k@1: (943, 1682) 44243 46.92' in out and 'ave: pre,recall,map,mrr,ndcg@10=' in out and 'std:' in out
     assert res.shape == (1, 5) and res[0, 4] > 0.3
+
+
+def test_mf_driver_runs_a_fold_from_files(ml100k, tmp_path, capsys):
+    """The `mf` driver (basic/testmf.py): raw ratings, rating sampler without negatives, RMSE / MAE / MSE lines."""
+    from collaborativefilteringusingtensorflow_b200 import drivers
+    from collaborativefilteringusingtensorflow_b200.utils import IOUtil
+    d = tmp_path / 'ml-100k'
+    d.mkdir()
+    for part in ('tra', 'tst'):
+        u, i, r = ml100k[part + '_raw']
+        IOUtil.saveTriads(list(zip(u.tolist(), i.tolist(), r.astype(float).tolist())), str(d / ('ratings__1_%s.txt' % part)))
+    res = drivers.run('mf', str(d) + '/', 943, 1682, folds=1, max_iter=4, seed=5)
+    out = capsys.readouterr().out
+    assert 'ml-100k: (943, 1682) 80000 84.84' in out and 'fold=0: rmse,mae,mse =' in out and 'ave=[' in out and 'std=[0.0000' in out
+    assert 'fold=1 iter= 4:' in out and '\tTst:rmse=' in out
+    assert res.shape == (1, 3) and 0.9 < res[0, 0] < 1.2 and abs(res[0, 2] - res[0, 0] ** 2) < 1e-9

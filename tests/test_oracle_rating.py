@@ -1,0 +1,53 @@
+"""The rating-path oracle (oracle/rating.py) against the golden vectors captured from the reference's own
+src/metrics/rating.py (tests/golden/rating_golden.json, made by oracle/gen_golden.py rating)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import rating as orc
+
+
+@pytest.fixture(scope='module')
+def golden():
+    return json.load(open(os.path.join(GOLDEN, 'rating_golden.json')))
+
+
+def test_metrics_match_the_reference_outputs(golden):
+    names = ['mae', 'mse', 'rmse', 'nope']
+    assert len(golden['cases']) >= 5
+    for c in golden['cases']:
+        yt, yp = np.array(c['ys_true']), np.array(c['ys_pred'])
+        got = orc.evaluate(yt, yp, names)
+        assert got[3] is None and c['scores']['nope'] is None
+        for k in range(3):
+            assert got[k] == pytest.approx(c['scores'][names[k]], rel=1e-14, abs=0)
+        assert orc.mean_absolute_error(yt, yp) == pytest.approx(c['mae'], rel=1e-14)
+        assert orc.mean_squared_error(yt, yp) == pytest.approx(c['mse'], rel=1e-14)
+        assert orc.root_mean_squared_error(yt, yp) == pytest.approx(c['rmse'], rel=1e-14)
+
+
+def test_toy_input_of_the_reference_main(golden):
+    c = golden['cases'][0]                       # rating.py:33
+    assert c['ys_true'] == [2.5, 1.5, 0] and c['ys_pred'] == [1, 2, 1]
+    assert c['mae'] == pytest.approx(1.0) and c['mse'] == pytest.approx(3.5 / 3) and c['rmse'] == pytest.approx(np.sqrt(3.5 / 3))
+
+
+def test_empty_input_divides_by_zero_like_the_reference():
+    with pytest.raises(ZeroDivisionError):
+        orc.mean_absolute_error(np.zeros(0), np.zeros(0))
+
+
+def test_mf_step_is_wrmf_with_unit_weight_and_descends(golden):
+    from oracle import steps
+    rng = np.random.default_rng(3)
+    nu, ni, d, B = 50, 40, 8, 64
+    U, V = steps.truncated_normal(rng, (nu, d)), steps.truncated_normal(rng, (ni, d))
+    accU, accV = np.full_like(U, 0.1), np.full_like(V, 0.1)
+    tra = np.stack([rng.integers(0, nu, 4 * B), rng.integers(0, ni, 4 * B), rng.integers(1, 6, 4 * B)], 1).astype(np.float64)
+    hist = orc.mf_train(U, V, accU, accV, tra, tra[:100], ['rmse'], (1, 5), 0.02, B, 6)
+    assert hist[-1][0] < hist[0][0] and hist[-1][1][0] < hist[0][1][0]
+    ep = golden['mf_ml100k']['epochs']
+    assert [round(e['rmse'], 4) for e in ep] == sorted([round(e['rmse'], 4) for e in ep], reverse=True) and ep[-1]['rmse'] < 1.0
