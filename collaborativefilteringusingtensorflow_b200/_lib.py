@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libcf_b200.so')
-ABI_VERSION = 14
+ABI_VERSION = 15
 
 # enums of cf_b200.h
 MODEL_BPR, MODEL_CML, MODEL_GBPR, MODEL_WRMF = 0, 1, 2, 3
@@ -46,6 +46,15 @@ class ApplyArgs(C.Structure):
         ('optimizer', C.c_int32), ('lr', C.c_float), ('clip_norm', C.c_float),
         ('meta', _p), ('slot', _p), ('slot_row', _p), ('staging', _p), ('staging_rows', C.c_int64), ('counters', _p),
         ('seg_grads', _p * MAX_PEERS), ('seg_start', C.c_int64 * (MAX_PEERS + 1)), ('n_segs', C.c_int32), ('first_seg', C.c_int32),
+    ]
+
+
+class SvdArgs(C.Structure):
+    _fields_ = [
+        ('U', _p), ('V', _p), ('K', _p), ('n_users', C.c_int64), ('n_items', C.c_int64),
+        ('d', C.c_int32), ('ld', C.c_int32), ('ldk', C.c_int32), ('reserved0', C.c_int32),
+        ('pairs', _p), ('ratings', _p), ('B', C.c_int64), ('reg', C.c_float), ('reserved1', C.c_int32),
+        ('gradU', _p), ('gradV', _p), ('gradK', _p), ('loss', _p), ('counters', _p),
     ]
 
 
@@ -93,6 +102,8 @@ _SIGNATURES = {
     'cf_clip_rows': (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, _p]),
     'cf_predict_pairs': (C.c_int, [_p, _p, _p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _p, C.c_int64, _p, _p, _p]),
     'cf_rating_metrics': (C.c_int, [_p, C.c_int32, _p, C.c_int64, C.c_double, C.c_double, _p, _p]),
+    'cf_svd_grads': (C.c_int, [C.POINTER(SvdArgs), _p]),
+    'cf_svd_predict_pairs': (C.c_int, [C.POINTER(SvdArgs), _p, _p]),
     'cf_apply_dense': (C.c_int, [C.POINTER(ApplyArgs), _p]),
     'cf_ipc_export': (C.c_int, [_p, _p, C.POINTER(C.c_int64)]),
     'cf_ipc_open': (C.c_int, [_p, C.POINTER(C.c_void_p)]),

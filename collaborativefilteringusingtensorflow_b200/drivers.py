@@ -1,7 +1,7 @@
 """The reference's experiment drivers for the hot-path models, as one module.
 
 Mirrors reference src/models/pl/testbprmf.py:19-125, testcml.py:19-102, testgbprmf.py:19-113,
-src/models/basic/testwrmf.py:19-96 and (rating prediction, `mf`) src/models/basic/testmf.py:14-78: the same module-level hyper-parameters, the same per-fold worker (load
+src/models/basic/testwrmf.py:19-96 and (rating prediction, `mf` / `svd`) src/models/basic/testmf.py:14-78, testsvd.py:14-79: the same module-level hyper-parameters, the same per-fold worker (load
 ``ratings__<fold>_tra.txt`` / ``_tst.txt``, binarise with ``rating > 3``, build the sampler and the model, train, print the
 fold's scores) and the same ``ave`` / ``std`` summary.  The reference wraps every fold in a ``multiprocessing.Pool`` only
 because ``tf.get_variable`` names collide (testbprmf.py:114-117); here folds run in-process.
@@ -14,6 +14,7 @@ import numpy as np
 from scipy.sparse import lil_matrix
 
 from .models.basic.models.mf import MF
+from .models.basic.models.svd import SVD
 from .models.basic.models.wrmf import WRMF
 from .models.pl.models.bprmf import BPRMF
 from .models.pl.models.cml import CML
@@ -38,6 +39,8 @@ HYPER = {
 
 # basic/testmf.py:14-24 (rating prediction: raw ratings, no binarisation)
 MF_HYPER = dict(eval_metrics=['rmse', 'mae', 'mse'], reg=.1, range_of_ratings=(1, 5), n_factors=100, batch_size=1000)
+# basic/testsvd.py:14-24 (the reference runs one fold only, testsvd.py:66)
+SVD_HYPER = dict(eval_metrics=['rmse', 'mae', 'mse'], reg=.1, range_of_ratings=(1, 5), n_factors=32, batch_size=100)
 
 
 def _triads(sR):
@@ -47,17 +50,17 @@ def _triads(sR):
     return np.stack([coo.row[order], coo.col[order], coo.data[order]], 1).astype(np.float64)
 
 
-def worker_mf(fold, n_users, n_items, dataset_dir, max_iter=None, seed=None, verbose=True):
-    """testmf.py:27-50."""
-    h = MF_HYPER
+def worker_mf(fold, n_users, n_items, dataset_dir, max_iter=None, seed=None, verbose=True, cls=MF, h=None):
+    """testmf.py:27-50 / testsvd.py:27-51."""
+    h = h or MF_HYPER
     trasR = loadSparseR(n_users, n_items, dataset_dir + 'ratings__' + str(fold + 1) + '_tra.txt')
     print(dataset_dir.split('/')[-2] + ':', trasR.shape, trasR.nnz, '%.2f' % (trasR.nnz / float(trasR.shape[0])))
     tra_tuple = _triads(trasR)
     tst_tuple = _triads(loadSparseR(n_users, n_items, dataset_dir + 'ratings__' + str(fold + 1) + '_tst.txt'))
     sampler = sampler_rating.Sampler(trasR=trasR, negRatio=.0, batch_size=h['batch_size'], seed=seed or 0)
     it = {} if max_iter is None else dict(max_iter=max_iter)
-    mf = MF(n_users, n_items, h['eval_metrics'], h['range_of_ratings'], h['reg'], h['n_factors'], h['batch_size'],
-            seed=seed, verbose=verbose, **it)
+    mf = cls(n_users, n_items, h['eval_metrics'], h['range_of_ratings'], h['reg'], h['n_factors'], h['batch_size'],
+             seed=seed, verbose=verbose, **it)
     scores = mf.train(fold + 1, tra_tuple, tst_tuple, sampler)
     print('fold=%d:' % fold, ','.join(['%s' % m for m in h['eval_metrics']]), '=', ','.join(['%.6f' % s for s in scores]))
     mf.close()
@@ -67,6 +70,8 @@ def worker_mf(fold, n_users, n_items, dataset_dir, max_iter=None, seed=None, ver
 def worker(model_name, fold, n_users, n_items, dataset_dir, max_iter=None, seed=None, verbose=True):
     if model_name == 'mf':
         return worker_mf(fold, n_users, n_items, dataset_dir, max_iter, seed, verbose)
+    if model_name == 'svd':
+        return worker_mf(fold, n_users, n_items, dataset_dir, max_iter, seed, verbose, cls=SVD, h=SVD_HYPER)
     h = HYPER[model_name]
     trasR = lil_matrix(matBinarize(loadSparseR(n_users, n_items, dataset_dir + 'ratings__' + str(fold + 1) + '_tra.txt'),
                                    binarize_threshold))
@@ -103,7 +108,7 @@ def run(model_name, dataset_dir, n_users, n_items, folds=5, max_iter=None, seed=
     """testbprmf.py:55-125: all folds, then ``ave`` / ``std`` over the folds."""
     results = [worker(model_name, fold, n_users, n_items, dataset_dir, max_iter, seed, verbose) for fold in range(folds)]
     results = np.array(results)
-    if model_name == 'mf':     # testmf.py:74-77
+    if model_name in ('mf', 'svd'):     # testmf.py:74-77
         aves = results.sum(0) / len(results)
         stds = np.sqrt(np.power(results - aves, 2).sum(0) / len(results))
         print('ave=[' + ','.join(['%.4f' % a for a in aves]) + ']', 'std=[' + ','.join(['%.4f' % d for d in stds]) + ']')
@@ -116,7 +121,7 @@ def run(model_name, dataset_dir, n_users, n_items, folds=5, max_iter=None, seed=
 
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
-    ap.add_argument('model', choices=sorted(HYPER) + ['mf'])
+    ap.add_argument('model', choices=sorted(HYPER) + ['mf', 'svd'])
     ap.add_argument('dataset_dir', help="directory with ratings__<k>_tra.txt / ratings__<k>_tst.txt (trailing '/')")
     ap.add_argument('n_users', type=int)
     ap.add_argument('n_items', type=int)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CF_ABI_VERSION 14
+#define CF_ABI_VERSION 15
 
 /* models */
 enum { CF_MODEL_BPR = 0, CF_MODEL_CML = 1, CF_MODEL_GBPR = 2, CF_MODEL_WRMF = 3 };
@@ -335,6 +335,36 @@ int cf_predict_pairs(const float* U, const float* V, const float* b, int64_t n_u
                      void* stream);
 int cf_rating_metrics(const void* pred, int32_t pred_is_f64, const double* truth, int64_t n, double lo, double hi,
                       double* sums, void* stream);
+
+/* SVD rating model (models/basic/models/svd.py): pred = sum((U_u K) * V_i) with a d x d kernel matrix K.
+ * cf_svd_grads is the gradient-only step of svd.py:52-80: for the B rows (pairs, ratings) it ADDS every pair's row
+ * gradients into the dense tables gradU[n_users, ld] / gradV[n_items, ld] and the summed e * U_u (x) V_i into
+ * gradK[d, ldk] (all zeroed by the caller) and the minibatch loss into *loss (or NULL); cf_apply_dense then applies the
+ * three tables (Adagrad on user_embed, kernel, item_embed: svd.py:74-80).  cf_svd_predict_pairs replaces `__predict`
+ * (svd.py:66-72) for the B rows of `pairs` (ratings / grad* / loss unused).  d <= 128. */
+typedef struct cf_svd_args {
+  const float* U;          /* [n_users, ld] */
+  const float* V;          /* [n_items, ld] */
+  const float* K;          /* [d, ldk] */
+  int64_t n_users;
+  int64_t n_items;
+  int32_t d;
+  int32_t ld;
+  int32_t ldk;
+  int32_t reserved0;
+  const int32_t* pairs;    /* [B, 2] */
+  const float* ratings;    /* [B] */
+  int64_t B;
+  float reg;
+  int32_t reserved1;
+  float* gradU;
+  float* gradV;
+  float* gradK;
+  double* loss;            /* [1] or NULL */
+  int32_t* counters;       /* [4] (flags in [1]) */
+} cf_svd_args;
+int cf_svd_grads(const cf_svd_args* args, void* stream);
+int cf_svd_predict_pairs(const cf_svd_args* args, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Host-side loader.  Replaces the per-line Python loop of utils/IOUtil.py:7-16 (`loadSparseR`): parses

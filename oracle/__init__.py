@@ -2,7 +2,7 @@
 
 This package restates, on the CPU, the arithmetic of the reference's hot path
 (BinFuPKU/CollaborativeFilteringUsingTensorflow: src/models/pl/models/{bprmf,cml,gbprmf}.py,
-src/models/basic/models/{wrmf,mf}.py, src/samplers/sampler_*.py, src/metrics/{ranking,rating}.py).
+src/models/basic/models/{wrmf,mf,svd}.py, src/samplers/sampler_*.py, src/metrics/{ranking,rating}.py).
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
 ``--impl reference`` legs may import it, and only as the checker or the timed CPU
@@ -19,7 +19,8 @@ Pinning status
   stream-level golden vectors exist.
 * ``oracle.rating``   -- metrics PINNED against the reference's own ``metrics/rating.py`` run live
   (tests/golden/rating_golden.json); the MF step / prediction restatement is unpinned like
-  ``oracle.steps`` (it IS ``oracle.steps.wrmf_step`` with weight 1).
+  ``oracle.steps`` (it IS ``oracle.steps.wrmf_step`` with weight 1); ``oracle.steps.svd_step`` is cross-checked
+  against a torch-autograd restatement of svd.py:52-80 (tests/golden/svd_golden.npz).
 * ``oracle.steps`` / ``oracle.scoring`` -- **PARITY UNPINNED against TensorFlow itself**: the
   arithmetic lives in third-party TensorFlow (>=1.13, unpinned, README.md:20-22), which is
   not installable here and for which the reference ships no tests or golden vectors.  The

@@ -20,6 +20,8 @@ What comes from where
 * rating_golden.json   -- outputs of the reference's own /root/reference/src/metrics/rating.py (imported as-is) on its
   ``__main__`` toy input and seeded random inputs; plus the numpy oracle's 5-epoch MF run on ml-100k fold 1 with the
   hyper-parameters of basic/testmf.py:18-26 (scored with the reference's rating.py).
+* svd_golden.npz / svd_ml100k_golden.json -- the SVD graph (svd.py:52-80) restated with torch autograd + Adagrad (two steps,
+  two shapes) and the numpy oracle's 3-epoch ml-100k run with basic/testsvd.py's hyper-parameters.
 * e2e_golden.json      -- oracle-trained ml-100k fold-1 metrics (reference hyper-parameters of testbprmf.py:21-30).
 """
 import json
@@ -107,6 +109,61 @@ def gen_rating():
                                           epochs=[dict(loss=h[0], rmse=h[1][0], mae=h[1][1], mse=h[1][2]) for h in hist]))
     json.dump(out, open(os.path.join(OUT, 'rating_golden.json'), 'w'))
     print('rating_golden: %d metric cases; MF ml-100k epochs: %s' % (len(cases), ['%.4f' % h[1][0] for h in hist]))
+
+
+def gen_svd():
+    """svd.py:52-80 restated with torch autograd + torch.optim.Adagrad (dense gradient on the kernel matrix, sparse rows
+    on the tables: zero-gradient rows are no-ops) -> tests/golden/svd_golden.npz; plus the numpy oracle's ml-100k run
+    with basic/testsvd.py's hyper-parameters (32 factors, batches of 100, reg .1, range (1, 5))."""
+    import torch
+    from oracle import rating as orc, steps
+    torch.set_num_threads(1)
+    rng = np.random.default_rng(11)
+    out = {}
+    nu, ni = 60, 90
+    for name, d, B in (('svd', 32, 100), ('svd_d7', 7, 64)):
+        params = dict(U=steps.truncated_normal(rng, (nu, d)), V=steps.truncated_normal(rng, (ni, d)),
+                      K=steps.truncated_normal(rng, (d, d)))
+        P = {k: torch.tensor(v, requires_grad=True) for k, v in params.items()}
+        opt = torch.optim.Adagrad(list(P.values()), lr=0.1, initial_accumulator_value=0.1, eps=0)
+        O = {k: v.copy() for k, v in params.items()}
+        A = {k: np.full_like(v, 0.1) for k, v in params.items()}
+        for k, v in params.items():
+            out['%s/init/%s' % (name, k)] = v
+        for s in range(2):
+            uir = np.stack([rng.integers(0, nu, B), rng.integers(0, ni, B), rng.integers(1, 11, B) / 2.0], 1)
+            opt.zero_grad()
+            u, i = P['U'][torch.tensor(uir[:, 0].astype(np.int64))], P['V'][torch.tensor(uir[:, 1].astype(np.int64))]
+            pred = ((u @ P['K']) * i).sum(1)
+            l2 = lambda t: (t * t).sum() / 2
+            loss = l2(pred - torch.tensor(uir[:, 2].astype(np.float32))) + 0.05 * (l2(u) + l2(i))
+            loss.backward()
+            opt.step()
+            ol = steps.svd_step(O['U'], O['V'], O['K'], A['U'], A['V'], A['K'], uir, 0.1, 0.05)
+            assert abs(ol - loss.item()) < 1e-5 * abs(ol)
+            out['%s/batch%d' % (name, s)] = uir
+            out['%s/loss%d' % (name, s)] = np.float64(loss.item())
+            for k in P:
+                got, acc = P[k].detach().numpy(), opt.state[P[k]]['sum'].numpy()
+                assert np.allclose(O[k], got, rtol=1e-5, atol=1e-6) and np.allclose(A[k], acc, rtol=1e-5, atol=1e-6), (name, s, k)
+                out['%s/step%d/%s' % (name, s, k)] = got.copy()
+                out['%s/step%d/acc%s' % (name, s, k)] = acc.copy()
+    np.savez_compressed(os.path.join(OUT, 'svd_golden.npz'), **out)
+    d = np.load(os.path.join(OUT, 'ml100k_fold1.npz'))
+    tra = np.stack([d['tra_u'], d['tra_i'], d['tra_r']], 1).astype(np.float64)
+    tst = np.stack([d['tst_u'], d['tst_i'], d['tst_r']], 1).astype(np.float64)
+    nu, ni, k, B = 943, 1682, 32, 100
+    init = np.random.default_rng(8)
+    U, V, K = steps.truncated_normal(init, (nu, k)), steps.truncated_normal(init, (ni, k)), steps.truncated_normal(init, (k, k))
+    accU, accV, accK = np.full_like(U, 0.1), np.full_like(V, 0.1), np.full_like(K, 0.1)
+    epochs = []
+    for ep in range(3):
+        losses = [steps.svd_step(U, V, K, accU, accV, accK, tra[b * B:(b + 1) * B], 0.1, 0.1) for b in range(len(tra) // B)]
+        sc = orc.evaluate(tst[:, 2], orc.svd_predict(U, V, K, tst[:, :2], (1, 5)), ['rmse', 'mae', 'mse'])
+        epochs.append(dict(loss=float(np.mean(losses)), rmse=float(sc[0]), mae=float(sc[1]), mse=float(sc[2])))
+    json.dump(dict(init_seed=8, n_factors=k, reg=0.1, batch_size=B, range_of_ratings=[1, 5], epochs=epochs),
+              open(os.path.join(OUT, 'svd_ml100k_golden.json'), 'w'))
+    print('svd_golden.npz: %d arrays; SVD ml-100k epochs: %s' % (len(out), ['%.4f' % e['rmse'] for e in epochs]))
 
 
 def load_ml100k(IOUtil, Util):
@@ -326,7 +383,7 @@ def gen_e2e(nu, ni, bins, ref_ranking):
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    what = set(sys.argv[1:]) or {'ranking', 'ml100k', 'steps', 'sampler', 'e2e', 'rating'}
+    what = set(sys.argv[1:]) or {'ranking', 'ml100k', 'steps', 'sampler', 'e2e', 'rating', 'svd'}
     ref_ranking, IOUtil, Util = ref_import()
     if 'ranking' in what:
         gen_ranking(ref_ranking)
@@ -334,6 +391,8 @@ if __name__ == '__main__':
         gen_steps()
     if 'rating' in what:
         gen_rating()
+    if 'svd' in what:
+        gen_svd()
     if what & {'ml100k', 'sampler', 'e2e'}:
         nu, ni, bins = gen_ml100k(IOUtil, Util)
         if 'e2e' in what:

@@ -51,3 +51,12 @@ def mf_train(U, V, accU, accV, tra_tuple, tst_tuple, eval_metrics, range_of_rati
         pred = mf_predict(U, V, tst_tuple[:, :2], range_of_ratings)
         out.append((float(np.mean(losses)), evaluate(tst_tuple[:, 2], pred, eval_metrics)))
     return out
+
+
+def svd_predict(U, V, K, useritem, range_of_ratings=None):
+    """svd.py:66-72 (+ the clip of :81): float32 predictions ``sum((U_u @ K) * V_i)`` of the (user, item) rows."""
+    u, i = useritem[:, 0].astype(np.int64), useritem[:, 1].astype(np.int64)
+    p = np.sum((U[u].astype(np.float64) @ K.astype(np.float64)) * V[i].astype(np.float64), axis=1).astype(np.float32)
+    if range_of_ratings is not None:
+        p = np.clip(p, np.float32(range_of_ratings[0]), np.float32(range_of_ratings[1]))
+    return p

@@ -6,6 +6,8 @@ Restates (numpy, fp32 forward math) what one ``sess.run(train_op)`` does in the 
 * CML    -- /root/reference/src/models/pl/models/cml.py:55-109 (loss), :119-129 (Adagrad + whole-table clip)
 * GBPRMF -- /root/reference/src/models/pl/models/gbprmf.py:58-93 (loss), :101-106 (Adagrad on U, V, b)
 * WRMF   -- /root/reference/src/models/basic/models/wrmf.py:52-75 (loss), :83-88 (Adagrad)
+* MF     -- /root/reference/src/models/basic/models/mf.py:54-78 = WRMF with weight 1 (oracle/rating.py)
+* SVD    -- /root/reference/src/models/basic/models/svd.py:52-80 (loss with the d x d kernel matrix, dense Adagrad on it)
 
 TF1 semantics relied on (third-party): gradients are evaluated at the
 pre-update parameters; IndexedSlices of every gather of a variable are concatenated and
@@ -195,6 +197,31 @@ def wrmf_step(U, V, accU, accV, uir, lr=0.1, reg=0.02, weight=1.0, optimizer=ADA
     gV = (w * e)[:, None] * Uu + reg * Vi
     apply_rows(U, accU, u, gU, lr, optimizer)
     apply_rows(V, accV, i, gV, lr, optimizer)
+    return float(loss)
+
+
+def svd_step(U, V, K, accU, accV, accK, uir, lr=0.1, reg=0.02, optimizer=ADAGRAD):
+    """svd.py:52-80: ``pred = sum((U_u @ K) * V_i)``, ``L = l2_loss(pred - r) + reg * (l2_loss(U_u) + l2_loss(V_i))``
+    (no L2 on K); Adagrad on U, V (sparse, duplicates summed) and on the whole kernel matrix K (dense gradient)."""
+    u, i = uir[:, 0].astype(np.int64), uir[:, 1].astype(np.int64)
+    r = uir[:, 2].astype(F)
+    Uu, Vi = U[u], V[i]
+    reg = F(reg)
+    t = (Vi @ K.T).astype(F)            # t[b, a] = sum_c K[a, c] V_i[c]
+    s = (Uu @ K).astype(F)              # s[b, c] = sum_a U_u[a] K[a, c]
+    e = np.sum(Uu * t, axis=1, dtype=F) - r
+    loss = 0.5 * np.sum(e * e, dtype=np.float64) + reg * 0.5 * (
+        np.sum(Uu * Uu, dtype=np.float64) + np.sum(Vi * Vi, dtype=np.float64))
+    gU = e[:, None] * t + reg * Uu
+    gV = e[:, None] * s + reg * Vi
+    gK = ((e[:, None] * Uu).astype(np.float64).T @ Vi.astype(np.float64)).astype(F)
+    apply_rows(U, accU, u, gU, lr, optimizer)
+    apply_rows(V, accV, i, gV, lr, optimizer)
+    if optimizer == ADAGRAD:
+        accK += gK * gK
+        K -= F(lr) * gK / np.sqrt(accK)
+    else:
+        K -= F(lr) * gK
     return float(loss)
 
 

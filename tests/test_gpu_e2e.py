@@ -98,6 +98,9 @@ def test_mf_driver_runs_a_fold_from_files(ml100k, tmp_path, capsys):
     for part in ('tra', 'tst'):
         u, i, r = ml100k[part + '_raw']
         IOUtil.saveTriads(list(zip(u.tolist(), i.tolist(), r.astype(float).tolist())), str(d / ('ratings__1_%s.txt' % part)))
+    res_svd = drivers.run('svd', str(d) + '/', 943, 1682, folds=1, max_iter=2, seed=5)
+    assert res_svd.shape == (1, 3) and 0.9 < res_svd[0, 0] < 1.3
+    capsys.readouterr()
     res = drivers.run('mf', str(d) + '/', 943, 1682, folds=1, max_iter=4, seed=5)
     out = capsys.readouterr().out
     assert 'ml-100k: (943, 1682) 80000 84.84' in out and 'fold=0: rmse,mae,mse =' in out and 'ave=[' in out and 'std=[0.0000' in out

@@ -123,3 +123,79 @@ def test_mf_trains_ml100k_like_the_oracle(golden, capsys):
     assert scores == pytest.approx([last['rmse'], last['mae'], last['mse']], rel=2e-3)
     assert scores[0] < 1.0
     mf.close()
+
+
+@pytest.mark.parametrize('name', ['svd', 'svd_d7'])
+def test_svd_step_golden(name):
+    """SVD (svd.py:52-80) on the GPU against the torch-autograd golden: tables, kernel matrix, accumulators, loss."""
+    from collaborativefilteringusingtensorflow_b200 import SVD
+    z = np.load(os.path.join(GOLDEN, 'svd_golden.npz'))
+    U0 = z[name + '/init/U']
+    nu, d = U0.shape
+    ni = z[name + '/init/V'].shape[0]
+    m = SVD(nu, ni, reg=0.05, n_factors=d, verbose=False, seed=3)
+    m.load_state_dict(dict(U=U0, V=z[name + '/init/V'], K=z[name + '/init/K'], accU=np.full_like(U0, 0.1),
+                           accV=np.full((ni, d), 0.1, np.float32), accK=np.full((d, d), 0.1, np.float32)))
+    for s in range(2):
+        loss = m.step(z['%s/batch%d' % (name, s)])
+        assert loss == pytest.approx(float(z['%s/loss%d' % (name, s)]), rel=1e-5)
+        st = {k: v.cpu().numpy() for k, v in m.state_dict().items()}
+        for k in ('U', 'V', 'K'):
+            np.testing.assert_allclose(st[k], z['%s/step%d/%s' % (name, s, k)], rtol=1e-5, atol=1e-6, err_msg='%s step %d %s' % (name, s, k))
+            np.testing.assert_allclose(st['acc' + k], z['%s/step%d/acc%s' % (name, s, k)], rtol=5e-5, atol=1e-6, err_msg='%s step %d acc%s' % (name, s, k))
+    assert float(m._gU.abs().max()) == 0.0 and float(m._gV.abs().max()) == 0.0 and float(m._gK.abs().max()) == 0.0
+
+
+def test_svd_predict_and_multi_batch_vs_oracle():
+    import torch
+    from collaborativefilteringusingtensorflow_b200 import SVD
+    nu, ni, d, B = 300, 200, 32, 100
+    m = SVD(nu, ni, reg=0.1, n_factors=d, batch_size=B, verbose=False, seed=6)
+    P = {k: v.cpu().numpy() for k, v in m.state_dict().items()}
+    rng = np.random.default_rng(12)
+    pairs = np.stack([rng.integers(0, nu, 3000), rng.integers(0, ni, 3000)], 1).astype(np.int32)
+    np.testing.assert_allclose(m.predict_pairs(pairs), orc.svd_predict(P['U'], P['V'], P['K'], pairs), rtol=1e-6, atol=1e-8)
+    # three minibatches in one call (the epoch loop's chunk) == three oracle steps
+    uir = np.stack([rng.integers(0, nu, 3 * B), rng.integers(0, ni, 3 * B), rng.integers(1, 6, 3 * B)], 1).astype(np.float64)
+    losses = m._train_arrays((uir,), B).cpu().numpy()
+    m.engine.check_flags()
+    for k in range(3):
+        ol = steps.svd_step(P['U'], P['V'], P['K'], P['accU'], P['accV'], P['accK'], uir[k * B:(k + 1) * B], 0.1, 0.1)
+        assert losses[k] == pytest.approx(ol, rel=1e-5)
+    st = {k: v.cpu().numpy() for k, v in m.state_dict().items()}
+    for k in ('U', 'V', 'K', 'accU', 'accV', 'accK'):
+        np.testing.assert_allclose(st[k], P[k], rtol=5e-5, atol=2e-6, err_msg=k)
+    bad = pairs[:4].copy()
+    bad[1, 0] = nu
+    with pytest.raises(RuntimeError, match='out of range'):
+        m.predict_pairs(bad)
+    with pytest.raises(ValueError):
+        SVD(10, 10, n_factors=129)
+
+
+def test_svd_trains_ml100k_like_the_oracle(capsys):
+    """basic/testsvd.py on fold 1 (32 factors, batches of 100, reg .1): deterministic given the initial tables."""
+    from scipy.sparse import coo_matrix
+    from collaborativefilteringusingtensorflow_b200 import SVD
+    from collaborativefilteringusingtensorflow_b200.samplers.sampler_rating import Sampler
+    g = json.load(open(os.path.join(GOLDEN, 'svd_ml100k_golden.json')))
+    z = np.load(os.path.join(GOLDEN, 'ml100k_fold1.npz'))
+    tra = np.stack([z['tra_u'], z['tra_i'], z['tra_r']], 1).astype(np.float64)
+    tst = np.stack([z['tst_u'], z['tst_i'], z['tst_r']], 1).astype(np.float64)
+    nu, ni, k = 943, 1682, g['n_factors']
+    trasR = coo_matrix((tra[:, 2].astype(np.float32), (tra[:, 0].astype(np.int64), tra[:, 1].astype(np.int64))), shape=(nu, ni)).tolil()
+    init = np.random.default_rng(g['init_seed'])
+    U0, V0, K0 = steps.truncated_normal(init, (nu, k)), steps.truncated_normal(init, (ni, k)), steps.truncated_normal(init, (k, k))
+    m = SVD(nu, ni, ['rmse', 'mae', 'mse'], tuple(g['range_of_ratings']), g['reg'], k, g['batch_size'],
+            max_iter=len(g['epochs']), verbose=True, seed=1)
+    m.load_state_dict(dict(U=U0, V=V0, K=K0, accU=np.full_like(U0, 0.1), accV=np.full_like(V0, 0.1), accK=np.full_like(K0, 0.1)))
+    scores = m.train(1, tra, tst, Sampler(trasR=trasR, negRatio=.0, batch_size=g['batch_size']))
+    lines = [l for l in capsys.readouterr().out.splitlines() if l.startswith('fold=1 iter=')]
+    assert len(lines) == len(g['epochs'])
+    for line, e in zip(lines, g['epochs']):
+        got = {kv.split('=')[0]: float(kv.split('=')[1]) for kv in line.split('Tst:')[1].split()}
+        assert got['rmse'] == pytest.approx(e['rmse'], abs=3e-3) and got['mae'] == pytest.approx(e['mae'], abs=3e-3)
+        assert float(line.split('TraLoss=')[1].split()[0]) == pytest.approx(e['loss'], rel=3e-3)
+    last = g['epochs'][-1]
+    assert scores == pytest.approx([last['rmse'], last['mae'], last['mse']], rel=3e-3)
+    m.close()

@@ -51,3 +51,19 @@ def test_mf_step_is_wrmf_with_unit_weight_and_descends(golden):
     assert hist[-1][0] < hist[0][0] and hist[-1][1][0] < hist[0][1][0]
     ep = golden['mf_ml100k']['epochs']
     assert [round(e['rmse'], 4) for e in ep] == sorted([round(e['rmse'], 4) for e in ep], reverse=True) and ep[-1]['rmse'] < 1.0
+
+
+def test_svd_step_matches_autograd_golden():
+    """oracle.steps.svd_step (hand-derived gradients, svd.py:52-80) against the torch-autograd restatement of the same
+    graph recorded in tests/golden/svd_golden.npz."""
+    from oracle import steps
+    z = np.load(os.path.join(GOLDEN, 'svd_golden.npz'))
+    for name in ('svd', 'svd_d7'):
+        P = {k: z['%s/init/%s' % (name, k)].copy() for k in ('U', 'V', 'K')}
+        A = {k: np.full_like(v, 0.1) for k, v in P.items()}
+        for s in range(2):
+            loss = steps.svd_step(P['U'], P['V'], P['K'], A['U'], A['V'], A['K'], z['%s/batch%d' % (name, s)], 0.1, 0.05)
+            assert loss == pytest.approx(float(z['%s/loss%d' % (name, s)]), rel=1e-5)
+            for k in ('U', 'V', 'K'):
+                np.testing.assert_allclose(P[k], z['%s/step%d/%s' % (name, s, k)], rtol=1e-5, atol=1e-6)
+                np.testing.assert_allclose(A[k], z['%s/step%d/acc%s' % (name, s, k)], rtol=1e-5, atol=1e-6)
