@@ -114,3 +114,18 @@ def test_single_gpu_step_kernels_keep_four_blocks_per_sm():
             assert regs <= 64 and stack == 0, (line, lines[i + 1])
             seen += 1
     assert seen == 4
+
+
+def test_integration_doc_stub_declares_the_full_step_struct():
+    """INTEGRATION.md shows the ctypes stub a maintainer would write; a stub with fewer fields than cf_step_args would make
+    the library read past the caller's struct, so the documented field list must equal the real mirror."""
+    text = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    start = text.index('class StepArgs(C.Structure):')
+    end = text.index('lib.cf_train_steps.argtypes', start)
+    ns = {'C': C}
+    exec(text[start:end], ns)
+    doc = ns['StepArgs']
+    assert [f[0] for f in doc._fields_] == [f[0] for f in _lib.StepArgs._fields_]
+    assert C.sizeof(doc) == C.sizeof(_lib.StepArgs)
+    for name, _ in doc._fields_:
+        assert getattr(doc, name).offset == getattr(_lib.StepArgs, name).offset, name
