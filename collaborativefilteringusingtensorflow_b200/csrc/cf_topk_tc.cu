@@ -4,12 +4,12 @@
 // Replaces `sess.run(tf.nn.top_k(matmul(U[test_users], V^T) (+b | cml distance), K'))` + the Python filter loop
 // (reference src/models/pl/models/bprmf.py:77-103, cml.py:111-144, gbprmf.py:95-121, basic/models/wrmf.py:77-111).
 //
-// Stage 0 (k_prep): fp32 tables -> fp16 operand matrices (fp16, not bf16: 8x tighter error band for the same MMA rate) with K padded to a multiple of 64.  The
-//   three scoring kinds all become plain dot products a'.b':   DOT       a' = u            b' = v
+// Stage 0 (k_prep): fp32 tables -> fp16 operand matrices (fp16, not bf16: 8x tighter error band for the same MMA rate)
+//   with K padded to a multiple of 64.  The three scoring kinds all become plain dot products a'.b':   DOT       a' = u            b' = v
 //                                                               DOT_BIAS  a' = [u, 1, 1]    b' = [v, hi(b_i), lo(b_i)]
 //                                                               NEG_SQDIST a' = [2u, 1, 1]  b' = [v, hi(-|v|^2), lo(-|v|^2)]
-//   (per-user constants such as -|u|^2 do not change a user's ranking).  eps_row = 2^-7.9 |a'| max_i|b'_i| bounds the bf16
-//   rounding + fp32 accumulation error of every score of the row.
+//   (per-user constants such as -|u|^2 do not change a user's ranking).  eps_row ~ 2^-10 |a'| max_i|b'_i| (exact form at
+//   its computation below) bounds the fp16 rounding + fp32 accumulation error of every score of the row.
 // Stage 1 (k_topk_tc): one CTA per (256 query rows, item split): A = 2 x (128 x Kp) resident in smem, B tiles of 128 items
 //   streamed by TMA through a ring, 2 x tcgen05.mma (M=128, N=128) per k-step into a double-buffered TMEM accumulator,
 //   8 epilogue warps (one thread per row) read the accumulators with tcgen05.ld and append (score, item) to the row's
