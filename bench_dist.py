@@ -4,7 +4,6 @@ users range-sharded, items sharded by item % N, per-minibatch NCCL all-to-all of
 (SURVEY.md 8e).  `--grow-catalogue` instead multiplies the catalogue by N (every rank owns n_items rows)."""
 import json
 import sys
-import os
 import time
 
 import torch

@@ -24,8 +24,6 @@ top-K, and the [T, K] lists are all-gathered and merged (cf_topk_merge).
 ``ItemExchange`` is pure index bookkeeping + collectives on whatever device its tensors live on, so it is tested on CPU
 with the gloo backend (tests/test_dist_gloo.py); the kernels plug in at steps 3 and 5.
 """
-import numpy as np
-
 from . import _lib
 
 

@@ -7,7 +7,7 @@ torch is used for device memory and streams only; all arithmetic is in libcf_b20
 import numpy as np
 
 from . import _lib
-from .sparse import DeviceCSR, null_csr
+from .sparse import null_csr
 
 _MODEL_IDS = {'bpr': _lib.MODEL_BPR, 'cml': _lib.MODEL_CML, 'gbpr': _lib.MODEL_GBPR, 'wrmf': _lib.MODEL_WRMF}
 _SCORE_KIND = {'bpr': _lib.SCORE_DOT, 'cml': _lib.SCORE_NEG_SQDIST, 'gbpr': _lib.SCORE_DOT_BIAS, 'wrmf': _lib.SCORE_DOT}

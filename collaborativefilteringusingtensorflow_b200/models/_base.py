@@ -2,9 +2,6 @@
 reference src/models/pl/models/bprmf.py:90-170 (identical skeleton in cml.py, gbprmf.py, basic/models/wrmf.py)."""
 import datetime as dt
 
-import numpy as np
-
-from .. import _lib
 from ..engine import FactorEngine
 from ..metrics import ranking
 from ..sparse import DeviceCSR

@@ -5,8 +5,6 @@ The minibatch objective ``l2_loss(<U_u, V_i> - r) + reg * (l2_loss(U_u) + l2_los
 ``weight = 1`` (wrmf.py:52-75), so the fused step kernel is the same instantiation (CF_MODEL_WRMF); what is new is the
 evaluation: predictions of the test tuples (cf_predict_pairs), clipped to ``range_of_ratings`` (mf.py:81), scored by
 metrics/rating.py (cf_rating_metrics)."""
-import datetime as dt
-
 import numpy as np
 
 from ..._base import RankingModelBase

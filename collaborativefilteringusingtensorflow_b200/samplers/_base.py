@@ -5,8 +5,6 @@ hand out one minibatch per ``next_batch()`` call.  Here a batch is a pure functi
 sampler object is only a cursor.  ``next_batch()`` keeps the reference's return types; ``next_chunk(n)`` is the fast
 path the model classes use (n minibatches as CUDA tensors, no host round trip).
 """
-import numpy as np
-
 from .. import _lib
 from ..engine import resolve_device
 from ..sparse import DeviceCSR, null_csr

@@ -129,3 +129,12 @@ def test_integration_doc_stub_declares_the_full_step_struct():
     assert C.sizeof(doc) == C.sizeof(_lib.StepArgs)
     for name, _ in doc._fields_:
         assert getattr(doc, name).offset == getattr(_lib.StepArgs, name).offset, name
+
+
+def test_python_sources_have_no_undefined_names_or_unused_imports():
+    """tools/lint_names.py over the repository (the GPU-only code paths cannot be exercised here, so at least every name
+    they load must be bound somewhere in its file)."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'lint_names.py')], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout

@@ -4,7 +4,6 @@ between fetch and push on a GPU box."""
 import os
 import socket
 
-import numpy as np
 import pytest
 import torch
 import torch.distributed as dist

@@ -5,7 +5,6 @@ exact top-K with masked, sorted results."""
 import os
 import sys
 
-import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu

@@ -2,7 +2,6 @@
 """Times full-catalog masked top-K (tensor-core path vs exact path) on synthetic tables; prints users/s and TFLOP/s."""
 import os
 import sys
-import time
 
 import torch
 
