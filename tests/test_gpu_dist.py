@@ -72,15 +72,16 @@ def test_item_mod_sharded_topk_merge_equals_single_shot():
     assert torch.equal(out_i, whole_i) and torch.equal(out_v, whole_v)
 
 
+@pytest.mark.parametrize('W', [4, 40])      # 40 negatives do not fit one tile of the d=128 kernel (30 entries): two tiles, CML two passes
 @pytest.mark.parametrize('kind', ['bpr', 'cml'])
-def test_peer_pull_from_three_shards_equals_fetched_rows(kind):
+def test_peer_pull_from_three_shards_equals_fetched_rows(kind, W):
     """The peer-pull step (item rows read from their owners' shards by GLOBAL id: item i = row i // P of shard i % P)
     against the fetched-rows exchange step on the same minibatch: same user update, same gradient rows.  The three
     "peers" are three tensors of this process -- the kernel only sees pointers."""
     import torch
     from collaborativefilteringusingtensorflow_b200 import BPRMF, CML, _lib
     from collaborativefilteringusingtensorflow_b200.dist import ItemExchange
-    nu, ni, d, B, W, P = 300, 1001, 128, 2048, 4, 3
+    nu, ni, d, B, P = 300, 1001, 128, 2048 if W == 4 else 512, 3
     mk = (lambda: BPRMF(nu, ni, n_factors=d, reg=0.05, verbose=False, seed=9)) if kind == 'bpr' else \
          (lambda: CML(nu, ni, n_factors=d, reg_cov=1.0, margin=1.0, init_stddev=0.05, verbose=False, seed=9))
     rng = np.random.default_rng(3)
@@ -179,14 +180,15 @@ def _mk4(kind, nu, ni, d):
 
 
 @pytest.mark.parametrize('halves', [1, 2])
-@pytest.mark.parametrize('kind,d', [('bpr', 128), ('cml', 64), ('gbpr', 64), ('gbpr', 20), ('wrmf', 100)])
-def test_replicated_mode_equals_fused_step(kind, d, halves):
+@pytest.mark.parametrize('kind,d,W', [('bpr', 128, 4), ('cml', 64, 4), ('gbpr', 64, 4), ('gbpr', 20, 4), ('wrmf', 100, 4),
+                                      ('gbpr', 64, 13), ('cml', 128, 33)])     # the last two: entries span two tiles
+def test_replicated_mode_equals_fused_step(kind, d, W, halves):
     """Gradient-only step into dense tables + cf_apply_dense (what every rank of ReplicatedTrainer runs) against the
     plain fused step.  halves=2 accumulates two half-batches into the same dense tables before the apply -- the sum the
     all_reduce forms over two ranks -- and must equal ONE step on the whole batch."""
     import torch
     from collaborativefilteringusingtensorflow_b200.dist import ReplicatedTrainer
-    nu, ni, B, W, G = 300, 200, 1024, 4, 3
+    nu, ni, B, G = 300, 200, 1024 if W == 4 else 256, 3
     a, b = _mk4(kind, nu, ni, d), _mk4(kind, nu, ni, d)
     b.load_state_dict(a.state_dict())
     rng = np.random.default_rng(8)
