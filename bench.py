@@ -380,7 +380,8 @@ def run_ours(args):
 
 def run_reference(args):
     """The reference arm: the reference's CPU implementation of the path.  TensorFlow 1.x cannot be installed here (no
-    network, no wheel), so this is the numpy oracle port (oracle/steps.py) of the TF1 graph on the host cores."""
+    network, no wheel), so this is the oracle port of the TF1 graph (oracle/steps_torch.py: torch CPU ops on every host
+    core, tested equal to the numpy restatement oracle/steps.py) plus the numpy rejection sampler."""
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
