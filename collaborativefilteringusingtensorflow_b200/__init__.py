@@ -1,5 +1,5 @@
 """B200-native pairwise-ranking training + full-catalog top-K evaluation behind the API of
-BinFuPKU/CollaborativeFilteringUsingTensorflow (models/pl/models/{bprmf,cml,gbprmf}.py, models/basic/models/{wrmf,mf,svd}.py,
+BinFuPKU/CollaborativeFilteringUsingTensorflow (models/pl/models/{bprmf,cml,gbprmf}.py, models/basic/models/{wrmf,mf,svd,pop}.py,
 samplers/sampler_{ranking,uij_ranking,gbpr,rating}.py, metrics/{ranking,rating}.py, utils/{IOUtil,Util}.py).
 
 All arithmetic runs in hand-written sm_100a CUDA (libcf_b200.so, C ABI in include/cf_b200.h); there is no CPU fallback.
@@ -20,6 +20,9 @@ def __getattr__(name):   # lazy: importing the package must work on a box withou
     if name == 'WRMF':
         from .models.basic.models.wrmf import WRMF
         return WRMF
+    if name == 'PopRank':
+        from .models.basic.models.pop import PopRank
+        return PopRank
     if name == 'SVD':
         from .models.basic.models.svd import SVD
         return SVD

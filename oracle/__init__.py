@@ -14,6 +14,9 @@ Pinning status
 * ``oracle.ranking``  -- PINNED: checked against the reference's own ``ranking.py`` run
   live in the build container and against the golden vectors captured from its
   ``__main__`` toy inputs (tests/golden/ranking_golden.json, made by oracle/gen_golden.py).
+* ``oracle.scoring.topn_masked`` + ``oracle.ranking`` end to end -- PINNED against the OUTPUT of the
+  reference's own PopRank (basic/models/pop.py, numpy only) run live on ml-100k fold 1: its recommended
+  lists and metric values (tests/golden/pop_golden.json).
 * ``oracle.samplers`` -- PINNED on invariants/dtypes/shapes against the reference samplers
   run live (tests/golden/sampler_golden.json); streams are unseeded in the reference so no
   stream-level golden vectors exist.

@@ -22,6 +22,8 @@ What comes from where
   hyper-parameters of basic/testmf.py:18-26 (scored with the reference's rating.py).
 * svd_golden.npz / svd_ml100k_golden.json -- the SVD graph (svd.py:52-80) restated with torch autograd + Adagrad (two steps,
   two shapes) and the numpy oracle's 3-epoch ml-100k run with basic/testsvd.py's hyper-parameters.
+* pop_golden.json      -- the reference's own PopRank (basic/models/pop.py, numpy only) run live on ml-100k fold 1: recommended
+  lists + metric values (pins the masked top-N with its tie rule and the metrics end to end against the reference).
 * e2e_golden.json      -- oracle-trained ml-100k fold-1 metrics (reference hyper-parameters of testbprmf.py:21-30).
 """
 import json
@@ -109,6 +111,26 @@ def gen_rating():
                                           epochs=[dict(loss=h[0], rmse=h[1][0], mae=h[1][1], mse=h[1][2]) for h in hist]))
     json.dump(out, open(os.path.join(OUT, 'rating_golden.json'), 'w'))
     print('rating_golden: %d metric cases; MF ml-100k epochs: %s' % (len(cases), ['%.4f' % h[1][0] for h in hist]))
+
+
+def gen_pop(bins):
+    """The reference's own PopRank (basic/models/pop.py, numpy only) run live on ml-100k fold 1 with testpop.py's
+    settings: its recommended lists and metric values pin the masked top-N (ties -> lower item id) and the metrics."""
+    sys.path.insert(0, os.path.join(REF, 'models', 'basic', 'models'))
+    import pop as ref_pop
+    names = ['pre', 'recall', 'map', 'mrr', 'ndcg']
+    out = {}
+    for topN in (10, 100):
+        m = ref_pop.PopRank(943, 1682, topN, 'cv', names)
+        scores = m.train(1, bins['tra'], bins['tst'])
+        test_users = sorted(set(np.asarray(bins['tst'].nonzero()[0]).tolist()))
+        lists = m._PopRank__recommend(bins['tra'], test_users)
+        out['top%d' % topN] = dict(scores=dict(zip(names, [float(x) for x in scores])), test_users=[int(u) for u in test_users],
+                                   lists=[[int(x) for x in l] for l in (lists if topN == 10 else lists[:60])])   # top-100: first 60 users
+    m = ref_pop.PopRank(943, 1682, 10, 'loov', ['hr', 'arhr'])
+    out['loov10'] = dict(scores=dict(zip(['hr', 'arhr'], [float(x) for x in m.train(1, bins['tra'], bins['tst'])])))
+    json.dump(out, open(os.path.join(OUT, 'pop_golden.json'), 'w'))
+    print('pop_golden:', out['top10']['scores'], out['loov10']['scores'])
 
 
 def gen_svd():
@@ -383,7 +405,7 @@ def gen_e2e(nu, ni, bins, ref_ranking):
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    what = set(sys.argv[1:]) or {'ranking', 'ml100k', 'steps', 'sampler', 'e2e', 'rating', 'svd'}
+    what = set(sys.argv[1:]) or {'ranking', 'ml100k', 'steps', 'sampler', 'e2e', 'rating', 'svd', 'pop'}
     ref_ranking, IOUtil, Util = ref_import()
     if 'ranking' in what:
         gen_ranking(ref_ranking)
@@ -393,8 +415,10 @@ if __name__ == '__main__':
         gen_rating()
     if 'svd' in what:
         gen_svd()
-    if what & {'ml100k', 'sampler', 'e2e'}:
+    if what & {'ml100k', 'sampler', 'e2e', 'pop'}:
         nu, ni, bins = gen_ml100k(IOUtil, Util)
+        if 'pop' in what:
+            gen_pop(bins)
         if 'e2e' in what:
             gen_e2e(nu, ni, bins, ref_ranking)
         if 'sampler' in what:

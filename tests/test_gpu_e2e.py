@@ -106,3 +106,25 @@ def test_mf_driver_runs_a_fold_from_files(ml100k, tmp_path, capsys):
     assert 'ml-100k: (943, 1682) 80000 84.84' in out and 'fold=0: rmse,mae,mse =' in out and 'ave=[' in out and 'std=[0.0000' in out
     assert 'fold=1 iter= 4:' in out and '\tTst:rmse=' in out
     assert res.shape == (1, 3) and 0.9 < res[0, 0] < 1.2 and abs(res[0, 2] - res[0, 0] ** 2) < 1e-9
+
+
+def test_poprank_equals_the_reference_run(ml100k):
+    """PopRank (basic/models/pop.py) is numpy-only, so the reference itself ran in the build container
+    (oracle/gen_golden.py pop): its recommended lists (stable sort: ties -> lower item id) and its metric values on ml-100k
+    fold 1 must be reproduced exactly by the masked top-N kernel + cf_rank_metrics."""
+    import json
+    import os
+    from conftest import GOLDEN
+    from collaborativefilteringusingtensorflow_b200 import PopRank
+    g = json.load(open(os.path.join(GOLDEN, 'pop_golden.json')))
+    names = ['pre', 'recall', 'map', 'mrr', 'ndcg']
+    for topN in (10, 100):
+        ref = g['top%d' % topN]
+        m = PopRank(943, 1682, topN, 'cv', names)
+        scores = m.train(1, ml100k['tra'], ml100k['tst'])
+        for name, s in zip(names, scores):
+            assert s == pytest.approx(ref['scores'][name], rel=1e-12, abs=1e-15), (topN, name)
+        users = ref['test_users'][:len(ref['lists'])]
+        assert m.recommend(users, topN, ml100k['tra']) == ref['lists']
+    loov = PopRank(943, 1682, 10, 'loov', ['hr', 'arhr']).train(1, ml100k['tra'], ml100k['tst'])
+    assert loov == pytest.approx([g['loov10']['scores']['hr'], g['loov10']['scores']['arhr']], rel=1e-12)

@@ -59,3 +59,27 @@ def test_live_against_reference():
         assert np.allclose(a, b, atol=1e-12)
         ys = rng.integers(0, n_items, n_users).tolist()
         assert np.allclose(orc.evaluateLOOV(ys, yp, ['hr', 'arhr'], k), ref.evaluateLOOV(ys, yp, ['hr', 'arhr'], k))
+
+
+def test_oracle_pipeline_reproduces_the_reference_poprank_run(ml100k):
+    """The reference's own PopRank (basic/models/pop.py, numpy only) ran in the build container (oracle/gen_golden.py pop)
+    on ml-100k fold 1.  The oracle's masked top-N (oracle.scoring: score desc, id asc) over popularity scores and the
+    oracle's metrics must reproduce its recommended lists and its metric values: an end-to-end pin of scoring + top-N +
+    metrics against reference OUTPUT, not just against a restatement."""
+    import json
+    from conftest import GOLDEN
+    from oracle import scoring
+    g = json.load(open(os.path.join(GOLDEN, 'pop_golden.json')))
+    tra, tst = ml100k['tra'], ml100k['tst']
+    pop = np.asarray((tra != 0).sum(0)).reshape(-1).astype(np.float64)
+    ref = g['top10']
+    users = ref['test_users']
+    scores = np.tile(pop, (len(users), 1))
+    lists = scoring.topn_masked(scores, [set(tra.rows[u]) for u in users], 10)
+    assert [list(map(int, l)) for l in lists] == ref['lists']
+    names = ['pre', 'recall', 'map', 'mrr', 'ndcg']
+    got = orc.evaluateCV([set(tst.rows[u]) for u in users], ref['lists'], names, 10)
+    for n, v in zip(names, got):
+        assert abs(v - ref['scores'][n]) < 1e-12, (n, v, ref['scores'][n])
+    loov = orc.evaluateLOOV([tst.rows[u][0] for u in users], ref['lists'], ['hr', 'arhr'], 10)
+    assert loov == pytest.approx([g['loov10']['scores']['hr'], g['loov10']['scores']['arhr']], rel=1e-12)
