@@ -12,6 +12,10 @@
 
 namespace {
 inline bool is_sep(char c) { return c == ',' || c == ';' || c == ' ' || c == '\t' || c == '\r'; }
+// the whole token must have been consumed (Python's int("3.0") / int("12abc") / float("4x") raise ValueError)
+inline bool whole_token(const char* tok, const char* parsed_end, const char* eol) {
+  return parsed_end != tok && (parsed_end >= eol || is_sep(*parsed_end));
+}
 }  // namespace
 
 extern "C" int cf_parse_triplets(const char* path, int64_t* n_out, int64_t** users_out, int64_t** items_out, double** ratings_out) {
@@ -36,6 +40,11 @@ extern "C" int cf_parse_triplets(const char* path, int64_t* n_out, int64_t** use
   int64_t* us = (int64_t*)malloc(sizeof(int64_t) * (size_t)(lines + 1));
   int64_t* is = (int64_t*)malloc(sizeof(int64_t) * (size_t)(lines + 1));
   double* rs = (double*)malloc(sizeof(double) * (size_t)(lines + 1));
+  if (!us || !is || !rs) {
+    free(buf); free(us); free(is); free(rs);
+    cf_set_error("cf_parse_triplets: out of host memory for %lld lines", (long long)lines);
+    return -1;
+  }
   int64_t n = 0;
   char* p = buf;
   char* end = buf + size + 1;
@@ -59,11 +68,11 @@ extern "C" int cf_parse_triplets(const char* path, int64_t* n_out, int64_t** use
       const long long u = strtoll(fld[0], &e1, 10);
       const long long i = strtoll(fld[1], &e2, 10);
       double r = 1.0;
-      bool ok = e1 != fld[0] && e2 != fld[1];
+      bool ok = whole_token(fld[0], e1, eol) && whole_token(fld[1], e2, eol);
       if (nf == 3) {
         char* e3;
         r = strtod(fld[2], &e3);
-        ok = ok && e3 != fld[2];
+        ok = ok && whole_token(fld[2], e3, eol);
       }
       if (!ok) {
         free(buf); free(us); free(is); free(rs);

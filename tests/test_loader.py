@@ -42,3 +42,27 @@ def test_roundtrip_of_ml100k_fixture(ml100k, tmp_path):
 def test_same_matrix_as_reference_loader_on_bundled_file(ml100k):
     m = IOUtil.loadSparseR(943, 1682, '/root/reference/data/movielens/ml-100k/ratings__1_tra.txt')
     assert (Util.matBinarize(m, 3).tocsr() != ml100k['tra'].tocsr()).nnz == 0
+
+
+@pytest.mark.parametrize('line', ['1\t2.5\t3.0', '1\t2\t4x', '12abc\t3\t1', 'a\tb'])
+def test_malformed_numbers_are_rejected_like_python_int_float(tmp_path, line):
+    """int('2.5') / float('4x') / int('12abc') raise ValueError in the reference's loop (IOUtil.py:12-15); a prefix parse
+    (strtoll stopping at the dot) must not be accepted silently."""
+    p = tmp_path / 'bad.txt'
+    p.write_text('0\t1\t1.0\n' + line + '\n')
+    with pytest.raises(RuntimeError, match='malformed line 2'):
+        IOUtil.loadTriplets(str(p))
+    with pytest.raises(ValueError):
+        IOUtil._loadTriplets_python(str(p))
+
+
+def test_empty_file_and_exponent_and_sign(tmp_path):
+    p = tmp_path / 'e.txt'
+    p.write_text('')
+    u, i, r = IOUtil.loadTriplets(str(p))
+    assert len(u) == len(i) == len(r) == 0
+    assert IOUtil.loadSparseR(3, 3, str(p)).nnz == 0
+    p.write_text('1 2 1e-1\n+2 0 -3.5\n')
+    u, i, r = IOUtil.loadTriplets(str(p))
+    pu, pi, pr = IOUtil._loadTriplets_python(str(p))
+    assert u.tolist() == pu.tolist() == [1, 2] and i.tolist() == pi.tolist() == [2, 0] and r.tolist() == pr.tolist() == [0.1, -3.5]
