@@ -138,3 +138,62 @@ def test_python_sources_have_no_undefined_names_or_unused_imports():
     import sys
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'lint_names.py')], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout
+
+
+def test_host_side_validation_of_the_newer_entry_points():
+    """Bad arguments are rejected on the host (status < 0 + cf_last_error), before anything touches a device."""
+    lib = _lib.lib()
+    inf = float('inf')
+    # rating path
+    assert lib.cf_predict_pairs(None, None, None, 1, 1, 4, 4, 0, None, 1, None, None, None) < 0 and b'NULL' in lib.cf_last_error()
+    assert lib.cf_predict_pairs(16, 32, None, 10, 10, 5, 6, 0, 64, 3, 128, 256, None) < 0 and b'multiple of 4' in lib.cf_last_error()
+    assert lib.cf_predict_pairs(16, 32, None, 10, 10, 4, 4, _lib.SCORE_DOT_BIAS, 64, 3, 128, 256, None) < 0 and b'score kind' in lib.cf_last_error()
+    assert lib.cf_predict_pairs(16, 32, None, 10, 10, 4, 4, 0, 64, 0, 128, 256, None) == 0          # n = 0: nothing to do
+    assert lib.cf_rating_metrics(16, 0, 32, 0, -inf, inf, 48, None) < 0 and b'no ratings' in lib.cf_last_error()
+    assert lib.cf_rating_metrics(16, 0, 32, 5, 2.0, 1.0, 48, None) < 0 and b'clip range' in lib.cf_last_error()
+    s = _lib.SvdArgs()
+    assert lib.cf_svd_grads(C.byref(s), None) < 0 and b'NULL' in lib.cf_last_error()
+    s.U, s.V, s.K, s.pairs, s.counters = 16, 32, 48, 64, 80
+    s.n_users, s.n_items, s.d, s.ld, s.ldk, s.B = 5, 5, 200, 200, 200, 10
+    assert lib.cf_svd_grads(C.byref(s), None) < 0 and b'up to 128' in lib.cf_last_error()
+    s.d, s.ld, s.ldk = 8, 8, 8
+    assert lib.cf_svd_grads(C.byref(s), None) < 0 and b'gradient tables' in lib.cf_last_error()
+    assert lib.cf_svd_predict_pairs(C.byref(s), None, None) < 0 and b'out is NULL' in lib.cf_last_error()
+    # owner-side applies
+    a = _lib.ApplyArgs()
+    assert lib.cf_apply_dense(C.byref(a), None) < 0 and b'NULL' in lib.cf_last_error()
+    a.table, a.grads, a.n_rows, a.d, a.ld, a.ldg = 16, 32, 10, 8, 8, 8
+    assert lib.cf_apply_dense(C.byref(a), None) < 0 and b'Adagrad needs' in lib.cf_last_error()      # optimizer 0 = Adagrad, no acc
+    a.acc, a.d, a.ld = 48, 8, 6
+    assert lib.cf_apply_dense(C.byref(a), None) < 0 and b'bad d/ld/ldg' in lib.cf_last_error()
+    r = _lib.ApplyArgs()
+    r.table, r.acc, r.rows, r.meta, r.slot, r.slot_row, r.staging, r.counters = 16, 32, 48, 64, 80, 96, 112, 128
+    r.n_rows, r.d, r.ld, r.ldg, r.n, r.staging_rows = 10, 8, 8, 8, 4, 4
+    assert lib.cf_apply_rows(C.byref(r), None) < 0 and b'NULL pointer' in lib.cf_last_error()          # neither grads nor segments
+    r.n_segs, r.first_seg = 2, 0
+    r.seg_grads[0], r.seg_grads[1] = 256, 512
+    r.seg_start[0], r.seg_start[1], r.seg_start[2] = 0, 3, 5
+    assert lib.cf_apply_rows(C.byref(r), None) < 0 and b'cover the n rows' in lib.cf_last_error()
+    r.seg_start[2], r.first_seg = 4, 2
+    assert lib.cf_apply_rows(C.byref(r), None) < 0 and b'first_seg' in lib.cf_last_error()
+    r.first_seg, r.n_segs = 0, 9
+    assert lib.cf_apply_rows(C.byref(r), None) < 0 and b'n_segs' in lib.cf_last_error()
+    # ALS stages, IPC
+    assert lib.cf_als_gram(None, 10, 8, 8, None, None, 0, None) < 0 and b'NULL' in lib.cf_last_error()
+    assert lib.cf_als_gram(16, 10, 200, 200, 32, 1024, 1 << 30, None) < 0 and b'bad shape' in lib.cf_last_error()
+    assert lib.cf_als_gram(16, 10, 8, 8, 32, 1024, 16, None) < 0 and b'workspace' in lib.cf_last_error()
+    assert lib.cf_ipc_export(None, None, None) < 0 and lib.cf_ipc_open(None, None) < 0 and lib.cf_ipc_close(None) < 0
+    # peer-pull arguments of the step
+    st = _lib.StepArgs()
+    st.U, st.V, st.pairs, st.negs = 16, 32, 64, 80
+    st.accU, st.accV = 96, 112
+    st.n_users, st.n_items, st.d, st.ld, st.B, st.W, st.n_batches = 10, 10, 8, 8, 4, 1, 1
+    st.model, st.optimizer, st.update = 0, 0, 1
+    st.metaU, st.metaV, st.slotU, st.slotV, st.slot_row, st.staging, st.counters = 128, 144, 160, 176, 192, 208, 224
+    st.staging_rows = lib.cf_step_staging_rows(0, 4, 1, 0)
+    st.n_peers = 9
+    assert lib.cf_train_steps(C.byref(st), None) < 0 and b'n_peers' in lib.cf_last_error()
+    st.n_peers = 2
+    assert lib.cf_train_steps(C.byref(st), None) < 0 and b'peer pull needs gradV' in lib.cf_last_error()
+    st.n_peers, st.gradU = 0, 256
+    assert lib.cf_train_steps(C.byref(st), None) < 0 and b'gradU needs gradV' in lib.cf_last_error()
