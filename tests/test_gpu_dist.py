@@ -128,7 +128,7 @@ def test_peer_pull_from_three_shards_equals_fetched_rows(kind, W):
         out[mode] = (eng.U.cpu().numpy(), Gbuf.cpu().numpy(), float(loss.item()))
     assert np.abs(out['fetch'][1]).max() > 0
     np.testing.assert_allclose(out['pull'][0], out['fetch'][0], rtol=2e-5, atol=2e-6)
-    np.testing.assert_allclose(out['pull'][1], out['fetch'][1], rtol=2e-5, atol=2e-5 if kind == 'cml' else 2e-6)   # red.add order differs
+    np.testing.assert_allclose(out['pull'][1], out['fetch'][1], rtol=2e-5, atol=5e-5 if kind == 'cml' else 4e-6)   # red.add order differs (run to run, too)
     assert abs(out['pull'][2] - out['fetch'][2]) <= 1e-6 * abs(out['fetch'][2])
 
 
@@ -224,7 +224,7 @@ def test_replicated_mode_equals_fused_step(kind, d, W, halves):
         sa, sb = _state(a), _state(b)
         for k in sa:
             scale = float(np.abs(sa[k]).max())
-            np.testing.assert_allclose(sb[k], sa[k], rtol=5e-5, atol=5e-5 * max(scale, 1.0) if kind == 'cml' else 2e-6 * max(scale, 1.0),   # CML: ~25 rank-weighted (x10) gradients per item row, fp32 sums regrouped
+            np.testing.assert_allclose(sb[k], sa[k], rtol=5e-5, atol=1e-4 * max(scale, 1.0) if kind == 'cml' else 4e-6 * max(scale, 1.0),   # CML: ~25 rank-weighted (x10) gradients per item row, fp32 sums regrouped
                                        err_msg='%s step %d %s' % (kind, s, k))
 
 
