@@ -46,23 +46,20 @@ def error_sums(ys_true, ys_pred, clip=None, device=None):
     return a, q, n
 
 
-# MAEs
 def mean_absolute_error(ys_true, ys_pred):
-    """Computes Mean Absolute Error between true and predicted arrays of ratings (rating.py:4-6)."""
+    """MAE: mean of |t - p| over the rating pairs (same name and value as rating.py:4-6)."""
     a, _, n = error_sums(ys_true, ys_pred)
     return 1 / n * a
 
 
-# MSEs
 def mean_squared_error(ys_true, ys_pred):
-    """Computes Mean Squared Error between true and predicted arrays of ratings (rating.py:9-11)."""
+    """MSE: mean of (t - p)^2 (same name and value as rating.py:9-11)."""
     _, q, n = error_sums(ys_true, ys_pred)
     return 1 / n * q
 
 
-# RMSEs
 def root_mean_squared_error(ys_true, ys_pred):
-    """Computes Root Mean Squared Error between true and predicted arrays of ratings (rating.py:14-16)."""
+    """RMSE: square root of the MSE (same name and value as rating.py:14-16)."""
     _, q, n = error_sums(ys_true, ys_pred)
     return float(np.sqrt(1 / n * q))
 
