@@ -5,8 +5,6 @@ The reference inserts one element at a time into a lil_matrix; here the file is 
 import numpy as np
 from scipy.sparse import coo_matrix, lil_matrix
 
-from .Util import split_row
-
 
 def loadTriplets(inFilePath):
     """(users, items, ratings) of every 2- or 3-field line, parsed by the native one-pass parser (cf_parse_triplets)."""
@@ -26,19 +24,6 @@ def loadTriplets(inFilePath):
         for p in (pu, pi, pr):
             lib.cf_free_host(C.cast(p, C.c_void_p))
     return u, i, r
-
-
-def _loadTriplets_python(inFilePath):
-    """The reference's per-line loop, kept for the parser's own test."""
-    us, is_, rs = [], [], []
-    with open(inFilePath, 'r') as infile:
-        for line in infile:
-            phs = split_row(line)
-            if len(phs) == 2:
-                us.append(int(phs[0])); is_.append(int(phs[1])); rs.append(1.0)
-            elif len(phs) == 3:
-                us.append(int(phs[0])); is_.append(int(phs[1])); rs.append(float(phs[2]))
-    return np.asarray(us, dtype=np.int64), np.asarray(is_, dtype=np.int64), np.asarray(rs, dtype=np.float64)
 
 
 def loadSparseR(usernum, itemnum, inFilePath):

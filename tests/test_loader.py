@@ -8,11 +8,24 @@ import pytest
 from collaborativefilteringusingtensorflow_b200.utils import IOUtil, Util
 
 
+def _reference_loop(inFilePath):
+    """The reference's per-line loop (utils/IOUtil.py:9-15), restated here as the checker of the native parser."""
+    us, is_, rs = [], [], []
+    with open(inFilePath, 'r') as infile:
+        for line in infile:
+            phs = Util.split_row(line)
+            if len(phs) == 2:
+                us.append(int(phs[0])); is_.append(int(phs[1])); rs.append(1.0)
+            elif len(phs) == 3:
+                us.append(int(phs[0])); is_.append(int(phs[1])); rs.append(float(phs[2]))
+    return np.asarray(us, dtype=np.int64), np.asarray(is_, dtype=np.int64), np.asarray(rs, dtype=np.float64)
+
+
 def test_parser_handles_separators_crlf_and_skips(tmp_path):
     p = tmp_path / 'r.txt'
     p.write_text('0\t1\t4.0\r\n2,3,5\n4;5;1.5\n6 7\n\nbad line with five fields x\n1\t1\t2.0\n0\t1\t3.0\n')
     u, i, r = IOUtil.loadTriplets(str(p))
-    pu, pi, pr = IOUtil._loadTriplets_python(str(p))
+    pu, pi, pr = _reference_loop(str(p))
     np.testing.assert_array_equal(u, pu)
     np.testing.assert_array_equal(i, pi)
     np.testing.assert_array_equal(r, pr)
@@ -53,7 +66,7 @@ def test_malformed_numbers_are_rejected_like_python_int_float(tmp_path, line):
     with pytest.raises(RuntimeError, match='malformed line 2'):
         IOUtil.loadTriplets(str(p))
     with pytest.raises(ValueError):
-        IOUtil._loadTriplets_python(str(p))
+        _reference_loop(str(p))
 
 
 def test_empty_file_and_exponent_and_sign(tmp_path):
@@ -64,5 +77,5 @@ def test_empty_file_and_exponent_and_sign(tmp_path):
     assert IOUtil.loadSparseR(3, 3, str(p)).nnz == 0
     p.write_text('1 2 1e-1\n+2 0 -3.5\n')
     u, i, r = IOUtil.loadTriplets(str(p))
-    pu, pi, pr = IOUtil._loadTriplets_python(str(p))
+    pu, pi, pr = _reference_loop(str(p))
     assert u.tolist() == pu.tolist() == [1, 2] and i.tolist() == pi.tolist() == [2, 0] and r.tolist() == pr.tolist() == [0.1, -3.5]
