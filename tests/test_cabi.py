@@ -197,3 +197,27 @@ def test_host_side_validation_of_the_newer_entry_points():
     assert lib.cf_train_steps(C.byref(st), None) < 0 and b'peer pull needs gradV' in lib.cf_last_error()
     st.n_peers, st.gradU = 0, 256
     assert lib.cf_train_steps(C.byref(st), None) < 0 and b'gradU needs gradV' in lib.cf_last_error()
+
+
+def test_reference_layout_is_importable_without_a_gpu():
+    """Every module a reference driver imports (testbprmf.py:5-13 and friends) exists under the same relative layout and
+    imports on a box without a GPU; constructing a model is what needs CUDA."""
+    import importlib
+    pkg = 'collaborativefilteringusingtensorflow_b200'
+    for mod, names in (('models.pl.models.bprmf', ['BPRMF']), ('models.pl.models.cml', ['CML']), ('models.pl.models.gbprmf', ['GBPRMF']),
+                       ('models.PL.models.bprmf', ['BPRMF']), ('models.basic.models.wrmf', ['WRMF']), ('models.basic.models.mf', ['MF']),
+                       ('models.basic.models.svd', ['SVD']), ('models.basic.models.pop', ['PopRank']),
+                       ('samplers.sampler_ranking', ['Sampler']), ('samplers.sampler_uij_ranking', ['Sampler']),
+                       ('samplers.sampler_gbpr', ['Sampler']), ('samplers.sampler_rating', ['Sampler']),
+                       ('metrics.ranking', ['evaluateCV', 'evaluateLOOV', 'precision_k_score', 'recall_k_score', 'ndcg_k_score',
+                                            'map_k_score', 'mrr_k_score', 'hr_k_score', 'arhr_k_score']),
+                       ('metrics.rating', ['evaluate', 'mean_absolute_error', 'mean_squared_error', 'root_mean_squared_error']),
+                       ('utils.IOUtil', ['loadSparseR', 'saveTriads']), ('utils.Util', ['split_row', 'matBinarize']),
+                       ('dist', ['DistributedTrainer', 'ReplicatedTrainer', 'DistributedALS', 'distributed_topk', 'distributed_evaluate']),
+                       ('drivers', ['run', 'worker'])):
+        m = importlib.import_module(pkg + '.' + mod)
+        for n in names:
+            assert hasattr(m, n), (mod, n)
+    top = importlib.import_module(pkg)
+    for n in ('BPRMF', 'CML', 'GBPRMF', 'WRMF', 'MF', 'SVD', 'PopRank'):
+        assert getattr(top, n).__name__ == n
