@@ -1,7 +1,9 @@
 """bench.py's N > 1 arm: weak scaling of the N=1 workload (same users, interactions and minibatch PER GPU; the item
 catalogue keeps its global size and is row-sharded, like BASELINE.json configs[4] keeps 10 M items for 8 x 12.5 M users):
-users range-sharded, items sharded by item % N, per-minibatch NCCL all-to-all of requested item rows and their gradients
-(SURVEY.md 8e).  `--grow-catalogue` instead multiplies the catalogue by N (every rank owns n_items rows)."""
+users range-sharded, items sharded by item % N, per-minibatch exchange of requested item rows and their gradients
+(SURVEY.md 8e).  `--grow-catalogue` instead multiplies the catalogue by N (every rank owns n_items rows).
+Every N > 1 line also carries `c5`: BASELINE.json configs[4] at this N (BPRMF, 12.5 M users and 625 M interactions per
+GPU, 10 M items row-sharded: the sharded step and the item-sharded 10 M-item top-100)."""
 import json
 import sys
 import time
@@ -10,19 +12,21 @@ import torch
 import torch.distributed as dist
 
 
-def run_distributed(args, rank, world, device):
-    import bench as B_
+def _max_over_ranks(x, device):
+    t = torch.tensor([float(x)], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sharded_training(B_, wl, args, rank, world, device, n_items_global, K, Wm, want_e2e=True):
+    """Builds this rank's share of the workload and times K sharded minibatches (barrier + synchronize on both sides, CUDA
+    events, max over ranks).  Returns (model, csr, trainer, dict of numbers)."""
     from collaborativefilteringusingtensorflow_b200.dist import DistributedTrainer, item_shard_rows
-    wl = dict(B_.WORKLOADS[args.workload])
-    if wl['model'] not in ('cml', 'bpr'):
-        raise SystemExit('the sharded path supports the cml / bpr workloads')
-    n_items_global = wl['n_items'] * (world if getattr(args, 'grow_catalogue', False) else 1)
-    B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
-    pk = B_.peaks()
-    csr = B_.synth_interactions(wl['n_users'], n_items_global, wl['nnz'], 2026 + rank, device)
+    B = args.batch
+    csr = B_.synth_interactions(wl['n_users'], n_items_global, wl['nnz'], B_.SEED + rank, device)
     local_wl = dict(wl, n_items=item_shard_rows(n_items_global, world, rank))
-    model = B_.make_model(local_wl, device, seed=2026 + rank, optimizer=args.optimizer, update='sync')
-    sampler = B_.make_sampler(wl, csr, B, 2026 + rank, device)
+    model = B_.make_model(local_wl, device, seed=B_.SEED + rank, optimizer=args.optimizer, update='sync')
+    sampler = B_.make_sampler(wl, csr, B, B_.SEED + rank, device)
     tr = DistributedTrainer(model, sampler, n_items_global, world, rank, item_transport=args.item_transport)
     tr.step(Wm)
     model.engine.check_flags()
@@ -30,11 +34,6 @@ def run_distributed(args, rank, world, device):
     del warm
     torch.cuda.synchronize()
     dist.barrier()
-
-    clk = B_.ClockSampler(device.index)
-    if rank == 0:
-        clk.start()
-        time.sleep(0.3)
     l0, s0, b0, p0 = tr.launches, sampler.launches, tr.bytes_sent, tr.bytes_pulled
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dist.barrier()
@@ -48,96 +47,147 @@ def run_distributed(args, rank, world, device):
     torch.cuda.synchronize()
     dist.barrier()
     t1 = time.time()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
+    ms = _max_over_ranks(e0.elapsed_time(e1), device)
     launches = (tr.launches - l0) + (sampler.launches - s0)
     if args.phases and rank == 0:
         evs, tr.step_events = [e0] + tr.step_events, None
         print('per-minibatch ms: ' + ' '.join('%.2f' % evs[k].elapsed_time(evs[k + 1]) for k in range(len(evs) - 1)), file=sys.stderr)
+    tr.step_events = None
     sent = (tr.bytes_sent - b0) / K
     pulled = (tr.bytes_pulled - p0) / K * (world - 1) / world     # the share of the item rows that lives on other GPUs
     model.engine.check_flags()
-
-    # e2e: host index buffers -> H2D -> sharded step -> D2H loss, every step
-    host = [t.cpu().pin_memory() for t in sampler.next_chunk(K)]
-    dist.barrier()
-    torch.cuda.synchronize()
-    e0.record()
-    for k in range(K):
-        dev = [t[k * B:(k + 1) * B].to(device, non_blocking=True) for t in host]
-        _ = tr.step_chunk(dev[0], dev[1], B).cpu()
-    e1.record()
-    torch.cuda.synchronize()
-    dist.barrier()
-    ms2 = torch.tensor([e0.elapsed_time(e1)], device=device)
-    dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    ms2 = float(ms2.item())
-    # ---- evaluation: item-sharded full-catalogue top-100 of rank 0's users, merged with an all-gather
-    topk = None
-    if args.topk_users > 0:
-        from collaborativefilteringusingtensorflow_b200.dist import distributed_topk, shard_mask_csr
-        from collaborativefilteringusingtensorflow_b200.sparse import DeviceCSR
-        Tq = min(args.topk_users, wl['n_users'])
-        eng = model.engine
-        # the query users live on rank 0: broadcast their embeddings and their training rows (global item ids)
-        q = eng.U[:Tq].clone() if rank == 0 else torch.empty(Tq, eng.ld, device=device)
-        dist.broadcast(q, 0)
-        sub = csr.select_rows(torch.arange(Tq, device=device)) if rank == 0 else None
-        meta = torch.tensor([sub.nnz if rank == 0 else 0], device=device)
-        dist.broadcast(meta, 0)
-        nnz = int(meta.item())
-        ind = sub.indices if rank == 0 else torch.empty(nnz, dtype=torch.int32, device=device)
-        rws = sub.rows if rank == 0 else torch.empty(nnz, dtype=torch.int32, device=device)
-        ptr = sub.indptr if rank == 0 else torch.empty(Tq + 1, dtype=torch.int64, device=device)
-        for t in (ind, rws, ptr):
-            dist.broadcast(t, 0)
-        mask = shard_mask_csr(DeviceCSR(ptr, ind, rws, None, (Tq, n_items_global)), world, rank)
-        distributed_topk(eng, q[:1024], 100, shard_mask_csr(DeviceCSR(ptr[:1025].clone(), ind[:int(ptr[1024])], rws[:int(ptr[1024])],
-                                                                      None, (1024, n_items_global)), world, rank), world, rank, method='tensor')
+    out = dict(ms=ms, t0=t0, t1=t1, launches=launches, losses=losses, sent=sent, pulled=pulled, e2e_ms=None, h2d=None)
+    if want_e2e:
+        # e2e: pinned host index buffers -> H2D -> sharded step -> D2H loss, every step
+        host = [t.cpu().pin_memory() for t in sampler.next_chunk(K)]
+        loss_host = torch.zeros(K, dtype=torch.float64).pin_memory()
         dist.barrier()
         torch.cuda.synchronize()
         e0.record()
-        gi, gv = distributed_topk(eng, q, 100, mask, world, rank, method='tensor')
+        for k in range(K):
+            dev = [t[k * B:(k + 1) * B].to(device, non_blocking=True) for t in host]
+            loss_host[k:k + 1].copy_(tr.step_chunk(dev[0], dev[1], B), non_blocking=True)
         e1.record()
         torch.cuda.synchronize()
         dist.barrier()
-        tms = torch.tensor([e0.elapsed_time(e1)], device=device)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        tms = float(tms.item())
-        fl = 2.0 * n_items_global * wl['d'] * Tq
-        topk = dict(metric='users/s full-catalog top-100 (mask train items), items sharded over %d GPUs, all-gather merge' % world,
-                    value=Tq / (tms * 1e-3), users=Tq, n_items=n_items_global, ms=tms, tflops_aggregate=fl / (tms * 1e-3) / 1e12,
-                    fallback_rows_rank0=int(eng.tc_stats[0].item()))
-    phases = None
-    if args.phases:
-        tr.phase_ms = {}
-        tr.step(5)
-        phases = {k: v / 5 for k, v in tr.phase_ms.items()}
-        tr.phase_ms = None
-    if rank != 0:
-        return
-    clocks = clk.stop(t0, t1)
+        out['e2e_ms'] = _max_over_ranks(e0.elapsed_time(e1), device)
+        out['h2d'] = sum(int(t[:B].numel()) * t.element_size() for t in host)
+    # per-phase CUDA-event times (synchronises after every phase, so the phases do not overlap: their sum exceeds a step)
+    tr.phase_ms = {}
+    tr.step(5)
+    ph = {k: v / 5 for k, v in tr.phase_ms.items()}
+    tr.phase_ms = None
+    keys = sorted(ph)
+    vals = torch.tensor([ph[k] for k in keys], device=device, dtype=torch.float64)
+    dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    out['phases'] = dict(zip(keys, [float(v) for v in vals.tolist()]))
+    return model, csr, tr, out
+
+
+def sharded_topk(B_, model, csr, n_items_global, wl, Tq, rank, world, device, pk):
+    """Item-sharded full-catalogue top-100 of rank 0's first Tq users, merged across ranks."""
+    from collaborativefilteringusingtensorflow_b200.dist import distributed_topk, shard_mask_csr
+    from collaborativefilteringusingtensorflow_b200.sparse import DeviceCSR
+    eng = model.engine
+    # the query users live on rank 0: broadcast their embeddings and their training rows (global item ids)
+    q = eng.U[:Tq].clone() if rank == 0 else torch.empty(Tq, eng.ld, device=device)
+    dist.broadcast(q, 0)
+    sub = csr.select_rows(torch.arange(Tq, device=device)) if rank == 0 else None
+    meta = torch.tensor([sub.nnz if rank == 0 else 0], device=device)
+    dist.broadcast(meta, 0)
+    nnz = int(meta.item())
+    ind = sub.indices if rank == 0 else torch.empty(nnz, dtype=torch.int32, device=device)
+    rws = sub.rows if rank == 0 else torch.empty(nnz, dtype=torch.int32, device=device)
+    ptr = sub.indptr if rank == 0 else torch.empty(Tq + 1, dtype=torch.int64, device=device)
+    for t in (ind, rws, ptr):
+        dist.broadcast(t, 0)
+    mask = shard_mask_csr(DeviceCSR(ptr, ind, rws, None, (Tq, n_items_global)), world, rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    distributed_topk(eng, q, 100, mask, world, rank, method='tensor')           # warm-up: sizes every workspace
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    gi, gv = distributed_topk(eng, q, 100, mask, world, rank, method='tensor')
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    tms = _max_over_ranks(e0.elapsed_time(e1), device)
+    fl = 2.0 * n_items_global * wl['d'] * Tq
+    tf = fl / (tms * 1e-3) / 1e12
+    return dict(metric='users/s full-catalog top-100 (mask train items), items sharded over %d GPUs, lists merged across ranks' % world,
+                value=Tq / (tms * 1e-3), unit='users/s', users=Tq, n_items=n_items_global, ms=tms, tflops_aggregate=tf,
+                frac_of_tensor_peak_per_gpu=tf / world / pk['bf16'], fallback_rows_rank0=int(eng.tc_stats[0].item()))
+
+
+def step_line(B_, wl, args, world, K, Wm, r, n_items_global, tr, pk):
+    B = args.batch
+    ms = r['ms']
     units = world * B * wl['W'] * K
     bpp = B_.bytes_per_pair(wl['model'], wl['d'], wl['W'], wl['G'], args.optimizer)
     achieved = bpp * B / (ms / K * 1e-3) / 1e9            # per GPU, whole sharded step (exchange included)
-    out = dict(metric='triple updates/s (fused pairwise-ranking step incl. on-device sampling) @d=%d' % wl['d'],
-               value=units / (ms * 1e-3), unit='triple updates/s', n_gpus=world, steps=K, warmup=Wm, ms_per_step=ms / K,
-               higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
-               config=dict(workload=wl['desc'] + ' -- users, interactions and minibatch PER GPU; %d items in total, row-sharded by '
-                           'item %% N; users range-sharded; NCCL all-to-all of item rows + gradients per minibatch'
-                           % n_items_global,
-                           batch_pairs_per_gpu=B, negatives=wl['W'], optimizer=args.optimizer, update='sync',
-                           item_transport=('peer (fused NVLink reads in k_step)' if tr._pull else 'nccl (all-to-all of unique rows)'),
-                           l2='inputs larger than L2 (random rows of GB-sized tables)'),
-               gpu_launches=launches,
-               e2e=dict(value=units / (ms2 * 1e-3), unit='triple updates/s', ms_per_step=ms2 / K,
-                        h2d_bytes_per_step=sum(int(t[:B].numel()) * t.element_size() for t in host), d2h_bytes_per_step=8),
-               roofline=dict(bound='hbm', kernel='whole sharded step per GPU (k_count + k_step + k_apply_staged + exchange + owner apply)',
-                             achieved=achieved, peak=pk['hbm'], unit='GB/s', frac=achieved / pk['hbm'], traffic=None,
-                             peak_source=pk['source']),
-               nvlink=dict(bytes_pulled_per_step_per_gpu=pulled,
-                           bytes_sent_per_step_per_gpu=sent, achieved_GBs=sent / (ms / K * 1e-3) / 1e9,
-                           peak_GBs_per_direction=770.0, note='rows out + gradients back + ids; measured peer copy 770 GB/s/dir'),
-               phases_ms_per_step=phases, topk=topk, cpu_baseline=None, clocks=clocks, loss_first_last=[float(losses[0]), float(losses[-1])])
+    nv_bytes = r['sent'] + r['pulled']
+    return dict(value=units / (ms * 1e-3), unit='triple updates/s', ms_per_step=ms / K, steps=K, gpu_launches=r['launches'],
+                item_transport=('peer (fused NVLink reads in k_step)' if tr._pull else 'nccl (all-to-all of unique rows)') +
+                               (' + owner-pull of gradient rows' if tr.peer_ptrs is not None else ' + all-to-all of gradient rows'),
+                roofline=dict(bound='hbm', kernel='whole sharded step per GPU (plan + k_count + k_step + k_apply_staged + exchange + owner apply)',
+                              achieved=achieved, peak=pk['hbm'], unit='GB/s', frac=achieved / pk['hbm'], traffic=None,
+                              peak_source=pk['source']),
+                nvlink=dict(bytes_per_step_per_gpu=nv_bytes, bytes_sent_nccl=r['sent'], bytes_read_peer=r['pulled'],
+                            achieved_GBs=nv_bytes / (ms / K * 1e-3) / 1e9, peak_GBs_per_direction=770.0,
+                            frac=nv_bytes / (ms / K * 1e-3) / 1e9 / 770.0,
+                            note='item rows in + gradient rows out + ids, per GPU per minibatch, over the whole step time; '
+                                 'measured peer copy 770 GB/s per direction'),
+                phases_ms_per_step=r['phases'],
+                loss_first_last=[float(r['losses'][0]), float(r['losses'][-1])])
+
+
+def run_distributed(args, rank, world, device):
+    import bench as B_
+    wl = dict(B_.WORKLOADS[args.workload])
+    if wl['model'] not in ('cml', 'bpr'):
+        raise SystemExit('the sharded path supports the cml / bpr workloads')
+    n_items_global = wl['n_items'] * (world if getattr(args, 'grow_catalogue', False) else 1)
+    B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
+    pk = B_.peaks()
+    clk = B_.ClockSampler(device.index)
+    if rank == 0:
+        clk.start()
+        time.sleep(0.3)
+    model, csr, tr, r = sharded_training(B_, wl, args, rank, world, device, n_items_global, K, Wm)
+    clocks = clk.stop(r['t0'], r['t1']) if rank == 0 else None
+    topk = None
+    if args.topk_users > 0:
+        topk = sharded_topk(B_, model, csr, n_items_global, wl, min(args.topk_users, wl['n_users']), rank, world, device, pk)
+    line = step_line(B_, wl, args, world, K, Wm, r, n_items_global, tr, pk)
+    tr.close()
+    del model, csr, tr
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE.json configs[4] at this N: BPRMF, 12.5M users + 625M interactions per GPU, 10M items row-sharded
+    c5 = None
+    if args.workload == 'c2' and not args.no_c5:
+        w5 = dict(B_.WORKLOADS['c5'])
+        K5 = max(3, min(K, args.other_steps))
+        m5, csr5, tr5, r5 = sharded_training(B_, w5, args, rank, world, device, w5['n_items'], K5, 3, want_e2e=False)
+        c5 = step_line(B_, w5, args, world, K5, 3, r5, w5['n_items'], tr5, pk)
+        c5['workload'] = w5['desc'] + ' -- at %d GPUs: %d users, %d interactions in total' % (world, world * w5['n_users'], world * csr5.nnz)
+        if args.topk_users > 0:
+            c5['topk'] = sharded_topk(B_, m5, csr5, w5['n_items'], w5, min(args.topk_users, w5['n_users']), rank, world, device, pk)
+        tr5.close()
+        del m5, csr5, tr5
+        torch.cuda.empty_cache()
+    if rank != 0:
+        return
+    units = world * B * wl['W'] * K
+    cfg = B_.same_config(wl, args)
+    cfg['workload'] = wl['desc'] + ' -- users, interactions and minibatch PER GPU; %d items in total, row-sharded by item %% N; ' \
+                                   'users range-sharded; item rows and gradient rows exchanged per minibatch' % n_items_global
+    cfg['batch_pairs_per_gpu'] = B
+    out = dict(metric=B_.metric_name(wl['d']), value=line['value'], unit='triple updates/s', n_gpus=world, steps=K, warmup=Wm,
+               ms_per_step=line['ms_per_step'], higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+               data='synthetic', config=cfg, gpu_launches=line['gpu_launches'], item_transport=line['item_transport'],
+               e2e=dict(value=units / (r['e2e_ms'] * 1e-3), unit='triple updates/s', ms_per_step=r['e2e_ms'] / K,
+                        h2d_bytes_per_step=r['h2d'], d2h_bytes_per_step=8),
+               roofline=line['roofline'], nvlink=line['nvlink'], phases_ms_per_step=line['phases_ms_per_step'], topk=topk, c5=c5,
+               cpu_baseline=None, clocks=clocks, loss_first_last=line['loss_first_last'])
     print(json.dumps(out))

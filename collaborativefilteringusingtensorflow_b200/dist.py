@@ -185,8 +185,21 @@ class DistributedTrainer(object):
                 warnings.warn('peer memory is not available (%s): item rows and gradients travel through NCCL' % e)
                 self.close()
                 self._gbuf, self._pull = None, False
-        if self.eng.kind == 'cml':   # one-time whole-table clip, then touched-row clips suffice
-            self.eng._full_clip(self.torch.cuda.current_stream(self.eng.device).cuda_stream)
+        self._bar = None              # preallocated 1-element tensor of the named cross-GPU barrier
+
+    def _barrier(self, why):
+        """Named cross-GPU barrier ON THE COMPUTE STREAM: a 1-element NCCL all_reduce enqueued on the current stream
+        completes only after every rank has enqueued it, i.e. after everything each rank enqueued before it.  The peer
+        transports rely on that order (remote NVLink reads of V / Gbuf against the owners' applies and zeroing), so the
+        process group must be NCCL -- gloo would synchronise the HOSTS and not order the streams."""
+        if self.world == 1:
+            return
+        dist = self.ex.dist
+        if dist.get_backend(self.ex.group) != 'nccl':
+            raise RuntimeError('peer transport needs an NCCL process group (barrier "%s" orders CUDA streams)' % why)
+        if self._bar is None:
+            self._bar = self.torch.zeros(1, device=self.eng.device)
+        dist.all_reduce(self._bar, group=self.ex.group)
 
     def _map_peer_shards(self):
         """Maps every peer's item shard into this process."""
@@ -359,8 +372,7 @@ class DistributedTrainer(object):
         _lib.check(self.lib.cf_train_steps(a, stream), 'cf_train_steps')
         ev = self._tick('k_count + k_step + k_apply_staged', ev)
         if peer:
-            if self.world > 1:   # every rank's gradient buffer is complete once all ranks are past their step kernels
-                self.ex.dist.all_reduce(torch.zeros(1, device=eng.device), group=self.ex.group)
+            self._barrier('gradient buffers complete')   # every rank is past its step kernel
             ev = self._tick('barrier (gradient buffers complete)', ev)
             recv, n = None, int(plan.recv_local_rows.numel())
         else:
@@ -384,6 +396,11 @@ class DistributedTrainer(object):
             ap.meta, ap.slot, ap.slot_row = _lib.ptr(ows['meta']), _lib.ptr(ows['slot']), _lib.ptr(ows['slot_row'])
             ap.staging, ap.staging_rows, ap.counters = _lib.ptr(ows['staging']), ows['staging'].shape[0], _lib.ptr(eng.counters)
             _lib.check(self.lib.cf_apply_rows(ap, stream), 'cf_apply_rows')
+        if eng._needs_full_clip:
+            # cml.py:119-129 clips BOTH whole tables after every step; after the first such clip every row has norm <= clip
+            # and the touched-row clip fused into the applies is the same thing.  Like
+            # engine.train_batches: step first, THEN clip -- the first minibatch's gradients see the unclipped init.
+            eng._full_clip(stream)
         ev = self._tick('owner apply (cf_apply_rows)', ev)
         self.launches += 3 + 3
         self.bytes_sent += ((0 if pull else plan.n_req) + (0 if peer else n)) * eng.ld * 4 + plan.n_req * 4
@@ -596,8 +613,6 @@ class ReplicatedTrainer(object):
             for t in (eng.U, eng.V, eng.accU, eng.accV, eng.b, eng.accb):
                 if t is not None:
                     dist.broadcast(t, 0, group=group)
-        if eng.kind == 'cml':    # one-time whole-table clip, then the clip fused into the apply suffices
-            eng._full_clip(torch.cuda.current_stream(eng.device).cuda_stream)
 
     def _apply(self, table, acc, grad, ld, d):
         eng = self.eng
@@ -623,6 +638,8 @@ class ReplicatedTrainer(object):
         self._apply(eng.V, eng.accV, self.gV, eng.ld, eng.d)
         if self.gb is not None:
             self._apply(eng.b, eng.accb, self.gb, 1, 1)
+        if eng._needs_full_clip:   # step first, then the one-time whole-table clip (cml.py:119-129)
+            eng._full_clip(self.torch.cuda.current_stream(eng.device).cuda_stream)
         self.launches += 3 + (1 if self.gb is not None else 0)
         return loss
 
