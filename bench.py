@@ -99,28 +99,33 @@ def synth_coo(n_users, n_items, nnz, seed, device):
     no per-user duplicates; returns the sorted keys user * n_items + item (torch int64, on `device` -- CUDA for the GPU
     arm, CPU for the reference arm: same code, same distribution).  Data generation only, not part of the hot path."""
     import torch
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
     mean = nnz / n_users
     cap = max(1.0, min(n_items / 2, 10 * mean))
     ranks = torch.arange(1, n_users + 1, device=device, dtype=torch.float64)
-    lo, hi = 0.0, float(nnz) * 10
-    for _ in range(60):        # scale c so that sum clamp(c / rank, 1, cap) = nnz (oversampled 3% for the dedupe)
-        c = 0.5 * (lo + hi)
-        tot = float(torch.clamp(c / ranks, 1.0, cap).sum())
-        lo, hi = (c, hi) if tot < nnz * 1.03 else (lo, c)
-    deg = torch.clamp(c / ranks, 1.0, cap).round().to(torch.int64)
-    deg = deg[torch.randperm(n_users, device=device, generator=g)]
-    users = torch.repeat_interleave(torch.arange(n_users, device=device, dtype=torch.int64), deg)
     pop = torch.arange(1, n_items + 1, device=device, dtype=torch.float64) ** -0.8
     cdf = torch.cumsum(pop / pop.sum(), 0)
-    r = torch.rand(users.numel(), device=device, generator=g, dtype=torch.float64)
-    items = torch.searchsorted(cdf, r).clamp_(max=n_items - 1)
-    del r
-    items = torch.randperm(n_items, device=device, generator=g)[items]      # popular items are not the low ids
-    key = torch.unique(users * n_items + items)                               # sorted, per-user duplicates dropped
-    del users, items
-    if key.numel() > nnz:                                                     # thin uniformly down to nnz
+    over = 1.03                # draws per kept interaction: per-user duplicates are dropped, so oversample (and retry
+    for attempt in range(4):   # with a larger factor when a small, skewed catalogue loses more than that)
+        g = torch.Generator(device=device)
+        g.manual_seed(seed)
+        lo, hi = 0.0, float(nnz) * 20
+        for _ in range(60):    # scale c so that sum clamp(c / rank, 1, cap) = over * nnz
+            c = 0.5 * (lo + hi)
+            tot = float(torch.clamp(c / ranks, 1.0, cap).sum())
+            lo, hi = (c, hi) if tot < nnz * over else (lo, c)
+        deg = torch.clamp(c / ranks, 1.0, cap).round().to(torch.int64)
+        deg = deg[torch.randperm(n_users, device=device, generator=g)]
+        users = torch.repeat_interleave(torch.arange(n_users, device=device, dtype=torch.int64), deg)
+        r = torch.rand(users.numel(), device=device, generator=g, dtype=torch.float64)
+        items = torch.searchsorted(cdf, r).clamp_(max=n_items - 1)
+        del r
+        items = torch.randperm(n_items, device=device, generator=g)[items]      # popular items are not the low ids
+        key = torch.unique(users * n_items + items)                               # sorted, per-user duplicates dropped
+        del users, items
+        if key.numel() >= nnz or attempt == 3:
+            break
+        over *= 1.02 * nnz / key.numel()
+    if key.numel() > nnz:                                                         # thin uniformly down to nnz
         keep = torch.randperm(key.numel(), device=device, generator=g)[:nnz]
         key = key[torch.sort(keep).values]
     return key
@@ -368,7 +373,9 @@ def time_training(wl, csr, B, K, Wm, device, optimizer, update, pk):
 def time_e2e(model, sampler, B, K, device):
     """The same K minibatches through the public API from HOST buffers: every step's index arrays come from pinned host
     memory (H2D on a copy stream, double-buffered so that the copy of minibatch k+1 runs under step k) and every step's
-    loss is read back into pinned host memory (async D2H, one event wait at the end)."""
+    loss is read back into pinned host memory (async D2H, one event wait at the end).  The metric includes sampling, so
+    every step ALSO launches the on-device sampler for one minibatch (the batches that are stepped on are the host ones,
+    like a reference `next_batch()` result fed through feed_dict)."""
     import torch
     host = [t.cpu().pin_memory() for t in sampler.next_chunk(K)]
     main = torch.cuda.current_stream(device)
@@ -390,6 +397,7 @@ def time_e2e(model, sampler, B, K, device):
                 dst.copy_(src[k * B:(k + 1) * B], non_blocking=True)
             ready[s].record(copy)
         main.wait_event(ready[s])
+        sampled = sampler.next_chunk(1)                      # the sampling work of this step (metric: "incl. sampling")
         loss_k = model._train_arrays(bufs[s], B)
         loss_host[k:k + 1].copy_(loss_k, non_blocking=True)  # D2H of the step's result
         free[s].record(main)
@@ -463,8 +471,9 @@ def run_ours(args):
     # ---- e2e: pinned host index buffers -> H2D -> step -> D2H loss, every step, through the public engine API
     ms_e2e, h2d, _ = time_e2e(model, sampler, B, K, device)
     e2e = dict(value=units / (ms_e2e * 1e-3), unit='triple updates/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=8,
-               ms_per_step=ms_e2e / K, pipeline='H2D of minibatch k+1 on a copy stream under step k (double-buffered); '
-                                                'per-step async D2H of the loss')
+               ms_per_step=ms_e2e / K, pipeline='per step: on-device sampling of one minibatch + H2D of the minibatch\'s index arrays '
+                                                'from pinned host memory (copy stream, double-buffered: the copy of minibatch k+1 runs '
+                                                'under step k) + the three step kernels + async D2H of the loss')
 
     # ---- secondary metric: users/s of full-catalog masked top-100 (tcgen05/TMA candidate pass + exact fp64 re-rank)
     topk = None
