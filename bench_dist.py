@@ -35,6 +35,7 @@ def sharded_training(B_, wl, args, rank, world, device, n_items_global, K, Wm, w
     torch.cuda.synchronize()
     dist.barrier()
     l0, s0, b0, p0 = tr.launches, sampler.launches, tr.bytes_sent, tr.bytes_pulled
+    q0 = int(tr.req_rows_dev.item()) if tr.req_rows_dev is not None else 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dist.barrier()
     torch.cuda.synchronize()
@@ -54,7 +55,15 @@ def sharded_training(B_, wl, args, rank, world, device, n_items_global, K, Wm, w
         print('per-minibatch ms: ' + ' '.join('%.2f' % evs[k].elapsed_time(evs[k + 1]) for k in range(len(evs) - 1)), file=sys.stderr)
     tr.step_events = None
     sent = (tr.bytes_sent - b0) / K
-    pulled = (tr.bytes_pulled - p0) / K * (world - 1) / world     # the share of the item rows that lives on other GPUs
+    remote = (world - 1) / world                                  # the share of the item rows that lives on other GPUs
+    pulled = (tr.bytes_pulled - p0) / K * remote                  # pull transport: one row per occurrence, read inside k_step
+    if tr.req_rows_dev is not None:
+        # device-side exchange: the unique rows this rank requested (exact, counted on the device).  Each is fetched once
+        # (fetch transport) and its gradient row is read once by its owner; by symmetry an owner reads as many remote
+        # gradient rows as a requester has remote unique rows (items hash uniformly over the owners)
+        uniq = (int(tr.req_rows_dev.item()) - q0) / K
+        rowb = model.engine.ld * 4
+        pulled += (0 if tr._pull else uniq * rowb * remote) + uniq * rowb * remote
     model.engine.check_flags()
     out = dict(ms=ms, t0=t0, t1=t1, launches=launches, losses=losses, sent=sent, pulled=pulled, e2e_ms=None, h2d=None)
     if want_e2e:

@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libcf_b200.so')
-ABI_VERSION = 15
+ABI_VERSION = 16
 
 # enums of cf_b200.h
 MODEL_BPR, MODEL_CML, MODEL_GBPR, MODEL_WRMF = 0, 1, 2, 3
@@ -46,6 +46,19 @@ class ApplyArgs(C.Structure):
         ('optimizer', C.c_int32), ('lr', C.c_float), ('clip_norm', C.c_float),
         ('meta', _p), ('slot', _p), ('slot_row', _p), ('staging', _p), ('staging_rows', C.c_int64), ('counters', _p),
         ('seg_grads', _p * MAX_PEERS), ('seg_start', C.c_int64 * (MAX_PEERS + 1)), ('n_segs', C.c_int32), ('first_seg', C.c_int32),
+    ]
+
+
+class ExchangeArgs(C.Structure):
+    _fields_ = [
+        ('n_ranks', C.c_int32), ('rank', C.c_int32), ('n_items_global', C.c_int64), ('cap', C.c_int64),
+        ('pairs', _p), ('negs', _p), ('B', C.c_int32), ('W', C.c_int32),
+        ('slot_of', _p), ('slot_pairs', _p), ('slot_negs', _p), ('slot_pos', _p),
+        ('counts', _p * MAX_PEERS), ('req', _p * MAX_PEERS), ('grads', _p * MAX_PEERS), ('tables', _p * MAX_PEERS),
+        ('fetched', _p), ('d', C.c_int32), ('ld', C.c_int32),
+        ('table', _p), ('acc', _p), ('n_rows', C.c_int64), ('model', C.c_int32), ('optimizer', C.c_int32),
+        ('lr', C.c_float), ('clip_norm', C.c_float),
+        ('meta', _p), ('slot', _p), ('slot_row', _p), ('staging', _p), ('staging_rows', C.c_int64), ('segs', _p), ('counters', _p),
     ]
 
 
@@ -99,6 +112,9 @@ _SIGNATURES = {
     'cf_step_staging_rows': (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     'cf_step_launches_per_batch': (C.c_int32, []),
     'cf_apply_rows': (C.c_int, [C.POINTER(ApplyArgs), _p]),
+    'cf_exchange_route': (C.c_int, [C.POINTER(ExchangeArgs), _p]),
+    'cf_exchange_prepare': (C.c_int, [C.POINTER(ExchangeArgs), _p]),
+    'cf_exchange_apply': (C.c_int, [C.POINTER(ExchangeArgs), _p]),
     'cf_clip_rows': (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, _p]),
     'cf_predict_pairs': (C.c_int, [_p, _p, _p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _p, C.c_int64, _p, _p, _p]),
     'cf_rating_metrics': (C.c_int, [_p, C.c_int32, _p, C.c_int64, C.c_double, C.c_double, _p, _p]),

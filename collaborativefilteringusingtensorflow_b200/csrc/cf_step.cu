@@ -144,6 +144,8 @@ step_kernel_t pick_kernel(int model, int nvec, int* lpg, bool ext) {
 }  // namespace
 
 
+cfstep::step_kernel_t cf_pick_apply_kernel(int nvec) { return pick_apply(nvec); }   // used by cf_exchange.cu
+
 extern "C" int64_t cf_step_staging_rows(int32_t model, int32_t B, int32_t W, int32_t G) {
   const int64_t R = (model == CF_MODEL_WRMF) ? 2 : 2 + (int64_t)W + G;
   return (int64_t)B * R;  // slot id = occurrence index of a duplicated row's second occurrence

@@ -141,11 +141,20 @@ def item_shard_rows(n_items_global, world, rank):
 class DistributedTrainer(object):
     """Row-sharded BPRMF / CML training over ``world`` GPUs.  ``model`` is a model object built with
     n_users = this rank's users and n_items = this rank's item-shard rows; ``sampler`` samples this rank's CSR (columns =
-    GLOBAL item ids)."""
+    GLOBAL item ids).
+
+    ``item_transport``:
+      'fetch' / 'peer' / 'auto'  the DEVICE-SIDE exchange (csrc/cf_exchange.cu): hand-written kernels over CUDA-IPC peer
+               memory; nothing returns to the host, NCCL only provides the two barriers of a minibatch.  'fetch' gathers
+               every requested row ONCE into a local buffer (right when minibatches repeat items: configs[1]); 'peer' lets
+               the fused step kernel read item rows from their owners per occurrence (right when they barely repeat:
+               configs[4]); 'auto' measures the repeat ratio of the first minibatch and picks (same answer on every rank).
+      'nccl'   the first version, kept as the portable baseline: torch-op plan + three NCCL all-to-alls (ids, rows,
+               gradients).  It is also what 'auto' falls back to, with a warning, when peer memory cannot be mapped."""
 
     def __init__(self, model, sampler, n_items_global, world, rank, group=None, item_transport='nccl'):
-        if item_transport not in ('nccl', 'peer', 'auto'):
-            raise ValueError("item_transport must be 'nccl', 'peer' or 'auto'")
+        if item_transport not in ('nccl', 'peer', 'fetch', 'auto'):
+            raise ValueError("item_transport must be 'nccl', 'peer', 'fetch' or 'auto'")
         self.torch = _lib.require_cuda()
         self.lib = _lib.lib()
         self.model, self.eng, self.sampler = model, model.engine, sampler
@@ -156,42 +165,41 @@ class DistributedTrainer(object):
         if self.eng.n_items != item_shard_rows(n_items_global, world, rank):
             raise ValueError('model.n_items must be the item-shard size %d' % item_shard_rows(n_items_global, world, rank))
         self.ex = ItemExchange(world, rank, group)
-        # the collective-free half of the plan of minibatch k+1 (dedupe, grouping by owner) runs on a side stream while
-        # minibatch k computes and exchanges rows
+        # the routing (dedupe + grouping by owner) of minibatch k+1 runs on a side stream while minibatch k computes
         self.side = self.torch.cuda.Stream(device=self.eng.device)
         self._keep = []
         self._ows = None
         self._ows_rows = 0
         self.launches = 0
-        self.bytes_sent = 0
-        self.bytes_pulled = 0         # peer-pull mode: item-row bytes the fused kernel read (local + over NVLink)
+        self.bytes_sent = 0           # payload that went through NCCL ('nccl' transport)
+        self.bytes_pulled = 0         # payload read from peer memory by our kernels: an upper bound counted on the host ...
+        self.req_rows_dev = None      # ... and the exact number of unique rows requested so far (device scalar, int64)
+        self.occurrences = 0
         self.step_events = None       # set to [] to collect one CUDA event per minibatch of step()
         self.phase_ms = None          # set to {} to collect per-phase CUDA-event times (synchronises every phase)
         self.item_transport = item_transport
         self.peer_ptrs = None         # device pointers of every rank's item shard (this rank's own included)
-        self._gbuf, self.peer_gbuf = None, None
-        self._peer_bases = []
+        self._opened = {}             # IPC handle bytes -> mapped base (an allocation is mapped once per process)
         self._pull = False
-        if item_transport != 'nccl':
-            try:
-                self._map_peer_shards()
-                n_neg = getattr(sampler, 'n_neg', None)
-                if n_neg is not None:     # otherwise the gradient buffer is shared on the first minibatch
-                    self._grad_buffer(int(sampler.batch_size) * (1 + int(n_neg)))
-            except PeerMappingError as e:
-                if item_transport == 'peer':
-                    raise
-                import warnings
-                warnings.warn('peer memory is not available (%s): item rows and gradients travel through NCCL' % e)
-                self.close()
-                self._gbuf, self._pull = None, False
+        self._dev = None              # buffers of the device-side exchange (allocated on the first minibatch)
+        self._k = 0
         self._bar = None              # preallocated 1-element tensor of the named cross-GPU barrier
+        self.device_side = item_transport != 'nccl'
+        if self.device_side:
+            if self.world > _lib.MAX_PEERS:
+                raise ValueError('the device-side exchange supports up to %d GPUs on one node' % _lib.MAX_PEERS)
+            self._pull = {'peer': True, 'fetch': False, 'auto': None}[item_transport]
+            n_neg = getattr(sampler, 'n_neg', None)
+            if n_neg is not None:     # otherwise the buffers are shared on the first minibatch
+                self._setup_or_fall_back(int(sampler.batch_size), int(n_neg))
 
+    # ------------------------------------------------------------------ plumbing
     def _barrier(self, why):
         """Named cross-GPU barrier ON THE COMPUTE STREAM: a 1-element NCCL all_reduce enqueued on the current stream
         completes only after every rank has enqueued it, i.e. after everything each rank enqueued before it.  The peer
-        transports rely on that order (remote NVLink reads of V / Gbuf against the owners' applies and zeroing), so the
-        process group must be NCCL -- gloo would synchronise the HOSTS and not order the streams."""
+        transports rely on that order (remote NVLink reads of mailboxes / item rows / gradient rows against the owners'
+        applies and the requesters' zeroing), so the process group must be NCCL -- gloo would synchronise the HOSTS and
+        not order the streams."""
         if self.world == 1:
             return
         dist = self.ex.dist
@@ -200,13 +208,6 @@ class DistributedTrainer(object):
         if self._bar is None:
             self._bar = self.torch.zeros(1, device=self.eng.device)
         dist.all_reduce(self._bar, group=self.ex.group)
-
-    def _map_peer_shards(self):
-        """Maps every peer's item shard into this process."""
-        if self.world > _lib.MAX_PEERS:
-            raise ValueError('peer pull supports up to %d GPUs on one node' % _lib.MAX_PEERS)
-        self._pull = True if self.item_transport == 'peer' else None    # 'auto': decided on the first minibatch
-        self.peer_ptrs = self._share(self.eng.V)
 
     def _share(self, t):
         """Exchanges CUDA IPC handles of tensor ``t`` (one per rank) and maps the peers' tensors into this process;
@@ -231,52 +232,125 @@ class DistributedTrainer(object):
         every = torch.empty(self.world * 72, dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(every, mine, group=self.ex.group)
         every = every.view(self.world, 72).cpu().numpy()
-        ptrs, opened = [], []
+        ptrs = []
         for r in range(self.world):
             if r == self.rank:
                 ptrs.append(t.data_ptr())
                 continue
             if err is not None:
                 continue
-            h = (C.c_ubyte * 64)(*every[r, :64].tolist())
-            base = C.c_void_p(0)
-            try:
-                _lib.check(self.lib.cf_ipc_open(C.addressof(h), C.byref(base)), 'cf_ipc_open')
-            except RuntimeError as e:
-                err = e
-                continue
-            opened.append(base.value)
-            ptrs.append(base.value + int.from_bytes(bytes(every[r, 64:72].tolist()), 'little'))
+            key = (r, bytes(every[r, :64].tolist()))
+            base = self._opened.get(key)
+            if base is None:
+                h = (C.c_ubyte * 64)(*every[r, :64].tolist())
+                b = C.c_void_p(0)
+                try:
+                    _lib.check(self.lib.cf_ipc_open(C.addressof(h), C.byref(b)), 'cf_ipc_open')
+                except RuntimeError as e:
+                    err = e
+                    continue
+                base = self._opened[key] = b.value
+            ptrs.append(base + int.from_bytes(bytes(every[r, 64:72].tolist()), 'little'))
         ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=dev)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.ex.group)
         if int(ok.item()) == 0:
-            for b in opened:
-                self.lib.cf_ipc_close(b)
+            self.close()
             raise PeerMappingError(str(err) if err is not None else 'another rank could not map a peer buffer')
-        self._peer_bases.extend(opened)
         return ptrs
 
-    def _grad_buffer(self, rows):
-        """The persistent, IPC-shared buffer of this rank's item-row gradients (owner-pull mode): sized once for the
-        largest possible minibatch (one row per item occurrence).  Collective on first use."""
-        if self._gbuf is None:
-            self._gbuf = self.torch.zeros(rows, self.eng.ld, device=self.eng.device)
-            self.peer_gbuf = self._share(self._gbuf)
-        if rows > self._gbuf.shape[0]:
-            raise ValueError('minibatch larger than the first one (%d > %d item occurrences)' % (rows, self._gbuf.shape[0]))
-        return self._gbuf
-
     def close(self):
-        """Unmaps the peers' shards (call on every rank before the tables are freed)."""
-        for b in self._peer_bases:
+        """Unmaps the peers' buffers (call on every rank before the tables are freed)."""
+        for b in self._opened.values():
             self.lib.cf_ipc_close(b)
-        self._peer_bases, self.peer_ptrs, self.peer_gbuf = [], None, None
+        self._opened, self.peer_ptrs = {}, None
+        if self._dev is not None:
+            self._dev = None
 
-    def _decide_transport(self, plan, n_occ):
-        """'auto': pull when the minibatches of all ranks together repeat items so rarely that one row per occurrence
-        over NVLink is cheaper than gather + all_to_all + scatter of one row per unique id (same answer on every rank)."""
+    def _setup_or_fall_back(self, B, W):
+        try:
+            self._setup_device_exchange(B, W)
+        except PeerMappingError as e:
+            if self.item_transport != 'auto':
+                raise
+            import warnings
+            warnings.warn('peer memory is not available (%s): item rows and gradients travel through NCCL' % e)
+            self.close()
+            self.device_side, self._pull, self._dev = False, False, None
+
+    def _setup_device_exchange(self, B, W):
+        """Allocates and IPC-shares the buffers of the device-side exchange, sized once for minibatches of B pairs with W
+        negatives.  Collective."""
+        torch, eng, P = self.torch, self.eng, self.world
+        dev = eng.device
+        occ = B * (1 + W)
+        L = (self.n_items_global + P - 1) // P
+        cap = min(occ, L)
+        slots = min(occ, self.n_items_global)
+        pad = lambda n: (n + 63) // 64 * 64
+        # ONE allocation holds everything the peers read besides the item shard: two mailboxes (minibatch parity) of
+        # [counts int32[64] | req int32[P, cap]] and the compact gradient buffer [slots, ld] (float32)
+        mail = 64 + pad(P * cap)
+        comm = torch.zeros(2 * mail + slots * eng.ld, dtype=torch.int32, device=dev)
+        d = dict(B=B, W=W, L=L, cap=cap, slots=slots, comm=comm, mail=mail)
+        d['gbuf'] = comm[2 * mail:].view(torch.float32).view(slots, eng.ld)
+        d['slot_of'] = torch.full((P * L,), -1, dtype=torch.int32, device=dev)
+        d['fetched'] = None            # allocated when the fetch transport is chosen
+        d['slot_pairs'] = [torch.zeros(B, 2, dtype=torch.int32, device=dev) for _ in range(2)]
+        d['slot_negs'] = [torch.zeros(B, W, dtype=torch.int32, device=dev) for _ in range(2)]
+        d['slot_pos'] = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(2)]
+        srows = min(P * cap, 2 * occ + 1024)       # expected receipts of an owner: occ (items hash uniformly over owners)
+        d['srows'] = srows
+        d['meta'] = torch.zeros(eng.n_items, dtype=torch.int32, device=dev)
+        d['slot'] = torch.zeros(eng.n_items, dtype=torch.int32, device=dev)
+        d['slot_row'] = torch.full((srows,), -1, dtype=torch.int32, device=dev)
+        d['staging'] = torch.zeros(srows, eng.ld + 4, device=dev)
+        d['segs'] = torch.zeros(4 * _lib.MAX_PEERS + 4, dtype=torch.int64, device=dev)
+        d['routed'] = [None, None]
+        comm_ptrs = self._share(comm)
+        self.peer_ptrs = self._share(eng.V)
+        d['comm_ptrs'] = comm_ptrs
+        self.req_rows_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._dev = d
+
+    def _xargs(self, par, pairs=None, negs=None):
+        d, eng, P = self._dev, self.eng, self.world
+        a = _lib.ExchangeArgs()
+        a.n_ranks, a.rank, a.n_items_global, a.cap = P, self.rank, self.n_items_global, d['cap']
+        a.pairs, a.negs, a.B, a.W = _lib.ptr(pairs), _lib.ptr(negs), d['B'], d['W']
+        a.slot_of = _lib.ptr(d['slot_of'])
+        a.slot_pairs, a.slot_negs, a.slot_pos = _lib.ptr(d['slot_pairs'][par]), _lib.ptr(d['slot_negs'][par]), _lib.ptr(d['slot_pos'][par])
+        for r in range(P):
+            base = d['comm_ptrs'][r]
+            a.counts[r] = base + 4 * par * d['mail']
+            a.req[r] = base + 4 * (par * d['mail'] + 64)
+            a.grads[r] = base + 4 * 2 * d['mail']
+            a.tables[r] = self.peer_ptrs[r]
+        a.fetched = _lib.ptr(d['fetched'])
+        a.d, a.ld = eng.d, eng.ld
+        a.table, a.acc, a.n_rows = _lib.ptr(eng.V), _lib.ptr(eng.accV), eng.n_items
+        a.model, a.optimizer = eng.model_id, 0 if eng.optimizer == 'adagrad' else 1
+        a.lr, a.clip_norm = eng.hyper['lr'], eng.hyper['clip_norm']
+        a.meta, a.slot, a.slot_row = _lib.ptr(d['meta']), _lib.ptr(d['slot']), _lib.ptr(d['slot_row'])
+        a.staging, a.staging_rows, a.segs = _lib.ptr(d['staging']), d['srows'], _lib.ptr(d['segs'])
+        a.counters = _lib.ptr(eng.counters)
+        return a
+
+    def _route(self, pairs, negs, par):
+        """Dedupe + routing of one minibatch on the CURRENT stream (fills mailbox ``par`` and the slot arrays ``par``)."""
         torch = self.torch
-        t = torch.tensor([float(plan.n_req), float(n_occ)], dtype=torch.float64, device=self.eng.device)
+        lp, ln = pairs.to(torch.int32).contiguous(), negs.to(torch.int32).contiguous()
+        a = self._xargs(par, lp, ln)
+        _lib.check(self.lib.cf_exchange_route(a, torch.cuda.current_stream(self.eng.device).cuda_stream), 'cf_exchange_route')
+        self._dev['routed'][par] = (lp, ln)       # keep the (possibly converted) index arrays alive until the step has run
+        self.launches += 2
+
+    def _decide_transport(self, par):
+        """'auto': pull when the minibatches of all ranks together repeat items so rarely that one row per occurrence
+        over NVLink is cheaper than gathering one row per unique id first (same answer on every rank).  One host
+        synchronisation, on the first minibatch only."""
+        torch, d = self.torch, self._dev
+        counts = d['comm'][par * d['mail']: par * d['mail'] + self.world]
+        t = torch.stack([counts.sum().double(), torch.tensor(float(d['B'] * (1 + d['W'])), dtype=torch.float64, device=counts.device)])
         if self.world > 1:
             self.ex.dist.all_reduce(t, group=self.ex.group)
         uniq, occ = t.tolist()
@@ -311,108 +385,137 @@ class DistributedTrainer(object):
         p = self.ex.plan_local(items, self.n_items_global)
         return p if local_only else self.ex.plan_exchange(p)
 
-    def step_chunk(self, pairs, negs, batch_size, want_loss=True, plan=None):
-        """One minibatch (rows == batch_size) of the sharded step on explicit local batches."""
+    def _step_args(self, B, W, want_loss):
         torch, eng = self.torch, self.eng
-        B = int(batch_size)
-        ev = self._tick('', None)
-        if int(pairs.shape[0]) != B:
-            raise ValueError('the sharded step takes one minibatch per call')
-        peer = self.peer_ptrs is not None
-        if plan is None:
-            plan = self.make_plan(pairs, negs, local_only=True)
-        if getattr(plan, 'recv_local_rows', None) is None:
-            # In peer mode this exchange is also the barrier between the owners' applies (and gradient reads) of the
-            # previous minibatch and this minibatch's remote reads / buffer reuse: it completes here only after every
-            # rank has enqueued it, i.e. after its previous apply.
-            plan = self.ex.plan_exchange(plan, all_counts=peer)
-        elif peer:
-            raise ValueError('peer transport needs the plan exchanged inside step_chunk (pass a plan_local plan)')
-        ev = self._tick('plan (dedupe + route ids)', ev)
-        pull = self.peer_ptrs is not None and (self._pull if self._pull is not None
-                                               else self._decide_transport(plan, pairs.shape[0] * (1 + negs.shape[1])))
         a = _lib.StepArgs()
-        if peer:   # gradients stay in this rank's shared buffer; the owners read them in place
-            Gbuf = self._grad_buffer(int(pairs.shape[0]) * (1 + int(negs.shape[1])))[:plan.n_req]
-            Gbuf.zero_()
-        if pull:
-            lp = pairs.to(torch.int32).contiguous()                                          # GLOBAL item ids
-            ln = negs.to(torch.int32).contiguous()
-            gp, gn = plan.occ_local[:, 0].contiguous(), plan.occ_local[:, 1:].contiguous()
-            a.V, a.n_items = _lib.ptr(eng.V), self.n_items_global
-            for r, q in enumerate(self.peer_ptrs):
-                a.peerV[r] = q
-            a.n_peers, a.gslot_pos, a.gslot_neg = self.world, _lib.ptr(gp), _lib.ptr(gn)
-        else:
-            Vbuf = self.ex.fetch(plan, eng.V)                                                # [n_req, ld]
-            ev = self._tick('fetch rows (gather + all_to_all)', ev)
-            if not peer:
-                Gbuf = torch.zeros_like(Vbuf)
-            lp = torch.stack([pairs[:, 0].to(torch.int32), plan.occ_local[:, 0]], dim=1).contiguous()
-            ln = plan.occ_local[:, 1:].contiguous()
-            a.V, a.n_items = _lib.ptr(Vbuf), plan.n_req
         a.U, a.accU, a.accV = _lib.ptr(eng.U), _lib.ptr(eng.accU), _lib.ptr(eng.accV)
         a.n_users, a.d, a.ld = eng.n_users, eng.d, eng.ld
-        a.pairs, a.negs = _lib.ptr(lp), _lib.ptr(ln)
-        a.B, a.W, a.G, a.n_batches = B, int(negs.shape[1]), 0, 1
+        a.B, a.W, a.G, a.n_batches = B, W, 0, 1
         a.model, a.optimizer, a.update = eng.model_id, 0 if eng.optimizer == 'adagrad' else 1, _lib.UPDATE_SYNC
         h = eng.hyper
         a.use_rank_weight = int(bool(h['use_rank_weight']))
         a.lr, a.reg, a.margin, a.clip_norm, a.rho, a.weight = h['lr'], h['reg'], h['margin'], h['clip_norm'], h['rho'], h['weight']
-        ws = eng._workspace(B, int(negs.shape[1]), 0)
+        ws = eng._workspace(B, W, 0)
         a.metaU, a.metaV = _lib.ptr(ws['metaU']), _lib.ptr(ws['metaV'])
         a.slotU, a.slotV, a.slot_row = _lib.ptr(ws['slotU']), _lib.ptr(ws['slotV']), _lib.ptr(ws['slot_row'])
         a.staging, a.staging_rows = _lib.ptr(ws['staging']), ws['staging'].shape[0]
         a.counters = _lib.ptr(eng.counters)
         loss = torch.zeros(1, dtype=torch.float64, device=eng.device) if want_loss else None
         a.loss = _lib.ptr(loss)
-        a.gradV, a.rank_items = _lib.ptr(Gbuf), self.n_items_global
+        a.rank_items = self.n_items_global
+        return a, loss
+
+    # ------------------------------------------------------------------ one minibatch
+    def step_chunk(self, pairs, negs, batch_size, want_loss=True, plan=None, routed=False, after_prepare=None):
+        """One minibatch (rows == batch_size) of the sharded step on explicit local batches."""
+        B = int(batch_size)
+        if int(pairs.shape[0]) != B:
+            raise ValueError('the sharded step takes one minibatch per call')
+        if self.device_side and self._dev is None:
+            self._setup_or_fall_back(B, int(negs.shape[1]))
+        if self.device_side:
+            return self._step_chunk_device(pairs, negs, B, want_loss, routed, after_prepare)
+        return self._step_chunk_nccl(pairs, negs, B, want_loss, plan)
+
+    def _step_chunk_device(self, pairs, negs, B, want_loss, routed, after_prepare):
+        torch, eng, d = self.torch, self.eng, self._dev
+        W = int(negs.shape[1])
+        if B != d['B'] or W != d['W']:
+            raise ValueError('minibatch shape (%d, %d) differs from the first one (%d, %d)' % (B, W, d['B'], d['W']))
+        par = self._k & 1
         stream = torch.cuda.current_stream(eng.device).cuda_stream
-        ev = self._tick('prep (remap ids, zero grads)', ev)
+        ev = self._tick('', None)
+        if not routed:
+            self._route(pairs, negs, par)
+        lp, ln = d['routed'][par]
+        ev = self._tick('route (dedupe + group by owner: k_route_assign, k_route_fill)', ev)
+        pull = self._pull if self._pull is not None else self._decide_transport(par)
+        if not pull and d['fetched'] is None:
+            d['fetched'] = torch.empty(d['slots'], eng.ld, device=eng.device)
+        self.req_rows_dev += d['comm'][par * d['mail']: par * d['mail'] + self.world].sum()
+        # barrier 1: every mailbox is complete, and every rank is past the owner-side apply of the previous minibatch (so
+        # item rows may be read remotely and the gradient buffer may be zeroed)
+        self._barrier('mailboxes complete')
+        ev = self._tick('barrier 1', ev)
+        x = self._xargs(par)
+        if pull:
+            x.fetched = None
+        _lib.check(self.lib.cf_exchange_prepare(x, stream), 'cf_exchange_prepare')
+        ev = self._tick('prepare (fetch rows over NVLink + zero grads + owner-side count: k_owner_segs, k_exchange_prepare)', ev)
+        if after_prepare is not None:
+            after_prepare()                      # the dedupe table is at rest again: the next minibatch may be routed
+        a, loss = self._step_args(B, W, want_loss)
+        if pull:    # item rows straight from their owners' shards inside the fused kernel (global ids)
+            a.V, a.n_items = _lib.ptr(eng.V), self.n_items_global
+            a.pairs, a.negs = _lib.ptr(lp), _lib.ptr(ln)
+            for r, q in enumerate(self.peer_ptrs):
+                a.peerV[r] = q
+            a.n_peers, a.gslot_pos, a.gslot_neg = self.world, _lib.ptr(d['slot_pos'][par]), _lib.ptr(d['slot_negs'][par])
+        else:       # the fetched copy of every requested row, ids = rows of the compact buffers
+            a.V, a.n_items = _lib.ptr(d['fetched']), d['slots']
+            a.pairs, a.negs = _lib.ptr(d['slot_pairs'][par]), _lib.ptr(d['slot_negs'][par])
+        a.gradV = _lib.ptr(d['gbuf'])
         _lib.check(self.lib.cf_train_steps(a, stream), 'cf_train_steps')
         ev = self._tick('k_count + k_step + k_apply_staged', ev)
-        if peer:
-            self._barrier('gradient buffers complete')   # every rank is past its step kernel
-            ev = self._tick('barrier (gradient buffers complete)', ev)
-            recv, n = None, int(plan.recv_local_rows.numel())
-        else:
-            recv = self.ex.push(plan, Gbuf)
-            ev = self._tick('push grads (all_to_all)', ev)                                                  # [n_recv, ld]
-            n = int(recv.shape[0])
-        if n:
-            ows = self._owner_workspace(n)
-            ap = _lib.ApplyArgs()
-            ap.table, ap.acc, ap.n_rows, ap.d, ap.ld = _lib.ptr(eng.V), _lib.ptr(eng.accV), eng.n_items, eng.d, eng.ld
-            ap.rows, ap.grads, ap.n, ap.ldg = _lib.ptr(plan.recv_local_rows), _lib.ptr(recv), n, eng.ld
-            if peer:   # read the gradient rows in place from the requesters' buffers (NVLink), requester by requester
-                ap.n_segs, start = self.world, 0
-                for q in range(self.world):
-                    ap.seg_start[q] = start
-                    ap.seg_grads[q] = self.peer_gbuf[q] + plan.peer_offsets[q] * eng.ld * 4
-                    start += plan.recv_counts[q]
-                ap.seg_start[self.world] = start
-                ap.first_seg = (self.rank + 1) % self.world     # stagger the owners over the requesters (no incast)
-            ap.model, ap.optimizer, ap.lr, ap.clip_norm = eng.model_id, a.optimizer, h['lr'], h['clip_norm']
-            ap.meta, ap.slot, ap.slot_row = _lib.ptr(ows['meta']), _lib.ptr(ows['slot']), _lib.ptr(ows['slot_row'])
-            ap.staging, ap.staging_rows, ap.counters = _lib.ptr(ows['staging']), ows['staging'].shape[0], _lib.ptr(eng.counters)
-            _lib.check(self.lib.cf_apply_rows(ap, stream), 'cf_apply_rows')
+        self._barrier('gradient buffers complete')          # every rank is past its step kernel
+        ev = self._tick('barrier 2', ev)
+        _lib.check(self.lib.cf_exchange_apply(x, stream), 'cf_exchange_apply')
         if eng._needs_full_clip:
             # cml.py:119-129 clips BOTH whole tables after every step; after the first such clip every row has norm <= clip
             # and the touched-row clip fused into the applies is the same thing (DESIGN.md section 5).  Like
             # engine.train_batches: step first, THEN clip -- the first minibatch's gradients see the unclipped init.
             eng._full_clip(stream)
+        ev = self._tick('owner apply (k_owner_scatter + k_apply_staged)', ev)
+        self._k += 1
+        self.launches += 2 + 3 + 2
+        self.occurrences += B * (1 + W)
+        self.bytes_pulled += (B * (1 + W) if pull else 0) * eng.ld * 4
+        return loss
+
+    def _step_chunk_nccl(self, pairs, negs, B, want_loss, plan):
+        torch, eng = self.torch, self.eng
+        ev = self._tick('', None)
+        if plan is None:
+            plan = self.make_plan(pairs, negs, local_only=True)
+        if getattr(plan, 'recv_local_rows', None) is None:
+            plan = self.ex.plan_exchange(plan)
+        ev = self._tick('plan (dedupe + route ids)', ev)
+        Vbuf = self.ex.fetch(plan, eng.V)                                                # [n_req, ld]
+        ev = self._tick('fetch rows (gather + all_to_all)', ev)
+        Gbuf = torch.zeros_like(Vbuf)
+        lp = torch.stack([pairs[:, 0].to(torch.int32), plan.occ_local[:, 0]], dim=1).contiguous()
+        ln = plan.occ_local[:, 1:].contiguous()
+        a, loss = self._step_args(B, int(negs.shape[1]), want_loss)
+        a.V, a.n_items = _lib.ptr(Vbuf), plan.n_req
+        a.pairs, a.negs = _lib.ptr(lp), _lib.ptr(ln)
+        a.gradV = _lib.ptr(Gbuf)
+        stream = torch.cuda.current_stream(eng.device).cuda_stream
+        ev = self._tick('prep (remap ids, zero grads)', ev)
+        _lib.check(self.lib.cf_train_steps(a, stream), 'cf_train_steps')
+        ev = self._tick('k_count + k_step + k_apply_staged', ev)
+        recv = self.ex.push(plan, Gbuf)
+        ev = self._tick('push grads (all_to_all)', ev)                                                  # [n_recv, ld]
+        n = int(recv.shape[0])
+        if n:
+            ows = self._owner_workspace(n)
+            ap = _lib.ApplyArgs()
+            ap.table, ap.acc, ap.n_rows, ap.d, ap.ld = _lib.ptr(eng.V), _lib.ptr(eng.accV), eng.n_items, eng.d, eng.ld
+            ap.rows, ap.grads, ap.n, ap.ldg = _lib.ptr(plan.recv_local_rows), _lib.ptr(recv), n, eng.ld
+            ap.model, ap.optimizer, ap.lr, ap.clip_norm = eng.model_id, a.optimizer, eng.hyper['lr'], eng.hyper['clip_norm']
+            ap.meta, ap.slot, ap.slot_row = _lib.ptr(ows['meta']), _lib.ptr(ows['slot']), _lib.ptr(ows['slot_row'])
+            ap.staging, ap.staging_rows, ap.counters = _lib.ptr(ows['staging']), ows['staging'].shape[0], _lib.ptr(eng.counters)
+            _lib.check(self.lib.cf_apply_rows(ap, stream), 'cf_apply_rows')
+        if eng._needs_full_clip:   # step first, then the one-time whole-table clip (cml.py:119-129; DESIGN.md section 5)
+            eng._full_clip(stream)
         ev = self._tick('owner apply (cf_apply_rows)', ev)
         self.launches += 3 + 3
-        self.bytes_sent += ((0 if pull else plan.n_req) + (0 if peer else n)) * eng.ld * 4 + plan.n_req * 4
-        if peer:
-            self.bytes_pulled += n * eng.ld * 4
-        if pull:
-            self.bytes_pulled += int(pairs.shape[0]) * (1 + int(negs.shape[1])) * eng.ld * 4
+        self.occurrences += B * (1 + int(negs.shape[1]))
+        self.bytes_sent += (plan.n_req + n) * eng.ld * 4 + plan.n_req * 4
         return loss
 
     def step(self, n_minibatches=1, want_loss=True):
-        """Sample + run n minibatches; returns their losses (CUDA float64).  The plan (dedupe + id routing) of minibatch
-        k+1 is built on a side stream while minibatch k computes and exchanges rows."""
+        """Sample + run n minibatches; returns their losses (CUDA float64).  The routing of minibatch k+1 (dedupe + grouping
+        by owner) runs on a side stream while minibatch k computes."""
         torch = self.torch
         B = self.sampler.batch_size
         chunk = self.sampler.next_chunk(n_minibatches)
@@ -422,6 +525,37 @@ class DistributedTrainer(object):
         def batch(k):
             return chunk[0][k * B:(k + 1) * B], chunk[1][k * B:(k + 1) * B]
 
+        out = []
+        if self.device_side and self._dev is None:
+            self._setup_or_fall_back(B, int(chunk[1].shape[1]))
+        if self.device_side:
+            ev_routed = [None, None]
+
+            def route_ahead(k):
+                # on the side stream, after prepare(k - 1) has returned the dedupe table to rest
+                ev = torch.cuda.Event()
+                ev.record(main)
+                self.side.wait_event(ev)
+                with torch.cuda.stream(self.side):
+                    self._route(*batch(k), (self._k + 1) & 1)
+                    done = torch.cuda.Event()
+                    done.record(self.side)
+                ev_routed[(self._k + 1) & 1] = done
+
+            for k in range(n_minibatches):
+                p, n = batch(k)
+                routed = False
+                if overlap and k > 0:
+                    main.wait_event(ev_routed[self._k & 1])
+                    routed = True
+                nxt = (lambda kk=k + 1: route_ahead(kk)) if overlap and k + 1 < n_minibatches else None
+                out.append(self.step_chunk(p, n, B, want_loss, routed=routed, after_prepare=nxt))
+                if self.step_events is not None:               # per-minibatch device timeline (no synchronisation)
+                    ev = torch.cuda.Event(enable_timing=True)
+                    ev.record(main)
+                    self.step_events.append(ev)
+            return torch.cat(out) if want_loss else None
+
         sampled = torch.cuda.Event()
         sampled.record(main)
         self.side.wait_event(sampled)      # the side stream only depends on the sampled indices, not on the steps
@@ -430,7 +564,6 @@ class DistributedTrainer(object):
             with torch.cuda.stream(self.side):
                 return self.make_plan(*batch(k), local_only=True)
 
-        out = []
         nxt = plan_async(0) if overlap else None
         for k in range(n_minibatches):
             plan = None

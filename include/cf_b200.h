@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CF_ABI_VERSION 15
+#define CF_ABI_VERSION 16
 
 /* models */
 enum { CF_MODEL_BPR = 0, CF_MODEL_CML = 1, CF_MODEL_GBPR = 2, CF_MODEL_WRMF = 3 };
@@ -176,6 +176,63 @@ int cf_apply_rows(const cf_apply_args* args, void* stream);
 int cf_ipc_export(const void* devptr, void* handle64, int64_t* offset_bytes);
 int cf_ipc_open(const void* handle64, void** base);
 int cf_ipc_close(void* base);
+
+/* Device-side item exchange of the sharded training step (csrc/cf_exchange.cu): nothing returns to the host and no payload
+ * goes through NCCL.  Every rank owns a MAILBOX (counts int32[CF_MAX_PEERS] + req int32[n_ranks, cap]: the unique local rows
+ * it requests from every owner), a compact gradient buffer grads[slots, ld] and its item shard; it maps its peers' with
+ * cf_ipc_open and passes all of them here (its own at index `rank`).  Per minibatch, with the caller's two cross-GPU barriers
+ * (any collective on `stream` that completes only after every rank has enqueued it, e.g. a 1-element NCCL all-reduce):
+ *   cf_exchange_route   (dedupe + routing of this rank's item ids: fills its mailbox and slot_pairs / slot_negs / slot_pos =
+ *                        the minibatch re-indexed by rows ("slots") of the compact buffers, owner-major)
+ *   -- barrier 1 --
+ *   cf_exchange_prepare (requester: gather each requested row once from its owner into fetched[slot] when fetched != NULL,
+ *                        zero grads[slot], return slot_of to rest; owner: count the requests per row of its shard)
+ *   cf_train_steps      (exchange mode: V = fetched, pairs = slot_pairs, negs = slot_negs, gradV = grads;
+ *                        or peer-pull mode: global ids, peerV = tables, gslot_pos = slot_pos, gslot_neg = slot_negs)
+ *   -- barrier 2 --
+ *   cf_exchange_apply   (owner: gradient rows read in place from the requesters' buffers, summed per row, applied once)
+ * Replaces nothing in the reference (it is single-device, bprmf.py:131). */
+typedef struct cf_exchange_args {
+  int32_t n_ranks;
+  int32_t rank;
+  int64_t n_items_global;
+  int64_t cap;             /* entries per (requester, owner) request list: >= min(B * (1 + W), ceil(n_items_global / n_ranks)) */
+  /* requester side: this rank's minibatch (GLOBAL item ids in pairs[:, 1] / negs) */
+  const int32_t* pairs;    /* [B, 2] */
+  const int32_t* negs;     /* [B, W] */
+  int32_t B;
+  int32_t W;
+  int32_t* slot_of;        /* [n_ranks * ceil(n_items_global / n_ranks)] dedupe table, all -1 at rest (returned to rest by prepare) */
+  int32_t* slot_pairs;     /* out [B, 2]: (user, slot of the positive item) */
+  int32_t* slot_negs;      /* out [B, W] */
+  int32_t* slot_pos;       /* out [B] */
+  /* every rank's mailbox, gradient buffer and item shard */
+  int32_t* counts[CF_MAX_PEERS];      /* int32[CF_MAX_PEERS] */
+  int32_t* req[CF_MAX_PEERS];         /* int32[n_ranks, cap] */
+  float* grads[CF_MAX_PEERS];         /* float[slots, ld], slots >= min(B * (1 + W), n_items_global) */
+  const float* tables[CF_MAX_PEERS];  /* float[rows of the shard, ld] */
+  float* fetched;          /* local float[slots, ld], or NULL (peer-pull mode: the step kernel reads the shards itself) */
+  int32_t d;
+  int32_t ld;
+  /* owner side: this rank's shard and the apply rule (as cf_apply_args) */
+  float* table;
+  float* acc;
+  int64_t n_rows;
+  int32_t model;
+  int32_t optimizer;
+  float lr;
+  float clip_norm;
+  uint32_t* meta;          /* [n_rows] zero at rest */
+  int32_t* slot;           /* [n_rows] */
+  uint32_t* slot_row;      /* [staging_rows] all 0xffffffff at rest */
+  float* staging;          /* [staging_rows, ld + 4] zero at rest */
+  int64_t staging_rows;    /* >= n_ranks * cap */
+  int64_t* segs;           /* device scratch, int64[4 * CF_MAX_PEERS + 4] */
+  int32_t* counters;       /* [4] (flags in [1]) */
+} cf_exchange_args;
+int cf_exchange_route(const cf_exchange_args* args, void* stream);
+int cf_exchange_prepare(const cf_exchange_args* args, void* stream);
+int cf_exchange_apply(const cf_exchange_args* args, void* stream);
 
 /* Replicated data-parallel mode: apply a dense, already all-reduced gradient table grads[n_rows, ldg] to table[n_rows, ld]
  * (rows / n / meta / slot / staging of cf_apply_args are not used; ld == 1 applies a bias vector).  Rows whose gradient

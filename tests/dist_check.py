@@ -26,7 +26,7 @@ def main():
     from collaborativefilteringusingtensorflow_b200.sparse import DeviceCSR
     from scipy.sparse import lil_matrix
     ok = True
-    transport = sys.argv[1] if len(sys.argv) > 1 else 'nccl'    # 'nccl' | 'peer' | 'auto'
+    transport = sys.argv[1] if len(sys.argv) > 1 else 'nccl'    # 'nccl' | 'peer' | 'fetch' | 'auto'
     for kind in ('bpr', 'cml'):
         nu_l, ni, d, B, W = 500, 1203, 128, 1024, 3
         nu = nu_l * world

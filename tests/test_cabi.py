@@ -44,7 +44,7 @@ def test_struct_sizes_match_the_compiled_header(tmp_path):
     if shutil.which('gcc') is None:
         pytest.skip('no gcc')
     names = dict(cf_step_args=_lib.StepArgs, cf_apply_args=_lib.ApplyArgs, cf_als_args=_lib.AlsArgs, cf_csr=_lib.Csr,
-                 cf_svd_args=_lib.SvdArgs,
+                 cf_svd_args=_lib.SvdArgs, cf_exchange_args=_lib.ExchangeArgs,
                  cf_sample_args=_lib.SampleArgs, cf_topk_args=_lib.TopkArgs)
     last = {n: c._fields_[-1][0] for n, c in names.items()}
     src = '#include <stdio.h>\n#include <stddef.h>\n#include "cf_b200.h"\nint main(void) {\n'
@@ -74,6 +74,12 @@ def test_host_side_validation_needs_no_gpu():
     assert lib.cf_topk_exact(C.byref(t), None) < 0
     t.U, t.V, t.out_idx, t.d, t.ld, t.T, t.K, t.n_items = 16, 32, 48, 8, 8, 4, 5000, 100
     assert lib.cf_topk_exact(C.byref(t), None) < 0 and b'K must be' in lib.cf_last_error()
+    x = _lib.ExchangeArgs()
+    assert lib.cf_exchange_route(C.byref(x), None) < 0 and b'n_ranks' in lib.cf_last_error()
+    x.n_ranks, x.rank, x.n_items_global, x.cap = 2, 0, 100, 50
+    assert lib.cf_exchange_prepare(C.byref(x), None) < 0 and b'mailbox' in lib.cf_last_error()
+    x.counts[0], x.counts[1], x.req[0], x.req[1] = 16, 32, 48, 64
+    assert lib.cf_exchange_apply(C.byref(x), None) < 0 and b'owner-side' in lib.cf_last_error()
     assert lib.cf_step_staging_rows(_lib.MODEL_CML, 100, 5, 0) == 700
     assert lib.cf_step_staging_rows(_lib.MODEL_WRMF, 200, 7, 3) == 400
 
