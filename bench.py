@@ -370,7 +370,7 @@ def time_training(wl, csr, B, K, Wm, device, optimizer, update, pk):
     return model, sampler, out
 
 
-def time_e2e(model, sampler, B, K, device):
+def time_e2e(model, sampler, B, K, device, step=None, pre=None):
     """The same K minibatches through the public API from HOST buffers: every step's index arrays come from pinned host
     memory (H2D on a copy stream, double-buffered so that the copy of minibatch k+1 runs under step k) and every step's
     loss is read back into pinned host memory (async D2H, one event wait at the end).  The metric includes sampling, so
@@ -385,7 +385,11 @@ def time_e2e(model, sampler, B, K, device):
     free = [torch.cuda.Event() for _ in range(2)]
     loss_host = torch.zeros(K, dtype=torch.float64).pin_memory()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step = step or (lambda bufs_: model._train_arrays(bufs_, B))
     torch.cuda.synchronize()
+    if pre is not None:
+        pre()                                                # N > 1: barrier, so that every rank starts together
+        torch.cuda.synchronize()
     e0.record()
     copy.wait_event(e0)
     for k in range(K):
@@ -398,7 +402,7 @@ def time_e2e(model, sampler, B, K, device):
             ready[s].record(copy)
         main.wait_event(ready[s])
         sampled = sampler.next_chunk(1)                      # the sampling work of this step (metric: "incl. sampling")
-        loss_k = model._train_arrays(bufs[s], B)
+        loss_k = step(bufs[s])
         loss_host[k:k + 1].copy_(loss_k, non_blocking=True)  # D2H of the step's result
         free[s].record(main)
     e1.record()

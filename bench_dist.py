@@ -63,24 +63,17 @@ def sharded_training(B_, wl, args, rank, world, device, n_items_global, K, Wm, w
         # gradient rows as a requester has remote unique rows (items hash uniformly over the owners)
         uniq = (int(tr.req_rows_dev.item()) - q0) / K
         rowb = model.engine.ld * 4
-        pulled += (0 if tr._pull else uniq * rowb * remote) + uniq * rowb * remote
+        # (pull transport: rows in per occurrence -- counted above -- and gradient rows OUT per occurrence, the other direction)
+        pulled += (tr.bytes_pulled - p0) / K * remote if tr._pull else 2 * uniq * rowb * remote
     model.engine.check_flags()
     out = dict(ms=ms, t0=t0, t1=t1, launches=launches, losses=losses, sent=sent, pulled=pulled, e2e_ms=None, h2d=None)
     if want_e2e:
-        # e2e: pinned host index buffers -> H2D -> sharded step -> D2H loss, every step
-        host = [t.cpu().pin_memory() for t in sampler.next_chunk(K)]
-        loss_host = torch.zeros(K, dtype=torch.float64).pin_memory()
+        # e2e: pinned host index buffers -> H2D (copy stream, double-buffered) -> on-device sampling launch -> sharded step ->
+        # D2H loss, every step (bench.time_e2e, the N = 1 loop with the sharded step plugged in)
+        ms2, h2d, _ = B_.time_e2e(None, sampler, B, K, device, step=lambda bufs: tr.step_chunk(bufs[0], bufs[1], B), pre=dist.barrier)
         dist.barrier()
-        torch.cuda.synchronize()
-        e0.record()
-        for k in range(K):
-            dev = [t[k * B:(k + 1) * B].to(device, non_blocking=True) for t in host]
-            loss_host[k:k + 1].copy_(tr.step_chunk(dev[0], dev[1], B), non_blocking=True)
-        e1.record()
-        torch.cuda.synchronize()
-        dist.barrier()
-        out['e2e_ms'] = _max_over_ranks(e0.elapsed_time(e1), device)
-        out['h2d'] = sum(int(t[:B].numel()) * t.element_size() for t in host)
+        out['e2e_ms'] = _max_over_ranks(ms2, device)
+        out['h2d'] = h2d
     # per-phase CUDA-event times (synchronises after every phase, so the phases do not overlap: their sum exceeds a step)
     tr.phase_ms = {}
     tr.step(5)
@@ -112,18 +105,19 @@ def sharded_topk(B_, model, csr, n_items_global, wl, Tq, rank, world, device, pk
         dist.broadcast(t, 0)
     mask = shard_mask_csr(DeviceCSR(ptr, ind, rws, None, (Tq, n_items_global)), world, rank)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    distributed_topk(eng, q, 100, mask, world, rank, method='tensor')           # warm-up: sizes every workspace
+    distributed_topk(eng, q, 100, mask, world, rank, method='tensor', gather=False)           # warm-up: sizes every workspace
     dist.barrier()
     torch.cuda.synchronize()
     e0.record()
-    gi, gv = distributed_topk(eng, q, 100, mask, world, rank, method='tensor')
+    lo, gi, gv = distributed_topk(eng, q, 100, mask, world, rank, method='tensor', gather=False)
     e1.record()
     torch.cuda.synchronize()
     dist.barrier()
     tms = _max_over_ranks(e0.elapsed_time(e1), device)
     fl = 2.0 * n_items_global * wl['d'] * Tq
     tf = fl / (tms * 1e-3) / 1e12
-    return dict(metric='users/s full-catalog top-100 (mask train items), items sharded over %d GPUs, lists merged across ranks' % world,
+    return dict(metric='users/s full-catalog top-100 (mask train items), items sharded over %d GPUs, local lists exchanged with one '
+                       'all-to-all, every rank merges 1/N of the users' % world,
                 value=Tq / (tms * 1e-3), unit='users/s', users=Tq, n_items=n_items_global, ms=tms, tflops_aggregate=tf,
                 frac_of_tensor_peak_per_gpu=tf / world / pk['bf16'], fallback_rows_rank0=int(eng.tc_stats[0].item()))
 
@@ -136,8 +130,11 @@ def step_line(B_, wl, args, world, K, Wm, r, n_items_global, tr, pk):
     achieved = bpp * B / (ms / K * 1e-3) / 1e9            # per GPU, whole sharded step (exchange included)
     nv_bytes = r['sent'] + r['pulled']
     return dict(value=units / (ms * 1e-3), unit='triple updates/s', ms_per_step=ms / K, steps=K, gpu_launches=r['launches'],
-                item_transport=('peer (fused NVLink reads in k_step)' if tr._pull else 'nccl (all-to-all of unique rows)') +
-                               (' + owner-pull of gradient rows' if tr.peer_ptrs is not None else ' + all-to-all of gradient rows'),
+                item_transport=(('device-side exchange over peer memory: ' +
+                                 ('item rows read per occurrence inside k_step and gradients red.added into the owners\' dense tables by the same kernel (pull + push)'
+                                  if tr._pull else 'unique item rows gathered once by k_exchange_prepare (fetch) + gradient rows read in place by the owners'))
+                                if tr.device_side else
+                                'nccl (all-to-all of ids, unique rows and gradient rows)'),
                 roofline=dict(bound='hbm', kernel='whole sharded step per GPU (plan + k_count + k_step + k_apply_staged + exchange + owner apply)',
                               achieved=achieved, peak=pk['hbm'], unit='GB/s', frac=achieved / pk['hbm'], traffic=None,
                               peak_source=pk['source']),

@@ -145,6 +145,8 @@ struct XDev {
   float* my_grads;
   float* fetched;
   int32_t* slot_of;
+  float* dense;          // push variant: this owner's dense gradient table [n_rows, ld] (the peers red.add into it)
+  int32_t* touched;      //               list of the rows that were requested this minibatch; its length is segs[3P+2]
   // segs (local device memory, written by k_owner_segs):
   //   [0 .. P]          start of requester p's ids in this owner's received index space ([P] = total received)
   //   [P+1 .. 2P]       first row of this owner's segment inside requester p's compact buffers
@@ -153,20 +155,26 @@ struct XDev {
 };
 
 __global__ void k_owner_segs(const __grid_constant__ XDev X) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // the P x P request counts live in the peers' mailboxes: every thread fetches ONE of them (a single thread walking all 64
+  // is a chain of 64 NVLink round trips: 0.25 ms at 8 GPUs)
+  __shared__ long long c[CF_MAX_PEERS][CF_MAX_PEERS];
+  const int p = threadIdx.x / CF_MAX_PEERS, o = threadIdx.x % CF_MAX_PEERS;
+  if (p < X.P && o < X.P) c[p][o] = min((long long)__ldcg(X.counts[p] + o), X.cap);
+  __syncthreads();
+  if (threadIdx.x != 0) return;
   long long start = 0;
-  for (int p = 0; p < X.P; ++p) {
+  for (int q = 0; q < X.P; ++q) {
     long long gbase = 0;
-    for (int o = 0; o < X.me; ++o) gbase += min((long long)__ldcg(X.counts[p] + o), X.cap);
-    X.segs[p] = start;
-    X.segs[X.P + 1 + p] = gbase;
-    start += min((long long)__ldcg(X.counts[p] + X.me), X.cap);
+    for (int w = 0; w < X.me; ++w) gbase += c[q][w];
+    X.segs[q] = start;
+    X.segs[X.P + 1 + q] = gbase;
+    start += c[q][X.me];
   }
   X.segs[X.P] = start;
   long long mine = 0;
-  for (int o = 0; o < X.P; ++o) {
-    X.segs[2 * X.P + 1 + o] = mine;
-    mine += min((long long)__ldcg(X.counts[X.me] + o), X.cap);
+  for (int w = 0; w < X.P; ++w) {
+    X.segs[2 * X.P + 1 + w] = mine;
+    mine += c[X.me][w];
   }
   X.segs[3 * X.P + 1] = mine;
 }
@@ -212,8 +220,10 @@ __global__ void __launch_bounds__(256) k_exchange_prepare(const __grid_constant_
           if (lane < X.nvec) stcg4(dst + 4 * lane, head[u]);
           for (int v = lane + 32; v < X.nvec; v += 32) stcg4(dst + 4 * v, ldcg4(src + 4 * v));
         }
-        float* g = X.my_grads + s * X.ld;
-        for (int v = lane; v < X.nvec; v += 32) stcg4(g + 4 * v, make_float4(0.f, 0.f, 0.f, 0.f));
+        if (X.dense == nullptr) {   // the compact gradient buffer collects this minibatch's gradients from zero
+          float* g = X.my_grads + s * X.ld;
+          for (int v = lane; v < X.nvec; v += 32) stcg4(g + 4 * v, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
         if (lane == 0) X.slot_of[(long long)own[u] * X.L + rows[u]] = -1;
       }
     }
@@ -222,6 +232,36 @@ __global__ void __launch_bounds__(256) k_exchange_prepare(const __grid_constant_
     __syncthreads();
     const long long n = s_start[X.P];
     const long long stride = (long long)(gridDim.x - ga) * blockDim.x;
+    if (X.dense != nullptr) {
+      // push variant: the first request of a row puts it on the list of rows to apply (positions from a block-aggregated
+      // counter: one global atomic per block and round, not one per row)
+      __shared__ int s_n;
+      __shared__ long long s_base;
+      for (long long t0 = (long long)(blockIdx.x - ga) * blockDim.x; t0 < n; t0 += stride) {
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        const long long t = t0 + threadIdx.x;
+        long long r = -1;
+        int mine = -1;
+        if (t < n) {
+          const int p = seg_of(s_start, X.P, t);
+          r = __ldcg(X.req[p] + (long long)X.me * X.cap + (t - s_start[p]));
+          if (r < 0 || r >= X.n_rows) { atomicOr(P.counters + 1, CF_FLAG_INDEX_RANGE); r = -1; }
+        }
+        const bool first = r >= 0 && atomicAdd(P.metaU + r, 1u) == 0u;
+        const unsigned m = __ballot_sync(0xffffffffu, first);
+        int wbase = 0;
+        if (m && lane == __ffs(m) - 1) wbase = atomicAdd(&s_n, __popc(m));
+        wbase = __shfl_sync(0xffffffffu, wbase, m ? __ffs(m) - 1 : 0);
+        if (first) mine = wbase + __popc(m & ((1u << lane) - 1u));
+        __syncthreads();
+        if (threadIdx.x == 0 && s_n) s_base = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(X.segs + 3 * X.P + 2), (unsigned long long)s_n);
+        __syncthreads();
+        if (first) X.touched[s_base + mine] = (int)r;
+        __syncthreads();
+      }
+      return;
+    }
     for (long long t = (long long)(blockIdx.x - ga) * blockDim.x + threadIdx.x; t < n; t += stride) {
       const int p = seg_of(s_start, X.P, t);
       const long long r = __ldcg(X.req[p] + (long long)X.me * X.cap + (t - s_start[p]));
@@ -276,6 +316,30 @@ __global__ void __launch_bounds__(256) k_owner_scatter(const __grid_constant__ X
   }
 }
 
+// push variant: every requested row's gradients were red.added into this owner's dense table by the requesters' step
+// kernels; apply each listed row once, return its gradient row and its request count to zero
+template <int LPG, int NV>
+__global__ void __launch_bounds__(256) k_owner_apply_dense(const __grid_constant__ XDev X, const __grid_constant__ StepDev P) {
+  const int lane = threadIdx.x & 31, gl = lane & (LPG - 1), leader = lane & ~(LPG - 1);
+  const unsigned gmask = LPG == 32 ? 0xffffffffu : (((1u << LPG) - 1u) << leader);
+  const long long ngroups = (long long)gridDim.x * blockDim.x / LPG;
+  const bool adagrad = P.optimizer == CF_OPT_ADAGRAD;
+  const long long n = X.segs[3 * X.P + 2];
+  for (long long k = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / LPG; k < n; k += ngroups) {
+    const long long r = __ldg(X.touched + k);
+    float* gp = X.dense + r * X.ld;
+    const Row<NV> g = load_row<LPG, NV>(gp, 0, 0, P.nvec, gl);
+    const Row<NV> cur = load_row<LPG, NV>(P.U, r, P.ld, P.nvec, gl);
+    Row<NV> acc, np;
+    if (adagrad) acc = load_row<LPG, NV>(P.accU, r, P.ld, P.nvec, gl, 1.f);
+    apply_math<LPG, NV>(P, cur, acc, g, np, gmask);
+    if (adagrad) store_row<LPG, NV>(P.accU, r, P.ld, P.nvec, gl, acc);
+    store_row<LPG, NV>(P.U, r, P.ld, P.nvec, gl, np);
+    store_row<LPG, NV>(gp, 0, 0, P.nvec, gl, zero_row<NV>());
+    if (gl == 0) __stcg(P.metaU + r, 0u);
+  }
+}
+
 int check_common(const cf_exchange_args* a, const char* who) {
   CF_CHECK_ARG(a != nullptr, "%s: args is NULL", who);
   CF_CHECK_ARG(a->n_ranks >= 1 && a->n_ranks <= CF_MAX_PEERS && a->rank >= 0 && a->rank < a->n_ranks, "%s: need 1 <= n_ranks <= %d and 0 <= rank < n_ranks", who, CF_MAX_PEERS);
@@ -293,6 +357,7 @@ XDev make_xdev(const cf_exchange_args* a) {
     X.counts[p] = a->counts[p]; X.req[p] = a->req[p]; X.grads[p] = a->grads[p]; X.tables[p] = a->tables[p];
   }
   X.my_grads = a->grads[a->rank]; X.fetched = a->fetched; X.slot_of = a->slot_of; X.segs = reinterpret_cast<long long*>(a->segs);
+  X.dense = a->dense_grads; X.touched = a->touched;
   return X;
 }
 
@@ -308,6 +373,14 @@ StepDev make_owner_dev(const cf_exchange_args* a) {
 }
 
 int check_owner(const cf_exchange_args* a, const char* who) {
+  if (a->dense_grads != nullptr) {   // push variant
+    CF_CHECK_ARG(a->table && a->meta && a->touched && a->counters && a->segs, "%s: NULL owner-side pointer", who);
+    CF_CHECK_ARG(a->d > 0 && a->ld >= a->d && a->ld % 4 == 0 && a->ld <= 512, "%s: bad d / ld", who);
+    CF_CHECK_ARG(a->optimizer == CF_OPT_SGD || a->acc, "%s: Adagrad needs the accumulator table", who);
+    CF_CHECK_ARG(a->n_rows > 0, "%s: empty shard", who);
+    if (a->model == CF_MODEL_CML) CF_CHECK_ARG(a->clip_norm > 0.f, "%s: CML needs clip_norm > 0", who);
+    return 0;
+  }
   CF_CHECK_ARG(a->table && a->meta && a->slot && a->slot_row && a->staging && a->counters && a->segs, "%s: NULL owner-side pointer", who);
   CF_CHECK_ARG(a->d > 0 && a->ld >= a->d && a->ld % 4 == 0 && a->ld <= 512, "%s: bad d / ld", who);
   CF_CHECK_ARG(a->optimizer == CF_OPT_SGD || a->acc, "%s: Adagrad needs the accumulator table", who);
@@ -348,7 +421,8 @@ extern "C" int cf_exchange_prepare(const cf_exchange_args* a, void* stream_) {
   if (a->fetched) for (int p = 0; p < a->n_ranks; ++p) CF_CHECK_ARG(a->tables[p] != nullptr, "cf_exchange_prepare: item shard of rank %d is NULL", p);
   const XDev X = make_xdev(a);
   const StepDev P = make_owner_dev(a);
-  k_owner_segs<<<1, 32, 0, stream>>>(X);
+  if (a->dense_grads) CF_CUDA_OK(cudaMemsetAsync(a->segs + 3 * a->n_ranks + 2, 0, sizeof(int64_t), stream));   // length of the touched list
+  k_owner_segs<<<1, CF_MAX_PEERS * CF_MAX_PEERS, 0, stream>>>(X);
   const int sms = cf_num_sms();
   const int ga = sms * 8, gb = sms * 4;
   k_exchange_prepare<<<ga + gb, 256, 0, stream>>>(X, P, ga);
@@ -364,6 +438,15 @@ extern "C" int cf_exchange_apply(const cf_exchange_args* a, void* stream_) {
   const StepDev P = make_owner_dev(a);
   const int sms = cf_num_sms();
   const int grid = sms * 16;
+  if (a->dense_grads) {
+    if (P.nvec <= 8) k_owner_apply_dense<8, 1><<<grid, 256, 0, stream>>>(X, P);
+    else if (P.nvec <= 16) k_owner_apply_dense<16, 1><<<grid, 256, 0, stream>>>(X, P);
+    else if (P.nvec <= 32) k_owner_apply_dense<32, 1><<<grid, 256, 0, stream>>>(X, P);
+    else if (P.nvec <= 64) k_owner_apply_dense<32, 2><<<grid, 256, 0, stream>>>(X, P);
+    else k_owner_apply_dense<32, 4><<<grid, 256, 0, stream>>>(X, P);
+    CF_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   if (P.nvec <= 8) k_owner_scatter<8, 1><<<grid, 256, 0, stream>>>(X, P);
   else if (P.nvec <= 16) k_owner_scatter<16, 1><<<grid, 256, 0, stream>>>(X, P);
   else if (P.nvec <= 32) k_owner_scatter<32, 1><<<grid, 256, 0, stream>>>(X, P);

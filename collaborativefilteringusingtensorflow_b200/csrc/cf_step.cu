@@ -199,15 +199,23 @@ static int train_steps_impl(const cf_step_args* a, cudaStream_t stream, cudaEven
   P.lds = a->ld + 4; P.counters = a->counters;
   P.gradV = a->gradV; P.rank_items = a->rank_items > 0 ? a->rank_items : a->n_items;
   P.gradU = a->gradU; P.gradb = a->gradb;
-  if (a->gradV) CF_CHECK_ARG(a->update == CF_UPDATE_SYNC, "cf_train_steps: exchange mode (gradV) needs SYNC mode");
+  if (a->gradV || a->n_peers) CF_CHECK_ARG(a->update == CF_UPDATE_SYNC, "cf_train_steps: exchange mode (gradV / peers) needs SYNC mode");
   if (a->gradV && a->model == CF_MODEL_GBPR)
     CF_CHECK_ARG(a->gradU && a->gradb && a->n_peers == 0, "cf_train_steps: GBPR in exchange mode needs gradU, gradV and gradb (replicated data-parallel mode)");
   if (a->gradU) CF_CHECK_ARG(a->gradV != nullptr && a->n_peers == 0, "cf_train_steps: gradU needs gradV (dense gradient tables of the replicated mode)");
   P.n_peers = a->n_peers; P.gslot_pos = a->gslot_pos; P.gslot_neg = a->gslot_neg;
   for (int k = 0; k < CF_MAX_PEERS; ++k) P.peerV[k] = k < a->n_peers ? a->peerV[k] : nullptr;
+  for (int k = 0; k < CF_MAX_PEERS; ++k) P.peerG[k] = k < a->n_peers ? a->peerG[k] : nullptr;
   if (a->n_peers != 0) {
     CF_CHECK_ARG(a->n_peers > 0 && a->n_peers <= CF_MAX_PEERS, "cf_train_steps: n_peers must be in [0, %d]", CF_MAX_PEERS);
-    CF_CHECK_ARG(a->gradV != nullptr && a->gslot_pos != nullptr && (W == 0 || a->gslot_neg != nullptr), "cf_train_steps: peer pull needs gradV and the gradient slots");
+    if (a->peerG[0] != nullptr) {   // push: gradients go to the owners' dense tables; gradV only marks the item rows as remote
+      for (int k = 0; k < a->n_peers; ++k) CF_CHECK_ARG(a->peerG[k] != nullptr, "cf_train_steps: peerG[%d] is NULL", k);
+      CF_CHECK_ARG(a->gslot_pos == nullptr && a->gslot_neg == nullptr, "cf_train_steps: peerG (push) and gslot_* (compact buffer) exclude each other");
+      P.gradV = a->peerG[0];
+      P.gslot_pos = nullptr; P.gslot_neg = nullptr;
+    } else {
+      CF_CHECK_ARG(a->gradV != nullptr && a->gslot_pos != nullptr && (W == 0 || a->gslot_neg != nullptr), "cf_train_steps: peer pull needs gradV and the gradient slots (or peerG)");
+    }
     CF_CHECK_ARG(a->n_batches == 1, "cf_train_steps: peer pull takes one minibatch per call");
     for (int k = 0; k < a->n_peers; ++k) CF_CHECK_ARG(a->peerV[k] != nullptr, "cf_train_steps: peerV[%d] is NULL", k);
   }

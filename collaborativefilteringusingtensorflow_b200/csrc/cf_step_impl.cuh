@@ -50,6 +50,9 @@ struct StepDev {
   const float* peerV[CF_MAX_PEERS];
   const int32_t *gslot_pos, *gslot_neg;
   int n_peers;
+  // push variant of the peer mode: the gradient of item i is red.added straight into its OWNER's dense gradient table
+  // peerG[i % n_peers] + (i / n_peers) * ld (NVLink, outbound while the row reads are inbound); gslot_* are not used
+  float* peerG[CF_MAX_PEERS];
   long long n_occ;       // slots scanned by k_apply_staged
 };
 
@@ -340,7 +343,7 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepDev P)
         }
         if (sync && commit_pass && my_local && (gl >= 2 || last_tile) && occ_lo > 1u)
           my_slot = __ldcg((is_user_tab ? P.slotU : P.slotV) + my_row);
-        if (pull && commit_pass) {   // peer pull: the row of gradV that collects my item row's gradient
+        if (pull && commit_pass && P.gslot_pos != nullptr) {   // peer pull: the row of gradV that collects my item row's gradient
           if (my_role == ROLE_NEG) my_slot = __ldg(P.gslot_neg + bb * P.W + (e0 + gl - 2));
           if (my_role == ROLE_ITEM && last_tile) my_slot = __ldg(P.gslot_pos + bb);
         }
@@ -466,6 +469,12 @@ __global__ void __launch_bounds__(256) k_step(const __grid_constant__ StepDev P)
               if (pull && !utab) gs = __shfl_sync(gmask, my_slot, leader + s);
             }
             float* gr = ((EXT && utab) ? P.gradU : P.gradV) + (long long)gs * P.ld;
+            if constexpr (EXT) {
+              if (pull && !utab && P.gslot_pos == nullptr) {   // push: the owner's dense gradient table, over NVLink
+                const int q = r / P.n_peers;
+                gr = P.peerG[r - q * P.n_peers] + (long long)q * P.ld;
+              }
+            }
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
               const int v = gl + k * LPG;

@@ -62,9 +62,12 @@ __device__ __forceinline__ unsigned ord_key(float f) {  // monotone float -> uin
 }
 __device__ __forceinline__ float ord_unkey(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
 
-// Warp-cooperative compaction of ONE row's candidate buffer (n entries): theta <- K-th largest value, keep >= theta - eps2.
-__device__ __forceinline__ void compact_row(float* cv, int32_t* ci, int n, int K, float eps2, int lane, float& theta_out,
-                                            int& cnt_out) {
+// Warp-cooperative compaction of ONE row's candidate buffer (n entries): entries [ver, n) were appended WITHOUT looking at
+// the user's training row (a binary search per hit inside the per-thread sweep is a chain of dependent global loads that
+// nothing hides: it was most of the sweep on small catalogues) -- they are checked here, 32 searches in flight; then
+// theta <- K-th largest value among the unmasked entries, keep >= theta - eps2.
+__device__ __forceinline__ void compact_row(float* cv, int32_t* ci, int n, int ver, int K, float eps2, const int32_t* tr_indices,
+                                            long long tlo, long long thi, int lane, float& theta_out, int& cnt_out) {
   constexpr int EPL = TC_CAP / 32;
   float v[EPL];
   int32_t id[EPL];
@@ -73,6 +76,16 @@ __device__ __forceinline__ void compact_row(float* cv, int32_t* ci, int n, int K
     const int e = lane + 32 * i;
     v[i] = e < n ? __ldcg(cv + e) : __uint_as_float(0xffffffffu);   // padding: key 0 (below every real score)
     id[i] = e < n ? __ldcg(ci + e) : -1;
+  }
+  if (thi > tlo) {
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+      const int e = lane + 32 * i;
+      if (e >= ver && e < n && csr_contains(tr_indices, tlo, thi, id[i])) {   // a training item: drop it
+        v[i] = __uint_as_float(0xffffffffu);
+        id[i] = -1;
+      }
+    }
   }
   unsigned prefix = 0u;
   for (int bit = 31; bit >= 0; --bit) {
@@ -84,13 +97,14 @@ __device__ __forceinline__ void compact_row(float* cv, int32_t* ci, int n, int K
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if (c >= K) prefix = cand;
   }
-  const float theta = ord_unkey(prefix);
+  // fewer than K unmasked entries so far: no threshold yet, keep them all
+  const float theta = prefix ? ord_unkey(prefix) : -INFINITY;
   const float cut = theta - eps2;
   int pos = 0;
   __syncwarp();
 #pragma unroll
   for (int i = 0; i < EPL; ++i) {
-    const bool keep = (lane + 32 * i < n) && v[i] >= cut;   // (padding is NaN: compares false)
+    const bool keep = id[i] >= 0 && v[i] >= cut;   // (padding and masked entries have id -1)
     const unsigned m = __ballot_sync(0xffffffffu, keep);
     if (keep) {
       const int p = pos + __popc(m & ((1u << lane) - 1u));
@@ -216,7 +230,7 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     const int row = row0 + mt * TC_M + q * 32 + lane;
     const bool valid = row < P.T;
     float theta = valid ? -INFINITY : INFINITY;
-    int cnt = 0;
+    int cnt = 0, ver = 0;   // entries [0, ver) of the buffer are known not to be training items
     const float eps2 = valid ? P.eps2[row] : 0.f;
     long long tlo = 0, thi = 0;
     if (valid && P.tr_indptr) {
@@ -254,17 +268,21 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
           float* rcv = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(cv), l));
           int32_t* rci = reinterpret_cast<int32_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(ci), l));
           const int rn = __shfl_sync(0xffffffffu, cnt, l);
+          const int rver = __shfl_sync(0xffffffffu, ver, l);
           const float re = __shfl_sync(0xffffffffu, eps2, l);
+          const long long rlo = __shfl_sync(0xffffffffu, tlo, l), rhi = __shfl_sync(0xffffffffu, thi, l);
           float nth;
           int ncnt;
-          compact_row(rcv, rci, rn, P.K, re, lane, nth, ncnt);
+          compact_row(rcv, rci, rn, rver, P.K, re, P.tr_indices, rlo, rhi, lane, nth, ncnt);
           if (lane == l) {
             theta = nth;
             cnt = ncnt;
+            ver = ncnt;
             if (ncnt > TC_CAP - 64) {  // too many items within 2 eps of the K-th best: give this row to the exact kernel
               overflowed = true;
               theta = INFINITY;
               cnt = 0;
+              ver = 0;
             }
           }
         }
@@ -288,7 +306,7 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
                 const float sv = __uint_as_float(r[j]);
                 if (sv >= thr) {
                   const int item = n0 + c * 32 + j;
-                  if (item < P.N && !csr_contains(P.tr_indices, tlo, thi, item)) {
+                  if (item < P.N) {   // (training items are dropped at the next compaction / by the re-rank)
                     cv[cnt] = sv;
                     ci[cnt] = item;
                     ++cnt;
@@ -419,6 +437,8 @@ struct RerankParams {
   const int32_t* cand_idx;
   const int32_t* cand_cnt;
   const int32_t* overflow;
+  const long long* tr_indptr;   // training CSR (NULL = no mask): candidates appended after a row's last compaction are unchecked
+  const int32_t* tr_indices;
   int32_t* out_idx;
   double* out_val;
   int32_t* stats;
@@ -437,6 +457,7 @@ __global__ void __launch_bounds__(256) k_rerank(const __grid_constant__ RerankPa
     }
     const long long u = P.users ? P.users[t] : t;
     for (int k = threadIdx.x; k < P.ld; k += blockDim.x) s_u[k] = P.U[u * P.ld + k];
+    const long long tlo = P.tr_indptr ? P.tr_indptr[u] : 0, thi = P.tr_indptr ? P.tr_indptr[u + 1] : 0;
     int total = 0;
     for (int s = 0; s < P.S; ++s) total += P.cand_cnt[(long long)t * P.S + s];
     int n2 = 32;
@@ -450,6 +471,11 @@ __global__ void __launch_bounds__(256) k_rerank(const __grid_constant__ RerankPa
       const int32_t* ci = P.cand_idx + ((long long)t * P.S + s) * TC_CAP;
       for (int e = threadIdx.x; e < c; e += blockDim.x) {
         const long long item = ci[e];
+        if (csr_contains(P.tr_indices, tlo, thi, (int)item)) {   // a training item: sorts behind every real candidate
+          s_val[base + e] = -INFINITY;
+          s_idx[base + e] = 0x7fffffff;
+          continue;
+        }
         const float4* vp = reinterpret_cast<const float4*>(P.V + item * P.ld);
         double sc = 0.0;
         if (P.kind == CF_SCORE_NEG_SQDIST) {
@@ -499,7 +525,7 @@ __global__ void __launch_bounds__(256) k_rerank(const __grid_constant__ RerankPa
       }
     }
     for (int k = threadIdx.x; k < P.K; k += blockDim.x) {
-      const bool ok = k < total;
+      const bool ok = k < total && s_idx[k] != 0x7fffffff;
       P.out_idx[(long long)t * P.K + k] = ok ? s_idx[k] : -1;
       if (P.out_val) P.out_val[(long long)t * P.K + k] = ok ? s_val[k] : -INFINITY;
     }
@@ -652,6 +678,7 @@ extern "C" int cf_topk_tc(const cf_topk_args* a, void* workspace, int64_t worksp
   RerankParams R = {};
   R.U = a->U; R.V = a->V; R.b = a->b; R.ld = a->ld; R.nvec = a->ld / 4; R.kind = a->kind; R.T = a->T; R.S = p.S; R.K = a->K;
   R.users = a->users; R.cand_val = cval; R.cand_idx = cidx; R.cand_cnt = ccnt; R.overflow = ovf;
+  R.tr_indptr = (const long long*)a->train.indptr; R.tr_indices = a->train.indices;
   R.out_idx = a->out_idx; R.out_val = a->out_val; R.stats = stats;
   int rg = a->T;
   if (rg > sms * 8) rg = sms * 8;

@@ -432,6 +432,14 @@ class DistributedTrainer(object):
         pull = self._pull if self._pull is not None else self._decide_transport(par)
         if not pull and d['fetched'] is None:
             d['fetched'] = torch.empty(d['slots'], eng.ld, device=eng.device)
+        if pull and d.get('gown') is None:
+            # pull transport: item rows arrive over NVLink inside k_step, and the gradient of every occurrence LEAVES in
+            # the same kernel -- red.added straight into the owner's dense gradient table (both NVLink directions are busy
+            # at once; the owners then apply their tables locally).  Shared once, on the first minibatch (collective: the
+            # transport decision is the same on every rank).
+            d['gown'] = torch.zeros(eng.n_items, eng.ld, device=eng.device)
+            d['touched'] = torch.zeros(eng.n_items, dtype=torch.int32, device=eng.device)
+            d['gown_ptrs'] = self._share(d['gown'])
         self.req_rows_dev += d['comm'][par * d['mail']: par * d['mail'] + self.world].sum()
         # barrier 1: every mailbox is complete, and every rank is past the owner-side apply of the previous minibatch (so
         # item rows may be read remotely and the gradient buffer may be zeroed)
@@ -440,6 +448,7 @@ class DistributedTrainer(object):
         x = self._xargs(par)
         if pull:
             x.fetched = None
+            x.dense_grads, x.touched = _lib.ptr(d['gown']), _lib.ptr(d['touched'])
         _lib.check(self.lib.cf_exchange_prepare(x, stream), 'cf_exchange_prepare')
         ev = self._tick('prepare (fetch rows over NVLink + zero grads + owner-side count: k_owner_segs, k_exchange_prepare)', ev)
         if after_prepare is not None:
@@ -450,11 +459,12 @@ class DistributedTrainer(object):
             a.pairs, a.negs = _lib.ptr(lp), _lib.ptr(ln)
             for r, q in enumerate(self.peer_ptrs):
                 a.peerV[r] = q
-            a.n_peers, a.gslot_pos, a.gslot_neg = self.world, _lib.ptr(d['slot_pos'][par]), _lib.ptr(d['slot_negs'][par])
+                a.peerG[r] = d['gown_ptrs'][r]
+            a.n_peers = self.world
         else:       # the fetched copy of every requested row, ids = rows of the compact buffers
             a.V, a.n_items = _lib.ptr(d['fetched']), d['slots']
             a.pairs, a.negs = _lib.ptr(d['slot_pairs'][par]), _lib.ptr(d['slot_negs'][par])
-        a.gradV = _lib.ptr(d['gbuf'])
+            a.gradV = _lib.ptr(d['gbuf'])
         _lib.check(self.lib.cf_train_steps(a, stream), 'cf_train_steps')
         ev = self._tick('k_count + k_step + k_apply_staged', ev)
         self._barrier('gradient buffers complete')          # every rank is past its step kernel
@@ -465,9 +475,9 @@ class DistributedTrainer(object):
             # and the touched-row clip fused into the applies is the same thing.  Like
             # engine.train_batches: step first, THEN clip -- the first minibatch's gradients see the unclipped init.
             eng._full_clip(stream)
-        ev = self._tick('owner apply (k_owner_scatter + k_apply_staged)', ev)
+        ev = self._tick('owner apply (k_owner_apply_dense)' if pull else 'owner apply (k_owner_scatter + k_apply_staged)', ev)
         self._k += 1
-        self.launches += 2 + 3 + 2
+        self.launches += 2 + 3 + (1 if pull else 2)
         self.occurrences += B * (1 + W)
         self.bytes_pulled += (B * (1 + W) if pull else 0) * eng.ld * 4
         return loss
@@ -595,10 +605,16 @@ def shard_mask_csr(sub_csr, world, rank):
     return DeviceCSR(indptr, cols.contiguous(), rows.contiguous(), None, (sub_csr.shape[0], item_shard_rows(sub_csr.shape[1], world, rank)))
 
 
-def distributed_topk(engine, query_rows, K, train_local_csr, world, rank, group=None, method='auto'):
+def distributed_topk(engine, query_rows, K, train_local_csr, world, rank, group=None, method='auto', gather=True):
     """query_rows: [T, ld] embeddings of the query users (already all-gathered / replicated on every rank).
     engine.V is this rank's item shard (local row j = global item j * world + rank); train_local_csr masks in LOCAL item
-    ids (row t = query t).  Returns the merged global top-K ids [T, K] (int32) and scores on every rank."""
+    ids (row t = query t).  Every rank keeps a local top-K over its shard; then
+      gather=True   the [T, K] lists are all-gathered and every rank merges all of them: returns the global top-K ids
+                    [T, K] (int32) and fp64 scores on EVERY rank (SURVEY 8e);
+      gather=False  the lists are exchanged with ONE all-to-all so that rank r receives the P lists of users
+                    [r * c, (r + 1) * c), c = ceil(T / P), and merges only those: returns (lo, ids [c', K], scores) for its own
+                    slice -- 1/P of the traffic and of the merge work per rank, which is what an evaluation needs (every user's
+                    metrics are computed once, their sums all-reduced: ``distributed_evaluate``)."""
     torch = _lib.require_cuda()
     import torch.distributed as dist
     lib = _lib.lib()
@@ -610,17 +626,34 @@ def distributed_topk(engine, query_rows, K, train_local_csr, world, rank, group=
     finally:
         engine.U, engine.n_users = saved_U, saved_n
     gidx = torch.where(idx >= 0, idx * world + rank, idx)
+    stream = torch.cuda.current_stream(idx.device).cuda_stream
     if world == 1:
-        return gidx, val
-    all_i = torch.empty(world, T, K, dtype=torch.int32, device=idx.device)
-    all_v = torch.empty(world, T, K, dtype=torch.float64, device=idx.device)
-    dist.all_gather_into_tensor(all_i, gidx.contiguous(), group=group)
-    dist.all_gather_into_tensor(all_v, val.contiguous(), group=group)
-    out_i = torch.empty(T, K, dtype=torch.int32, device=idx.device)
-    out_v = torch.empty(T, K, dtype=torch.float64, device=idx.device)
-    _lib.check(lib.cf_topk_merge(all_i.data_ptr(), all_v.data_ptr(), world, T, K, out_i.data_ptr(), out_v.data_ptr(),
-                                 torch.cuda.current_stream(idx.device).cuda_stream), 'cf_topk_merge')
-    return out_i, out_v
+        return (gidx, val) if gather else (0, gidx, val)
+    if gather:
+        all_i = torch.empty(world, T, K, dtype=torch.int32, device=idx.device)
+        all_v = torch.empty(world, T, K, dtype=torch.float64, device=idx.device)
+        dist.all_gather_into_tensor(all_i, gidx.contiguous(), group=group)
+        dist.all_gather_into_tensor(all_v, val.contiguous(), group=group)
+        out_i = torch.empty(T, K, dtype=torch.int32, device=idx.device)
+        out_v = torch.empty(T, K, dtype=torch.float64, device=idx.device)
+        _lib.check(lib.cf_topk_merge(all_i.data_ptr(), all_v.data_ptr(), world, T, K, out_i.data_ptr(), out_v.data_ptr(), stream),
+                   'cf_topk_merge')
+        return out_i, out_v
+    c = (T + world - 1) // world
+    if c * world != T:      # pad the user dimension so that every rank sends equal chunks
+        gidx = torch.cat([gidx, torch.full((c * world - T, K), -1, dtype=torch.int32, device=idx.device)])
+        val = torch.cat([val, torch.full((c * world - T, K), float('-inf'), dtype=torch.float64, device=idx.device)])
+    recv_i = torch.empty(world, c, K, dtype=torch.int32, device=idx.device)
+    recv_v = torch.empty(world, c, K, dtype=torch.float64, device=idx.device)
+    dist.all_to_all_single(recv_i, gidx.contiguous(), group=group)
+    dist.all_to_all_single(recv_v, val.contiguous(), group=group)
+    out_i = torch.empty(c, K, dtype=torch.int32, device=idx.device)
+    out_v = torch.empty(c, K, dtype=torch.float64, device=idx.device)
+    _lib.check(lib.cf_topk_merge(recv_i.data_ptr(), recv_v.data_ptr(), world, c, K, out_i.data_ptr(), out_v.data_ptr(), stream),
+               'cf_topk_merge')
+    lo = rank * c
+    n_mine = max(0, min(T, lo + c) - lo)
+    return lo, out_i[:n_mine], out_v[:n_mine]
 
 
 def _world(group=None):

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CF_ABI_VERSION 16
+#define CF_ABI_VERSION 17
 
 /* models */
 enum { CF_MODEL_BPR = 0, CF_MODEL_CML = 1, CF_MODEL_GBPR = 2, CF_MODEL_WRMF = 3 };
@@ -123,6 +123,11 @@ typedef struct cf_step_args {
    * dense gradient tables and nothing is applied; the caller all-reduces them and applies them with cf_apply_dense */
   float* gradU;             /* [n_users, ld] or NULL */
   float* gradb;             /* [n_items] (GBPR) or NULL */
+  /* push variant of the peer-pull mode (n_peers > 0, peerG[0] != NULL; gradV / gslot_* are then not used): the gradient of
+   * every occurrence of item i is red.added straight into its OWNER's dense gradient table peerG[i % n_peers] at row
+   * i / n_peers (stride ld; zero at rest; mapped with cf_ipc_open) -- gradient rows leave over NVLink while item rows
+   * arrive, and the owner applies its table locally (cf_exchange_apply with dense_grads) */
+  float* peerG[CF_MAX_PEERS];
 } cf_step_args;
 
 int cf_train_steps(const cf_step_args* args, void* stream);
@@ -229,6 +234,11 @@ typedef struct cf_exchange_args {
   int64_t staging_rows;    /* >= n_ranks * cap */
   int64_t* segs;           /* device scratch, int64[4 * CF_MAX_PEERS + 4] */
   int32_t* counters;       /* [4] (flags in [1]) */
+  /* push variant (with cf_step_args.peerG): dense_grads = this rank's dense gradient table [n_rows, ld] (zero at rest; the
+   * peers red.add into it), touched = int32[n_rows] scratch for the list of rows that received a gradient.  grads / fetched /
+   * slot / slot_row / staging are then not used: prepare only counts and lists the requested rows, apply walks the list. */
+  float* dense_grads;
+  int32_t* touched;
 } cf_exchange_args;
 int cf_exchange_route(const cf_exchange_args* args, void* stream);
 int cf_exchange_prepare(const cf_exchange_args* args, void* stream);

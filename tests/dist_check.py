@@ -99,6 +99,16 @@ def main():
             same = bool(torch.equal(wi, gi) and torch.equal(wv, gv))
             print('%s sharded top-%d == single GPU: %s' % (kind, K, same))
             ok &= same
+        # the all-to-all form: every rank merges only its slice of the users; the slices together are the same lists
+        lo, si, sv = distributed_topk(local_m.engine, q, K, DeviceCSR.from_scipy(local_mask, dev), world, rank, gather=False)
+        same = bool(torch.equal(si, gi[lo:lo + si.shape[0]]) and torch.equal(sv, gv[lo:lo + si.shape[0]]))
+        cover = torch.tensor([si.shape[0]], device=dev)
+        dist.all_reduce(cover)
+        flag = torch.tensor([int(same and int(cover.item()) == T)], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print('%s sharded top-%d, sliced merge (all-to-all) == all-gather merge on every rank: %s' % (kind, K, bool(flag.item())))
+            ok &= bool(flag.item())
     # ---- metrics: users sharded, sums all-reduced (every rank gets the global values)
     from collaborativefilteringusingtensorflow_b200.dist import DistributedALS, distributed_evaluate
     from collaborativefilteringusingtensorflow_b200.metrics.ranking import evaluateCV
