@@ -64,7 +64,7 @@ def sharded_training(B_, wl, args, rank, world, device, n_items_global, K, Wm, w
         uniq = (int(tr.req_rows_dev.item()) - q0) / K
         rowb = model.engine.ld * 4
         # (pull transport: rows in per occurrence -- counted above -- and gradient rows OUT per occurrence, the other direction)
-        pulled += (tr.bytes_pulled - p0) / K * remote if tr._pull else 2 * uniq * rowb * remote
+        pulled += (tr.bytes_pulled - p0) / K * remote if tr._push else (1 if tr._pull else 2) * uniq * rowb * remote
     model.engine.check_flags()
     out = dict(ms=ms, t0=t0, t1=t1, launches=launches, losses=losses, sent=sent, pulled=pulled, e2e_ms=None, h2d=None)
     if want_e2e:
@@ -132,6 +132,7 @@ def step_line(B_, wl, args, world, K, Wm, r, n_items_global, tr, pk):
     return dict(value=units / (ms * 1e-3), unit='triple updates/s', ms_per_step=ms / K, steps=K, gpu_launches=r['launches'],
                 item_transport=(('device-side exchange over peer memory: ' +
                                  ('item rows read per occurrence inside k_step and gradients red.added into the owners\' dense tables by the same kernel (pull + push)'
+                                  if tr._push else 'item rows read per occurrence inside k_step (pull) + gradient rows read in place by the owners'
                                   if tr._pull else 'unique item rows gathered once by k_exchange_prepare (fetch) + gradient rows read in place by the owners'))
                                 if tr.device_side else
                                 'nccl (all-to-all of ids, unique rows and gradient rows)'),

@@ -26,6 +26,12 @@ def __getattr__(name):   # lazy: importing the package must work on a box withou
     if name == 'SVD':
         from .models.basic.models.svd import SVD
         return SVD
+    if name == 'ItemCF':
+        from .models.basic.models.itemcf import ItemCF
+        return ItemCF
+    if name == 'UserCF':
+        from .models.basic.models.usercf import UserCF
+        return UserCF
     if name == 'MF':
         from .models.basic.models.mf import MF
         return MF

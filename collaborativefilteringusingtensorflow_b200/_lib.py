@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libcf_b200.so')
-ABI_VERSION = 17
+ABI_VERSION = 18
 
 # enums of cf_b200.h
 MODEL_BPR, MODEL_CML, MODEL_GBPR, MODEL_WRMF = 0, 1, 2, 3
@@ -85,6 +85,16 @@ class Csr(C.Structure):
                 ('n_rows', C.c_int64), ('n_cols', C.c_int64), ('nnz', C.c_int64)]
 
 
+class NeighborArgs(C.Structure):
+    _fields_ = [('rows', Csr), ('cols', Csr), ('K', C.c_int32), ('tie_high_index_first', C.c_int32),
+                ('out_idx', _p), ('out_sim', _p), ('norms', _p), ('scratch', _p), ('cand', _p), ('grid_rows', C.c_int64)]
+
+
+class NeighborScoreArgs(C.Structure):
+    _fields_ = [('train', Csr), ('users', _p), ('T', C.c_int32), ('K', C.c_int32), ('nbr_idx', _p), ('nbr_sim', _p),
+                ('mode', C.c_int32), ('reserved', C.c_int32), ('out_scores', _p)]
+
+
 class SampleArgs(C.Structure):
     _fields_ = [
         ('train', Csr), ('train_t', Csr), ('seed', C.c_uint64), ('epoch', C.c_int64), ('batch0', C.c_int64),
@@ -116,6 +126,10 @@ _SIGNATURES = {
     'cf_exchange_route': (C.c_int, [C.POINTER(ExchangeArgs), _p]),
     'cf_exchange_prepare': (C.c_int, [C.POINTER(ExchangeArgs), _p]),
     'cf_exchange_apply': (C.c_int, [C.POINTER(ExchangeArgs), _p]),
+    'cf_neighbors_concurrent_rows': (C.c_int64, []),
+    'cf_neighbors': (C.c_int, [C.POINTER(NeighborArgs), _p]),
+    'cf_neighbor_scores': (C.c_int, [C.POINTER(NeighborScoreArgs), _p]),
+    'cf_topk_dense': (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _p, C.POINTER(Csr), _p, _p, _p]),
     'cf_clip_rows': (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, _p]),
     'cf_predict_pairs': (C.c_int, [_p, _p, _p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _p, C.c_int64, _p, _p, _p]),
     'cf_rating_metrics': (C.c_int, [_p, C.c_int32, _p, C.c_int64, C.c_double, C.c_double, _p, _p]),

@@ -149,12 +149,17 @@ class DistributedTrainer(object):
                every requested row ONCE into a local buffer (right when minibatches repeat items: configs[1]); 'peer' lets
                the fused step kernel read item rows from their owners per occurrence (right when they barely repeat:
                configs[4]); 'auto' measures the repeat ratio of the first minibatch and picks (same answer on every rank).
+               In both, the owners read the gradient rows in place from the requesters' compact buffers.  'peer-push' is
+               'peer' with the gradients going the other way: k_step red.adds every occurrence's gradient straight into
+               the owner's dense gradient table over NVLink (both link directions busy at once).  Measured on configs[4]
+               at 2 GPUs it LOSES (3.60 vs 3.31 ms per minibatch: the dense tables turn the L2-resident atomics of the
+               compact buffer into DRAM read-modify-writes on both sides), so it is not what 'auto' picks.
       'nccl'   the first version, kept as the portable baseline: torch-op plan + three NCCL all-to-alls (ids, rows,
                gradients).  It is also what 'auto' falls back to, with a warning, when peer memory cannot be mapped."""
 
     def __init__(self, model, sampler, n_items_global, world, rank, group=None, item_transport='nccl'):
-        if item_transport not in ('nccl', 'peer', 'fetch', 'auto'):
-            raise ValueError("item_transport must be 'nccl', 'peer', 'fetch' or 'auto'")
+        if item_transport not in ('nccl', 'peer', 'peer-push', 'fetch', 'auto'):
+            raise ValueError("item_transport must be 'nccl', 'peer', 'peer-push', 'fetch' or 'auto'")
         self.torch = _lib.require_cuda()
         self.lib = _lib.lib()
         self.model, self.eng, self.sampler = model, model.engine, sampler
@@ -181,6 +186,7 @@ class DistributedTrainer(object):
         self.peer_ptrs = None         # device pointers of every rank's item shard (this rank's own included)
         self._opened = {}             # IPC handle bytes -> mapped base (an allocation is mapped once per process)
         self._pull = False
+        self._push = False
         self._dev = None              # buffers of the device-side exchange (allocated on the first minibatch)
         self._k = 0
         self._bar = None              # preallocated 1-element tensor of the named cross-GPU barrier
@@ -188,7 +194,8 @@ class DistributedTrainer(object):
         if self.device_side:
             if self.world > _lib.MAX_PEERS:
                 raise ValueError('the device-side exchange supports up to %d GPUs on one node' % _lib.MAX_PEERS)
-            self._pull = {'peer': True, 'fetch': False, 'auto': None}[item_transport]
+            self._pull = {'peer': True, 'peer-push': True, 'fetch': False, 'auto': None}[item_transport]
+            self._push = item_transport == 'peer-push'
             n_neg = getattr(sampler, 'n_neg', None)
             if n_neg is not None:     # otherwise the buffers are shared on the first minibatch
                 self._setup_or_fall_back(int(sampler.batch_size), int(n_neg))
@@ -432,11 +439,11 @@ class DistributedTrainer(object):
         pull = self._pull if self._pull is not None else self._decide_transport(par)
         if not pull and d['fetched'] is None:
             d['fetched'] = torch.empty(d['slots'], eng.ld, device=eng.device)
-        if pull and d.get('gown') is None:
-            # pull transport: item rows arrive over NVLink inside k_step, and the gradient of every occurrence LEAVES in
-            # the same kernel -- red.added straight into the owner's dense gradient table (both NVLink directions are busy
-            # at once; the owners then apply their tables locally).  Shared once, on the first minibatch (collective: the
-            # transport decision is the same on every rank).
+        push = pull and self._push
+        if push and d.get('gown') is None:
+            # 'peer-push': item rows arrive over NVLink inside k_step, and the gradient of every occurrence LEAVES in the
+            # same kernel -- red.added straight into the owner's dense gradient table (the owners then apply their tables
+            # locally).  Shared once, on the first minibatch (collective).
             d['gown'] = torch.zeros(eng.n_items, eng.ld, device=eng.device)
             d['touched'] = torch.zeros(eng.n_items, dtype=torch.int32, device=eng.device)
             d['gown_ptrs'] = self._share(d['gown'])
@@ -448,6 +455,7 @@ class DistributedTrainer(object):
         x = self._xargs(par)
         if pull:
             x.fetched = None
+        if push:
             x.dense_grads, x.touched = _lib.ptr(d['gown']), _lib.ptr(d['touched'])
         _lib.check(self.lib.cf_exchange_prepare(x, stream), 'cf_exchange_prepare')
         ev = self._tick('prepare (fetch rows over NVLink + zero grads + owner-side count: k_owner_segs, k_exchange_prepare)', ev)
@@ -459,8 +467,11 @@ class DistributedTrainer(object):
             a.pairs, a.negs = _lib.ptr(lp), _lib.ptr(ln)
             for r, q in enumerate(self.peer_ptrs):
                 a.peerV[r] = q
-                a.peerG[r] = d['gown_ptrs'][r]
+                if push:
+                    a.peerG[r] = d['gown_ptrs'][r]
             a.n_peers = self.world
+            if not push:    # the compact gradient buffer, one row per unique requested item (read in place by the owners)
+                a.gradV, a.gslot_pos, a.gslot_neg = _lib.ptr(d['gbuf']), _lib.ptr(d['slot_pos'][par]), _lib.ptr(d['slot_negs'][par])
         else:       # the fetched copy of every requested row, ids = rows of the compact buffers
             a.V, a.n_items = _lib.ptr(d['fetched']), d['slots']
             a.pairs, a.negs = _lib.ptr(d['slot_pairs'][par]), _lib.ptr(d['slot_negs'][par])
@@ -475,9 +486,9 @@ class DistributedTrainer(object):
             # and the touched-row clip fused into the applies is the same thing.  Like
             # engine.train_batches: step first, THEN clip -- the first minibatch's gradients see the unclipped init.
             eng._full_clip(stream)
-        ev = self._tick('owner apply (k_owner_apply_dense)' if pull else 'owner apply (k_owner_scatter + k_apply_staged)', ev)
+        ev = self._tick('owner apply (k_owner_apply_dense)' if push else 'owner apply (k_owner_scatter + k_apply_staged)', ev)
         self._k += 1
-        self.launches += 2 + 3 + (1 if pull else 2)
+        self.launches += 2 + 3 + (1 if push else 2)
         self.occurrences += B * (1 + W)
         self.bytes_pulled += (B * (1 + W) if pull else 0) * eng.ld * 4
         return loss

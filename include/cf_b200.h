@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CF_ABI_VERSION 17
+#define CF_ABI_VERSION 18
 
 /* models */
 enum { CF_MODEL_BPR = 0, CF_MODEL_CML = 1, CF_MODEL_GBPR = 2, CF_MODEL_WRMF = 3 };
@@ -432,6 +432,52 @@ typedef struct cf_svd_args {
 } cf_svd_args;
 int cf_svd_grads(const cf_svd_args* args, void* stream);
 int cf_svd_predict_pairs(const cf_svd_args* args, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Neighbourhood models and the user-similarity preprocessing of PRIGP / CPLR.
+ * cf_neighbors replaces `__calsim__` + `__topk__` of models/basic/models/itemcf.py:19-40 (entities = items, features =
+ * users), usercf.py:19-28,36-37 and pl/models/prigp.py:60-81, cplr_u.py:64-87 (entities = users, features = items): for
+ * every entity the K most similar other entities by cosine similarity over their feature rows,
+ *   sim(a, b) = (<a, b> / |lo|) / |hi|  in IEEE float32, lo < hi the two indices (the order of the reference's in-place
+ * divisions, itemcf.py:21-26), diagonal zero, ordered by (sim desc, index -- higher first when tie_high_index_first, what a
+ * stable ascending argsort followed by [-K:] keeps; the reference's unstable argsort leaves ties undefined).  Entities with
+ * fewer than K positive similarities are padded with -1 / 0.
+ * cf_neighbor_scores replaces `__predict__` (itemcf.py:42-50 with mode 0, nbr_* = the items' neighbours; usercf.py:31-44
+ * with mode 1, nbr_* = the users' neighbours): out_scores[t, :] += the reference's float64 accumulation of float32
+ * products (exact, hence order-independent); the caller zeroes out_scores.
+ * cf_topk_dense replaces `np.argsort(predicts)[-maxsz-topN:][::-1]` + the filter loop (itemcf.py:52-66): the N best
+ * columns of every dense score row outside the user's training row (scores is used as scratch: taken and masked
+ * entries are overwritten with -inf).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct cf_neighbor_args {
+  cf_csr rows;             /* entity -> features (values NULL = binary) */
+  cf_csr cols;             /* its transpose: feature -> entities */
+  int32_t K;
+  int32_t tie_high_index_first;
+  int32_t* out_idx;        /* [n_entities, K] */
+  float* out_sim;          /* [n_entities, K] */
+  float* norms;            /* scratch [n_entities] */
+  float* scratch;          /* [2 * grid_rows, n_entities] zero at rest */
+  int32_t* cand;           /* scratch [grid_rows, n_entities] */
+  int64_t grid_rows;       /* entities processed concurrently (cf_neighbors_concurrent_rows() is a good value) */
+} cf_neighbor_args;
+int64_t cf_neighbors_concurrent_rows(void);
+int cf_neighbors(const cf_neighbor_args* args, void* stream);
+
+typedef struct cf_neighbor_score_args {
+  cf_csr train;            /* user -> items training CSR (values NULL = binary) */
+  const int32_t* users;    /* [T] query users or NULL = 0..T-1 */
+  int32_t T;
+  int32_t K;
+  const int32_t* nbr_idx;  /* [n_items, K] (mode 0) or [n_users, K] (mode 1) */
+  const float* nbr_sim;
+  int32_t mode;
+  int32_t reserved;
+  double* out_scores;      /* [T, n_items] */
+} cf_neighbor_score_args;
+int cf_neighbor_scores(const cf_neighbor_score_args* args, void* stream);
+int cf_topk_dense(double* scores, int64_t n_items, int32_t T, int32_t N, int32_t tie_high_index_first, const int32_t* users,
+                  const cf_csr* mask, int32_t* out_idx, double* out_val, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Host-side loader.  Replaces the per-line Python loop of utils/IOUtil.py:7-16 (`loadSparseR`): parses

@@ -24,6 +24,8 @@ What comes from where
   two shapes) and the numpy oracle's 3-epoch ml-100k run with basic/testsvd.py's hyper-parameters.
 * pop_golden.json      -- the reference's own PopRank (basic/models/pop.py, numpy only) run live on ml-100k fold 1: recommended
   lists + metric values (pins the masked top-N with its tie rule and the metrics end to end against the reference).
+* cf_golden.npz        -- the reference's own ItemCF / UserCF (basic/models/itemcf.py, usercf.py, numpy only) run live on ml-100k
+  fold 1, stage by stage (similarities, neighbour choice, scores, lists, metric values).
 * e2e_golden.json      -- oracle-trained ml-100k fold-1 metrics (reference hyper-parameters of testbprmf.py:21-30).
 """
 import json
@@ -131,6 +133,80 @@ def gen_pop(bins):
     out['loov10'] = dict(scores=dict(zip(['hr', 'arhr'], [float(x) for x in m.train(1, bins['tra'], bins['tst'])])))
     json.dump(out, open(os.path.join(OUT, 'pop_golden.json'), 'w'))
     print('pop_golden:', out['top10']['scores'], out['loov10']['scores'])
+
+
+def gen_cf(nu, ni, bins):
+    """The reference's own ItemCF / UserCF (basic/models/itemcf.py, usercf.py: numpy only) run live on ml-100k fold 1
+    (testicf.py: topK = 5; usercf default topK = 50; topN = 10).  Their argsort is unstable, so exact lists are only
+    defined where no two candidates tie at a cut; everything is therefore pinned STAGE BY STAGE, each stage fed with the
+    reference's own previous-stage output: similarity values (bit-exact float32), neighbour choice (value multisets, and
+    index sets on rows without a tie at the cut), scores (exact float64), top-N (exact where the scores do not tie)."""
+    from oracle import neighbors as onb
+    sys.path.insert(0, os.path.join(REF, 'models', 'basic', 'models'))
+    import itemcf as ref_icf
+    import usercf as ref_ucf
+    names = ['pre', 'recall', 'map', 'mrr', 'ndcg']
+    tra, tst = bins['tra'], bins['tst']
+    test_users = list(set(np.asarray(tst.nonzero()[0])))
+    out = {}
+    # ---- ItemCF
+    m = ref_icf.ItemCF(nu, ni, 5, 10, 'cv', names)
+    sim = m.__calsim__(tra)
+    assert sim.dtype == np.float32
+    mine = onb.cosine_sim(tra.T.tocsr())
+    assert np.array_equal(mine, sim), 'oracle item similarity differs from the reference'
+    rows_i = [0, 1, 49, 99, 257, 600, 1200, 1681]
+    out['icf_sim_rows'], out['icf_sim_rows_val'] = np.array(rows_i, np.int32), sim[rows_i]
+    out['icf_sim_sum'], out['icf_sim_sqsum'] = np.float64(sim.astype(np.float64).sum()), np.float64((sim.astype(np.float64) ** 2).sum())
+    tie = np.zeros(ni, dtype=bool)
+    for i in range(ni):
+        srt = np.sort(sim[i])[::-1]
+        tie[i] = srt[4] == srt[5] and srt[4] > 0
+    simK = m.__topk__(sim.copy())
+    nbr_idx = np.full((ni, 5), -1, np.int32)
+    nbr_val = np.zeros((ni, 5), np.float32)
+    for i in range(ni):
+        nz = np.nonzero(simK[i])[0]
+        order = nz[np.lexsort((-nz, -simK[i, nz]))]
+        nbr_idx[i, :len(order)], nbr_val[i, :len(order)] = order, simK[i, order]
+    out['icf_nbr_idx'], out['icf_nbr_val'], out['icf_tie_at_cut'] = nbr_idx, nbr_val, tie
+    m._ItemCF__simMat = simK
+    users8 = [int(u) for u in sorted(test_users)[::115]][:8]
+    pred = np.asarray(m.__predict__(tra, users8))
+    assert np.array_equal(onb.item_scores(tra, users8, nbr_idx, nbr_val), pred), 'oracle item scores differ from the reference'
+    out['icf_users8'], out['icf_pred8'] = np.array(users8, np.int32), pred
+    lists = m._ItemCF__recommend(tra, sorted(test_users))
+    out['icf_test_users'] = np.array(sorted(test_users), np.int32)
+    out['icf_lists'] = np.array([[int(x) for x in l] + [-1] * (10 - len(l)) for l in lists], np.int32)
+    out['icf_scores'] = np.array([float(x) for x in m.train(1, tra, tst)])
+    # ---- UserCF
+    u = ref_ucf.UserCF(nu, ni, 50, 10, 'cv', names)
+    usim = u.__calsim__(tra)
+    assert np.array_equal(onb.cosine_sim(tra.tocsr()), usim), 'oracle user similarity differs from the reference'
+    rows_u = [0, 5, 100, 404, 700, 942]
+    out['ucf_sim_rows'], out['ucf_sim_rows_val'] = np.array(rows_u, np.int32), usim[rows_u]
+    out['ucf_sim_sum'] = np.float64(usim.astype(np.float64).sum())
+    unbr = np.full((nu, 50), -1, np.int32)
+    utie = np.zeros(nu, dtype=bool)
+    for a in range(nu):
+        inds = np.argsort(usim[a, :])[-50:]                      # usercf.py:37, the reference's own (unstable) choice
+        inds = inds[usim[a, inds] > 0]
+        inds = inds[np.lexsort((-inds, -usim[a, inds]))]
+        unbr[a, :len(inds)] = inds
+        srt = np.sort(usim[a])[::-1]
+        utie[a] = srt[49] == srt[50] and srt[49] > 0
+    out['ucf_nbr_idx'], out['ucf_tie_at_cut'] = unbr, utie
+    u._UserCF__simMat = usim
+    upred = np.asarray(u.__predict__(tra, users8))
+    unbr_val = np.where(unbr >= 0, usim[np.arange(nu)[:, None], np.maximum(unbr, 0)], 0).astype(np.float32)
+    assert np.array_equal(onb.user_scores(tra, users8, unbr, unbr_val), upred), 'oracle user scores differ from the reference'
+    out['ucf_pred8'] = upred
+    ulists = u._UserCF__recommend(tra, sorted(test_users))
+    out['ucf_lists'] = np.array([[int(x) for x in l] + [-1] * (10 - len(l)) for l in ulists], np.int32)
+    out['ucf_scores'] = np.array([float(x) for x in u.train(1, tra, tst)])
+    np.savez_compressed(os.path.join(OUT, 'cf_golden.npz'), **out)
+    print('cf_golden: ItemCF', dict(zip(names, out['icf_scores'].round(4))), 'rows with a tie at the cut: %d of %d;' % (tie.sum(), ni),
+          'UserCF', dict(zip(names, out['ucf_scores'].round(4))), 'rows with a tie at the cut: %d of %d' % (utie.sum(), nu))
 
 
 def gen_svd():
@@ -405,7 +481,7 @@ def gen_e2e(nu, ni, bins, ref_ranking):
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    what = set(sys.argv[1:]) or {'ranking', 'ml100k', 'steps', 'sampler', 'e2e', 'rating', 'svd', 'pop'}
+    what = set(sys.argv[1:]) or {'ranking', 'ml100k', 'steps', 'sampler', 'e2e', 'rating', 'svd', 'pop', 'cf'}
     ref_ranking, IOUtil, Util = ref_import()
     if 'ranking' in what:
         gen_ranking(ref_ranking)
@@ -415,10 +491,12 @@ if __name__ == '__main__':
         gen_rating()
     if 'svd' in what:
         gen_svd()
-    if what & {'ml100k', 'sampler', 'e2e', 'pop'}:
+    if what & {'ml100k', 'sampler', 'e2e', 'pop', 'cf'}:
         nu, ni, bins = gen_ml100k(IOUtil, Util)
         if 'pop' in what:
             gen_pop(bins)
+        if 'cf' in what:
+            gen_cf(nu, ni, bins)
         if 'e2e' in what:
             gen_e2e(nu, ni, bins, ref_ranking)
         if 'sampler' in what:

@@ -8,6 +8,8 @@
 //        3 TS + TMA    A in tensor memory, B streamed by TMA (what k_topk_tc would become)
 //        4 SS N=256 static   one MMA per 256 items (N = 256: the A operand is read once per 256 items)
 //        5 SS N=256 + TMA    (two stages of 64 KB)
+//        6..11 = 0..5 with the two M-tiles' MMAs INTERLEAVED (k outer, M-tile inner: consecutive instructions accumulate
+//        into different TMEM tiles instead of forming one dependent chain)
 // Also checks that the TS path computes the same accumulators as the SS path (TMEM layout of the A operand).
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -54,8 +56,10 @@ __global__ void __launch_bounds__(192, 1) k_mma(const __grid_constant__ CUtensor
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool ts = P.mode == 2 || P.mode == 3;
-  const bool stream = P.mode == 1 || P.mode == 3 || P.mode == 5;
+  const int bmode = P.mode % 6;
+  const bool inter = P.mode >= 6;
+  const bool ts = bmode == 2 || bmode == 3;
+  const bool stream = bmode == 1 || bmode == 3 || bmode == 5;
   const int a_bytes = MT * KC * CHUNK_BYTES;
   const int b_stage_bytes = KC * CHUNK_BYTES * (P.nB / 128);
   uint8_t* sA = smem;
@@ -125,23 +129,41 @@ __global__ void __launch_bounds__(192, 1) k_mma(const __grid_constant__ CUtensor
         tc_fence_after();
       }
       const uint64_t b0 = b00 + (uint64_t)((st * b_stage_bytes) >> 4);
+      uint32_t d_tm[MT];
       for (int mt = 0; mt < MT; ++mt) {
-        uint32_t d_tmem;
         if (P.nB == 128) {
-          d_tmem = tmem_base + (uint32_t)(slot * 128);          // ring of 3 accumulator slots
+          d_tm[mt] = tmem_base + (uint32_t)(slot * 128);        // ring of 3 accumulator slots
           if (++slot == 3) slot = 0;
         } else {
-          d_tmem = tmem_base + (uint32_t)(mt * 256);            // N = 256: one 256-column accumulator per M tile
+          d_tm[mt] = tmem_base + (uint32_t)(mt * 256);          // N = 256: one 256-column accumulator per M tile
         }
-        const int chunk_bytes = CHUNK_BYTES * (P.nB / 128);     // one K chunk of the B stage
+      }
+      const int chunk_bytes = CHUNK_BYTES * (P.nB / 128);       // one K chunk of the B stage
+      if (!inter) {
+        for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+          for (int kc = 0; kc < KC; ++kc) {
+#pragma unroll
+            for (int k = 0; k < KCH / 16; ++k) {
+              const uint64_t offa = (uint64_t)((kc * CHUNK_BYTES + k * 32) >> 4);
+              const uint64_t offb = (uint64_t)((kc * chunk_bytes + k * 32) >> 4);
+              if (ts) tc_mma_ts(d_tm[mt], tmem_base + a_col + (uint32_t)(mt * 64 + kc * 32 + k * 8), b0 + offb, idesc, (kc | k) ? 1u : 0u);
+              else tc_mma_bf16(d_tm[mt], a0[mt] + offa, b0 + offb, idesc, (kc | k) ? 1u : 0u);
+            }
+          }
+        }
+      } else {
 #pragma unroll
         for (int kc = 0; kc < KC; ++kc) {
 #pragma unroll
           for (int k = 0; k < KCH / 16; ++k) {
             const uint64_t offa = (uint64_t)((kc * CHUNK_BYTES + k * 32) >> 4);
             const uint64_t offb = (uint64_t)((kc * chunk_bytes + k * 32) >> 4);
-            if (ts) tc_mma_ts(d_tmem, tmem_base + a_col + (uint32_t)(mt * 64 + kc * 32 + k * 8), b0 + offb, idesc, (kc | k) ? 1u : 0u);
-            else tc_mma_bf16(d_tmem, a0[mt] + offa, b0 + offb, idesc, (kc | k) ? 1u : 0u);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              if (ts) tc_mma_ts(d_tm[mt], tmem_base + a_col + (uint32_t)(mt * 64 + kc * 32 + k * 8), b0 + offb, idesc, (kc | k) ? 1u : 0u);
+              else tc_mma_bf16(d_tm[mt], a0[mt] + offa, b0 + offb, idesc, (kc | k) ? 1u : 0u);
+            }
           }
         }
       }
@@ -260,9 +282,9 @@ int main(int argc, char** argv) {
   printf("TS vs SS accumulators: max |diff| = %.3g (max |value| %.3g); SS vs host fp64: max |diff| = %.3g\n", maxd, maxv, maxh);
 
   const char* names[6] = {"SS static", "SS + TMA ring", "TS static (A in TMEM)", "TS + TMA ring", "SS N=256 static", "SS N=256 + TMA ring"};
-  for (int mode = 0; mode < 6; ++mode) {
+  for (int mode = 0; mode < 12; ++mode) {
     for (int stages : {2, 4, 6}) {
-      const int nB = mode >= 4 ? 256 : 128;
+      const int nB = (mode % 6) >= 4 ? 256 : 128;
       if ((nB == 256) != (stages == 2)) continue;
       const size_t smem = MT * KC * CHUNK_BYTES + (size_t)stages * KC * CHUNK_BYTES * (nB / 128) + 512 + 1024;
       if (smem > 227 * 1024) continue;
@@ -284,7 +306,7 @@ int main(int argc, char** argv) {
       for (auto c : cyc) avg += c;
       avg /= sms;
       const double flops = (double)sms * n_tiles * 2.0 * 256 * 128 * 128;
-      printf("mode %d %-28s stages %d: %8.3f ms  %7.1f TFLOP/s  %6.1f cycles per 128x128x16 MMA (SM clock)\n", mode, names[mode], stages,
+      printf("mode %2d %-22s%s stages %d: %8.3f ms  %7.1f TFLOP/s  %6.1f cycles per 128x128x16 MMA (SM clock)\n", mode, names[mode % 6], mode >= 6 ? " interleaved" : "            ", stages,
              best, flops / (best * 1e-3) / 1e12, avg / ((double)n_tiles * 16));
     }
   }

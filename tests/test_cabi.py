@@ -44,7 +44,8 @@ def test_struct_sizes_match_the_compiled_header(tmp_path):
     if shutil.which('gcc') is None:
         pytest.skip('no gcc')
     names = dict(cf_step_args=_lib.StepArgs, cf_apply_args=_lib.ApplyArgs, cf_als_args=_lib.AlsArgs, cf_csr=_lib.Csr,
-                 cf_svd_args=_lib.SvdArgs, cf_exchange_args=_lib.ExchangeArgs,
+                 cf_svd_args=_lib.SvdArgs, cf_exchange_args=_lib.ExchangeArgs, cf_neighbor_args=_lib.NeighborArgs,
+                 cf_neighbor_score_args=_lib.NeighborScoreArgs,
                  cf_sample_args=_lib.SampleArgs, cf_topk_args=_lib.TopkArgs)
     last = {n: c._fields_[-1][0] for n, c in names.items()}
     src = '#include <stdio.h>\n#include <stddef.h>\n#include "cf_b200.h"\nint main(void) {\n'
@@ -213,6 +214,7 @@ def test_reference_layout_is_importable_without_a_gpu():
     for mod, names in (('models.pl.models.bprmf', ['BPRMF']), ('models.pl.models.cml', ['CML']), ('models.pl.models.gbprmf', ['GBPRMF']),
                        ('models.PL.models.bprmf', ['BPRMF']), ('models.basic.models.wrmf', ['WRMF']), ('models.basic.models.mf', ['MF']),
                        ('models.basic.models.svd', ['SVD']), ('models.basic.models.pop', ['PopRank']),
+                       ('models.basic.models.itemcf', ['ItemCF']), ('models.basic.models.usercf', ['UserCF']),
                        ('samplers.sampler_ranking', ['Sampler']), ('samplers.sampler_uij_ranking', ['Sampler']),
                        ('samplers.sampler_gbpr', ['Sampler']), ('samplers.sampler_rating', ['Sampler']),
                        ('metrics.ranking', ['evaluateCV', 'evaluateLOOV', 'precision_k_score', 'recall_k_score', 'ndcg_k_score',
@@ -225,5 +227,5 @@ def test_reference_layout_is_importable_without_a_gpu():
         for n in names:
             assert hasattr(m, n), (mod, n)
     top = importlib.import_module(pkg)
-    for n in ('BPRMF', 'CML', 'GBPRMF', 'WRMF', 'MF', 'SVD', 'PopRank'):
+    for n in ('BPRMF', 'CML', 'GBPRMF', 'WRMF', 'MF', 'SVD', 'PopRank', 'ItemCF', 'UserCF'):
         assert getattr(top, n).__name__ == n

@@ -21,7 +21,7 @@ def _free_port():
     return port
 
 
-@pytest.mark.parametrize('transport', ['nccl', 'peer', 'fetch', 'auto'])
+@pytest.mark.parametrize('transport', ['nccl', 'peer', 'peer-push', 'fetch', 'auto'])
 def test_two_gpu_parity_under_torchrun(transport):
     import torch
     if torch.cuda.device_count() < 2:
