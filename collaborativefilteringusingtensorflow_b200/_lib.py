@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libcf_b200.so')
-ABI_VERSION = 18
+ABI_VERSION = 19
 
 # enums of cf_b200.h
 MODEL_BPR, MODEL_CML, MODEL_GBPR, MODEL_WRMF = 0, 1, 2, 3
@@ -85,6 +85,22 @@ class Csr(C.Structure):
                 ('n_rows', C.c_int64), ('n_cols', C.c_int64), ('nnz', C.c_int64)]
 
 
+TUPLE_PRIGP, TUPLE_CPLR = 0, 1
+
+
+class TupleArgs(C.Structure):
+    _fields_ = [('U', _p), ('V', _p), ('b', _p), ('n_users', C.c_int64), ('n_items', C.c_int64), ('d', C.c_int32), ('ld', C.c_int32),
+                ('model', C.c_int32), ('reserved', C.c_int32), ('tuples', _p), ('coefs', _p), ('B', C.c_int64),
+                ('alpha', C.c_float), ('beta', C.c_float), ('gamma', C.c_float), ('reg', C.c_float),
+                ('gradU', _p), ('gradV', _p), ('gradb', _p), ('loss', _p), ('counters', _p)]
+
+
+class TupleSampleArgs(C.Structure):
+    _fields_ = [('train', Csr), ('coef', Csr), ('collab', Csr), ('eligible', _p), ('n_eligible', C.c_int64),
+                ('seed', C.c_uint64), ('epoch', C.c_int64), ('batch0', C.c_int64), ('n_batches', C.c_int32), ('B', C.c_int32),
+                ('model', C.c_int32), ('reserved', C.c_int32), ('out_tuples', _p), ('out_coefs', _p), ('flags', _p)]
+
+
 class NeighborArgs(C.Structure):
     _fields_ = [('rows', Csr), ('cols', Csr), ('K', C.c_int32), ('tie_high_index_first', C.c_int32),
                 ('out_idx', _p), ('out_sim', _p), ('norms', _p), ('scratch', _p), ('cand', _p), ('grid_rows', C.c_int64)]
@@ -130,6 +146,8 @@ _SIGNATURES = {
     'cf_neighbors': (C.c_int, [C.POINTER(NeighborArgs), _p]),
     'cf_neighbor_scores': (C.c_int, [C.POINTER(NeighborScoreArgs), _p]),
     'cf_topk_dense': (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _p, C.POINTER(Csr), _p, _p, _p]),
+    'cf_tuple_grads': (C.c_int, [C.POINTER(TupleArgs), _p]),
+    'cf_sample_tuples': (C.c_int, [C.POINTER(TupleSampleArgs), _p]),
     'cf_clip_rows': (C.c_int, [_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, _p]),
     'cf_predict_pairs': (C.c_int, [_p, _p, _p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _p, C.c_int64, _p, _p, _p]),
     'cf_rating_metrics': (C.c_int, [_p, C.c_int32, _p, C.c_int64, C.c_double, C.c_double, _p, _p]),

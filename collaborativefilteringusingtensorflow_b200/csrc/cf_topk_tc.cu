@@ -32,7 +32,12 @@ namespace {
 
 constexpr int TC_M = 128;        // rows per MMA
 constexpr int TC_MT = 2;         // M tiles per CTA (256 query rows)
-constexpr int TC_N = 128;        // items per B tile
+constexpr int TC_N = 128;        // items per B tile of the narrow kernel (n_factors > 126: KC >= 3)
+constexpr int TC_NW = 256;       // items per B tile of the wide kernel: ONE tcgen05.mma covers N = 256 items.  Measured on B200
+                                 // (tests/micro/mma_micro.cu, 148 CTAs, no epilogue): a 128 x 128 x 16 MMA costs ~122 cycles
+                                 // whatever feeds it (A in shared or tensor memory, static B or a TMA ring, M-tiles interleaved or
+                                 // not), a 128 x 256 x 16 one ~175: ~70 cycles per instruction + 0.41 per column, so N = 256
+                                 // does 1.4x the flops per cycle (1.15 -> 1.56 PFLOP/s static, 1.35 through a 2-stage TMA ring)
 constexpr int TC_KCH = 64;       // bf16 elements per 128-byte swizzle chunk
 constexpr int TC_CHUNK_BYTES = TC_M * TC_KCH * 2;   // 16 KB: one TMA box {64, 128}
 constexpr int TC_CAP = 512;      // candidate buffer entries per (row, split)
@@ -41,7 +46,7 @@ constexpr int TC_THREADS = 384;  // warp 0: TMA, 1: MMA, 2: TMEM alloc, 3: idle,
 constexpr int TC_MAX_STAGES = 6;
 
 struct TcParams {
-  int T, N, KC, n_tiles, S, stages, K;
+  int T, N, KC, n_tiles, S, stages, K;   // n_tiles: B tiles of NB items
   const int32_t* users;            // [T] user id of every query row (for the training-row mask), or NULL = row index
   const long long* tr_indptr;      // training CSR (NULL = no mask)
   const int32_t* tr_indices;
@@ -118,13 +123,16 @@ __device__ __forceinline__ void compact_row(float* cv, int32_t* ci, int n, int v
   cnt_out = pos;
 }
 
+template <int NB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmV, const __grid_constant__ TcParams P) {
+  constexpr bool WIDE = NB == TC_NW;   // WIDE: one 256-column accumulator per M tile (tfull / tempty indexed by the M tile);
+                                       // narrow: two stages of 2 x 128 columns (indexed by the tile's parity)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KC = P.KC;
-  const int a_bytes = TC_MT * KC * TC_CHUNK_BYTES, b_stage_bytes = KC * TC_CHUNK_BYTES;
+  const int a_bytes = TC_MT * KC * TC_CHUNK_BYTES, b_chunk_bytes = (NB / 128) * TC_CHUNK_BYTES, b_stage_bytes = KC * b_chunk_bytes;
   uint8_t* sA = smem;
   uint8_t* sB = smem + a_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)P.stages * b_stage_bytes);
@@ -150,7 +158,7 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     mbar_init(a_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull + s, 1);
-      mbar_init(tempty + s, 8 * 32);
+      mbar_init(tempty + s, (WIDE ? 4 : 8) * 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -177,15 +185,15 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
         mbar_wait(empty + st, ph ^ 1u);
         mbar_arrive_expect_tx(full + st, (uint32_t)b_stage_bytes);
         for (int kc = 0; kc < KC; ++kc)
-          tma_load_2d(&tmV, full + st, sB + (size_t)st * b_stage_bytes + (size_t)kc * TC_CHUNK_BYTES, kc * TC_KCH,
-                      (tile_lo + t) * TC_N);
+          tma_load_2d(&tmV, full + st, sB + (size_t)st * b_stage_bytes + (size_t)kc * b_chunk_bytes, kc * TC_KCH,
+                      (tile_lo + t) * NB);
         if (++st == P.stages) { st = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer (one thread)
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_fp16(TC_M, TC_N);
+      const uint32_t idesc = umma_idesc_fp16(TC_M, NB);
       // Descriptors are precomputed: the single issuing thread must spend only a few instructions per MMA (building two
       // 64-bit descriptors from scratch took ~30 dependent instructions = ~3x the 64-cycle MMA itself and starved the
       // tensor pipe).  Within the 256 KB shared window the 14-bit address field never carries, so an offset is one add.
@@ -200,25 +208,28 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
       uint64_t b0 = b00;
       for (int t = 0; t < nt; ++t) {
         const int acc = t & 1;
-        mbar_wait(tempty + acc, ((uint32_t)(t >> 1) & 1u) ^ 1u);
+        if (!WIDE) mbar_wait(tempty + acc, ((uint32_t)(t >> 1) & 1u) ^ 1u);
         mbar_wait(full + st, ph);
         tc_fence_after();
 #pragma unroll
         for (int mt = 0; mt < TC_MT; ++mt) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * (TC_MT * TC_N) + mt * TC_N);
+          if (WIDE) mbar_wait(tempty + mt, ((uint32_t)t & 1u) ^ 1u);   // the epilogue has drained this M tile's previous scores
+          const uint32_t d_tmem = tmem_base + (uint32_t)(WIDE ? mt * NB : acc * (TC_MT * TC_N) + mt * TC_N);
 #pragma unroll
           for (int kc = 0; kc < 4; ++kc) {
             if (kc < KC) {
 #pragma unroll
               for (int k = 0; k < TC_KCH / 16; ++k) {   // UMMA_K = 16 halfs = 32 bytes inside the 128-byte swizzle atom
-                const uint64_t off = (uint64_t)((kc * TC_CHUNK_BYTES + k * 32) >> 4);
-                tc_mma_bf16(d_tmem, a0[mt] + off, b0 + off, idesc, (kc | k) ? 1u : 0u);
+                const uint64_t offa = (uint64_t)((kc * TC_CHUNK_BYTES + k * 32) >> 4);
+                const uint64_t offb = (uint64_t)((kc * b_chunk_bytes + k * 32) >> 4);
+                tc_mma_bf16(d_tmem, a0[mt] + offa, b0 + offb, idesc, (kc | k) ? 1u : 0u);
               }
             }
           }
+          if (WIDE) tc_commit(tfull + mt);   // this M tile's 256 scores per row are ready while the other M tile computes
         }
         tc_commit(empty + st);     // smem stage free once these MMAs have read it
-        tc_commit(tfull + acc);    // accumulator ready for the epilogue
+        if (!WIDE) tc_commit(tfull + acc);    // accumulator ready for the epilogue
         b0 += b_stage_step;
         if (++st == P.stages) { st = 0; ph ^= 1u; b0 = b00; }
       }
@@ -243,17 +254,17 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     bool overflowed = false;
 
     for (int t = 0; t < nt; ++t) {
-      const int acc = t & 1;
-      mbar_wait(tfull + acc, (uint32_t)(t >> 1) & 1u);
+      const int acc = WIDE ? mt : (t & 1);
+      mbar_wait(tfull + acc, WIDE ? ((uint32_t)t & 1u) : ((uint32_t)(t >> 1) & 1u));
       tc_fence_after();
-      const int n0 = (tile_lo + t) * TC_N;
-      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * (TC_MT * TC_N) + mt * TC_N);
+      const int n0 = (tile_lo + t) * NB;
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(WIDE ? mt * NB : acc * (TC_MT * TC_N) + mt * TC_N);
 #pragma unroll 1
-      for (int c = 0; c < TC_N / 32; ++c) {
+      for (int c = 0; c < NB / 32; ++c) {
         uint32_t r[32];
         tc_ld32(tbase + (uint32_t)(c * 32), r);
         tc_wait_ld();
-        if (c == TC_N / 32 - 1) {   // every column of this accumulator stage is in registers: hand it back to the MMA warp
+        if (c == NB / 32 - 1) {   // every column of this accumulator is in registers: hand it back to the MMA warp
           tc_fence_before();
           mbar_arrive(tempty + acc);
         }
@@ -549,12 +560,12 @@ encode_tiled_t get_encode() {
   return fn;
 }
 
-int make_map(CUtensorMap* tm, void* base, long long rows, int Kp) {
+int make_map(CUtensorMap* tm, void* base, long long rows, int Kp, int box_rows = TC_M) {
   encode_tiled_t enc = get_encode();
   CF_CHECK_ARG(enc != nullptr, "cf_topk_tc: cuTensorMapEncodeTiled is not available from the driver");
   const cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
-  const cuuint32_t box[2] = {TC_KCH, TC_M};
+  const cuuint32_t box[2] = {TC_KCH, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -563,7 +574,7 @@ int make_map(CUtensorMap* tm, void* base, long long rows, int Kp) {
 }
 
 struct TcPlan {
-  int Kp, KC, S, stages;
+  int Kp, KC, S, stages, NB;
   long long T_pad, N_pad;
   size_t off_vb, off_qb, off_eps, off_cval, off_cidx, off_ccnt, off_ovf, off_bmax, total;
   size_t smem;
@@ -576,9 +587,11 @@ int plan_tc(const cf_topk_args* a, TcPlan* p) {
   p->Kp = (int)align_up((size_t)a->d + aug, TC_KCH);
   p->KC = p->Kp / TC_KCH;
   CF_CHECK_ARG(p->KC >= 1 && p->KC <= 4, "cf_topk_tc: n_factors up to 254 are served by the tensor path (d=%d)", a->d);
+  p->NB = p->KC <= 2 ? TC_NW : TC_N;     // the wide kernel needs A (64 KB at KC = 2) + two 64 KB stages of B in shared memory
+  if (const char* e = getenv("CF_TC_NARROW")) if (atoi(e) > 0) p->NB = TC_N;   // A/B knob
   p->T_pad = (long long)align_up((size_t)a->T, TC_MT * TC_M);
-  p->N_pad = (long long)align_up((size_t)a->n_items, TC_N);
-  const long long row_tiles = p->T_pad / (TC_MT * TC_M), n_tiles = p->N_pad / TC_N;
+  p->N_pad = (long long)align_up((size_t)a->n_items, p->NB);
+  const long long row_tiles = p->T_pad / (TC_MT * TC_M), n_tiles = p->N_pad / p->NB;
   int S = (int)((cf_num_sms() + row_tiles - 1) / row_tiles);   // just enough item splits to give every SM a CTA: each
                                                                // split restarts its rows' thresholds from -inf
   if (S < 1) S = 1;
@@ -586,7 +599,7 @@ int plan_tc(const cf_topk_args* a, TcPlan* p) {
   if (S > RR_CAP / TC_CAP) S = RR_CAP / TC_CAP;
   if (S > n_tiles) S = (int)n_tiles;
   p->S = S;
-  const size_t a_bytes = (size_t)TC_MT * p->KC * TC_CHUNK_BYTES, b_bytes = (size_t)p->KC * TC_CHUNK_BYTES;
+  const size_t a_bytes = (size_t)TC_MT * p->KC * TC_CHUNK_BYTES, b_bytes = (size_t)p->KC * TC_CHUNK_BYTES * (p->NB / 128);
   int stages = (int)((200 * 1024 - a_bytes) / b_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   CF_CHECK_ARG(stages >= 2, "cf_topk_tc: not enough shared memory for a 2-stage ring");
@@ -665,15 +678,20 @@ extern "C" int cf_topk_tc(const cf_topk_args* a, void* workspace, int64_t worksp
 
   CUtensorMap tmQ, tmV;
   if (int rc = make_map(&tmQ, Qb, p.T_pad, p.Kp)) return rc;
-  if (int rc = make_map(&tmV, Vb, p.N_pad, p.Kp)) return rc;
+  if (int rc = make_map(&tmV, Vb, p.N_pad, p.Kp, p.NB)) return rc;
   TcParams P = {};
-  P.T = a->T; P.N = (int)a->n_items; P.KC = p.KC; P.n_tiles = (int)(p.N_pad / TC_N); P.S = p.S; P.stages = p.stages; P.K = a->K;
+  P.T = a->T; P.N = (int)a->n_items; P.KC = p.KC; P.n_tiles = (int)(p.N_pad / p.NB); P.S = p.S; P.stages = p.stages; P.K = a->K;
   P.users = a->users; P.tr_indptr = (const long long*)a->train.indptr; P.tr_indices = a->train.indices;
   P.eps2 = eps2; P.cand_val = cval; P.cand_idx = cidx; P.cand_cnt = ccnt; P.overflow = ovf;
-  P.dbg_scores = dbg_scores; P.dbg_ld = p.N_pad;
-  CF_CUDA_OK(cudaFuncSetAttribute(k_topk_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  P.dbg_scores = dbg_scores; P.dbg_ld = (long long)align_up((size_t)a->n_items, TC_NW);   // the same stride for both kernels
   dim3 grid((unsigned)(p.T_pad / (TC_MT * TC_M)), (unsigned)p.S);
-  k_topk_tc<<<grid, TC_THREADS, p.smem, stream>>>(tmQ, tmV, P);
+  if (p.NB == TC_NW) {
+    CF_CUDA_OK(cudaFuncSetAttribute(k_topk_tc<TC_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    k_topk_tc<TC_NW><<<grid, TC_THREADS, p.smem, stream>>>(tmQ, tmV, P);
+  } else {
+    CF_CUDA_OK(cudaFuncSetAttribute(k_topk_tc<TC_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    k_topk_tc<TC_N><<<grid, TC_THREADS, p.smem, stream>>>(tmQ, tmV, P);
+  }
 
   RerankParams R = {};
   R.U = a->U; R.V = a->V; R.b = a->b; R.ld = a->ld; R.nvec = a->ld / 4; R.kind = a->kind; R.T = a->T; R.S = p.S; R.K = a->K;

@@ -290,7 +290,7 @@ class FactorEngine(object):
             base = (self._tc_ws.data_ptr() + 1023) // 1024 * 1024
             dbg = None
             if debug_scores:
-                dbg = torch.zeros(T, (self.n_items + 127) // 128 * 128, dtype=torch.float32, device=self.device)
+                dbg = torch.zeros(T, (self.n_items + 255) // 256 * 256, dtype=torch.float32, device=self.device)
             if getattr(self, 'tc_stats', None) is None:
                 self.tc_stats = torch.zeros(4, dtype=torch.int32, device=self.device)   # see cf_b200.h: cf_topk_tc stats
             _lib.check(self.lib.cf_topk_tc(a, base, need, _lib.ptr(dbg), _lib.ptr(self.tc_stats), stream), 'cf_topk_tc')

@@ -52,7 +52,7 @@ class DeviceCSR(object):
     def transpose(self):
         """item -> users CSR (the reference's ``item_posUserList``, sampler_gbpr.py:15)."""
         if self._t is None:
-            self._t = DeviceCSR.from_device_coo(self.indices, self.rows, (self.shape[1], self.shape[0]))
+            self._t = DeviceCSR.from_device_coo(self.indices, self.rows, (self.shape[1], self.shape[0]), self.values)
         return self._t
 
     def select_rows(self, row_ids):

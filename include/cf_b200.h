@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CF_ABI_VERSION 18
+#define CF_ABI_VERSION 19
 
 /* models */
 enum { CF_MODEL_BPR = 0, CF_MODEL_CML = 1, CF_MODEL_GBPR = 2, CF_MODEL_WRMF = 3 };
@@ -331,7 +331,8 @@ int cf_topk_exact(const cf_topk_args* args, void* stream);
  * tcgen05.mma/TMA scoring with a candidate-superset epilogue (the score matrix never leaves the SM), then an exact fp64
  * re-rank of the candidates; rows whose candidate buffer overflows fall back to the exact kernel inside the same call.
  * K <= 200, d <= 254.  `workspace` (device, 1024-byte aligned) must hold cf_topk_tc_workspace_bytes(args) bytes.
- * dbg_scores: NULL, or [T, round_up(n_items,128)] to receive the raw bf16-GEMM scores (tests).
+* dbg_scores: NULL, or [T, round_up(n_items, 256)] to receive the raw fp16-GEMM scores (tests; row stride = n_items rounded
+ * up to 256).
  * stats: NULL, or device int32[4] = {rows that fell back to the exact kernel, total candidates re-ranked,
  * float bits of the largest 2*eps, float bits of max_i |b'_i|}. */
 int64_t cf_topk_tc_workspace_bytes(const cf_topk_args* args);
@@ -432,6 +433,63 @@ typedef struct cf_svd_args {
 } cf_svd_args;
 int cf_svd_grads(const cf_svd_args* args, void* stream);
 int cf_svd_predict_pairs(const cf_svd_args* args, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * The remaining pairwise family: PRIGP (models/pl/models/prigp.py) and CPLR (cplr_u.py).
+ * Both score x_um = <U_u, V_m> + b_m over up to four item slots of a tuple.  cf_tuple_grads is the gradient-only step of
+ * prigp.py:92-137 (tuples [B, 5] = (u, i, j, t, k); bias NOT trained, :134) / cplr_u.py:99-144 (tuples [B, 4] = (u, i, t, j),
+ * coefs [B, 2] = (coef[u, i], coef[u, t])): it ADDS every tuple's row gradients into the dense tables gradU / gradV (and
+ * gradb for CPLR; all zeroed by the caller) and the minibatch loss into *loss (or NULL); cf_apply_dense then applies them
+ * (TF1 Adagrad on the touched rows).  Scoring is CF_SCORE_DOT_BIAS (prigp.py:124-128).
+ * cf_sample_tuples replaces the producer threads of samplers/sampler_prigp.py:22-52 (PRIGP: `train` with its COO rows, `coef`
+ * = the coefficient matrix of prigp.py:83-90 as a CSR with values) and samplers/sampler_uitj_ranking.py:22-38 (CPLR: `coef`
+ * of cplr_u.py:89-97, `collab` = its rows minus the positives, `eligible` = the users with positives, collaborative items
+ * and room for a negative).  Stream position = (seed, epoch, batch0): identical arguments give identical batches.
+ * ------------------------------------------------------------------------------------------------ */
+enum { CF_TUPLE_PRIGP = 0, CF_TUPLE_CPLR = 1 };
+typedef struct cf_tuple_args {
+  const float* U;          /* [n_users, ld] */
+  const float* V;          /* [n_items, ld] */
+  const float* b;          /* [n_items] */
+  int64_t n_users;
+  int64_t n_items;
+  int32_t d;
+  int32_t ld;
+  int32_t model;           /* CF_TUPLE_* */
+  int32_t reserved;
+  const int32_t* tuples;   /* [B, 5] (PRIGP) or [B, 4] (CPLR) */
+  const float* coefs;      /* [B, 2] (CPLR) or NULL */
+  int64_t B;
+  float alpha;
+  float beta;              /* CPLR */
+  float gamma;             /* CPLR */
+  float reg;
+  float* gradU;
+  float* gradV;
+  float* gradb;            /* CPLR; ignored for PRIGP */
+  double* loss;            /* [1] or NULL */
+  int32_t* counters;       /* [4] (flags in [1]) */
+} cf_tuple_args;
+int cf_tuple_grads(const cf_tuple_args* args, void* stream);
+
+typedef struct cf_tuple_sample_args {
+  cf_csr train;            /* user -> positive items (rows[] required for PRIGP) */
+  cf_csr coef;             /* user -> items with a non-zero coefficient, values = the coefficients */
+  cf_csr collab;           /* CPLR: user -> collaborative items (coefficient row minus positives); indptr NULL for PRIGP */
+  const int32_t* eligible; /* CPLR: users that may be drawn */
+  int64_t n_eligible;
+  uint64_t seed;
+  int64_t epoch;
+  int64_t batch0;
+  int32_t n_batches;
+  int32_t B;
+  int32_t model;           /* CF_TUPLE_* */
+  int32_t reserved;
+  int32_t* out_tuples;     /* [n_batches * B, 5 | 4] */
+  float* out_coefs;        /* CPLR: [n_batches * B, 2] */
+  int32_t* flags;
+} cf_tuple_sample_args;
+int cf_sample_tuples(const cf_tuple_sample_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Neighbourhood models and the user-similarity preprocessing of PRIGP / CPLR.

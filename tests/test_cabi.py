@@ -45,7 +45,7 @@ def test_struct_sizes_match_the_compiled_header(tmp_path):
         pytest.skip('no gcc')
     names = dict(cf_step_args=_lib.StepArgs, cf_apply_args=_lib.ApplyArgs, cf_als_args=_lib.AlsArgs, cf_csr=_lib.Csr,
                  cf_svd_args=_lib.SvdArgs, cf_exchange_args=_lib.ExchangeArgs, cf_neighbor_args=_lib.NeighborArgs,
-                 cf_neighbor_score_args=_lib.NeighborScoreArgs,
+                 cf_neighbor_score_args=_lib.NeighborScoreArgs, cf_tuple_args=_lib.TupleArgs, cf_tuple_sample_args=_lib.TupleSampleArgs,
                  cf_sample_args=_lib.SampleArgs, cf_topk_args=_lib.TopkArgs)
     last = {n: c._fields_[-1][0] for n, c in names.items()}
     src = '#include <stdio.h>\n#include <stddef.h>\n#include "cf_b200.h"\nint main(void) {\n'
