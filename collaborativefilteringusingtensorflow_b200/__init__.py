@@ -26,6 +26,12 @@ def __getattr__(name):   # lazy: importing the package must work on a box withou
     if name == 'SVD':
         from .models.basic.models.svd import SVD
         return SVD
+    if name == 'PRIGP':
+        from .models.pl.models.prigp import PRIGP
+        return PRIGP
+    if name == 'CPLR':
+        from .models.pl.models.cplr_u import CPLR
+        return CPLR
     if name == 'ItemCF':
         from .models.basic.models.itemcf import ItemCF
         return ItemCF

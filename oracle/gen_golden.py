@@ -24,6 +24,7 @@ What comes from where
   two shapes) and the numpy oracle's 3-epoch ml-100k run with basic/testsvd.py's hyper-parameters.
 * pop_golden.json      -- the reference's own PopRank (basic/models/pop.py, numpy only) run live on ml-100k fold 1: recommended
   lists + metric values (pins the masked top-N with its tie rule and the metrics end to end against the reference).
+* tuple_golden.npz     -- PRIGP / CPLR graphs (prigp.py:92-137, cplr_u.py:99-144) restated with torch autograd + Adagrad.
 * cf_golden.npz        -- the reference's own ItemCF / UserCF (basic/models/itemcf.py, usercf.py, numpy only) run live on ml-100k
   fold 1, stage by stage (similarities, neighbour choice, scores, lists, metric values).
 * e2e_golden.json      -- oracle-trained ml-100k fold-1 metrics (reference hyper-parameters of testbprmf.py:21-30).
@@ -133,6 +134,69 @@ def gen_pop(bins):
     out['loov10'] = dict(scores=dict(zip(['hr', 'arhr'], [float(x) for x in m.train(1, bins['tra'], bins['tst'])])))
     json.dump(out, open(os.path.join(OUT, 'pop_golden.json'), 'w'))
     print('pop_golden:', out['top10']['scores'], out['loov10']['scores'])
+
+
+def gen_tuples():
+    """PRIGP / CPLR: TensorFlow is not installable, so the TF graphs of prigp.py:92-137 and cplr_u.py:99-144 are restated
+    with torch autograd + torch.optim.Adagrad(initial_accumulator_value=0.1, eps=0) -- an INDEPENDENT restatement of the
+    hand-derived gradients of oracle/steps.py (two steps each; PRIGP leaves item_bias out of the optimizer, :134)."""
+    import torch
+    from oracle.steps import truncated_normal
+    torch.set_num_threads(1)
+    rng = np.random.default_rng(11)
+    out = {}
+
+    def l2(t):
+        return (t * t).sum() / 2
+
+    def nls(x):
+        return -torch.log(torch.sigmoid(x))
+
+    def prigp_loss(P, t, h):
+        U, V, b = P['U'], P['V'], P['b']
+        u, m = U[t[:, 0]], t[:, 1:]
+        x = (u[:, None, :] * V[m]).sum(-1) + b[m]
+        return nls(x[:, 0] - x[:, 1]).sum() + h['alpha'] * nls(x[:, 2] - x[:, 3]).sum() + h['reg'] * (l2(u) + l2(V[m]) + l2(b[m]))
+
+    def cplr_loss(P, t, c, h):
+        U, V, b = P['U'], P['V'], P['b']
+        u, m = U[t[:, 0]], t[:, 1:]
+        x = (u[:, None, :] * V[m]).sum(-1) + b[m]
+        ctj, cij = c[:, 1] + 1.0, c[:, 0] + 1.0
+        cit = cij / ctj
+        return (h['alpha'] * nls(cit * (x[:, 0] - x[:, 1])).sum() + h['beta'] * nls(ctj * (x[:, 1] - x[:, 2])).sum()
+                + h['gamma'] * nls(cij * (x[:, 0] - x[:, 2])).sum() + h['reg'] * (l2(u) + l2(V[m]) + l2(b[m])))
+
+    nu, ni, B = 50, 70, 100
+    for name, d, width, h in (('prigp', 32, 5, dict(lr=0.1, reg=0.1, alpha=10.0)), ('prigp_d20', 12, 5, dict(lr=0.1, reg=0.01, alpha=1.0)),
+                              ('cplr', 32, 4, dict(lr=0.1, reg=0.1, alpha=1.0, beta=0.5, gamma=2.0)),
+                              ('cplr_d20', 12, 4, dict(lr=0.1, reg=0.01, alpha=1.0, beta=1.0, gamma=1.0))):
+        params = dict(U=truncated_normal(rng, (nu, d)), V=truncated_normal(rng, (ni, d)), b=truncated_normal(rng, (ni,)))
+        P = {k: torch.tensor(v, requires_grad=True) for k, v in params.items()}
+        trained = ['U', 'V'] if width == 5 else ['U', 'V', 'b']
+        opt = torch.optim.Adagrad([P[k] for k in trained], lr=h['lr'], initial_accumulator_value=0.1, eps=0)
+        for k, v in params.items():
+            out['%s/init/%s' % (name, k)] = v
+        for s_ in range(2):
+            t = np.concatenate([rng.integers(0, nu, (B, 1)), rng.integers(0, ni, (B, width - 1))], axis=1)
+            if width == 5:
+                t[::7, 3], t[::7, 4] = t[::7, 1], t[::7, 2]        # the sampler's default t = i, k = j (sampler_prigp.py:36)
+            c = (rng.random((B, 2)) * 3).astype(np.float32)
+            c[::5] = 0
+            opt.zero_grad()
+            loss = prigp_loss(P, torch.tensor(t), h) if width == 5 else cplr_loss(P, torch.tensor(t), torch.tensor(c), h)
+            loss.backward()
+            opt.step()
+            out['%s/loss%d' % (name, s_)] = np.float64(loss.item())
+            out['%s/batch%d/tuples' % (name, s_)] = t
+            out['%s/batch%d/coefs' % (name, s_)] = c
+            for k in P:
+                out['%s/step%d/%s' % (name, s_, k)] = P[k].detach().numpy().copy()
+                if k in trained:
+                    out['%s/step%d/acc%s' % (name, s_, k)] = opt.state[P[k]]['sum'].numpy().copy()
+        out[name + '/hyper'] = np.array(json.dumps(h))
+    np.savez_compressed(os.path.join(OUT, 'tuple_golden.npz'), **out)
+    print('tuple_golden.npz:', len(out), 'arrays')
 
 
 def gen_cf(nu, ni, bins):
@@ -481,7 +545,7 @@ def gen_e2e(nu, ni, bins, ref_ranking):
 
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
-    what = set(sys.argv[1:]) or {'ranking', 'ml100k', 'steps', 'sampler', 'e2e', 'rating', 'svd', 'pop', 'cf'}
+    what = set(sys.argv[1:]) or {'ranking', 'ml100k', 'steps', 'sampler', 'e2e', 'rating', 'svd', 'pop', 'cf', 'tuples'}
     ref_ranking, IOUtil, Util = ref_import()
     if 'ranking' in what:
         gen_ranking(ref_ranking)
@@ -491,6 +555,8 @@ if __name__ == '__main__':
         gen_rating()
     if 'svd' in what:
         gen_svd()
+    if 'tuples' in what:
+        gen_tuples()
     if what & {'ml100k', 'sampler', 'e2e', 'pop', 'cf'}:
         nu, ni, bins = gen_ml100k(IOUtil, Util)
         if 'pop' in what:

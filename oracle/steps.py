@@ -8,6 +8,8 @@ Restates (numpy, fp32 forward math) what one ``sess.run(train_op)`` does in the 
 * WRMF   -- /root/reference/src/models/basic/models/wrmf.py:52-75 (loss), :83-88 (Adagrad)
 * MF     -- /root/reference/src/models/basic/models/mf.py:54-78 = WRMF with weight 1 (oracle/rating.py)
 * SVD    -- /root/reference/src/models/basic/models/svd.py:52-80 (loss with the d x d kernel matrix, dense Adagrad on it)
+* PRIGP  -- /root/reference/src/models/pl/models/prigp.py:92-137 (5-tuples; Adagrad on U, V only)
+* CPLR   -- /root/reference/src/models/pl/models/cplr_u.py:99-144 (coefficient-weighted 4-tuples; Adagrad on U, V, b)
 
 TF1 semantics relied on (third-party): gradients are evaluated at the
 pre-update parameters; IndexedSlices of every gather of a variable are concatenated and
@@ -233,3 +235,51 @@ def truncated_normal(rng, shape, mean=0.0, stddev=0.1):
         x[bad] = rng.standard_normal(int(bad.sum()))
         bad = np.abs(x) > 2
     return (mean + stddev * x).astype(F)
+
+
+def prigp_step(U, V, b, accU, accV, uijtk, lr=0.1, reg=0.01, alpha=1.0, optimizer=ADAGRAD):
+    """/root/reference/src/models/pl/models/prigp.py:92-137.  x_um = <U_u, V_m> + b_m;
+    L = sum -log s(x_ui - x_uj) + alpha sum -log s(x_ut - x_uk) + reg (l2(U_u) + l2(V[i,j,t,k]) + l2(b[i,j,t,k]));
+    Adagrad on user_embed and item_embed ONLY (var_list, prigp.py:134): the bias is read, never updated."""
+    u = uijtk[:, 0].astype(np.int64)
+    m = uijtk[:, 1:].astype(np.int64)                           # [B, 4] = (i, j, t, k)
+    Uu, Vm, bm = U[u], V[m], b[m]
+    reg, alpha = F(reg), F(alpha)
+    x = np.sum(Uu[:, None, :] * Vm, axis=2, dtype=F) + bm       # [B, 4]
+    x1, x2 = x[:, 0] - x[:, 1], x[:, 2] - x[:, 3]
+    loss = np.sum(_softplus_neg(x1), dtype=np.float64) + alpha * np.sum(_softplus_neg(x2), dtype=np.float64) + reg * 0.5 * (
+        np.sum(Uu * Uu, dtype=np.float64) + np.sum(Vm * Vm, dtype=np.float64) + np.sum(bm * bm, dtype=np.float64))
+    s1, s2 = _sigm1(x1), alpha * _sigm1(x2)
+    g = np.stack([s1, -s1, s2, -s2], axis=1).astype(F)          # dL/dx_um
+    gU = np.einsum('bm,bmd->bd', g, Vm).astype(F) + reg * Uu
+    gV = g[:, :, None] * Uu[:, None, :] + reg * Vm
+    apply_rows(U, accU, u, gU, lr, optimizer)
+    apply_rows(V, accV, m.reshape(-1), gV.reshape(-1, V.shape[1]), lr, optimizer)
+    return float(loss)
+
+
+def cplr_step(U, V, b, accU, accV, accb, uitj, coefs, lr=0.1, reg=0.01, alpha=1.0, beta=1.0, gamma=1.0, optimizer=ADAGRAD):
+    """/root/reference/src/models/pl/models/cplr_u.py:99-144.  c_ij = coef_ui + 1, c_tj = coef_ut + 1, c_it = c_ij / c_tj;
+    L = alpha sum -log s(c_it (x_ui - x_ut)) + beta sum -log s(c_tj (x_ut - x_uj)) + gamma sum -log s(c_ij (x_ui - x_uj))
+        + reg (l2(U_u) + l2(V[i,t,j]) + l2(b[i,t,j]));  Adagrad on user_embed, item_embed and item_bias (:141)."""
+    u = uitj[:, 0].astype(np.int64)
+    m = uitj[:, 1:].astype(np.int64)                            # [B, 3] = (i, t, j)
+    Uu, Vm, bm = U[u], V[m], b[m]
+    reg, alpha, beta, gamma = F(reg), F(alpha), F(beta), F(gamma)
+    coefs = np.asarray(coefs, dtype=F)
+    cij, ctj = coefs[:, 0] + F(1), coefs[:, 1] + F(1)
+    cit = (cij / ctj).astype(F)
+    x = np.sum(Uu[:, None, :] * Vm, axis=2, dtype=F) + bm
+    z1, z2, z3 = cit * (x[:, 0] - x[:, 1]), ctj * (x[:, 1] - x[:, 2]), cij * (x[:, 0] - x[:, 2])
+    loss = (alpha * np.sum(_softplus_neg(z1), dtype=np.float64) + beta * np.sum(_softplus_neg(z2), dtype=np.float64)
+            + gamma * np.sum(_softplus_neg(z3), dtype=np.float64) + reg * 0.5 * (
+                np.sum(Uu * Uu, dtype=np.float64) + np.sum(Vm * Vm, dtype=np.float64) + np.sum(bm * bm, dtype=np.float64)))
+    a1, a2, a3 = alpha * cit * _sigm1(z1), beta * ctj * _sigm1(z2), gamma * cij * _sigm1(z3)
+    g = np.stack([a1 + a3, a2 - a1, -a2 - a3], axis=1).astype(F)
+    gU = np.einsum('bm,bmd->bd', g, Vm).astype(F) + reg * Uu
+    gV = g[:, :, None] * Uu[:, None, :] + reg * Vm
+    gb = g + reg * bm
+    apply_rows(U, accU, u, gU, lr, optimizer)
+    apply_rows(V, accV, m.reshape(-1), gV.reshape(-1, V.shape[1]), lr, optimizer)
+    apply_rows(b, accb, m.reshape(-1), gb.reshape(-1), lr, optimizer)
+    return float(loss)

@@ -215,6 +215,77 @@ __global__ void __launch_bounds__(192, 1) k_mma(const __grid_constant__ CUtensor
   }
 }
 
+// ---- TMEM read throughput: 8 warps (two per lane quadrant) read 32 lanes x NCOL columns per instruction, back to back
+template <int NCOL>
+__device__ __forceinline__ void ld_cols(uint32_t taddr, uint32_t& sink) {
+  if constexpr (NCOL == 32) {
+    uint32_t r[32];
+    tc_ld32(taddr, r);
+    tc_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) sink ^= r[j];
+  } else if constexpr (NCOL == 16) {
+    uint32_t r[16];
+    tc_ld16(taddr, r);
+    tc_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) sink ^= r[j];
+  } else {
+    uint32_t r[64];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
+        "%25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, "
+        "%49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]),
+          "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]),
+          "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]),
+          "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr)
+        : "memory");
+    tc_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 64; ++j) sink ^= r[j];
+  }
+}
+
+template <int NCOL>
+__global__ void __launch_bounds__(256, 1) k_ldtm(int iters, int nwarps, long long* cycles, uint32_t* out) {
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t base = tmem_slot + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t sink = 0;
+  __syncthreads();
+  const long long c0 = clock64();
+  if (warp < nwarps) {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll 1
+      for (int c = 0; c < 512; c += NCOL) ld_cols<NCOL>(base + (uint32_t)c, sink);
+    }
+  }
+  __syncthreads();
+  const long long c1 = clock64();
+  if (threadIdx.x == 0) cycles[blockIdx.x] = c1 - c0;
+  out[blockIdx.x * 256 + threadIdx.x] = sink;
+  (void)lane;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+  }
+}
+
 typedef CUresult (*encode_tiled_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -281,6 +352,27 @@ int main(int argc, char** argv) {
     }
   printf("TS vs SS accumulators: max |diff| = %.3g (max |value| %.3g); SS vs host fp64: max |diff| = %.3g\n", maxd, maxv, maxh);
 
+  {   // TMEM read throughput (no MMA running): bytes per SM clock
+    uint32_t* dsink;
+    CK(cudaMalloc(&dsink, (size_t)sms * 256 * 4));
+    const int iters = 2000;
+    for (int nw : {1, 4, 8}) {
+      for (int ncol : {16, 32, 64}) {
+        if (ncol == 16) k_ldtm<16><<<sms, 256>>>(iters, nw, dcyc, dsink);
+        else if (ncol == 32) k_ldtm<32><<<sms, 256>>>(iters, nw, dcyc, dsink);
+        else k_ldtm<64><<<sms, 256>>>(iters, nw, dcyc, dsink);
+        CK(cudaDeviceSynchronize());
+        std::vector<long long> cyc(sms);
+        CK(cudaMemcpy(cyc.data(), dcyc, sms * 8, cudaMemcpyDeviceToHost));
+        double avg = 0;
+        for (auto c : cyc) avg += c;
+        avg /= sms;
+        const double bytes = (double)nw * iters * 512.0 * 32 * 4;
+        printf("LDTM 32x32b.x%-2d  %d warps: %7.1f bytes per cycle per SM (%.1f cycles per instruction per warp)\n", ncol, nw, bytes / avg,
+               avg / (iters * (512.0 / ncol)));
+      }
+    }
+  }
   const char* names[6] = {"SS static", "SS + TMA ring", "TS static (A in TMEM)", "TS + TMA ring", "SS N=256 static", "SS N=256 + TMA ring"};
   for (int mode = 0; mode < 12; ++mode) {
     for (int stages : {2, 4, 6}) {

@@ -212,7 +212,8 @@ def test_reference_layout_is_importable_without_a_gpu():
     import importlib
     pkg = 'collaborativefilteringusingtensorflow_b200'
     for mod, names in (('models.pl.models.bprmf', ['BPRMF']), ('models.pl.models.cml', ['CML']), ('models.pl.models.gbprmf', ['GBPRMF']),
-                       ('models.PL.models.bprmf', ['BPRMF']), ('models.basic.models.wrmf', ['WRMF']), ('models.basic.models.mf', ['MF']),
+                       ('models.PL.models.bprmf', ['BPRMF']), ('models.pl.models.prigp', ['PRIGP']), ('models.pl.models.cplr_u', ['CPLR']),
+                       ('samplers.sampler_prigp', ['Sampler']), ('samplers.sampler_uitj_ranking', ['Sampler']), ('models.basic.models.wrmf', ['WRMF']), ('models.basic.models.mf', ['MF']),
                        ('models.basic.models.svd', ['SVD']), ('models.basic.models.pop', ['PopRank']),
                        ('models.basic.models.itemcf', ['ItemCF']), ('models.basic.models.usercf', ['UserCF']),
                        ('samplers.sampler_ranking', ['Sampler']), ('samplers.sampler_uij_ranking', ['Sampler']),
@@ -227,5 +228,5 @@ def test_reference_layout_is_importable_without_a_gpu():
         for n in names:
             assert hasattr(m, n), (mod, n)
     top = importlib.import_module(pkg)
-    for n in ('BPRMF', 'CML', 'GBPRMF', 'WRMF', 'MF', 'SVD', 'PopRank', 'ItemCF', 'UserCF'):
+    for n in ('BPRMF', 'CML', 'GBPRMF', 'WRMF', 'MF', 'SVD', 'PopRank', 'ItemCF', 'UserCF', 'PRIGP', 'CPLR'):
         assert getattr(top, n).__name__ == n
