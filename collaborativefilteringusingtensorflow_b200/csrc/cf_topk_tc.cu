@@ -41,7 +41,7 @@ constexpr int TC_NW = 256;       // items per B tile of the wide kernel: ONE tcg
 constexpr int TC_KCH = 64;       // bf16 elements per 128-byte swizzle chunk
 constexpr int TC_CHUNK_BYTES = TC_M * TC_KCH * 2;   // 16 KB: one TMA box {64, 128}
 constexpr int TC_CAP = 512;      // candidate buffer entries per (row, split)
-constexpr int TC_KMAX = 200;     // largest K served by the tensor path (CAP - 32 >= 2K with room for the 2-eps band)
+constexpr int TC_KMAX = 200;     // largest K served by the tensor path (a compacted row keeps K + the 2-eps band <= CAP - 128)
 constexpr int TC_THREADS = 384;  // warp 0: TMA, 1: MMA, 2: TMEM alloc, 3: idle, 4..11: epilogue
 constexpr int TC_MAX_STAGES = 6;
 
@@ -258,94 +258,77 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     int32_t* ci = P.cand_idx + ((long long)row * P.S + split) * TC_CAP;
     bool overflowed = false;
 
-    // one chunk of 32 scores of this thread's row: make room, test against the row's threshold, append the hits
-    auto process = [&](const uint32_t (&r)[32], int n0c) {
-      if (P.dbg_scores && valid) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) P.dbg_scores[(long long)row * P.dbg_ld + n0c + j] = __uint_as_float(r[j]);
-      }
-      unsigned need = __ballot_sync(0xffffffffu, cnt > TC_CAP - 32);   // make room: a chunk appends at most 32 entries
-      while (need) {
-        const int l = __ffs(need) - 1;
-        need &= need - 1;
-        float* rcv = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(cv), l));
-        int32_t* rci = reinterpret_cast<int32_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(ci), l));
-        const int rn = __shfl_sync(0xffffffffu, cnt, l);
-        const int rver = __shfl_sync(0xffffffffu, ver, l);
-        const float re = __shfl_sync(0xffffffffu, eps2, l);
-        const long long rlo = __shfl_sync(0xffffffffu, tlo, l), rhi = __shfl_sync(0xffffffffu, thi, l);
-        float nth;
-        int ncnt;
-        compact_row(rcv, rci, rn, rver, P.K, re, P.tr_indices, rlo, rhi, lane, nth, ncnt);
-        if (lane == l) {
-          theta = nth;
-          cnt = ncnt;
-          ver = ncnt;
-          if (ncnt > TC_CAP - 64) {  // too many items within 2 eps of the K-th best: give this row to the exact kernel
-            overflowed = true;
-            theta = INFINITY;
-            cnt = 0;
-            ver = 0;
-          }
-        }
-      }
-      // Four groups of 8 columns: group maxima first (FMNMX3 trees); only a group whose maximum reaches the row's
-      // threshold is scanned value by value.  Late in the sweep hits are rare, so a chunk costs ~20 instructions.
-      const float thr = theta - eps2;
-      float g[4];
-#pragma unroll
-      for (int gq = 0; gq < 4; ++gq) {
-        const float a0 = fmaxf(fmaxf(__uint_as_float(r[8 * gq]), __uint_as_float(r[8 * gq + 1])), __uint_as_float(r[8 * gq + 2]));
-        const float a1 = fmaxf(fmaxf(__uint_as_float(r[8 * gq + 3]), __uint_as_float(r[8 * gq + 4])), __uint_as_float(r[8 * gq + 5]));
-        g[gq] = fmaxf(fmaxf(a0, a1), fmaxf(__uint_as_float(r[8 * gq + 6]), __uint_as_float(r[8 * gq + 7])));
-      }
-      const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
-      if (m >= thr) {
-#pragma unroll
-        for (int gq = 0; gq < 4; ++gq) {
-          if (g[gq] >= thr) {
-#pragma unroll
-            for (int j = 8 * gq; j < 8 * gq + 8; ++j) {
-              const float sv = __uint_as_float(r[j]);
-              if (sv >= thr) {
-                const int item = n0c + j;
-                if (item < P.N) {   // (training items are dropped at the next compaction / by the re-rank)
-                  cv[cnt] = sv;
-                  ci[cnt] = item;
-                  ++cnt;
-                }
-              }
-            }
-          }
-        }
-      }
-    };
-
-    constexpr int NC = NB / 32;   // chunks of 32 columns per accumulator (even)
+    // The sweep costs instructions, not bandwidth: ncu showed ~110 warp instructions per 32 scores in the first version
+    // (room check, four group maxima, four reconvergence points per chunk) and the epilogue warps busy 80 % of the time,
+    // with instruction-fetch stalls on top.  Now: ONE room check per 128 columns (a block appends at most 128 entries per
+    // row), per chunk a single FMNMX3 tree over the 32 scores and one compare; the scan + append of a chunk that holds a
+    // hit is the rare path.
+    const bool dbg = P.dbg_scores != nullptr;
     for (int t = 0; t < nt; ++t) {
       const int acc = WIDE ? mt : (t & 1);
       mbar_wait(tfull + acc, WIDE ? ((uint32_t)t & 1u) : ((uint32_t)(t >> 1) & 1u));
       tc_fence_after();
       const int n0 = (tile_lo + t) * NB;
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(WIDE ? mt * NB : acc * (TC_MT * TC_N) + mt * TC_N);
-      // Double-buffered TMEM reads: a tcgen05.ld + wait::ld pair alone costs ~118 cycles per 32 columns (measured,
-      // tests/micro/mma_micro.cu), as much as the processing of the chunk -- the next chunk is in flight while this one
-      // is tested.  (wait::ld waits for every outstanding load of the thread, so the order is wait -> issue next -> process.)
-      uint32_t ra[32], rb[32];
-      tc_ld32(tbase, ra);
 #pragma unroll 1
-      for (int c = 0; c < NC; c += 2) {
-        tc_wait_ld();
-        tc_ld32(tbase + (uint32_t)((c + 1) * 32), rb);
-        process(ra, n0 + c * 32);
-        tc_wait_ld();
-        if (c + 2 < NC) {
-          tc_ld32(tbase + (uint32_t)((c + 2) * 32), ra);
-        } else {                   // every column of this accumulator is in registers: hand it back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(tempty + acc);
+      for (int hb = 0; hb < NB / 128; ++hb) {
+        unsigned need = __ballot_sync(0xffffffffu, cnt > TC_CAP - 128);   // make room for the next 128 columns
+        while (need) {
+          const int l = __ffs(need) - 1;
+          need &= need - 1;
+          float* rcv = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(cv), l));
+          int32_t* rci = reinterpret_cast<int32_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(ci), l));
+          const int rn = __shfl_sync(0xffffffffu, cnt, l);
+          const int rver = __shfl_sync(0xffffffffu, ver, l);
+          const float re = __shfl_sync(0xffffffffu, eps2, l);
+          const long long rlo = __shfl_sync(0xffffffffu, tlo, l), rhi = __shfl_sync(0xffffffffu, thi, l);
+          float nth;
+          int ncnt;
+          compact_row(rcv, rci, rn, rver, P.K, re, P.tr_indices, rlo, rhi, lane, nth, ncnt);
+          if (lane == l) {
+            theta = nth;
+            cnt = ncnt;
+            ver = ncnt;
+            if (ncnt > TC_CAP - 128) {  // too many items within 2 eps of the K-th best: give this row to the exact kernel
+              overflowed = true;
+              theta = INFINITY;
+              cnt = 0;
+              ver = 0;
+            }
+          }
         }
-        process(rb, n0 + (c + 1) * 32);
+        const float thr = theta - eps2;   // (theta only moves at a compaction)
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c = hb * 4 + cc;
+          uint32_t r[32];
+          tc_ld32(tbase + (uint32_t)(c * 32), r);
+          tc_wait_ld();
+          if (c == NB / 32 - 1) {   // every column of this accumulator is in registers: hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(tempty + acc);
+          }
+          if (dbg && valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) P.dbg_scores[(long long)row * P.dbg_ld + n0 + c * 32 + j] = __uint_as_float(r[j]);
+          }
+          float m = fmaxf(fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])), __uint_as_float(r[2]));
+#pragma unroll
+          for (int j = 3; j + 1 < 32; j += 2) m = fmaxf(fmaxf(m, __uint_as_float(r[j])), __uint_as_float(r[j + 1]));
+          m = fmaxf(m, __uint_as_float(r[31]));
+          if (m >= thr) {   // rare: at least one of the 32 scores reaches the row's threshold
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float sv = __uint_as_float(r[j]);
+              const int item = n0 + c * 32 + j;
+              if (sv >= thr && item < P.N) {   // (training items are dropped at the next compaction / by the re-rank)
+                cv[cnt] = sv;
+                ci[cnt] = item;
+                ++cnt;
+              }
+            }
+          }
+        }
       }
     }
     if (valid) {

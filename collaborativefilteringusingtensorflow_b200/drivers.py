@@ -1,7 +1,8 @@
 """The reference's experiment drivers for the hot-path models, as one module.
 
-Mirrors reference src/models/pl/testbprmf.py:19-125, testcml.py:19-102, testgbprmf.py:19-113,
-src/models/basic/testwrmf.py:19-96 and (rating prediction, `mf` / `svd`) src/models/basic/testmf.py:14-78, testsvd.py:14-79: the same module-level hyper-parameters, the same per-fold worker (load
+Mirrors reference src/models/pl/testbprmf.py:19-125, testcml.py:19-102, testgbprmf.py:19-113, testprigp.py:17-109,
+testcplr_u.py:17-126, src/models/basic/testwrmf.py:19-96, testicf.py:14-115, testucf.py:14-116 and (rating prediction, `mf` /
+`svd`) src/models/basic/testmf.py:14-78, testsvd.py:14-79: the same module-level hyper-parameters, the same per-fold worker (load
 ``ratings__<fold>_tra.txt`` / ``_tst.txt``, binarise with ``rating > 3``, build the sampler and the model, train, print the
 fold's scores) and the same ``ave`` / ``std`` summary.  The reference wraps every fold in a ``multiprocessing.Pool`` only
 because ``tf.get_variable`` names collide (testbprmf.py:114-117); here folds run in-process.
@@ -13,12 +14,16 @@ import argparse
 import numpy as np
 from scipy.sparse import lil_matrix
 
+from .models.basic.models.itemcf import ItemCF
 from .models.basic.models.mf import MF
 from .models.basic.models.svd import SVD
+from .models.basic.models.usercf import UserCF
 from .models.basic.models.wrmf import WRMF
 from .models.pl.models.bprmf import BPRMF
 from .models.pl.models.cml import CML
+from .models.pl.models.cplr_u import CPLR
 from .models.pl.models.gbprmf import GBPRMF
+from .models.pl.models.prigp import PRIGP
 from .samplers import sampler_gbpr, sampler_ranking, sampler_rating
 from .utils.IOUtil import loadSparseR
 from .utils.Util import matBinarize
@@ -34,6 +39,10 @@ HYPER = {
                 negSample=5),                                                                                     # testcml.py:22-34
     'gbprmf': dict(gsize=1, rho=.4, reg=.01, topN=100, n_factors=100, batch_size=100, negSample=5),               # testgbprmf.py:23-32
     'wrmf': dict(weight=2., reg=.1, topN=10, negRatio=1, n_factors=100, batch_size=100),                          # testwrmf.py:22-30
+    'prigp': dict(topK=5, alpha=10, reg=.1, topN=100, n_factors=100, batch_size=1000),                            # testprigp.py:21-31
+    'cplr': dict(topK=200, reg=.1, topN=100, alpha=1., beta=1., gamma=1., n_factors=100, batch_size=100),         # testcplr_u.py:21-33
+    'itemcf': dict(topK=5, topN=100),                                                                             # testicf.py:18-22
+    'usercf': dict(topK=5, topN=100),                                                                             # testucf.py:18-22
 }
 
 
@@ -95,6 +104,20 @@ def worker(model_name, fold, n_users, n_items, dataset_dir, max_iter=None, seed=
         sampler = sampler_rating.Sampler(trasR, h['negRatio'], h['batch_size'], seed=seed or 0)
         model = WRMF(n_users, n_items, h['topN'], split_method, eval_metrics, h['weight'], h['reg'], h['n_factors'],
                      h['batch_size'], **it, **kw)
+    elif model_name in ('itemcf', 'usercf'):      # testicf.py:37-38: no sampler, no epochs
+        model = (ItemCF if model_name == 'itemcf' else UserCF)(n_users, n_items, h['topK'], h['topN'], split_method, eval_metrics)
+        scores = model.train(fold + 1, trasR, tstsR)
+        print(dataset_dir.split('/')[-2] + '@%d:' % (fold + 1),
+              ','.join(['%s' % m for m in eval_metrics]) + '@%d=' % h['topN'] + ','.join(['%.6f' % s for s in scores]))
+        return scores
+    elif model_name == 'prigp':                   # testprigp.py:44-48: the model builds its own sampler
+        sampler = None
+        model = PRIGP(n_users, n_items, h['topK'], h['topN'], split_method, eval_metrics, h['alpha'], h['reg'], h['n_factors'],
+                      h['batch_size'], **it, **kw)
+    elif model_name == 'cplr':                    # testcplr_u.py:49-53
+        sampler = None
+        model = CPLR(n_users, n_items, h['topK'], h['topN'], split_method, eval_metrics, h['alpha'], h['beta'], h['gamma'], h['reg'],
+                     h['n_factors'], h['batch_size'], **it, **kw)
     else:
         raise ValueError('unknown model %r' % model_name)
     scores = model.train(fold + 1, trasR, tstsR, sampler)

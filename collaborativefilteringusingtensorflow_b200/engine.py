@@ -348,8 +348,14 @@ class FactorEngine(object):
         a.ldx, a.ldy = int(X.stride(0)), int(Y.stride(0))
         a.indptr, a.indices = _lib.ptr(csr.indptr), _lib.ptr(csr.indices)
         a.weight, a.reg = float(self.hyper['weight']), float(self.hyper['reg'])
+        # with a workspace the rows with few observed columns take the low-rank (Woodbury) path of cf_als.cu
+        need = int(self.lib.cf_als_workspace_bytes(int(Y.shape[0])))
+        if getattr(self, '_als_ws', None) is None or self._als_ws.numel() < need + 1024:
+            self._als_ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+        a.workspace = (self._als_ws.data_ptr() + 1023) // 1024 * 1024
+        a.workspace_bytes = need
         _lib.check(self.lib.cf_als_solve_rows(a, _lib.ptr(G), torch.cuda.current_stream(self.device).cuda_stream), 'cf_als_solve_rows')
-        self.launches += 1
+        self.launches += 4
 
     def predict_pairs(self, pairs):
         """Scores of explicit (user, item) rows (``__predict`` of mf.py:66-72 fed with ``tst_tuple[:, :-1]``): float32

@@ -375,7 +375,9 @@ int cf_als_half_sweep(const cf_als_args* args, void* stream);
 /* The two stages of the half-sweep on their own, for the multi-GPU sweep (rows of X sharded, Y replicated):
  * cf_als_gram ACCUMULATES Y^T Y of the given rows into G[128, 128] (row stride 128; the caller zeroes G, every rank
  * passes its slice of Y and the partial Grams are all-reduced); cf_als_solve_rows solves args->X's rows from the
- * complete Gram (args->workspace is not used). */
+ * complete Gram.  args->workspace is optional there: with cf_als_workspace_bytes(n_y) bytes (and weight > 1) the rows with
+ * at most 64 observed columns are solved by the low-rank update  x = p - Z_u^T (I / (weight - 1) + Y_u Z_u^T)^-1 Y_u p,
+ * Z = Y (G + reg I)^-1, p = weight * sum z  (an n_u x n_u Cholesky instead of a 128 x 128 one), as cf_als_half_sweep does. */
 int cf_als_gram(const float* Y, int64_t n_y, int32_t d, int32_t ldy, float* G, void* workspace, int64_t workspace_bytes,
                 void* stream);
 int cf_als_solve_rows(const cf_als_args* args, const float* G, void* stream);

@@ -84,3 +84,37 @@ def test_row_sharded_sweep_equals_whole_sweep(P):
         a.engine.als_half_sweep('items', csr.transpose())
         DistributedALS(c.engine, csr, csr.transpose()).half_sweep('items')
         np.testing.assert_allclose(c.state_dict()['V'].cpu().numpy(), a.state_dict()['V'].cpu().numpy(), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('d,weight', [(128, 3.0), (40, 11.0)])
+def test_short_rows_low_rank_path_and_long_rows_full_solve_in_one_sweep(d, weight):
+    """Rows with at most 64 observed columns take the low-rank (Woodbury) update, longer ones the 128 x 128 Cholesky; both must
+    equal the dense float64 solve of the same normal equations (and CF_ALS_DIRECT=1, the full solve for every row)."""
+    import os
+    from scipy.sparse import lil_matrix
+    from collaborativefilteringusingtensorflow_b200 import WRMF
+    from collaborativefilteringusingtensorflow_b200.sparse import DeviceCSR
+    rng = np.random.default_rng(d)
+    nu, ni, reg = 150, 400, 0.25
+    R = lil_matrix((nu, ni), dtype=np.float32)
+    for u in range(nu):
+        k = [0, 1, 2, 63, 64, 65, 66, 200][u % 8] if u < 64 else int(rng.integers(0, 130))
+        if k:
+            R[u, rng.choice(ni, size=k, replace=False)] = 1
+    csr = None
+    outs = {}
+    for mode in ('mixed', 'direct'):
+        if mode == 'direct':
+            os.environ['CF_ALS_DIRECT'] = '1'
+        try:
+            m = WRMF(nu, ni, weight=weight, reg=reg, n_factors=d, verbose=False, seed=1, solver='als')
+            csr = DeviceCSR.from_scipy(R, m.device)
+            V0 = m.state_dict()['V'].cpu().numpy().astype(np.float64)
+            m.engine.als_half_sweep('users', csr)
+            outs[mode] = m.state_dict()['U'].cpu().numpy()
+        finally:
+            os.environ.pop('CF_ALS_DIRECT', None)
+    want = orc.half_sweep(V0, R.rows, weight, reg)
+    for mode in outs:
+        np.testing.assert_allclose(outs[mode], want, rtol=2e-3, atol=2e-4 * np.abs(want).max(), err_msg=mode)
+    assert np.abs(outs['mixed'][np.diff(R.tocsr().indptr) == 0]).max() == 0.0       # nothing observed: x = 0
