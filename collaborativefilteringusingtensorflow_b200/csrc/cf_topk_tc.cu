@@ -83,12 +83,35 @@ __device__ __forceinline__ void compact_row(float* cv, int32_t* ci, int n, int v
     id[i] = e < n ? __ldcg(ci + e) : -1;
   }
   if (thi > tlo) {
+    // EPL binary searches per lane, advanced TOGETHER one probe at a time: the probes of a round are independent loads
+    // (one search after the other is a chain of ~7 dependent global loads per entry: 16 x 7 round trips per compaction,
+    // which was most of the sweep on a 500 k-item catalogue)
+    int slo[EPL], shi[EPL];
+    const int len = (int)(thi - tlo);
 #pragma unroll
     for (int i = 0; i < EPL; ++i) {
       const int e = lane + 32 * i;
-      if (e >= ver && e < n && csr_contains(tr_indices, tlo, thi, id[i])) {   // a training item: drop it
-        v[i] = __uint_as_float(0xffffffffu);
-        id[i] = -1;
+      const bool chk = e >= ver && e < n;
+      slo[i] = 0;
+      shi[i] = chk ? len : 0;
+    }
+    const int* row = tr_indices + tlo;
+    for (int span = len; span > 0; span >>= 1) {     // ceil(log2(len + 1)) rounds empty every interval
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) {
+        if (slo[i] < shi[i]) {
+          const int mid = (slo[i] + shi[i]) >> 1;
+          const int w = __ldg(row + mid);
+          if (w == id[i]) {                          // a training item: drop it
+            v[i] = __uint_as_float(0xffffffffu);
+            id[i] = -1;
+            shi[i] = slo[i];
+          } else if (w < id[i]) {
+            slo[i] = mid + 1;
+          } else {
+            shi[i] = mid;
+          }
+        }
       }
     }
   }
@@ -589,8 +612,12 @@ int plan_tc(const cf_topk_args* a, TcPlan* p) {
   p->Kp = (int)align_up((size_t)a->d + aug, TC_KCH);
   p->KC = p->Kp / TC_KCH;
   CF_CHECK_ARG(p->KC >= 1 && p->KC <= 4, "cf_topk_tc: n_factors up to 254 are served by the tensor path (d=%d)", a->d);
-  p->NB = p->KC <= 2 ? TC_NW : TC_N;     // the wide kernel needs A (64 KB at KC = 2) + two 64 KB stages of B in shared memory
-  if (const char* e = getenv("CF_TC_NARROW")) if (atoi(e) > 0) p->NB = TC_N;   // A/B knob
+  // The wide kernel (needs KC <= 2: A 64 KB + two 64 KB stages of B) issues 1.4x the flops per MMA cycle, but with one accumulator per
+  // M tile the epilogue of an M tile must finish inside the OTHER M tile's MMA time, and under MMA load a tcgen05.ld of 32 columns
+  // takes ~350 cycles (TMEM accumulate traffic crowds the reads out; 118 cycles idle): 8 chunks = 2800 > 1400.  Measured end to
+  // end it ties with the narrow kernel (329 k vs 335 k users/s on 10 M items), so it is opt-in: CF_TC_WIDE=1.
+  p->NB = TC_N;
+  if (const char* e = getenv("CF_TC_WIDE")) if (atoi(e) > 0 && p->KC <= 2) p->NB = TC_NW;
   p->T_pad = (long long)align_up((size_t)a->T, TC_MT * TC_M);
   p->N_pad = (long long)align_up((size_t)a->n_items, p->NB);
   const long long row_tiles = p->T_pad / (TC_MT * TC_M), n_tiles = p->N_pad / p->NB;

@@ -81,3 +81,25 @@ def test_values_outside_fp16_range_fall_back_to_exact():
     ei = m.engine.topk(users, K, None, method='exact')
     ti = m.engine.topk(users, K, None, method='tensor')
     assert torch.equal(ei, ti) and int(m.engine.tc_stats[0].item()) == nu
+
+
+def test_wide_kernel_equals_the_exact_kernel(monkeypatch):
+    """CF_TC_WIDE=1: the 256-item-tile kernel (one N = 256 tcgen05.mma per tile, one accumulator per M tile) returns the
+    same lists and fp64 scores as the exact kernel (the default for every d is the 128-item-tile kernel)."""
+    import numpy as np
+    import torch
+    from scipy.sparse import lil_matrix
+    from collaborativefilteringusingtensorflow_b200 import BPRMF, CML
+    from collaborativefilteringusingtensorflow_b200.sparse import DeviceCSR
+    monkeypatch.setenv('CF_TC_WIDE', '1')
+    rng = np.random.default_rng(3)
+    for cls, nu, ni, d, K in ((BPRMF, 300, 5000, 128, 100), (CML, 257, 3001, 64, 37), (BPRMF, 64, 777, 20, 200)):
+        m = cls(nu, ni, n_factors=d, verbose=False, seed=2)
+        tra = lil_matrix((nu, ni), dtype=np.float32)
+        for u in range(nu):
+            tra[u, rng.choice(ni, 25, replace=False)] = 1
+        csr = DeviceCSR.from_scipy(tra, m.device)
+        users = torch.arange(nu, dtype=torch.int32, device=m.device)
+        ti, tv = m.engine.topk(users, K, csr, return_values=True, method='tensor')
+        ei, ev = m.engine.topk(users, K, csr, return_values=True, method='exact')
+        assert torch.equal(ti, ei) and torch.equal(tv, ev)

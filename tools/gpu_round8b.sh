@@ -1,0 +1,16 @@
+#!/bin/bash
+tag=${1:-run}
+mkdir -p gpurun_out
+( timeout 600 python -m pytest tests/test_gpu_topk_tensor.py tests/test_gpu_full_size.py -x -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" )
+tail -6 gpurun_out/${tag}_pytest.log
+( timeout 600 python bench.py --steps 10 --warmup 3 --no-other-configs --no-cpu-baseline > gpurun_out/${tag}_bench_N1.json 2> gpurun_out/${tag}_bench_N1.err; echo "bench N1 rc=$?" )
+python - <<PY
+import json
+for f in ('gpurun_out/${tag}_bench_N1.json',):
+    try:
+        j=json.loads(open(f).read().strip().splitlines()[-1]); t=j['topk']; c=t['c5_catalogue']
+        print(f, '500k: %.0f users/s (%.3f)  10M: %.0f users/s (%.3f burst, %.3f sustained) fb %d/%d' % (t['value'], t['frac_of_tensor_peak'], c['value'], c['frac_of_tensor_peak'], c['frac_of_sustained_tensor_peak'], t['fallback_rows'], c['fallback_rows']))
+    except Exception as e: print(f, 'failed', e)
+PY
+python tools/als_prof.py > gpurun_out/${tag}_als_plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_als_ -c 8 -o gpurun_out/${tag}_als python tools/als_prof.py > gpurun_out/${tag}_als_ncu.log 2>&1
+cat gpurun_out/${tag}_als_plain.log | tail -2
