@@ -134,8 +134,6 @@ struct SolveParams {
   long long n_x;
   int d, ldx, ldy;
   float weight, reg;
-  int skip_le;          // rows with at most this many observed columns are solved by k_als_woodbury instead (-1: none)
-  const float* Z;       // [n_y, 128] = Y (G + reg I)^-1 (Woodbury path)
 };
 
 // one CTA per row of X; A (d x d, fp32, leading dimension d + 1) lives in shared memory
@@ -234,7 +232,6 @@ __global__ void __launch_bounds__(256, 2) k_als_solve_blocked(const __grid_const
   const bool lower = ty >= tx;
   const int d = P.d;
   for (long long u = blockIdx.x; u < P.n_x; u += gridDim.x) {
-    if (P.indptr[u + 1] - P.indptr[u] <= P.skip_le) continue;   // block-uniform: a short row, solved by the low-rank kernel
     float a[BS][BS];
     if (lower) {
 #pragma unroll
@@ -384,176 +381,627 @@ __global__ void __launch_bounds__(256, 2) k_als_solve_blocked(const __grid_const
   }
 }
 
-// ---- low-rank (Woodbury) path for rows with few observed columns.  Measured on a configs[3]-shaped slice (1 M rows, 50 M
-// interactions, median 21 per row): the register-blocked solve above spends ~260 k cycles per row, most of them in the
-// 128 x 128 Cholesky whatever the row's length.  But A_u = G0 + c Y_u^T Y_u (G0 = Y^T Y + reg I, c = weight - 1) is a rank-n_u
-// update of a matrix that is the SAME for every row, so with Z = Y G0^-1 (one GEMM per half-sweep)
-//     x_u = p - Z_u^T (I / c + Y_u Z_u^T)^-1 (Y_u p),   p = weight * sum_a z_a
-// needs an n_u x n_u Cholesky instead: 9 k flops at the median row instead of 700 k.
-constexpr int WB_N = 64;      // longest row solved this way (shared memory: two [64][129] row tiles + S[64][65])
+// ---- the whitened path (weight > 1).  With G0 = Y^T Y + reg I = L L^T and W = Y L^-T (w_a = L^-1 y_a, one dense pass per
+// half-sweep) the normal equations of row u with observed set P_u (n = |P_u|, c = weight - 1) become, for x = L^-T xt,
+//     (I + c W_u^T W_u) xt = weight * W_u^T 1                                                     (128 x 128, n > 128)
+//     xt = W_u^T (weight * 1 - t),   (I / c + W_u W_u^T) t = weight * (W_u W_u^T) 1              (n x n,  n <= 128)
+// Both matrices are the identity plus a small positive term (sum_a |w_a|^2 over the WHOLE catalogue is <= 128), so fp32
+// Cholesky is comfortable, and a row costs an n x n solve instead of a 128 x 128 one when it is short -- which is most
+// rows (configs[3]: median 21 observed columns).  Three kernels share the rows by length:
+//   k_als_small<16>, <32>   n <= 16 / 17..32: one WARP per row, the n x n system in registers (one row per lane), shuffles
+//   k_als_rows_tc           n > 32: one CTA per row; the Gram (W_u W_u^T for n <= 128, W_u^T W_u in 64-row chunks beyond)
+//                           runs on tcgen05 (bf16 hi/lo split, 3 MMAs per k-step, fp32 accumulator in TMEM) from operand
+//                           tiles the CTA writes itself in the SWIZZLE_128B K-major layout; then a register-blocked
+//                           Cholesky (8 x 8 blocks, two barriers per block column, right-hand side carried as an extra
+//                           row so the forward substitution is free) and a block back-substitution out of registers.
+// X = Xt L^-1 is one more dense pass (k_als_mul).
+constexpr int SM_LD = 132;    // row stride of a gathered fp32 row tile (16-byte aligned rows, conflict-free 128-bit access)
 
-// G0^-1 in fp64 by Gauss-Jordan without pivoting (G0 is SPD); one block, the [128][256] tableau lives in global scratch
-__global__ void __launch_bounds__(1024) k_als_inverse(const float* __restrict__ G, float reg, int d, double* __restrict__ W,
-                                                       float* __restrict__ Ginv) {
+// G0 = G + reg I (identity on the padding) -> L (fp64, in shared memory) -> L^-1 and its transpose in fp32
+__global__ void __launch_bounds__(1024) k_als_prep(const float* __restrict__ G, float reg, int d, float* __restrict__ Linv,
+                                                    float* __restrict__ LinvT) {
+  extern __shared__ double sL[];                       // [128][129]
+  constexpr int LD = ALS_D + 1;
   const int tid = threadIdx.x;
-  for (int e = tid; e < ALS_D * 2 * ALS_D; e += blockDim.x) {
-    const int i = e / (2 * ALS_D), j = e % (2 * ALS_D);
-    double v;
-    if (j < ALS_D) v = (i < d && j < d) ? (double)G[i * ALS_D + j] + (i == j ? (double)reg : 0.0) : (i == j ? 1.0 : 0.0);
-    else v = (j - ALS_D == i) ? 1.0 : 0.0;
-    W[e] = v;
+  for (int e = tid; e < ALS_D * ALS_D; e += blockDim.x) {
+    const int i = e >> 7, j = e & 127;
+    sL[i * LD + j] = (i < d && j < d) ? (double)G[e] + (i == j ? (double)reg : 0.0) : (i == j ? 1.0 : 0.0);
   }
   __syncthreads();
-  __shared__ double s_col[ALS_D];
-  __shared__ double s_piv;
-  for (int k = 0; k < ALS_D; ++k) {
-    if (tid == 0) s_piv = 1.0 / W[k * 2 * ALS_D + k];
+  for (int k = 0; k < ALS_D; ++k) {                    // right-looking Cholesky, lower triangle
+    if (tid == 0) sL[k * LD + k] = sqrt(fmax(sL[k * LD + k], 1e-300));
     __syncthreads();
-    for (int j = tid; j < 2 * ALS_D; j += blockDim.x) W[k * 2 * ALS_D + j] *= s_piv;
-    if (tid < ALS_D) s_col[tid] = W[tid * 2 * ALS_D + k];
+    const double inv = 1.0 / sL[k * LD + k];
+    for (int i = k + 1 + tid; i < ALS_D; i += blockDim.x) sL[i * LD + k] *= inv;
     __syncthreads();
-    for (int e = tid; e < ALS_D * 2 * ALS_D; e += blockDim.x) {
-      const int i = e / (2 * ALS_D), j = e % (2 * ALS_D);
-      if (i != k) W[e] -= s_col[i] * W[k * 2 * ALS_D + j];
+    const int m = ALS_D - 1 - k;
+    for (int e = tid; e < m * m; e += blockDim.x) {
+      const int i = k + 1 + e / m, j = k + 1 + e % m;
+      if (j <= i) sL[i * LD + j] -= sL[i * LD + k] * sL[j * LD + k];
     }
     __syncthreads();
   }
+  // in-place inverse of the lower triangle, last column first: X[j+1:, j] = -X[j+1:, j+1:] L[j+1:, j] / L[j][j]
+  for (int j = ALS_D - 1; j >= 0; --j) {
+    double x = 0.0;
+    const int i = tid;
+    if (i > j && i < ALS_D)
+      for (int k = j + 1; k <= i; ++k) x += sL[i * LD + k] * sL[k * LD + j];
+    __syncthreads();
+    const double dj = 1.0 / sL[j * LD + j];
+    __syncthreads();
+    if (i > j && i < ALS_D) sL[i * LD + j] = -x * dj;
+    if (i == j) sL[j * LD + j] = dj;
+    __syncthreads();
+  }
   for (int e = tid; e < ALS_D * ALS_D; e += blockDim.x) {
-    const int i = e / ALS_D, j = e % ALS_D;
-    Ginv[e] = (i < d && j < d) ? (float)W[i * 2 * ALS_D + ALS_D + j] : 0.f;
+    const int i = e >> 7, j = e & 127;
+    const float v = j <= i ? (float)sL[i * LD + j] : 0.f;
+    Linv[i * ALS_D + j] = v;
+    LinvT[j * ALS_D + i] = v;
   }
 }
 
-// Z[n, 128] = Y[n, :d] Ginv[:d, :128]  (fp32; 32 rows per block, Ginv resident in shared memory)
-__global__ void __launch_bounds__(256) k_als_z(const float* __restrict__ Y, long long n, int d, int ldy, const float* __restrict__ Ginv,
-                                               float* __restrict__ Z) {
+// out[r, :ncols] = in[r, :d] M  (M [128][128] fp32 resident in shared memory; 32 rows per block and pass; in == out is fine:
+// a block reads its 32 rows completely before it writes them)
+__global__ void __launch_bounds__(256) k_als_mul(const float* in, long long n, int d, int ld_in, const float* __restrict__ M,
+                                                 float* out, int ld_out, int ncols) {
   extern __shared__ float sm[];
-  float* Gs = sm;                    // [128][128]
-  float* Ys = Gs + ALS_D * ALS_D;    // [32][128]
-  for (int e = threadIdx.x; e < ALS_D * ALS_D; e += blockDim.x) Gs[e] = Ginv[e];
+  float* Ms = sm;                     // [128][128]
+  float* Ys = Ms + ALS_D * ALS_D;     // [32][SM_LD]
+  for (int e = threadIdx.x; e < ALS_D * ALS_D; e += blockDim.x) Ms[e] = M[e];
   const int col = threadIdx.x & 127, half = threadIdx.x >> 7;     // thread: one column, 16 of the 32 rows
+  const int d4 = (d + 3) & ~3;
   for (long long r0 = (long long)blockIdx.x * 32; r0 < n; r0 += (long long)gridDim.x * 32) {
     __syncthreads();
     for (int e = threadIdx.x; e < 32 * ALS_D; e += blockDim.x) {
-      const long long r = r0 + e / ALS_D;
-      const int k = e % ALS_D;
-      Ys[e] = (r < n && k < d) ? Y[r * ldy + k] : 0.f;
+      const long long r = r0 + (e >> 7);
+      const int k = e & 127;
+      Ys[(e >> 7) * SM_LD + k] = (r < n && k < d) ? in[r * ld_in + k] : 0.f;
     }
     __syncthreads();
     float acc[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-    for (int k = 0; k < d; ++k) {
-      const float g = Gs[k * ALS_D + col];
+    for (int k = 0; k < d4; k += 4) {
+      const float g0 = Ms[k * ALS_D + col], g1 = Ms[(k + 1) * ALS_D + col], g2 = Ms[(k + 2) * ALS_D + col], g3 = Ms[(k + 3) * ALS_D + col];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) acc[i] = fmaf(Ys[(half * 16 + i) * ALS_D + k], g, acc[i]);
+      for (int i = 0; i < 16; ++i) {
+        const float4 y = *reinterpret_cast<const float4*>(Ys + (half * 16 + i) * SM_LD + k);
+        acc[i] = fmaf(y.x, g0, acc[i]);
+        acc[i] = fmaf(y.y, g1, acc[i]);
+        acc[i] = fmaf(y.z, g2, acc[i]);
+        acc[i] = fmaf(y.w, g3, acc[i]);
+      }
     }
+    __syncthreads();
+    if (col < ncols) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const long long r = r0 + half * 16 + i;
-      if (r < n) Z[r * ALS_D + col] = acc[i];
+      for (int i = 0; i < 16; ++i) {
+        const long long r = r0 + half * 16 + i;
+        if (r < n) out[r * ld_out + col] = acc[i];
+      }
     }
   }
 }
 
-__global__ void __launch_bounds__(128) k_als_woodbury(const __grid_constant__ SolveParams P) {
+struct WhiteParams {
+  float* X;                 // [n_x, ldx]: receives xt (the first d columns); k_als_mul turns it into x afterwards
+  const float* W;           // [n_y, 128] = Y L^-T
+  const long long* indptr;
+  const int32_t* indices;
+  long long n_x;
+  int d, ldx;
+  float weight;
+  int* cursor;              // k_als_rows_tc: next chunk of 256 rows (zeroed before the launch)
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- rows with N_LO < n <= NMAX observed columns (and, in the <16> instance, the empty rows): one warp per row
+template <int NMAX, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_als_small(const __grid_constant__ WhiteParams P) {
+  constexpr int N_LO = NMAX == 16 ? 0 : 16;
+  constexpr int SLD = NMAX + 1;
   extern __shared__ float sm[];
-  constexpr int LD = ALS_D + 1;
-  float* Ys = sm;                      // [WB_N][129]
-  float* Zs = Ys + WB_N * LD;          // [WB_N][129]
-  float* S = Zs + WB_N * LD;           // [WB_N][WB_N + 1]
-  float* p = S + WB_N * (WB_N + 1);    // [128]
-  float* r = p + ALS_D;                // [WB_N]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float c = P.weight - 1.f;
-  for (long long u = blockIdx.x; u < P.n_x; u += gridDim.x) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* Wt = sm + (size_t)warp * (NMAX * SM_LD + NMAX * SLD);   // [NMAX][SM_LD] gathered rows of W
+  float* Ss = Wt + NMAX * SM_LD;                                  // [NMAX][SLD]  W_u W_u^T
+  const float c = P.weight - 1.f, invc = 1.f / c;
+  const long long nw = (long long)gridDim.x * WARPS;
+  for (long long u = (long long)blockIdx.x * WARPS + warp; u < P.n_x; u += nw) {
     const long long lo = P.indptr[u];
-    const int n = (int)(P.indptr[u + 1] - lo);
-    if (n > P.skip_le) continue;       // block-uniform: a long row, solved by k_als_solve_blocked
-    __syncthreads();
-    if (n == 0) {                      // nothing observed: b = 0, so x = 0
-      if (tid < P.d) P.X[u * P.ldx + tid] = 0.f;
+    const int n = (int)min(P.indptr[u + 1] - lo, (long long)(NMAX + 1));
+    if (n == 0 && N_LO == 0) {                         // nothing observed: the right-hand side is 0, so x = 0
+      for (int k = lane; k < P.d; k += 32) P.X[u * P.ldx + k] = 0.f;
       continue;
     }
-    for (int a = warp; a < n; a += 4) {          // gather the observed rows of Y and Z
-      const long long i = P.indices[lo + a];
-      for (int k = lane; k < ALS_D; k += 32) {
-        Ys[a * LD + k] = k < P.d ? P.Y[i * P.ldy + k] : 0.f;
-        Zs[a * LD + k] = P.Z[i * ALS_D + k];
+    if (n <= N_LO || n > NMAX) continue;
+    __syncwarp();
+    // gather: one 512-byte row per instruction; rows n.. are zero (the padded system decouples)
+    const int idx = lane < n ? P.indices[lo + lane] : 0;
+#pragma unroll 4
+    for (int a = 0; a < NMAX; ++a) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a < n) v = __ldg(reinterpret_cast<const float4*>(P.W + (long long)__shfl_sync(0xffffffffu, idx, a) * ALS_D) + lane);
+      *reinterpret_cast<float4*>(Wt + a * SM_LD + 4 * lane) = v;
+    }
+    __syncwarp();
+    // S0 = W_u W_u^T: lane a keeps 64 columns of its own row in registers; the other rows arrive as broadcast 128-bit loads,
+    // four at a time (four independent accumulators)
+    const int arow = lane < NMAX ? lane : 0;
+    const int ng = (n + 3) >> 2;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      float own[64];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float4 v = *reinterpret_cast<const float4*>(Wt + arow * SM_LD + 64 * pass + 4 * j);
+        own[4 * j] = v.x; own[4 * j + 1] = v.y; own[4 * j + 2] = v.z; own[4 * j + 3] = v.w;
+      }
+#pragma unroll 1
+      for (int g = 0; g < ng; ++g) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const float* wb = Wt + (4 * g) * SM_LD + 64 * pass;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 b0 = *reinterpret_cast<const float4*>(wb + 4 * j);
+          const float4 b1 = *reinterpret_cast<const float4*>(wb + SM_LD + 4 * j);
+          const float4 b2 = *reinterpret_cast<const float4*>(wb + 2 * SM_LD + 4 * j);
+          const float4 b3 = *reinterpret_cast<const float4*>(wb + 3 * SM_LD + 4 * j);
+          a0 = fmaf(own[4 * j], b0.x, a0); a0 = fmaf(own[4 * j + 1], b0.y, a0); a0 = fmaf(own[4 * j + 2], b0.z, a0); a0 = fmaf(own[4 * j + 3], b0.w, a0);
+          a1 = fmaf(own[4 * j], b1.x, a1); a1 = fmaf(own[4 * j + 1], b1.y, a1); a1 = fmaf(own[4 * j + 2], b1.z, a1); a1 = fmaf(own[4 * j + 3], b1.w, a1);
+          a2 = fmaf(own[4 * j], b2.x, a2); a2 = fmaf(own[4 * j + 1], b2.y, a2); a2 = fmaf(own[4 * j + 2], b2.z, a2); a2 = fmaf(own[4 * j + 3], b2.w, a2);
+          a3 = fmaf(own[4 * j], b3.x, a3); a3 = fmaf(own[4 * j + 1], b3.y, a3); a3 = fmaf(own[4 * j + 2], b3.z, a3); a3 = fmaf(own[4 * j + 3], b3.w, a3);
+        }
+        if (lane < NMAX) {
+          float* s = Ss + lane * SLD + 4 * g;
+          if (pass == 0) { s[0] = a0; s[1] = a1; s[2] = a2; s[3] = a3; }
+          else { s[0] += a0; s[1] += a1; s[2] += a2; s[3] += a3; }
+        }
       }
     }
-    __syncthreads();
-    {                                            // p = weight * sum_a z_a
-      float acc = 0.f;
-      for (int a = 0; a < n; ++a) acc += Zs[a * LD + tid];
-      p[tid] = P.weight * acc;
+    __syncwarp();
+    // lane a <- row a of S0 (columns >= 4 ng were never written: they are zero by construction of the padding)
+    float S[NMAX];
+    float r0 = 0.f;
+#pragma unroll
+    for (int b = 0; b < NMAX; ++b) {
+      S[b] = (lane < n && b < 4 * ng) ? Ss[arow * SLD + b] : 0.f;
+      if (b >= n) S[b] = 0.f;
+      r0 += S[b];
+      if (b == lane) S[b] += invc;
     }
+    // Cholesky of I / c + S0, one row per lane; column k is broadcast by shuffles
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k) {
+      if (k >= n) break;
+      const float dkk = __shfl_sync(0xffffffffu, S[k], k);
+      const float Lk = lane >= k ? S[k] * rsqrtf(fmaxf(dkk, 1e-30f)) : 0.f;   // lane k: sqrt(dkk); lanes > k: L[a][k]
+      S[k] = Lk;
+#pragma unroll
+      for (int j = k + 1; j < NMAX; ++j) S[j] = fmaf(-Lk, __shfl_sync(0xffffffffu, Lk, j), S[j]);
+    }
+    float dinv = 1.f;
+#pragma unroll
+    for (int b = 0; b < NMAX; ++b)
+      if (b == lane) dinv = 1.f / S[b];
+    // L z = weight * (S0 1)
+    float z = P.weight * r0;
+#pragma unroll
+    for (int k = 0; k < NMAX; ++k) {
+      if (k >= n) break;
+      const float zk = __shfl_sync(0xffffffffu, z * dinv, k);
+      if (lane == k) z = zk;
+      else if (lane > k) z = fmaf(-S[k], zk, z);
+    }
+    // L^T t = z
+    float t = 0.f;
+#pragma unroll
+    for (int a = NMAX - 1; a >= 0; --a) {
+      if (a >= n) continue;
+      const float part = (lane > a && lane < n) ? S[a] * t : 0.f;
+      const float sum = warp_sum(part);
+      if (lane == a) t = (z - sum) * dinv;
+    }
+    const float coef = lane < n ? P.weight - t : 0.f;
+    // xt = W_u^T (weight - t)
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int a = 0; a < n; ++a) {
+      const float ca = __shfl_sync(0xffffffffu, coef, a);
+      const float4 v = *reinterpret_cast<const float4*>(Wt + a * SM_LD + 4 * lane);
+      acc.x = fmaf(ca, v.x, acc.x); acc.y = fmaf(ca, v.y, acc.y); acc.z = fmaf(ca, v.z, acc.z); acc.w = fmaf(ca, v.w, acc.w);
+    }
+    float* xr = P.X + u * P.ldx + 4 * lane;
+    if (4 * lane + 0 < P.d) xr[0] = acc.x;
+    if (4 * lane + 1 < P.d) xr[1] = acc.y;
+    if (4 * lane + 2 < P.d) xr[2] = acc.z;
+    if (4 * lane + 3 < P.d) xr[3] = acc.w;
+  }
+}
+
+// ---- rows with more than 32 observed columns: one CTA per row, tcgen05 Gram + register-blocked Cholesky
+constexpr int RT_TILE = 16384;                 // one operand tile: 128 rows x 64 bf16, SWIZZLE_128B K-major (what a TMA box {64, 128} writes)
+constexpr int RT_A_BYTES = ALS_D * (ALS_D + 1) * 4;   // the fp32 system, aliased onto the four operand tiles once the MMAs are done
+
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& h, __nv_bfloat16& l) {
+  h = __float2bfloat16_rn(v);
+  l = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+__global__ void __launch_bounds__(256, 2) k_als_rows_tc(const __grid_constant__ WhiteParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* tiles = smem;                                             // 4 x 16 KB operand tiles ...
+  float* A = reinterpret_cast<float*>(smem);                         // ... later the fp32 system [128][129]
+  float* panel = reinterpret_cast<float*>(smem + ((RT_A_BYTES + 127) & ~127));   // [16][64] block column L_ik
+  float* zrow = panel + NBK * 64;              // [8]   the right-hand side's block of the current block column
+  float* diagA = zrow + 8;                     // [64]  the diagonal block about to be factored
+  float* zvec = diagA + 64;                    // [128] z, then the solution
+  float* svec = zvec + ALS_D;                  // [8][128] per-warp partial sums of the gathered rows / [2][128] row sums
+  int* rlist = reinterpret_cast<int*>(svec + 8 * ALS_D);             // [256] rows of this chunk that belong here
+  int* ridx = rlist + 256;                                           // [128] the observed columns of a short row
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ridx + ALS_D);        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  int* wcnt = reinterpret_cast<int*>(tmem_slot + 1);                 // [8] members per warp, [8] = total, [9] = chunk id
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tx = tid & 15, ty = tid >> 4;
+  const bool lower = ty >= tx;
+  // the right-hand side rides along as an extra block row: its block of block column j lives in an otherwise idle thread
+  const bool is_aug = (ty == 0 && tx >= 1) || (ty == 1 && tx == 2);
+  const int aug_col = ty == 0 ? tx : 0;
+  const float c = P.weight - 1.f, invc = 1.f / c;
+
+  if (tid == 0) {
+    mbar_init(bars, 1);
+    mbar_init(bars + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = umma_idesc_bf16(ROWS, ALS_D);
+  uint32_t nwait0 = 0u, nwait1 = 0u;     // completed phases of the two mbarriers (every thread keeps the same count)
+
+  const long long n_chunks = (P.n_x + 255) / 256;
+  for (;;) {
+    // ---- take the next chunk of 256 rows (long rows cost 10x a short one: static striding leaves SMs idle at the end)
+    __syncthreads();                       // (the previous chunk's list and counters are no longer read)
+    if (tid == 0) wcnt[9] = atomicAdd(P.cursor, 1);
     __syncthreads();
-    // S = I / c + Y_u Z_u^T (lower triangle) and r = Y_u p: one dot product of length 128 per (a, b <= a) / per a, by warps
-    const int npair = n * (n + 1) / 2;
-    for (int e = warp; e < npair + n; e += 4) {
-      int a, b;
-      const float* rhs;
-      if (e < npair) {
-        a = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
-        while (a * (a + 1) / 2 > e) --a;
-        while ((a + 1) * (a + 2) / 2 <= e) ++a;
-        b = e - a * (a + 1) / 2;
-        rhs = Zs + b * LD;
+    const long long chunk0 = (long long)wcnt[9] * 256;
+    if (wcnt[9] >= n_chunks) break;
+    {
+      const long long u = chunk0 + tid;
+      const bool mine = u < P.n_x && (P.indptr[u + 1] - P.indptr[u]) > 32;
+      const unsigned m = __ballot_sync(0xffffffffu, mine);
+      if (lane == 0) wcnt[warp] = __popc(m);
+      __syncthreads();
+      int base = 0;
+      for (int w = 0; w < warp; ++w) base += wcnt[w];
+      if (mine) rlist[base + __popc(m & ((1u << lane) - 1u))] = tid;
+      if (tid == 0) {
+        int tot = 0;
+        for (int w = 0; w < 8; ++w) tot += wcnt[w];
+        wcnt[8] = tot;
+      }
+      __syncthreads();
+    }
+    const int nmine = wcnt[8];
+    for (int ri = 0; ri < nmine; ++ri) {
+      const long long u = chunk0 + rlist[ri];
+      const long long lo = P.indptr[u];
+      const long long nl = P.indptr[u + 1] - lo;
+      const bool wide = nl > ALS_D;         // 128 x 128 system (I + c W^T W); otherwise n x n (I / c + W W^T)
+      const int n = wide ? ALS_D : (int)nl; // order of the system
+      // =========================================================== Gram on the tensor cores
+      if (!wide) {
+        // tiles: hi[kc 0], hi[kc 1], lo[kc 0], lo[kc 1]; row a of the tile = gathered row a, zero beyond n
+        // (all loads of a warp's 16 rows are issued before the first conversion: one round trip, not sixteen)
+        const int my_a = warp + 8 * (lane & 15);
+        const int my_idx = my_a < n ? P.indices[lo + my_a] : -1;
+        if (lane < 16 && my_a < n) ridx[my_a] = my_idx;
+        float4 v[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const int ia = __shfl_sync(0xffffffffu, my_idx, r);
+          v[r] = ia >= 0 ? __ldg(reinterpret_cast<const float4*>(P.W + (long long)ia * ALS_D) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const int a = warp + 8 * r;
+          __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+          split_bf16(v[r].x, h0, l0); split_bf16(v[r].y, h1, l1); split_bf16(v[r].z, h2, l2); split_bf16(v[r].w, h3, l3);
+          const int off = (lane >> 4) * RT_TILE + a * 128 + ((((lane & 15) >> 1) ^ (a & 7)) << 4) + (lane & 1) * 8;
+          *reinterpret_cast<uint2*>(tiles + off) = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
+          *reinterpret_cast<uint2*>(tiles + 2 * RT_TILE + off) = make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+          tc_fence_after();
+          const uint32_t hb = smem_u32(tiles), lb = smem_u32(tiles + 2 * RT_TILE);
+#pragma unroll
+          for (int kc = 0; kc < 2; ++kc)
+#pragma unroll
+            for (int k = 0; k < KCH / 16; ++k) {
+              const uint64_t dh = umma_desc_sw128(hb + kc * RT_TILE + k * 32), dl = umma_desc_sw128(lb + kc * RT_TILE + k * 32);
+              tc_mma_bf16(tmem_base, dh, dh, idesc, (kc | k) ? 1u : 0u);
+              tc_mma_bf16(tmem_base, dh, dl, idesc, 1u);
+              tc_mma_bf16(tmem_base, dl, dh, idesc, 1u);
+            }
+          tc_commit(bars);
+        }
+        mbar_wait(bars, nwait0 & 1u);
+        ++nwait0;
       } else {
-        a = e - npair;
-        b = -1;
-        rhs = p;
-      }
-      float acc = 0.f;
+        // chunks of 64 gathered rows; tile[i][a - 64 ch] = W[a][i] (the contraction runs over the gathered rows), two buffers
+        const int nch = (int)((nl + 63) >> 6);
+        float sacc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int ch = 0; ch < nch; ++ch) {
+          const int buf = ch & 1;
+          if (ch >= 2) {                      // the MMAs of chunk ch - 2 have finished reading this buffer
+            if (buf == 0) { mbar_wait(bars, nwait0 & 1u); ++nwait0; }
+            else { mbar_wait(bars + 1, nwait1 & 1u); ++nwait1; }
+          }
+          const long long a0 = (long long)ch * 64 + warp * 8;
+          long long src[8];
 #pragma unroll
-      for (int k = 0; k < ALS_D; k += 32) acc = fmaf(Ys[a * LD + k + lane], rhs[k + lane], acc);
+          for (int q = 0; q < 8; ++q) src[q] = (a0 + q < nl) ? (long long)P.indices[lo + a0 + q] * ALS_D : -1;
+          uint8_t* th = tiles + buf * 2 * RT_TILE;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) {
-        if (b >= 0) S[a * (WB_N + 1) + b] = acc + (a == b ? 1.f / c : 0.f);
-        else r[a] = acc;
+          for (int ig = 0; ig < 4; ++ig) {
+            const int i = lane + 32 * ig;
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = src[q] >= 0 ? __ldg(P.W + src[q] + i) : 0.f;
+            uint32_t hp[4], lp[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              __nv_bfloat16 ha, hb2, la, lb2;
+              split_bf16(v[2 * q], ha, la);
+              split_bf16(v[2 * q + 1], hb2, lb2);
+              hp[q] = pack_bf16(ha, hb2);
+              lp[q] = pack_bf16(la, lb2);
+              sacc[ig] += v[2 * q] + v[2 * q + 1];
+            }
+            const int off = i * 128 + ((warp ^ (i & 7)) << 4);
+            *reinterpret_cast<uint4*>(th + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+            *reinterpret_cast<uint4*>(th + RT_TILE + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncthreads();
+          if (tid == 0) {
+            tc_fence_after();
+            const uint32_t hb = smem_u32(th), lb = smem_u32(th + RT_TILE);
+#pragma unroll
+            for (int k = 0; k < KCH / 16; ++k) {
+              const uint64_t dh = umma_desc_sw128(hb + k * 32), dl = umma_desc_sw128(lb + k * 32);
+              tc_mma_bf16(tmem_base, dh, dh, idesc, (ch | k) ? 1u : 0u);
+              tc_mma_bf16(tmem_base, dh, dl, idesc, 1u);
+              tc_mma_bf16(tmem_base, dl, dh, idesc, 1u);
+            }
+            tc_commit(bars + buf);
+          }
+        }
+        // drain: the last one or two chunks
+        if (nch >= 2) {
+          if (((nch - 2) & 1) == 0) { mbar_wait(bars, nwait0 & 1u); ++nwait0; }
+          else { mbar_wait(bars + 1, nwait1 & 1u); ++nwait1; }
+        }
+        if (((nch - 1) & 1) == 0) { mbar_wait(bars, nwait0 & 1u); ++nwait0; }
+        else { mbar_wait(bars + 1, nwait1 & 1u); ++nwait1; }
+#pragma unroll
+        for (int ig = 0; ig < 4; ++ig) svec[warp * ALS_D + lane + 32 * ig] = sacc[ig];
       }
-    }
-    __syncthreads();
-    // Cholesky of S (n x n, right-looking by columns), then L z = r, L^T t = z
-    for (int k = 0; k < n; ++k) {
-      if (tid == 0) S[k * (WB_N + 1) + k] = sqrtf(fmaxf(S[k * (WB_N + 1) + k], 1e-30f));
+      tc_fence_after();
+      // =========================================================== accumulator -> the fp32 system in shared memory
+      {
+        const int q = warp & 3, hf = warp >> 2;
+        const int row = q * 32 + lane;
+        float rs = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          uint32_t r[32];
+          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * 64 + cc * 32), r);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = hf * 64 + cc * 32 + j;
+            const float g = __uint_as_float(r[j]);
+            rs += g;
+            A[row * (ALS_D + 1) + col] = wide ? fmaf(c, g, row == col ? 1.f : 0.f) : g + (row == col ? invc : 0.f);
+          }
+        }
+        if (!wide) svec[hf * ALS_D + row] = rs;
+      }
+      tc_fence_before();
       __syncthreads();
-      const float inv = 1.f / S[k * (WB_N + 1) + k];
-      for (int i = k + 1 + tid; i < n; i += blockDim.x) S[i * (WB_N + 1) + k] *= inv;
-      __syncthreads();
-      const int m = n - k - 1;
-      for (int e = tid; e < m * m; e += blockDim.x) {
-        const int i = k + 1 + e / m, j = k + 1 + e % m;
-        if (j <= i) S[i * (WB_N + 1) + j] = fmaf(-S[i * (WB_N + 1) + k], S[j * (WB_N + 1) + k], S[i * (WB_N + 1) + j]);
+      // =========================================================== register blocks + right-hand side
+      float a[BS][BS];
+      float g[BS];
+      if (lower) {
+#pragma unroll
+        for (int i = 0; i < BS; ++i)
+#pragma unroll
+          for (int j = 0; j < BS; ++j) a[i][j] = A[(BS * ty + i) * (ALS_D + 1) + BS * tx + j];
+      }
+      if (is_aug) {
+#pragma unroll
+        for (int j = 0; j < BS; ++j) {
+          const int e = BS * aug_col + j;
+          float s = 0.f;
+          if (wide) {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s += svec[w * ALS_D + e];
+          } else {
+            s = e < n ? svec[e] + svec[ALS_D + e] : 0.f;
+          }
+          g[j] = P.weight * s;
+        }
+      }
+      if (ty == 0 && tx == 0) {
+#pragma unroll
+        for (int i = 0; i < BS; ++i)
+#pragma unroll
+          for (int j = 0; j < BS; ++j) diagA[i * BS + j] = a[i][j];
       }
       __syncthreads();
-    }
-    if (warp == 0) {
-      for (int k = 0; k < n; ++k) {
+      const int nb = (n + BS - 1) / BS;
+      // =========================================================== blocked Cholesky, two barriers per block column
+      for (int kb = 0; kb < nb; ++kb) {
+        const bool in_panel = tx == kb && ty >= kb && ty < nb;
+        const bool aug_here = is_aug && aug_col == kb;
+        if (in_panel || aug_here) {
+          float dg[BS][BS], inv[BS];
+#pragma unroll
+          for (int i = 0; i < BS; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) dg[i][j] = diagA[i * BS + j];
+#pragma unroll
+          for (int k = 0; k < BS; ++k) {
+            inv[k] = rsqrtf(fmaxf(dg[k][k], 1e-30f));
+            dg[k][k] *= inv[k];
+#pragma unroll
+            for (int i = k + 1; i < BS; ++i) dg[i][k] *= inv[k];
+#pragma unroll
+            for (int i = k + 1; i < BS; ++i)
+#pragma unroll
+              for (int j = k + 1; j <= i; ++j) dg[i][j] = fmaf(-dg[i][k], dg[j][k], dg[i][j]);
+          }
+          if (aug_here) {                    // z_kb = g L_kk^-T
+#pragma unroll
+            for (int j = 0; j < BS; ++j) {
+              float v = g[j];
+#pragma unroll
+              for (int q = 0; q < j; ++q) v = fmaf(-g[q], dg[j][q], v);
+              g[j] = v * inv[j];
+            }
+#pragma unroll
+            for (int j = 0; j < BS; ++j) {
+              zrow[j] = g[j];
+              zvec[BS * kb + j] = g[j];
+            }
+          } else if (ty == kb) {             // the diagonal block keeps its factor (the back-substitution reads it from registers)
+#pragma unroll
+            for (int i = 0; i < BS; ++i)
+#pragma unroll
+              for (int j = 0; j < BS; ++j) a[i][j] = j <= i ? dg[i][j] : 0.f;
+          } else {                           // L_ik = A_ik L_kk^-T
+#pragma unroll
+            for (int i = 0; i < BS; ++i)
+#pragma unroll
+              for (int j = 0; j < BS; ++j) {
+                float v = a[i][j];
+#pragma unroll
+                for (int q = 0; q < j; ++q) v = fmaf(-a[i][q], dg[j][q], v);
+                a[i][j] = v * inv[j];
+              }
+#pragma unroll
+            for (int i = 0; i < BS; ++i)
+#pragma unroll
+              for (int j = 0; j < BS; ++j) panel[ty * 64 + i * BS + j] = a[i][j];
+          }
+        }
+        __syncthreads();
+        if (lower && tx > kb && ty < nb) {   // A_ij -= L_ik L_jk^T
+          const float* li = panel + ty * 64;
+          const float* lj = panel + tx * 64;
+#pragma unroll
+          for (int q = 0; q < BS; ++q) {
+            float ci[BS], cj[BS];
+#pragma unroll
+            for (int i = 0; i < BS; ++i) {
+              ci[i] = li[i * BS + q];
+              cj[i] = lj[i * BS + q];
+            }
+#pragma unroll
+            for (int i = 0; i < BS; ++i)
+#pragma unroll
+              for (int j = 0; j < BS; ++j) a[i][j] = fmaf(-ci[i], cj[j], a[i][j]);
+          }
+          if (ty == kb + 1 && tx == kb + 1) {
+#pragma unroll
+            for (int i = 0; i < BS; ++i)
+#pragma unroll
+              for (int j = 0; j < BS; ++j) diagA[i * BS + j] = a[i][j];
+          }
+        }
+        if (is_aug && aug_col > kb && aug_col < nb) {   // g_j -= z_kb L_jk^T
+          const float* lj = panel + aug_col * 64;
+#pragma unroll
+          for (int j = 0; j < BS; ++j) {
+            float v = g[j];
+#pragma unroll
+            for (int q = 0; q < BS; ++q) v = fmaf(-zrow[q], lj[j * BS + q], v);
+            g[j] = v;
+          }
+        }
+        __syncthreads();
+      }
+      // =========================================================== L^T x = z, block by block out of the register blocks
+      for (int kb = nb - 1; kb >= 0; --kb) {
+        if (ty == kb && tx == kb) {
+          float xb[BS];
+#pragma unroll
+          for (int k = BS - 1; k >= 0; --k) {
+            float v = zvec[BS * kb + k];
+#pragma unroll
+            for (int q = k + 1; q < BS; ++q) v = fmaf(-a[q][k], xb[q], v);
+            xb[k] = v / a[k][k];
+          }
+#pragma unroll
+          for (int k = 0; k < BS; ++k) zvec[BS * kb + k] = xb[k];
+        }
+        __syncthreads();
+        if (ty == kb && tx < kb) {           // z_tx -= L_(kb,tx)^T x_kb
+          float xb[BS];
+#pragma unroll
+          for (int i = 0; i < BS; ++i) xb[i] = zvec[BS * kb + i];
+#pragma unroll
+          for (int j = 0; j < BS; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < BS; ++i) s = fmaf(a[i][j], xb[i], s);
+            zvec[BS * tx + j] -= s;
+          }
+        }
+        __syncthreads();
+      }
+      // =========================================================== xt
+      if (wide) {
+        if (tid < P.d) P.X[u * P.ldx + tid] = zvec[tid];
+      } else {
+        // xt = W_u^T (weight - t): two halves of the gathered rows, one column per thread
+        const int k = tid & 127, hf = tid >> 7;
         float acc = 0.f;
-        for (int j = lane; j < k; j += 32) acc = fmaf(S[k * (WB_N + 1) + j], r[j], acc);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) r[k] = (r[k] - acc) / S[k * (WB_N + 1) + k];
-        __syncwarp();
+#pragma unroll 8
+        for (int e = hf; e < n; e += 2) acc = fmaf(P.weight - zvec[e], __ldg(P.W + (long long)ridx[e] * ALS_D + k), acc);
+        if (hf == 1) svec[k] = acc;
+        __syncthreads();
+        if (hf == 0 && k < P.d) P.X[u * P.ldx + k] = acc + svec[k];
       }
-      for (int k = n - 1; k >= 0; --k) {
-        float acc = 0.f;
-        for (int j = k + 1 + lane; j < n; j += 32) acc = fmaf(S[j * (WB_N + 1) + k], r[j], acc);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) r[k] = (r[k] - acc) / S[k * (WB_N + 1) + k];
-        __syncwarp();
-      }
+      __syncthreads();                       // zvec / svec / A are rewritten by the next row
     }
-    __syncthreads();
-    {                                            // x = p - Z_u^T t
-      float acc = p[tid];
-      for (int a = 0; a < n; ++a) acc = fmaf(-Zs[a * LD + tid], r[a], acc);
-      if (tid < P.d) P.X[u * P.ldx + tid] = acc;
-    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
   }
 }
 
@@ -582,15 +1030,16 @@ int make_plane_map(CUtensorMap* tm, void* base, long long n_pad) {
 
 }  // namespace
 
-// workspace layout: [hi | lo bf16 planes of Y^T] [G fp32 128x128] [Ginv fp32 128x128] [Gauss-Jordan tableau fp64 128x256] [Z fp32 n_y x 128]
+// workspace layout: [hi | lo bf16 planes of Y^T] [G fp32 128x128] [L^-1 fp32 128x128] [L^-T fp32 128x128] [cursor] [W fp32 n_y x 128]
 static size_t ws_off_g(long long n_pad) { return (((size_t)2 * ALS_D * n_pad * 2 + 1023) / 1024) * 1024; }
-static size_t ws_off_ginv(long long n_pad) { return ws_off_g(n_pad) + (size_t)ALS_D * ALS_D * 4; }
-static size_t ws_off_w(long long n_pad) { return ws_off_ginv(n_pad) + (size_t)ALS_D * ALS_D * 4; }
-static size_t ws_off_z(long long n_pad) { return ws_off_w(n_pad) + (size_t)ALS_D * 2 * ALS_D * 8; }
+static size_t ws_off_linv(long long n_pad) { return ws_off_g(n_pad) + (size_t)ALS_D * ALS_D * 4; }
+static size_t ws_off_linvt(long long n_pad) { return ws_off_linv(n_pad) + (size_t)ALS_D * ALS_D * 4; }
+static size_t ws_off_cursor(long long n_pad) { return ws_off_linvt(n_pad) + (size_t)ALS_D * ALS_D * 4; }
+static size_t ws_off_w(long long n_pad) { return ws_off_cursor(n_pad) + 1024; }
 
 extern "C" int64_t cf_als_workspace_bytes(int64_t n_y) {
   const long long n_pad = (n_y + KCH - 1) / KCH * KCH;
-  return (int64_t)(ws_off_z(n_pad) + (size_t)n_y * ALS_D * 4 + 2048);
+  return (int64_t)(ws_off_w(n_pad) + (size_t)n_y * ALS_D * 4 + 2048);
 }
 
 // Gram stage: G += Y^T Y over the given rows (bf16 hi/lo planes + tcgen05); G is NOT zeroed here
@@ -613,33 +1062,57 @@ static int als_gram(const float* Y, long long n_y, int d, int ldy, float* G, uin
   return 0;
 }
 
-// Solve stage: every row of X from the (complete) Gram G and its observed rows of Y.  With a workspace (and weight > 1) the
-// rows with at most WB_N observed columns take the low-rank path, the others the full 128 x 128 solve.
+constexpr int SMALL16_WARPS = 8, SMALL32_WARPS = 5;
+static size_t small_smem(int nmax, int warps) { return (size_t)warps * (nmax * SM_LD + nmax * (nmax + 1)) * 4; }
+static size_t rows_tc_smem() {
+  return (size_t)((RT_A_BYTES + 127) & ~127) + (NBK * 64 + 8 + 64 + ALS_D + 8 * ALS_D) * 4 + (256 + ALS_D) * 4 + 16 + 4 + 10 * 4 + 64 + 1024;
+}
+
+// Solve stage: every row of X from the (complete) Gram G and its observed rows of Y.  With a workspace and weight > 1 the
+// whitened path above; otherwise (or with CF_ALS_DIRECT=1) the direct 128 x 128 solve of every row.
 static int als_solve(const cf_als_args* a, const float* G, cudaStream_t stream, uint8_t* ws) {
+  const int sms = cf_num_sms();
+  if (ws != nullptr && a->weight > 1.f && !getenv("CF_ALS_DIRECT")) {
+    const long long n_pad = (a->n_y + KCH - 1) / KCH * KCH;
+    float* Linv = reinterpret_cast<float*>(ws + ws_off_linv(n_pad));
+    float* LinvT = reinterpret_cast<float*>(ws + ws_off_linvt(n_pad));
+    int* cursor = reinterpret_cast<int*>(ws + ws_off_cursor(n_pad));
+    float* W = reinterpret_cast<float*>(ws + ws_off_w(n_pad));
+    const size_t psmem = (size_t)ALS_D * (ALS_D + 1) * 8;
+    CF_CUDA_OK(cudaFuncSetAttribute(k_als_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+    k_als_prep<<<1, 1024, psmem, stream>>>(G, a->reg, a->d, Linv, LinvT);
+    const size_t msmem = ((size_t)ALS_D * ALS_D + 32 * SM_LD) * 4;
+    CF_CUDA_OK(cudaFuncSetAttribute(k_als_mul, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
+    long long mg = (a->n_y + 31) / 32;
+    if (mg > (long long)sms * 2) mg = (long long)sms * 2;
+    k_als_mul<<<(unsigned)mg, 256, msmem, stream>>>(a->Y, a->n_y, a->d, a->ldy, LinvT, W, ALS_D, ALS_D);   // W = Y L^-T
+    CF_CUDA_OK(cudaMemsetAsync(cursor, 0, 4, stream));
+    WhiteParams P;
+    P.X = a->X; P.W = W; P.indptr = (const long long*)a->indptr; P.indices = a->indices; P.n_x = a->n_x; P.d = a->d;
+    P.ldx = a->ldx; P.weight = a->weight; P.cursor = cursor;
+    const size_t s16 = small_smem(16, SMALL16_WARPS), s32 = small_smem(32, SMALL32_WARPS), srt = rows_tc_smem();
+    CF_CUDA_OK(cudaFuncSetAttribute(k_als_small<16, SMALL16_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s16));
+    CF_CUDA_OK(cudaFuncSetAttribute(k_als_small<32, SMALL32_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s32));
+    CF_CUDA_OK(cudaFuncSetAttribute(k_als_rows_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)srt));
+    long long g16 = (a->n_x + SMALL16_WARPS - 1) / SMALL16_WARPS, g32 = (a->n_x + SMALL32_WARPS - 1) / SMALL32_WARPS;
+    if (g16 > (long long)sms * 2) g16 = (long long)sms * 2;
+    if (g32 > (long long)sms * 2) g32 = (long long)sms * 2;
+    long long grt = (a->n_x + 255) / 256;
+    if (grt > (long long)sms * 2) grt = (long long)sms * 2;
+    k_als_rows_tc<<<(unsigned)grt, 256, srt, stream>>>(P);      // the long rows first: they are the tail
+    k_als_small<32, SMALL32_WARPS><<<(unsigned)g32, SMALL32_WARPS * 32, s32, stream>>>(P);
+    k_als_small<16, SMALL16_WARPS><<<(unsigned)g16, SMALL16_WARPS * 32, s16, stream>>>(P);
+    long long xg = (a->n_x + 31) / 32;
+    if (xg > (long long)sms * 2) xg = (long long)sms * 2;
+    k_als_mul<<<(unsigned)xg, 256, msmem, stream>>>(a->X, a->n_x, a->d, a->ldx, Linv, a->X, a->ldx, a->d);   // X = Xt L^-1
+    CF_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   SolveParams S;
   S.X = a->X; S.Y = a->Y; S.G = G; S.indptr = (const long long*)a->indptr; S.indices = a->indices;
   S.n_x = a->n_x; S.d = a->d; S.ldx = a->ldx; S.ldy = a->ldy; S.weight = a->weight; S.reg = a->reg;
-  S.skip_le = -1; S.Z = nullptr;
-  if (ws != nullptr && a->weight > 1.f && !getenv("CF_ALS_DIRECT")) {
-    const long long n_pad = (a->n_y + KCH - 1) / KCH * KCH;
-    float* Ginv = reinterpret_cast<float*>(ws + ws_off_ginv(n_pad));
-    double* W = reinterpret_cast<double*>(ws + ws_off_w(n_pad));
-    float* Z = reinterpret_cast<float*>(ws + ws_off_z(n_pad));
-    k_als_inverse<<<1, 1024, 0, stream>>>(G, a->reg, a->d, W, Ginv);
-    const size_t zsmem = ((size_t)ALS_D * ALS_D + 32 * ALS_D) * 4;
-    CF_CUDA_OK(cudaFuncSetAttribute(k_als_z, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zsmem));
-    long long zg = (a->n_y + 31) / 32;
-    if (zg > (long long)cf_num_sms() * 2) zg = (long long)cf_num_sms() * 2;
-    k_als_z<<<(unsigned)zg, 256, zsmem, stream>>>(a->Y, a->n_y, a->d, a->ldy, Ginv, Z);
-    S.skip_le = WB_N; S.Z = Z;
-    const size_t wsmem = ((size_t)2 * WB_N * (ALS_D + 1) + WB_N * (WB_N + 1) + ALS_D + WB_N) * 4;
-    CF_CUDA_OK(cudaFuncSetAttribute(k_als_woodbury, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
-    long long wg = a->n_x;
-    if (wg > (long long)cf_num_sms() * 16) wg = (long long)cf_num_sms() * 16;
-    k_als_woodbury<<<(unsigned)wg, 128, wsmem, stream>>>(S);
-  }
   long long sg = a->n_x;
-  const long long cap = (long long)cf_num_sms() * 8;
+  const long long cap = (long long)sms * 8;
   if (sg > cap) sg = cap;
   if (getenv("CF_ALS_COLUMNWISE")) {   // the first, column-wise kernel (kept for A/B measurements)
     const size_t ssmem = ((size_t)a->d * (a->d + 1) + a->d + 8 * a->d) * 4;

@@ -51,8 +51,7 @@ struct TcParams {
   const long long* tr_indptr;      // training CSR (NULL = no mask)
   const int32_t* tr_indices;
   const float* eps2;               // [T_pad] 2 * eps_row
-  float* cand_val;                 // [T_pad, S, CAP]
-  int32_t* cand_idx;
+  uint2* cand;                     // [T_pad, S, CAP] entries {score bits, item}: one 8-byte store per hit
   int32_t* cand_cnt;               // [T_pad, S]
   int32_t* overflow;               // [T_pad]
   float* dbg_scores;               // optional [T_pad, dbg_ld] dump of the raw accumulators
@@ -70,28 +69,35 @@ __device__ __forceinline__ float ord_unkey(unsigned k) { return __uint_as_float(
 // Warp-cooperative compaction of ONE row's candidate buffer (n entries): entries [ver, n) were appended WITHOUT looking at
 // the user's training row (a binary search per hit inside the per-thread sweep is a chain of dependent global loads that
 // nothing hides: it was most of the sweep on small catalogues) -- they are checked here, 32 searches in flight; then
-// theta <- K-th largest value among the unmasked entries, keep >= theta - eps2.
-__device__ __forceinline__ void compact_row(float* cv, int32_t* ci, int n, int ver, int K, float eps2, const int32_t* tr_indices,
-                                            long long tlo, long long thi, int lane, float& theta_out, int& cnt_out) {
+// theta <- (a lower bound within 2^-15 relative of) the K-th largest value among the unmasked entries, keep >= theta - eps2.
+// A compaction stalls its warp and, two tiles later, the CTA's MMA pipeline, and on a 500 k-item catalogue every row needs
+// ~6 of them (the thresholds start at -inf in every CTA): its latency is what the small-catalogue throughput hangs on.
+// Hence: the counting rounds of the radix select reduce with redux.sync (one instruction) instead of a five-step shuffle
+// tree, and stop after the 24 leading bits (any lower bound of the K-th value keeps the superset property).
+__device__ __forceinline__ void compact_row(uint2* ce, int n, int ver, int K, float eps2, const int32_t* tr_indices,
+                                            long long tlo, long long thi, int lane, int n_items, float& theta_out, int& cnt_out) {
   constexpr int EPL = TC_CAP / 32;
   float v[EPL];
   int32_t id[EPL];
 #pragma unroll
   for (int i = 0; i < EPL; ++i) {
     const int e = lane + 32 * i;
-    v[i] = e < n ? __ldcg(cv + e) : __uint_as_float(0xffffffffu);   // padding: key 0 (below every real score)
-    id[i] = e < n ? __ldcg(ci + e) : -1;
+    const uint2 x = e < n ? __ldcg(ce + e) : make_uint2(0xffffffffu, 0xffffffffu);
+    v[i] = __uint_as_float(x.x);
+    id[i] = (int32_t)x.y;
+    if ((unsigned)id[i] >= (unsigned)n_items) {   // an empty slot, or a padding column of the last tile: key 0 (below every real score)
+      v[i] = __uint_as_float(0xffffffffu);
+      id[i] = -1;
+    }
   }
   if (thi > tlo) {
     // EPL binary searches per lane, advanced TOGETHER one probe at a time: the probes of a round are independent loads
-    // (one search after the other is a chain of ~7 dependent global loads per entry: 16 x 7 round trips per compaction,
-    // which was most of the sweep on a 500 k-item catalogue)
     int slo[EPL], shi[EPL];
     const int len = (int)(thi - tlo);
 #pragma unroll
     for (int i = 0; i < EPL; ++i) {
       const int e = lane + 32 * i;
-      const bool chk = e >= ver && e < n;
+      const bool chk = e >= ver && id[i] >= 0;
       slo[i] = 0;
       shi[i] = chk ? len : 0;
     }
@@ -115,14 +121,17 @@ __device__ __forceinline__ void compact_row(float* cv, int32_t* ci, int n, int v
       }
     }
   }
+  unsigned key[EPL];
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) key[i] = ord_key(v[i]);
   unsigned prefix = 0u;
-  for (int bit = 31; bit >= 0; --bit) {
+#pragma unroll 1
+  for (int bit = 31; bit >= 8; --bit) {
     const unsigned cand = prefix | (1u << bit);
     int c = 0;
 #pragma unroll
-    for (int i = 0; i < EPL; ++i) c += ord_key(v[i]) >= cand;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    for (int i = 0; i < EPL; ++i) c += key[i] >= cand;
+    c = __reduce_add_sync(0xffffffffu, c);
     if (c >= K) prefix = cand;
   }
   // fewer than K unmasked entries so far: no threshold yet, keep them all
@@ -134,11 +143,7 @@ __device__ __forceinline__ void compact_row(float* cv, int32_t* ci, int n, int v
   for (int i = 0; i < EPL; ++i) {
     const bool keep = id[i] >= 0 && v[i] >= cut;   // (padding and masked entries have id -1)
     const unsigned m = __ballot_sync(0xffffffffu, keep);
-    if (keep) {
-      const int p = pos + __popc(m & ((1u << lane) - 1u));
-      cv[p] = v[i];
-      ci[p] = id[i];
-    }
+    if (keep) ce[pos + __popc(m & ((1u << lane) - 1u))] = make_uint2(__float_as_uint(v[i]), (unsigned)id[i]);
     pos += __popc(m);
   }
   __syncwarp();
@@ -277,8 +282,7 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
       tlo = P.tr_indptr[u];
       thi = P.tr_indptr[u + 1];
     }
-    float* cv = P.cand_val + ((long long)row * P.S + split) * TC_CAP;
-    int32_t* ci = P.cand_idx + ((long long)row * P.S + split) * TC_CAP;
+    uint2* ce = P.cand + ((long long)row * P.S + split) * TC_CAP;
     bool overflowed = false;
 
     // The sweep costs instructions, not bandwidth: ncu showed ~110 warp instructions per 32 scores in the first version
@@ -299,15 +303,14 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
         while (need) {
           const int l = __ffs(need) - 1;
           need &= need - 1;
-          float* rcv = reinterpret_cast<float*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(cv), l));
-          int32_t* rci = reinterpret_cast<int32_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(ci), l));
+          uint2* rce = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(ce), l));
           const int rn = __shfl_sync(0xffffffffu, cnt, l);
           const int rver = __shfl_sync(0xffffffffu, ver, l);
           const float re = __shfl_sync(0xffffffffu, eps2, l);
           const long long rlo = __shfl_sync(0xffffffffu, tlo, l), rhi = __shfl_sync(0xffffffffu, thi, l);
           float nth;
           int ncnt;
-          compact_row(rcv, rci, rn, rver, P.K, re, P.tr_indices, rlo, rhi, lane, nth, ncnt);
+          compact_row(rce, rn, rver, P.K, re, P.tr_indices, rlo, rhi, lane, P.N, nth, ncnt);
           if (lane == l) {
             theta = nth;
             cnt = ncnt;
@@ -335,19 +338,30 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
 #pragma unroll
             for (int j = 0; j < 32; ++j) P.dbg_scores[(long long)row * P.dbg_ld + n0 + c * 32 + j] = __uint_as_float(r[j]);
           }
-          float m = fmaxf(fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])), __uint_as_float(r[2]));
+          // group maxima of 8 (FMNMX3 trees), then their maximum: a chunk without a hit costs 18 instructions; a hit makes the
+          // warp scan only the groups that hold one (on a 500 k-item catalogue 6 % of a row's chunks hold a hit, so 86 % of
+          // a WARP's chunks do: the scan is the common path there, and it appends with one 8-byte store per hit; padding
+          // columns of the last tile are dropped by the compaction and the re-rank, not here)
+          float mg[4];
 #pragma unroll
-          for (int j = 3; j + 1 < 32; j += 2) m = fmaxf(fmaxf(m, __uint_as_float(r[j])), __uint_as_float(r[j + 1]));
-          m = fmaxf(m, __uint_as_float(r[31]));
-          if (m >= thr) {   // rare: at least one of the 32 scores reaches the row's threshold
+          for (int g = 0; g < 4; ++g) {
+            float x = fmaxf(fmaxf(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1])), __uint_as_float(r[8 * g + 2]));
+            x = fmaxf(fmaxf(x, __uint_as_float(r[8 * g + 3])), __uint_as_float(r[8 * g + 4]));
+            x = fmaxf(fmaxf(x, __uint_as_float(r[8 * g + 5])), __uint_as_float(r[8 * g + 6]));
+            mg[g] = fmaxf(x, __uint_as_float(r[8 * g + 7]));
+          }
+          const float m = fmaxf(fmaxf(fmaxf(mg[0], mg[1]), mg[2]), mg[3]);
+          if (m >= thr) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float sv = __uint_as_float(r[j]);
-              const int item = n0 + c * 32 + j;
-              if (sv >= thr && item < P.N) {   // (training items are dropped at the next compaction / by the re-rank)
-                cv[cnt] = sv;
-                ci[cnt] = item;
-                ++cnt;
+            for (int g = 0; g < 4; ++g) {
+              if (mg[g] >= thr) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  if (__uint_as_float(r[8 * g + j]) >= thr) {
+                    ce[cnt] = make_uint2(r[8 * g + j], (unsigned)(n0 + c * 32 + 8 * g + j));
+                    ++cnt;
+                  }
+                }
               }
             }
           }
@@ -469,8 +483,8 @@ struct RerankParams {
   const float *U, *V, *b;
   int ld, nvec, kind, T, S, K;
   const int32_t* users;
-  const float* cand_val;
-  const int32_t* cand_idx;
+  const uint2* cand;
+  int n_items;
   const int32_t* cand_cnt;
   const int32_t* overflow;
   const long long* tr_indptr;   // training CSR (NULL = no mask): candidates appended after a row's last compaction are unchecked
@@ -504,10 +518,10 @@ __global__ void __launch_bounds__(256) k_rerank(const __grid_constant__ RerankPa
     int base = 0;
     for (int s = 0; s < P.S; ++s) {
       const int c = P.cand_cnt[(long long)t * P.S + s];
-      const int32_t* ci = P.cand_idx + ((long long)t * P.S + s) * TC_CAP;
+      const uint2* ce = P.cand + ((long long)t * P.S + s) * TC_CAP;
       for (int e = threadIdx.x; e < c; e += blockDim.x) {
-        const long long item = ci[e];
-        if (csr_contains(P.tr_indices, tlo, thi, (int)item)) {   // a training item: sorts behind every real candidate
+        const long long item = (long long)ce[e].y;
+        if (item >= P.n_items || csr_contains(P.tr_indices, tlo, thi, (int)item)) {   // a padding column / a training item: sorts behind every real candidate
           s_val[base + e] = -INFINITY;
           s_idx[base + e] = 0x7fffffff;
           continue;
@@ -601,7 +615,7 @@ int make_map(CUtensorMap* tm, void* base, long long rows, int Kp, int box_rows =
 struct TcPlan {
   int Kp, KC, S, stages, NB;
   long long T_pad, N_pad;
-  size_t off_vb, off_qb, off_eps, off_cval, off_cidx, off_ccnt, off_ovf, off_bmax, total;
+  size_t off_vb, off_qb, off_eps, off_cand, off_ccnt, off_ovf, off_bmax, total;
   size_t smem;
 };
 
@@ -638,8 +652,7 @@ int plan_tc(const cf_topk_args* a, TcPlan* p) {
   p->off_vb = off; off = align_up(off + (size_t)p->N_pad * p->Kp * 2, 1024);
   p->off_qb = off; off = align_up(off + (size_t)p->T_pad * p->Kp * 2, 1024);
   p->off_eps = off; off = align_up(off + (size_t)p->T_pad * 4, 256);
-  p->off_cval = off; off = align_up(off + (size_t)p->T_pad * S * TC_CAP * 4, 256);
-  p->off_cidx = off; off = align_up(off + (size_t)p->T_pad * S * TC_CAP * 4, 256);
+  p->off_cand = off; off = align_up(off + (size_t)p->T_pad * S * TC_CAP * 8, 256);
   p->off_ccnt = off; off = align_up(off + (size_t)p->T_pad * S * 4, 256);
   p->off_ovf = off; off = align_up(off + (size_t)p->T_pad * 4, 256);
   p->off_bmax = off; off = align_up(off + 256, 256);
@@ -682,8 +695,7 @@ extern "C" int cf_topk_tc(const cf_topk_args* a, void* workspace, int64_t worksp
   __half* Vb = reinterpret_cast<__half*>(ws + p.off_vb);
   __half* Qb = reinterpret_cast<__half*>(ws + p.off_qb);
   float* eps2 = reinterpret_cast<float*>(ws + p.off_eps);
-  float* cval = reinterpret_cast<float*>(ws + p.off_cval);
-  int32_t* cidx = reinterpret_cast<int32_t*>(ws + p.off_cidx);
+  uint2* cand = reinterpret_cast<uint2*>(ws + p.off_cand);
   int32_t* ccnt = reinterpret_cast<int32_t*>(ws + p.off_ccnt);
   int32_t* ovf = reinterpret_cast<int32_t*>(ws + p.off_ovf);
   float* bmax = reinterpret_cast<float*>(ws + p.off_bmax);
@@ -711,7 +723,7 @@ extern "C" int cf_topk_tc(const cf_topk_args* a, void* workspace, int64_t worksp
   TcParams P = {};
   P.T = a->T; P.N = (int)a->n_items; P.KC = p.KC; P.n_tiles = (int)(p.N_pad / p.NB); P.S = p.S; P.stages = p.stages; P.K = a->K;
   P.users = a->users; P.tr_indptr = (const long long*)a->train.indptr; P.tr_indices = a->train.indices;
-  P.eps2 = eps2; P.cand_val = cval; P.cand_idx = cidx; P.cand_cnt = ccnt; P.overflow = ovf;
+  P.eps2 = eps2; P.cand = cand; P.cand_cnt = ccnt; P.overflow = ovf;
   P.dbg_scores = dbg_scores; P.dbg_ld = (long long)align_up((size_t)a->n_items, TC_NW);   // the same stride for both kernels
   dim3 grid((unsigned)(p.T_pad / (TC_MT * TC_M)), (unsigned)p.S);
   if (p.NB == TC_NW) {
@@ -724,7 +736,7 @@ extern "C" int cf_topk_tc(const cf_topk_args* a, void* workspace, int64_t worksp
 
   RerankParams R = {};
   R.U = a->U; R.V = a->V; R.b = a->b; R.ld = a->ld; R.nvec = a->ld / 4; R.kind = a->kind; R.T = a->T; R.S = p.S; R.K = a->K;
-  R.users = a->users; R.cand_val = cval; R.cand_idx = cidx; R.cand_cnt = ccnt; R.overflow = ovf;
+  R.users = a->users; R.cand = cand; R.n_items = (int)a->n_items; R.cand_cnt = ccnt; R.overflow = ovf;
   R.tr_indptr = (const long long*)a->train.indptr; R.tr_indices = a->train.indices;
   R.out_idx = a->out_idx; R.out_val = a->out_val; R.stats = stats;
   int rg = a->T;

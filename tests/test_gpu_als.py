@@ -88,8 +88,9 @@ def test_row_sharded_sweep_equals_whole_sweep(P):
 
 @pytest.mark.parametrize('d,weight', [(128, 3.0), (40, 11.0)])
 def test_short_rows_low_rank_path_and_long_rows_full_solve_in_one_sweep(d, weight):
-    """Rows with at most 64 observed columns take the low-rank (Woodbury) update, longer ones the 128 x 128 Cholesky; both must
-    equal the dense float64 solve of the same normal equations (and CF_ALS_DIRECT=1, the full solve for every row)."""
+    """Every row-length class of the whitened solve (empty; <= 16 and 17..32: one warp per row; 33..128: n x n system from a
+    tcgen05 Gram; > 128: 128 x 128 system from a chunked tcgen05 Gram) must equal the dense float64 solve of the same normal
+    equations, and so must CF_ALS_DIRECT=1 (the direct 128 x 128 solve of every row)."""
     import os
     from scipy.sparse import lil_matrix
     from collaborativefilteringusingtensorflow_b200 import WRMF
@@ -98,7 +99,7 @@ def test_short_rows_low_rank_path_and_long_rows_full_solve_in_one_sweep(d, weigh
     nu, ni, reg = 150, 400, 0.25
     R = lil_matrix((nu, ni), dtype=np.float32)
     for u in range(nu):
-        k = [0, 1, 2, 63, 64, 65, 66, 200][u % 8] if u < 64 else int(rng.integers(0, 130))
+        k = [0, 1, 2, 15, 16, 17, 31, 32, 33, 40, 63, 64, 65, 127, 128, 129, 192, 193, 200, 390][u % 20] if u < 80 else int(rng.integers(0, 150))
         if k:
             R[u, rng.choice(ni, size=k, replace=False)] = 1
     csr = None
