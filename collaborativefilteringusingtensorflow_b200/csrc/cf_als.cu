@@ -644,7 +644,8 @@ __global__ void __launch_bounds__(256, 2) k_als_rows_tc(const __grid_constant__ 
   float* panel = reinterpret_cast<float*>(smem + ((RT_A_BYTES + 127) & ~127));   // [16][64] block column L_ik
   float* zrow = panel + NBK * 64;              // [8]   the right-hand side's block of the current block column
   float* diagA = zrow + 8;                     // [64]  the diagonal block about to be factored
-  float* zvec = diagA + 64;                    // [128] z, then the solution
+  float* dinvs = diagA + 64;                   // [16][64] inverses of the factored diagonal blocks (row-major, lower)
+  float* zvec = dinvs + NBK * 64;              // [128] z, then the solution
   float* svec = zvec + ALS_D;                  // [8][128] per-warp partial sums of the gathered rows / [2][128] row sums
   int* rlist = reinterpret_cast<int*>(svec + 8 * ALS_D);             // [256] rows of this chunk that belong here
   int* ridx = rlist + 256;                                           // [128] the observed columns of a short row
@@ -895,11 +896,22 @@ __global__ void __launch_bounds__(256, 2) k_als_rows_tc(const __grid_constant__ 
               zrow[j] = g[j];
               zvec[BS * kb + j] = g[j];
             }
-          } else if (ty == kb) {             // the diagonal block keeps its factor (the back-substitution reads it from registers)
+          } else if (ty == kb) {             // the diagonal thread publishes L_kk^-1 for the back-substitution (off the critical path:
+                                             // the panel threads are busy with their 8 x 8 solves meanwhile)
 #pragma unroll
-            for (int i = 0; i < BS; ++i)
+            for (int j = 0; j < BS; ++j) {
+              float xc[BS];
+              xc[j] = inv[j];
 #pragma unroll
-              for (int j = 0; j < BS; ++j) a[i][j] = j <= i ? dg[i][j] : 0.f;
+              for (int i = j + 1; i < BS; ++i) {
+                float v = 0.f;
+#pragma unroll
+                for (int q = j; q < i; ++q) v = fmaf(dg[i][q], xc[q], v);
+                xc[i] = -v * inv[i];
+              }
+#pragma unroll
+              for (int i = 0; i < BS; ++i) dinvs[kb * 64 + i * BS + j] = i >= j ? xc[i] : 0.f;
+            }
           } else {                           // L_ik = A_ik L_kk^-T
 #pragma unroll
             for (int i = 0; i < BS; ++i)
@@ -952,31 +964,48 @@ __global__ void __launch_bounds__(256, 2) k_als_rows_tc(const __grid_constant__ 
         }
         __syncthreads();
       }
-      // =========================================================== L^T x = z, block by block out of the register blocks
-      for (int kb = nb - 1; kb >= 0; --kb) {
-        if (ty == kb && tx == kb) {
-          float xb[BS];
+      // =========================================================== L^T x = z: x_kb = L_kk^-T z_kb with the published inverse
+      // blocks (a mat-vec, no division chain); block row kb then removes x_kb from every z_j, j < kb, out of its register
+      // blocks, and the thread of block (kb, kb - 1) -- the last one to touch z_(kb-1) -- finishes x_(kb-1) right away: one
+      // barrier per block column
+      if (ty == nb - 1 && tx == nb - 1) {
+        const float* di = dinvs + (nb - 1) * 64;
+        float xb[BS];
 #pragma unroll
-          for (int k = BS - 1; k >= 0; --k) {
-            float v = zvec[BS * kb + k];
+        for (int j = 0; j < BS; ++j) {
+          float v = 0.f;
 #pragma unroll
-            for (int q = k + 1; q < BS; ++q) v = fmaf(-a[q][k], xb[q], v);
-            xb[k] = v / a[k][k];
-          }
-#pragma unroll
-          for (int k = 0; k < BS; ++k) zvec[BS * kb + k] = xb[k];
+          for (int i = j; i < BS; ++i) v = fmaf(di[i * BS + j], zvec[BS * (nb - 1) + i], v);
+          xb[j] = v;
         }
-        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < BS; ++j) zvec[BS * (nb - 1) + j] = xb[j];
+      }
+      __syncthreads();
+      for (int kb = nb - 1; kb >= 1; --kb) {
         if (ty == kb && tx < kb) {           // z_tx -= L_(kb,tx)^T x_kb
-          float xb[BS];
+          float xb[BS], zj[BS];
 #pragma unroll
           for (int i = 0; i < BS; ++i) xb[i] = zvec[BS * kb + i];
 #pragma unroll
           for (int j = 0; j < BS; ++j) {
-            float s = 0.f;
+            float v = zvec[BS * tx + j];
 #pragma unroll
-            for (int i = 0; i < BS; ++i) s = fmaf(a[i][j], xb[i], s);
-            zvec[BS * tx + j] -= s;
+            for (int i = 0; i < BS; ++i) v = fmaf(-a[i][j], xb[i], v);
+            zj[j] = v;
+          }
+          if (tx == kb - 1) {                // z_(kb-1) is complete: x_(kb-1) = L^-T z_(kb-1)
+            const float* di = dinvs + (kb - 1) * 64;
+#pragma unroll
+            for (int j = 0; j < BS; ++j) {
+              float v = 0.f;
+#pragma unroll
+              for (int i = j; i < BS; ++i) v = fmaf(di[i * BS + j], zj[i], v);
+              zvec[BS * tx + j] = v;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < BS; ++j) zvec[BS * tx + j] = zj[j];
           }
         }
         __syncthreads();
@@ -985,14 +1014,29 @@ __global__ void __launch_bounds__(256, 2) k_als_rows_tc(const __grid_constant__ 
       if (wide) {
         if (tid < P.d) P.X[u * P.ldx + tid] = zvec[tid];
       } else {
-        // xt = W_u^T (weight - t): two halves of the gathered rows, one column per thread
-        const int k = tid & 127, hf = tid >> 7;
-        float acc = 0.f;
-#pragma unroll 8
-        for (int e = hf; e < n; e += 2) acc = fmaf(P.weight - zvec[e], __ldg(P.W + (long long)ridx[e] * ALS_D + k), acc);
-        if (hf == 1) svec[k] = acc;
+        // xt = W_u^T (weight - t): warp w takes the gathered rows w, w + 8, ... (all its loads in flight at once), a lane four
+        // columns; the eight partial sums meet in shared memory
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const int e = warp + 8 * r;
+          v[r] = e < n ? __ldg(reinterpret_cast<const float4*>(P.W + (long long)ridx[e] * ALS_D) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const int e = warp + 8 * r;
+          const float cf = e < n ? P.weight - zvec[e] : 0.f;
+          acc.x = fmaf(cf, v[r].x, acc.x); acc.y = fmaf(cf, v[r].y, acc.y); acc.z = fmaf(cf, v[r].z, acc.z); acc.w = fmaf(cf, v[r].w, acc.w);
+        }
+        *reinterpret_cast<float4*>(svec + warp * ALS_D + 4 * lane) = acc;
         __syncthreads();
-        if (hf == 0 && k < P.d) P.X[u * P.ldx + k] = acc + svec[k];
+        if (tid < P.d) {
+          float x = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) x += svec[w * ALS_D + tid];
+          P.X[u * P.ldx + tid] = x;
+        }
       }
       __syncthreads();                       // zvec / svec / A are rewritten by the next row
     }
@@ -1065,7 +1109,7 @@ static int als_gram(const float* Y, long long n_y, int d, int ldy, float* G, uin
 constexpr int SMALL16_WARPS = 8, SMALL32_WARPS = 5;
 static size_t small_smem(int nmax, int warps) { return (size_t)warps * (nmax * SM_LD + nmax * (nmax + 1)) * 4; }
 static size_t rows_tc_smem() {
-  return (size_t)((RT_A_BYTES + 127) & ~127) + (NBK * 64 + 8 + 64 + ALS_D + 8 * ALS_D) * 4 + (256 + ALS_D) * 4 + 16 + 4 + 10 * 4 + 64 + 1024;
+  return (size_t)((RT_A_BYTES + 127) & ~127) + (NBK * 64 + 8 + 64 + NBK * 64 + ALS_D + 8 * ALS_D) * 4 + (256 + ALS_D) * 4 + 16 + 4 + 10 * 4 + 64 + 1024;
 }
 
 // Solve stage: every row of X from the (complete) Gram G and its observed rows of Y.  With a workspace and weight > 1 the

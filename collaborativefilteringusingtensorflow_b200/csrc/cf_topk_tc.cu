@@ -68,17 +68,25 @@ __device__ __forceinline__ float ord_unkey(unsigned k) { return __uint_as_float(
 
 // Warp-cooperative compaction of ONE row's candidate buffer (n entries): entries [ver, n) were appended WITHOUT looking at
 // the user's training row (a binary search per hit inside the per-thread sweep is a chain of dependent global loads that
-// nothing hides: it was most of the sweep on small catalogues) -- they are checked here, 32 searches in flight; then
+// nothing hides: it was most of the sweep on small catalogues) -- they are checked here; then
 // theta <- (a lower bound within 2^-15 relative of) the K-th largest value among the unmasked entries, keep >= theta - eps2.
 // A compaction stalls its warp and, two tiles later, the CTA's MMA pipeline, and on a 500 k-item catalogue every row needs
 // ~6 of them (the thresholds start at -inf in every CTA): its latency is what the small-catalogue throughput hangs on.
-// Hence: the counting rounds of the radix select reduce with redux.sync (one instruction) instead of a five-step shuffle
-// tree, and stop after the 24 leading bits (any lower bound of the K-th value keeps the superset property).
+// Hence (1) the mask check is a MERGE, not 16 global binary searches per lane: a split sweeps its items in ascending order,
+// so the unchecked entries are ascending and all lie above the last checked one; `tcur` remembers how far into the user's
+// sorted training row the earlier compactions got, the next 32 training items arrive with ONE coalesced load (one per lane)
+// and every entry looks itself up in that register segment with five shuffles -- one memory round trip per compaction
+// instead of seven dependent ones; (2) the counting rounds of the radix select reduce with redux.sync (one instruction)
+// instead of a five-step shuffle tree, and stop after the 24 leading bits (any lower bound of the K-th value keeps the
+// superset property).
 __device__ __forceinline__ void compact_row(uint2* ce, int n, int ver, int K, float eps2, const int32_t* tr_indices,
-                                            long long tlo, long long thi, int lane, int n_items, float& theta_out, int& cnt_out) {
+                                            long long& tcur, long long thi, int lane, int n_items, float& theta_out, int& cnt_out) {
   constexpr int EPL = TC_CAP / 32;
   float v[EPL];
   int32_t id[EPL];
+  const bool masking = thi > tcur && n > ver;
+  const int last_x = masking ? (int)__ldcg(&ce[n - 1].y) : -1;       // the largest unchecked item id (entries ascend)
+  int seg = (masking && tcur + lane < thi) ? __ldg(tr_indices + tcur + lane) : 0x7fffffff;
 #pragma unroll
   for (int i = 0; i < EPL; ++i) {
     const int e = lane + 32 * i;
@@ -90,36 +98,31 @@ __device__ __forceinline__ void compact_row(uint2* ce, int n, int ver, int K, fl
       id[i] = -1;
     }
   }
-  if (thi > tlo) {
-    // EPL binary searches per lane, advanced TOGETHER one probe at a time: the probes of a round are independent loads
-    int slo[EPL], shi[EPL];
-    const int len = (int)(thi - tlo);
-#pragma unroll
-    for (int i = 0; i < EPL; ++i) {
-      const int e = lane + 32 * i;
-      const bool chk = e >= ver && id[i] >= 0;
-      slo[i] = 0;
-      shi[i] = chk ? len : 0;
-    }
-    const int* row = tr_indices + tlo;
-    for (int span = len; span > 0; span >>= 1) {     // ceil(log2(len + 1)) rounds empty every interval
+  if (masking) {
+    long long pos = tcur;
+    for (;;) {
+      const int seg_next = (pos + 32 + lane < thi) ? __ldg(tr_indices + pos + 32 + lane) : 0x7fffffff;   // in flight during the lookups
 #pragma unroll
       for (int i = 0; i < EPL; ++i) {
-        if (slo[i] < shi[i]) {
-          const int mid = (slo[i] + shi[i]) >> 1;
-          const int w = __ldg(row + mid);
-          if (w == id[i]) {                          // a training item: drop it
-            v[i] = __uint_as_float(0xffffffffu);
-            id[i] = -1;
-            shi[i] = slo[i];
-          } else if (w < id[i]) {
-            slo[i] = mid + 1;
-          } else {
-            shi[i] = mid;
-          }
+        const int x = (lane + 32 * i >= ver) ? id[i] : -1;           // (checked entries and empty slots look up -1: never found)
+        int lb = 0;                                                   // lower bound of x among the 32 sorted lanes
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+          const int probe = __shfl_sync(0xffffffffu, seg, lb + step - 1);
+          if (probe < x) lb += step;
+        }
+        const int found = __shfl_sync(0xffffffffu, seg, lb & 31);
+        if (found == x && lb < 32 && x >= 0) {                        // a training item: drop it
+          v[i] = __uint_as_float(0xffffffffu);
+          id[i] = -1;
         }
       }
+      const int c = __popc(__ballot_sync(0xffffffffu, seg <= last_x));   // (sorted: a prefix of the lanes)
+      pos += c;
+      if (c < 32) break;                                              // the segment reaches beyond the last entry (or the row ended)
+      seg = seg_next;
     }
+    tcur = pos;
   }
   unsigned key[EPL];
 #pragma unroll
@@ -291,6 +294,34 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     // row), per chunk a single FMNMX3 tree over the 32 scores and one compare; the scan + append of a chunk that holds a
     // hit is the rare path.
     const bool dbg = P.dbg_scores != nullptr;
+    // compaction of the rows of the lanes in `need`, one row at a time by the whole warp
+    auto compact_lanes = [&](unsigned need) {
+      while (need) {
+        const int l = __ffs(need) - 1;
+        need &= need - 1;
+        uint2* rce = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(ce), l));
+        const int rn = __shfl_sync(0xffffffffu, cnt, l);
+        const int rver = __shfl_sync(0xffffffffu, ver, l);
+        const float re = __shfl_sync(0xffffffffu, eps2, l);
+        long long rcur = __shfl_sync(0xffffffffu, tlo, l);        // (tlo is the row's cursor into its training row)
+        const long long rhi = __shfl_sync(0xffffffffu, thi, l);
+        float nth;
+        int ncnt;
+        compact_row(rce, rn, rver, P.K, re, P.tr_indices, rcur, rhi, lane, P.N, nth, ncnt);
+        if (lane == l) {
+          tlo = rcur;
+          theta = nth;
+          cnt = ncnt;
+          ver = ncnt;
+          if (ncnt > TC_CAP - 128) {  // too many items within 2 eps of the K-th best: give this row to the exact kernel
+            overflowed = true;
+            theta = INFINITY;
+            cnt = 0;
+            ver = 0;
+          }
+        }
+      }
+    };
     for (int t = 0; t < nt; ++t) {
       const int acc = WIDE ? mt : (t & 1);
       mbar_wait(tfull + acc, WIDE ? ((uint32_t)t & 1u) : ((uint32_t)(t >> 1) & 1u));
@@ -299,49 +330,17 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(WIDE ? mt * NB : acc * (TC_MT * TC_N) + mt * TC_N);
 #pragma unroll 1
       for (int hb = 0; hb < NB / 128; ++hb) {
-        unsigned need = __ballot_sync(0xffffffffu, cnt > TC_CAP - 128);   // make room for the next 128 columns
-        while (need) {
-          const int l = __ffs(need) - 1;
-          need &= need - 1;
-          uint2* rce = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(ce), l));
-          const int rn = __shfl_sync(0xffffffffu, cnt, l);
-          const int rver = __shfl_sync(0xffffffffu, ver, l);
-          const float re = __shfl_sync(0xffffffffu, eps2, l);
-          const long long rlo = __shfl_sync(0xffffffffu, tlo, l), rhi = __shfl_sync(0xffffffffu, thi, l);
-          float nth;
-          int ncnt;
-          compact_row(rce, rn, rver, P.K, re, P.tr_indices, rlo, rhi, lane, P.N, nth, ncnt);
-          if (lane == l) {
-            theta = nth;
-            cnt = ncnt;
-            ver = ncnt;
-            if (ncnt > TC_CAP - 128) {  // too many items within 2 eps of the K-th best: give this row to the exact kernel
-              overflowed = true;
-              theta = INFINITY;
-              cnt = 0;
-              ver = 0;
-            }
-          }
-        }
+        compact_lanes(__ballot_sync(0xffffffffu, cnt > TC_CAP - 128));   // make room for the next 128 columns
         const float thr = theta - eps2;   // (theta only moves at a compaction)
-#pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
-          const int c = hb * 4 + cc;
-          uint32_t r[32];
-          tc_ld32(tbase + (uint32_t)(c * 32), r);
-          tc_wait_ld();
-          if (c == NB / 32 - 1) {   // every column of this accumulator is in registers: hand it back to the MMA warp
-            tc_fence_before();
-            mbar_arrive(tempty + acc);
-          }
+        // One chunk of 32 scores of this thread's row.  Group maxima of 8 (FMNMX3 trees), then their maximum: a chunk without
+        // a hit costs 18 instructions; a hit makes the warp scan only the groups that hold one (on a 500 k-item catalogue 6 %
+        // of a row's chunks hold a hit, so 86 % of a WARP's chunks do: the scan is the common path there, and it appends
+        // with one 8-byte store per hit; padding columns of the last tile are dropped by the compaction and the re-rank).
+        auto sweep = [&](const uint32_t (&r)[32], int c) {
           if (dbg && valid) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) P.dbg_scores[(long long)row * P.dbg_ld + n0 + c * 32 + j] = __uint_as_float(r[j]);
           }
-          // group maxima of 8 (FMNMX3 trees), then their maximum: a chunk without a hit costs 18 instructions; a hit makes the
-          // warp scan only the groups that hold one (on a 500 k-item catalogue 6 % of a row's chunks hold a hit, so 86 % of
-          // a WARP's chunks do: the scan is the common path there, and it appends with one 8-byte store per hit; padding
-          // columns of the last tile are dropped by the compaction and the re-rank, not here)
           float mg[4];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -365,9 +364,32 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
               }
             }
           }
+        };
+        // software-pipelined TMEM reads: the load of chunk c + 1 is in flight while chunk c is swept (under MMA load a
+        // tcgen05.ld takes 350+ cycles: in sequence with the sweep the epilogue of a tile outlasted the tile's MMAs, and the
+        // issuing thread spent 23 % of its time waiting for an accumulator to drain)
+        uint32_t ra[32], rb[32];
+        tc_ld32(tbase + (uint32_t)(hb * 128), ra);
+#pragma unroll
+        for (int cc = 0; cc < 4; cc += 2) {
+          const int c = hb * 4 + cc;
+          tc_wait_ld(ra);
+          tc_ld32(tbase + (uint32_t)((c + 1) * 32), rb);
+          sweep(ra, c);
+          tc_wait_ld(rb);
+          if (cc + 2 < 4) {
+            tc_ld32(tbase + (uint32_t)((c + 2) * 32), ra);
+          } else if (c + 1 == NB / 32 - 1) {   // every column of this accumulator is in registers: hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(tempty + acc);
+          }
+          sweep(rb, c + 1);
         }
       }
     }
+    // a last compaction leaves K + the 2-eps band per (row, split) instead of whatever arrived since the previous one
+    // (~280 -> ~110 at K = 100): the exact re-rank scores and sorts that many fewer candidates
+    compact_lanes(__ballot_sync(0xffffffffu, valid && !overflowed && cnt > P.K + 16));
     if (valid) {
       P.cand_cnt[(long long)row * P.S + split] = cnt;
       if (overflowed) P.overflow[row] = 1;
@@ -499,14 +521,14 @@ __device__ __forceinline__ bool rr_before(double va, int ia, double vb, int ib) 
 __global__ void __launch_bounds__(256) k_rerank(const __grid_constant__ RerankParams P) {
   __shared__ double s_val[RR_CAP];
   __shared__ int s_idx[RR_CAP];
-  __shared__ __align__(16) float s_u[512];
+  __shared__ __align__(16) double s_u[512];   // the query row, widened once (fp32 -> fp64 conversions run at a quarter of the FMA rate)
   for (int t = blockIdx.x; t < P.T; t += gridDim.x) {
     if (P.overflow[t]) {            // recomputed by the exact streaming kernel
       if (P.stats && threadIdx.x == 0) atomicAdd(P.stats, 1);
       continue;
     }
     const long long u = P.users ? P.users[t] : t;
-    for (int k = threadIdx.x; k < P.ld; k += blockDim.x) s_u[k] = P.U[u * P.ld + k];
+    for (int k = threadIdx.x; k < P.ld; k += blockDim.x) s_u[k] = (double)P.U[u * P.ld + k];
     const long long tlo = P.tr_indptr ? P.tr_indptr[u] : 0, thi = P.tr_indptr ? P.tr_indptr[u + 1] : 0;
     int total = 0;
     for (int s = 0; s < P.S; ++s) total += P.cand_cnt[(long long)t * P.S + s];
@@ -529,23 +551,25 @@ __global__ void __launch_bounds__(256) k_rerank(const __grid_constant__ RerankPa
         const float4* vp = reinterpret_cast<const float4*>(P.V + item * P.ld);
         double sc = 0.0;
         if (P.kind == CF_SCORE_NEG_SQDIST) {
+#pragma unroll 8
           for (int k4 = 0; k4 < P.nvec; ++k4) {
             const float4 v = __ldg(vp + k4);
-            const float4 qv = *reinterpret_cast<const float4*>(s_u + 4 * k4);
-            double df = (double)qv.x - (double)v.x; sc = __dadd_rn(sc, __dmul_rn(df, df));
-            df = (double)qv.y - (double)v.y; sc = __dadd_rn(sc, __dmul_rn(df, df));
-            df = (double)qv.z - (double)v.z; sc = __dadd_rn(sc, __dmul_rn(df, df));
-            df = (double)qv.w - (double)v.w; sc = __dadd_rn(sc, __dmul_rn(df, df));
+            const double* q = s_u + 4 * k4;
+            double df = q[0] - (double)v.x; sc = __dadd_rn(sc, __dmul_rn(df, df));
+            df = q[1] - (double)v.y; sc = __dadd_rn(sc, __dmul_rn(df, df));
+            df = q[2] - (double)v.z; sc = __dadd_rn(sc, __dmul_rn(df, df));
+            df = q[3] - (double)v.w; sc = __dadd_rn(sc, __dmul_rn(df, df));
           }
           sc = -sc;
         } else {
+#pragma unroll 8
           for (int k4 = 0; k4 < P.nvec; ++k4) {
             const float4 v = __ldg(vp + k4);
-            const float4 qv = *reinterpret_cast<const float4*>(s_u + 4 * k4);
-            sc = fma((double)qv.x, (double)v.x, sc);
-            sc = fma((double)qv.y, (double)v.y, sc);
-            sc = fma((double)qv.z, (double)v.z, sc);
-            sc = fma((double)qv.w, (double)v.w, sc);
+            const double* q = s_u + 4 * k4;
+            sc = fma(q[0], (double)v.x, sc);
+            sc = fma(q[1], (double)v.y, sc);
+            sc = fma(q[2], (double)v.z, sc);
+            sc = fma(q[3], (double)v.w, sc);
           }
           if (P.kind == CF_SCORE_DOT_BIAS) sc = __dadd_rn(sc, (double)__ldg(P.b + item));
         }
