@@ -590,7 +590,9 @@ def als_slice(cfg, device, pk):
                           cholesky=dict(flops=c_flops, tflops=c_flops / s / 1e12, frac_of_fp32_fma_peak=c_flops / s / 1e12 / fma_peak,
                                         fp32_fma_peak_tflops=fma_peak),
                           gather=dict(bytes=g_bytes, GBs=g_bytes / s / 1e9, frac_of_hbm_peak=g_bytes / s / 1e9 / pk['hbm'])),
-               note='fractions are each term\'s work over the WHOLE half-sweep time (they overlap inside one kernel)',
+               note='the three terms are the ALGORITHMIC work of the direct form (SURVEY 8d: per-row Gram 2 nnz d^2, d^3/3 Cholesky per row, '
+                    'nnz * 4d gathered bytes), each over the WHOLE half-sweep time; the solver itself does less: rows with n <= 128 observed '
+                    'columns solve an n x n system in the whitened basis (DESIGN 4.6), so these are equivalent rates, not pipe utilisation',
                phases_ms=phases)
     del m, eng, csr
     torch.cuda.empty_cache()

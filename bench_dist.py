@@ -122,6 +122,33 @@ def sharded_topk(B_, model, csr, n_items_global, wl, Tq, rank, world, device, pk
                 frac_of_tensor_peak_per_gpu=tf / world / pk['bf16'], fallback_rows_rank0=int(eng.tc_stats[0].item()))
 
 
+def user_sharded_topk_bench(B_, model, csr, n_items_global, wl, Tq, rank, world, device, pk):
+    """Full-catalogue top-100 of Tq users in total, Tq / N of them on every rank (each rank's OWN first users, with their own
+    training rows): the item table is all-gathered inside the timed region, then every rank scores its users against the
+    whole catalogue.  value = Tq / max-over-ranks time."""
+    from collaborativefilteringusingtensorflow_b200.dist import user_sharded_topk
+    eng = model.engine
+    Tl = min((Tq + world - 1) // world, eng.n_users)
+    users = torch.arange(Tl, dtype=torch.int32, device=device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    user_sharded_topk(eng, users[:4096], 100, csr, n_items_global, world, rank, method='tensor', return_values=False)
+    user_sharded_topk(eng, users, 100, csr, n_items_global, world, rank, method='tensor', return_values=False)   # sizes the workspace
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    user_sharded_topk(eng, users, 100, csr, n_items_global, world, rank, method='tensor', return_values=False)
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    tms = _max_over_ranks(e0.elapsed_time(e1), device)
+    fl = 2.0 * n_items_global * wl['d'] * Tl * world
+    tf = fl / (tms * 1e-3) / 1e12
+    return dict(metric='users/s full-catalog top-100 (mask train items), users sharded over %d GPUs: the row-sharded item table is '
+                       'all-gathered (inside the timed region) and every rank scores its own users against the whole catalogue' % world,
+                value=Tl * world / (tms * 1e-3), unit='users/s', users=Tl * world, n_items=n_items_global, ms=tms, tflops_aggregate=tf,
+                frac_of_tensor_peak_per_gpu=tf / world / pk['bf16'], fallback_rows_rank0=int(eng.tc_stats[0].item()))
+
+
 def step_line(B_, wl, args, world, K, Wm, r, n_items_global, tr, pk):
     B = args.batch
     ms = r['ms']
@@ -164,7 +191,9 @@ def run_distributed(args, rank, world, device):
     clocks = clk.stop(r['t0'], r['t1']) if rank == 0 else None
     topk = None
     if args.topk_users > 0:
-        topk = sharded_topk(B_, model, csr, n_items_global, wl, min(args.topk_users, wl['n_users']), rank, world, device, pk)
+        Tq = min(args.topk_users, wl['n_users'])
+        topk = user_sharded_topk_bench(B_, model, csr, n_items_global, wl, Tq, rank, world, device, pk)
+        topk['item_sharded'] = sharded_topk(B_, model, csr, n_items_global, wl, Tq, rank, world, device, pk)
     line = step_line(B_, wl, args, world, K, Wm, r, n_items_global, tr, pk)
     tr.close()
     del model, csr, tr
@@ -179,7 +208,8 @@ def run_distributed(args, rank, world, device):
         c5 = step_line(B_, w5, args, world, K5, 3, r5, w5['n_items'], tr5, pk)
         c5['workload'] = w5['desc'] + ' -- at %d GPUs: %d users, %d interactions in total' % (world, world * w5['n_users'], world * csr5.nnz)
         if args.topk_users > 0:
-            c5['topk'] = sharded_topk(B_, m5, csr5, w5['n_items'], w5, min(args.topk_users, w5['n_users']), rank, world, device, pk)
+            c5['topk'] = user_sharded_topk_bench(B_, m5, csr5, w5['n_items'], w5, min(args.topk_users, w5['n_users']), rank, world, device, pk)
+            c5['topk']['item_sharded'] = sharded_topk(B_, m5, csr5, w5['n_items'], w5, min(args.topk_users, w5['n_users']), rank, world, device, pk)
         tr5.close()
         del m5, csr5, tr5
         torch.cuda.empty_cache()

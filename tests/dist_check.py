@@ -109,6 +109,32 @@ def main():
         if rank == 0:
             print('%s sharded top-%d, sliced merge (all-to-all) == all-gather merge on every rank: %s' % (kind, K, bool(flag.item())))
             ok &= bool(flag.item())
+        # the user-sharded form: the item table is all-gathered, every rank scores ITS slice of the users against the
+        # whole catalogue (global item ids in the mask); the slices together are the single-GPU lists
+        from collaborativefilteringusingtensorflow_b200.dist import user_sharded_topk
+        c_u = (T + world - 1) // world
+        ulo, uhi = min(T, rank * c_u), min(T, (rank + 1) * c_u)
+        saved_U, saved_nu = local_m.engine.U, local_m.engine.n_users
+        local_m.engine.U, local_m.engine.n_users = q.contiguous(), T       # (the query tile stands in for the rank's own users)
+        try:
+            if uhi > ulo:
+                full_rows = lil_matrix((T, ni), dtype=np.float32)           # the mask is indexed by user id
+                for t in range(ulo, uhi):
+                    full_rows[t, tra.rows[t]] = 1
+                ui, uv = user_sharded_topk(local_m.engine, torch.arange(ulo, uhi, dtype=torch.int32, device=dev), K,
+                                           DeviceCSR.from_scipy(full_rows, dev), ni, world, rank)
+                same = bool(torch.equal(ui, gi[ulo:uhi]) and torch.equal(uv, gv[ulo:uhi]))
+            else:
+                from collaborativefilteringusingtensorflow_b200.dist import gather_item_table
+                gather_item_table(local_m.engine, ni, world, rank)          # (collective: every rank takes part)
+                same = True
+        finally:
+            local_m.engine.U, local_m.engine.n_users = saved_U, saved_nu
+        flag = torch.tensor([int(same)], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print('%s user-sharded top-%d (gathered item table) == all-gather merge on every rank: %s' % (kind, K, bool(flag.item())))
+            ok &= bool(flag.item())
     # ---- metrics: users sharded, sums all-reduced (every rank gets the global values)
     from collaborativefilteringusingtensorflow_b200.dist import DistributedALS, distributed_evaluate
     from collaborativefilteringusingtensorflow_b200.metrics.ranking import evaluateCV
