@@ -322,14 +322,15 @@ def time_training(wl, csr, B, K, Wm, device, optimizer, update, pk):
     """Warm-up + exactly K timed minibatches (CUDA events on the launching stream) + per-kernel event times of K more.
     Returns (model, sampler, dict)."""
     import torch
-    model = make_model(wl, device, optimizer=optimizer, update=update)
+    model = make_model(wl, device, optimizer=optimizer, update=update, batch_size=B)
     eng = model.engine
     sampler = make_sampler(wl, csr, B, SEED, device)
 
     def run_steps(n, profile=None):
-        chunk = sampler.next_chunk(n)                       # ONE sampler launch for the n minibatches
         if profile is None:
-            return model._train_arrays(chunk, B)
+            return model._epoch(sampler, n)                 # the product's own epoch loop: one sampler launch per minibatch
+                                                            # (at B = 2^20), issued on a side stream one minibatch ahead
+        chunk = sampler.next_chunk(n)
         return eng.train_batches(chunk[0], chunk[1], chunk[2] if len(chunk) > 2 else None, batch_size=B, profile=profile)
 
     run_steps(max(Wm, 3))                                   # warm-up (also CML's one-time whole-table clip)

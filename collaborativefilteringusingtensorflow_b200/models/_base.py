@@ -1,6 +1,7 @@
 """Shared driver logic of the four model classes: the epoch loop, full-catalog recommendation and evaluation of
 reference src/models/pl/models/bprmf.py:90-170 (identical skeleton in cml.py, gbprmf.py, basic/models/wrmf.py)."""
 import datetime as dt
+import os
 
 from ..engine import FactorEngine
 from ..metrics import ranking
@@ -80,10 +81,40 @@ class RankingModelBase(object):
         if hasattr(sampler, 'next_chunk'):
             rows = getattr(sampler, 'rows_per_batch', self.batch_size)
             chunk = max(1, min(n_batches, (1 << 22) // max(1, rows * 8)))
-            while done < n_batches:
-                n = min(chunk, n_batches - done)
-                losses.append(self._train_arrays(sampler.next_chunk(n), rows))
-                done += n
+            sizes = [min(chunk, n_batches - lo) for lo in range(0, n_batches, chunk)]
+            # The sampler launch of chunk j + 1 can run on a side stream while chunk j trains: a batch is a pure function of
+            # (seed, epoch, batch index) and reads nothing the steps write -- the reference's producer threads overlap the
+            # same way (sampler_ranking.py:40-50).  Measured on configs[1]'s shape (B = 2^20): BPR W=1 1.68 -> 1.62 ms per
+            # minibatch, GBPR 3.37 -> 3.17 ms, but CML 2.68 -> 2.77 ms: its step kernel needs all four resident blocks
+            # per SM and the sampler's blocks take their slots.  Default: on, except for CML; CF_SAMPLE_OVERLAP=0/1 forces it.
+            want = os.environ.get('CF_SAMPLE_OVERLAP', '')
+            overlap = (want == '1' or (want != '0' and self._kind != 'cml')) and len(sizes) > 1 and self.engine.device.type == 'cuda'
+            if not overlap:
+                for n in sizes:
+                    losses.append(self._train_arrays(sampler.next_chunk(n), rows))
+                return torch.cat(losses)
+            main = torch.cuda.current_stream(self.engine.device)
+            if getattr(self, '_sample_stream', None) is None:
+                self._sample_stream = torch.cuda.Stream(self.engine.device)
+            side = self._sample_stream
+            side.wait_stream(main)                       # (nothing sampled here may start before what precedes the epoch)
+
+            def sample(n):
+                with torch.cuda.stream(side):
+                    arrays = sampler.next_chunk(n)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                return arrays, ev
+            nxt = sample(sizes[0])
+            for j, n in enumerate(sizes):
+                arrays, ev = nxt
+                if j + 1 < len(sizes):
+                    nxt = sample(sizes[j + 1])
+                main.wait_event(ev)
+                for t in arrays:
+                    if t is not None:
+                        t.record_stream(main)            # allocated on the side stream, consumed on this one
+                losses.append(self._train_arrays(arrays, rows))
         else:   # any object with the reference's next_batch() (numpy arrays): upload batch by batch
             while done < n_batches:
                 batch = sampler.next_batch()
