@@ -181,7 +181,7 @@ class ClockSampler(object):
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
         for r in rows:
@@ -189,13 +189,14 @@ class ClockSampler(object):
             try:
                 sm.append(float(f[0]))
                 mx.append(float(f[1]))
+                pw.append(float(f[2]))
             except Exception:
                 continue
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith('active'):
                     reasons.add(n)
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+                    reasons=sorted(reasons), samples=len(sm), power_w=float(np.median(pw)) if pw else None)
 
 
 # ---------------------------------------------------------------------------------------------- CPU baseline (oracle)
@@ -415,18 +416,26 @@ def time_e2e(model, sampler, B, K, device, step=None, pre=None):
 
 def time_topk(engine, users, mask, K=100, warm=4096):
     """users/s of the tensor-core top-K over all `users` in ONE call (whole call: operand prep, tcgen05 candidate pass,
-    exact re-rank, fallback rows); a short warm-up call first; plain time of the one timed call."""
+    exact re-rank, fallback rows); a short warm-up call first; plain time of the one timed call.  SM clocks and power are
+    sampled during the timed call: a long tensor-core sweep runs into the board's power cap (sw_power_cap, SM clock well
+    below max), which is why the fraction of the SUSTAINED tensor peak is reported next to the burst one."""
     import torch
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     engine.topk(users[:warm], K, mask, method='tensor')
     engine.topk(users, K, mask, method='tensor')             # sizes the workspace (first-time cudaMalloc) -- not timed
     torch.cuda.synchronize()
+    clk = ClockSampler(engine.device.index or 0)
+    clk.start()
+    time.sleep(0.25)
+    t0 = time.time()
     e0.record()
     engine.topk(users, K, mask, method='tensor')
     e1.record()
     torch.cuda.synchronize()
+    t1 = time.time()
+    clocks = clk.stop(t0, t1)
     st = engine.tc_stats.cpu().numpy()
-    return e0.elapsed_time(e1), int(st[0]), float(st[1]) / max(1, len(users) - int(st[0]))
+    return e0.elapsed_time(e1), int(st[0]), float(st[1]) / max(1, len(users) - int(st[0])), clocks
 
 
 def topk_object(ms, T, n_items, d, fb, cand, pk, **extra):
@@ -487,12 +496,12 @@ def run_ours(args):
         g = torch.Generator(device=device)
         g.manual_seed(SEED)
         users = torch.randperm(wl['n_users'], device=device, generator=g)[:Tq].to(torch.int32)   # Philox-chosen sample
-        tk_ms, fb, cand = time_topk(eng, users, csr)
+        tk_ms, fb, cand, tk_clk = time_topk(eng, users, csr)
         topk = topk_object(tk_ms, Tq, wl['n_items'], wl['d'], fb, cand, pk,
                            metric='users/s full-catalog top-100 (mask train items), exact result via tensor-core candidate pass',
                            kernels='k_prep x2 + k_topk_tc (tcgen05.mma fp16 operands, fp32 TMEM accumulators, TMA) + k_rerank (fp64) '
                                    '+ k_topk_exact (fallback rows)',
-                           model='the %s model trained above' % wl['model'])
+                           model='the %s model trained above' % wl['model'], clocks=tk_clk)
         if args.topk_c5_items > 0:
             # configs[4]'s catalogue on one GPU (item-sharded over P GPUs: see the N > 1 lines): BPRMF scoring, 10M items
             from collaborativefilteringusingtensorflow_b200.engine import FactorEngine
@@ -501,8 +510,8 @@ def run_ours(args):
             big = FactorEngine('bpr', Tq, args.topk_c5_items, 128, device, seed=7)
             big.accU = big.accV = None                      # scoring only
             uq = torch.arange(Tq, dtype=torch.int32, device=device)
-            ms5, fb5, cand5 = time_topk(big, uq, None)
-            topk['c5_catalogue'] = topk_object(ms5, Tq, args.topk_c5_items, 128, fb5, cand5, pk)
+            ms5, fb5, cand5, clk5 = time_topk(big, uq, None)
+            topk['c5_catalogue'] = topk_object(ms5, Tq, args.topk_c5_items, 128, fb5, cand5, pk, clocks=clk5)
             del big
             torch.cuda.empty_cache()
 

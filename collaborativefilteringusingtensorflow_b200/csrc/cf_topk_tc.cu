@@ -154,6 +154,102 @@ __device__ __forceinline__ void compact_row(uint2* ce, int n, int ver, int K, fl
   cnt_out = pos;
 }
 
+// The per-thread state of one query row's candidate buffer (one per (row, item split) -- and, in the paired kernel, per column
+// half), shared by both sweep kernels.
+struct RowSweep {
+  float theta, eps2;
+  int cnt, ver;              // entries [0, ver) of the buffer are known not to be training items
+  long long tcur, thi;       // cursor into / end of the user's sorted training row
+  uint2* ce;
+  bool valid, overflowed;
+
+  __device__ __forceinline__ void init(const TcParams& P, int row, long long buffer) {
+    valid = row < P.T;
+    theta = valid ? -INFINITY : INFINITY;
+    cnt = 0;
+    ver = 0;
+    eps2 = valid ? P.eps2[row] : 0.f;
+    tcur = 0;
+    thi = 0;
+    if (valid && P.tr_indptr) {
+      const long long u = P.users ? P.users[row] : row;
+      tcur = P.tr_indptr[u];
+      thi = P.tr_indptr[u + 1];
+    }
+    ce = P.cand + buffer * TC_CAP;
+    overflowed = false;
+  }
+
+  // compaction of the rows of the lanes in `need`, one row at a time by the whole warp
+  __device__ __forceinline__ void compact(unsigned need, int lane, const TcParams& P) {
+    while (need) {
+      const int l = __ffs(need) - 1;
+      need &= need - 1;
+      uint2* rce = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(ce), l));
+      const int rn = __shfl_sync(0xffffffffu, cnt, l);
+      const int rver = __shfl_sync(0xffffffffu, ver, l);
+      const float re = __shfl_sync(0xffffffffu, eps2, l);
+      long long rcur = __shfl_sync(0xffffffffu, tcur, l);
+      const long long rhi = __shfl_sync(0xffffffffu, thi, l);
+      float nth;
+      int ncnt;
+      compact_row(rce, rn, rver, P.K, re, P.tr_indices, rcur, rhi, lane, P.N, nth, ncnt);
+      if (lane == l) {
+        tcur = rcur;
+        theta = nth;
+        cnt = ncnt;
+        ver = ncnt;
+        if (ncnt > TC_CAP - 128) {  // too many items within 2 eps of the K-th best: give this row to the exact kernel
+          overflowed = true;
+          theta = INFINITY;
+          cnt = 0;
+          ver = 0;
+        }
+      }
+    }
+  }
+
+  // One chunk of 32 scores (items item0 ..).  Group maxima of 8 (FMNMX3 trees), then their maximum: a chunk without a hit
+  // costs 18 instructions; a hit makes the warp scan only the groups that hold one (on a 500 k-item catalogue 6 % of a
+  // row's chunks hold a hit, so 86 % of a WARP's chunks do: the scan is the common path there, and it appends with one
+  // 8-byte store per hit; padding columns of the last tile are dropped by the compaction and the re-rank).
+  __device__ __forceinline__ void sweep(const uint32_t (&r)[32], int item0, float thr) {
+    float mg[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float x = fmaxf(fmaxf(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1])), __uint_as_float(r[8 * g + 2]));
+      x = fmaxf(fmaxf(x, __uint_as_float(r[8 * g + 3])), __uint_as_float(r[8 * g + 4]));
+      x = fmaxf(fmaxf(x, __uint_as_float(r[8 * g + 5])), __uint_as_float(r[8 * g + 6]));
+      mg[g] = fmaxf(x, __uint_as_float(r[8 * g + 7]));
+    }
+    const float m = fmaxf(fmaxf(fmaxf(mg[0], mg[1]), mg[2]), mg[3]);
+    if (m >= thr) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (mg[g] >= thr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (__uint_as_float(r[8 * g + j]) >= thr) {
+              ce[cnt] = make_uint2(r[8 * g + j], (unsigned)(item0 + 8 * g + j));
+              ++cnt;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // a last compaction leaves K + the 2-eps band per buffer instead of whatever arrived since the previous one
+  // (~280 -> ~110 at K = 100): the exact re-rank scores and sorts that many fewer candidates
+  __device__ __forceinline__ void finish(const TcParams& P, int row, long long buffer, int lane) {
+    compact(__ballot_sync(0xffffffffu, valid && !overflowed && cnt > P.K + 16), lane, P);
+    if (valid) {
+      P.cand_cnt[buffer] = cnt;
+      if (overflowed) P.overflow[row] = 1;
+    }
+  }
+};
+
 template <int NB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmV, const __grid_constant__ TcParams P) {
@@ -275,53 +371,14 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     const int ew = warp - 4;
     const int mt = ew >> 2, q = warp & 3;
     const int row = row0 + mt * TC_M + q * 32 + lane;
-    const bool valid = row < P.T;
-    float theta = valid ? -INFINITY : INFINITY;
-    int cnt = 0, ver = 0;   // entries [0, ver) of the buffer are known not to be training items
-    const float eps2 = valid ? P.eps2[row] : 0.f;
-    long long tlo = 0, thi = 0;
-    if (valid && P.tr_indptr) {
-      const long long u = P.users ? P.users[row] : row;
-      tlo = P.tr_indptr[u];
-      thi = P.tr_indptr[u + 1];
-    }
-    uint2* ce = P.cand + ((long long)row * P.S + split) * TC_CAP;
-    bool overflowed = false;
-
+    const long long buffer = (long long)row * P.S + split;
+    RowSweep rs;
+    rs.init(P, row, buffer);
     // The sweep costs instructions, not bandwidth: ncu showed ~110 warp instructions per 32 scores in the first version
     // (room check, four group maxima, four reconvergence points per chunk) and the epilogue warps busy 80 % of the time,
     // with instruction-fetch stalls on top.  Now: ONE room check per 128 columns (a block appends at most 128 entries per
-    // row), per chunk a single FMNMX3 tree over the 32 scores and one compare; the scan + append of a chunk that holds a
-    // hit is the rare path.
+    // row), per chunk 18 instructions unless it holds a hit (RowSweep::sweep).
     const bool dbg = P.dbg_scores != nullptr;
-    // compaction of the rows of the lanes in `need`, one row at a time by the whole warp
-    auto compact_lanes = [&](unsigned need) {
-      while (need) {
-        const int l = __ffs(need) - 1;
-        need &= need - 1;
-        uint2* rce = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(ce), l));
-        const int rn = __shfl_sync(0xffffffffu, cnt, l);
-        const int rver = __shfl_sync(0xffffffffu, ver, l);
-        const float re = __shfl_sync(0xffffffffu, eps2, l);
-        long long rcur = __shfl_sync(0xffffffffu, tlo, l);        // (tlo is the row's cursor into its training row)
-        const long long rhi = __shfl_sync(0xffffffffu, thi, l);
-        float nth;
-        int ncnt;
-        compact_row(rce, rn, rver, P.K, re, P.tr_indices, rcur, rhi, lane, P.N, nth, ncnt);
-        if (lane == l) {
-          tlo = rcur;
-          theta = nth;
-          cnt = ncnt;
-          ver = ncnt;
-          if (ncnt > TC_CAP - 128) {  // too many items within 2 eps of the K-th best: give this row to the exact kernel
-            overflowed = true;
-            theta = INFINITY;
-            cnt = 0;
-            ver = 0;
-          }
-        }
-      }
-    };
     for (int t = 0; t < nt; ++t) {
       const int acc = WIDE ? mt : (t & 1);
       mbar_wait(tfull + acc, WIDE ? ((uint32_t)t & 1u) : ((uint32_t)(t >> 1) & 1u));
@@ -330,44 +387,9 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(WIDE ? mt * NB : acc * (TC_MT * TC_N) + mt * TC_N);
 #pragma unroll 1
       for (int hb = 0; hb < NB / 128; ++hb) {
-        compact_lanes(__ballot_sync(0xffffffffu, cnt > TC_CAP - 128));   // make room for the next 128 columns
-        const float thr = theta - eps2;   // (theta only moves at a compaction)
-        // One chunk of 32 scores of this thread's row.  Group maxima of 8 (FMNMX3 trees), then their maximum: a chunk without
-        // a hit costs 18 instructions; a hit makes the warp scan only the groups that hold one (on a 500 k-item catalogue 6 %
-        // of a row's chunks hold a hit, so 86 % of a WARP's chunks do: the scan is the common path there, and it appends
-        // with one 8-byte store per hit; padding columns of the last tile are dropped by the compaction and the re-rank).
-        auto sweep = [&](const uint32_t (&r)[32], int c) {
-          if (dbg && valid) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) P.dbg_scores[(long long)row * P.dbg_ld + n0 + c * 32 + j] = __uint_as_float(r[j]);
-          }
-          float mg[4];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float x = fmaxf(fmaxf(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1])), __uint_as_float(r[8 * g + 2]));
-            x = fmaxf(fmaxf(x, __uint_as_float(r[8 * g + 3])), __uint_as_float(r[8 * g + 4]));
-            x = fmaxf(fmaxf(x, __uint_as_float(r[8 * g + 5])), __uint_as_float(r[8 * g + 6]));
-            mg[g] = fmaxf(x, __uint_as_float(r[8 * g + 7]));
-          }
-          const float m = fmaxf(fmaxf(fmaxf(mg[0], mg[1]), mg[2]), mg[3]);
-          if (m >= thr) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              if (mg[g] >= thr) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  if (__uint_as_float(r[8 * g + j]) >= thr) {
-                    ce[cnt] = make_uint2(r[8 * g + j], (unsigned)(n0 + c * 32 + 8 * g + j));
-                    ++cnt;
-                  }
-                }
-              }
-            }
-          }
-        };
-        // software-pipelined TMEM reads: the load of chunk c + 1 is in flight while chunk c is swept (under MMA load a
-        // tcgen05.ld takes 350+ cycles: in sequence with the sweep the epilogue of a tile outlasted the tile's MMAs, and the
-        // issuing thread spent 23 % of its time waiting for an accumulator to drain)
+        rs.compact(__ballot_sync(0xffffffffu, rs.cnt > TC_CAP - 128), lane, P);   // make room for the next 128 columns
+        const float thr = rs.theta - rs.eps2;   // (theta only moves at a compaction)
+        // software-pipelined TMEM reads: the load of chunk c + 1 is in flight while chunk c is swept
         uint32_t ra[32], rb[32];
         tc_ld32(tbase + (uint32_t)(hb * 128), ra);
 #pragma unroll
@@ -375,7 +397,11 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
           const int c = hb * 4 + cc;
           tc_wait_ld(ra);
           tc_ld32(tbase + (uint32_t)((c + 1) * 32), rb);
-          sweep(ra, c);
+          if (dbg && rs.valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) P.dbg_scores[(long long)row * P.dbg_ld + n0 + c * 32 + j] = __uint_as_float(ra[j]);
+          }
+          rs.sweep(ra, n0 + c * 32, thr);
           tc_wait_ld(rb);
           if (cc + 2 < 4) {
             tc_ld32(tbase + (uint32_t)((c + 2) * 32), ra);
@@ -383,17 +409,15 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
             tc_fence_before();
             mbar_arrive(tempty + acc);
           }
-          sweep(rb, c + 1);
+          if (dbg && rs.valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) P.dbg_scores[(long long)row * P.dbg_ld + n0 + (c + 1) * 32 + j] = __uint_as_float(rb[j]);
+          }
+          rs.sweep(rb, n0 + (c + 1) * 32, thr);
         }
       }
     }
-    // a last compaction leaves K + the 2-eps band per (row, split) instead of whatever arrived since the previous one
-    // (~280 -> ~110 at K = 100): the exact re-rank scores and sorts that many fewer candidates
-    compact_lanes(__ballot_sync(0xffffffffu, valid && !overflowed && cnt > P.K + 16));
-    if (valid) {
-      P.cand_cnt[(long long)row * P.S + split] = cnt;
-      if (overflowed) P.overflow[row] = 1;
-    }
+    rs.finish(P, row, buffer, lane);
   }
 
   tc_fence_before();
@@ -401,6 +425,167 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---- the paired kernel (CF_TC_PAIR): clusters of two CTAs on the two SMs of a TPC issue ONE tcgen05.mma.cta_group::2 of
+// M = 256 (128 query rows per CTA), N = 256 per k-step.  Each CTA TMA-loads HALF of every 256-item B tile (the 2-SM form of
+// the load counts its bytes on the leader's mbarrier) and the hardware feeds both halves to both tensor cores: the N = 256
+// MMA rate (~1.5 PFLOP/s ceiling instead of ~1.13 for N = 128, tests/micro/mma_micro.cu) at the L2 -> SM traffic of the
+// single-CTA kernel, and a two-deep ring of 256-column accumulators.  Only the leader's thread issues MMAs; its commits are
+// multicast to both CTAs' barriers; both CTAs' epilogue warps hand an accumulator back on the LEADER's barrier.  Per CTA the
+// epilogue is the same sweep, but 128 rows x 256 columns per tile: two warps per TMEM lane quadrant, one per column half,
+// each with its own candidate buffer and threshold (so a row has 2 S buffers; the re-rank merges them as it merges splits).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+k_topk_tc_pair(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmV, const __grid_constant__ TcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0u;
+  const int KC = P.KC;
+  const int a_bytes = KC * TC_CHUNK_BYTES, b_stage_bytes = KC * TC_CHUNK_BYTES;   // 128 query rows; 128 of a tile's 256 items
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)P.stages * b_stage_bytes);
+  uint64_t* full = bars;                       // [stages]  (the leader's are used)
+  uint64_t* empty = bars + TC_MAX_STAGES;      // [stages]  (every CTA's own)
+  uint64_t* a_full = bars + 2 * TC_MAX_STAGES; //           (leader)
+  uint64_t* tfull = a_full + 1;                // [2]       (every CTA's own)
+  uint64_t* tempty = tfull + 2;                // [2]       (leader: 8 epilogue warps of each CTA arrive)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int row0 = (int)(blockIdx.x >> 1) * 256 + (int)rank * TC_M;
+  const int split = blockIdx.y;
+  const int tiles_per_split = (P.n_tiles + P.S - 1) / P.S;
+  const int tile_lo = split * tiles_per_split;
+  const int tile_hi = min(P.n_tiles, tile_lo + tiles_per_split);
+  const int nt = max(0, tile_hi - tile_lo);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P.stages; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(a_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull + s, 1);
+      mbar_init(tempty + s, 16);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {   // (the same warp in both CTAs)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();      // both CTAs' barriers exist before any remote arrive, multicast commit or 2-SM load targets them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;" ::: "memory");
+    if (warp == 0) {
+      // ================================================================== TMA producer (both CTAs: each its half)
+      if (lane == 0) {
+        if (leader) mbar_arrive_expect_tx(a_full, 2u * (uint32_t)a_bytes);
+        for (int kc = 0; kc < KC; ++kc) tma_load_2d_pair(&tmQ, a_full, sA + (size_t)kc * TC_CHUNK_BYTES, kc * TC_KCH, row0);
+        int st = 0;
+        uint32_t ph = 0u;
+        for (int t = 0; t < nt; ++t) {
+          mbar_wait(empty + st, ph ^ 1u);
+          if (leader) mbar_arrive_expect_tx(full + st, 2u * (uint32_t)b_stage_bytes);
+          for (int kc = 0; kc < KC; ++kc)
+            tma_load_2d_pair(&tmV, full + st, sB + (size_t)st * b_stage_bytes + (size_t)kc * TC_CHUNK_BYTES, kc * TC_KCH,
+                             (tile_lo + t) * TC_NW + (int)rank * TC_M);
+          if (++st == P.stages) { st = 0; ph ^= 1u; }
+        }
+      }
+    } else if (warp == 1 && leader) {
+      // ================================================================== MMA issuer (one thread of the leader CTA)
+      if (lane == 0) {
+        const uint32_t idesc = umma_idesc_fp16(2 * TC_M, TC_NW);
+        const uint64_t a0 = umma_desc_sw128(smem_u32(sA));
+        const uint64_t b00 = umma_desc_sw128(smem_u32(sB));
+        const uint64_t b_stage_step = (uint64_t)(b_stage_bytes >> 4);
+        mbar_wait(a_full, 0u);
+        int st = 0;
+        uint32_t ph = 0u;
+        uint64_t b0 = b00;
+        for (int t = 0; t < nt; ++t) {
+          const int acc = t & 1;
+          mbar_wait(tempty + acc, ((uint32_t)(t >> 1) & 1u) ^ 1u);   // both CTAs have drained this accumulator
+          mbar_wait(full + st, ph);                                  // both halves of the B tile have landed
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_NW);
+#pragma unroll
+          for (int kc = 0; kc < 4; ++kc) {
+            if (kc < KC) {
+#pragma unroll
+              for (int k = 0; k < TC_KCH / 16; ++k) {
+                const uint64_t off = (uint64_t)((kc * TC_CHUNK_BYTES + k * 32) >> 4);
+                tc_mma_f16_pair(d_tmem, a0 + off, b0 + off, idesc, (kc | k) ? 1u : 0u);
+              }
+            }
+          }
+          tc_commit_pair(empty + st);      // the smem stage is free in both CTAs once these MMAs have read it
+          tc_commit_pair(tfull + acc);     // the accumulator is ready for both CTAs' epilogues
+          b0 += b_stage_step;
+          if (++st == P.stages) { st = 0; ph ^= 1u; b0 = b00; }
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;" ::: "memory");
+    // ================================================================== epilogue: one thread per (query row, column half)
+    const int q = warp & 3, h = (warp - 4) >> 2;
+    const int row = row0 + q * 32 + lane;
+    const long long buffer = ((long long)row * P.S + split) * 2 + h;
+    RowSweep rs;
+    rs.init(P, row, buffer);
+    const bool dbg = P.dbg_scores != nullptr;
+    for (int t = 0; t < nt; ++t) {
+      const int acc = t & 1;
+      mbar_wait(tfull + acc, (uint32_t)(t >> 1) & 1u);
+      tc_fence_after();
+      const int n0 = (tile_lo + t) * TC_NW + h * 128;
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_NW + h * 128);
+      rs.compact(__ballot_sync(0xffffffffu, rs.cnt > TC_CAP - 128), lane, P);   // make room for the next 128 columns
+      const float thr = rs.theta - rs.eps2;
+      uint32_t ra[32], rb[32];
+      tc_ld32(tbase, ra);
+#pragma unroll
+      for (int c = 0; c < 4; c += 2) {
+        tc_wait_ld(ra);
+        tc_ld32(tbase + (uint32_t)((c + 1) * 32), rb);
+        if (dbg && rs.valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) P.dbg_scores[(long long)row * P.dbg_ld + n0 + c * 32 + j] = __uint_as_float(ra[j]);
+        }
+        rs.sweep(ra, n0 + c * 32, thr);
+        tc_wait_ld(rb);
+        if (c + 2 < 4) {
+          tc_ld32(tbase + (uint32_t)((c + 2) * 32), ra);
+        } else {        // this warp's 128 columns are in registers: one arrival per warp on the leader's barrier
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty + acc, 0u);
+        }
+        if (dbg && rs.valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) P.dbg_scores[(long long)row * P.dbg_ld + n0 + (c + 1) * 32 + j] = __uint_as_float(rb[j]);
+        }
+        rs.sweep(rb, n0 + (c + 1) * 32, thr);
+      }
+    }
+    rs.finish(P, row, buffer, lane);
+  }
+
+  tc_fence_before();
+  cluster_sync_all();      // no CTA of the pair leaves (or frees tensor memory) while the other may still signal it
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -637,7 +822,7 @@ int make_map(CUtensorMap* tm, void* base, long long rows, int Kp, int box_rows =
 }
 
 struct TcPlan {
-  int Kp, KC, S, stages, NB;
+  int Kp, KC, S, stages, NB, pair, S_cand;   // S_cand: candidate buffers per row (S item splits, x 2 column halves in the paired kernel)
   long long T_pad, N_pad;
   size_t off_vb, off_qb, off_eps, off_cand, off_ccnt, off_ovf, off_bmax, total;
   size_t smem;
@@ -655,18 +840,29 @@ int plan_tc(const cf_topk_args* a, TcPlan* p) {
   // takes ~350 cycles (TMEM accumulate traffic crowds the reads out; 118 cycles idle): 8 chunks = 2800 > 1400.  Measured end to
   // end it ties with the narrow kernel (329 k vs 335 k users/s on 10 M items), so it is opt-in: CF_TC_WIDE=1.
   p->NB = TC_N;
+  p->pair = 0;
   if (const char* e = getenv("CF_TC_WIDE")) if (atoi(e) > 0 && p->KC <= 2) p->NB = TC_NW;
+  // The cta_group::2 kernel is built, tested bit-identical and opt-in (CF_TC_PAIR=1): measured on 1 M users x 10 M items it
+  // TIES with the single-CTA kernel to 0.04 % (2956.7 vs 2957.9 ms).  Both are power-bound: nvidia-smi during the sweep shows
+  // 990-1015 W with sw_power_cap active and the SM clock at 1.44-1.48 GHz (max 1.965), and reading only HALF of every
+  // accumulator (an experiment, wrong results) buys 4.5 %.  At that clock the N = 128 MMA form tops out at ~840 TFLOP/s:
+  // the sweep runs at the MMA rate of the throttled clock, and a faster MMA form only lowers the clock further.
+  if (const char* e = getenv("CF_TC_PAIR")) if (atoi(e) > 0) { p->pair = 1; p->NB = TC_NW; }
   p->T_pad = (long long)align_up((size_t)a->T, TC_MT * TC_M);
   p->N_pad = (long long)align_up((size_t)a->n_items, p->NB);
-  const long long row_tiles = p->T_pad / (TC_MT * TC_M), n_tiles = p->N_pad / p->NB;
-  int S = (int)((cf_num_sms() + row_tiles - 1) / row_tiles);   // just enough item splits to give every SM a CTA: each
-                                                               // split restarts its rows' thresholds from -inf
+  const long long row_tiles = p->T_pad / (TC_MT * TC_M), n_tiles = p->N_pad / p->NB;   // (row_tiles: CTAs, or CTA pairs)
+  const long long slots = p->pair ? cf_num_sms() / 2 : cf_num_sms();
+  int S = (int)((slots + row_tiles - 1) / row_tiles);   // just enough item splits to give every SM a CTA: each
+                                                        // split restarts its rows' thresholds from -inf
   if (S < 1) S = 1;
   if (const char* e = getenv("CF_TC_SPLITS")) S = atoi(e) > 0 ? atoi(e) : S;   // tuning knob
-  if (S > RR_CAP / TC_CAP) S = RR_CAP / TC_CAP;
+  const int s_max = RR_CAP / TC_CAP / (p->pair ? 2 : 1);
+  if (S > s_max) S = s_max;
   if (S > n_tiles) S = (int)n_tiles;
   p->S = S;
-  const size_t a_bytes = (size_t)TC_MT * p->KC * TC_CHUNK_BYTES, b_bytes = (size_t)p->KC * TC_CHUNK_BYTES * (p->NB / 128);
+  p->S_cand = p->pair ? 2 * S : S;
+  const size_t a_bytes = (size_t)(p->pair ? 1 : TC_MT) * p->KC * TC_CHUNK_BYTES;
+  const size_t b_bytes = (size_t)p->KC * TC_CHUNK_BYTES * (p->pair ? 1 : p->NB / 128);
   int stages = (int)((200 * 1024 - a_bytes) / b_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   CF_CHECK_ARG(stages >= 2, "cf_topk_tc: not enough shared memory for a 2-stage ring");
@@ -676,8 +872,8 @@ int plan_tc(const cf_topk_args* a, TcPlan* p) {
   p->off_vb = off; off = align_up(off + (size_t)p->N_pad * p->Kp * 2, 1024);
   p->off_qb = off; off = align_up(off + (size_t)p->T_pad * p->Kp * 2, 1024);
   p->off_eps = off; off = align_up(off + (size_t)p->T_pad * 4, 256);
-  p->off_cand = off; off = align_up(off + (size_t)p->T_pad * S * TC_CAP * 8, 256);
-  p->off_ccnt = off; off = align_up(off + (size_t)p->T_pad * S * 4, 256);
+  p->off_cand = off; off = align_up(off + (size_t)p->T_pad * p->S_cand * TC_CAP * 8, 256);
+  p->off_ccnt = off; off = align_up(off + (size_t)p->T_pad * p->S_cand * 4, 256);
   p->off_ovf = off; off = align_up(off + (size_t)p->T_pad * 4, 256);
   p->off_bmax = off; off = align_up(off + 256, 256);
   p->total = off;
@@ -725,7 +921,7 @@ extern "C" int cf_topk_tc(const cf_topk_args* a, void* workspace, int64_t worksp
   float* bmax = reinterpret_cast<float*>(ws + p.off_bmax);
   CF_CUDA_OK(cudaMemsetAsync(bmax, 0, 256, stream));
   CF_CUDA_OK(cudaMemsetAsync(ovf, 0, (size_t)p.T_pad * 4, stream));
-  CF_CUDA_OK(cudaMemsetAsync(ccnt, 0, (size_t)p.T_pad * p.S * 4, stream));
+  CF_CUDA_OK(cudaMemsetAsync(ccnt, 0, (size_t)p.T_pad * p.S_cand * 4, stream));
   const int sms = cf_num_sms();
 
   PrepParams pi = {};
@@ -743,23 +939,28 @@ extern "C" int cf_topk_tc(const cf_topk_args* a, void* workspace, int64_t worksp
 
   CUtensorMap tmQ, tmV;
   if (int rc = make_map(&tmQ, Qb, p.T_pad, p.Kp)) return rc;
-  if (int rc = make_map(&tmV, Vb, p.N_pad, p.Kp, p.NB)) return rc;
+  if (int rc = make_map(&tmV, Vb, p.N_pad, p.Kp, p.pair ? TC_M : p.NB)) return rc;   // (the paired kernel: each CTA loads half a tile)
   TcParams P = {};
   P.T = a->T; P.N = (int)a->n_items; P.KC = p.KC; P.n_tiles = (int)(p.N_pad / p.NB); P.S = p.S; P.stages = p.stages; P.K = a->K;
   P.users = a->users; P.tr_indptr = (const long long*)a->train.indptr; P.tr_indices = a->train.indices;
   P.eps2 = eps2; P.cand = cand; P.cand_cnt = ccnt; P.overflow = ovf;
   P.dbg_scores = dbg_scores; P.dbg_ld = (long long)align_up((size_t)a->n_items, TC_NW);   // the same stride for both kernels
   dim3 grid((unsigned)(p.T_pad / (TC_MT * TC_M)), (unsigned)p.S);
-  if (p.NB == TC_NW) {
+  if (p.pair) {
+    grid.x *= 2;     // clusters of two CTAs, 128 query rows each
+    CF_CUDA_OK(cudaFuncSetAttribute(k_topk_tc_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    k_topk_tc_pair<<<grid, TC_THREADS, p.smem, stream>>>(tmQ, tmV, P);
+  } else if (p.NB == TC_NW) {
     CF_CUDA_OK(cudaFuncSetAttribute(k_topk_tc<TC_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     k_topk_tc<TC_NW><<<grid, TC_THREADS, p.smem, stream>>>(tmQ, tmV, P);
   } else {
     CF_CUDA_OK(cudaFuncSetAttribute(k_topk_tc<TC_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     k_topk_tc<TC_N><<<grid, TC_THREADS, p.smem, stream>>>(tmQ, tmV, P);
   }
+  CF_CUDA_OK(cudaGetLastError());
 
   RerankParams R = {};
-  R.U = a->U; R.V = a->V; R.b = a->b; R.ld = a->ld; R.nvec = a->ld / 4; R.kind = a->kind; R.T = a->T; R.S = p.S; R.K = a->K;
+  R.U = a->U; R.V = a->V; R.b = a->b; R.ld = a->ld; R.nvec = a->ld / 4; R.kind = a->kind; R.T = a->T; R.S = p.S_cand; R.K = a->K;
   R.users = a->users; R.cand = cand; R.n_items = (int)a->n_items; R.cand_cnt = ccnt; R.overflow = ovf;
   R.tr_indptr = (const long long*)a->train.indptr; R.tr_indices = a->train.indices;
   R.out_idx = a->out_idx; R.out_val = a->out_val; R.stats = stats;

@@ -103,3 +103,27 @@ def test_wide_kernel_equals_the_exact_kernel(monkeypatch):
         ti, tv = m.engine.topk(users, K, csr, return_values=True, method='tensor')
         ei, ev = m.engine.topk(users, K, csr, return_values=True, method='exact')
         assert torch.equal(ti, ei) and torch.equal(tv, ev)
+
+
+def test_paired_kernel_equals_the_exact_kernel(monkeypatch):
+    """CF_TC_PAIR=1: the cta_group::2 kernel (clusters of two CTAs, one M = 256, N = 256 tcgen05.mma per k-step, two candidate
+    buffers per row and split) returns the same lists and fp64 scores as the exact kernel."""
+    import numpy as np
+    import torch
+    from scipy.sparse import lil_matrix
+    from collaborativefilteringusingtensorflow_b200 import BPRMF, CML, GBPRMF
+    from collaborativefilteringusingtensorflow_b200.sparse import DeviceCSR
+    monkeypatch.setenv('CF_TC_PAIR', '1')
+    rng = np.random.default_rng(5)
+    for cls, nu, ni, d, K in ((BPRMF, 300, 5000, 128, 100), (CML, 257, 3001, 64, 37), (BPRMF, 64, 777, 20, 200),
+                              (GBPRMF, 130, 40000, 200, 50), (CML, 1000, 20011, 128, 100)):
+        m = cls(nu, ni, n_factors=d, verbose=False, seed=2)
+        tra = lil_matrix((nu, ni), dtype=np.float32)
+        for u in range(nu):
+            tra[u, rng.choice(ni, 25, replace=False)] = 1
+        csr = DeviceCSR.from_scipy(tra, m.device)
+        users = torch.arange(nu, dtype=torch.int32, device=m.device)
+        ti, tv = m.engine.topk(users, K, csr, return_values=True, method='tensor')
+        ei, ev = m.engine.topk(users, K, csr, return_values=True, method='exact')
+        assert torch.equal(ti, ei) and torch.equal(tv, ev), (cls.__name__, nu, ni, d, K)
+        assert int(m.engine.tc_stats[0].item()) == 0       # no row fell back to the exact kernel
