@@ -493,7 +493,7 @@ struct WhiteParams {
   long long n_x;
   int d, ldx;
   float weight;
-  int* cursor;              // k_als_rows_tc: next chunk of 256 rows (zeroed before the launch)
+  int* cursor;              // k_als_rows_tc: next chunk of rows (zeroed before the launch)
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -627,6 +627,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_als_small(const __grid_constant_
 // ---- rows with more than 32 observed columns: one CTA per row, tcgen05 Gram + register-blocked Cholesky
 constexpr int RT_TILE = 16384;                 // one operand tile: 128 rows x 64 bf16, SWIZZLE_128B K-major (what a TMA box {64, 128} writes)
 constexpr int RT_A_BYTES = ALS_D * (ALS_D + 1) * 4;   // the fp32 system, aliased onto the four operand tiles once the MMAs are done
+constexpr int RT_WARPS = 5, RT_THREADS = RT_WARPS * 32;
+constexpr int RT_TRI = NBK * (NBK + 1) / 2;            // 136 blocks of the lower triangle
 
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
@@ -636,29 +638,38 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& h, __nv_bfloa
   l = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
-__global__ void __launch_bounds__(256, 2) k_als_rows_tc(const __grid_constant__ WhiteParams P) {
+__global__ void __launch_bounds__(RT_THREADS, 3) k_als_rows_tc(const __grid_constant__ WhiteParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* tiles = smem;                                             // 4 x 16 KB operand tiles ...
   float* A = reinterpret_cast<float*>(smem);                         // ... later the fp32 system [128][129]
-  float* panel = reinterpret_cast<float*>(smem + ((RT_A_BYTES + 127) & ~127));   // [16][64] block column L_ik
+  // once the register blocks are loaded the system's shared-memory copy is dead: the factorisation's scratch lives there
+  float* panel = reinterpret_cast<float*>(smem);   // [16][64] block column L_ik
   float* zrow = panel + NBK * 64;              // [8]   the right-hand side's block of the current block column
   float* diagA = zrow + 8;                     // [64]  the diagonal block about to be factored
   float* dinvs = diagA + 64;                   // [16][64] inverses of the factored diagonal blocks (row-major, lower)
   float* zvec = dinvs + NBK * 64;              // [128] z, then the solution
-  float* svec = zvec + ALS_D;                  // [8][128] per-warp partial sums of the gathered rows / [2][128] row sums
-  int* rlist = reinterpret_cast<int*>(svec + 8 * ALS_D);             // [256] rows of this chunk that belong here
-  int* ridx = rlist + 256;                                           // [128] the observed columns of a short row
+  float* svec = reinterpret_cast<float*>(smem + ((RT_A_BYTES + 127) & ~127));   // [5][128] per-warp partial sums / [128] row sums
+  int* rlist = reinterpret_cast<int*>(svec + RT_WARPS * ALS_D);      // [160] rows of this chunk that belong here
+  int* ridx = rlist + RT_THREADS;                                    // [128] the observed columns of a short row
   uint64_t* bars = reinterpret_cast<uint64_t*>(ridx + ALS_D);        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-  int* wcnt = reinterpret_cast<int*>(tmem_slot + 1);                 // [8] members per warp, [8] = total, [9] = chunk id
+  int* wcnt = reinterpret_cast<int*>(tmem_slot + 1);                 // [5] members per warp, [5] = total, [6] = chunk id
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tx = tid & 15, ty = tid >> 4;
-  const bool lower = ty >= tx;
-  // the right-hand side rides along as an extra block row: its block of block column j lives in an otherwise idle thread
-  const bool is_aug = (ty == 0 && tx >= 1) || (ty == 1 && tx == 2);
-  const int aug_col = ty == 0 ? tx : 0;
+  // 136 threads own the 8 x 8 blocks of the lower triangle (thread t <-> block (ty, tx), tx <= ty, row by row), 16 more carry
+  // the right-hand side as an extra block row (one block column each), 8 idle: 5 warps instead of the 8 a square 16 x 16
+  // thread grid needs -- three CTAs per SM fit (registers), and the factorisation is bound by its barrier chain, not by issue
+  const bool lower = tid < RT_TRI;
+  int ty = -1, tx = -2;                        // (no role matches these)
+  if (lower) {
+    ty = (int)((sqrtf(8.f * (float)tid + 1.f) - 1.f) * 0.5f);
+    while (ty * (ty + 1) / 2 > tid) --ty;
+    while ((ty + 1) * (ty + 2) / 2 <= tid) ++ty;
+    tx = tid - ty * (ty + 1) / 2;
+  }
+  const bool is_aug = tid >= RT_TRI && tid < RT_TRI + NBK;
+  const int aug_col = tid - RT_TRI;
   const float c = P.weight - 1.f, invc = 1.f / c;
 
   if (tid == 0) {
@@ -677,14 +688,14 @@ __global__ void __launch_bounds__(256, 2) k_als_rows_tc(const __grid_constant__ 
   const uint32_t idesc = umma_idesc_bf16(ROWS, ALS_D);
   uint32_t nwait0 = 0u, nwait1 = 0u;     // completed phases of the two mbarriers (every thread keeps the same count)
 
-  const long long n_chunks = (P.n_x + 255) / 256;
+  const long long n_chunks = (P.n_x + RT_THREADS - 1) / RT_THREADS;
   for (;;) {
-    // ---- take the next chunk of 256 rows (long rows cost 10x a short one: static striding leaves SMs idle at the end)
+    // ---- take the next chunk of 160 rows (long rows cost 10x a short one: static striding leaves SMs idle at the end)
     __syncthreads();                       // (the previous chunk's list and counters are no longer read)
-    if (tid == 0) wcnt[9] = atomicAdd(P.cursor, 1);
+    if (tid == 0) wcnt[RT_WARPS + 1] = atomicAdd(P.cursor, 1);
     __syncthreads();
-    const long long chunk0 = (long long)wcnt[9] * 256;
-    if (wcnt[9] >= n_chunks) break;
+    const long long chunk0 = (long long)wcnt[RT_WARPS + 1] * RT_THREADS;
+    if (wcnt[RT_WARPS + 1] >= n_chunks) break;
     {
       const long long u = chunk0 + tid;
       const bool mine = u < P.n_x && (P.indptr[u + 1] - P.indptr[u]) > 32;
@@ -696,12 +707,12 @@ __global__ void __launch_bounds__(256, 2) k_als_rows_tc(const __grid_constant__ 
       if (mine) rlist[base + __popc(m & ((1u << lane) - 1u))] = tid;
       if (tid == 0) {
         int tot = 0;
-        for (int w = 0; w < 8; ++w) tot += wcnt[w];
-        wcnt[8] = tot;
+        for (int w = 0; w < RT_WARPS; ++w) tot += wcnt[w];
+        wcnt[RT_WARPS] = tot;
       }
       __syncthreads();
     }
-    const int nmine = wcnt[8];
+    const int nmine = wcnt[RT_WARPS];
     for (int ri = 0; ri < nmine; ++ri) {
       const long long u = chunk0 + rlist[ri];
       const long long lo = P.indptr[u];
@@ -711,24 +722,30 @@ __global__ void __launch_bounds__(256, 2) k_als_rows_tc(const __grid_constant__ 
       // =========================================================== Gram on the tensor cores
       if (!wide) {
         // tiles: hi[kc 0], hi[kc 1], lo[kc 0], lo[kc 1]; row a of the tile = gathered row a, zero beyond n
-        // (all loads of a warp's 16 rows are issued before the first conversion: one round trip, not sixteen)
-        const int my_a = warp + 8 * (lane & 15);
-        const int my_idx = my_a < n ? P.indices[lo + my_a] : -1;
-        if (lane < 16 && my_a < n) ridx[my_a] = my_idx;
-        float4 v[16];
+        // (warp w takes the tile rows w, w + 5, ...: 26 at most, in two batches of 13 whose loads are all issued before the
+        // first conversion -- two round trips, not twenty-six)
+        const int my_a = warp + RT_WARPS * lane;
+        const int my_idx = (lane < 26 && my_a < n) ? P.indices[lo + my_a] : -1;
+        if (lane < 26 && my_a < n) ridx[my_a] = my_idx;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          float4 v[13];
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          const int ia = __shfl_sync(0xffffffffu, my_idx, r);
-          v[r] = ia >= 0 ? __ldg(reinterpret_cast<const float4*>(P.W + (long long)ia * ALS_D) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+          for (int r = 0; r < 13; ++r) {
+            const int ia = __shfl_sync(0xffffffffu, my_idx, 13 * half + r);
+            v[r] = ia >= 0 ? __ldg(reinterpret_cast<const float4*>(P.W + (long long)ia * ALS_D) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          const int a = warp + 8 * r;
-          __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-          split_bf16(v[r].x, h0, l0); split_bf16(v[r].y, h1, l1); split_bf16(v[r].z, h2, l2); split_bf16(v[r].w, h3, l3);
-          const int off = (lane >> 4) * RT_TILE + a * 128 + ((((lane & 15) >> 1) ^ (a & 7)) << 4) + (lane & 1) * 8;
-          *reinterpret_cast<uint2*>(tiles + off) = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
-          *reinterpret_cast<uint2*>(tiles + 2 * RT_TILE + off) = make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
+          for (int r = 0; r < 13; ++r) {
+            const int a = warp + RT_WARPS * (13 * half + r);
+            if (a < ALS_D) {
+              __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+              split_bf16(v[r].x, h0, l0); split_bf16(v[r].y, h1, l1); split_bf16(v[r].z, h2, l2); split_bf16(v[r].w, h3, l3);
+              const int off = (lane >> 4) * RT_TILE + a * 128 + ((((lane & 15) >> 1) ^ (a & 7)) << 4) + (lane & 1) * 8;
+              *reinterpret_cast<uint2*>(tiles + off) = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
+              *reinterpret_cast<uint2*>(tiles + 2 * RT_TILE + off) = make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
+            }
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
@@ -758,11 +775,13 @@ __global__ void __launch_bounds__(256, 2) k_als_rows_tc(const __grid_constant__ 
             if (buf == 0) { mbar_wait(bars, nwait0 & 1u); ++nwait0; }
             else { mbar_wait(bars + 1, nwait1 & 1u); ++nwait1; }
           }
-          const long long a0 = (long long)ch * 64 + warp * 8;
+          uint8_t* th = tiles + buf * 2 * RT_TILE;
+#pragma unroll 1
+          for (int sc = warp; sc < 8; sc += RT_WARPS) {   // eight 16-byte column chunks of the tile over five warps
+          const long long a0 = (long long)ch * 64 + sc * 8;
           long long src[8];
 #pragma unroll
           for (int q = 0; q < 8; ++q) src[q] = (a0 + q < nl) ? (long long)P.indices[lo + a0 + q] * ALS_D : -1;
-          uint8_t* th = tiles + buf * 2 * RT_TILE;
 #pragma unroll
           for (int ig = 0; ig < 4; ++ig) {
             const int i = lane + 32 * ig;
@@ -779,9 +798,10 @@ __global__ void __launch_bounds__(256, 2) k_als_rows_tc(const __grid_constant__ 
               lp[q] = pack_bf16(la, lb2);
               sacc[ig] += v[2 * q] + v[2 * q + 1];
             }
-            const int off = i * 128 + ((warp ^ (i & 7)) << 4);
+            const int off = i * 128 + ((sc ^ (i & 7)) << 4);
             *reinterpret_cast<uint4*>(th + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
             *reinterpret_cast<uint4*>(th + RT_TILE + off) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+          }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncthreads();
@@ -810,24 +830,23 @@ __global__ void __launch_bounds__(256, 2) k_als_rows_tc(const __grid_constant__ 
       }
       tc_fence_after();
       // =========================================================== accumulator -> the fp32 system in shared memory
-      {
-        const int q = warp & 3, hf = warp >> 2;
-        const int row = q * 32 + lane;
+      if (warp < 4) {                        // warp q reads TMEM lane quadrant q: one matrix row per thread
+        const int row = warp * 32 + lane;
         float rs = 0.f;
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
           uint32_t r[32];
-          tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * 64 + cc * 32), r);
+          tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cc * 32), r);
           tc_wait_ld();
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int col = hf * 64 + cc * 32 + j;
+            const int col = cc * 32 + j;
             const float g = __uint_as_float(r[j]);
             rs += g;
             A[row * (ALS_D + 1) + col] = wide ? fmaf(c, g, row == col ? 1.f : 0.f) : g + (row == col ? invc : 0.f);
           }
         }
-        if (!wide) svec[hf * ALS_D + row] = rs;
+        if (!wide) svec[row] = rs;
       }
       tc_fence_before();
       __syncthreads();
@@ -847,13 +866,14 @@ __global__ void __launch_bounds__(256, 2) k_als_rows_tc(const __grid_constant__ 
           float s = 0.f;
           if (wide) {
 #pragma unroll
-            for (int w = 0; w < 8; ++w) s += svec[w * ALS_D + e];
+            for (int w = 0; w < RT_WARPS; ++w) s += svec[w * ALS_D + e];
           } else {
-            s = e < n ? svec[e] + svec[ALS_D + e] : 0.f;
+            s = e < n ? svec[e] : 0.f;
           }
           g[j] = P.weight * s;
         }
       }
+      __syncthreads();                       // every block is in registers: the system's shared-memory copy becomes scratch
       if (ty == 0 && tx == 0) {
 #pragma unroll
         for (int i = 0; i < BS; ++i)
@@ -1014,27 +1034,30 @@ __global__ void __launch_bounds__(256, 2) k_als_rows_tc(const __grid_constant__ 
       if (wide) {
         if (tid < P.d) P.X[u * P.ldx + tid] = zvec[tid];
       } else {
-        // xt = W_u^T (weight - t): warp w takes the gathered rows w, w + 8, ... (all its loads in flight at once), a lane four
-        // columns; the eight partial sums meet in shared memory
+        // xt = W_u^T (weight - t): warp w takes the gathered rows w, w + 5, ... (13 loads in flight at a time), a lane four
+        // columns; the five partial sums meet in shared memory
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 v[16];
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          float4 v[13];
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          const int e = warp + 8 * r;
-          v[r] = e < n ? __ldg(reinterpret_cast<const float4*>(P.W + (long long)ridx[e] * ALS_D) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+          for (int r = 0; r < 13; ++r) {
+            const int e = warp + RT_WARPS * (13 * half + r);
+            v[r] = e < n ? __ldg(reinterpret_cast<const float4*>(P.W + (long long)ridx[e] * ALS_D) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-          const int e = warp + 8 * r;
-          const float cf = e < n ? P.weight - zvec[e] : 0.f;
-          acc.x = fmaf(cf, v[r].x, acc.x); acc.y = fmaf(cf, v[r].y, acc.y); acc.z = fmaf(cf, v[r].z, acc.z); acc.w = fmaf(cf, v[r].w, acc.w);
+          for (int r = 0; r < 13; ++r) {
+            const int e = warp + RT_WARPS * (13 * half + r);
+            const float cf = e < n ? P.weight - zvec[e] : 0.f;
+            acc.x = fmaf(cf, v[r].x, acc.x); acc.y = fmaf(cf, v[r].y, acc.y); acc.z = fmaf(cf, v[r].z, acc.z); acc.w = fmaf(cf, v[r].w, acc.w);
+          }
         }
         *reinterpret_cast<float4*>(svec + warp * ALS_D + 4 * lane) = acc;
         __syncthreads();
         if (tid < P.d) {
           float x = 0.f;
 #pragma unroll
-          for (int w = 0; w < 8; ++w) x += svec[w * ALS_D + tid];
+          for (int w = 0; w < RT_WARPS; ++w) x += svec[w * ALS_D + tid];
           P.X[u * P.ldx + tid] = x;
         }
       }
@@ -1109,7 +1132,7 @@ static int als_gram(const float* Y, long long n_y, int d, int ldy, float* G, uin
 constexpr int SMALL16_WARPS = 8, SMALL32_WARPS = 5;
 static size_t small_smem(int nmax, int warps) { return (size_t)warps * (nmax * SM_LD + nmax * (nmax + 1)) * 4; }
 static size_t rows_tc_smem() {
-  return (size_t)((RT_A_BYTES + 127) & ~127) + (NBK * 64 + 8 + 64 + NBK * 64 + ALS_D + 8 * ALS_D) * 4 + (256 + ALS_D) * 4 + 16 + 4 + 10 * 4 + 64 + 1024;
+  return (size_t)((RT_A_BYTES + 127) & ~127) + (size_t)RT_WARPS * ALS_D * 4 + (RT_THREADS + ALS_D) * 4 + 16 + 4 + (RT_WARPS + 2) * 4 + 64 + 1024;
 }
 
 // Solve stage: every row of X from the (complete) Gram G and its observed rows of Y.  With a workspace and weight > 1 the
@@ -1141,9 +1164,9 @@ static int als_solve(const cf_als_args* a, const float* G, cudaStream_t stream, 
     long long g16 = (a->n_x + SMALL16_WARPS - 1) / SMALL16_WARPS, g32 = (a->n_x + SMALL32_WARPS - 1) / SMALL32_WARPS;
     if (g16 > (long long)sms * 2) g16 = (long long)sms * 2;
     if (g32 > (long long)sms * 2) g32 = (long long)sms * 2;
-    long long grt = (a->n_x + 255) / 256;
-    if (grt > (long long)sms * 2) grt = (long long)sms * 2;
-    k_als_rows_tc<<<(unsigned)grt, 256, srt, stream>>>(P);      // the long rows first: they are the tail
+    long long grt = (a->n_x + RT_THREADS - 1) / RT_THREADS;
+    if (grt > (long long)sms * 3) grt = (long long)sms * 3;
+    k_als_rows_tc<<<(unsigned)grt, RT_THREADS, srt, stream>>>(P);      // the long rows first: they are the tail
     k_als_small<32, SMALL32_WARPS><<<(unsigned)g32, SMALL32_WARPS * 32, s32, stream>>>(P);
     k_als_small<16, SMALL16_WARPS><<<(unsigned)g16, SMALL16_WARPS * 32, s16, stream>>>(P);
     long long xg = (a->n_x + 31) / 32;
