@@ -426,7 +426,7 @@ def time_topk(engine, users, mask, K=100, warm=4096):
     torch.cuda.synchronize()
     clk = ClockSampler(engine.device.index or 0)
     clk.start()
-    time.sleep(0.25)
+    time.sleep(0.7)                                          # (nvidia-smi needs a few hundred ms before its first sample)
     t0 = time.time()
     e0.record()
     engine.topk(users, K, mask, method='tensor')
