@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libcf_b200.so')
-ABI_VERSION = 19
+ABI_VERSION = 20
 
 # enums of cf_b200.h
 MODEL_BPR, MODEL_CML, MODEL_GBPR, MODEL_WRMF = 0, 1, 2, 3
@@ -117,6 +117,7 @@ class SampleArgs(C.Structure):
         ('n_batches', C.c_int32), ('B', C.c_int32), ('W', C.c_int32), ('G', C.c_int32),
         ('n_neg_rows', C.c_int32), ('shuffle', C.c_int32),
         ('out_pairs', _p), ('out_negs', _p), ('out_group', _p), ('out_ratings', _p), ('flags', _p),
+        ('pair_set', _p), ('pair_set_bits', C.c_int32), ('reserved', C.c_int32),
     ]
 
 
@@ -159,6 +160,8 @@ _SIGNATURES = {
     'cf_ipc_close': (C.c_int, [_p]),
     'cf_sample_ranking': (C.c_int, [C.POINTER(SampleArgs), _p]),
     'cf_sample_rating': (C.c_int, [C.POINTER(SampleArgs), _p]),
+    'cf_pair_set_bits': (C.c_int32, [C.c_int64]),
+    'cf_pair_set_build': (C.c_int, [C.POINTER(Csr), _p, C.c_int32, _p]),
     'cf_topk_exact': (C.c_int, [C.POINTER(TopkArgs), _p]),
     'cf_topk_tc_workspace_bytes': (C.c_int64, [C.POINTER(TopkArgs)]),
     'cf_topk_tc': (C.c_int, [C.POINTER(TopkArgs), _p, C.c_int64, _p, _p, _p]),

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CF_ABI_VERSION 19
+#define CF_ABI_VERSION 20
 
 /* models */
 enum { CF_MODEL_BPR = 0, CF_MODEL_CML = 1, CF_MODEL_GBPR = 2, CF_MODEL_WRMF = 3 };
@@ -290,7 +290,15 @@ typedef struct cf_sample_args {
   int32_t* out_group;      /* [n_batches*B, G] or NULL */
   float* out_ratings;      /* rating sampler: [n_batches*(B+n_neg_rows)] or NULL */
   int32_t* flags;          /* device int32, CF_FLAG_* OR-ed in */
+  const uint64_t* pair_set;     /* optional: open-addressing set of the training pairs built by cf_pair_set_build; the    */
+  int32_t pair_set_bits;        /* negatives' membership test is then ONE probe (a 32-byte sector) instead of a bisection */
+  int32_t reserved;             /* of the user's CSR row (its last 3-4 probes are cold: the sampler is bound by them)    */
 } cf_sample_args;
+
+/* The set of all (user, item) training pairs as a linear-probing hash table of 2^bits 64-bit slots (key = user * n_cols +
+ * item + 1, 0 = empty; bits = cf_pair_set_bits(nnz) keeps the load at or below one half).  Same answers as the bisection. */
+int32_t cf_pair_set_bits(int64_t nnz);
+int cf_pair_set_build(const cf_csr* train, uint64_t* table, int32_t bits, void* stream);
 
 int cf_sample_ranking(const cf_sample_args* args, void* stream);   /* ranking / uij / gbpr */
 int cf_sample_rating(const cf_sample_args* args, void* stream);    /* sampler_rating */

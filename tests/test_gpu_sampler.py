@@ -116,3 +116,27 @@ def test_degenerate_user_is_flagged_not_spun_on():
     with pytest.raises(RuntimeError, match='every item'):
         for _ in range(5):
             s.next_batch()
+
+
+def test_pair_set_membership_gives_the_same_batches_as_the_bisection(monkeypatch):
+    """The negatives' rejection test through the hash set of the training pairs (cf_pair_set_build; default for large
+    training sets) must reproduce the bisection of the user's CSR row bit for bit: same draws, same answers."""
+    import numpy as np
+    import torch
+    from scipy.sparse import lil_matrix
+    from collaborativefilteringusingtensorflow_b200.samplers import _base, sampler_gbpr, sampler_ranking
+    rng = np.random.default_rng(11)
+    nu, ni = 400, 90                      # dense rows: many rejections
+    tra = lil_matrix((nu, ni), dtype=np.float32)
+    for u in range(nu):
+        tra[u, rng.choice(ni, size=int(rng.integers(1, 70)), replace=False)] = 1
+    outs = {}
+    for mode in ('hash', 'bisect'):
+        monkeypatch.setattr(_base.DeviceSamplerBase, 'PAIR_SET_MIN_NNZ', 0 if mode == 'hash' else 1 << 40)
+        s = sampler_ranking.Sampler(tra, 4, 128, seed=5)
+        g = sampler_gbpr.Sampler(tra, 3, 2, 64, seed=6)
+        outs[mode] = [t.cpu() for t in s.next_chunk(7)] + [t.cpu() for t in g.next_chunk(5)]
+        assert bool(s._pair_set) == (mode == 'hash')
+        s.check_flags()
+    for a, b in zip(outs['hash'], outs['bisect']):
+        assert torch.equal(a, b)
