@@ -8,7 +8,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libcf_b200.so')
-ABI_VERSION = 20
+ABI_VERSION = 21
 
 # enums of cf_b200.h
 MODEL_BPR, MODEL_CML, MODEL_GBPR, MODEL_WRMF = 0, 1, 2, 3
@@ -35,7 +35,7 @@ class StepArgs(C.Structure):
         ('metaU', _p), ('metaV', _p), ('slotU', _p), ('slotV', _p), ('slot_row', _p), ('staging', _p),
         ('staging_rows', C.c_int64), ('counters', _p), ('loss', _p), ('gradV', _p), ('rank_items', C.c_int64),
         ('peerV', _p * MAX_PEERS), ('gslot_pos', _p), ('gslot_neg', _p), ('n_peers', C.c_int32), ('reserved0', C.c_int32),
-        ('gradU', _p), ('gradb', _p), ('peerG', _p * MAX_PEERS),
+        ('gradU', _p), ('gradb', _p), ('peerG', _p * MAX_PEERS), ('event_after_step', _p),
     ]
 
 

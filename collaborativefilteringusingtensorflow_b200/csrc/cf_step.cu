@@ -269,6 +269,7 @@ static int train_steps_impl(const cf_step_args* a, cudaStream_t stream, cudaEven
     if (a->update == CF_UPDATE_SYNC && !all_ext) k_count<<<(unsigned)cgrid, 256, 0, stream>>>(P);
     if (ev) CF_CUDA_OK(cudaEventRecord(ev[4 * nb + 1], stream));
     kern<<<(unsigned)grid, 256, smem, stream>>>(P);
+    if (a->event_after_step && nb == a->n_batches - 1) CF_CUDA_OK(cudaEventRecord((cudaEvent_t)a->event_after_step, stream));
     if (ev) CF_CUDA_OK(cudaEventRecord(ev[4 * nb + 2], stream));
     if (a->update == CF_UPDATE_SYNC && !all_ext) kapply<<<(unsigned)agrid, 256, 0, stream>>>(P);
     if (ev) CF_CUDA_OK(cudaEventRecord(ev[4 * nb + 3], stream));

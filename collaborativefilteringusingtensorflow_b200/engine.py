@@ -148,7 +148,7 @@ class FactorEngine(object):
         return x
 
     def train_batches(self, pairs, negs=None, group=None, ratings=None, batch_size=None, want_loss=True, profile=None,
-                      grad_tables=None):
+                      grad_tables=None, after_step_event=None):
         """Run ``n = rows / batch_size`` consecutive minibatches (the inner loop of bprmf.py:143-148).
         Index arrays may be numpy or torch (any int dtype); returns the per-minibatch loss as a CUDA float64
         tensor (or None).  ``grad_tables=(gU, gV, gb)`` (dense, zeroed; gb only for GBPR) switches to the replicated
@@ -198,6 +198,11 @@ class FactorEngine(object):
         a.counters = _lib.ptr(self.counters)
         loss = torch.zeros(nb, dtype=torch.float64, device=self.device) if want_loss else None
         a.loss = _lib.ptr(loss)
+        if after_step_event is None:          # (or left by the epoch loop for the next call: models/_base.py::_epoch)
+            after_step_event, self.pending_after_step_event = getattr(self, 'pending_after_step_event', None), None
+        if after_step_event is not None:      # torch.cuda.Event recorded after the last minibatch's fused step kernel
+            after_step_event.record(torch.cuda.current_stream(self.device))   # (creates the lazily-made handle; re-recorded by the library)
+            a.event_after_step = after_step_event.cuda_event
         stream = torch.cuda.current_stream(self.device).cuda_stream
         if grad_tables is not None:
             if nb != 1 or self.update != 'sync':

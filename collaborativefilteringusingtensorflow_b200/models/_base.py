@@ -82,14 +82,20 @@ class RankingModelBase(object):
             rows = getattr(sampler, 'rows_per_batch', self.batch_size)
             chunk = max(1, min(n_batches, (1 << 22) // max(1, rows * 8)))
             sizes = [min(chunk, n_batches - lo) for lo in range(0, n_batches, chunk)]
-            # The sampler launch of chunk j + 1 can run on a side stream while chunk j trains: a batch is a pure function of
-            # (seed, epoch, batch index) and reads nothing the steps write -- the reference's producer threads overlap the
-            # same way (sampler_ranking.py:40-50).  Measured on configs[1]'s shape (B = 2^20): BPR W=1 1.68 -> 1.62 ms per
-            # minibatch, GBPR 3.37 -> 3.17 ms, but CML 2.68 -> 2.77 ms: its step kernel needs all four resident blocks
-            # per SM and the sampler's blocks take their slots.  Default: on, except for CML; CF_SAMPLE_OVERLAP=0/1 forces it.
+            # The sampler launches run on a side stream, ahead of the training stream: a batch is a pure function of (seed,
+            # epoch, batch index) and reads nothing the steps write -- the reference's producer threads overlap the same way
+            # (sampler_ranking.py:40-50).  Two schedules:
+            #   'eager'  chunk j + 1 is sampled while chunk j trains (under its fused step kernel);
+            #   'late'   chunk j + 2 is sampled once the fused step kernel of chunk j has finished (cf_step_args.
+            #            event_after_step), i.e. under the staged apply of j and the counting kernel of j + 1.
+            # Measured on configs[1]'s shape (B = 2^20): eager: BPR W=1 1.68 -> 1.62 ms per minibatch, GBPR 3.37 -> 3.17 ms, but
+            # CML 2.68 -> 2.77 ms (its step kernel needs all four resident blocks per SM and the sampler's blocks take their
+            # slots).  Default: eager, late for CML; CF_SAMPLE_OVERLAP=0 (one stream) / 1 (eager) / 2 (late) forces one.
             want = os.environ.get('CF_SAMPLE_OVERLAP', '')
-            overlap = (want == '1' or (want != '0' and self._kind != 'cml')) and len(sizes) > 1 and self.engine.device.type == 'cuda'
-            if not overlap:
+            mode = {'0': None, '1': 'eager', '2': 'late'}.get(want, 'late' if self._kind == 'cml' else 'eager')
+            if len(sizes) < 2 or self.engine.device.type != 'cuda':
+                mode = None
+            if mode is None:
                 for n in sizes:
                     losses.append(self._train_arrays(sampler.next_chunk(n), rows))
                 return torch.cat(losses)
@@ -99,22 +105,48 @@ class RankingModelBase(object):
             side = self._sample_stream
             side.wait_stream(main)                       # (nothing sampled here may start before what precedes the epoch)
 
-            def sample(n):
+            # index buffers: a ring of `ahead + 1` persistent slots inside the sampler (no allocation per minibatch).  A slot is
+            # rewritten only after the chunk that used it has trained: eager -- the side stream waits for that chunk's
+            # `trained` event; late -- it waits for the step kernel of a LATER chunk anyway.
+            ahead = 2 if mode == 'late' else 1
+            ring = ahead + 1 if hasattr(sampler, 'ring_slot') else 0
+            trained = [None] * max(ring, 1)
+
+            def sample(j):
                 with torch.cuda.stream(side):
-                    arrays = sampler.next_chunk(n)
+                    if ring:
+                        sampler.ring_slot = j % ring
+                        if trained[j % ring] is not None:
+                            side.wait_event(trained[j % ring])
+                    try:
+                        arrays = sampler.next_chunk(sizes[j])
+                    finally:
+                        if ring:
+                            sampler.ring_slot = None
                     ev = torch.cuda.Event()
                     ev.record(side)
                 return arrays, ev
-            nxt = sample(sizes[0])
-            for j, n in enumerate(sizes):
-                arrays, ev = nxt
-                if j + 1 < len(sizes):
-                    nxt = sample(sizes[j + 1])
+            queue = [sample(j) for j in range(min(ahead, len(sizes)))]
+            for j in range(len(sizes)):
+                arrays, ev = queue.pop(0)
+                if mode == 'eager' and j + 1 < len(sizes):
+                    queue.append(sample(j + 1))
                 main.wait_event(ev)
-                for t in arrays:
-                    if t is not None:
-                        t.record_stream(main)            # allocated on the side stream, consumed on this one
+                if not ring:
+                    for t in arrays:
+                        if t is not None:
+                            t.record_stream(main)        # allocated on the side stream, consumed on this one
+                if mode == 'late' and j + 2 < len(sizes):
+                    stepped = torch.cuda.Event()
+                    self.engine.pending_after_step_event = stepped
                 losses.append(self._train_arrays(arrays, rows))
+                if ring:
+                    trained[j % ring] = torch.cuda.Event()
+                    trained[j % ring].record(main)
+                if mode == 'late' and j + 2 < len(sizes):
+                    side.wait_event(stepped)             # the fused step kernel of chunk j is done: sample chunk j + 2
+                    queue.append(sample(j + 2))
+            main.wait_stream(side)
         else:   # any object with the reference's next_batch() (numpy arrays): upload batch by batch
             while done < n_batches:
                 batch = sampler.next_batch()

@@ -62,6 +62,20 @@ class DeviceSamplerBase(object):
         if self._pair_set:
             a.pair_set, a.pair_set_bits = _lib.ptr(self._pair_set[0]), self._pair_set[1]
 
+    # -- output buffers ---------------------------------------------------------------------------
+    ring_slot = None      # set by the epoch loop of the model classes: next_chunk then writes into persistent buffers of
+                          # that slot instead of fresh tensors (an allocation per minibatch on a side stream makes the
+                          # caching allocator synchronise now and then: single minibatches came out 2-3x slower)
+
+    def _empty(self, key, shape, dtype):
+        if self.ring_slot is None:
+            return self.torch.empty(*shape, dtype=dtype, device=self.device)
+        pool = self.__dict__.setdefault('_ring', {})
+        t = pool.get((self.ring_slot, key))
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = pool[(self.ring_slot, key)] = self.torch.empty(*shape, dtype=dtype, device=self.device)
+        return t
+
     # -- cursor ---------------------------------------------------------------------------------
     def seek(self, epoch, batch=0):
         self.epoch, self.batch = int(epoch), int(batch)

@@ -20,7 +20,7 @@ class Sampler(TupleSamplerBase):
 
     def next_chunk(self, n):
         """n minibatches as ONE CUDA int32 tensor [n * B, 5]."""
-        out = self.torch.empty(n * self.batch_size, 5, dtype=self.torch.int32, device=self.device)
+        out = self._empty('tuples', (n * self.batch_size, 5), self.torch.int32)
         off = 0
         for epoch, batch0, count in self._segments(n):
             self._launch(count, epoch, batch0, out, None, off)

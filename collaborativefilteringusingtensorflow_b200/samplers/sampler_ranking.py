@@ -17,9 +17,9 @@ class Sampler(DeviceSamplerBase):
     def next_chunk(self, n):
         """n minibatches as CUDA int32 tensors: (pairs[n*B,2], negs[n*B,W][, group[n*B,G]])."""
         torch, B, W, G = self.torch, self.batch_size, self.n_neg, self.gsize
-        pairs = torch.empty(n * B, 2, dtype=torch.int32, device=self.device)
-        negs = torch.empty(n * B, max(W, 1), dtype=torch.int32, device=self.device) if W else None
-        group = torch.empty(n * B, G, dtype=torch.int32, device=self.device) if G else None
+        pairs = self._empty('pairs', (n * B, 2), torch.int32)
+        negs = self._empty('negs', (n * B, max(W, 1)), torch.int32) if W else None
+        group = self._empty('group', (n * B, G), torch.int32) if G else None
         off = 0
         for epoch, batch0, count in self._segments(n):
             a = self._args(epoch, batch0, count)

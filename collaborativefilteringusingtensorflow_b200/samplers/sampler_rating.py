@@ -18,8 +18,8 @@ class Sampler(DeviceSamplerBase):
     def next_chunk(self, n):
         """n minibatches as CUDA tensors: (ids[n*Bt,2] int32, ratings[n*Bt] float32)."""
         torch, Bt = self.torch, self.rows_per_batch
-        ids = torch.empty(n * Bt, 2, dtype=torch.int32, device=self.device)
-        ratings = torch.empty(n * Bt, dtype=torch.float32, device=self.device)
+        ids = self._empty('ids', (n * Bt, 2), torch.int32)
+        ratings = self._empty('ratings', (n * Bt,), torch.float32)
         off = 0
         for epoch, batch0, count in self._segments(n):
             a = self._args(epoch, batch0, count)

@@ -24,8 +24,8 @@ class Sampler(TupleSamplerBase):
     def next_chunk(self, n):
         """n minibatches as CUDA tensors (uitj int32 [n * B, 4], coefs float32 [n * B, 2])."""
         torch = self.torch
-        out = torch.empty(n * self.batch_size, 4, dtype=torch.int32, device=self.device)
-        coefs = torch.empty(n * self.batch_size, 2, dtype=torch.float32, device=self.device)
+        out = self._empty('tuples', (n * self.batch_size, 4), torch.int32)
+        coefs = self._empty('coefs', (n * self.batch_size, 2), torch.float32)
         self._launch(n, 0, self.batch, out, coefs, 0)
         self.batch += n
         return out, coefs

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CF_ABI_VERSION 20
+#define CF_ABI_VERSION 21
 
 /* models */
 enum { CF_MODEL_BPR = 0, CF_MODEL_CML = 1, CF_MODEL_GBPR = 2, CF_MODEL_WRMF = 3 };
@@ -128,6 +128,10 @@ typedef struct cf_step_args {
    * i / n_peers (stride ld; zero at rest; mapped with cf_ipc_open) -- gradient rows leave over NVLink while item rows
    * arrive, and the owner applies its table locally (cf_exchange_apply with dense_grads) */
   float* peerG[CF_MAX_PEERS];
+  /* optional cudaEvent_t recorded on `stream` right after the fused step kernel of the LAST minibatch of the call (before its
+   * staged apply): lets the caller start independent work -- the sampler launch of a later minibatch on another stream --
+   * under the short kernels that follow, not under the occupancy-bound step kernel */
+  void* event_after_step;
 } cf_step_args;
 
 int cf_train_steps(const cf_step_args* args, void* stream);

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     # field order/types are mirrored by hand; sizes follow from the C layout rules (natural alignment)
     assert C.sizeof(_lib.Csr) == 4 * 8 + 3 * 8
-    assert C.sizeof(_lib.StepArgs) == 6 * 8 + 2 * 8 + 2 * 4 + 4 * 8 + 4 * 4 + 4 * 4 + 6 * 4 + 6 * 8 + 8 + 2 * 8 + 2 * 8 + 8 * 8 + 2 * 8 + 2 * 4 + 2 * 8 + 8 * 8
+    assert C.sizeof(_lib.StepArgs) == 6 * 8 + 2 * 8 + 2 * 4 + 4 * 8 + 4 * 4 + 4 * 4 + 6 * 4 + 6 * 8 + 8 + 2 * 8 + 2 * 8 + 8 * 8 + 2 * 8 + 2 * 4 + 2 * 8 + 8 * 8 + 8
     assert C.sizeof(_lib.SampleArgs) == 2 * C.sizeof(_lib.Csr) + 3 * 8 + 6 * 4 + 5 * 8 + 8 + 2 * 4
     assert C.sizeof(_lib.TopkArgs) == 3 * 8 + 2 * 8 + 2 * 4 + 8 + 3 * 4 + 4 + C.sizeof(_lib.Csr) + 3 * 8 + 2 * 8
 

@@ -1,0 +1,14 @@
+#!/bin/bash
+tag=${1:-run}
+mkdir -p gpurun_out
+for ov in 2 0 1; do
+( CF_SAMPLE_OVERLAP=$ov timeout 900 python bench.py --steps 50 --warmup 5 --no-cpu-baseline --topk-users 0 > gpurun_out/${tag}_bench_ov${ov}.json 2> gpurun_out/${tag}_bench_ov${ov}.err; echo "bench overlap=$ov rc=$?" )
+python - <<PY
+import json
+j=json.loads(open('gpurun_out/${tag}_bench_ov${ov}.json').read().strip().splitlines()[-1])
+print('overlap=$ov value %.3f G  ms %.3f  whole_step_frac %.3f e2e %.3f G' % (j['value']/1e9, j['ms_per_step'], j['roofline']['whole_step_frac'], j['e2e']['value']/1e9))
+for k,v in j['other_configs'].items():
+    print('   ', k, v.get('value'), v.get('ms_per_step', v.get('ms_per_half_sweep')), (v.get('roofline') or {}).get('whole_step_frac'))
+PY
+done
+( timeout 600 python -m pytest tests/test_gpu_e2e.py tests/test_gpu_steps.py tests/test_gpu_sampler.py -x -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest rc=$?" ); tail -3 gpurun_out/${tag}_pytest.log
