@@ -41,7 +41,8 @@ constexpr int TC_NW = 256;       // items per B tile of the wide kernel: ONE tcg
 constexpr int TC_KCH = 64;       // bf16 elements per 128-byte swizzle chunk
 constexpr int TC_CHUNK_BYTES = TC_M * TC_KCH * 2;   // 16 KB: one TMA box {64, 128}
 constexpr int TC_CAP = 512;      // candidate buffer entries per (row, split)
-constexpr int TC_KMAX = 200;     // largest K served by the tensor path (a compacted row keeps K + the 2-eps band <= CAP - 128)
+constexpr int TC_KMAX = 200;     // largest K of ONE sweep (a compacted row keeps K + the 2-eps band <= CAP - 128)
+constexpr int TC_KMAX_ROUNDS = 1024;   // largest K of a call: K > TC_KMAX is served in rounds of TC_KMAX (see cf_topk_tc)
 constexpr int TC_THREADS = 384;  // warp 0: TMA, 1: MMA, 2: TMEM alloc, 3: idle, 4..11: epilogue
 constexpr int TC_MAX_STAGES = 6;
 
@@ -56,6 +57,7 @@ struct TcParams {
   int32_t* overflow;               // [T_pad]
   float* dbg_scores;               // optional [T_pad, dbg_ld] dump of the raw accumulators
   long long dbg_ld;
+  int mask_by_row;                 // rounds (K > TC_KMAX): the mask CSR is indexed by the query row, not by the user id
 };
 
 using namespace tc;
@@ -172,7 +174,7 @@ struct RowSweep {
     tcur = 0;
     thi = 0;
     if (valid && P.tr_indptr) {
-      const long long u = P.users ? P.users[row] : row;
+      const long long u = (P.users && !P.mask_by_row) ? P.users[row] : row;
       tcur = P.tr_indptr[u];
       thi = P.tr_indptr[u + 1];
     }
@@ -699,6 +701,9 @@ struct RerankParams {
   int32_t* out_idx;
   double* out_val;
   int32_t* stats;
+  int out_ld, out_off;          // the row's K results go to out[t * out_ld + out_off ..]  (rounds: a slice of the caller's [T, K])
+  int mask_by_row;              // rounds: the mask CSR is indexed by the query row
+  int count_overflow;           // add the rows left to the exact kernel to stats[0] (rounds count them once, from the sticky flags)
 };
 
 __device__ __forceinline__ bool rr_before(double va, int ia, double vb, int ib) { return va > vb || (va == vb && ia < ib); }
@@ -709,12 +714,13 @@ __global__ void __launch_bounds__(256) k_rerank(const __grid_constant__ RerankPa
   __shared__ __align__(16) double s_u[512];   // the query row, widened once (fp32 -> fp64 conversions run at a quarter of the FMA rate)
   for (int t = blockIdx.x; t < P.T; t += gridDim.x) {
     if (P.overflow[t]) {            // recomputed by the exact streaming kernel
-      if (P.stats && threadIdx.x == 0) atomicAdd(P.stats, 1);
+      if (P.stats && P.count_overflow && threadIdx.x == 0) atomicAdd(P.stats, 1);
       continue;
     }
     const long long u = P.users ? P.users[t] : t;
+    const long long mrow = P.mask_by_row ? t : u;
     for (int k = threadIdx.x; k < P.ld; k += blockDim.x) s_u[k] = (double)P.U[u * P.ld + k];
-    const long long tlo = P.tr_indptr ? P.tr_indptr[u] : 0, thi = P.tr_indptr ? P.tr_indptr[u + 1] : 0;
+    const long long tlo = P.tr_indptr ? P.tr_indptr[mrow] : 0, thi = P.tr_indptr ? P.tr_indptr[mrow + 1] : 0;
     int total = 0;
     for (int s = 0; s < P.S; ++s) total += P.cand_cnt[(long long)t * P.S + s];
     int n2 = 32;
@@ -785,10 +791,144 @@ __global__ void __launch_bounds__(256) k_rerank(const __grid_constant__ RerankPa
     }
     for (int k = threadIdx.x; k < P.K; k += blockDim.x) {
       const bool ok = k < total && s_idx[k] != 0x7fffffff;
-      P.out_idx[(long long)t * P.K + k] = ok ? s_idx[k] : -1;
-      if (P.out_val) P.out_val[(long long)t * P.K + k] = ok ? s_val[k] : -INFINITY;
+      P.out_idx[(long long)t * P.out_ld + P.out_off + k] = ok ? s_idx[k] : -1;
+      if (P.out_val) P.out_val[(long long)t * P.out_ld + P.out_off + k] = ok ? s_val[k] : -INFINITY;
     }
     __syncthreads();
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------ K > TC_KMAX: rounds
+// A call with K in (TC_KMAX, TC_KMAX_ROUNDS] (the tail of cml.py:203-211 re-recommends once at topN = 1000) is served in
+// ceil(K / TC_KMAX) rounds of the same sweep + re-rank: round r returns the exact top-TC_KMAX among the items that are
+// neither training items nor results of the rounds before it, so the concatenation of the rounds IS the exact top-K in
+// (score desc, id asc) order.  "Results of the rounds before" are masked like training items: before round r >= 1,
+// k_mask_merge writes a mask CSR indexed by QUERY ROW whose row t is the sorted union of the user's training row and the
+// row's 200 r earlier results (missing results -- fewer unmasked items than K -- become 0x7fffffff sentinels at the end
+// of the row, which keeps the row sorted and matches no item).  Rows of the merged CSR sit at
+// rowoff[t] + t * 200 r (rowoff = exclusive scan of the query rows' training-row lengths, computed once), so no
+// allocation and no host round trip depends on the data.  The operand matrices are prepared once.  A row whose candidate
+// buffer overflows in any round, or whose merged row does not fit the workspace (only possible when `users` repeats a
+// user), is flagged "sticky" and recomputed in full by the exact kernel at the end of the call.
+constexpr int MM_CAP = TC_KMAX_ROUNDS;
+constexpr int MM_SENTINEL = 0x7fffffff;
+
+struct MaskParams {
+  const int32_t* users;           // [T] or NULL
+  const long long* tr_indptr;     // the caller's training CSR (by user id) or NULL
+  const int32_t* tr_indices;
+  int T, K, prev, prev_max;       // prev: earlier results per row in this round; prev_max: in the last round
+  long long cap;                  // entries of ind2
+  long long* rowoff;              // [T + 1]
+  long long* indptr2;             // [T + 1] the round's mask CSR, by query row
+  int32_t* ind2;
+  int32_t* sticky;                // [T]
+  const int32_t* out_idx;         // the caller's [T, K]
+};
+
+__device__ __forceinline__ long long mm_row_len(const MaskParams& P, int t) {
+  if (!P.tr_indptr) return 0;
+  const long long u = P.users ? P.users[t] : t;
+  return P.tr_indptr[u + 1] - P.tr_indptr[u];
+}
+
+__global__ void __launch_bounds__(1024) k_mask_scan(const __grid_constant__ MaskParams P) {
+  __shared__ long long s_part[1024];
+  const int tid = threadIdx.x;
+  const long long per = ((long long)P.T + 1023) / 1024;
+  const long long lo = min((long long)P.T, tid * per), hi = min((long long)P.T, lo + per);
+  long long sum = 0;
+  for (long long t = lo; t < hi; ++t) sum += mm_row_len(P, (int)t);
+  s_part[tid] = sum;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const long long v = tid >= off ? s_part[tid - off] : 0;
+    __syncthreads();
+    s_part[tid] += v;
+    __syncthreads();
+  }
+  long long run = s_part[tid] - sum;
+  for (long long t = lo; t < hi; ++t) {
+    P.rowoff[t] = run;
+    run += mm_row_len(P, (int)t);
+    P.sticky[t] = (run + (t + 1) * P.prev_max > P.cap) ? 1 : 0;   // the row's widest merged form must end inside ind2
+  }
+  if (tid == 1023) P.rowoff[P.T] = s_part[1023];
+}
+
+__device__ __forceinline__ int mm_lower_bound(const int32_t* a, int n, int x) {   // #elements < x of the sorted a[0..n)
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) k_mask_merge(const __grid_constant__ MaskParams P) {
+  __shared__ int32_t s_prev[MM_CAP];
+  for (int t = blockIdx.x; t < P.T; t += gridDim.x) {
+    const long long u = P.users ? P.users[t] : t;
+    const long long tlo = P.tr_indptr ? P.tr_indptr[u] : 0;
+    const int len = P.tr_indptr ? (int)(P.tr_indptr[u + 1] - tlo) : 0;
+    const long long f_lo = P.rowoff[t] + (long long)t * P.prev, f_hi = P.rowoff[t + 1] + (long long)(t + 1) * P.prev;
+    const long long lo = min(f_lo, P.cap), hi = min(f_hi, P.cap);
+    if (threadIdx.x == 0) {
+      P.indptr2[t] = lo;
+      if (t == P.T - 1) P.indptr2[P.T] = hi;
+    }
+    if (hi < f_hi) {   // does not fit (flagged sticky by the scan): a harmless row of sentinels
+      for (long long e = lo + threadIdx.x; e < hi; e += blockDim.x) P.ind2[e] = MM_SENTINEL;
+      continue;
+    }
+    const bool dead = P.sticky[t] != 0;   // its earlier results were never written
+    int n2 = 32;
+    while (n2 < P.prev) n2 <<= 1;
+    for (int j = threadIdx.x; j < n2; j += blockDim.x) {
+      int id = MM_SENTINEL;
+      if (j < P.prev && !dead) {
+        id = P.out_idx[(long long)t * P.K + j];
+        if (id < 0) id = MM_SENTINEL;
+      }
+      s_prev[j] = id;
+    }
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int x = threadIdx.x; x < n2; x += blockDim.x) {
+          const int p = x ^ j;
+          if (p > x) {
+            const int va = s_prev[x], vb = s_prev[p];
+            if (((x & k) == 0) ? (va > vb) : (va < vb)) { s_prev[x] = vb; s_prev[p] = va; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    const int32_t* tr = P.tr_indices + tlo;
+    for (int j = threadIdx.x; j < len; j += blockDim.x) {
+      const int x = tr[j];
+      P.ind2[lo + j + mm_lower_bound(s_prev, P.prev, x)] = x;
+    }
+    for (int j = threadIdx.x; j < P.prev; j += blockDim.x) {
+      const int x = s_prev[j];
+      P.ind2[lo + j + (x == MM_SENTINEL ? len : mm_lower_bound(tr, len, x))] = x;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_sticky_or(int32_t* sticky, const int32_t* ovf, int T, int32_t* count) {
+  int c = 0;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+    const int s = sticky[t] | ovf[t];
+    sticky[t] = s;
+    c += s != 0;
+  }
+  if (count) {   // (last round only) rows handed to the exact kernel
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
   }
 }
 
@@ -826,6 +966,9 @@ struct TcPlan {
   long long T_pad, N_pad;
   size_t off_vb, off_qb, off_eps, off_cand, off_ccnt, off_ovf, off_bmax, total;
   size_t smem;
+  int rounds;                                // ceil(K / TC_KMAX); the rest is used when rounds > 1
+  long long mask_cap;                        // entries of the per-round mask CSR
+  size_t off_sticky, off_rowoff, off_indptr2, off_ind2;
 };
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -876,6 +1019,16 @@ int plan_tc(const cf_topk_args* a, TcPlan* p) {
   p->off_ccnt = off; off = align_up(off + (size_t)p->T_pad * p->S_cand * 4, 256);
   p->off_ovf = off; off = align_up(off + (size_t)p->T_pad * 4, 256);
   p->off_bmax = off; off = align_up(off + 256, 256);
+  p->rounds = (a->K + TC_KMAX - 1) / TC_KMAX;
+  p->mask_cap = 0;
+  if (p->rounds > 1) {
+    CF_CHECK_ARG(a->train.indptr == nullptr || a->train.nnz >= 0, "cf_topk_tc: train.nnz is required for K > %d", TC_KMAX);
+    p->mask_cap = (a->train.indptr ? (long long)a->train.nnz : 0ll) + (long long)a->T * TC_KMAX * (p->rounds - 1);
+    p->off_sticky = off; off = align_up(off + (size_t)p->T_pad * 4, 256);
+    p->off_rowoff = off; off = align_up(off + ((size_t)a->T + 1) * 8, 256);
+    p->off_indptr2 = off; off = align_up(off + ((size_t)a->T + 1) * 8, 256);
+    p->off_ind2 = off; off = align_up(off + (size_t)p->mask_cap * 4 + 4, 256);
+  }
   p->total = off;
   return 0;
 }
@@ -884,7 +1037,7 @@ int validate_tc(const cf_topk_args* a, const char* who) {
   CF_CHECK_ARG(a != nullptr, "%s: args is NULL", who);
   CF_CHECK_ARG(a->d > 0 && a->ld >= a->d && a->ld % 4 == 0 && a->ld <= 512, "%s: need 0 < d <= ld <= 512, ld %% 4 == 0", who);
   CF_CHECK_ARG(a->T > 0 && a->n_items > 0 && a->n_items < (1ll << 31), "%s: T and n_items must be positive", who);
-  CF_CHECK_ARG(a->K > 0 && a->K <= TC_KMAX, "%s: K must be in [1, %d] for the tensor path (got %d)", who, TC_KMAX, a->K);
+  CF_CHECK_ARG(a->K > 0 && a->K <= TC_KMAX_ROUNDS, "%s: K must be in [1, %d] for the tensor path (got %d)", who, TC_KMAX_ROUNDS, a->K);
   CF_CHECK_ARG(a->kind >= CF_SCORE_DOT && a->kind <= CF_SCORE_NEG_SQDIST, "%s: unknown scoring kind %d", who, a->kind);
   CF_CHECK_ARG(a->item_lo == 0 && (a->item_hi == 0 || a->item_hi == a->n_items), "%s: item ranges are not supported here (shard V instead)", who);
   return 0;
@@ -941,32 +1094,67 @@ extern "C" int cf_topk_tc(const cf_topk_args* a, void* workspace, int64_t worksp
   if (int rc = make_map(&tmQ, Qb, p.T_pad, p.Kp)) return rc;
   if (int rc = make_map(&tmV, Vb, p.N_pad, p.Kp, p.pair ? TC_M : p.NB)) return rc;   // (the paired kernel: each CTA loads half a tile)
   TcParams P = {};
-  P.T = a->T; P.N = (int)a->n_items; P.KC = p.KC; P.n_tiles = (int)(p.N_pad / p.NB); P.S = p.S; P.stages = p.stages; P.K = a->K;
+  P.T = a->T; P.N = (int)a->n_items; P.KC = p.KC; P.n_tiles = (int)(p.N_pad / p.NB); P.S = p.S; P.stages = p.stages;
   P.users = a->users; P.tr_indptr = (const long long*)a->train.indptr; P.tr_indices = a->train.indices;
   P.eps2 = eps2; P.cand = cand; P.cand_cnt = ccnt; P.overflow = ovf;
   P.dbg_scores = dbg_scores; P.dbg_ld = (long long)align_up((size_t)a->n_items, TC_NW);   // the same stride for both kernels
-  dim3 grid((unsigned)(p.T_pad / (TC_MT * TC_M)), (unsigned)p.S);
-  if (p.pair) {
-    grid.x *= 2;     // clusters of two CTAs, 128 query rows each
-    CF_CUDA_OK(cudaFuncSetAttribute(k_topk_tc_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    k_topk_tc_pair<<<grid, TC_THREADS, p.smem, stream>>>(tmQ, tmV, P);
-  } else if (p.NB == TC_NW) {
-    CF_CUDA_OK(cudaFuncSetAttribute(k_topk_tc<TC_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    k_topk_tc<TC_NW><<<grid, TC_THREADS, p.smem, stream>>>(tmQ, tmV, P);
-  } else {
-    CF_CUDA_OK(cudaFuncSetAttribute(k_topk_tc<TC_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    k_topk_tc<TC_N><<<grid, TC_THREADS, p.smem, stream>>>(tmQ, tmV, P);
-  }
-  CF_CUDA_OK(cudaGetLastError());
-
   RerankParams R = {};
-  R.U = a->U; R.V = a->V; R.b = a->b; R.ld = a->ld; R.nvec = a->ld / 4; R.kind = a->kind; R.T = a->T; R.S = p.S_cand; R.K = a->K;
+  R.U = a->U; R.V = a->V; R.b = a->b; R.ld = a->ld; R.nvec = a->ld / 4; R.kind = a->kind; R.T = a->T; R.S = p.S_cand;
   R.users = a->users; R.cand = cand; R.n_items = (int)a->n_items; R.cand_cnt = ccnt; R.overflow = ovf;
-  R.tr_indptr = (const long long*)a->train.indptr; R.tr_indices = a->train.indices;
-  R.out_idx = a->out_idx; R.out_val = a->out_val; R.stats = stats;
+  R.tr_indptr = P.tr_indptr; R.tr_indices = P.tr_indices;
+  R.out_idx = a->out_idx; R.out_val = a->out_val; R.stats = stats; R.out_ld = a->K; R.count_overflow = p.rounds == 1;
   int rg = a->T;
   if (rg > sms * 8) rg = sms * 8;
-  k_rerank<<<rg, 256, 0, stream>>>(R);
-  CF_CUDA_OK(cudaGetLastError());
-  return cf_topk_exact_flagged(a, ovf, stream);
+
+  MaskParams M = {};
+  int32_t* sticky = nullptr;
+  if (p.rounds > 1) {     // K > TC_KMAX: rounds of TC_KMAX over a growing mask (see k_mask_merge)
+    sticky = reinterpret_cast<int32_t*>(ws + p.off_sticky);
+    M.users = a->users; M.tr_indptr = P.tr_indptr; M.tr_indices = P.tr_indices;
+    M.T = a->T; M.K = a->K; M.prev_max = TC_KMAX * (p.rounds - 1); M.cap = p.mask_cap;
+    M.rowoff = reinterpret_cast<long long*>(ws + p.off_rowoff);
+    M.indptr2 = reinterpret_cast<long long*>(ws + p.off_indptr2);
+    M.ind2 = reinterpret_cast<int32_t*>(ws + p.off_ind2);
+    M.sticky = sticky; M.out_idx = a->out_idx;
+    k_mask_scan<<<1, 1024, 0, stream>>>(M);
+    CF_CUDA_OK(cudaGetLastError());
+  }
+  for (int r = 0; r < p.rounds; ++r) {
+    const int Kr = a->K - r * TC_KMAX < TC_KMAX ? a->K - r * TC_KMAX : TC_KMAX;
+    if (r > 0) {
+      CF_CUDA_OK(cudaMemsetAsync(ovf, 0, (size_t)p.T_pad * 4, stream));
+      CF_CUDA_OK(cudaMemsetAsync(ccnt, 0, (size_t)p.T_pad * p.S_cand * 4, stream));
+      M.prev = r * TC_KMAX;
+      int mg = a->T;
+      if (mg > sms * 8) mg = sms * 8;
+      k_mask_merge<<<mg, 256, 0, stream>>>(M);
+      CF_CUDA_OK(cudaGetLastError());
+      P.tr_indptr = M.indptr2; P.tr_indices = M.ind2; P.mask_by_row = 1; P.dbg_scores = nullptr;
+      R.tr_indptr = M.indptr2; R.tr_indices = M.ind2; R.mask_by_row = 1;
+    }
+    P.K = Kr;
+    dim3 grid((unsigned)(p.T_pad / (TC_MT * TC_M)), (unsigned)p.S);
+    if (p.pair) {
+      grid.x *= 2;     // clusters of two CTAs, 128 query rows each
+      CF_CUDA_OK(cudaFuncSetAttribute(k_topk_tc_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+      k_topk_tc_pair<<<grid, TC_THREADS, p.smem, stream>>>(tmQ, tmV, P);
+    } else if (p.NB == TC_NW) {
+      CF_CUDA_OK(cudaFuncSetAttribute(k_topk_tc<TC_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+      k_topk_tc<TC_NW><<<grid, TC_THREADS, p.smem, stream>>>(tmQ, tmV, P);
+    } else {
+      CF_CUDA_OK(cudaFuncSetAttribute(k_topk_tc<TC_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+      k_topk_tc<TC_N><<<grid, TC_THREADS, p.smem, stream>>>(tmQ, tmV, P);
+    }
+    CF_CUDA_OK(cudaGetLastError());
+    R.K = Kr; R.out_off = r * TC_KMAX;
+    k_rerank<<<rg, 256, 0, stream>>>(R);
+    CF_CUDA_OK(cudaGetLastError());
+    if (p.rounds > 1) {
+      int sg = (a->T + 255) / 256;
+      if (sg > sms * 8) sg = sms * 8;
+      k_sticky_or<<<sg, 256, 0, stream>>>(sticky, ovf, a->T, (r == p.rounds - 1) ? stats : nullptr);
+      CF_CUDA_OK(cudaGetLastError());
+    }
+  }
+  return cf_topk_exact_flagged(a, p.rounds > 1 ? sticky : ovf, stream);
 }

@@ -269,19 +269,19 @@ class FactorEngine(object):
 
     def topk(self, users, K, train_csr=None, return_values=False, item_range=None, method='auto', debug_scores=False):
         """Masked top-K item ids [T, K] int32 (and fp64 scores): bprmf.py:90-103 in one pass.
-        method: 'exact' (fp64 CUDA cores), 'tensor' (tcgen05 bf16 candidate pass + exact re-rank; identical results,
-        K <= 200, d <= 254) or 'auto' (tensor for large problems)."""
+        method: 'exact' (fp64 CUDA cores), 'tensor' (tcgen05 fp16 candidate pass + exact re-rank; identical results,
+        K <= 1024 -- above 200 in rounds of 200 --, d <= 254) or 'auto' (tensor for large problems)."""
         torch = self.torch
         if K <= 0:
             raise ValueError('K must be positive')
         a, users_t, T = self._topk_args(users, K, train_csr, item_range)
         if T == 0:
             raise ValueError('no query users')
-        tensor_ok = K <= 200 and self.d <= 254 and item_range is None
+        tensor_ok = K <= 1024 and self.d <= 254 and item_range is None
         if method == 'auto':
             method = 'tensor' if tensor_ok and T * self.n_items >= self.TENSOR_MIN_WORK else 'exact'
         if method == 'tensor' and not tensor_ok:
-            raise ValueError('the tensor-core top-K path needs K <= 200, n_factors <= 254 and no item range')
+            raise ValueError('the tensor-core top-K path needs K <= 1024, n_factors <= 254 and no item range')
         out_idx = torch.empty(T, K, dtype=torch.int32, device=self.device)
         out_val = torch.empty(T, K, dtype=torch.float64, device=self.device) if return_values else None
         a.out_idx, a.out_val = _lib.ptr(out_idx), _lib.ptr(out_val)
@@ -299,7 +299,8 @@ class FactorEngine(object):
             if getattr(self, 'tc_stats', None) is None:
                 self.tc_stats = torch.zeros(4, dtype=torch.int32, device=self.device)   # see cf_b200.h: cf_topk_tc stats
             _lib.check(self.lib.cf_topk_tc(a, base, need, _lib.ptr(dbg), _lib.ptr(self.tc_stats), stream), 'cf_topk_tc')
-            self.launches += 5
+            rounds = (K + 199) // 200
+            self.launches += 3 + 2 * rounds + (3 * rounds - 1 if rounds > 1 else 0)
             if debug_scores:
                 return out_idx, out_val, dbg
         else:

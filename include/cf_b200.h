@@ -339,10 +339,13 @@ typedef struct cf_topk_args {
 
 int cf_topk_exact(const cf_topk_args* args, void* stream);
 
-/* Same result as cf_topk_exact (bit-identical indices and fp64 scores), computed by the tensor-core path: bf16
+/* Same result as cf_topk_exact (bit-identical indices and fp64 scores), computed by the tensor-core path: fp16
  * tcgen05.mma/TMA scoring with a candidate-superset epilogue (the score matrix never leaves the SM), then an exact fp64
  * re-rank of the candidates; rows whose candidate buffer overflows fall back to the exact kernel inside the same call.
- * K <= 200, d <= 254.  `workspace` (device, 1024-byte aligned) must hold cf_topk_tc_workspace_bytes(args) bytes.
+ * K <= 1024, d <= 254.  K > 200 (cml.py:203-211 re-recommends at topN = 1000) runs ceil(K / 200) rounds of the same sweep:
+ * round r masks the training items AND the results of the earlier rounds (a per-query-row mask CSR merged on the device),
+ * so the rounds concatenate to the exact top-K; args->train.nnz must be set then (it sizes that mask).
+ * `workspace` (device, 1024-byte aligned) must hold cf_topk_tc_workspace_bytes(args) bytes.
 * dbg_scores: NULL, or [T, round_up(n_items, 256)] to receive the raw fp16-GEMM scores (tests; row stride = n_items rounded
  * up to 256).
  * stats: NULL, or device int32[4] = {rows that fell back to the exact kernel, total candidates re-ranked,

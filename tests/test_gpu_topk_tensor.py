@@ -127,3 +127,42 @@ def test_paired_kernel_equals_the_exact_kernel(monkeypatch):
         ei, ev = m.engine.topk(users, K, csr, return_values=True, method='exact')
         assert torch.equal(ti, ei) and torch.equal(tv, ev), (cls.__name__, nu, ni, d, K)
         assert int(m.engine.tc_stats[0].item()) == 0       # no row fell back to the exact kernel
+
+
+@pytest.mark.parametrize('kind,nu,ni,d,K,T,masked', [('cml', 700, 30011, 128, 1000, 600, True), ('bpr', 300, 9000, 64, 201, 300, True),
+                                                    ('gbpr', 520, 12345, 100, 500, 520, True), ('bpr', 260, 5000, 128, 1000, 260, False),
+                                                    ('cml', 300, 1500, 32, 1000, 300, True), ('bpr', 64, 700, 20, 1024, 64, True)])
+def test_topk_above_200_runs_in_rounds_and_equals_exact(kind, nu, ni, d, K, T, masked):
+    """K in (200, 1024] (the CML tail re-recommends at topN = 1000, cml.py:203-211): rounds of 200 over a mask that grows by
+    the earlier rounds' results; lists and fp64 scores equal the exact kernel's, including exact ties, catalogues with
+    fewer unmasked items than K (-1 padding) and a query list that repeats users."""
+    import torch
+    rng = np.random.default_rng(nu + ni + K)
+    m = _model(kind, nu, ni, d, std=0.3 if kind != 'cml' else 0.1)
+    with torch.no_grad():
+        m.engine.V[ni // 2:ni // 2 + 4] = m.engine.V[5]
+        if kind == 'gbpr':
+            m.engine.b[ni // 2:ni // 2 + 4] = m.engine.b[5]
+    csr = _train_csr(rng, nu, ni, 300 if ni < 2000 else 60, m.device) if masked else None
+    u = rng.permutation(nu)[:T].astype(np.int32)
+    u[-3:] = u[:3]                                   # repeated query users
+    users = torch.from_numpy(u).to(m.device)
+    ei, ev = m.engine.topk(users, min(K, ni), csr, return_values=True, method='exact')
+    ti, tv = m.engine.topk(users, min(K, ni), csr, return_values=True, method='tensor')
+    assert torch.equal(ei, ti), 'first mismatch at %s' % (torch.nonzero(ei != ti)[:3].tolist(),)
+    assert torch.equal(ev, tv)
+    st = m.engine.tc_stats.cpu().numpy()
+    assert st[0] <= max(3, T // 50), 'the tensor path handed %d of %d rows to the exact fallback' % (st[0], T)
+
+
+def test_rounds_hand_overflowed_rows_to_the_exact_kernel():
+    """Identical items: every sweep overflows its candidate buffers -> the rows turn sticky and the exact kernel writes all K."""
+    import torch
+    nu, ni, d, K = 260, 4000, 64, 450
+    m = _model('bpr', nu, ni, d)
+    with torch.no_grad():
+        m.engine.V[:, :d] = m.engine.V[0, :d]
+    users = torch.arange(nu, dtype=torch.int32, device=m.device)
+    ti = m.engine.topk(users, K, None, method='tensor')
+    assert torch.equal(ti, torch.arange(K, dtype=torch.int32, device=m.device).expand(nu, K))
+    assert int(m.engine.tc_stats[0].item()) == nu
