@@ -229,3 +229,40 @@ def test_empty_and_ragged_inputs_raise():
         m.step(np.zeros((0, 2), dtype=np.int32), np.zeros((0, 1), dtype=np.int64))
     with pytest.raises(ValueError):
         m.step(np.zeros((4, 2), dtype=np.int32), np.zeros((3, 1), dtype=np.int64))
+
+
+@pytest.mark.parametrize('kind,W', [('bpr', 1), ('cml', 1)])
+@pytest.mark.parametrize('d', [128, 100, 68])
+@pytest.mark.parametrize('optimizer', ['adagrad', 'sgd'])
+def test_specialised_step_kernel_equals_the_generic_one(monkeypatch, kind, W, d, optimizer):
+    """cf_step_fast.cu (unrolled + software-pipelined; taken for BPR / CML with one negative per pair at 64 < ld <= 128) runs the
+    generic kernel's arithmetic operation for operation: on a minibatch without repeated rows the tables and accumulators
+    are bit-identical; with repeats only the order of the staged red.adds differs (as it does from run to run)."""
+    import torch
+    nu, ni, B = 6000, 5000 * (1 + W), 5000
+    kw = dict(reg=0.05) if kind == 'bpr' else dict(reg_cov=1.0, margin=1.0, use_rank_weight=True, clip_norm=1.0,
+                                                   init_stddev=0.9 / np.sqrt(d))
+    rng = np.random.default_rng(d + W)
+    uniq_pairs = np.stack([rng.permutation(nu)[:B], rng.permutation(5000)], 1).astype(np.int32)
+    uniq_negs = (5000 + rng.permutation(5000 * W)).reshape(B, W).astype(np.int64)          # no row occurs twice
+    dup_pairs = np.stack([rng.integers(0, 300, B), rng.integers(0, 200, B)], 1).astype(np.int32)
+    dup_negs = rng.integers(0, 200, (B, W)).astype(np.int64)                                # almost every row repeats
+    states, losses = [], []
+    for generic in (True, False):
+        if generic:
+            monkeypatch.setenv('CF_STEP_GENERIC', '1')
+        else:
+            monkeypatch.delenv('CF_STEP_GENERIC')
+        m = _mk(kind, nu, ni, d, lr=0.1, optimizer=optimizer, **kw)
+        l1 = m.step(uniq_pairs, uniq_negs)
+        s1 = _state(m)
+        l2 = m.step(dup_pairs, dup_negs)
+        l3 = m.step(uniq_pairs[:777], uniq_negs[:777])          # ragged tail: fewer pairs than warps in the grid
+        states.append((s1, _state(m)))
+        losses.append((l1, l2, l3))
+    (g1, g2), (f1, f2) = states
+    for k in g1:
+        assert np.array_equal(g1[k], f1[k]), '%s differs on a minibatch without repeated rows' % k
+        _close(f2[k], g2[k], '%s W=%d d=%d %s' % (kind, W, d, k), stress=True)
+    for a, b in zip(*losses):
+        assert abs(a - b) <= 1e-6 * abs(a)
