@@ -319,6 +319,14 @@ def make_sampler(wl, csr, B, seed, device):
     return sampler_ranking.Sampler(csr, wl['W'], B, seed=seed, device=device)
 
 
+def step_kernel_name(wl, update):
+    """Which step kernel cf_train_steps launches for this workload (cf_step.cu: the specialised forms of cf_step_fast.cu serve
+    one negative per pair and GBPR with 5 negatives and a group of 3 or 1, SYNC mode, rows of 36..128 floats)."""
+    fast = update == 'sync' and 32 < wl['d'] <= 128 and os.environ.get('CF_STEP_GENERIC', '0') in ('', '0') and (
+        (wl['model'] in ('bpr', 'cml') and wl['W'] == 1) or (wl['model'] == 'gbpr' and wl['W'] == 5 and wl['G'] in (1, 3)))
+    return 'k_step_fast' if fast else 'k_step'
+
+
 def time_training(wl, csr, B, K, Wm, device, optimizer, update, pk):
     """Warm-up + exactly K timed minibatches (CUDA events on the launching stream) + per-kernel event times of K more.
     Returns (model, sampler, dict)."""
@@ -363,7 +371,7 @@ def time_training(wl, csr, B, K, Wm, device, optimizer, update, pk):
     achieved = bpp * B / ((step_ms + apply_ms) * 1e-3) / 1e9
     whole = bpp * B / (ms / K * 1e-3) / 1e9
     out = dict(ms=ms, t0=t0, t1=t1, launches=launches, losses=losses, units=B * wl['W'] * K,
-               roofline=dict(bound='hbm', kernel='cfstep::k_step<%s> + cfstep::k_apply_staged' % wl['model'], achieved=achieved,
+               roofline=dict(bound='hbm', kernel='cfstep::%s<%s> + cfstep::k_apply_staged' % (step_kernel_name(wl, update), wl['model']), achieved=achieved,
                              peak=pk['hbm'], unit='GB/s', frac=achieved / pk['hbm'], traffic=None, peak_source=pk['source'],
                              algorithmic_bytes_per_launch=bpp * B, kernel_ms_per_launch=step_ms + apply_ms,
                              step_kernel_ms=step_ms, apply_kernel_ms=apply_ms, count_kernel_ms=count_ms,

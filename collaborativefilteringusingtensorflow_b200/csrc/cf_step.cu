@@ -146,7 +146,7 @@ step_kernel_t pick_kernel(int model, int nvec, int* lpg, bool ext) {
 
 
 cfstep::step_kernel_t cf_pick_apply_kernel(int nvec) { return pick_apply(nvec); }   // used by cf_exchange.cu
-cfstep::step_kernel_t cf_step_pick_fast(int model, int W, int* nbuf, int* slots);      // cf_step_fast.cu
+cfstep::step_kernel_t cf_step_pick_fast(int model, int W, int G, int lpg, int* nbuf, int* slots);   // cf_step_fast.cu
 
 extern "C" int64_t cf_step_staging_rows(int32_t model, int32_t B, int32_t W, int32_t G) {
   const int64_t R = (model == CF_MODEL_WRMF) ? 2 : 2 + (int64_t)W + G;
@@ -244,15 +244,16 @@ static int train_steps_impl(const cf_step_args* a, cudaStream_t stream, cudaEven
   CF_CHECK_ARG((2 + T) * slot_bytes <= budget1, "cf_train_steps: rows too wide for the shared-memory staging (ld=%d)", a->ld);
   P.T = T;
   size_t smem = (size_t)((2 + T) * slot_bytes);
-  // the reference's own settings (BPR with 1 negative, CML with 5; also 5 / 1) at 64 < ld <= 128, single GPU, SYNC: the
-  // unrolled, software-pipelined form of the same arithmetic (cf_step_fast.cu).  CF_STEP_GENERIC=1 keeps the generic kernel.
+  // one negative per pair (BPRMF's reference setting) / GBPR with 5 negatives and a group of 3 or 1, rows of 36..128 floats,
+  // single GPU, SYNC: the unrolled, software-pipelined form of the same arithmetic (cf_step_fast.cu).  CF_STEP_GENERIC=1
+  // keeps the generic kernel (tests compare the two).
   const char* genv = getenv("CF_STEP_GENERIC");
   const bool generic_only = genv && atoi(genv) > 0;
-  if (!generic_only && a->update == CF_UPDATE_SYNC && !a->gradV && !a->gradU && a->n_peers == 0 && P.nvec > 16 && P.nvec <= 32) {
+  if (!generic_only && a->update == CF_UPDATE_SYNC && !a->gradV && !a->gradU && a->n_peers == 0 && P.nvec > 8 && P.nvec <= 32) {
     int nbuf = 0, slots = 0;
-    if (step_kernel_t fast = cf_step_pick_fast(a->model, W, &nbuf, &slots)) {
+    if (step_kernel_t fast = cf_step_pick_fast(a->model, W, G, lpg, &nbuf, &slots)) {
       kern = fast;
-      smem = (size_t)8 * nbuf * 2 * slots * a->ld * 4;
+      smem = (size_t)groups_per_block * nbuf * 2 * slots * a->ld * 4;
     }
   }
   CF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

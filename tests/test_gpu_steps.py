@@ -231,22 +231,27 @@ def test_empty_and_ragged_inputs_raise():
         m.step(np.zeros((4, 2), dtype=np.int32), np.zeros((3, 1), dtype=np.int64))
 
 
-@pytest.mark.parametrize('kind,W', [('bpr', 1), ('cml', 1)])
-@pytest.mark.parametrize('d', [128, 100, 68])
+@pytest.mark.parametrize('kind,W,G', [('bpr', 1, 0), ('cml', 1, 0), ('gbpr', 5, 3), ('gbpr', 5, 1)])
+@pytest.mark.parametrize('d', [128, 100, 68, 64, 40])
 @pytest.mark.parametrize('optimizer', ['adagrad', 'sgd'])
-def test_specialised_step_kernel_equals_the_generic_one(monkeypatch, kind, W, d, optimizer):
-    """cf_step_fast.cu (unrolled + software-pipelined; taken for BPR / CML with one negative per pair at 64 < ld <= 128) runs the
-    generic kernel's arithmetic operation for operation: on a minibatch without repeated rows the tables and accumulators
-    are bit-identical; with repeats only the order of the staged red.adds differs (as it does from run to run)."""
-    import torch
-    nu, ni, B = 6000, 5000 * (1 + W), 5000
-    kw = dict(reg=0.05) if kind == 'bpr' else dict(reg_cov=1.0, margin=1.0, use_rank_weight=True, clip_norm=1.0,
-                                                   init_stddev=0.9 / np.sqrt(d))
+def test_specialised_step_kernel_equals_the_generic_one(monkeypatch, kind, W, G, d, optimizer):
+    """cf_step_fast.cu (unrolled + software-pipelined; taken for one negative per pair and for GBPR with 5 negatives and a group
+    of 3 or 1, at 32 < ld <= 128) runs the generic kernel's arithmetic operation for operation: on a minibatch without
+    repeated rows the tables and accumulators are bit-identical; with repeats only the order of the staged red.adds differs
+    (as it does from run to run)."""
+    nu, ni, B = 5000 * (2 + G), 5000 * (1 + W), 5000
+    kw = dict(reg=0.05) if kind == 'bpr' else dict(reg=0.01, rho=0.4, gsize=G) if kind == 'gbpr' else \
+        dict(reg_cov=1.0, margin=1.0, use_rank_weight=True, clip_norm=1.0, init_stddev=0.9 / np.sqrt(d))
     rng = np.random.default_rng(d + W)
-    uniq_pairs = np.stack([rng.permutation(nu)[:B], rng.permutation(5000)], 1).astype(np.int32)
-    uniq_negs = (5000 + rng.permutation(5000 * W)).reshape(B, W).astype(np.int64)          # no row occurs twice
-    dup_pairs = np.stack([rng.integers(0, 300, B), rng.integers(0, 200, B)], 1).astype(np.int32)
-    dup_negs = rng.integers(0, 200, (B, W)).astype(np.int64)                                # almost every row repeats
+    uperm = rng.permutation(nu)
+    uniq = [np.stack([uperm[:B], rng.permutation(5000)], 1).astype(np.int32),
+            (5000 + rng.permutation(5000 * W)).reshape(B, W).astype(np.int64)]                 # no row occurs twice
+    dup = [np.stack([rng.integers(0, 300, B), rng.integers(0, 200, B)], 1).astype(np.int32),
+           rng.integers(0, 200, (B, W)).astype(np.int64)]                                       # almost every row repeats
+    if G:
+        uniq.append(uperm[B:B + B * G].reshape(B, G).astype(np.int64))
+        dup.append(rng.integers(0, 300, (B, G)).astype(np.int64))
+        dup[2][::7, 0] = dup[0][::7, 0]                                                         # the user inside its own group
     states, losses = [], []
     for generic in (True, False):
         if generic:
@@ -254,10 +259,10 @@ def test_specialised_step_kernel_equals_the_generic_one(monkeypatch, kind, W, d,
         else:
             monkeypatch.delenv('CF_STEP_GENERIC')
         m = _mk(kind, nu, ni, d, lr=0.1, optimizer=optimizer, **kw)
-        l1 = m.step(uniq_pairs, uniq_negs)
+        l1 = m.step(*uniq)
         s1 = _state(m)
-        l2 = m.step(dup_pairs, dup_negs)
-        l3 = m.step(uniq_pairs[:777], uniq_negs[:777])          # ragged tail: fewer pairs than warps in the grid
+        l2 = m.step(*dup)
+        l3 = m.step(*[x[:777] for x in uniq])          # ragged tail: fewer pairs than groups in the grid
         states.append((s1, _state(m)))
         losses.append((l1, l2, l3))
     (g1, g2), (f1, f2) = states
