@@ -58,6 +58,7 @@ struct TcParams {
   float* dbg_scores;               // optional [T_pad, dbg_ld] dump of the raw accumulators
   long long dbg_ld;
   int mask_by_row;                 // rounds (K > TC_KMAX): the mask CSR is indexed by the query row, not by the user id
+  int warm;                        // warm-up tiles per split (k_topk_tc; see RowSweep::sweep_warm)
 };
 
 using namespace tc;
@@ -241,6 +242,46 @@ struct RowSweep {
     }
   }
 
+  // Threshold warm-up.  A sweep that starts at theta = -inf appends EVERY score until the first compaction and every fifth one
+  // until the second: the first ~16 k items of a split cost ten times the steady state, which is nothing on a 10 M-item
+  // catalogue and a third of the sweep on a 500 k one.  So the first `warm` tiles of a split are swept twice.  The first time
+  // only ONE entry per chunk of 32 columns is appended -- the chunk's maximum, with its item id: at most TC_CAP real
+  // (score, item) entries, ascending by item like any other -- and a compaction at the end of the warm-up turns them into
+  // theta_0 = the K-th best of the unmasked ones.  Any K unmasked items bound the K-th best score of the whole catalogue from
+  // below, so the superset argument holds for theta_0 as it does for the running threshold.  Then the buffer is
+  // emptied, the mask cursor rewound and the sweep proper starts at tile 0 with theta_0 (~ the 110th best of 16 k items for
+  // K = 100: 0.7 % of the scores pass from the first tile on).  Price: `warm` extra tiles of MMA (3 % at 500 k items).
+  __device__ __forceinline__ void sweep_warm(const uint32_t (&r)[32], int item0) {
+    float mg[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float x = fmaxf(fmaxf(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1])), __uint_as_float(r[8 * g + 2]));
+      x = fmaxf(fmaxf(x, __uint_as_float(r[8 * g + 3])), __uint_as_float(r[8 * g + 4]));
+      x = fmaxf(fmaxf(x, __uint_as_float(r[8 * g + 5])), __uint_as_float(r[8 * g + 6]));
+      mg[g] = fmaxf(x, __uint_as_float(r[8 * g + 7]));
+    }
+    const float m = fmaxf(fmaxf(fmaxf(mg[0], mg[1]), mg[2]), mg[3]);
+    if (valid) {
+      int idx = 0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (mg[g] == m) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (__uint_as_float(r[8 * g + j]) == m) idx = 8 * g + j;
+        }
+      }
+      ce[cnt] = make_uint2(__float_as_uint(m), (unsigned)(item0 + idx));
+      ++cnt;
+    }
+  }
+  __device__ __forceinline__ void end_warmup(const TcParams& P, int row, int lane) {
+    compact(__ballot_sync(0xffffffffu, valid && cnt > 0), lane, P);
+    cnt = 0;
+    ver = 0;
+    if (valid && P.tr_indptr) tcur = P.tr_indptr[(P.users && !P.mask_by_row) ? P.users[row] : row];
+  }
+
   // a last compaction leaves K + the 2-eps band per buffer instead of whatever arrived since the previous one
   // (~280 -> ~110 at K = 100): the exact re-rank scores and sorts that many fewer candidates
   __device__ __forceinline__ void finish(const TcParams& P, int row, long long buffer, int lane) {
@@ -278,6 +319,8 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
   const int tile_lo = split * tiles_per_split;
   const int tile_hi = min(P.n_tiles, tile_lo + tiles_per_split);
   const int nt = max(0, tile_hi - tile_lo);
+  const int wt = min(P.warm, nt);   // warm-up tiles: iterations [0, wt) sweep tiles 0 .. wt-1 for thresholds only, [wt, wt + nt) are the sweep
+  const int ntt = nt + wt;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < P.stages; ++s) {
@@ -313,12 +356,12 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
           tma_load_2d(&tmQ, a_full, sA + (size_t)(mt * KC + kc) * TC_CHUNK_BYTES, kc * TC_KCH, row0 + mt * TC_M);
       int st = 0;
       uint32_t ph = 0u;
-      for (int t = 0; t < nt; ++t) {
+      for (int t = 0; t < ntt; ++t) {
         mbar_wait(empty + st, ph ^ 1u);
         mbar_arrive_expect_tx(full + st, (uint32_t)b_stage_bytes);
         for (int kc = 0; kc < KC; ++kc)
           tma_load_2d(&tmV, full + st, sB + (size_t)st * b_stage_bytes + (size_t)kc * b_chunk_bytes, kc * TC_KCH,
-                      (tile_lo + t) * NB);
+                      (tile_lo + (t < wt ? t : t - wt)) * NB);
         if (++st == P.stages) { st = 0; ph ^= 1u; }
       }
     }
@@ -338,7 +381,7 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
       int st = 0;
       uint32_t ph = 0u;
       uint64_t b0 = b00;
-      for (int t = 0; t < nt; ++t) {
+      for (int t = 0; t < ntt; ++t) {
         const int acc = t & 1;
         if (!WIDE) mbar_wait(tempty + acc, ((uint32_t)(t >> 1) & 1u) ^ 1u);
         mbar_wait(full + st, ph);
@@ -381,15 +424,17 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     // with instruction-fetch stalls on top.  Now: ONE room check per 128 columns (a block appends at most 128 entries per
     // row), per chunk 18 instructions unless it holds a hit (RowSweep::sweep).
     const bool dbg = P.dbg_scores != nullptr;
-    for (int t = 0; t < nt; ++t) {
+    for (int t = 0; t < ntt; ++t) {
       const int acc = WIDE ? mt : (t & 1);
+      const bool warm = t < wt;
+      if (t == wt && wt > 0) rs.end_warmup(P, row, lane);   // thresholds from the warm-up entries; the sweep proper starts at tile 0
       mbar_wait(tfull + acc, WIDE ? ((uint32_t)t & 1u) : ((uint32_t)(t >> 1) & 1u));
       tc_fence_after();
-      const int n0 = (tile_lo + t) * NB;
+      const int n0 = (tile_lo + (warm ? t : t - wt)) * NB;
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(WIDE ? mt * NB : acc * (TC_MT * TC_N) + mt * TC_N);
 #pragma unroll 1
       for (int hb = 0; hb < NB / 128; ++hb) {
-        rs.compact(__ballot_sync(0xffffffffu, rs.cnt > TC_CAP - 128), lane, P);   // make room for the next 128 columns
+        if (!warm) rs.compact(__ballot_sync(0xffffffffu, rs.cnt > TC_CAP - 128), lane, P);   // make room for the next 128 columns
         const float thr = rs.theta - rs.eps2;   // (theta only moves at a compaction)
         // software-pipelined TMEM reads: the load of chunk c + 1 is in flight while chunk c is swept
         uint32_t ra[32], rb[32];
@@ -403,7 +448,7 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
 #pragma unroll
             for (int j = 0; j < 32; ++j) P.dbg_scores[(long long)row * P.dbg_ld + n0 + c * 32 + j] = __uint_as_float(ra[j]);
           }
-          rs.sweep(ra, n0 + c * 32, thr);
+          if (warm) rs.sweep_warm(ra, n0 + c * 32); else rs.sweep(ra, n0 + c * 32, thr);
           tc_wait_ld(rb);
           if (cc + 2 < 4) {
             tc_ld32(tbase + (uint32_t)((c + 2) * 32), ra);
@@ -415,7 +460,7 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
 #pragma unroll
             for (int j = 0; j < 32; ++j) P.dbg_scores[(long long)row * P.dbg_ld + n0 + (c + 1) * 32 + j] = __uint_as_float(rb[j]);
           }
-          rs.sweep(rb, n0 + (c + 1) * 32, thr);
+          if (warm) rs.sweep_warm(rb, n0 + (c + 1) * 32); else rs.sweep(rb, n0 + (c + 1) * 32, thr);
         }
       }
     }
@@ -703,15 +748,21 @@ struct RerankParams {
   int32_t* stats;
   int out_ld, out_off;          // the row's K results go to out[t * out_ld + out_off ..]  (rounds: a slice of the caller's [T, K])
   int mask_by_row;              // rounds: the mask CSR is indexed by the query row
+  int cap;                      // shared-memory entries (power of two >= S * TC_CAP)
   int count_overflow;           // add the rows left to the exact kernel to stats[0] (rounds count them once, from the sticky flags)
 };
 
 __device__ __forceinline__ bool rr_before(double va, int ia, double vb, int ib) { return va > vb || (va == vb && ia < ib); }
 
+// Dynamic shared memory: [cap] fp64 scores | [512] fp64 query row | [cap] item ids, cap = the power of two >= S_cand * TC_CAP
+// (<= RR_CAP).  With one split per row (every call with >= 148 * 256 query rows) that is 10 KB instead of 28: sixteen blocks of
+// 128 threads per SM instead of eight of 256 -- a row's re-rank is a chain of short latency-bound phases (gather, score, ~30
+// barriers of sort), so rows in flight are what its throughput hangs on.
 __global__ void __launch_bounds__(256) k_rerank(const __grid_constant__ RerankParams P) {
-  __shared__ double s_val[RR_CAP];
-  __shared__ int s_idx[RR_CAP];
-  __shared__ __align__(16) double s_u[512];   // the query row, widened once (fp32 -> fp64 conversions run at a quarter of the FMA rate)
+  extern __shared__ __align__(16) uint8_t rr_smem[];
+  double* s_val = reinterpret_cast<double*>(rr_smem);
+  double* s_u = s_val + P.cap;                // the query row, widened once (fp32 -> fp64 conversions run at a quarter of the FMA rate)
+  int* s_idx = reinterpret_cast<int*>(s_u + 512);
   for (int t = blockIdx.x; t < P.T; t += gridDim.x) {
     if (P.overflow[t]) {            // recomputed by the exact streaming kernel
       if (P.stats && P.count_overflow && threadIdx.x == 0) atomicAdd(P.stats, 1);
@@ -1098,13 +1149,25 @@ extern "C" int cf_topk_tc(const cf_topk_args* a, void* workspace, int64_t worksp
   P.users = a->users; P.tr_indptr = (const long long*)a->train.indptr; P.tr_indices = a->train.indices;
   P.eps2 = eps2; P.cand = cand; P.cand_cnt = ccnt; P.overflow = ovf;
   P.dbg_scores = dbg_scores; P.dbg_ld = (long long)align_up((size_t)a->n_items, TC_NW);   // the same stride for both kernels
+  {   // threshold warm-up (RowSweep::sweep_warm): at most TC_CAP chunk maxima per buffer, at most an eighth of the split
+    const int tiles_per_split = (P.n_tiles + p.S - 1) / p.S;
+    int warm = TC_CAP / (p.NB / 32);
+    if (warm > tiles_per_split / 8) warm = tiles_per_split / 8;
+    if (const char* e = getenv("CF_TC_WARM")) warm = atoi(e) < warm ? atoi(e) : warm;   // tuning knob (0 = off)
+    P.warm = (p.pair || warm < 0) ? 0 : warm;
+  }
   RerankParams R = {};
   R.U = a->U; R.V = a->V; R.b = a->b; R.ld = a->ld; R.nvec = a->ld / 4; R.kind = a->kind; R.T = a->T; R.S = p.S_cand;
   R.users = a->users; R.cand = cand; R.n_items = (int)a->n_items; R.cand_cnt = ccnt; R.overflow = ovf;
   R.tr_indptr = P.tr_indptr; R.tr_indices = P.tr_indices;
   R.out_idx = a->out_idx; R.out_val = a->out_val; R.stats = stats; R.out_ld = a->K; R.count_overflow = p.rounds == 1;
+  int rr_cap = 512;
+  while (rr_cap < p.S_cand * TC_CAP) rr_cap <<= 1;
+  R.cap = rr_cap;
+  const int rr_threads = rr_cap <= 512 ? 128 : 256;
+  const size_t rr_smem = (size_t)rr_cap * 12 + 512 * 8;
   int rg = a->T;
-  if (rg > sms * 8) rg = sms * 8;
+  if (rg > sms * 16) rg = sms * 16;
 
   MaskParams M = {};
   int32_t* sticky = nullptr;
@@ -1147,7 +1210,7 @@ extern "C" int cf_topk_tc(const cf_topk_args* a, void* workspace, int64_t worksp
     }
     CF_CUDA_OK(cudaGetLastError());
     R.K = Kr; R.out_off = r * TC_KMAX;
-    k_rerank<<<rg, 256, 0, stream>>>(R);
+    k_rerank<<<rg, rr_threads, rr_smem, stream>>>(R);
     CF_CUDA_OK(cudaGetLastError());
     if (p.rounds > 1) {
       int sg = (a->T + 255) / 256;
