@@ -59,6 +59,7 @@ struct TcParams {
   long long dbg_ld;
   int mask_by_row;                 // rounds (K > TC_KMAX): the mask CSR is indexed by the query row, not by the user id
   int warm;                        // warm-up tiles per split (k_topk_tc; see RowSweep::sweep_warm)
+  int coop, coop_low;              // cooperative compactions (k_topk_tc): on / rows above this many entries join
 };
 
 using namespace tc;
@@ -312,6 +313,7 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
   uint64_t* tfull = a_full + 1;                // [2]
   uint64_t* tempty = tfull + 2;                // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  volatile int* s_coop = reinterpret_cast<volatile int*>(tmem_slot + 1);   // tile (+1) of the latest forced compaction in this CTA
 
   const int row0 = blockIdx.x * (TC_MT * TC_M);
   const int split = blockIdx.y;
@@ -332,6 +334,7 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
       mbar_init(tfull + s, 1);
       mbar_init(tempty + s, (WIDE ? 4 : 8) * 32);
     }
+    *s_coop = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -424,6 +427,13 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
     // with instruction-fetch stalls on top.  Now: ONE room check per 128 columns (a block appends at most 128 entries per
     // row), per chunk 18 instructions unless it holds a hit (RowSweep::sweep).
     const bool dbg = P.dbg_scores != nullptr;
+    // Cooperative compactions.  A warp that compacts does not drain its quadrant of the accumulator, and one tile later the MMA
+    // pipeline -- the whole CTA -- waits for it: compactions scattered over the eight epilogue warps stall the CTA for the SUM of
+    // their durations (on a 500 k-item catalogue at K = 100: ~3 per row, ~2 us each, 8 warps x 32 rows = a fifth of the sweep).
+    // So a warp that MUST compact (a row above CAP - 128) announces it in shared memory, and every warp that sees the
+    // announcement compacts, within a tile, all of its rows above a lower mark: the warps stall together instead of in turn.
+    int coop_seen = 0;
+    const int coop_low = P.coop_low;
     for (int t = 0; t < ntt; ++t) {
       const int acc = WIDE ? mt : (t & 1);
       const bool warm = t < wt;
@@ -434,7 +444,20 @@ k_topk_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUten
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(WIDE ? mt * NB : acc * (TC_MT * TC_N) + mt * TC_N);
 #pragma unroll 1
       for (int hb = 0; hb < NB / 128; ++hb) {
-        if (!warm) rs.compact(__ballot_sync(0xffffffffu, rs.cnt > TC_CAP - 128), lane, P);   // make room for the next 128 columns
+        if (!warm) {   // make room for the next 128 columns
+          unsigned need = __ballot_sync(0xffffffffu, rs.cnt > TC_CAP - 128);
+          int f = *s_coop;
+          if (need) {
+            if (lane == 0) *s_coop = t + 1;
+            f = t + 1;
+          }
+          f = __shfl_sync(0xffffffffu, f, 0);
+          if (f > coop_seen && P.coop) {
+            coop_seen = f;
+            need = __ballot_sync(0xffffffffu, rs.valid && !rs.overflowed && rs.cnt > coop_low);
+          }
+          rs.compact(need, lane, P);
+        }
         const float thr = rs.theta - rs.eps2;   // (theta only moves at a compaction)
         // software-pipelined TMEM reads: the load of chunk c + 1 is in flight while chunk c is swept
         uint32_t ra[32], rb[32];
@@ -1155,6 +1178,10 @@ extern "C" int cf_topk_tc(const cf_topk_args* a, void* workspace, int64_t worksp
     if (warm > tiles_per_split / 8) warm = tiles_per_split / 8;
     if (const char* e = getenv("CF_TC_WARM")) warm = atoi(e) < warm ? atoi(e) : warm;   // tuning knob (0 = off)
     P.warm = (p.pair || warm < 0) ? 0 : warm;
+    P.coop = 1;
+    if (const char* e = getenv("CF_TC_COOP")) P.coop = atoi(e) > 0;   // tuning knobs
+    P.coop_low = 0;                                                   // (0: chosen per round from its K, below)
+    if (const char* e = getenv("CF_TC_COOP_LOW")) P.coop_low = atoi(e);
   }
   RerankParams R = {};
   R.U = a->U; R.V = a->V; R.b = a->b; R.ld = a->ld; R.nvec = a->ld / 4; R.kind = a->kind; R.T = a->T; R.S = p.S_cand;
@@ -1182,6 +1209,7 @@ extern "C" int cf_topk_tc(const cf_topk_args* a, void* workspace, int64_t worksp
     k_mask_scan<<<1, 1024, 0, stream>>>(M);
     CF_CUDA_OK(cudaGetLastError());
   }
+  const int coop_low_env = P.coop_low;
   for (int r = 0; r < p.rounds; ++r) {
     const int Kr = a->K - r * TC_KMAX < TC_KMAX ? a->K - r * TC_KMAX : TC_KMAX;
     if (r > 0) {
@@ -1196,6 +1224,7 @@ extern "C" int cf_topk_tc(const cf_topk_args* a, void* workspace, int64_t worksp
       R.tr_indptr = M.indptr2; R.tr_indices = M.ind2; R.mask_by_row = 1;
     }
     P.K = Kr;
+    if (coop_low_env <= 0) P.coop_low = (Kr + 16 + TC_CAP - 128) / 2;   // half way between a compacted row and a full one
     dim3 grid((unsigned)(p.T_pad / (TC_MT * TC_M)), (unsigned)p.S);
     if (p.pair) {
       grid.x *= 2;     // clusters of two CTAs, 128 query rows each
