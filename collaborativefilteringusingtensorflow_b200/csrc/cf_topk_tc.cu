@@ -288,7 +288,7 @@ struct RowSweep {
   __device__ __forceinline__ void finish(const TcParams& P, int row, long long buffer, int lane) {
     compact(__ballot_sync(0xffffffffu, valid && !overflowed && cnt > P.K + 16), lane, P);
     if (valid) {
-      P.cand_cnt[buffer] = cnt;
+      P.cand_cnt[buffer] = cnt | (ver << 16);   // (entries below ver are known not to be training items)
       if (overflowed) P.overflow[row] = 1;
     }
   }
@@ -783,9 +783,9 @@ __device__ __forceinline__ bool rr_before(double va, int ia, double vb, int ib) 
 // barriers of sort), so rows in flight are what its throughput hangs on.
 __global__ void __launch_bounds__(256) k_rerank(const __grid_constant__ RerankParams P) {
   extern __shared__ __align__(16) uint8_t rr_smem[];
-  double* s_val = reinterpret_cast<double*>(rr_smem);
-  double* s_u = s_val + P.cap;                // the query row, widened once (fp32 -> fp64 conversions run at a quarter of the FMA rate)
-  int* s_idx = reinterpret_cast<int*>(s_u + 512);
+  double* s_u = reinterpret_cast<double*>(rr_smem);   // the query row, widened once (fp32 -> fp64 conversions run at a quarter of the FMA rate)
+  double* s_val = s_u + 512;
+  int* s_idx = reinterpret_cast<int*>(s_val + P.cap);
   for (int t = blockIdx.x; t < P.T; t += gridDim.x) {
     if (P.overflow[t]) {            // recomputed by the exact streaming kernel
       if (P.stats && P.count_overflow && threadIdx.x == 0) atomicAdd(P.stats, 1);
@@ -796,50 +796,75 @@ __global__ void __launch_bounds__(256) k_rerank(const __grid_constant__ RerankPa
     for (int k = threadIdx.x; k < P.ld; k += blockDim.x) s_u[k] = (double)P.U[u * P.ld + k];
     const long long tlo = P.tr_indptr ? P.tr_indptr[mrow] : 0, thi = P.tr_indptr ? P.tr_indptr[mrow + 1] : 0;
     int total = 0;
-    for (int s = 0; s < P.S; ++s) total += P.cand_cnt[(long long)t * P.S + s];
+    for (int s = 0; s < P.S; ++s) total += P.cand_cnt[(long long)t * P.S + s] & 0xffff;
     int n2 = 32;
     while (n2 < total) n2 <<= 1;
     if (P.stats && threadIdx.x == 0) atomicAdd(P.stats + 1, total);
     __syncthreads();
-    // gather + exact score
+    // gather + exact score.  The kernel is bound by shared-memory instructions (ncu: mio_throttle + short_scoreboard = 29 of 45
+    // stall cycles per issue): every candidate re-reads the whole query row.  So a thread scores TWO candidates (e and e + half)
+    // per pass over the row, with 16-byte shared loads; each candidate's own sum keeps its sequential-k order (bit-identical
+    // to k_topk_exact).  Entries below `ver` were checked against the training row by the sweep's last compaction.
     int base = 0;
     for (int s = 0; s < P.S; ++s) {
-      const int c = P.cand_cnt[(long long)t * P.S + s];
+      const int packed = P.cand_cnt[(long long)t * P.S + s];
+      const int c = packed & 0xffff, ver = packed >> 16;
       const uint2* ce = P.cand + ((long long)t * P.S + s) * TC_CAP;
-      for (int e = threadIdx.x; e < c; e += blockDim.x) {
-        const long long item = (long long)ce[e].y;
-        if (item >= P.n_items || csr_contains(P.tr_indices, tlo, thi, (int)item)) {   // a padding column / a training item: sorts behind every real candidate
-          s_val[base + e] = -INFINITY;
-          s_idx[base + e] = 0x7fffffff;
-          continue;
+      const int half = (c + 1) >> 1;
+      for (int e = threadIdx.x; e < half; e += blockDim.x) {
+        const int e1 = e + half;
+        long long item[2] = {(long long)ce[e].y, e1 < c ? (long long)ce[e1].y : (long long)P.n_items};
+        bool live[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int eh = h ? e1 : e;
+          live[h] = item[h] < P.n_items && !(eh >= ver && csr_contains(P.tr_indices, tlo, thi, (int)item[h]));
+          if (!live[h]) item[h] = 0;   // (a padding column / a training item: scored on row 0 and discarded)
         }
-        const float4* vp = reinterpret_cast<const float4*>(P.V + item * P.ld);
-        double sc = 0.0;
+        const float4* vp0 = reinterpret_cast<const float4*>(P.V + item[0] * P.ld);
+        const float4* vp1 = reinterpret_cast<const float4*>(P.V + item[1] * P.ld);
+        double sc0 = 0.0, sc1 = 0.0;
         if (P.kind == CF_SCORE_NEG_SQDIST) {
-#pragma unroll 8
+#pragma unroll 4
           for (int k4 = 0; k4 < P.nvec; ++k4) {
-            const float4 v = __ldg(vp + k4);
-            const double* q = s_u + 4 * k4;
-            double df = q[0] - (double)v.x; sc = __dadd_rn(sc, __dmul_rn(df, df));
-            df = q[1] - (double)v.y; sc = __dadd_rn(sc, __dmul_rn(df, df));
-            df = q[2] - (double)v.z; sc = __dadd_rn(sc, __dmul_rn(df, df));
-            df = q[3] - (double)v.w; sc = __dadd_rn(sc, __dmul_rn(df, df));
+            const float4 v0 = __ldg(vp0 + k4), v1 = __ldg(vp1 + k4);
+            const double2 qa = *reinterpret_cast<const double2*>(s_u + 4 * k4), qb = *reinterpret_cast<const double2*>(s_u + 4 * k4 + 2);
+            double df = qa.x - (double)v0.x; sc0 = __dadd_rn(sc0, __dmul_rn(df, df));
+            df = qa.y - (double)v0.y; sc0 = __dadd_rn(sc0, __dmul_rn(df, df));
+            df = qb.x - (double)v0.z; sc0 = __dadd_rn(sc0, __dmul_rn(df, df));
+            df = qb.y - (double)v0.w; sc0 = __dadd_rn(sc0, __dmul_rn(df, df));
+            df = qa.x - (double)v1.x; sc1 = __dadd_rn(sc1, __dmul_rn(df, df));
+            df = qa.y - (double)v1.y; sc1 = __dadd_rn(sc1, __dmul_rn(df, df));
+            df = qb.x - (double)v1.z; sc1 = __dadd_rn(sc1, __dmul_rn(df, df));
+            df = qb.y - (double)v1.w; sc1 = __dadd_rn(sc1, __dmul_rn(df, df));
           }
-          sc = -sc;
+          sc0 = -sc0;
+          sc1 = -sc1;
         } else {
-#pragma unroll 8
+#pragma unroll 4
           for (int k4 = 0; k4 < P.nvec; ++k4) {
-            const float4 v = __ldg(vp + k4);
-            const double* q = s_u + 4 * k4;
-            sc = fma(q[0], (double)v.x, sc);
-            sc = fma(q[1], (double)v.y, sc);
-            sc = fma(q[2], (double)v.z, sc);
-            sc = fma(q[3], (double)v.w, sc);
+            const float4 v0 = __ldg(vp0 + k4), v1 = __ldg(vp1 + k4);
+            const double2 qa = *reinterpret_cast<const double2*>(s_u + 4 * k4), qb = *reinterpret_cast<const double2*>(s_u + 4 * k4 + 2);
+            sc0 = fma(qa.x, (double)v0.x, sc0);
+            sc0 = fma(qa.y, (double)v0.y, sc0);
+            sc0 = fma(qb.x, (double)v0.z, sc0);
+            sc0 = fma(qb.y, (double)v0.w, sc0);
+            sc1 = fma(qa.x, (double)v1.x, sc1);
+            sc1 = fma(qa.y, (double)v1.y, sc1);
+            sc1 = fma(qb.x, (double)v1.z, sc1);
+            sc1 = fma(qb.y, (double)v1.w, sc1);
           }
-          if (P.kind == CF_SCORE_DOT_BIAS) sc = __dadd_rn(sc, (double)__ldg(P.b + item));
+          if (P.kind == CF_SCORE_DOT_BIAS) {
+            sc0 = __dadd_rn(sc0, (double)__ldg(P.b + item[0]));
+            sc1 = __dadd_rn(sc1, (double)__ldg(P.b + item[1]));
+          }
         }
-        s_val[base + e] = sc;
-        s_idx[base + e] = (int)item;
+        s_val[base + e] = live[0] ? sc0 : -INFINITY;
+        s_idx[base + e] = live[0] ? (int)item[0] : 0x7fffffff;
+        if (e1 < c) {
+          s_val[base + e1] = live[1] ? sc1 : -INFINITY;
+          s_idx[base + e1] = live[1] ? (int)item[1] : 0x7fffffff;
+        }
       }
       base += c;
     }
