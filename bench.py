@@ -671,7 +671,7 @@ def main():
     ap.add_argument('--no-other-configs', action='store_true')
     ap.add_argument('--no-c5', action='store_true', help='N > 1: skip the configs[4] sub-run')
     ap.add_argument('--grow-catalogue', action='store_true', help='N > 1: n_items x N items in total instead of a fixed catalogue')
-    ap.add_argument('--item-transport', default='auto', choices=['nccl', 'peer', 'peer-push', 'fetch', 'auto'],
+    ap.add_argument('--item-transport', default='auto', choices=['nccl', 'peer', 'peer-push', 'fetch', 'replicate', 'auto'],
                     help='N > 1: how item rows reach the step (NCCL all-to-all of unique rows / NVLink peer reads in the kernel)')
     ap.add_argument('--phases', action='store_true', help='N > 1: also print the per-minibatch timeline to stderr')
     args = ap.parse_args()

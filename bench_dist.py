@@ -157,7 +157,9 @@ def step_line(B_, wl, args, world, K, Wm, r, n_items_global, tr, pk):
     achieved = bpp * B / (ms / K * 1e-3) / 1e9            # per GPU, whole sharded step (exchange included)
     nv_bytes = r['sent'] + r['pulled']
     return dict(value=units / (ms * 1e-3), unit='triple updates/s', ms_per_step=ms / K, steps=K, gpu_launches=r['launches'],
-                item_transport=(('device-side exchange over peer memory: ' +
+                item_transport=('item table replicated on every GPU (users stay sharded): item-row gradients red.added into a dense table by '
+                                'k_step, ONE NCCL all-reduce of that table, cf_apply_dense on every rank' if getattr(tr, '_replicate', False) else
+                                ('device-side exchange over peer memory: ' +
                                  ('item rows read per occurrence inside k_step and gradients red.added into the owners\' dense tables by the same kernel (pull + push)'
                                   if tr._push else 'item rows read per occurrence inside k_step (pull) + gradient rows read in place by the owners'
                                   if tr._pull else 'unique item rows gathered once by k_exchange_prepare (fetch) + gradient rows read in place by the owners'))
@@ -217,8 +219,10 @@ def run_distributed(args, rank, world, device):
         return
     units = world * B * wl['W'] * K
     cfg = B_.same_config(wl, args)
-    cfg['workload'] = wl['desc'] + ' -- users, interactions and minibatch PER GPU; %d items in total, row-sharded by item %% N; ' \
-                                   'users range-sharded; item rows and gradient rows exchanged per minibatch' % n_items_global
+    cfg['workload'] = wl['desc'] + ' -- users, interactions and minibatch PER GPU; %d items in total, row-sharded by item %% N ' \
+                                   '(the engines, evaluation and state); users range-sharded; per minibatch: %s' % (
+                                       n_items_global, 'dense item gradients all-reduced over per-GPU replicas of the item table'
+                                       if line['item_transport'].startswith('item table replicated') else 'item rows and gradient rows exchanged')
     cfg['batch_pairs_per_gpu'] = B
     out = dict(metric=B_.metric_name(wl['d']), value=line['value'], unit='triple updates/s', n_gpus=world, steps=K, warmup=Wm,
                ms_per_step=line['ms_per_step'], higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',

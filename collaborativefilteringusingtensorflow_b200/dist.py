@@ -154,12 +154,21 @@ class DistributedTrainer(object):
                the owner's dense gradient table over NVLink (both link directions busy at once).  Measured on configs[4]
                at 2 GPUs it LOSES (3.60 vs 3.31 ms per minibatch: the dense tables turn the L2-resident atomics of the
                compact buffer into DRAM read-modify-writes on both sides), so it is not what 'auto' picks.
+      'replicate'  for catalogues that are SMALL against the minibatch (configs[1]: 6.3 M item occurrences per GPU and
+               minibatch over 500 k items -- every rank requests almost every row every minibatch, so the row exchange moves
+               the whole table and its gradients anyway, plus dedupe, routing, two barriers and an owner-side scatter): every
+               rank keeps a replica of the whole item table (built once from the shards, laid out shard after shard; the
+               engine's own table becomes a view of its block), the fused step red.adds item-row gradients into a dense table
+               of the same layout, ONE NCCL reduce-scatter hands every rank the summed gradients of its shard,
+               `cf_apply_dense` applies them there (the accumulators stay sharded) and ONE all-gather spreads the updated rows.
+               Users stay sharded.  Measured on configs[1] at 8 GPUs with an all-reduce + full apply on every rank: 13.4 G triple
+               updates/s against 11.4 G for the row exchange.  'auto' takes it when B * (1 + W) >= 2 * n_items_global.
       'nccl'   the first version, kept as the portable baseline: torch-op plan + three NCCL all-to-alls (ids, rows,
                gradients).  It is also what 'auto' falls back to, with a warning, when peer memory cannot be mapped."""
 
     def __init__(self, model, sampler, n_items_global, world, rank, group=None, item_transport='nccl'):
-        if item_transport not in ('nccl', 'peer', 'peer-push', 'fetch', 'auto'):
-            raise ValueError("item_transport must be 'nccl', 'peer', 'peer-push', 'fetch' or 'auto'")
+        if item_transport not in ('nccl', 'peer', 'peer-push', 'fetch', 'auto', 'replicate'):
+            raise ValueError("item_transport must be 'nccl', 'peer', 'peer-push', 'fetch', 'replicate' or 'auto'")
         self.torch = _lib.require_cuda()
         self.lib = _lib.lib()
         self.model, self.eng, self.sampler = model, model.engine, sampler
@@ -190,13 +199,17 @@ class DistributedTrainer(object):
         self._dev = None              # buffers of the device-side exchange (allocated on the first minibatch)
         self._k = 0
         self._bar = None              # preallocated 1-element tensor of the named cross-GPU barrier
-        self.device_side = item_transport != 'nccl'
+        self._replicate = True if item_transport == 'replicate' else None if item_transport == 'auto' else False
+        self._rep = None              # 'replicate': the item-table replica, its accumulators and the dense gradient table
+        self.device_side = item_transport not in ('nccl', 'replicate')
+        n_neg = getattr(sampler, 'n_neg', None)
+        if n_neg is not None and self._use_replica(int(sampler.batch_size), int(n_neg)):
+            self.device_side = False
         if self.device_side:
             if self.world > _lib.MAX_PEERS:
                 raise ValueError('the device-side exchange supports up to %d GPUs on one node' % _lib.MAX_PEERS)
             self._pull = {'peer': True, 'peer-push': True, 'fetch': False, 'auto': None}[item_transport]
             self._push = item_transport == 'peer-push'
-            n_neg = getattr(sampler, 'n_neg', None)
             if n_neg is not None:     # otherwise the buffers are shared on the first minibatch
                 self._setup_or_fall_back(int(sampler.batch_size), int(n_neg))
 
@@ -418,11 +431,93 @@ class DistributedTrainer(object):
         B = int(batch_size)
         if int(pairs.shape[0]) != B:
             raise ValueError('the sharded step takes one minibatch per call')
+        if self._use_replica(B, int(negs.shape[1])):
+            return self._step_chunk_replica(pairs, negs, B, want_loss)
         if self.device_side and self._dev is None:
             self._setup_or_fall_back(B, int(negs.shape[1]))
         if self.device_side:
             return self._step_chunk_device(pairs, negs, B, want_loss, routed, after_prepare)
         return self._step_chunk_nccl(pairs, negs, B, want_loss, plan)
+
+    # ------------------------------------------------------------------ 'replicate': item table replicated, dense gradients all-reduced
+    def _use_replica(self, B, W):
+        """'auto' decides from sizes alone (so every rank decides alike, without a collective): the replica wins when a
+        rank's minibatch holds at least twice as many item occurrences as the catalogue has rows."""
+        if self._replicate is None:
+            self._replicate = self.world > 1 and B * (1 + W) >= 2 * self.n_items_global
+            if self._replicate:
+                self.device_side = False
+        return self._replicate
+
+    def _setup_replica(self):
+        """Builds the replica from the shards (collective, once).  Layout: the P shards one after the other (item i sits at
+        row (i % P) * L + i // P, L = ceil(n_items / P)), so that a rank's shard is one contiguous block -- the unit of the
+        reduce-scatter and of the all-gather -- and the engine's own item table becomes a VIEW of that block: evaluation and
+        state_dict() read current rows without any copy."""
+        torch, eng, P = self.torch, self.eng, self.world
+        L = (self.n_items_global + P - 1) // P
+        if P == 1:
+            V = eng.V
+        else:
+            V = torch.zeros(P * L, eng.ld, device=eng.device)
+            V[self.rank * L:self.rank * L + eng.n_items].copy_(eng.V)
+            self.ex.dist.all_gather_into_tensor(V, V[self.rank * L:(self.rank + 1) * L], group=self.ex.group)
+            eng.V = V[self.rank * L:self.rank * L + eng.n_items]
+        self._rep = dict(V=V, L=L, g=torch.zeros(P * L, eng.ld, device=eng.device),
+                         gblk=torch.zeros(L, eng.ld, device=eng.device) if P > 1 else None)
+
+    def _replica_rows(self, ids):
+        """global item id -> row of the replica"""
+        P = self.world
+        if P == 1:
+            return ids
+        q = ids // P
+        return (ids - q * P) * self._rep['L'] + q
+
+    def _step_chunk_replica(self, pairs, negs, B, want_loss):
+        torch, eng, P = self.torch, self.eng, self.world
+        if self._rep is None:
+            self._setup_replica()
+        rep = self._rep
+        L = rep['L']
+        pairs, negs = eng._as_i32(pairs), eng._as_i32(negs)
+        W = int(negs.shape[1])
+        stream = torch.cuda.current_stream(eng.device).cuda_stream
+        ev = self._tick('', None)
+        if P > 1:
+            pairs = torch.stack([pairs[:, 0], self._replica_rows(pairs[:, 1])], 1).contiguous()
+            negs = self._replica_rows(negs).contiguous()
+        a, loss = self._step_args(B, W, want_loss)
+        # the fused step in exchange mode: user rows are counted / staged / applied locally, every item-row gradient is
+        # red.added into the dense table (row = the item's row in the replica)
+        a.V, a.n_items = _lib.ptr(rep['V']), P * L
+        a.pairs, a.negs, a.gradV = _lib.ptr(pairs), _lib.ptr(negs), _lib.ptr(rep['g'])
+        _lib.check(self.lib.cf_train_steps(a, stream), 'cf_train_steps')
+        ev = self._tick('k_count + k_step + k_apply_staged', ev)
+        g_mine = rep['g']
+        if P > 1:       # every rank receives the summed gradients of ITS shard
+            self.ex.dist.reduce_scatter_tensor(rep['gblk'], rep['g'], group=self.ex.group)
+            g_mine = rep['gblk']
+        ev = self._tick('reduce-scatter of the dense item gradients (NCCL)', ev)
+        ap = _lib.ApplyArgs()
+        ap.table, ap.acc, ap.n_rows, ap.d, ap.ld = _lib.ptr(eng.V), _lib.ptr(eng.accV), eng.n_items, eng.d, eng.ld
+        ap.grads, ap.ldg = _lib.ptr(g_mine), eng.ld
+        ap.model, ap.optimizer = eng.model_id, 0 if eng.optimizer == 'adagrad' else 1
+        ap.lr, ap.clip_norm = eng.hyper['lr'], eng.hyper['clip_norm']
+        _lib.check(self.lib.cf_apply_dense(ap, stream), 'cf_apply_dense')      # applies the touched rows (and re-zeroes their gradients)
+        if eng._needs_full_clip:
+            # cml.py:119-129: step first, THEN the whole-table clip (engine.train_batches; DESIGN.md section 5): this rank's
+            # users and its item shard -- the all-gather below spreads the clipped rows
+            eng._full_clip(stream)
+        ev = self._tick('owner apply (k_apply_dense on the shard)', ev)
+        if P > 1:
+            self.ex.dist.all_gather_into_tensor(rep['V'], rep['V'][self.rank * L:(self.rank + 1) * L], group=self.ex.group)
+            rep['g'].zero_()
+        ev = self._tick('all-gather of the updated item rows (NCCL) + zeroing of the gradient table', ev)
+        self.launches += 3 + 1
+        self.occurrences += B * (1 + W)
+        self.bytes_sent += int(2 * (P - 1) * L * eng.ld * 4)   # reduce-scatter + all-gather volume per rank
+        return loss
 
     def _step_chunk_device(self, pairs, negs, B, want_loss, routed, after_prepare):
         torch, eng, d = self.torch, self.eng, self._dev
@@ -541,6 +636,15 @@ class DistributedTrainer(object):
         B = self.sampler.batch_size
         chunk = self.sampler.next_chunk(n_minibatches)
         main = torch.cuda.current_stream(self.eng.device)
+        if self._use_replica(B, int(chunk[1].shape[1])):
+            out = []
+            for k in range(n_minibatches):
+                out.append(self._step_chunk_replica(chunk[0][k * B:(k + 1) * B], chunk[1][k * B:(k + 1) * B], B, want_loss))
+                if self.step_events is not None:
+                    ev = torch.cuda.Event(enable_timing=True)
+                    ev.record(main)
+                    self.step_events.append(ev)
+            return torch.cat(out) if want_loss else None
         overlap = self.phase_ms is None and self.world > 1
 
         def batch(k):
@@ -665,6 +769,18 @@ def distributed_topk(engine, query_rows, K, train_local_csr, world, rank, group=
     lo = rank * c
     n_mine = max(0, min(T, lo + c) - lo)
     return lo, out_i[:n_mine], out_v[:n_mine]
+
+
+def _gather_item_rows(t, n_items_global, world, group=None):
+    """Row-sharded [rows of item % P == rank, ...] tensors of every rank -> the full tensor in item order (collective)."""
+    torch = _lib.require_cuda()
+    import torch.distributed as dist
+    P = int(world)
+    L = (int(n_items_global) + P - 1) // P
+    send = t if t.shape[0] == L else torch.cat([t, torch.zeros((L - t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)])
+    got = torch.empty((P, L) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(got, send.contiguous(), group=group)
+    return got.transpose(0, 1).reshape((L * P,) + tuple(t.shape[1:]))[:n_items_global].contiguous()   # item l * P + p sits at [p][l]
 
 
 def gather_item_table(engine, n_items_global, world, rank, group=None):

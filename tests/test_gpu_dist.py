@@ -10,7 +10,7 @@ def _state(m):
     return {k: v.cpu().numpy() for k, v in m.state_dict().items()}
 
 
-@pytest.mark.parametrize('transport', ['nccl', 'peer', 'peer-push', 'fetch', 'auto'])
+@pytest.mark.parametrize('transport', ['nccl', 'peer', 'peer-push', 'fetch', 'auto', 'replicate'])
 @pytest.mark.parametrize('kind', ['bpr', 'cml'])
 def test_exchange_mode_world1_equals_fused_step(kind, transport):
     import torch
