@@ -158,7 +158,8 @@ def step_line(B_, wl, args, world, K, Wm, r, n_items_global, tr, pk):
     nv_bytes = r['sent'] + r['pulled']
     return dict(value=units / (ms * 1e-3), unit='triple updates/s', ms_per_step=ms / K, steps=K, gpu_launches=r['launches'],
                 item_transport=('item table replicated on every GPU (users stay sharded): item-row gradients red.added into a dense table by '
-                                'k_step, ONE NCCL all-reduce of that table, cf_apply_dense on every rank' if getattr(tr, '_replicate', False) else
+                                'k_step, one NCCL reduce-scatter, cf_apply_dense on the owner\'s shard, one all-gather of the updated rows'
+                                if getattr(tr, '_replicate', False) else
                                 ('device-side exchange over peer memory: ' +
                                  ('item rows read per occurrence inside k_step and gradients red.added into the owners\' dense tables by the same kernel (pull + push)'
                                   if tr._push else 'item rows read per occurrence inside k_step (pull) + gradient rows read in place by the owners'
@@ -218,15 +219,14 @@ def run_distributed(args, rank, world, device):
     if rank != 0:
         return
     units = world * B * wl['W'] * K
-    cfg = B_.same_config(wl, args)
-    cfg['workload'] = wl['desc'] + ' -- users, interactions and minibatch PER GPU; %d items in total, row-sharded by item %% N ' \
-                                   '(the engines, evaluation and state); users range-sharded; per minibatch: %s' % (
-                                       n_items_global, 'dense item gradients all-reduced over per-GPU replicas of the item table'
-                                       if line['item_transport'].startswith('item table replicated') else 'item rows and gradient rows exchanged')
-    cfg['batch_pairs_per_gpu'] = B
+    cfg = B_.same_config(wl, args)          # the same `config` object as the N = 1 line and the reference arm print
+    sharding = ('users, interactions and minibatch PER GPU (weak scaling, batch_pairs per GPU = %d); %d items in total, row-sharded by item %% N '
+                '(the engines, evaluation and state); users range-sharded; per minibatch: %s' % (
+                    B, n_items_global, 'dense item gradients reduce-scattered over per-GPU replicas of the item table'
+                    if line['item_transport'].startswith('item table replicated') else 'item rows and gradient rows exchanged'))
     out = dict(metric=B_.metric_name(wl['d']), value=line['value'], unit='triple updates/s', n_gpus=world, steps=K, warmup=Wm,
                ms_per_step=line['ms_per_step'], higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
-               data='synthetic', config=cfg, gpu_launches=line['gpu_launches'], item_transport=line['item_transport'],
+               data='synthetic', config=cfg, sharding=sharding, gpu_launches=line['gpu_launches'], item_transport=line['item_transport'],
                e2e=dict(value=units / (r['e2e_ms'] * 1e-3), unit='triple updates/s', ms_per_step=r['e2e_ms'] / K,
                         h2d_bytes_per_step=r['h2d'], d2h_bytes_per_step=8),
                roofline=line['roofline'], nvlink=line['nvlink'], phases_ms_per_step=line['phases_ms_per_step'], topk=topk, c5=c5,
