@@ -532,6 +532,10 @@ def run_ours(args):
         wb = WORKLOADS['c2-bpr'] if args.workload == 'c2' else dict(wl, model='bpr', W=1, G=0, hyper=dict(reg=0.1, lr=0.1), desc='BPRMF on the same shape, W=1')
         mb, sb, tb = time_training(wb, csr, B, Ko, Wm, device, args.optimizer, args.update, pk)
         mse, h2db, _ = time_e2e(mb, sb, B, Ko, device)
+        if args.workload == 'c2':
+            tb['roofline']['traffic'], tsrc_b = measured_traffic('c2-bpr', B, args.optimizer, args.update)
+            if tsrc_b:
+                tb['roofline']['traffic_source'] = tsrc_b
         other['bpr_w1'] = dict(workload=wb['desc'], value=tb['units'] / (tb['ms'] * 1e-3), unit='triple updates/s', steps=Ko,
                                ms_per_step=tb['ms'] / Ko, batch_pairs=B, roofline=tb['roofline'],
                                e2e=dict(value=tb['units'] / (mse * 1e-3), unit='triple updates/s', ms_per_step=mse / Ko,
@@ -544,6 +548,9 @@ def run_ours(args):
             csr3 = synth_interactions(w3['n_users'], w3['n_items'], w3['nnz'], SEED, device)
             m3, s3, t3 = time_training(w3, csr3, B, Ko, Wm, device, args.optimizer, args.update, pk)
             t3['roofline']['note'] = 'tables + accumulators are 42 MB x 2: L2-resident, the HBM fraction is not a DRAM claim'
+            t3['roofline']['traffic'], tsrc_3 = measured_traffic('c3', B, args.optimizer, args.update)
+            if tsrc_3:
+                t3['roofline']['traffic_source'] = tsrc_3
             other['c3_gbpr'] = dict(workload=w3['desc'], value=t3['units'] / (t3['ms'] * 1e-3), unit='triple updates/s (pairs x W)',
                                     steps=Ko, ms_per_step=t3['ms'] / Ko, batch_pairs=B, nnz=csr3.nnz, roofline=t3['roofline'],
                                     loss_first_last=[float(t3['losses'][0]), float(t3['losses'][-1])])

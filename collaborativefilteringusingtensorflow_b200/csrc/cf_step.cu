@@ -146,7 +146,7 @@ step_kernel_t pick_kernel(int model, int nvec, int* lpg, bool ext) {
 
 
 cfstep::step_kernel_t cf_pick_apply_kernel(int nvec) { return pick_apply(nvec); }   // used by cf_exchange.cu
-cfstep::step_kernel_t cf_step_pick_fast(int model, int W, int G, int lpg, int* nbuf, int* slots);   // cf_step_fast.cu
+cfstep::step_kernel_t cf_step_pick_fast(int model, int W, int G, int lpg, int* nbuf, int* slots, int* threads);   // cf_step_fast.cu
 
 extern "C" int64_t cf_step_staging_rows(int32_t model, int32_t B, int32_t W, int32_t G) {
   const int64_t R = (model == CF_MODEL_WRMF) ? 2 : 2 + (int64_t)W + G;
@@ -244,23 +244,25 @@ static int train_steps_impl(const cf_step_args* a, cudaStream_t stream, cudaEven
   CF_CHECK_ARG((2 + T) * slot_bytes <= budget1, "cf_train_steps: rows too wide for the shared-memory staging (ld=%d)", a->ld);
   P.T = T;
   size_t smem = (size_t)((2 + T) * slot_bytes);
+  int threads = 256;
   // one negative per pair (BPRMF's reference setting) / GBPR with 5 negatives and a group of 3 or 1, rows of 36..128 floats,
   // single GPU, SYNC: the unrolled, software-pipelined form of the same arithmetic (cf_step_fast.cu).  CF_STEP_GENERIC=1
   // keeps the generic kernel (tests compare the two).
   const char* genv = getenv("CF_STEP_GENERIC");
   const bool generic_only = genv && atoi(genv) > 0;
   if (!generic_only && a->update == CF_UPDATE_SYNC && !a->gradV && !a->gradU && a->n_peers == 0 && P.nvec > 8 && P.nvec <= 32) {
-    int nbuf = 0, slots = 0;
-    if (step_kernel_t fast = cf_step_pick_fast(a->model, W, G, lpg, &nbuf, &slots)) {
+    int nbuf = 0, slots = 0, thr = 256;
+    if (step_kernel_t fast = cf_step_pick_fast(a->model, W, G, lpg, &nbuf, &slots, &thr)) {
       kern = fast;
-      smem = (size_t)groups_per_block * nbuf * 2 * slots * a->ld * 4;
+      threads = thr;
+      smem = (size_t)(threads / lpg) * nbuf * 2 * slots * a->ld * 4;
     }
   }
   CF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
-  CF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+  CF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
   if (occ < 1) occ = 1;
-  long long grid = (a->B + groups_per_block - 1) / groups_per_block;
+  long long grid = (a->B + (threads / lpg) - 1) / (threads / lpg);
   const long long cap = (long long)sms * occ;
   if (grid > cap) grid = cap;
   step_kernel_t kapply = pick_apply(P.nvec);
@@ -282,7 +284,7 @@ static int train_steps_impl(const cf_step_args* a, cudaStream_t stream, cudaEven
     const bool all_ext = a->gradU && a->gradV;   // nothing is applied locally: no occurrence counts, no staged rows
     if (a->update == CF_UPDATE_SYNC && !all_ext) k_count<<<(unsigned)cgrid, 256, 0, stream>>>(P);
     if (ev) CF_CUDA_OK(cudaEventRecord(ev[4 * nb + 1], stream));
-    kern<<<(unsigned)grid, 256, smem, stream>>>(P);
+    kern<<<(unsigned)grid, threads, smem, stream>>>(P);
     if (a->event_after_step && nb == a->n_batches - 1) CF_CUDA_OK(cudaEventRecord((cudaEvent_t)a->event_after_step, stream));
     if (ev) CF_CUDA_OK(cudaEventRecord(ev[4 * nb + 2], stream));
     if (a->update == CF_UPDATE_SYNC && !all_ext) kapply<<<(unsigned)agrid, 256, 0, stream>>>(P);

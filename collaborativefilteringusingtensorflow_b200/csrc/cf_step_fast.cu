@@ -17,6 +17,7 @@
 // buffers at 2 blocks per SM, generic 1.932 ms): with seven 512-byte rows per pair the generic kernel is bound by DRAM traffic,
 // not by issue rate, so it stays.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -30,8 +31,8 @@ __device__ __forceinline__ void cp_async_wait_pending() { asm volatile("cp.async
 
 // slots of a pair: 0 = user, 1 = positive item, 2 .. 2+W-1 = negatives, 2+W .. = group users (GBPR); lane s of the group keeps
 // slot s's row id, occurrence word, staging slot (and item bias)
-template <int MODEL, int W, int G, int LPG, int NBUF, int MINB>
-__global__ void __launch_bounds__(256, MINB) k_step_fast(const __grid_constant__ StepDev P) {
+template <int MODEL, int W, int G, int LPG, int NBUF, int MINB, int THREADS = 256>
+__global__ void __launch_bounds__(THREADS, MINB) k_step_fast(const __grid_constant__ StepDev P) {
   static_assert(MODEL == CF_MODEL_BPR || MODEL == CF_MODEL_CML || MODEL == CF_MODEL_GBPR, "BPR / CML / GBPR");
   static_assert(MODEL == CF_MODEL_GBPR || G == 0, "only GBPR has group users");
   constexpr int NS = 2 + W + G;
@@ -246,10 +247,11 @@ __global__ void __launch_bounds__(256, MINB) k_step_fast(const __grid_constant__
 }  // namespace cfstep
 
 // the specialised kernel for (model, W, G, lanes per pair), or NULL; *nbuf = shared-memory row buffers per group,
-// *slots = rows per buffer half
-cfstep::step_kernel_t cf_step_pick_fast(int model, int W, int G, int lpg, int* nbuf, int* slots) {
+// *slots = rows per buffer half, *threads = block size
+cfstep::step_kernel_t cf_step_pick_fast(int model, int W, int G, int lpg, int* nbuf, int* slots, int* threads) {
   using namespace cfstep;
   *slots = 2 + W + (model == CF_MODEL_GBPR ? G : 0);
+  *threads = 256;
   if (model == CF_MODEL_BPR && W == 1) {
     *nbuf = 2;
     return lpg == 32 ? k_step_fast<CF_MODEL_BPR, 1, 0, 32, 2, 4> : lpg == 16 ? k_step_fast<CF_MODEL_BPR, 1, 0, 16, 2, 4> : nullptr;
@@ -259,12 +261,19 @@ cfstep::step_kernel_t cf_step_pick_fast(int model, int W, int G, int lpg, int* n
     return lpg == 32 ? k_step_fast<CF_MODEL_CML, 1, 0, 32, 2, 4> : lpg == 16 ? k_step_fast<CF_MODEL_CML, 1, 0, 16, 2, 4> : nullptr;
   }
   if (model == CF_MODEL_GBPR && W == 5 && (G == 3 || G == 1)) {
-    // one row buffer per group, two blocks per SM.  Two buffers (one block of 16 groups per SM, the next pair's twenty rows in
-    // flight during the compute) were measured on configs[2]: 2.22 ms against 1.18 ms -- the tables are L2-resident there and
-    // the step lives on warps, not on bytes in flight.
+    // one row buffer per group.  Two buffers (one block of 16 groups per SM, the next pair's twenty rows in flight during the
+    // compute) were measured on configs[2]: 2.22 ms against 1.18 ms -- the tables are L2-resident there and the step lives on
+    // warps, not on bytes in flight (ncu of the 256-thread form: 16 warps per SM, "wait" and shared-memory dependencies lead the
+    // stalls).  Hence blocks of 128 threads at <= 102 registers: five blocks = 20 warps per SM.
     *nbuf = 1;
-    if (G == 3) return lpg == 32 ? k_step_fast<CF_MODEL_GBPR, 5, 3, 32, 1, 2> : lpg == 16 ? k_step_fast<CF_MODEL_GBPR, 5, 3, 16, 1, 2> : nullptr;
-    return lpg == 32 ? k_step_fast<CF_MODEL_GBPR, 5, 1, 32, 1, 2> : lpg == 16 ? k_step_fast<CF_MODEL_GBPR, 5, 1, 16, 1, 2> : nullptr;
+    *threads = 128;
+    if (const char* e = getenv("CF_STEP_FAST_T256")) if (atoi(e) > 0) *threads = 256;   // A/B knob
+    if (*threads == 256) {
+      if (G == 3) return lpg == 32 ? k_step_fast<CF_MODEL_GBPR, 5, 3, 32, 1, 2> : lpg == 16 ? k_step_fast<CF_MODEL_GBPR, 5, 3, 16, 1, 2> : nullptr;
+      return lpg == 32 ? k_step_fast<CF_MODEL_GBPR, 5, 1, 32, 1, 2> : lpg == 16 ? k_step_fast<CF_MODEL_GBPR, 5, 1, 16, 1, 2> : nullptr;
+    }
+    if (G == 3) return lpg == 32 ? k_step_fast<CF_MODEL_GBPR, 5, 3, 32, 1, 5, 128> : lpg == 16 ? k_step_fast<CF_MODEL_GBPR, 5, 3, 16, 1, 5, 128> : nullptr;
+    return lpg == 32 ? k_step_fast<CF_MODEL_GBPR, 5, 1, 32, 1, 5, 128> : lpg == 16 ? k_step_fast<CF_MODEL_GBPR, 5, 1, 16, 1, 5, 128> : nullptr;
   }
   return nullptr;
 }
