@@ -178,6 +178,53 @@ def step_line(B_, wl, args, world, K, Wm, r, n_items_global, tr, pk):
                 loss_first_last=[float(r['losses'][0]), float(r['losses'][-1])])
 
 
+def sharded_als(B_, cfg, rank, world, device, pk):
+    """BASELINE.json configs[3] at this N (ALS): one USER half-sweep of WRMF weighted ALS with the users
+    range-sharded -- every rank holds cfg['n_users'] users and cfg['nnz'] interactions of its own (weak scaling, as in the
+    training line), both factor tables replicated.  Per half-sweep: partial tcgen05 Gram of the rank's slice of the item
+    table -> all-reduce of the 128 x 128 Gram -> cf_als_solve_rows on the rank's users -> all-gather of the solved rows.
+    Device-timed between barriers, max over ranks."""
+    from collaborativefilteringusingtensorflow_b200 import WRMF
+    from collaborativefilteringusingtensorflow_b200.dist import DistributedALS
+    nu, ni, nnz, d = cfg['n_users'], cfg['n_items'], cfg['nnz'], cfg['d']
+    csr = B_.synth_interactions(nu, ni, nnz, B_.SEED + 31 * rank, device)
+    m = WRMF(world * nu, ni, weight=cfg['weight'], reg=cfg['reg'], n_factors=d, verbose=False, seed=1, solver='als', device=device)
+    eng = m.engine
+    eng.accU = eng.accV = None
+    torch.cuda.empty_cache()
+    als = DistributedALS(eng, csr, None)
+    als.half_sweep('users')                                   # warm-up (sizes the workspace, opens the communicators)
+    torch.cuda.synchronize()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    dist.barrier()
+    torch.cuda.synchronize()
+    e[0].record()
+    als.half_sweep('users')
+    e[1].record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    lo, hi = DistributedALS.row_range(world * nu, world, rank)
+    e[2].record()
+    eng.als_solve_rows(eng.U[lo:hi], eng.V, csr, als.G)       # the rank's solve alone (no Gram, no collectives)
+    e[3].record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e[0].elapsed_time(e[1]), e[2].elapsed_time(e[3])], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, solve_ms = float(t[0]), float(t[1])
+    nz = csr.nnz
+    out = dict(workload='configs[3] at %d GPUs: WRMF weighted ALS user half-sweep, %d users per GPU (%d in total, of 10M) x %d items, %d '
+                        'interactions per GPU, d=%d, weight %.1f, reg %.1f; users range-sharded, tables replicated' % (
+                            world, nu, world * nu, ni, nz, d, cfg['weight'], cfg['reg']),
+               value=world * nu / (ms * 1e-3), unit='rows solved/s', ms_per_half_sweep=ms, solve_only_ms=solve_ms,
+               exchange_ms=ms - solve_ms, nnz_per_gpu=nz,
+               all_gather_bytes_per_gpu=float(world * nu * d * 4),
+               note='half-sweep = partial Gram + all-reduce(64 KB) + local solve + all-gather of the solved rows (NCCL); '
+                    'solve_only_ms is the rank\'s cf_als_solve_rows alone, max over ranks')
+    del m, eng, csr, als
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_distributed(args, rank, world, device):
     import bench as B_
     wl = dict(B_.WORKLOADS[args.workload])
@@ -216,6 +263,9 @@ def run_distributed(args, rank, world, device):
         tr5.close()
         del m5, csr5, tr5
         torch.cuda.empty_cache()
+    als = None
+    if args.workload == 'c2' and not args.no_other_configs:
+        als = sharded_als(B_, B_.ALS_SLICE, rank, world, device, pk)
     if rank != 0:
         return
     units = world * B * wl['W'] * K
@@ -229,6 +279,6 @@ def run_distributed(args, rank, world, device):
                data='synthetic', config=cfg, sharding=sharding, gpu_launches=line['gpu_launches'], item_transport=line['item_transport'],
                e2e=dict(value=units / (r['e2e_ms'] * 1e-3), unit='triple updates/s', ms_per_step=r['e2e_ms'] / K,
                         h2d_bytes_per_step=r['h2d'], d2h_bytes_per_step=8),
-               roofline=line['roofline'], nvlink=line['nvlink'], phases_ms_per_step=line['phases_ms_per_step'], topk=topk, c5=c5,
+               roofline=line['roofline'], nvlink=line['nvlink'], phases_ms_per_step=line['phases_ms_per_step'], topk=topk, c5=c5, c4_als=als,
                cpu_baseline=None, clocks=clocks, loss_first_last=line['loss_first_last'])
     print(json.dumps(out))

@@ -218,13 +218,20 @@ class DistributedTrainer(object):
         """Named cross-GPU barrier ON THE COMPUTE STREAM: a 1-element NCCL all_reduce enqueued on the current stream
         completes only after every rank has enqueued it, i.e. after everything each rank enqueued before it.  The peer
         transports rely on that order (remote NVLink reads of mailboxes / item rows / gradient rows against the owners'
-        applies and the requesters' zeroing), so the process group must be NCCL -- gloo would synchronise the HOSTS and
-        not order the streams."""
+        applies and the requesters' zeroing), so the process group must be NCCL -- a gloo collective synchronises the
+        HOSTS and does not order the streams.  The one exception is opt-in (CF_DIST_HOST_BARRIER=1, set by the one-GPU
+        form of tests/dist_check.py, where NCCL cannot run): synchronise the device, then a host barrier -- every rank's
+        device work is complete before any rank goes on, which orders at least as much (and costs a pipeline drain)."""
         if self.world == 1:
             return
         dist = self.ex.dist
         if dist.get_backend(self.ex.group) != 'nccl':
-            raise RuntimeError('peer transport needs an NCCL process group (barrier "%s" orders CUDA streams)' % why)
+            import os
+            if os.environ.get('CF_DIST_HOST_BARRIER') != '1':
+                raise RuntimeError('peer transport needs an NCCL process group (barrier "%s" orders CUDA streams)' % why)
+            self.torch.cuda.synchronize()
+            dist.barrier(group=self.ex.group)
+            return
         if self._bar is None:
             self._bar = self.torch.zeros(1, device=self.eng.device)
         dist.all_reduce(self._bar, group=self.ex.group)
@@ -867,7 +874,8 @@ class DistributedALS(object):
     half-sweep solves are range-sharded (rank r solves rows [r * chunk, (r + 1) * chunk) with chunk = ceil(n / world)).
     Per half-sweep: partial Gram of the rank's slice of the FIXED side (tcgen05) -> all_reduce of the 128 x 128 Gram (64
     KB) -> solve the local rows (cf_als_solve_rows) -> all_gather of the solved rows.  ``engine`` holds the full U / V;
-    ``user_csr`` / ``item_csr`` are the CSRs of the rank's OWN row range (columns = global ids of the other side)."""
+    ``user_csr`` / ``item_csr`` are the CSRs of the rank's OWN row range (columns = global ids of the other side); one of
+    them may be None when only the other side's half-sweep is run (half_sweep of the missing side raises)."""
 
     def __init__(self, engine, user_csr, item_csr, group=None):
         self.torch = _lib.require_cuda()
@@ -877,7 +885,7 @@ class DistributedALS(object):
         self.G = self.torch.zeros(128, 128, device=engine.device)
         for side, n in (('users', engine.n_users), ('items', engine.n_items)):
             lo, hi = self.row_range(n, self.world, self.rank)
-            if self.csr[side].shape[0] != hi - lo:
+            if self.csr[side] is not None and self.csr[side].shape[0] != hi - lo:
                 raise ValueError('%s CSR must hold rows [%d, %d) of this rank' % (side, lo, hi))
 
     @staticmethod
@@ -888,6 +896,8 @@ class DistributedALS(object):
     def half_sweep(self, side):
         torch, eng = self.torch, self.eng
         import torch.distributed as dist
+        if self.csr[side] is None:
+            raise ValueError('no %s CSR was given to this DistributedALS' % side)
         X, Y = (eng.U, eng.V) if side == 'users' else (eng.V, eng.U)
         n_x, n_y = int(X.shape[0]), int(Y.shape[0])
         self.G.zero_()

@@ -109,8 +109,14 @@ def cml_forward(U, V, pairs, negs, margin, use_rank_weight, n_items):
         omega = np.log(rank + F(1.0)).astype(F)
     else:
         omega = np.ones_like(dp)
+    kpp = np.min(np.abs(imp_arg), axis=1) if imp_arg.size else np.zeros(0, F)
+    if dn.shape[1] > 1 and dn.shape[0]:
+        # a near-tie of the two closest negatives is a kink of the min too (exact ties = the same item drawn twice are not)
+        ds = np.sort(dn, axis=1)
+        gap = ds[:, 1] - ds[:, 0]
+        kpp = np.minimum(kpp, np.where(gap == 0, np.inf, gap).astype(F))
     return dict(Uu=Uu, Vi=Vi, Vj=Vj, dp=dp, dn=dn, dmin=dmin, h=h, omega=omega,
-                kink=float(np.min(np.abs(imp_arg))) if imp_arg.size else np.inf)
+                kink=float(np.min(np.abs(imp_arg))) if imp_arg.size else np.inf, kink_per_pair=kpp)
 
 
 def cml_step(U, V, accU, accV, pairs, negs, lr=0.1, reg_cov=1.0, margin=1.5, use_rank_weight=True,

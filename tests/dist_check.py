@@ -16,11 +16,65 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
+def stage_collectives_through_host():
+    """ONE-GPU form of this script (CF_DIST_BACKEND=gloo): NCCL refuses two ranks on one device, so the ranks -- separate
+    processes that share GPU 0 -- talk over gloo, and every collective on a CUDA tensor is staged through the host here:
+    device synchronise, copy out, the CPU collective, copy back.  That keeps what the product relies on (a collective
+    completes only after everything every rank enqueued before it) and changes nothing else: the device-side exchange
+    still runs over CUDA-IPC mappings of the other PROCESS's buffers, the kernels and the plan are the ones of N GPUs."""
+    real = {n: getattr(dist, n) for n in ('all_reduce', 'broadcast', 'all_gather', 'all_gather_into_tensor',
+                                          'all_to_all_single', 'reduce_scatter_tensor')}
+
+    def out_in(name, n_out, flat=False):
+        def f(*a, **kw):
+            a = list(a)
+            cu = [k for k in range(len(a)) if torch.is_tensor(a[k]) and a[k].is_cuda]
+            if not cu:
+                return real[name](*a, **kw)
+            torch.cuda.synchronize()
+            dev_t = {k: a[k] for k in cu}
+            fl = flat or (name == 'all_to_all_single' and len(a) == 2 and not kw.get('output_split_sizes') and not kw.get('input_split_sizes'))
+            for k in cu:
+                a[k] = dev_t[k].cpu().reshape(-1) if fl else dev_t[k].cpu()   # gloo checks shapes, NCCL only sizes
+            real[name](*a, **kw)
+            for k in cu[:n_out]:
+                dev_t[k].copy_(a[k].view(dev_t[k].shape))
+            torch.cuda.synchronize()
+        return f
+    dist.all_reduce = out_in('all_reduce', 1)
+    dist.broadcast = out_in('broadcast', 1)
+    dist.all_gather_into_tensor = out_in('all_gather_into_tensor', 1, flat=True)
+    dist.all_to_all_single = out_in('all_to_all_single', 1)
+    dist.reduce_scatter_tensor = out_in('reduce_scatter_tensor', 1, flat=True)
+
+    def all_gather(outs, t, group=None):
+        if not t.is_cuda:
+            return real['all_gather'](outs, t, group=group)
+        torch.cuda.synchronize()
+        host = [torch.empty(o.shape, dtype=o.dtype) for o in outs]
+        real['all_gather'](host, t.cpu(), group=group)
+        for o, h in zip(outs, host):
+            o.copy_(h)
+        torch.cuda.synchronize()
+    dist.all_gather = all_gather
+
+
 def main():
     rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    dist.init_process_group('nccl', device_id=dev)
+    backend = os.environ.get('CF_DIST_BACKEND', 'nccl')
+    if backend == 'nccl':
+        torch.cuda.set_device(local)
+        dev = torch.device('cuda', local)
+        dist.init_process_group('nccl', device_id=dev)
+    else:
+        local = local % torch.cuda.device_count()               # the ranks share the GPUs there are (one: all on cuda:0)
+        torch.cuda.set_device(local)
+        dev = torch.device('cuda', local)
+        dist.init_process_group('gloo')
+        stage_collectives_through_host()
+        os.environ['CF_DIST_HOST_BARRIER'] = '1'                # dist.py: the named barrier = device synchronise + host barrier
+        if rank == 0:
+            print('backend gloo: %d ranks on %d GPU(s), collectives staged through the host' % (world, torch.cuda.device_count()))
     from collaborativefilteringusingtensorflow_b200 import BPRMF, CML
     from collaborativefilteringusingtensorflow_b200.dist import DistributedTrainer, distributed_topk, item_shard_rows
     from collaborativefilteringusingtensorflow_b200.sparse import DeviceCSR

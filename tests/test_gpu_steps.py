@@ -17,11 +17,20 @@ def _close(a, b, what='', stress=False):
     """Golden-vector tests: rtol 1e-5 + atol 1e-6 (north_star: 'within 1e-5 relative (fp32)').
     Stress shapes (hundreds of duplicate gradients per row, rank-weighted CML coefficients ~10): the fp32 sum of the
     duplicates is order-dependent at ~eps * sum|g_i| in ANY implementation (TF's segment-sum included), so elements
-    near zero are compared at 1e-5 of the largest row norm of the table; Adagrad accumulators hold g^2 (twice the relative error)."""
+    near zero are compared at 1e-5 of THEIR OWN ROW's norm (1e-5 relative per row vector); Adagrad accumulators hold g^2
+    (twice the relative error)."""
     a, b = np.asarray(a), np.asarray(b)
     rtol = 5e-5 if 'acc' in what else RTOL
-    atol = max(ATOL, 1e-5 * float(np.sqrt((b.reshape(b.shape[0], -1).astype(np.float64) ** 2).sum(1)).max())) if stress else ATOL
-    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol, err_msg=what)
+    if not stress:
+        np.testing.assert_allclose(a, b, rtol=rtol, atol=ATOL, err_msg=what)
+        return
+    b2 = b.reshape(b.shape[0], -1).astype(np.float64)
+    a2 = a.reshape(b2.shape).astype(np.float64)
+    atol = np.maximum(ATOL, 1e-5 * np.sqrt((b2 ** 2).sum(1)))[:, None]
+    bad = np.abs(a2 - b2) > rtol * np.abs(b2) + atol
+    assert not bad.any(), '%s: %d elements off, worst |diff| %.3g at row %d (row norm %.3g)' % (
+        what, int(bad.sum()), float(np.abs(a2 - b2).max()), int(np.abs(a2 - b2).max(1).argmax()),
+        float(np.sqrt((b2 ** 2).sum(1))[np.abs(a2 - b2).max(1).argmax()]))
 
 
 def _mk(kind, nu, ni, d, **kw):
@@ -138,9 +147,11 @@ def test_cml_vs_oracle(d, B, W, nu, ni):
     P = _state(m)
     for s in range(2):
         pairs, negs = _rand_batch(rng, nu, ni, B, W)
-        f = steps.cml_forward(P['U'], P['V'], pairs, negs, 1.0, True, ni)
-        if f['kink'] < 1e-5:
-            pytest.skip('random batch sits on a relu/indicator kink')
+        # pairs whose hinge / impostor argument sits within rounding distance of the relu / indicator kink are dropped
+        # (fp32 summation order decides their side in any implementation); the rest of the minibatch is compared
+        keep = steps.cml_forward(P['U'], P['V'], pairs, negs, 1.0, True, ni)['kink_per_pair'] >= 1e-5
+        assert keep.mean() > 0.9
+        pairs, negs = np.ascontiguousarray(pairs[keep]), np.ascontiguousarray(negs[keep])
         loss = m.step(pairs, negs)
         ol = steps.cml_step(P['U'], P['V'], P['accU'], P['accV'], pairs, negs, 0.1, 1.0, 1.0, True, 1.0)
         st = _state(m)
