@@ -24,11 +24,16 @@ Pinning status
   (tests/golden/rating_golden.json); the MF step / prediction restatement is unpinned like
   ``oracle.steps`` (it IS ``oracle.steps.wrmf_step`` with weight 1); ``oracle.steps.svd_step`` is cross-checked
   against a torch-autograd restatement of svd.py:52-80 (tests/golden/svd_golden.npz).
-* ``oracle.steps`` / ``oracle.scoring`` -- **PARITY UNPINNED against TensorFlow itself**: the
+* ``oracle.steps`` / ``oracle.scoring`` -- **PARITY UNPINNED against the TensorFlow binary**: the
   arithmetic lives in third-party TensorFlow (>=1.13, unpinned, README.md:20-22), which is
-  not installable here and for which the reference ships no tests or golden vectors.  The
-  restatement follows the reference call sites line by line and TF1's published semantics
-   and is cross-checked against an independent torch-autograd
-  restatement of the same TF graph with ``torch.optim.Adagrad(initial_accumulator_value=0.1,
-  eps=0)`` (tests/golden/step_golden.npz, made by oracle/gen_golden.py).
+  not installable here and for which the reference ships no tests or golden vectors.  Pinned
+  instead to (1) the reference's OWN model files, imported unmodified from /root/reference and run
+  through their train() on the torch-backed TF-1.x stand-in ``oracle/tf1_shim`` (made by
+  oracle/gen_refgraph_golden.py -> tests/golden/{step,tuple,svd}_refgraph_golden.npz: tables,
+  accumulators, losses after every step and the metric values train() returned), and (2) an
+  independent torch-autograd restatement of the same TF graphs with
+  ``torch.optim.Adagrad(initial_accumulator_value=0.1, eps=0)`` (tests/golden/step_golden.npz,
+  made by oracle/gen_golden.py).  The stand-in follows TF1's published semantics (SURVEY.md
+  Appendix A/B; listed in its header); it is an interpretation of TensorFlow, not TensorFlow.
+* ``oracle/tf1_shim`` -- the stand-in itself; imported only by oracle/gen_refgraph_golden.py.
 """

@@ -1,0 +1,254 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE.  Runs the reference's OWN model files -- imported unmodified from /root/reference -- on the
+torch-backed TensorFlow-1.x stand-in of oracle/tf1_shim (TensorFlow has no wheel in this image) and writes
+tests/golden/step_refgraph_golden.npz: for every case of tests/golden/step_golden.npz (same initial tables, same
+minibatches, same hyper-parameters) the tables, Adagrad accumulators and losses after every step of the reference's
+``train()`` loop, and the metric values its end-of-epoch evaluation returned (its own ``__recommend`` = top_k + the Python
+filter, its own metrics/ranking.py).  A fake sampler feeds the recorded minibatches through ``next_batch()``.
+
+    python oracle/gen_refgraph_golden.py        (in the build container; /root/reference does not travel to the GPU box)
+
+It also prints how far these results are from the torch-autograd RESTATEMENT that generated step_golden.npz: both must
+agree to float32 rounding, which pins the restatement (and with it oracle/steps.py) to the reference's graph code."""
+import contextlib
+import importlib
+import io
+import json
+import os
+import sys
+
+import numpy as np
+from scipy.sparse import lil_matrix
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = '/root/reference/src'
+sys.path.insert(0, os.path.join(ROOT, 'oracle', 'tf1_shim'))
+for p in ('models/pl/models', 'models/basic/models', 'metrics', 'samplers'):
+    sys.path.insert(1, os.path.join(REF, p))
+import tensorflow as tf          # the stand-in  # noqa: E402
+
+OUT = os.path.join(ROOT, 'tests', 'golden')
+VAR = dict(U='user_embed', V='item_embed', b='item_bias')
+
+
+class FakeSampler(object):
+    """next_batch() hands out the recorded minibatches in turn and snapshots the model state before each one."""
+
+    def __init__(self, batches, pack):
+        self.batches, self.pack, self.k, self.snaps = batches, pack, 0, []
+
+    @staticmethod
+    def snapshot():
+        st = {v.name: v.value.detach().numpy().copy() for v in tf.VARIABLES}
+        opt = tf.OPTIMIZERS[-1]                               # the optimizer of train()'s own train_op
+        for v, a in opt.accum.items():
+            st['acc/' + v.name] = (a.numpy().copy() if a is not None else np.full(v.shape, 0.1, np.float32))
+        return st
+
+    def next_batch(self):
+        if self.k > 0:
+            self.snaps.append(self.snapshot())
+        b = self.batches[self.k]
+        self.k += 1
+        return self.pack(b)
+
+
+def run_case(g, name, module, cls, kwargs, pack, names):
+    tf.reset_default_graph()
+    mod = importlib.reload(importlib.import_module(module))
+    keys = [k for k in ('U', 'V', 'b') if '%s/init/%s' % (name, k) in g.files]
+    init = {k: g['%s/init/%s' % (name, k)] for k in keys}
+    nu, ni = init['U'].shape[0], init['V'].shape[0]
+    steps = 0
+    while '%s/batch%d/0' % (name, steps) in g.files:
+        steps += 1
+    nb = sum(1 for f in g.files if f.startswith('%s/batch0/' % name))
+    batches = [[g['%s/batch%d/%d' % (name, s, i)] for i in range(nb)] for s in range(steps)]
+    B = len(batches[0][0])
+    rng = np.random.default_rng(sum(ord(ch) for ch in name))      # (hash() of a str changes from process to process)
+    cells = rng.choice(nu * ni, steps * B + 40, replace=False)
+    tra, tst = lil_matrix((nu, ni), dtype=np.float32), lil_matrix((nu, ni), dtype=np.float32)
+    for c in cells[:steps * B]:                                # int(nnz / batch_size) = the recorded steps (bprmf.py:134)
+        tra[c // ni, c % ni] = 1
+    for c in cells[steps * B:]:
+        tst[c // ni, c % ni] = 1
+    topn = 5
+    model = getattr(mod, cls)(nu, ni, topN=topn, split_method='cv', eval_metrics=names, n_factors=init['U'].shape[1],
+                              batch_size=B, max_iter=1, **kwargs)
+    for k in keys:
+        tf.INIT_OVERRIDE[VAR[k]] = init[k]
+    sampler = FakeSampler(batches, pack)
+    losses = []
+    real_run = tf.Session.run
+
+    def logging_run(self, fetches, feed_dict=None):
+        out = real_run(self, fetches, feed_dict)
+        if isinstance(fetches, tuple) and not hasattr(fetches, 'indices') and len(fetches) == 2:   # train_op = (optimize, loss)
+            losses.append(float(out[1]))
+        return out
+    tf.Session.run = logging_run
+    try:
+        with contextlib.redirect_stdout(io.StringIO()) as log:
+            scores = model.train(1, tra.tocsr(), tst.tocsr(), sampler)
+    finally:
+        tf.Session.run = real_run
+    sampler.snaps.append(sampler.snapshot())
+    assert sampler.k == steps and len(losses) == steps, (sampler.k, len(losses))
+    out = {}
+    worst = 0.0
+    for s in range(steps):
+        out['%s/loss%d' % (name, s)] = np.float64(losses[s])
+        worst = max(worst, abs(losses[s] - float(g['%s/loss%d' % (name, s)])) / abs(losses[s]))
+        for k in keys:
+            for pre, src in (('', VAR[k]), ('acc', 'acc/' + VAR[k])):
+                a = sampler.snaps[s][src]
+                out['%s/step%d/%s%s' % (name, s, pre, k)] = a
+                want = g['%s/step%d/%s%s' % (name, s, pre, k)]
+                worst = max(worst, float(np.max(np.abs(a - want) / (np.abs(want) + 1e-3))))
+    out[name + '/eval'] = np.array(json.dumps(dict(
+        topN=topn, metrics=names, scores=[float(x) for x in scores],
+        tra=[[int(r), int(c)] for r, c in zip(*tra.nonzero())], tst=[[int(r), int(c)] for r, c in zip(*tst.nonzero())])))
+    print('%-18s %s.%s.train(): %d steps, losses %s, eval %s; max rel. distance to the autograd restatement %.2e'
+          % (name, module, cls, steps, ['%.4f' % x for x in losses], ['%.4f' % x for x in scores], worst))
+    print('   reference printed:', log.getvalue().strip().splitlines()[-1][:150])
+    return out, worst
+
+
+def drive_graph(model, cls, feeds, n_steps):
+    """For the models whose train() needs the whole preprocessing pipeline (PRIGP / CPLR: user similarities, their own
+    sampler classes): the reference's graph (its ``__optimize__`` / ``__loss`` properties, its placeholders) driven by
+    the five lines its train() wraps around it (prigp.py:197-212)."""
+    train_op = (model.__optimize__, getattr(model, '_%s__loss' % cls))        # "must before the initializer"
+    sess = tf.Session(config=tf.ConfigProto())
+    sess.run(tf.global_variables_initializer())
+    losses, snaps = [], []
+    for s in range(n_steps):
+        _, loss = sess.run(train_op, feeds(s))
+        losses.append(float(loss))
+        snaps.append(FakeSampler.snapshot())
+    return losses, snaps
+
+
+def tuple_cases():
+    g = np.load(os.path.join(OUT, 'tuple_golden.npz'))
+    out, worst = {}, 0.0
+    for name in ('prigp', 'prigp_d20', 'cplr', 'cplr_d20'):
+        tf.reset_default_graph()
+        h = json.loads(str(g[name + '/hyper']))
+        init = {k: g['%s/init/%s' % (name, k)] for k in ('U', 'V', 'b')}
+        nu, ni, d = init['U'].shape[0], init['V'].shape[0], init['U'].shape[1]
+        B = g[name + '/batch0/tuples'].shape[0]
+        if name.startswith('prigp'):
+            mod, cls = importlib.reload(importlib.import_module('prigp')), 'PRIGP'
+            m = mod.PRIGP(nu, ni, alpha=h['alpha'], reg=h['reg'], n_factors=d, batch_size=B, lr=h['lr'])
+            feeds = lambda s: {m._PRIGP__uijtk_placeholder: g['%s/batch%d/tuples' % (name, s)]}
+        else:
+            mod, cls = importlib.reload(importlib.import_module('cplr_u')), 'CPLR'
+            m = mod.CPLR(nu, ni, alpha=h['alpha'], beta=h['beta'], gamma=h['gamma'], reg=h['reg'], n_factors=d, batch_size=B, lr=h['lr'])
+            feeds = lambda s: {m._CPLR__uitj_placeholder: g['%s/batch%d/tuples' % (name, s)],
+                               m._CPLR__coefs_placeholder: g['%s/batch%d/coefs' % (name, s)]}
+        for k in init:
+            tf.INIT_OVERRIDE[VAR[k]] = init[k]
+        losses, snaps = drive_graph(m, cls, feeds, 2)
+        w = 0.0
+        for s in range(2):
+            out['%s/loss%d' % (name, s)] = np.float64(losses[s])
+            w = max(w, abs(losses[s] - float(g['%s/loss%d' % (name, s)])) / abs(losses[s]))
+            for k in init:
+                for pre, src in (('', VAR[k]), ('acc', 'acc/' + VAR[k])):
+                    key = '%s/step%d/%s%s' % (name, s, pre, k)
+                    if src not in snaps[s]:
+                        assert key not in g.files, key            # PRIGP leaves item_bias out of the optimizer (prigp.py:145)
+                        continue
+                    out[key] = snaps[s][src]
+                    w = max(w, float(np.max(np.abs(out[key] - g[key]) / (np.abs(g[key]) + 1e-3))))
+        print('%-18s %s graph: losses %s; max rel. distance to the autograd restatement %.2e' % (name, cls, ['%.4f' % x for x in losses], w))
+        worst = max(worst, w)
+    np.savez_compressed(os.path.join(OUT, 'tuple_refgraph_golden.npz'), **out)
+    print('tuple_refgraph_golden.npz: %d arrays; worst relative distance to tuple_golden.npz %.2e' % (len(out), worst))
+
+
+def svd_cases():
+    """svd.py through its own train(): recorded (user, item, rating) minibatches, its own clipped-prediction evaluation
+    with the reference's metrics/rating.py."""
+    g = np.load(os.path.join(OUT, 'svd_golden.npz'))
+    out, worst = {}, 0.0
+    for name in ('svd', 'svd_d7'):
+        tf.reset_default_graph()
+        mod = importlib.reload(importlib.import_module('svd'))
+        init = {k: g['%s/init/%s' % (name, k)] for k in ('U', 'V', 'K')}
+        nu, ni, d = init['U'].shape[0], init['V'].shape[0], init['U'].shape[1]
+        batches = [[g['%s/batch%d' % (name, s)]] for s in range(2)]
+        B = len(batches[0][0])
+        rng = np.random.default_rng(5)
+        tst = np.stack([rng.integers(0, nu, 80), rng.integers(0, ni, 80), rng.integers(1, 11, 80) / 2.0], 1)
+        m = mod.SVD(nu, ni, eval_metrics=['rmse', 'mae'], range_of_ratings=(0.5, 5), reg=0.05, n_factors=d, batch_size=B, max_iter=1, lr=0.1)
+        for k, v in dict(U='user_embed', V='item_embed', K='kernel').items():
+            tf.INIT_OVERRIDE[v] = init[k]
+        sampler = FakeSampler(batches, lambda b: b[0])
+        losses = []
+        real_run = tf.Session.run
+
+        def logging_run(self, fetches, feed_dict=None):
+            o = real_run(self, fetches, feed_dict)
+            if isinstance(fetches, tuple) and len(fetches) == 2:
+                losses.append(float(o[1]))
+            return o
+        tf.Session.run = logging_run
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                scores = m.train(1, np.zeros((2 * B, 3)), tst, sampler)
+        finally:
+            tf.Session.run = real_run
+        sampler.snaps.append(sampler.snapshot())
+        w = 0.0
+        for s in range(2):
+            out['%s/loss%d' % (name, s)] = np.float64(losses[s])
+            w = max(w, abs(losses[s] - float(g['%s/loss%d' % (name, s)])) / abs(losses[s]))
+            for k, v in dict(U='user_embed', V='item_embed', K='kernel').items():
+                for pre, src in (('', v), ('acc', 'acc/' + v)):
+                    key = '%s/step%d/%s%s' % (name, s, pre, k)
+                    out[key] = sampler.snaps[s][src]
+                    w = max(w, float(np.max(np.abs(out[key] - g[key]) / (np.abs(g[key]) + 1e-3))))
+        out[name + '/eval'] = np.array(json.dumps(dict(metrics=['rmse', 'mae'], scores=[float(x) for x in scores], tst=tst.tolist(),
+                                                       range_of_ratings=[0.5, 5])))
+        print('%-18s svd.SVD.train(): losses %s, eval %s; max rel. distance to the autograd restatement %.2e'
+              % (name, ['%.4f' % x for x in losses], ['%.5f' % x for x in scores], w))
+        worst = max(worst, w)
+    np.savez_compressed(os.path.join(OUT, 'svd_refgraph_golden.npz'), **out)
+    print('svd_refgraph_golden.npz: %d arrays; worst relative distance to svd_golden.npz %.2e' % (len(out), worst))
+
+
+def main():
+    tuple_cases()
+    svd_cases()
+    g = np.load(os.path.join(OUT, 'step_golden.npz'))
+    names = ['pre', 'recall', 'map', 'mrr', 'ndcg']
+    out, worst = {}, 0.0
+    pn = lambda b: (b[0].astype(np.int32), b[1].astype(np.int32))
+    cases = []
+    for name in ('bpr', 'bpr_w3'):
+        h = json.loads(str(g[name + '/hyper']))
+        cases.append((name, 'bprmf', 'BPRMF', dict(reg=h['reg'], lr=h['lr']), pn))
+    for name in ('cml', 'cml_norank_noreg'):
+        h = json.loads(str(g[name + '/hyper']))
+        cases.append((name, 'cml', 'CML', dict(reg_cov=h['reg_cov'], margin=h['margin'], use_rank_weight=h['use_rank_weight'],
+                                               clip_norm=h['clip_norm'], lr=h['lr']), pn))
+    for name in ('gbpr', 'gbpr_g1'):
+        h = json.loads(str(g[name + '/hyper']))
+        G = g[name + '/batch0/2'].shape[1]
+        cases.append((name, 'gbprmf', 'GBPRMF', dict(rho=h['rho'], gsize=G, reg=h['reg'], lr=h['lr']),
+                      lambda b: (b[0].astype(np.int32), b[1].astype(np.int32), b[2].astype(np.int32))))   # sampler_gbpr: pairs, negatives, group
+    h = json.loads(str(g['wrmf/hyper']))
+    cases.append(('wrmf', 'wrmf', 'WRMF', dict(weight=h['weight'], reg=h['reg'], lr=h['lr']),
+                  lambda b: np.concatenate([b[0].astype(np.float64), b[1].astype(np.float64)[:, None]], 1)))
+    for name, module, cls, kw, pack in cases:
+        o, w = run_case(g, name, module, cls, kw, pack, names)
+        out.update(o)
+        worst = max(worst, w)
+    np.savez_compressed(os.path.join(OUT, 'step_refgraph_golden.npz'), **out)
+    print('step_refgraph_golden.npz: %d arrays; worst relative distance to step_golden.npz %.2e' % (len(out), worst))
+
+
+if __name__ == '__main__':
+    main()

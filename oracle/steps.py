@@ -17,8 +17,11 @@ duplicate rows SUMMED, then ``SparseApplyAdagrad`` runs once per unique row:
 ``acc += g*g; var -= lr * g / sqrt(acc)`` with ``acc0 = 0.1`` and no epsilon; ``lr`` is the
 constant captured at graph build (bprmf.py:134 -- the ``*= .98`` at :159 is cosmetic).
 
-PARITY UNPINNED against TensorFlow itself (not installable here; the reference has no tests for
-this path).  Cross-checked against a torch-autograd restatement in oracle/gen_golden.py.
+Pinning: TensorFlow itself is not installable here and the reference has no tests for this path, so
+PARITY IS UNPINNED AGAINST THE TENSORFLOW BINARY.  What pins it instead: (1) the reference's own model
+files, imported unmodified and run through their train() on the TF-1.x stand-in of oracle/tf1_shim
+(oracle/gen_refgraph_golden.py -> tests/golden/*_refgraph_golden.npz: state after every step and the
+metric values train() returned); (2) a torch-autograd restatement of the graphs (oracle/gen_golden.py).
 
 Duplicate-row gradient sums are accumulated in float64 and rounded once to float32, so the
 oracle sits in the middle of any fp32 summation order (TF's segment-sum or the GPU's atomics).

@@ -28,9 +28,13 @@ def pytest_collection_modifyitems(config, items):
                 it.add_marker(skip)
 
 
-@pytest.fixture(scope='session')
-def step_golden():
-    return np.load(os.path.join(GOLDEN, 'step_golden.npz'), allow_pickle=False)
+@pytest.fixture(scope='session', params=['autograd', 'refgraph'])
+def step_golden(request):
+    """Two sources of expected values for the same inputs (tests/golden/README.md): 'autograd' = the torch-autograd
+    restatement of the TF1 graphs (oracle/gen_golden.py); 'refgraph' = the reference's OWN model files, imported
+    unmodified and run through their train() on the TF1 stand-in of oracle/tf1_shim (oracle/gen_refgraph_golden.py)."""
+    import refgraph_cases
+    return refgraph_cases.golden('step', request.param)
 
 
 @pytest.fixture(scope='session')

@@ -125,11 +125,14 @@ def test_mf_trains_ml100k_like_the_oracle(golden, capsys):
     mf.close()
 
 
+@pytest.mark.parametrize('source', ['autograd', 'refgraph'])
 @pytest.mark.parametrize('name', ['svd', 'svd_d7'])
-def test_svd_step_golden(name):
-    """SVD (svd.py:52-80) on the GPU against the torch-autograd golden: tables, kernel matrix, accumulators, loss."""
+def test_svd_step_golden(name, source):
+    """SVD (svd.py:52-80) on the GPU against the torch-autograd golden and against the reference's own svd.py run through
+    its train() on the TF1 stand-in ('refgraph'): tables, kernel matrix, accumulators, loss."""
     from collaborativefilteringusingtensorflow_b200 import SVD
-    z = np.load(os.path.join(GOLDEN, 'svd_golden.npz'))
+    import refgraph_cases
+    z = refgraph_cases.golden('svd', source)
     U0 = z[name + '/init/U']
     nu, d = U0.shape
     ni = z[name + '/init/V'].shape[0]

@@ -21,9 +21,12 @@ def _model(name, nu, ni, d, h, seed=1):
     return CPLR(nu, ni, alpha=h['alpha'], beta=h['beta'], gamma=h['gamma'], reg=h['reg'], n_factors=d, lr=h['lr'], verbose=False, seed=seed)
 
 
+@pytest.mark.parametrize('source', ['autograd', 'refgraph'])
 @pytest.mark.parametrize('name', ['prigp', 'prigp_d20', 'cplr', 'cplr_d20'])
-def test_tuple_steps_equal_the_autograd_golden(name):
-    tg = np.load(os.path.join(GOLDEN, 'tuple_golden.npz'))
+def test_tuple_steps_equal_the_autograd_golden(name, source):
+    """source 'refgraph': the expected values come from the reference's own prigp.py / cplr_u.py graphs (TF1 stand-in)."""
+    import refgraph_cases
+    tg = refgraph_cases.golden('tuple', source)
     h = json.loads(str(tg[name + '/hyper']))
     init = {k: tg['%s/init/%s' % (name, k)] for k in ('U', 'V', 'b')}
     m = _model(name, init['U'].shape[0], init['V'].shape[0], init['U'].shape[1], h)

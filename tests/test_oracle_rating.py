@@ -53,11 +53,14 @@ def test_mf_step_is_wrmf_with_unit_weight_and_descends(golden):
     assert [round(e['rmse'], 4) for e in ep] == sorted([round(e['rmse'], 4) for e in ep], reverse=True) and ep[-1]['rmse'] < 1.0
 
 
-def test_svd_step_matches_autograd_golden():
+@pytest.mark.parametrize('source', ['autograd', 'refgraph'])
+def test_svd_step_matches_autograd_golden(source):
     """oracle.steps.svd_step (hand-derived gradients, svd.py:52-80) against the torch-autograd restatement of the same
-    graph recorded in tests/golden/svd_golden.npz."""
+    graph recorded in tests/golden/svd_golden.npz, and against the reference's own svd.py run through its train() on the
+    TF1 stand-in (svd_refgraph_golden.npz)."""
     from oracle import steps
-    z = np.load(os.path.join(GOLDEN, 'svd_golden.npz'))
+    import refgraph_cases
+    z = refgraph_cases.golden('svd', source)
     for name in ('svd', 'svd_d7'):
         P = {k: z['%s/init/%s' % (name, k)].copy() for k in ('U', 'V', 'K')}
         A = {k: np.full_like(v, 0.1) for k, v in P.items()}
@@ -67,3 +70,16 @@ def test_svd_step_matches_autograd_golden():
             for k in ('U', 'V', 'K'):
                 np.testing.assert_allclose(P[k], z['%s/step%d/%s' % (name, s, k)], rtol=1e-5, atol=1e-6)
                 np.testing.assert_allclose(A[k], z['%s/step%d/acc%s' % (name, s, k)], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('name', ['svd', 'svd_d7'])
+def test_oracle_svd_evaluation_matches_the_reference_train_loop(name):
+    """rmse / mae the reference's OWN svd.py train() returned (its clipped predictions, its metrics/rating.py; run on the TF1
+    stand-in, oracle/gen_refgraph_golden.py) against the oracle's predictions + metrics on the tables it ended with."""
+    import refgraph_cases
+    from oracle import rating as orc
+    z = refgraph_cases.golden('svd', 'refgraph')
+    ev = json.loads(str(z[name + '/eval']))
+    tst = np.asarray(ev['tst'])
+    pred = orc.svd_predict(z[name + '/step1/U'], z[name + '/step1/V'], z[name + '/step1/K'], tst[:, :2], ev['range_of_ratings'])
+    np.testing.assert_allclose(orc.evaluate(tst[:, 2], pred, ev['metrics']), ev['scores'], rtol=1e-6)

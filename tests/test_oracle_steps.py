@@ -129,3 +129,23 @@ def test_torch_multithreaded_port_matches_numpy_oracle():
             steps_torch.cml_step(b[0], b[1], b[2], b[3], torch.from_numpy(pairs), torch.from_numpy(negs), 0.1, 1.0, 1.0, True, 1.0)
         for x, y in zip(a, b):
             np.testing.assert_allclose(y.numpy(), x, rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize('name', ['bpr', 'bpr_w3', 'cml', 'cml_norank_noreg', 'gbpr', 'gbpr_g1', 'wrmf'])
+def test_oracle_scoring_and_metrics_match_the_reference_train_loop(name):
+    """The metric values the reference's OWN train() returned after its end-of-epoch evaluation (its __recommend = top_k +
+    Python filter, its metrics/ranking.py; run on the TF1 stand-in, oracle/gen_refgraph_golden.py) against the oracle's
+    scoring + masked top-N + metrics on the tables the reference ended with."""
+    from oracle import ranking, scoring
+    import refgraph_cases as R
+    c = R.case(*R.load(), name)
+    ev, f = c['ev'], c['final']
+    kind = dict(cml=scoring.NEG_SQDIST, gbpr=scoring.DOT_BIAS).get(R.KIND[name], scoring.DOT)
+    users = sorted(set(r for r, _ in ev['tst']))
+    truth = [set(c['tst'].rows[u]) for u in users]
+    seen = [set(c['tra'].rows[u]) for u in users]
+    topn = 1000 if R.KIND[name] == 'cml' else ev['topN']                      # cml.py:203-211: the tail re-scores at 1000
+    s = scoring.scores_f64(f['U'][users], f['V'], kind, f.get('b'))
+    top = scoring.topn_masked(s, seen, min(topn, s.shape[1]))
+    got = ranking.evaluateCV(truth, [[int(x) for x in r if x >= 0] for r in top], ev['metrics'], topn)
+    np.testing.assert_allclose(got, ev['scores'], rtol=0, atol=1e-12)

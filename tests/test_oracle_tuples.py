@@ -1,6 +1,6 @@
 """The numpy restatement of the PRIGP / CPLR minibatch steps (oracle/steps.py: hand-derived gradients + TF1 Adagrad on the
 summed row gradients) against an independent torch-autograd restatement of the same TF graphs (tests/golden/
-tuple_golden.npz, oracle/gen_golden.py tuples).  PARITY UNPINNED against TensorFlow itself (not installable)."""
+tuple_golden.npz, oracle/gen_golden.py tuples).  Also against the reference's own prigp.py / cplr_u.py graphs run on the TF-1.x stand-in (tuple_refgraph_golden.npz).  TensorFlow itself is not installable."""
 import json
 import os
 
@@ -12,9 +12,12 @@ from oracle import steps
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 
-@pytest.fixture(scope='module')
-def tg():
-    return np.load(os.path.join(GOLDEN, 'tuple_golden.npz'))
+@pytest.fixture(scope='module', params=['autograd', 'refgraph'])
+def tg(request):
+    """'autograd': the torch-autograd restatement; 'refgraph': the reference's own prigp.py / cplr_u.py graphs run on the TF1
+    stand-in (oracle/gen_refgraph_golden.py)."""
+    import refgraph_cases
+    return refgraph_cases.golden('tuple', request.param)
 
 
 @pytest.mark.parametrize('name', ['prigp', 'prigp_d20', 'cplr', 'cplr_d20'])
