@@ -219,7 +219,52 @@ def svd_cases():
     print('svd_refgraph_golden.npz: %d arrays; worst relative distance to svd_golden.npz %.2e' % (len(out), worst))
 
 
+def e2e_reference(max_iter=50):
+    """The body of the reference driver's worker() (pl/testbprmf.py:32-52) on ml-100k fold 1 with its own hyper-parameters
+    (:21-30; max_iter is BPRMF's default 50), built from the reference's own modules: utils/IOUtil.loadSparseR,
+    utils/Util.matBinarize, samplers/sampler_ranking.Sampler (its producer thread, np.random seeded here) and
+    models/bprmf.BPRMF.train() on the TF1 stand-in.  Records every line train() printed (TraLoss + the five metrics per
+    epoch) -> tests/golden/e2e_refgraph_golden.json."""
+    import re
+    import time
+    sys.path.insert(1, os.path.join(REF, 'utils'))
+    from IOUtil import loadSparseR
+    from Util import matBinarize
+    from sampler_ranking import Sampler
+    tf.reset_default_graph()
+    tf.set_random_seed(2026)
+    np.random.seed(2026)
+    mod = importlib.reload(importlib.import_module('bprmf'))
+    dataset_dir = '/root/reference/data/movielens/ml-100k/'
+    n_users, n_items, fold = 943, 1682, 0
+    reg, topN, split_method, eval_metrics, n_factors, batch_size, negSample = .1, 10, 'cv', ['pre', 'recall', 'map', 'mrr', 'ndcg'], 100, 100, 1
+    trasR = lil_matrix(matBinarize(loadSparseR(n_users, n_items, dataset_dir + 'ratings__%d_tra.txt' % (fold + 1)), 3))
+    tstsR = lil_matrix(matBinarize(loadSparseR(n_users, n_items, dataset_dir + 'ratings__%d_tst.txt' % (fold + 1)), 3))
+    sampler = Sampler(trasR=trasR, n_neg=negSample, batch_size=batch_size)
+    m = mod.BPRMF(n_users, n_items, topN, split_method, eval_metrics, reg, n_factors, batch_size, max_iter)
+    t0 = time.time()
+    with contextlib.redirect_stdout(io.StringIO()) as log:
+        scores = m.train(fold + 1, trasR, tstsR, sampler)
+    hist = []
+    for line in log.getvalue().splitlines():
+        mt = re.search(r'iter=\s*(\d+):\s+TraLoss=([0-9.]+).*Tst@10:(.*)$', line)
+        if mt:
+            hist.append(dict(epoch=int(mt.group(1)), TraLoss=float(mt.group(2)),
+                             **{kv.split('=')[0]: float(kv.split('=')[1]) for kv in mt.group(3).split()}))
+    assert len(hist) == max_iter, len(hist)
+    json.dump(dict(model='BPRMF', source='reference bprmf.py + sampler_ranking.py + IOUtil/Util, run on oracle/tf1_shim',
+                   hyper=dict(n_factors=n_factors, batch_size=batch_size, n_neg=negSample, reg=reg, lr=0.1, topN=topN, max_iter=max_iter),
+                   nnz=int(trasR.nnz), final_scores=[float(x) for x in scores], history=hist),
+              open(os.path.join(OUT, 'e2e_refgraph_golden.json'), 'w'), indent=1)
+    print('e2e_refgraph_golden.json: %d epochs in %.0f s; epoch 10 / 20 / %d ndcg@10 %.4f / %.4f / %.4f, final %s'
+          % (max_iter, time.time() - t0, max_iter, hist[9]['ndcg'], hist[19]['ndcg'], hist[-1]['ndcg'], ['%.4f' % x for x in scores]))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == 'e2e':
+        e2e_reference()
+        sys.stdout.flush()
+        os._exit(0)                       # the reference sampler's producer thread never ends
     tuple_cases()
     svd_cases()
     g = np.load(os.path.join(OUT, 'step_golden.npz'))

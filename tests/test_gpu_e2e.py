@@ -31,6 +31,37 @@ def test_bprmf_ml100k_ndcg_matches_oracle_run(ml100k, capsys):
     m.close()
 
 
+def test_bprmf_ml100k_50_epochs_matches_the_reference_driver_run(ml100k, capsys):
+    """tests/golden/e2e_refgraph_golden.json: the body of the reference driver's worker() (pl/testbprmf.py:32-52) run from the
+    reference's OWN modules -- IOUtil.loadSparseR, Util.matBinarize, sampler_ranking.Sampler with its producer thread,
+    bprmf.BPRMF.train() for its default 50 epochs -- on the TF1 stand-in (oracle/gen_refgraph_golden.py e2e).  The product
+    gets the same constructor call and must follow the same trajectory: NDCG@10 within +-0.02 at epochs 20 and 50
+    (unseeded sampler, run-to-run noise ~ +-0.01), the mean training loss of the last epoch within 3 %."""
+    import re
+    from collaborativefilteringusingtensorflow_b200.models.pl.models.bprmf import BPRMF
+    from collaborativefilteringusingtensorflow_b200.samplers.sampler_ranking import Sampler
+    gold = json.load(open(os.path.join(GOLDEN, 'e2e_refgraph_golden.json')))
+    h = gold['hyper']
+    tra, tst = ml100k['tra'], ml100k['tst']
+    assert tra.nnz == gold['nnz']                                       # the reference's loader + binarisation saw the same matrix
+    sampler = Sampler(trasR=tra, n_neg=h['n_neg'], batch_size=h['batch_size'], seed=7)
+    m = BPRMF(943, 1682, h['topN'], 'cv', NAMES, h['reg'], h['n_factors'], h['batch_size'], seed=7)   # testbprmf.py:46
+    scores = m.train(1, tra, tst, sampler)
+    out = capsys.readouterr().out
+    rows = re.findall(r'iter=\s*(\d+):\s+TraLoss=([0-9.]+).*ndcg=([0-9.]+)', out)
+    assert len(rows) == h['max_iter'] == 50
+    ours = {int(e): (float(l), float(n)) for e, l, n in rows}
+    ref = {x['epoch']: (x['TraLoss'], x['ndcg']) for x in gold['history']}
+    for ep in (20, 50):
+        assert abs(ours[ep][1] - ref[ep][1]) < 0.02, (ep, ours[ep], ref[ep])
+    assert abs(ours[50][0] - ref[50][0]) < 0.03 * ref[50][0], (ours[50], ref[50])
+    assert abs(ours[1][0] - ref[1][0]) < 0.05 * ref[1][0], (ours[1], ref[1])
+    got = dict(zip(NAMES, scores))
+    want = dict(zip(NAMES, gold['final_scores']))
+    assert abs(got['pre'] - want['pre']) < 0.02 and abs(got['recall'] - want['recall']) < 0.02 and abs(got['mrr'] - want['mrr']) < 0.04, (got, want)
+    m.close()
+
+
 def test_cml_gbpr_wrmf_train_on_ml100k(ml100k):
     from collaborativefilteringusingtensorflow_b200 import CML, GBPRMF, WRMF
     from collaborativefilteringusingtensorflow_b200.samplers import sampler_gbpr, sampler_ranking, sampler_rating
