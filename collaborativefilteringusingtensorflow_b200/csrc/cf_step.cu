@@ -269,7 +269,14 @@ static int train_steps_impl(const cf_step_args* a, cudaStream_t stream, cudaEven
   const long long R = (a->model == CF_MODEL_WRMF) ? 2 : 2 + W + G;
   P.n_occ = (long long)a->B * R;
   long long agrid = ((long long)a->B * R + 255) / 256;   // every thread scans one slot code per iteration
-  if (agrid > (long long)sms * 16) agrid = (long long)sms * 16;
+  // CF_APPLY_BLOCKS_PER_SM (default 16 = two waves of the 8 resident blocks): fewer leaves block slots to a sampler launch
+  // that runs beside the apply on another stream (models/_base.py::_epoch)
+  static int apply_bps = 0;
+  if (!apply_bps) {
+    const char* e = getenv("CF_APPLY_BLOCKS_PER_SM");
+    apply_bps = (e && atoi(e) > 0) ? atoi(e) : 16;
+  }
+  if (agrid > (long long)sms * apply_bps) agrid = (long long)sms * apply_bps;
   long long cgrid = ((long long)a->B * R + 255) / 256;
   if (cgrid > (long long)sms * 8) cgrid = (long long)sms * 8;
 

@@ -101,7 +101,10 @@ class RankingModelBase(object):
                 return torch.cat(losses)
             main = torch.cuda.current_stream(self.engine.device)
             if getattr(self, '_sample_stream', None) is None:
-                self._sample_stream = torch.cuda.Stream(self.engine.device)
+                # CF_SAMPLE_PRIORITY=1: a high-priority stream -- the sampler's blocks take the block slots the training
+                # kernels free before those kernels' own next blocks do
+                prio = -1 if os.environ.get('CF_SAMPLE_PRIORITY', '0') == '1' else 0
+                self._sample_stream = torch.cuda.Stream(self.engine.device, priority=prio)
             side = self._sample_stream
             side.wait_stream(main)                       # (nothing sampled here may start before what precedes the epoch)
 

@@ -219,12 +219,14 @@ def svd_cases():
     print('svd_refgraph_golden.npz: %d arrays; worst relative distance to svd_golden.npz %.2e' % (len(out), worst))
 
 
-def e2e_reference(max_iter=50):
-    """The body of the reference driver's worker() (pl/testbprmf.py:32-52) on ml-100k fold 1 with its own hyper-parameters
-    (:21-30; max_iter is BPRMF's default 50), built from the reference's own modules: utils/IOUtil.loadSparseR,
-    utils/Util.matBinarize, samplers/sampler_ranking.Sampler (its producer thread, np.random seeded here) and
-    models/bprmf.BPRMF.train() on the TF1 stand-in.  Records every line train() printed (TraLoss + the five metrics per
-    epoch) -> tests/golden/e2e_refgraph_golden.json."""
+def e2e_reference(which='bpr', max_iter=50):
+    """The body of the reference drivers' worker() (pl/testbprmf.py:32-52, pl/testcml.py:35-57) on ml-100k fold 1 with their
+    own hyper-parameters (max_iter is the models' default 50), built from the reference's own modules: utils/IOUtil.
+    loadSparseR, utils/Util.matBinarize, samplers/sampler_ranking.Sampler (its producer thread, np.random seeded here) and
+    models/bprmf.BPRMF.train() / models/cml.CML.train() on the TF1 stand-in.  Records every line train() printed (TraLoss +
+    the five metrics per epoch; CML: also its tail at topN = 5 .. 1000) -> tests/golden/e2e_refgraph_golden.json /
+    e2e_cml_refgraph_golden.json.  (CML's tail asks top_k for max|train set| + 1000 of 1682 items; the stand-in returns all
+    1682 where TensorFlow would refuse -- the driver was written for larger catalogues.)"""
     import re
     import time
     sys.path.insert(1, os.path.join(REF, 'utils'))
@@ -234,35 +236,70 @@ def e2e_reference(max_iter=50):
     tf.reset_default_graph()
     tf.set_random_seed(2026)
     np.random.seed(2026)
-    mod = importlib.reload(importlib.import_module('bprmf'))
     dataset_dir = '/root/reference/data/movielens/ml-100k/'
     n_users, n_items, fold = 943, 1682, 0
-    reg, topN, split_method, eval_metrics, n_factors, batch_size, negSample = .1, 10, 'cv', ['pre', 'recall', 'map', 'mrr', 'ndcg'], 100, 100, 1
+    topN, split_method, eval_metrics = 10, 'cv', ['pre', 'recall', 'map', 'mrr', 'ndcg']
     trasR = lil_matrix(matBinarize(loadSparseR(n_users, n_items, dataset_dir + 'ratings__%d_tra.txt' % (fold + 1)), 3))
     tstsR = lil_matrix(matBinarize(loadSparseR(n_users, n_items, dataset_dir + 'ratings__%d_tst.txt' % (fold + 1)), 3))
-    sampler = Sampler(trasR=trasR, n_neg=negSample, batch_size=batch_size)
-    m = mod.BPRMF(n_users, n_items, topN, split_method, eval_metrics, reg, n_factors, batch_size, max_iter)
+    if which == 'bpr':
+        reg, n_factors, batch_size, negSample = .1, 100, 100, 1                                   # testbprmf.py:21-30
+        mod = importlib.reload(importlib.import_module('bprmf'))
+        sampler = Sampler(trasR=trasR, n_neg=negSample, batch_size=batch_size)
+        m = mod.BPRMF(n_users, n_items, topN, split_method, eval_metrics, reg, n_factors, batch_size, max_iter)
+        hyper = dict(n_factors=n_factors, batch_size=batch_size, n_neg=negSample, reg=reg, lr=0.1, topN=topN, max_iter=max_iter)
+        fname = 'e2e_refgraph_golden.json'
+    elif which == 'gbpr':
+        gsize, rho, reg, topN, n_factors, batch_size, negSample = 1, .4, .01, 100, 100, 100, 5       # testgbprmf.py:23-32 (its douban
+        from sampler_gbpr import Sampler as GSampler                                                # set is absent: ml-100k instead)
+        mod = importlib.reload(importlib.import_module('gbprmf'))
+        sampler = GSampler(trasR, gsize, negSample, batch_size)
+        max_iter = 30                                                                               # GBPRMF's default
+        m = mod.GBPRMF(n_users, n_items, topN, rho, gsize, split_method, eval_metrics, reg, n_factors, batch_size)
+        hyper = dict(n_factors=n_factors, batch_size=batch_size, n_neg=negSample, gsize=gsize, rho=rho, reg=reg, lr=0.1, topN=topN,
+                     max_iter=max_iter)
+        fname = 'e2e_gbpr_refgraph_golden.json'
+    elif which == 'wrmf':
+        weight, reg, negRatio, n_factors, batch_size = 2., .1, 1, 100, 100                          # basic/testwrmf.py:22-30
+        from sampler_rating import Sampler as RSampler
+        mod = importlib.reload(importlib.import_module('wrmf'))
+        sampler = RSampler(trasR, negRatio, batch_size)
+        m = mod.WRMF(n_users, n_items, topN, split_method, eval_metrics, weight, reg, n_factors, batch_size)
+        hyper = dict(n_factors=n_factors, batch_size=batch_size, negRatio=negRatio, weight=weight, reg=reg, lr=0.1, topN=topN,
+                     max_iter=max_iter)
+        fname = 'e2e_wrmf_refgraph_golden.json'
+    else:
+        margin, reg_cov, use_rank_weight, clip_norm, n_factors, batch_size, negSample = 1., 1., True, 1.0, 50, 50, 5   # testcml.py:26-34
+        mod = importlib.reload(importlib.import_module('cml'))
+        sampler = Sampler(trasR, n_neg=negSample, batch_size=batch_size)
+        m = mod.CML(n_users, n_items, topN, split_method, eval_metrics, reg_cov, margin, use_rank_weight, clip_norm, n_factors,
+                    batch_size, max_iter)
+        hyper = dict(n_factors=n_factors, batch_size=batch_size, n_neg=negSample, reg_cov=reg_cov, margin=margin,
+                     use_rank_weight=use_rank_weight, clip_norm=clip_norm, lr=0.1, topN=topN, max_iter=max_iter)
+        fname = 'e2e_cml_refgraph_golden.json'
     t0 = time.time()
     with contextlib.redirect_stdout(io.StringIO()) as log:
         scores = m.train(fold + 1, trasR, tstsR, sampler)
-    hist = []
+    hist, tail = [], []
+    kv = lambda txt: {x.split('=')[0]: float(x.split('=')[1]) for x in txt.split()}
     for line in log.getvalue().splitlines():
-        mt = re.search(r'iter=\s*(\d+):\s+TraLoss=([0-9.]+).*Tst@10:(.*)$', line)
+        mt = re.search(r'iter=\s*(\d+):\s+TraLoss=([0-9.]+).*Tst[@0-9]*:(.*?)(\s+timecost.*)?$', line)
         if mt:
-            hist.append(dict(epoch=int(mt.group(1)), TraLoss=float(mt.group(2)),
-                             **{kv.split('=')[0]: float(kv.split('=')[1]) for kv in mt.group(3).split()}))
+            hist.append(dict(epoch=int(mt.group(1)), TraLoss=float(mt.group(2)), **kv(mt.group(3))))
+            continue
+        mt = re.search(r'fold=\d+:\s+Tst@(\d+):(.*)$', line)
+        if mt:
+            tail.append(dict(topN=int(mt.group(1)), **kv(mt.group(2))))
     assert len(hist) == max_iter, len(hist)
-    json.dump(dict(model='BPRMF', source='reference bprmf.py + sampler_ranking.py + IOUtil/Util, run on oracle/tf1_shim',
-                   hyper=dict(n_factors=n_factors, batch_size=batch_size, n_neg=negSample, reg=reg, lr=0.1, topN=topN, max_iter=max_iter),
-                   nnz=int(trasR.nnz), final_scores=[float(x) for x in scores], history=hist),
-              open(os.path.join(OUT, 'e2e_refgraph_golden.json'), 'w'), indent=1)
-    print('e2e_refgraph_golden.json: %d epochs in %.0f s; epoch 10 / 20 / %d ndcg@10 %.4f / %.4f / %.4f, final %s'
-          % (max_iter, time.time() - t0, max_iter, hist[9]['ndcg'], hist[19]['ndcg'], hist[-1]['ndcg'], ['%.4f' % x for x in scores]))
+    json.dump(dict(model=type(m).__name__, source='reference %s + sampler_ranking.py + IOUtil/Util, run on oracle/tf1_shim' % mod.__name__,
+                   hyper=hyper, nnz=int(trasR.nnz), final_scores=[float(x) for x in scores], history=hist, tail=tail),
+              open(os.path.join(OUT, fname), 'w'), indent=1)
+    print('%s: %d epochs in %.0f s; epoch 10 / 20 / %d ndcg %.4f / %.4f / %.4f, final %s'
+          % (fname, max_iter, time.time() - t0, max_iter, hist[9]['ndcg'], hist[19]['ndcg'], hist[-1]['ndcg'], ['%.4f' % x for x in scores]))
 
 
 def main():
-    if len(sys.argv) > 1 and sys.argv[1] == 'e2e':
-        e2e_reference()
+    if len(sys.argv) > 1 and sys.argv[1].startswith('e2e'):
+        e2e_reference(dict(e2e='bpr').get(sys.argv[1], sys.argv[1][4:]))          # e2e | e2e-cml | e2e-gbpr | e2e-wrmf
         sys.stdout.flush()
         os._exit(0)                       # the reference sampler's producer thread never ends
     tuple_cases()

@@ -62,6 +62,69 @@ def test_bprmf_ml100k_50_epochs_matches_the_reference_driver_run(ml100k, capsys)
     m.close()
 
 
+def test_cml_ml100k_50_epochs_matches_the_reference_driver_run(ml100k, capsys):
+    """tests/golden/e2e_cml_refgraph_golden.json: pl/testcml.py's worker() body from the reference's own modules (loader,
+    binarisation, sampler thread, cml.CML.train() for 50 epochs + its topN = 5..1000 tail) on the TF1 stand-in.  The product,
+    built with the same constructor call, must follow the trajectory: NDCG@10 within +-0.02 at epochs 20 and 50, the last
+    epoch's mean loss within 5 %, and the tail (recommend once at 1000, score the prefixes: cml.py:203-211) within +-0.02
+    on ndcg / recall at every topN."""
+    import re
+    from collaborativefilteringusingtensorflow_b200 import CML
+    from collaborativefilteringusingtensorflow_b200.samplers.sampler_ranking import Sampler
+    gold = json.load(open(os.path.join(GOLDEN, 'e2e_cml_refgraph_golden.json')))
+    h = gold['hyper']
+    tra, tst = ml100k['tra'], ml100k['tst']
+    sampler = Sampler(tra, n_neg=h['n_neg'], batch_size=h['batch_size'], seed=11)
+    m = CML(943, 1682, h['topN'], 'cv', NAMES, h['reg_cov'], h['margin'], h['use_rank_weight'], h['clip_norm'], h['n_factors'],
+            h['batch_size'], seed=11)                                                                  # testcml.py:49
+    scores = m.train(1, tra, tst, sampler)
+    out = capsys.readouterr().out
+    rows = re.findall(r'iter=\s*(\d+):\s+TraLoss=([0-9.]+).*ndcg=([0-9.]+)', out)
+    assert len(rows) == h['max_iter'] == 50
+    ours = {int(e): (float(l), float(n)) for e, l, n in rows}
+    ref = {x['epoch']: (x['TraLoss'], x['ndcg']) for x in gold['history']}
+    for ep in (20, 50):
+        assert abs(ours[ep][1] - ref[ep][1]) < 0.02, (ep, ours[ep], ref[ep])
+    assert abs(ours[50][0] - ref[50][0]) < 0.05 * ref[50][0], (ours[50], ref[50])
+    tail = re.findall(r'fold=1:\s+Tst@(\d+):(.*)', out)
+    assert [int(t) for t, _ in tail] == [x['topN'] for x in gold['tail']] == [5, 10, 20, 50, 100, 200, 500, 1000]
+    for (t, txt), want in zip(tail, gold['tail']):
+        got = {kv.split('=')[0]: float(kv.split('=')[1]) for kv in txt.split()}
+        assert abs(got['ndcg'] - want['ndcg']) < 0.02 and abs(got['recall'] - want['recall']) < 0.02, (t, got, want)
+    assert abs(scores[NAMES.index('ndcg')] - gold['final_scores'][NAMES.index('ndcg')]) < 0.02
+    m.close()
+
+
+def test_gbpr_and_wrmf_ml100k_follow_the_reference_driver_runs(ml100k, capsys):
+    """e2e_gbpr_refgraph_golden.json / e2e_wrmf_refgraph_golden.json: the worker() bodies of pl/testgbprmf.py (its douban set
+    is absent: ml-100k) and basic/testwrmf.py from the reference's own modules (sampler_gbpr / sampler_rating threads, the
+    models' own train() for their default 30 / 50 epochs) on the TF1 stand-in.  Same constructor calls here; the last epoch's
+    ndcg / recall / pre within +-0.02 (mrr +-0.04), its mean training loss within 5 %."""
+    import re
+    from collaborativefilteringusingtensorflow_b200 import GBPRMF, WRMF
+    from collaborativefilteringusingtensorflow_b200.samplers import sampler_gbpr, sampler_rating
+    tra, tst = ml100k['tra'], ml100k['tst']
+    for kind in ('gbpr', 'wrmf'):
+        gold = json.load(open(os.path.join(GOLDEN, 'e2e_%s_refgraph_golden.json' % kind)))
+        h = gold['hyper']
+        if kind == 'gbpr':
+            m = GBPRMF(943, 1682, h['topN'], h['rho'], h['gsize'], 'cv', NAMES, h['reg'], h['n_factors'], h['batch_size'], seed=5)  # testgbprmf.py:48
+            sampler = sampler_gbpr.Sampler(tra, h['gsize'], h['n_neg'], h['batch_size'], seed=5)
+        else:
+            m = WRMF(943, 1682, h['topN'], 'cv', NAMES, h['weight'], h['reg'], h['n_factors'], h['batch_size'], seed=5)             # testwrmf.py:43
+            sampler = sampler_rating.Sampler(tra, h['negRatio'], h['batch_size'], seed=5)
+        scores = m.train(1, tra, tst, sampler)
+        out = capsys.readouterr().out
+        rows = re.findall(r'iter=\s*(\d+):\s+TraLoss=([0-9.]+)', out)
+        assert len(rows) == h['max_iter'] == len(gold['history'])
+        last = gold['history'][-1]
+        assert abs(float(rows[-1][1]) - last['TraLoss']) < 0.05 * last['TraLoss'], (kind, rows[-1], last)
+        got, want = dict(zip(NAMES, scores)), dict(zip(NAMES, gold['final_scores']))
+        for k, tol in (('ndcg', 0.02), ('recall', 0.02), ('pre', 0.02), ('mrr', 0.04)):
+            assert abs(got[k] - want[k]) < tol, (kind, k, got, want)
+        m.close()
+
+
 def test_cml_gbpr_wrmf_train_on_ml100k(ml100k):
     from collaborativefilteringusingtensorflow_b200 import CML, GBPRMF, WRMF
     from collaborativefilteringusingtensorflow_b200.samplers import sampler_gbpr, sampler_ranking, sampler_rating
