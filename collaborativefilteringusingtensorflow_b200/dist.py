@@ -481,15 +481,34 @@ class DistributedTrainer(object):
         q = ids // P
         return (ids - q * P) * self._rep['L'] + q
 
-    def _step_chunk_replica(self, pairs, negs, B, want_loss):
+    def _wait_replica_comm(self):
+        """The all-gather of the previous minibatch's updated item rows (and the zeroing of the gradient table) run on the
+        communication stream; whoever reads the item table or starts the next fused step on the compute stream waits here."""
+        if getattr(self, '_comm_pending', False):
+            self.torch.cuda.current_stream(self.eng.device).wait_stream(self._comm)
+            self._comm_pending = False
+
+    def _step_chunk_replica(self, pairs, negs, B, want_loss, defer_gather_wait=False):
+        """``defer_gather_wait``: leave the all-gather of the updated rows running on the communication stream when this
+        call returns (step() does that between consecutive minibatches; the next call, or step()'s end, waits for it)."""
         torch, eng, P = self.torch, self.eng, self.world
+        import os
         if self._rep is None:
             self._setup_replica()
         rep = self._rep
         L = rep['L']
         pairs, negs = eng._as_i32(pairs), eng._as_i32(negs)
         W = int(negs.shape[1])
-        stream = torch.cuda.current_stream(eng.device).cuda_stream
+        main = torch.cuda.current_stream(eng.device)
+        stream = main.cuda_stream
+        # Two streams (CF_REPLICA_OVERLAP=0 puts everything back on one): the reduce-scatter of the item gradients starts when
+        # the fused step kernel has finished (cf_step_args.event_after_step) and runs under the staged apply of the USER rows;
+        # the gradient table is zeroed and the updated rows are all-gathered on the communication stream while the compute
+        # stream goes on to whatever precedes the next fused step.  The phase timer synchronises after every phase anyway.
+        overlap = P > 1 and self.phase_ms is None and os.environ.get('CF_REPLICA_OVERLAP', '1') != '0'
+        if overlap and getattr(self, '_comm', None) is None:
+            self._comm, self._comm_pending = torch.cuda.Stream(eng.device), False
+            self._ev_step, self._ev_rs, self._ev_applied = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         ev = self._tick('', None)
         if P > 1:
             pairs = torch.stack([pairs[:, 0], self._replica_rows(pairs[:, 1])], 1).contiguous()
@@ -499,11 +518,23 @@ class DistributedTrainer(object):
         # red.added into the dense table (row = the item's row in the replica)
         a.V, a.n_items = _lib.ptr(rep['V']), P * L
         a.pairs, a.negs, a.gradV = _lib.ptr(pairs), _lib.ptr(negs), _lib.ptr(rep['g'])
+        self._wait_replica_comm()                   # the replica is complete and the gradient table is zero again
+        if overlap:
+            self._ev_step.record(main)              # (creates the handle; the library re-records it after the fused step kernel)
+            a.event_after_step = self._ev_step.cuda_event
         _lib.check(self.lib.cf_train_steps(a, stream), 'cf_train_steps')
         ev = self._tick('k_count + k_step + k_apply_staged', ev)
         g_mine = rep['g']
         if P > 1:       # every rank receives the summed gradients of ITS shard
-            self.ex.dist.reduce_scatter_tensor(rep['gblk'], rep['g'], group=self.ex.group)
+            if overlap:
+                self._comm.wait_event(self._ev_step)
+                with torch.cuda.stream(self._comm):
+                    self.ex.dist.reduce_scatter_tensor(rep['gblk'], rep['g'], group=self.ex.group)
+                    self._ev_rs.record(self._comm)
+                    rep['g'].zero_()                # after the reduce-scatter has read it; under the owner apply
+                main.wait_event(self._ev_rs)
+            else:
+                self.ex.dist.reduce_scatter_tensor(rep['gblk'], rep['g'], group=self.ex.group)
             g_mine = rep['gblk']
         ev = self._tick('reduce-scatter of the dense item gradients (NCCL)', ev)
         ap = _lib.ApplyArgs()
@@ -518,8 +549,17 @@ class DistributedTrainer(object):
             eng._full_clip(stream)
         ev = self._tick('owner apply (k_apply_dense on the shard)', ev)
         if P > 1:
-            self.ex.dist.all_gather_into_tensor(rep['V'], rep['V'][self.rank * L:(self.rank + 1) * L], group=self.ex.group)
-            rep['g'].zero_()
+            if overlap:
+                self._ev_applied.record(main)
+                self._comm.wait_event(self._ev_applied)
+                with torch.cuda.stream(self._comm):
+                    self.ex.dist.all_gather_into_tensor(rep['V'], rep['V'][self.rank * L:(self.rank + 1) * L], group=self.ex.group)
+                self._comm_pending = True
+                if not defer_gather_wait:
+                    self._wait_replica_comm()
+            else:
+                self.ex.dist.all_gather_into_tensor(rep['V'], rep['V'][self.rank * L:(self.rank + 1) * L], group=self.ex.group)
+                rep['g'].zero_()
         ev = self._tick('all-gather of the updated item rows (NCCL) + zeroing of the gradient table', ev)
         self.launches += 3 + 1
         self.occurrences += B * (1 + W)
@@ -641,12 +681,60 @@ class DistributedTrainer(object):
         by owner) runs on a side stream while minibatch k computes."""
         torch = self.torch
         B = self.sampler.batch_size
-        chunk = self.sampler.next_chunk(n_minibatches)
         main = torch.cuda.current_stream(self.eng.device)
+        W_known = getattr(self.sampler, 'n_neg', None)
+        import os
+        if (W_known is not None and n_minibatches > 1 and self.phase_ms is None and self.step_events is None
+                and self._use_replica(B, int(W_known)) and os.environ.get('CF_REPLICA_OVERLAP', '1') != '0'):
+            # 'replicate' transport, pipelined: minibatch k + 1 is SAMPLED on the side stream while the updated item rows of
+            # minibatch k are all-gathered on the communication stream (the sampler waits for the owner apply of k, i.e. it
+            # starts with the all-gather: both are idle time for the SMs otherwise).  A batch is a pure function of (seed,
+            # epoch, batch index), so the minibatches are the ones next_chunk(n) would return; the index buffers live in a
+            # ring of three persistent slots inside the sampler (models/_base.py::_epoch does the same on one GPU).
+            side, sampler = self.side, self.sampler
+            ring = 3 if hasattr(sampler, 'ring_slot') else 0
+            used = [None] * 3
+            side.wait_stream(main)
+
+            def sample(j, after=None):
+                if after is not None:
+                    side.wait_event(after)
+                with torch.cuda.stream(side):
+                    if ring:
+                        sampler.ring_slot = j % ring
+                        if used[j % ring] is not None:
+                            side.wait_event(used[j % ring])
+                    try:
+                        arrays = sampler.next_chunk(1)
+                    finally:
+                        if ring:
+                            sampler.ring_slot = None
+                    done = torch.cuda.Event()
+                    done.record(side)
+                return arrays, done
+            nxt = sample(0)
+            out = []
+            for k in range(n_minibatches):
+                arrays, done = nxt
+                main.wait_event(done)
+                if not ring:
+                    for t in arrays:
+                        if t is not None:
+                            t.record_stream(main)
+                out.append(self._step_chunk_replica(arrays[0], arrays[1], B, want_loss, defer_gather_wait=k + 1 < n_minibatches))
+                if ring:
+                    used[k % ring] = torch.cuda.Event()
+                    used[k % ring].record(main)
+                if k + 1 < n_minibatches:
+                    nxt = sample(k + 1, after=self._ev_applied)
+            main.wait_stream(side)
+            return torch.cat(out) if want_loss else None
+        chunk = self.sampler.next_chunk(n_minibatches)
         if self._use_replica(B, int(chunk[1].shape[1])):
             out = []
             for k in range(n_minibatches):
-                out.append(self._step_chunk_replica(chunk[0][k * B:(k + 1) * B], chunk[1][k * B:(k + 1) * B], B, want_loss))
+                out.append(self._step_chunk_replica(chunk[0][k * B:(k + 1) * B], chunk[1][k * B:(k + 1) * B], B, want_loss,
+                                                    defer_gather_wait=k + 1 < n_minibatches))
                 if self.step_events is not None:
                     ev = torch.cuda.Event(enable_timing=True)
                     ev.record(main)

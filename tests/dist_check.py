@@ -189,6 +189,49 @@ def main():
         if rank == 0:
             print('%s user-sharded top-%d (gathered item table) == all-gather merge on every rank: %s' % (kind, K, bool(flag.item())))
             ok &= bool(flag.item())
+    # ---- the trainer's own step(): sampler-driven minibatches.  With the 'replicate' transport step() is a three-stream
+    # pipeline (sampling of k + 1 and the all-gather of k beside the compute stream); it must give what the same minibatches
+    # give one after the other on one stream (CF_REPLICA_OVERLAP=0), up to the order of the atomic adds
+    if transport in ('replicate', 'auto'):
+        from collaborativefilteringusingtensorflow_b200.samplers.sampler_ranking import Sampler
+        nu_l, ni, d, B, W = 500, 1203, 128, 1024, 3
+        rs = np.random.default_rng(100 + rank)
+        R_local = lil_matrix((nu_l, ni), dtype=np.float32)
+        cells = rs.choice(nu_l * ni, 9 * B + 17, replace=False)
+        R_local[cells // ni, cells % ni] = 1
+        results = []
+        for overlap in ('1', '0', '0'):
+            os.environ['CF_REPLICA_OVERLAP'] = overlap
+            mm = CML(nu_l, item_shard_rows(ni, world, rank), n_factors=d, reg_cov=1.0, margin=1.0, verbose=False, seed=50 + rank, device=dev)
+            sm = Sampler(R_local, n_neg=W, batch_size=B, seed=9 + rank)
+            trs = DistributedTrainer(mm, sm, ni, world, rank, item_transport='replicate')
+            losses = torch.cat([trs.step(4), trs.step(1), trs.step(3)])          # 8 minibatches, pipelined inside each call
+            mm.engine.check_flags()
+            results.append((mm.state_dict(), losses.clone()))
+            trs.close()
+        os.environ.pop('CF_REPLICA_OVERLAP')
+        # Eight CML minibatches apart, two runs of the SAME schedule already differ by the order of their float atomics
+        # (item-row gradients red.added into the dense table; rank-weighted coefficients ~10 with heavy cancellation).  That
+        # noise is measured -- the one-stream form run twice -- and the pipelined run must be no farther from a one-stream
+        # run than 10x that (+ a floor of 1e-5 relative; N = 2 on B200: ratios 0.3 .. 2.6): a stale or half-gathered item row would be
+        # off by 1e-2 and more.
+        (a_, la), (b_, lb), (c_, lc) = results
+        good, report = True, []
+        for k in ('U', 'V', 'accU', 'accV'):
+            noise = float(((b_[k] - c_[k]).abs() / (c_[k].abs() + 1e-2)).max())
+            diff = float(((a_[k] - b_[k]).abs() / (b_[k].abs() + 1e-2)).max())
+            report.append('%s %.2e (noise %.2e)' % (k, diff, noise))
+            good &= diff <= 10 * noise + 1e-5 and diff < 1e-2
+        nl, dl = float(((lb - lc).abs() / lc.abs()).max()), float(((la - lb).abs() / lb.abs()).max())
+        report.append('loss %.2e (noise %.2e)' % (dl, nl))
+        good &= dl <= 10 * nl + 1e-8 and dl < 1e-5
+        print('rank %d pipelined step() vs one stream, max relative distance: %s' % (rank, ', '.join(report)))
+        flag = torch.tensor([int(good)], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print('replicate: pipelined step() (sampling + all-gather beside the compute stream) == one stream on every rank: %s'
+                  % bool(flag.item()))
+            ok &= bool(flag.item())
     # ---- metrics: users sharded, sums all-reduced (every rank gets the global values)
     from collaborativefilteringusingtensorflow_b200.dist import DistributedALS, distributed_evaluate
     from collaborativefilteringusingtensorflow_b200.metrics.ranking import evaluateCV
