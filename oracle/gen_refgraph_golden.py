@@ -7,6 +7,8 @@ minibatches, same hyper-parameters) the tables, Adagrad accumulators and losses 
 filter, its own metrics/ranking.py).  A fake sampler feeds the recorded minibatches through ``next_batch()``.
 
     python oracle/gen_refgraph_golden.py        (in the build container; /root/reference does not travel to the GPU box)
+    python oracle/gen_refgraph_golden.py e2e | e2e-cml | e2e-gbpr | e2e-wrmf     the drivers' worker() bodies on ml-100k (minutes each)
+    python oracle/gen_refgraph_golden.py coef                                     PRIGP / CPLR preprocessing on ml-100k
 
 It also prints how far these results are from the torch-autograd RESTATEMENT that generated step_golden.npz: both must
 agree to float32 rounding, which pins the restatement (and with it oracle/steps.py) to the reference's graph code."""
@@ -297,7 +299,51 @@ def e2e_reference(which='bpr', max_iter=50):
           % (fname, max_iter, time.time() - t0, max_iter, hist[9]['ndcg'], hist[19]['ndcg'], hist[-1]['ndcg'], ['%.4f' % x for x in scores]))
 
 
+def coef_cases(topK=5):
+    """The numpy preprocessing inside the reference's PRIGP / CPLR classes (prigp.py:64-90, cplr_u.py:66-97: user-user
+    cosine similarities, the topK most similar users per user through np.argsort, the coefficient matrix).  The classes
+    cannot be constructed without TensorFlow, so this is the first time the reference's own methods run: the stand-in
+    builds the instance, ``__calsim__`` / ``__topk__`` / ``__calcoef__`` are called as train() calls them (prigp.py:173-175)
+    on ml-100k fold 1 -> tests/golden/coef_refgraph_golden.npz (kept neighbours + similarities of every user, a flag where
+    the cut falls inside a tie -- np.argsort's order is undefined there --, row sums and sample rows of both coefficient
+    matrices, fp64 checksums)."""
+    sys.path.insert(1, os.path.join(REF, 'utils'))
+    from IOUtil import loadSparseR
+    from Util import matBinarize
+    trasR = lil_matrix(matBinarize(loadSparseR(943, 1682, '/root/reference/data/movielens/ml-100k/ratings__1_tra.txt'), 3))
+    out = dict(topK=np.int64(topK))
+    rows = np.array([0, 1, 7, 100, 400, 640, 941, 942])
+    for name, module, cls in (('prigp', 'prigp', 'PRIGP'), ('cplr', 'cplr_u', 'CPLR')):
+        tf.reset_default_graph()
+        mod = importlib.reload(importlib.import_module(module))
+        m = getattr(mod, cls)(943, 1682, topK=topK, n_factors=8)
+        sim = m.__calsim__(trasR)
+        kept = m.__topk__(sim.copy())
+        setattr(m, '_%s__simMat' % cls, kept)
+        coef = np.asarray(m.__calcoef__(trasR).todense())
+        srt = np.sort(sim, axis=1)[:, ::-1]
+        idx = np.full((943, topK), -1, np.int64)
+        val = np.zeros((943, topK), sim.dtype)
+        for u in range(943):
+            nz = np.nonzero(kept[u])[0]
+            nz = nz[np.lexsort((nz, -kept[u, nz]))]
+            idx[u, :len(nz)], val[u, :len(nz)] = nz, kept[u, nz]
+        out.update({name + '/nbr_idx': idx, name + '/nbr_sim': val, name + '/tie_at_cut': srt[:, topK - 1] == srt[:, topK],
+                    name + '/sim_rows': sim[rows], name + '/sim_checksum': np.float64(sim.astype(np.float64).sum()),
+                    name + '/sim_sq_checksum': np.float64((sim.astype(np.float64) ** 2).sum()),
+                    name + '/coef_rows': coef[rows], name + '/coef_row_sums': coef.sum(1), name + '/coef_col_sums': coef.sum(0),
+                    name + '/coef_nnz': np.int64((coef != 0).sum())})
+        print('%-6s %s: similarities %s %s, %d users with a tie at the cut, coefficient matrix nnz %d, sum %.6f'
+              % (name, cls, sim.shape, sim.dtype, int(out[name + '/tie_at_cut'].sum()), int(out[name + '/coef_nnz']), coef.sum()))
+    out['rows'] = rows
+    np.savez_compressed(os.path.join(OUT, 'coef_refgraph_golden.npz'), **out)
+    print('coef_refgraph_golden.npz: %d arrays' % len(out))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == 'coef':
+        coef_cases()
+        return
     if len(sys.argv) > 1 and sys.argv[1].startswith('e2e'):
         e2e_reference(dict(e2e='bpr').get(sys.argv[1], sys.argv[1][4:]))          # e2e | e2e-cml | e2e-gbpr | e2e-wrmf
         sys.stdout.flush()
