@@ -9,6 +9,7 @@ filter, its own metrics/ranking.py).  A fake sampler feeds the recorded minibatc
     python oracle/gen_refgraph_golden.py        (in the build container; /root/reference does not travel to the GPU box)
     python oracle/gen_refgraph_golden.py e2e | e2e-cml | e2e-gbpr | e2e-wrmf     the drivers' worker() bodies on ml-100k (minutes each)
     python oracle/gen_refgraph_golden.py coef                                     PRIGP / CPLR preprocessing on ml-100k
+    python oracle/gen_refgraph_golden.py rating-e2e                               testmf.py / testsvd.py bodies on ml-100k
 
 It also prints how far these results are from the torch-autograd RESTATEMENT that generated step_golden.npz: both must
 agree to float32 rounding, which pins the restatement (and with it oracle/steps.py) to the reference's graph code."""
@@ -25,6 +26,7 @@ from scipy.sparse import lil_matrix
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = '/root/reference/src'
 sys.path.insert(0, os.path.join(ROOT, 'oracle', 'tf1_shim'))
+sys.path.insert(1, ROOT)
 for p in ('models/pl/models', 'models/basic/models', 'metrics', 'samplers'):
     sys.path.insert(1, os.path.join(REF, p))
 import tensorflow as tf          # the stand-in  # noqa: E402
@@ -340,7 +342,80 @@ def coef_cases(topK=5):
     print('coef_refgraph_golden.npz: %d arrays' % len(out))
 
 
+def rating_e2e():
+    """The worker() bodies of basic/testmf.py:28-48 and basic/testsvd.py:28-48 on ml-100k fold 1 from the reference's own
+    modules (IOUtil.loadSparseR, sampler_rating.Sampler with negRatio 0 -- its batches are the file-order slices, shuffled
+    inside the slice only, so the run is deterministic up to summation order --, MF.train() / SVD.train() on the TF1
+    stand-in), started from the initial tables of the numpy oracle's runs (tests/golden/rating_golden.json: mf_ml100k,
+    svd_ml100k_golden.json) and run for as many epochs -> tests/golden/rating_e2e_refgraph_golden.json: per-epoch mean loss
+    and full-precision rmse / mae / mse (the reference's metrics/rating.py), next to the distance to the oracle's epochs."""
+    from oracle.steps import truncated_normal
+    sys.path.insert(1, os.path.join(REF, 'utils'))
+    from IOUtil import loadSparseR
+    from sampler_rating import Sampler
+    d = '/root/reference/data/movielens/ml-100k/'
+    n_users, n_items, fold = 943, 1682, 0
+    eval_metrics, reg, range_of_ratings = ['rmse', 'mae', 'mse'], .1, (1, 5)
+    trasR = loadSparseR(n_users, n_items, d + 'ratings__%d_tra.txt' % (fold + 1))
+    tra_tuple = np.array([(user, item, trasR[user, item]) for user, item in np.asarray(trasR.nonzero()).T])
+    tstsR = loadSparseR(n_users, n_items, d + 'ratings__%d_tst.txt' % (fold + 1))
+    tst_tuple = np.array([(user, item, tstsR[user, item]) for user, item in np.asarray(tstsR.nonzero()).T])
+    gold = dict(mf=json.load(open(os.path.join(OUT, 'rating_golden.json')))['mf_ml100k'],
+                svd=json.load(open(os.path.join(OUT, 'svd_ml100k_golden.json'))))
+    out = {}
+    for which in ('mf', 'svd'):
+        tf.reset_default_graph()
+        g = gold[which]
+        k, B, epochs = g['n_factors'], g['batch_size'], len(g['epochs'])
+        init = np.random.default_rng(g['init_seed'])
+        tf.INIT_OVERRIDE['user_embed'] = truncated_normal(init, (n_users, k))
+        tf.INIT_OVERRIDE['item_embed'] = truncated_normal(init, (n_items, k))
+        mod = importlib.reload(importlib.import_module(which))
+        sampler = Sampler(trasR=trasR, negRatio=.0, batch_size=B)
+        if which == 'mf':
+            m = mod.MF(n_users, n_items, eval_metrics, range_of_ratings, reg, k, B, epochs)                 # testmf.py:43
+        else:
+            tf.INIT_OVERRIDE['kernel'] = truncated_normal(init, (k, k))
+            m = mod.SVD(n_users, n_items, eval_metrics, range_of_ratings, reg, k, B, epochs)                # testsvd.py:40
+        losses, scores_log = [], []
+        real_run, real_eval = tf.Session.run, mod.evaluate
+
+        def logging_run(self, fetches, feed_dict=None):
+            o = real_run(self, fetches, feed_dict)
+            if isinstance(fetches, tuple) and len(fetches) == 2:
+                losses.append(float(o[1]))
+            return o
+
+        def logging_eval(*a, **kw):
+            sc = real_eval(*a, **kw)
+            scores_log.append([float(x) for x in sc])
+            return sc
+        tf.Session.run, mod.evaluate = logging_run, logging_eval
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                m.train(fold + 1, tra_tuple, tst_tuple, sampler)
+        finally:
+            tf.Session.run, mod.evaluate = real_run, real_eval
+        nb = len(tra_tuple) // B
+        assert len(losses) == nb * epochs and len(scores_log) == epochs
+        eps, worst = [], 0.0
+        for e in range(epochs):
+            row = dict(loss=float(np.mean(losses[e * nb:(e + 1) * nb])), **dict(zip(eval_metrics, scores_log[e])))
+            eps.append(row)
+            worst = max(worst, max(abs(row[k_] - g['epochs'][e][k_]) / abs(row[k_]) for k_ in row))
+        out[which] = dict(source='reference %s.py + sampler_rating.py + IOUtil, run on oracle/tf1_shim' % which, init_seed=g['init_seed'],
+                          n_factors=k, reg=reg, batch_size=B, range_of_ratings=list(range_of_ratings), epochs=eps,
+                          max_rel_distance_to_oracle_run=worst)
+        print('%-4s %d epochs of %d minibatches: rmse %s; max relative distance to the oracle run %.2e'
+              % (which, epochs, nb, ['%.4f' % r['rmse'] for r in eps], worst))
+    json.dump(out, open(os.path.join(OUT, 'rating_e2e_refgraph_golden.json'), 'w'), indent=1)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == 'rating-e2e':
+        rating_e2e()
+        sys.stdout.flush()
+        os._exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'coef':
         coef_cases()
         return

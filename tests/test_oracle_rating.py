@@ -83,3 +83,19 @@ def test_oracle_svd_evaluation_matches_the_reference_train_loop(name):
     tst = np.asarray(ev['tst'])
     pred = orc.svd_predict(z[name + '/step1/U'], z[name + '/step1/V'], z[name + '/step1/K'], tst[:, :2], ev['range_of_ratings'])
     np.testing.assert_allclose(orc.evaluate(tst[:, 2], pred, ev['metrics']), ev['scores'], rtol=1e-6)
+
+
+@pytest.mark.parametrize('which', ['mf', 'svd'])
+def test_oracle_ml100k_runs_equal_the_reference_driver_runs(which):
+    """tests/golden/rating_e2e_refgraph_golden.json: the worker() bodies of basic/testmf.py / testsvd.py from the reference's
+    OWN modules (loader, sampler_rating with negRatio 0 = deterministic file-order minibatches, MF.train() / SVD.train() on
+    the TF1 stand-in; oracle/gen_refgraph_golden.py rating-e2e), started from the oracle runs' initial tables.  The numpy
+    oracle's epochs (rating_golden.json: mf_ml100k, svd_ml100k_golden.json -- the ones the GPU tests follow epoch by epoch)
+    must be the reference's: mean loss and rmse / mae / mse of every epoch to 1e-5 relative (measured: 7.5e-9 / 5.5e-6)."""
+    ref = json.load(open(os.path.join(GOLDEN, 'rating_e2e_refgraph_golden.json')))[which]
+    ours = (json.load(open(os.path.join(GOLDEN, 'rating_golden.json')))['mf_ml100k'] if which == 'mf'
+            else json.load(open(os.path.join(GOLDEN, 'svd_ml100k_golden.json'))))
+    assert len(ref['epochs']) == len(ours['epochs']) and ref['n_factors'] == ours['n_factors'] and ref['batch_size'] == ours['batch_size']
+    for a, b in zip(ref['epochs'], ours['epochs']):
+        for k in ('loss', 'rmse', 'mae', 'mse'):
+            assert b[k] == pytest.approx(a[k], rel=1e-5), (which, k, a, b)
