@@ -262,6 +262,23 @@ def e2e_reference(which='bpr', max_iter=50):
         hyper = dict(n_factors=n_factors, batch_size=batch_size, n_neg=negSample, gsize=gsize, rho=rho, reg=reg, lr=0.1, topN=topN,
                      max_iter=max_iter)
         fname = 'e2e_gbpr_refgraph_golden.json'
+    elif which in ('prigp', 'cplr'):
+        # pl/testprigp.py:21-45 / pl/testcplr_u.py:21-47: these train() build their own sampler (sampler_prigp /
+        # sampler_uitj_ranking threads) from the coefficient matrix of the preprocessing; no sampler argument
+        topN, n_factors = 100, 100
+        if which == 'prigp':
+            topK, alpha, reg, batch_size = 5, 10, .1, 1000
+            mod = importlib.reload(importlib.import_module('prigp'))
+            m = mod.PRIGP(n_users, n_items, topK, topN, split_method, eval_metrics, alpha, reg, n_factors, batch_size)
+            hyper = dict(topK=topK, alpha=alpha, reg=reg, n_factors=n_factors, batch_size=batch_size, lr=0.1, topN=topN, max_iter=max_iter)
+        else:
+            topK, reg, alpha, beta, gamma, batch_size = 200, .1, 1., 1., 1., 100
+            mod = importlib.reload(importlib.import_module('cplr_u'))
+            m = mod.CPLR(n_users, n_items, topK, topN, split_method, eval_metrics, alpha, beta, gamma, reg, n_factors, batch_size)
+            hyper = dict(topK=topK, alpha=alpha, beta=beta, gamma=gamma, reg=reg, n_factors=n_factors, batch_size=batch_size, lr=0.1,
+                         topN=topN, max_iter=max_iter)
+        sampler = None
+        fname = 'e2e_%s_refgraph_golden.json' % which
     elif which == 'wrmf':
         weight, reg, negRatio, n_factors, batch_size = 2., .1, 1, 100, 100                          # basic/testwrmf.py:22-30
         from sampler_rating import Sampler as RSampler
@@ -282,7 +299,7 @@ def e2e_reference(which='bpr', max_iter=50):
         fname = 'e2e_cml_refgraph_golden.json'
     t0 = time.time()
     with contextlib.redirect_stdout(io.StringIO()) as log:
-        scores = m.train(fold + 1, trasR, tstsR, sampler)
+        scores = m.train(fold + 1, trasR, tstsR, sampler) if sampler is not None else m.train(fold + 1, trasR, tstsR)
     hist, tail = [], []
     kv = lambda txt: {x.split('=')[0]: float(x.split('=')[1]) for x in txt.split()}
     for line in log.getvalue().splitlines():
