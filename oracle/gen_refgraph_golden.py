@@ -10,6 +10,7 @@ filter, its own metrics/ranking.py).  A fake sampler feeds the recorded minibatc
     python oracle/gen_refgraph_golden.py e2e | e2e-cml | e2e-gbpr | e2e-wrmf     the drivers' worker() bodies on ml-100k (minutes each)
     python oracle/gen_refgraph_golden.py coef                                     PRIGP / CPLR preprocessing on ml-100k
     python oracle/gen_refgraph_golden.py rating-e2e                               testmf.py / testsvd.py bodies on ml-100k
+    python oracle/gen_refgraph_golden.py signatures                               constructor / train() / sampler signatures
 
 It also prints how far these results are from the torch-autograd RESTATEMENT that generated step_golden.npz: both must
 agree to float32 rounding, which pins the restatement (and with it oracle/steps.py) to the reference's graph code."""
@@ -428,7 +429,44 @@ def rating_e2e():
     json.dump(out, open(os.path.join(OUT, 'rating_e2e_refgraph_golden.json'), 'w'), indent=1)
 
 
+def signatures():
+    """The drop-in boundary, read off the reference itself: inspect.signature of every model class' constructor and train(),
+    of every sampler's constructor and next_batch() -- possible for the TensorFlow-importing modules now that the stand-in
+    lets them be imported -> tests/golden/signatures_golden.json (parameter names in order + their defaults)."""
+    import inspect
+    sys.path.insert(1, os.path.join(REF, 'utils'))
+
+    def sig(f):
+        out = []
+        for n, p_ in inspect.signature(f).parameters.items():
+            if n == 'self':
+                continue
+            d = None if p_.default is inspect.Parameter.empty else p_.default
+            out.append([n, p_.default is not inspect.Parameter.empty, list(d) if isinstance(d, tuple) else d])
+        return out
+    out = {}
+    for module, cls in (('bprmf', 'BPRMF'), ('cml', 'CML'), ('gbprmf', 'GBPRMF'), ('prigp', 'PRIGP'), ('cplr_u', 'CPLR'),
+                        ('wrmf', 'WRMF'), ('mf', 'MF'), ('svd', 'SVD'), ('pop', 'PopRank'), ('itemcf', 'ItemCF'), ('usercf', 'UserCF')):
+        mod = importlib.import_module(module)
+        c = getattr(mod, cls)
+        out['models/%s.%s' % (module, cls)] = dict(init=sig(c.__init__), train=sig(c.train),
+                                                  close=hasattr(c, 'close'))
+    for module in ('sampler_ranking', 'sampler_uij_ranking', 'sampler_gbpr', 'sampler_rating', 'sampler_prigp', 'sampler_uitj_ranking'):
+        c = importlib.import_module(module).Sampler
+        out['samplers/%s.Sampler' % module] = dict(init=sig(c.__init__), next_batch=sig(c.next_batch))
+    for module, names in (('ranking', ('evaluateCV', 'evaluateLOOV')), ('rating', ('evaluate',)), ('IOUtil', ('loadSparseR',)),
+                          ('Util', ('matBinarize',))):
+        mod = importlib.import_module(module)
+        for n in names:
+            out['%s.%s' % (module, n)] = dict(call=sig(getattr(mod, n)))
+    json.dump(out, open(os.path.join(OUT, 'signatures_golden.json'), 'w'), indent=1)
+    print('signatures_golden.json: %d entries' % len(out))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == 'signatures':
+        signatures()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'rating-e2e':
         rating_e2e()
         sys.stdout.flush()
