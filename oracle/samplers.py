@@ -5,6 +5,8 @@ Restates the ``__sample_function__`` bodies of
   /root/reference/src/samplers/sampler_uij_ranking.py:22-38  -> uij[B,3] int64
   /root/reference/src/samplers/sampler_gbpr.py:25-43         -> (+ group[B,G] int64, np.random.choice w/ replacement)
   /root/reference/src/samplers/sampler_rating.py:22-39       -> [B + int(B*negRatio), 3] float64, positives in file order
+  /root/reference/src/samplers/sampler_prigp.py:22-52        -> uijtk[B,5] int64 (collaborative pair t, k from the coefficient rows)
+  /root/reference/src/samplers/sampler_uitj_ranking.py:22-40 -> (uitj[B,4] int64, coefs[B,2] float64)
 as plain generators over a seeded ``numpy.random.Generator`` (the reference is unseeded and runs in a
 producer thread; distribution, shapes, dtypes and the epoch structure are what is restated).
 
@@ -99,6 +101,94 @@ def rating_batches(trasR, negRatio=0.0, batch_size=500, seed=0):
             batch = batch.copy()
             rng.shuffle(batch)                                      # :38 in-batch shuffle
             yield batch
+
+
+def _coef_rows(coefMat):
+    """The coefficient matrix (prigp.py:83-90 / cplr_u.py:89-97) as sorted CSR arrays without stored zeros."""
+    csr = coefMat.tocsr().astype(np.float64)
+    csr.eliminate_zeros()
+    csr.sort_indices()
+    return csr
+
+
+def _choice_in_rows(rng, indptr, indices, users):
+    """np.random.choice(list(row_set[u]), 1)[0] for every u: uniform over the row's stored columns; also the CSR slot."""
+    lo = indptr[users].astype(np.int64)
+    n = (indptr[users + 1] - indptr[users]).astype(np.int64)
+    slot = lo + np.minimum((rng.random(len(users)) * n).astype(np.int64), n - 1)
+    return indices[slot].astype(np.int64), slot
+
+
+def prigp_batches(trasR, coefMat, batch_size=100, seed=0):
+    """sampler_prigp.py:22-52.  Per epoch the positives are shuffled and cut into whole batches (:24-25); per row: j uniform
+    outside the user's positives (:30-34); without coefficients (t, k) = (i, j) (:36); otherwise t uniform in the user's
+    coefficient row (:38) and k uniform outside it (:39-41); when the row holds more than one DISTINCT value and a standard
+    normal draw is below nnz(row) / n_items (:43 -- np.random.randn, not rand, so the branch is taken with probability
+    Phi(nnz / n_items) >= 1/2), k is redrawn inside the row until its coefficient differs from t's (:44-46) and the pair is
+    ordered so that t carries the larger coefficient (:47-48)."""
+    rng = np.random.default_rng(seed)
+    pairs = _pairs_of(trasR).astype(np.int64)
+    is_pos = _posmask_fn(trasR)
+    coef = _coef_rows(coefMat)
+    in_coef = _posmask_fn(coef)
+    indptr, indices, vals = coef.indptr, coef.indices, coef.data
+    n_items = trasR.shape[1]
+    nnz_row = np.diff(indptr)
+    distinct = np.array([len(set(vals[indptr[u]:indptr[u + 1]])) for u in range(coef.shape[0])])   # user_coefItemset_vals
+    while True:
+        rng.shuffle(pairs)
+        for b in range(int(len(pairs) / batch_size)):
+            pb = pairs[b * batch_size:(b + 1) * batch_size]
+            u, i = pb[:, 0], pb[:, 1]
+            j = _draw_negs(rng, is_pos, u, n_items, (len(pb),)).astype(np.int64)
+            t, k = i.copy(), j.copy()
+            has = np.nonzero(nnz_row[u] > 0)[0]
+            if len(has):
+                uh = u[has]
+                th, slot_t = _choice_in_rows(rng, indptr, indices, uh)
+                kh = _draw_negs(rng, in_coef, uh, n_items, (len(has),)).astype(np.int64)
+                inside = (distinct[uh] > 1) & (rng.standard_normal(len(has)) < nnz_row[uh] / float(n_items))
+                todo = np.nonzero(inside)[0]
+                slot_k = np.zeros(len(has), dtype=np.int64)
+                while len(todo):                                                   # :44-46
+                    kh[todo], slot_k[todo] = _choice_in_rows(rng, indptr, indices, uh[todo])
+                    todo = todo[vals[slot_t[todo]] == vals[slot_k[todo]]]
+                swap = inside & (vals[slot_t] < vals[np.where(inside, slot_k, slot_t)])
+                th[swap], kh[swap] = kh[swap], th[swap]
+                t[has], k[has] = th, kh
+            yield np.stack([u, i, j, t, k], axis=1)
+
+
+def uitj_batches(trasR, coefMat, batch_size=1000, seed=0):
+    """sampler_uitj_ranking.py:22-40.  ui[u] = the positives, ut[u] = coefficient columns that are not positives (:12-13).
+    Every row draws its user uniformly among those with positives, collaborative items and room for a negative (:27-28),
+    i uniform in ui[u], t uniform in ut[u], j uniform outside both (:29-33); coefs = (coef[u, i], coef[u, t]) (:35)."""
+    rng = np.random.default_rng(seed)
+    n_users, n_items = trasR.shape
+    tra = trasR.tocsr().astype(np.float64)
+    tra.eliminate_zeros()
+    tra.sort_indices()
+    coef = _coef_rows(coefMat)
+    collab = coef - coef.multiply(tra != 0)                # ut: the coefficient entries outside the positives
+    collab = collab.tocsr()
+    collab.eliminate_zeros()
+    collab.sort_indices()
+    is_pos, is_collab = _posmask_fn(tra), _posmask_fn(collab)
+    npos, ncol = np.diff(tra.indptr), np.diff(collab.indptr)
+    eligible = np.nonzero((npos > 0) & (ncol > 0) & (npos + ncol < n_items))[0]
+    dense_lookup = coef.todok() if n_users * n_items > 50_000_000 else None
+    coef_dense = None if dense_lookup is not None else coef.toarray()
+    taken = lambda uu, jj: is_pos(uu, jj) | is_collab(uu, jj)
+    while True:
+        u = eligible[(rng.random(batch_size) * len(eligible)).astype(np.int64)]
+        i, _ = _choice_in_rows(rng, tra.indptr, tra.indices, u)
+        t, _ = _choice_in_rows(rng, collab.indptr, collab.indices, u)
+        j = _draw_negs(rng, taken, u, n_items, (batch_size,)).astype(np.int64)
+        if coef_dense is not None:
+            c = np.stack([coef_dense[u, i], coef_dense[u, t]], axis=1)
+        else:
+            c = np.array([[dense_lookup.get((a, b), 0.0), dense_lookup.get((a, d), 0.0)] for a, b, d in zip(u, i, t)])
+        yield np.stack([u, i, t, j], axis=1).astype(np.int64), c.astype(np.float64)
 
 
 # ---------------------------------------------------------------- invariant checkers

@@ -77,3 +77,63 @@ def test_preprocessing_equals_the_reference_methods(ml100k, name, weighted):
     else:
         assert np.array_equal(coef[rows], g[name + '/coef_rows'])
         assert np.array_equal(coef.sum(1), g[name + '/coef_row_sums']) and np.array_equal(coef.sum(0), g[name + '/coef_col_sums'])
+
+
+def test_tuple_samplers_follow_the_reference_samplers(ml100k):
+    """oracle.samplers.prigp_batches / uitj_batches against the contracts of sampler_prigp.py:22-52 and
+    sampler_uitj_ranking.py:22-40 (shapes, dtypes, set memberships, the coefficient order of the collaborative pair, one pass
+    over the shuffled positives per epoch, Phi(nnz / n_items) as the rate of the inside-the-row branch)."""
+    from scipy.sparse import csr_matrix
+    from oracle import samplers, train_tuples
+    tra = ml100k['tra']
+    ni = tra.shape[1]
+    pos = np.asarray(tra.todense()) > 0
+    coef = train_tuples.coefficients(tra, 5, False)
+    B, nb = 1000, int(tra.nnz / 1000)
+    gen = samplers.prigp_batches(tra, csr_matrix(coef), B, seed=4)
+    epoch = np.concatenate([next(gen) for _ in range(nb)])
+    assert epoch.dtype == np.int64 and epoch.shape == (nb * B, 5)
+    u, i, j, t, k = epoch.T
+    assert pos[u, i].all() and not pos[u, j].any()
+    assert len(set(zip(u.tolist(), i.tolist()))) == nb * B                      # an epoch draws every positive at most once
+    has = (coef != 0).sum(1)[u] > 0
+    assert np.array_equal(t[~has], i[~has]) and np.array_equal(k[~has], j[~has])   # :36: no coefficients -> (t, k) = (i, j)
+    assert (coef[u[has], t[has]] != 0).all()
+    inside = has & (coef[u, k] != 0)
+    assert (coef[u[inside], t[inside]] > coef[u[inside], k[inside]]).all()       # :44-48: other value, larger one first
+    distinct = np.array([len(set(row[row != 0])) for row in coef])
+    can = has & (distinct[u] > 1)
+    from math import erf, sqrt
+    want = np.mean([0.5 * (1 + erf(x / sqrt(2))) for x in ((coef != 0).sum(1)[u[can]] / float(ni))])
+    assert abs(inside[can].mean() - want) < 0.01, (inside[can].mean(), want)     # :43 draws a NORMAL against nnz / n_items
+    # CPLR: rows normalised by their mean, (u, i, t, j) with t a coefficient column outside the positives
+    coefw = train_tuples.coefficients(tra, 200, True)
+    nz = coefw != 0
+    np.testing.assert_allclose(coefw.sum(1)[nz.any(1)] / nz.sum(1)[nz.any(1)], 1.0, rtol=1e-12)     # cplr_u.py:193-196
+    uitj, c = next(samplers.uitj_batches(tra, csr_matrix(coefw), 5000, seed=4))
+    assert uitj.dtype == np.int64 and uitj.shape == (5000, 4) and c.dtype == np.float64 and c.shape == (5000, 2)
+    u, i, t, j = uitj.T
+    assert pos[u, i].all() and (nz[u, t] & ~pos[u, t]).all() and not (pos[u, j] | nz[u, j]).any()
+    assert np.array_equal(c[:, 0], coefw[u, i]) and np.array_equal(c[:, 1], coefw[u, t])
+    assert len(np.unique(u)) > 800                                               # users drawn uniformly, not by their degree
+
+
+@pytest.mark.parametrize('which', ['prigp', 'cplr'])
+def test_oracle_training_follows_the_reference_driver_runs(ml100k, which):
+    """tests/golden/e2e_prigp_refgraph_golden.json / e2e_cplr_refgraph_golden.json: the worker() bodies of pl/testprigp.py and
+    pl/testcplr_u.py run from the reference's own modules (their preprocessing, their sampler threads, their train()) on the
+    TF-1.x stand-in.  The oracle's end-to-end restatement (oracle/train_tuples.py: its own preprocessing, samplers and steps;
+    another seed, the reference is unseeded) follows the same trajectory: after 5 and 10 epochs the mean training loss within
+    3 % and pre / recall / ndcg @100 within 0.02 (the full 50 epochs, tools/oracle_tuple_trajectories.py ->
+    profiles/r5_oracle_tuple_trajectories.log: last-epoch loss within 0.8 %, ndcg within 0.007)."""
+    from oracle import train_tuples
+    gold = json.load(open(os.path.join(GOLDEN, 'e2e_%s_refgraph_golden.json' % which)))
+    assert ml100k['tra'].nnz == gold['nnz']
+    hist = train_tuples.run(which, ml100k['tra'], ml100k['tst'], gold['hyper'], seed=3, epochs=10, eval_epochs={5, 10})
+    ref = {x['epoch']: x for x in gold['history']}
+    assert [x['epoch'] for x in hist] == [5, 10]
+    for x in hist:
+        r = ref[x['epoch']]
+        assert abs(x['TraLoss'] - r['TraLoss']) < 0.03 * r['TraLoss'], (x, r)
+        for k in ('pre', 'recall', 'ndcg'):
+            assert abs(x[k] - r[k]) < 0.02, (k, x, r)
