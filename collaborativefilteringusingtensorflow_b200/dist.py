@@ -873,8 +873,9 @@ def _gather_item_rows(t, n_items_global, world, group=None):
     P = int(world)
     L = (int(n_items_global) + P - 1) // P
     send = t if t.shape[0] == L else torch.cat([t, torch.zeros((L - t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)])
-    got = torch.empty((P, L) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    got = torch.empty((P * L,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)      # rank p's rows at [p * L, (p + 1) * L)
     dist.all_gather_into_tensor(got, send.contiguous(), group=group)
+    got = got.view((P, L) + tuple(t.shape[1:]))
     return got.transpose(0, 1).reshape((L * P,) + tuple(t.shape[1:]))[:n_items_global].contiguous()   # item l * P + p sits at [p][l]
 
 
@@ -882,20 +883,11 @@ def gather_item_table(engine, n_items_global, world, rank, group=None):
     """The row-sharded item table (local row j = global item j * world + rank) all-gathered into the full
     [n_items_global, ld] table in item order (and the item bias, if the model has one).  10 M items x 512 B = 5 GB: a
     fraction of one B200's 180 GB, which is what makes the user-sharded evaluation below possible."""
-    torch = _lib.require_cuda()
-    import torch.distributed as dist
     P = int(world)
     if P == 1:
         return engine.V, engine.b
-    L = (int(n_items_global) + P - 1) // P
-
-    def gather(t):
-        send = t if t.shape[0] == L else torch.cat([t, torch.zeros((L - t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)])
-        got = torch.empty((P, L) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(got, send.contiguous(), group=group)
-        return got.transpose(0, 1).reshape((L * P,) + tuple(t.shape[1:]))[:n_items_global].contiguous()   # item l * P + p sits at [p][l]
-    V = gather(engine.V)
-    b = gather(engine.b) if getattr(engine, 'b', None) is not None else None
+    V = _gather_item_rows(engine.V, n_items_global, P, group)
+    b = _gather_item_rows(engine.b, n_items_global, P, group) if getattr(engine, 'b', None) is not None else None
     return V, b
 
 

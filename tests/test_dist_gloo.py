@@ -102,3 +102,86 @@ def test_single_rank_exchange_is_identity():
     rows = ex.fetch(plan, shard)
     assert torch.equal(rows[plan.occ_local.to(torch.int64)][..., 0], ids.to(torch.float32))
     assert torch.equal(ex.push(plan, rows), rows)
+
+
+def _layout_worker(rank, world, port, n_items, ld, q):
+    """Host-side layout arithmetic of the N > 1 evaluation / 'replicate' / ALS paths on CPU tensors over gloo.  The product is
+    CUDA-only (`_lib.require_cuda()` raises here); these functions only index and call collectives, so the TEST hands them
+    torch itself -- nothing of this patch exists outside this process."""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import types
+        from collaborativefilteringusingtensorflow_b200 import _lib, dist as D
+        from collaborativefilteringusingtensorflow_b200.sparse import DeviceCSR
+        _lib.require_cuda = lambda: torch
+        n_local = D.item_shard_rows(n_items, world, rank)
+        row_of = lambda ids: ids.to(torch.float32)[:, None] * 10 + torch.arange(ld, dtype=torch.float32)[None, :] * 0.001
+        shard = row_of(torch.arange(n_local) * world + rank)          # local row j = global item j * world + rank
+        # -- the gathered item table of the user-sharded evaluation: item order, also when world does not divide n_items
+        full = D._gather_item_rows(shard, n_items, world)
+        assert full.shape == (n_items, ld) and torch.equal(full, row_of(torch.arange(n_items)))
+        bias = D._gather_item_rows(shard[:, 0].contiguous(), n_items, world)
+        assert torch.equal(bias, row_of(torch.arange(n_items))[:, 0])
+        # -- the 'replicate' transport's replica: shard after shard, the engine's own table a VIEW of its block
+        eng = types.SimpleNamespace(V=shard.clone(), ld=ld, n_items=n_local, device=torch.device('cpu'))
+        ex = types.SimpleNamespace(dist=dist, group=None)
+        tr = types.SimpleNamespace(torch=torch, eng=eng, world=world, rank=rank, n_items_global=n_items, ex=ex)
+        D.DistributedTrainer._setup_replica(tr)
+        rep, L = tr._rep['V'], tr._rep['L']
+        assert L == (n_items + world - 1) // world and rep.shape == (world * L, ld) and tr._rep['g'].shape == rep.shape
+        ids = torch.randperm(n_items, generator=torch.Generator().manual_seed(5))
+        assert torch.equal(rep[D.DistributedTrainer._replica_rows(tr, ids)], row_of(ids))
+        assert eng.V.shape == (n_local, ld) and eng.V.data_ptr() == rep[rank * L:].data_ptr()      # no copy: a view of the block
+        eng.V[0, 0] = -7.0
+        assert float(rep[rank * L, 0]) == -7.0
+        # every replica row is either one item's row or padding of a short shard (stays zero, never addressed)
+        used = torch.zeros(world * L, dtype=torch.bool)
+        used[D.DistributedTrainer._replica_rows(tr, torch.arange(n_items))] = True
+        assert int(used.sum()) == n_items and bool((rep[~used] == 0).all())
+        # -- 'auto' takes the replica exactly when a rank's minibatch holds >= 2 x n_items item occurrences (sizes only: the
+        #    same answer on every rank without a collective)
+        for B, W, want in ((n_items, 1, True), (n_items - 1, 1, False), (n_items // 3 + 1, 5, True), (1, 1, False)):
+            t2 = types.SimpleNamespace(_replicate=None, world=world, n_items_global=n_items, device_side=True)
+            assert D.DistributedTrainer._use_replica(t2, B, W) is want and t2.device_side is (not want)
+        # -- the mask rows of the item-sharded top-K: owned items only, in local ids
+        g = torch.Generator().manual_seed(11)
+        dense = torch.rand(7, n_items, generator=g) < 0.05
+        r, c = torch.nonzero(dense, as_tuple=True)
+        indptr = torch.zeros(8, dtype=torch.int64)
+        indptr[1:] = torch.cumsum(dense.sum(1), 0)
+        sub = DeviceCSR(indptr, c.to(torch.int32), r.to(torch.int32), None, (7, n_items))
+        loc = D.shard_mask_csr(sub, world, rank)
+        assert loc.shape == (7, n_local)
+        back = torch.zeros(7, n_local, dtype=torch.bool)
+        back[loc.rows.to(torch.int64), loc.indices.to(torch.int64)] = True
+        assert torch.equal(back, dense[:, rank::world])
+        assert torch.equal(loc.indptr[1:] - loc.indptr[:-1], dense[:, rank::world].sum(1))
+        # -- ALS row ranges: disjoint, ordered, covering, a rank may be empty
+        for n in (1, world - 1, world, 10 * world + 1, n_items):
+            rng_ = [D.DistributedALS.row_range(n, world, k) for k in range(world)]
+            assert rng_[0][0] == 0 and rng_[-1][1] == n and all(a[1] == b[0] for a, b in zip(rng_, rng_[1:])) and all(lo <= hi for lo, hi in rng_)
+        q.put((rank, 'ok'))
+    except Exception:
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,n_items', [(2, 1001), (3, 1001), (3, 999), (4, 10)])
+def test_sharded_table_layouts_over_gloo(world, n_items):
+    """dist._gather_item_rows, DistributedTrainer._setup_replica / _replica_rows / _use_replica, shard_mask_csr and
+    DistributedALS.row_range (items `item % P`, users by range) on world_size 2 / 3 / 4."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_layout_worker, args=(r, world, port, n_items, 6, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in res:
+        assert msg == 'ok', 'rank %d: %s' % (rank, msg)
