@@ -684,7 +684,7 @@ class DistributedTrainer(object):
         main = torch.cuda.current_stream(self.eng.device)
         W_known = getattr(self.sampler, 'n_neg', None)
         import os
-        if (W_known is not None and n_minibatches > 1 and self.phase_ms is None and self.step_events is None
+        if (self.world > 1 and W_known is not None and n_minibatches > 1 and self.phase_ms is None and self.step_events is None
                 and self._use_replica(B, int(W_known)) and os.environ.get('CF_REPLICA_OVERLAP', '1') != '0'):
             # 'replicate' transport, pipelined: minibatch k + 1 is SAMPLED on the side stream while the updated item rows of
             # minibatch k are all-gathered on the communication stream (the sampler waits for the owner apply of k, i.e. it

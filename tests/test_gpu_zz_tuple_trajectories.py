@@ -1,0 +1,47 @@
+"""PRIGP / CPLR on ml-100k for the reference drivers' 50 epochs against the trajectories of the reference's own driver bodies
+(tests/golden/e2e_prigp_refgraph_golden.json, e2e_cplr_refgraph_golden.json).  Collected after every other GPU file: written
+when the round's GPU minutes were spent, so it has not run on a B200 yet; the oracle-side twin runs on the host
+(tests/test_oracle_tuples.py::test_oracle_training_follows_the_reference_driver_runs)."""
+import json
+import os
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+@pytest.mark.parametrize('cls', ['PRIGP', 'CPLR'])
+def test_ml100k_50_epochs_follow_the_reference_driver_runs(ml100k, cls, capsys):
+    """tests/golden/e2e_prigp_refgraph_golden.json / e2e_cplr_refgraph_golden.json: the worker() bodies of pl/testprigp.py:21-45
+    (topK 5, alpha 10, reg .1, 100 factors, batches of 1000) and pl/testcplr_u.py:21-47 (topK 200, alpha = beta = gamma = 1,
+    reg .1, batches of 100) run from the reference's own modules -- its preprocessing inside the classes, its sampler threads,
+    its train() for 50 epochs -- on the TF-1.x stand-in (oracle/gen_refgraph_golden.py e2e-prigp | e2e-cplr).  The product gets
+    the same positional constructor call and the same train(fold, trasR, tstsR) call and must follow the trajectory: NDCG@100
+    and recall@100 within 0.02 at epochs 20 and 50, the last epoch's mean training loss within 5 % (the reference's samplers
+    are unseeded; the CPU oracle's own end-to-end run lands within 0.8 % / 0.007 of it:
+    profiles/r5_oracle_tuple_trajectories.log, tests/test_oracle_tuples.py)."""
+    import re
+    import collaborativefilteringusingtensorflow_b200 as pkg
+    names = ['pre', 'recall', 'map', 'mrr', 'ndcg']
+    gold = json.load(open(os.path.join(GOLDEN, 'e2e_%s_refgraph_golden.json' % cls.lower())))
+    h = gold['hyper']
+    tra, tst = ml100k['tra'], ml100k['tst']
+    assert tra.nnz == gold['nnz']
+    if cls == 'PRIGP':                                                                      # testprigp.py:41
+        m = pkg.PRIGP(943, 1682, h['topK'], h['topN'], 'cv', names, h['alpha'], h['reg'], h['n_factors'], h['batch_size'], seed=13)
+    else:                                                                                   # testcplr_u.py:43
+        m = pkg.CPLR(943, 1682, h['topK'], h['topN'], 'cv', names, h['alpha'], h['beta'], h['gamma'], h['reg'], h['n_factors'],
+                     h['batch_size'], seed=13)
+    scores = m.train(1, tra, tst)
+    out = capsys.readouterr().out
+    rows = re.findall(r'iter=\s*(\d+):\s+TraLoss=([0-9.]+).*recall=([0-9.]+).*ndcg=([0-9.]+)', out)
+    assert len(rows) == h['max_iter'] == 50
+    ours = {int(e): (float(l), float(r), float(n)) for e, l, r, n in rows}
+    ref = {x['epoch']: (x['TraLoss'], x['recall'], x['ndcg']) for x in gold['history']}
+    for ep in (20, 50):
+        assert abs(ours[ep][1] - ref[ep][1]) < 0.02 and abs(ours[ep][2] - ref[ep][2]) < 0.02, (ep, ours[ep], ref[ep])
+    assert abs(ours[50][0] - ref[50][0]) < 0.05 * ref[50][0], (ours[50], ref[50])
+    got, want = dict(zip(names, scores)), dict(zip(names, gold['final_scores']))
+    assert abs(got['pre'] - want['pre']) < 0.02 and abs(got['mrr'] - want['mrr']) < 0.05, (got, want)
+    m.close()
