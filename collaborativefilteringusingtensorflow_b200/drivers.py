@@ -1,7 +1,7 @@
 """The reference's experiment drivers for the hot-path models, as one module.
 
 Mirrors reference src/models/pl/testbprmf.py:19-125, testcml.py:19-102, testgbprmf.py:19-113, testprigp.py:17-109,
-testcplr_u.py:17-126, src/models/basic/testwrmf.py:19-96, testicf.py:14-115, testucf.py:14-116 and (rating prediction, `mf` /
+testcplr_u.py:17-126, src/models/basic/testwrmf.py:19-96, testicf.py:14-115, testucf.py:14-116, testpop.py:14-115 and (rating prediction, `mf` /
 `svd`) src/models/basic/testmf.py:14-78, testsvd.py:14-79: the same module-level hyper-parameters, the same per-fold worker (load
 ``ratings__<fold>_tra.txt`` / ``_tst.txt``, binarise with ``rating > 3``, build the sampler and the model, train, print the
 fold's scores) and the same ``ave`` / ``std`` summary.  The reference wraps every fold in a ``multiprocessing.Pool`` only
@@ -16,6 +16,7 @@ from scipy.sparse import lil_matrix
 
 from .models.basic.models.itemcf import ItemCF
 from .models.basic.models.mf import MF
+from .models.basic.models.pop import PopRank
 from .models.basic.models.svd import SVD
 from .models.basic.models.usercf import UserCF
 from .models.basic.models.wrmf import WRMF
@@ -43,6 +44,7 @@ HYPER = {
     'cplr': dict(topK=200, reg=.1, topN=100, alpha=1., beta=1., gamma=1., n_factors=100, batch_size=100),         # testcplr_u.py:21-33
     'itemcf': dict(topK=5, topN=100),                                                                             # testicf.py:18-22
     'usercf': dict(topK=5, topN=100),                                                                             # testucf.py:18-22
+    'pop': dict(topN=100),                                                                                        # testpop.py:17
 }
 
 
@@ -104,8 +106,11 @@ def worker(model_name, fold, n_users, n_items, dataset_dir, max_iter=None, seed=
         sampler = sampler_rating.Sampler(trasR, h['negRatio'], h['batch_size'], seed=seed or 0)
         model = WRMF(n_users, n_items, h['topN'], split_method, eval_metrics, h['weight'], h['reg'], h['n_factors'],
                      h['batch_size'], **it, **kw)
-    elif model_name in ('itemcf', 'usercf'):      # testicf.py:37-38: no sampler, no epochs
-        model = (ItemCF if model_name == 'itemcf' else UserCF)(n_users, n_items, h['topK'], h['topN'], split_method, eval_metrics)
+    elif model_name in ('itemcf', 'usercf', 'pop'):      # testicf.py:37-38, testpop.py:33-34: no sampler, no epochs
+        if model_name == 'pop':
+            model = PopRank(n_users, n_items, h['topN'], split_method, eval_metrics)
+        else:
+            model = (ItemCF if model_name == 'itemcf' else UserCF)(n_users, n_items, h['topK'], h['topN'], split_method, eval_metrics)
         scores = model.train(fold + 1, trasR, tstsR)
         print(dataset_dir.split('/')[-2] + '@%d:' % (fold + 1),
               ','.join(['%s' % m for m in eval_metrics]) + '@%d=' % h['topN'] + ','.join(['%.6f' % s for s in scores]))
