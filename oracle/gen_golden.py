@@ -404,6 +404,30 @@ def gen_sampler(bins):
     print('sampler_golden.json:', json.dumps(out)[:400], '...')
 
 
+def gen_tuple_samplers(bins):
+    """The reference's own sampler_prigp.Sampler / sampler_uitj_ranking.Sampler (numpy + a producer thread each) run live on
+    ml-100k fold 1 with the coefficient matrices of the drivers' settings (testprigp.py: topK 5, neighbour counts;
+    testcplr_u.py: topK 200, similarity sums divided by the row mean) -- the matrices come from the oracle's preprocessing,
+    which is pinned to the reference's own (coef_refgraph_golden.npz).  One PRIGP epoch (44 batches of 1000) and 442 CPLR
+    batches of 100 -> tests/golden/tuple_sampler_golden.json."""
+    import sampler_prigp, sampler_uitj_ranking   # noqa
+    from scipy.sparse import lil_matrix
+    from oracle import samplers as chk
+    from oracle import train_tuples
+    tra = bins['tra']
+    np.random.seed(2026)
+    out = {}
+    coef = train_tuples.coefficients(tra, 5, False)
+    s = sampler_prigp.Sampler(tra, lil_matrix(coef), 1000)
+    nb = int(tra.nnz / 1000)
+    out['prigp'] = chk.tuple_sampler_stats(tra, coef, [s.next_batch() for _ in range(nb)], 'prigp')
+    coefw = train_tuples.coefficients(tra, 200, True)
+    s = sampler_uitj_ranking.Sampler(tra, lil_matrix(coefw), 100)
+    out['cplr'] = chk.tuple_sampler_stats(tra, coefw, [s.next_batch() for _ in range(442)], 'cplr')
+    json.dump(out, open(os.path.join(OUT, 'tuple_sampler_golden.json'), 'w'), indent=1)
+    print('tuple_sampler_golden.json:', json.dumps(out))
+
+
 # ---------------------------------------------------------------- torch-autograd restatement of the TF graphs
 def _torch_models():
     import torch
@@ -557,7 +581,7 @@ if __name__ == '__main__':
         gen_svd()
     if 'tuples' in what:
         gen_tuples()
-    if what & {'ml100k', 'sampler', 'e2e', 'pop', 'cf'}:
+    if what & {'ml100k', 'sampler', 'e2e', 'pop', 'cf', 'tuple-samplers'}:
         nu, ni, bins = gen_ml100k(IOUtil, Util)
         if 'pop' in what:
             gen_pop(bins)
@@ -567,5 +591,7 @@ if __name__ == '__main__':
             gen_e2e(nu, ni, bins, ref_ranking)
         if 'sampler' in what:
             gen_sampler(bins)
+        if 'tuple-samplers' in what:
+            gen_tuple_samplers(bins)
     sys.stdout.flush()
     os._exit(0)      # the reference's sampler threads never stop (sampler_ranking.py:23)

@@ -220,3 +220,42 @@ def group_members_are_valid(trasR, items, group):
     is_pos = _posmask_fn(trasR)
     ib = np.broadcast_to(np.asarray(items).reshape(-1, 1), group.shape)
     return bool(is_pos(group.reshape(-1), ib.reshape(-1)).all())
+
+
+def tuple_sampler_stats(tra, coef, batches, kind):
+    """Distribution statistics of PRIGP (uijtk) / CPLR (uitj, coefs) batches: what tests compare between the reference's
+    samplers run live, the oracle's restatement and the device samplers.  ``coef``: dense float64 [n_users, n_items]."""
+    pos = np.asarray(tra.todense()) > 0
+    nz = coef != 0
+    ni = tra.shape[1]
+    if kind == 'prigp':
+        b = np.concatenate(batches)
+        u, i, j, t, k = b.T
+        has = nz.sum(1)[u] > 0
+        distinct = np.array([len(set(row[row != 0])) for row in coef])
+        can = has & (distinct[u] > 1)
+        inside = has & nz[u, k]
+        return dict(rows=int(len(b)), dtype=str(b.dtype), shape=list(batches[0].shape),
+                    pairs_positive=bool(pos[u, i].all()), j_not_positive=bool(not pos[u, j].any()),
+                    no_coef_rows_copy_ij=bool(np.array_equal(t[~has], i[~has]) and np.array_equal(k[~has], j[~has])),
+                    t_in_coef_row=bool(nz[u[has], t[has]].all()),
+                    inside_pairs_ordered=bool((coef[u[inside], t[inside]] > coef[u[inside], k[inside]]).all()),
+                    distinct_pairs=int(len(set(zip(u.tolist(), i.tolist())))),
+                    frac_rows_with_coef=float(has.mean()), inside_rate=float(inside[can].mean()),
+                    mean_coef_t_inside=float(coef[u[inside], t[inside]].mean()), mean_coef_k_inside=float(coef[u[inside], k[inside]].mean()),
+                    mean_coef_t_outside=float(coef[u[has & ~inside], t[has & ~inside]].mean()),
+                    frac_t_is_positive=float(pos[u[has], t[has]].mean()), mean_j=float(j.mean()) / ni,
+                    mean_k_outside=float(k[has & ~inside].mean()) / ni)
+    uitj = np.concatenate([x[0] for x in batches])
+    c = np.concatenate([x[1] for x in batches])
+    u, i, t, j = uitj.T
+    npos, ncol = pos.sum(1), (nz & ~pos).sum(1)
+    eligible = (npos > 0) & (ncol > 0) & (npos + ncol < ni)
+    return dict(rows=int(len(uitj)), dtype=str(uitj.dtype), coef_dtype=str(c.dtype), shape=list(batches[0][0].shape),
+                coef_shape=list(batches[0][1].shape), i_positive=bool(pos[u, i].all()),
+                t_collaborative=bool((nz[u, t] & ~pos[u, t]).all()), j_outside_both=bool(not (pos[u, j] | nz[u, j]).any()),
+                coefs_are_matrix_entries=bool(np.array_equal(c[:, 0], coef[u, i]) and np.array_equal(c[:, 1], coef[u, t])),
+                users_all_eligible=bool(eligible[u].all()), n_eligible=int(eligible.sum()),
+                distinct_users=int(len(np.unique(u))), mean_user_degree=float(npos[u].mean()),
+                mean_coef_i=float(c[:, 0].mean()), mean_coef_t=float(c[:, 1].mean()), mean_j=float(j.mean()) / ni)
+

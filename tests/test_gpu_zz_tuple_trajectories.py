@@ -45,3 +45,35 @@ def test_ml100k_50_epochs_follow_the_reference_driver_runs(ml100k, cls, capsys):
     got, want = dict(zip(names, scores)), dict(zip(names, gold['final_scores']))
     assert abs(got['pre'] - want['pre']) < 0.02 and abs(got['mrr'] - want['mrr']) < 0.05, (got, want)
     m.close()
+
+
+def test_device_tuple_samplers_match_the_reference_samplers_run_live(ml100k):
+    """tests/golden/tuple_sampler_golden.json (the reference's sampler_prigp.Sampler / sampler_uitj_ranking.Sampler run live,
+    oracle/gen_golden.py tuple-samplers): the device samplers (cf_sample_tuples), built with the reference's constructor
+    calls and read through next_batch(), give the same dtypes, shapes, invariants and distribution statistics; tolerances
+    twice those the oracle's samplers meet on the host (tests/test_oracle_tuples.py)."""
+    import numpy as np
+    from scipy.sparse import csr_matrix
+    from collaborativefilteringusingtensorflow_b200.samplers import sampler_prigp, sampler_uitj_ranking
+    from oracle import samplers as chk
+    from oracle import train_tuples
+    gold = json.load(open(os.path.join(GOLDEN, 'tuple_sampler_golden.json')))
+    tra = ml100k['tra']
+    coef = train_tuples.coefficients(tra, 5, False)                                   # testprigp.py: topK 5, neighbour counts
+    s = sampler_prigp.Sampler(tra, csr_matrix(coef), 1000, seed=21)
+    got, want = chk.tuple_sampler_stats(tra, coef, [s.next_batch() for _ in range(int(tra.nnz / 1000))], 'prigp'), gold['prigp']
+    for k, v in want.items():
+        if not isinstance(v, float):
+            assert got[k] == v, (k, got[k], v)
+    for k, tol in (('frac_rows_with_coef', 1e-12), ('inside_rate', 0.02), ('mean_coef_t_inside', 0.1), ('mean_coef_k_inside', 0.06),
+                   ('mean_coef_t_outside', 0.06), ('frac_t_is_positive', 0.02), ('mean_j', 0.02), ('mean_k_outside', 0.02)):
+        assert abs(got[k] - want[k]) <= tol, (k, got[k], want[k])
+    coefw = train_tuples.coefficients(tra, 200, True)                                 # testcplr_u.py: topK 200, row-normalised sums
+    coefw32 = coefw.astype(np.float32).astype(np.float64)                             # the device CSR holds float32 coefficients
+    s = sampler_uitj_ranking.Sampler(tra, csr_matrix(coefw), 100, seed=21)
+    got, want = chk.tuple_sampler_stats(tra, coefw32, [s.next_batch() for _ in range(442)], 'cplr'), gold['cplr']
+    for k, v in want.items():
+        if not isinstance(v, float):
+            assert got[k] == v, (k, got[k], v)
+    for k, tol in (('mean_user_degree', 2.0), ('mean_coef_i', 0.2), ('mean_coef_t', 0.04), ('mean_j', 0.02)):
+        assert abs(got[k] - want[k]) <= tol, (k, got[k], want[k])

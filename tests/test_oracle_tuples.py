@@ -137,3 +137,32 @@ def test_oracle_training_follows_the_reference_driver_runs(ml100k, which):
         assert abs(x['TraLoss'] - r['TraLoss']) < 0.03 * r['TraLoss'], (x, r)
         for k in ('pre', 'recall', 'ndcg'):
             assert abs(x[k] - r[k]) < 0.02, (k, x, r)
+
+
+def test_tuple_samplers_match_the_reference_samplers_run_live(ml100k):
+    """tests/golden/tuple_sampler_golden.json: the reference's own sampler_prigp.Sampler / sampler_uitj_ranking.Sampler (numpy
+    + their producer threads) run live on ml-100k fold 1 with the drivers' coefficient matrices (oracle/gen_golden.py
+    tuple-samplers): one PRIGP epoch, 442 CPLR batches.  The oracle's restatements give the same dtypes, shapes and
+    invariants and the same distribution: branch rates, mean coefficients of the drawn items, mean negatives, the users'
+    degree profile -- within a few standard errors of samples that size."""
+    from scipy.sparse import csr_matrix
+    from oracle import samplers, train_tuples
+    gold = json.load(open(os.path.join(GOLDEN, 'tuple_sampler_golden.json')))
+    tra = ml100k['tra']
+    coef = train_tuples.coefficients(tra, 5, False)
+    gen = samplers.prigp_batches(tra, csr_matrix(coef), 1000, seed=21)
+    got, want = samplers.tuple_sampler_stats(tra, coef, [next(gen) for _ in range(int(tra.nnz / 1000))], 'prigp'), gold['prigp']
+    for k, v in want.items():
+        if not isinstance(v, float):
+            assert got[k] == v, (k, got[k], v)
+    for k, tol in (('frac_rows_with_coef', 1e-12), ('inside_rate', 0.01), ('mean_coef_t_inside', 0.05), ('mean_coef_k_inside', 0.03),
+                   ('mean_coef_t_outside', 0.03), ('frac_t_is_positive', 0.01), ('mean_j', 0.01), ('mean_k_outside', 0.01)):
+        assert abs(got[k] - want[k]) <= tol, (k, got[k], want[k])
+    coefw = train_tuples.coefficients(tra, 200, True)
+    gen = samplers.uitj_batches(tra, csr_matrix(coefw), 100, seed=21)
+    got, want = samplers.tuple_sampler_stats(tra, coefw, [next(gen) for _ in range(442)], 'cplr'), gold['cplr']
+    for k, v in want.items():
+        if not isinstance(v, float):
+            assert got[k] == v, (k, got[k], v)
+    for k, tol in (('mean_user_degree', 1.0), ('mean_coef_i', 0.1), ('mean_coef_t', 0.02), ('mean_j', 0.01)):
+        assert abs(got[k] - want[k]) <= tol, (k, got[k], want[k])
