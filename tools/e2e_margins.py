@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Prints how close the ml-100k runs of tests/test_gpu_e2e.py (same constructor calls, same seeds) come to the reference
-driver trajectories in tests/golden/e2e*_refgraph_golden.json: the margins of those tests' +-0.02 / 3-5 % thresholds."""
+driver trajectories in tests/golden/e2e*_refgraph_golden.json: the margins of those tests' +-0.02 / 3-5 % thresholds (PRIGP /
+CPLR: tests/test_gpu_zz_tuple_trajectories.py)."""
 import contextlib
 import io
 import json
@@ -34,7 +35,8 @@ def main():
     d = ml100k()
     tra, tst = d['tra'], d['tst']
     for kind, fname in (('bpr', 'e2e_refgraph_golden.json'), ('cml', 'e2e_cml_refgraph_golden.json'),
-                        ('gbpr', 'e2e_gbpr_refgraph_golden.json'), ('wrmf', 'e2e_wrmf_refgraph_golden.json')):
+                        ('gbpr', 'e2e_gbpr_refgraph_golden.json'), ('wrmf', 'e2e_wrmf_refgraph_golden.json'),
+                        ('prigp', 'e2e_prigp_refgraph_golden.json'), ('cplr', 'e2e_cplr_refgraph_golden.json')):
         gold = json.load(open(os.path.join(GOLDEN, fname)))
         h = gold['hyper']
         if kind == 'bpr':
@@ -47,11 +49,18 @@ def main():
         elif kind == 'gbpr':
             m = pkg.GBPRMF(943, 1682, h['topN'], h['rho'], h['gsize'], 'cv', NAMES, h['reg'], h['n_factors'], h['batch_size'], seed=5)
             s = sampler_gbpr.Sampler(tra, h['gsize'], h['n_neg'], h['batch_size'], seed=5)
+        elif kind == 'prigp':     # the constructor calls and seeds of tests/test_gpu_zz_tuple_trajectories.py; train() builds the sampler
+            m = pkg.PRIGP(943, 1682, h['topK'], h['topN'], 'cv', NAMES, h['alpha'], h['reg'], h['n_factors'], h['batch_size'], seed=13)
+            s = None
+        elif kind == 'cplr':
+            m = pkg.CPLR(943, 1682, h['topK'], h['topN'], 'cv', NAMES, h['alpha'], h['beta'], h['gamma'], h['reg'], h['n_factors'],
+                         h['batch_size'], seed=13)
+            s = None
         else:
             m = pkg.WRMF(943, 1682, h['topN'], 'cv', NAMES, h['weight'], h['reg'], h['n_factors'], h['batch_size'], seed=5)
             s = sampler_rating.Sampler(tra, h['negRatio'], h['batch_size'], seed=5)
         with contextlib.redirect_stdout(io.StringIO()) as log:
-            scores = m.train(1, tra, tst, s)
+            scores = m.train(1, tra, tst, s) if s is not None else m.train(1, tra, tst)
         rows = re.findall(r'iter=\s*(\d+):\s+TraLoss=([0-9.]+).*ndcg=([0-9.]+)', log.getvalue())
         ours = {int(e): (float(l), float(n)) for e, l, n in rows}
         ref = {x['epoch']: (x['TraLoss'], x['ndcg']) for x in gold['history']}
