@@ -428,6 +428,33 @@ def gen_tuple_samplers(bins):
     print('tuple_sampler_golden.json:', json.dumps(out))
 
 
+def gen_pair_sampler_stats(bins):
+    """The reference's sampler_ranking / sampler_gbpr / sampler_rating run live on ml-100k fold 1 (their producer threads,
+    np.random seeded here): distribution statistics of one epoch (ranking: W = 5, B = 100; gbpr: G = 3, W = 5, B = 100) and of
+    200 rating batches (negRatio 1, B = 100) -> tests/golden/pair_sampler_stats_golden.json.  Batches hit by the reference's
+    view/shuffle race (see gen_sampler) are left out."""
+    import sampler_ranking, sampler_gbpr, sampler_rating   # noqa
+    from oracle import samplers as chk
+    tra = bins['tra']
+    np.random.seed(2026)
+    nb = int(tra.nnz / 100)
+    out = {}
+    s = sampler_ranking.Sampler(trasR=tra, n_neg=5, batch_size=100)
+    bs = [s.next_batch() for _ in range(nb)]
+    bs = [b for b in bs if chk.negatives_are_valid(tra, np.array(b[0])[:, 0], b[1]) and chk.pairs_are_positives(tra, np.array(b[0]))]
+    out['ranking'] = dict(batches_used=len(bs), **chk.pair_sampler_stats(tra, 'ranking', bs))
+    s = sampler_gbpr.Sampler(tra, 3, 5, 100)
+    bs = [s.next_batch() for _ in range(nb)]
+    bs = [b for b in bs if chk.negatives_are_valid(tra, np.array(b[0])[:, 0], b[1]) and chk.pairs_are_positives(tra, np.array(b[0]))
+          and chk.group_members_are_valid(tra, np.array(b[0])[:, 1], b[2])]
+    out['gbpr'] = dict(batches_used=len(bs), **chk.pair_sampler_stats(tra, 'gbpr', bs))
+    s = sampler_rating.Sampler(tra, 1, 100)
+    bs = [s.next_batch() for _ in range(200)]
+    out['rating'] = dict(batches_used=len(bs), **chk.pair_sampler_stats(tra, 'rating', bs))
+    json.dump(out, open(os.path.join(OUT, 'pair_sampler_stats_golden.json'), 'w'), indent=1)
+    print('pair_sampler_stats_golden.json:', json.dumps(out))
+
+
 # ---------------------------------------------------------------- torch-autograd restatement of the TF graphs
 def _torch_models():
     import torch
@@ -581,7 +608,7 @@ if __name__ == '__main__':
         gen_svd()
     if 'tuples' in what:
         gen_tuples()
-    if what & {'ml100k', 'sampler', 'e2e', 'pop', 'cf', 'tuple-samplers'}:
+    if what & {'ml100k', 'sampler', 'e2e', 'pop', 'cf', 'tuple-samplers', 'sampler-stats'}:
         nu, ni, bins = gen_ml100k(IOUtil, Util)
         if 'pop' in what:
             gen_pop(bins)
@@ -593,5 +620,7 @@ if __name__ == '__main__':
             gen_sampler(bins)
         if 'tuple-samplers' in what:
             gen_tuple_samplers(bins)
+        if 'sampler-stats' in what:
+            gen_pair_sampler_stats(bins)
     sys.stdout.flush()
     os._exit(0)      # the reference's sampler threads never stop (sampler_ranking.py:23)

@@ -259,3 +259,55 @@ def tuple_sampler_stats(tra, coef, batches, kind):
                 distinct_users=int(len(np.unique(u))), mean_user_degree=float(npos[u].mean()),
                 mean_coef_i=float(c[:, 0].mean()), mean_coef_t=float(c[:, 1].mean()), mean_j=float(j.mean()) / ni)
 
+
+def pair_sampler_stats(tra, kind, batches):
+    """Distribution statistics of the hot-path samplers' batches (a16, a18, a19): what tests compare between the reference's
+    samplers run live, the oracle's restatements and the device samplers.  ``batches`` as next_batch() returns them."""
+    nu, ni = tra.shape
+    pos = np.asarray(tra.todense()) > 0
+    deg_u, deg_i = pos.sum(1), pos.sum(0)
+    if kind in ('ranking', 'gbpr'):
+        pairs = np.concatenate([np.asarray(b[0]) for b in batches]).astype(np.int64)
+        negs = np.concatenate([np.asarray(b[1]) for b in batches]).astype(np.int64)
+        u, i = pairs[:, 0], pairs[:, 1]
+        out = dict(rows=int(len(pairs)), pairs_positive=bool(pos[u, i].all()), negatives_valid=bool(not pos[u[:, None], negs].any()),
+                   distinct_pairs=int(len(set(zip(u.tolist(), i.tolist())))),
+                   mean_neg=float(negs.mean()) / ni, frac_neg_low_half=float((negs < ni // 2).mean()),
+                   mean_neg_popularity=float(deg_i[negs].mean()), mean_pair_user_degree=float(deg_u[u].mean()))
+        if kind == 'gbpr':
+            grp = np.concatenate([np.asarray(b[2]) for b in batches]).astype(np.int64)
+            out.update(group_valid=bool(pos[grp, i[:, None]].all()), frac_group_is_user=float((grp == u[:, None]).mean()),
+                       expected_frac_group_is_user=float((1.0 / deg_i[i]).mean()), mean_group_user_degree=float(deg_u[grp].mean()))
+        return out
+    rows = np.concatenate([np.asarray(b) for b in batches])
+    uu, ii, rr = rows[:, 0].astype(np.int64), rows[:, 1].astype(np.int64), rows[:, 2]
+    neg = rr == 0
+    return dict(rows=int(len(rows)), batch_rows=int(len(batches[0])), positives_per_batch=int((np.asarray(batches[0])[:, 2] > 0).sum()),
+                positives_positive=bool(pos[uu[~neg], ii[~neg]].all()), negatives_valid=bool(not pos[uu[neg], ii[neg]].any()),
+                distinct_positive_pairs=int(len(set(zip(uu[~neg].tolist(), ii[~neg].tolist())))),
+                mean_neg_user=float(uu[neg].mean()) / nu, mean_neg_item=float(ii[neg].mean()) / ni,
+                mean_neg_user_degree=float(deg_u[uu[neg]].mean()), mean_neg_item_popularity=float(deg_i[ii[neg]].mean()))
+
+
+# tolerances for comparing two samples' pair_sampler_stats: >= 4 standard errors of the DIFFERENCE of two samples of one
+# ml-100k epoch (220 500 negatives) / 200 rating batches (20 000 negatives; item popularity there has std 41 -> SE 0.29 per
+# sample, user degree std 44 -> SE 0.31)
+PAIR_STATS_TOL = dict(mean_neg=0.005, frac_neg_low_half=0.006, mean_neg_popularity=0.5, mean_pair_user_degree=1.0,
+                      frac_group_is_user=0.003, expected_frac_group_is_user=0.001, mean_group_user_degree=1.0,
+                      mean_neg_user=0.012, mean_neg_item=0.012, mean_neg_user_degree=2.0, mean_neg_item_popularity=1.8)
+
+
+def compare_pair_stats(got, want, scale=1.0):
+    """None if ``got`` agrees with ``want`` (booleans and per-batch counts equal, every row a distinct positive pair,
+    distribution statistics within ``scale`` x PAIR_STATS_TOL), else a description of the first difference."""
+    for k, v in want.items():
+        if k in ('rows', 'batches_used', 'distinct_pairs', 'distinct_positive_pairs'):
+            continue
+        if isinstance(v, float):
+            if abs(got[k] - v) > scale * PAIR_STATS_TOL[k]:
+                return '%s: %r vs %r' % (k, got[k], v)
+        elif got[k] != v:
+            return '%s: %r vs %r' % (k, got[k], v)
+    if 'distinct_pairs' in got and got['distinct_pairs'] != got['rows']:
+        return 'an epoch repeats a pair'
+    return None

@@ -77,3 +77,22 @@ def test_device_tuple_samplers_match_the_reference_samplers_run_live(ml100k):
             assert got[k] == v, (k, got[k], v)
     for k, tol in (('mean_user_degree', 2.0), ('mean_coef_i', 0.2), ('mean_coef_t', 0.04), ('mean_j', 0.02)):
         assert abs(got[k] - want[k]) <= tol, (k, got[k], want[k])
+
+
+def test_device_pair_samplers_match_the_reference_samplers_run_live(ml100k):
+    """tests/golden/pair_sampler_stats_golden.json (sampler_ranking / sampler_gbpr / sampler_rating of the reference run live,
+    oracle/gen_golden.py sampler-stats): the device samplers of the hot path (cf_sample_ranking, cf_sample_rating), built with
+    the reference's constructor calls and read through next_batch(), draw from the same distributions -- one epoch each
+    (W = 5, B = 100; G = 3), 200 rating batches at negRatio 1; tolerances 1.5 x those the oracle's samplers meet on the host
+    (oracle.samplers.PAIR_STATS_TOL: >= 4 standard errors)."""
+    from collaborativefilteringusingtensorflow_b200.samplers import sampler_gbpr, sampler_ranking, sampler_rating
+    from oracle import samplers as chk
+    gold = json.load(open(os.path.join(GOLDEN, 'pair_sampler_stats_golden.json')))
+    tra = ml100k['tra']
+    nb = int(tra.nnz / 100)
+    s = sampler_ranking.Sampler(trasR=tra, n_neg=5, batch_size=100, seed=31)
+    assert chk.compare_pair_stats(chk.pair_sampler_stats(tra, 'ranking', [s.next_batch() for _ in range(nb)]), gold['ranking'], 1.5) is None
+    s = sampler_gbpr.Sampler(tra, 3, 5, 100, seed=32)
+    assert chk.compare_pair_stats(chk.pair_sampler_stats(tra, 'gbpr', [s.next_batch() for _ in range(nb)]), gold['gbpr'], 1.5) is None
+    s = sampler_rating.Sampler(tra, 1, 100, seed=34)
+    assert chk.compare_pair_stats(chk.pair_sampler_stats(tra, 'rating', [s.next_batch() for _ in range(200)]), gold['rating'], 1.5) is None

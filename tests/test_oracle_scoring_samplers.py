@@ -55,3 +55,25 @@ def test_oracle_samplers_invariants(ml100k):
     assert set(map(tuple, b[b[:, 2] > 0][:, :2].astype(int).tolist())) == set(map(tuple, samplers._pairs_of(tra)[:100].tolist()))
     u = next(samplers.uij_batches(tra, 100, seed=4))
     assert u.shape == (100, 3) and u.dtype == np.int64
+
+
+def test_oracle_samplers_match_the_reference_samplers_run_live(ml100k):
+    """tests/golden/pair_sampler_stats_golden.json: sampler_ranking / sampler_gbpr / sampler_rating of the reference run live
+    (oracle/gen_golden.py sampler-stats): one epoch each (W = 5, B = 100; G = 3) and 200 rating batches at negRatio 1.  The
+    oracle's restatements draw from the same distributions: negatives uniform over the non-positives (mean id, share in the
+    lower half of the catalogue, mean popularity), every positive once per epoch (so the pairs' mean user degree is
+    degree-weighted), group members uniform over the item's users WITH replacement and including the user itself at rate
+    mean(1 / deg(i)), rating negatives uniform over users (not degree-weighted)."""
+    gold = json.load(open(os.path.join(GOLDEN, 'pair_sampler_stats_golden.json')))
+    tra = ml100k['tra']
+    nb = int(tra.nnz / 100)
+    gen = samplers.ranking_batches(tra, 5, 100, seed=31)
+    assert samplers.compare_pair_stats(samplers.pair_sampler_stats(tra, 'ranking', [next(gen) for _ in range(nb)]), gold['ranking']) is None
+    gen = samplers.gbpr_batches(tra, 3, 5, 100, seed=32)
+    assert samplers.compare_pair_stats(samplers.pair_sampler_stats(tra, 'gbpr', [next(gen) for _ in range(nb)]), gold['gbpr']) is None
+    gen = samplers.rating_batches(tra, 1, 100, seed=33)
+    assert samplers.compare_pair_stats(samplers.pair_sampler_stats(tra, 'rating', [next(gen) for _ in range(200)]), gold['rating']) is None
+    # the check has teeth: degree-weighted negative users (a plausible mis-restatement of sampler_rating.py:31) are caught
+    bad = dict(gold['rating'], mean_neg_user_degree=float((np.asarray(tra.todense()) > 0).sum(1).astype(float).dot(
+        (np.asarray(tra.todense()) > 0).sum(1)) / tra.nnz))
+    assert samplers.compare_pair_stats(samplers.pair_sampler_stats(tra, 'rating', [next(gen) for _ in range(200)]), bad) is not None
