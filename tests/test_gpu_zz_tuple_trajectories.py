@@ -1,7 +1,10 @@
-"""PRIGP / CPLR on ml-100k for the reference drivers' 50 epochs against the trajectories of the reference's own driver bodies
-(tests/golden/e2e_prigp_refgraph_golden.json, e2e_cplr_refgraph_golden.json).  Collected after every other GPU file: written
-when the round's GPU minutes were spent, so it has not run on a B200 yet; the oracle-side twin runs on the host
-(tests/test_oracle_tuples.py::test_oracle_training_follows_the_reference_driver_runs)."""
+"""Late additions of round 2, collected after every other GPU file because they were written when the round's GPU minutes were
+spent and have not run on a B200 yet (their oracle-side twins run on the host: tests/test_oracle_tuples.py,
+tests/test_oracle_scoring_samplers.py):
+* PRIGP / CPLR on ml-100k for the reference drivers' 50 epochs against the trajectories of the reference's own driver bodies
+  (tests/golden/e2e_prigp_refgraph_golden.json, e2e_cplr_refgraph_golden.json);
+* the device samplers' distributions against the reference's sampler modules run live (tuple_sampler_golden.json,
+  pair_sampler_stats_golden.json)."""
 import json
 import os
 
