@@ -185,3 +185,86 @@ def test_sharded_table_layouts_over_gloo(world, n_items):
         p.join(timeout=60)
     for rank, msg in res:
         assert msg == 'ok', 'rank %d: %s' % (rank, msg)
+
+
+def _metrics_worker(rank, world, port, q):
+    """dist.distributed_evaluate (SURVEY 8e "Metrics": per-user partial sums, one all-reduce) over gloo.  The per-user values
+    come from the CUDA kernel in the product; here the TEST substitutes the oracle's per-user summands for it, so that what
+    runs is the function's own arithmetic: which columns are summed, the user count, mean for CV / sum for LOOV, None for
+    unknown names, the exceptions of ranking.py, a rank without users."""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import types
+        import numpy as np
+        from collaborativefilteringusingtensorflow_b200 import _lib, dist as D
+        from collaborativefilteringusingtensorflow_b200.metrics import ranking as R
+        from oracle import ranking as O
+        _lib.require_cuda = lambda: torch
+
+        def per_user(truth, pred, k, loov=False, device=None):
+            vals = torch.zeros(len(truth), 8, dtype=torch.float64)
+            for t, (y, p) in enumerate(zip(truth, pred.tolist())):
+                p = [x for x in p if x >= 0]
+                if loov:
+                    head = p[:k]
+                    vals[t, 5] = float(y in head)
+                    vals[t, 6] = 1.0 / (head.index(y) + 1) if y in head else 0.0
+                else:
+                    vals[t, :5] = torch.tensor(O.per_user_cv(y, p, k) if len(y) else (0.0, 0.0, 0.0, 0.0, 0.0), dtype=torch.float64)
+            lens = torch.tensor([1 if loov else len(y) for y in truth])
+            return vals, types.SimpleNamespace(row_lengths=lambda: lens)
+        R.per_user = per_user
+        rng = np.random.default_rng(3)                       # the same global problem on every rank
+        n_items, k, T = 60, 7, 23
+        truth = [set(rng.choice(n_items, size=int(rng.integers(1, 6)), replace=False).tolist()) for _ in range(T)]
+        pred = np.stack([rng.permutation(n_items)[:k] for _ in range(T)]).astype(np.int32)
+        owners = world - 1 if world > 2 else world           # world 3: the last rank holds no users
+        cut = [T * r // owners for r in range(owners + 1)] + [T] * (world - owners)
+        lo, hi = cut[rank], cut[rank + 1]
+        names = ['pre', 'recall', 'auc', 'map', 'mrr', 'ndcg']
+        got = D.distributed_evaluate(truth[lo:hi], torch.from_numpy(pred[lo:hi]), names, k, 'cv')
+        want = O.evaluateCV(truth, [p.tolist() for p in pred], names, k)
+        assert got[2] is None and want[2] is None            # unknown metric name -> None (ranking.py:94-109)
+        assert np.allclose([g for g in got if g is not None], [w for w in want if w is not None], rtol=1e-12, atol=0), (got, want)
+        ys = [int(rng.choice(sorted(t))) for t in truth]
+        got = D.distributed_evaluate(ys[lo:hi], torch.from_numpy(pred[lo:hi]), ['hr', 'ndcg', 'arhr'], k, 'loov')
+        want = O.evaluateLOOV(ys, [p.tolist() for p in pred], ['hr', 'ndcg', 'arhr'], k)
+        assert got[1] is None and np.allclose([got[0], got[2]], [want[0], want[2]], rtol=1e-12)      # sums, not means
+        # a user without test items anywhere makes 'map' raise on EVERY rank (ranking.py:53 divides by len(truth))
+        truth2 = list(truth)
+        truth2[0] = set()
+        for m, exc in ((['map'], ZeroDivisionError), (['pre'], None)):
+            try:
+                D.distributed_evaluate(truth2[lo:hi], torch.from_numpy(pred[lo:hi]), m, k, 'cv')
+                raised = None
+            except ZeroDivisionError as e:
+                raised = type(e)
+            assert raised is exc, (m, raised)
+        try:                                                 # k <= 0: ranking.py:12-13's ValueError, on every rank, before the collective
+            D.distributed_evaluate(truth[lo:hi], torch.from_numpy(pred[lo:hi]), names, 0, 'cv')
+            assert False, 'no ValueError'
+        except ValueError:
+            pass
+        q.put((rank, 'ok'))
+    except Exception:
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_sharded_metrics_over_gloo(world):
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_metrics_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in res:
+        assert msg == 'ok', 'rank %d: %s' % (rank, msg)
