@@ -268,3 +268,77 @@ def test_sharded_metrics_over_gloo(world):
         p.join(timeout=60)
     for rank, msg in res:
         assert msg == 'ok', 'rank %d: %s' % (rank, msg)
+
+
+def _als_worker(rank, world, port, q):
+    """dist.DistributedALS (SURVEY 8e "ALS": partial Gram -> all_reduce -> solve the rank's row range -> all_gather) over gloo.
+    The two kernels (cf_als_gram, cf_als_solve_rows) are replaced INSIDE THE TEST by dense float64 stand-ins, so what runs is
+    the class's own sharding: row ranges, which rows feed the partial Gram, the padded all-gather, both sides of a sweep."""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import types
+        import numpy as np
+        from collaborativefilteringusingtensorflow_b200 import _lib, dist as D
+        from oracle import als as oals
+        _lib.require_cuda = lambda: torch
+        rng = np.random.default_rng(17)                      # the same problem on every rank
+        nu, ni, d, weight, reg = 23, 17, 6, 3.0, 0.2
+        Rm = rng.random((nu, ni)) < 0.25
+        U0 = rng.standard_normal((nu, d)).astype(np.float32)
+        V0 = rng.standard_normal((ni, d)).astype(np.float32)
+        eng = types.SimpleNamespace(U=torch.from_numpy(U0.copy()), V=torch.from_numpy(V0.copy()), n_users=nu, n_items=ni, d=d,
+                                    device=torch.device('cpu'))
+
+        def als_gram(Y, G):
+            G[:d, :d] += (Y.double().T @ Y.double()).float()
+
+        def als_solve_rows(X, Y, csr, G):
+            Yd, Gd = Y.double().numpy(), G[:d, :d].double().numpy()
+            for r, cols in enumerate(csr.cols):
+                Yp = Yd[cols]
+                A = Gd + (weight - 1.0) * (Yp.T @ Yp) + reg * np.eye(d)
+                X[r] = torch.from_numpy(np.linalg.solve(A, weight * Yp.sum(0))).float()
+        eng.als_gram, eng.als_solve_rows = als_gram, als_solve_rows
+
+        def local_csr(M, n):
+            lo, hi = D.DistributedALS.row_range(n, world, rank)
+            return types.SimpleNamespace(shape=(hi - lo, M.shape[1]), cols=[np.flatnonzero(M[r]) for r in range(lo, hi)])
+        als = D.DistributedALS(eng, local_csr(Rm, nu), local_csr(Rm.T, ni))
+        assert (als.world, als.rank) == (world, rank)
+        als.half_sweep('users')
+        want_u = oals.half_sweep(V0, [np.flatnonzero(r) for r in Rm], weight, reg)
+        assert np.allclose(eng.U.numpy(), want_u, rtol=2e-4, atol=2e-5), np.abs(eng.U.numpy() - want_u).max()
+        als.half_sweep('items')                              # uses the users just solved, on every rank the full table
+        want_v = oals.half_sweep(eng.U.numpy(), [np.flatnonzero(c) for c in Rm.T], weight, reg)
+        assert np.allclose(eng.V.numpy(), want_v, rtol=2e-4, atol=2e-5), np.abs(eng.V.numpy() - want_v).max()
+        every = [torch.zeros_like(eng.U) for _ in range(world)]
+        dist.all_gather(every, eng.U)
+        assert all(torch.equal(every[0], e) for e in every)  # the replicated tables stay identical across ranks
+        try:
+            D.DistributedALS(eng, types.SimpleNamespace(shape=(nu + 1, ni), cols=[]), None)
+            assert False, 'a CSR of the wrong row range was accepted'
+        except ValueError:
+            pass
+        q.put((rank, 'ok'))
+    except Exception:
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 4])
+def test_sharded_als_over_gloo(world):
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_als_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in res:
+        assert msg == 'ok', 'rank %d: %s' % (rank, msg)
