@@ -840,8 +840,8 @@ def distributed_topk(engine, query_rows, K, train_local_csr, world, rank, group=
     if world == 1:
         return (gidx, val) if gather else (0, gidx, val)
     if gather:
-        all_i = torch.empty(world, T, K, dtype=torch.int32, device=idx.device)
-        all_v = torch.empty(world, T, K, dtype=torch.float64, device=idx.device)
+        all_i = torch.empty(world * T, K, dtype=torch.int32, device=idx.device)       # rank p's [T, K] list at rows [p * T, (p + 1) * T)
+        all_v = torch.empty(world * T, K, dtype=torch.float64, device=idx.device)
         dist.all_gather_into_tensor(all_i, gidx.contiguous(), group=group)
         dist.all_gather_into_tensor(all_v, val.contiguous(), group=group)
         out_i = torch.empty(T, K, dtype=torch.int32, device=idx.device)
@@ -853,8 +853,8 @@ def distributed_topk(engine, query_rows, K, train_local_csr, world, rank, group=
     if c * world != T:      # pad the user dimension so that every rank sends equal chunks
         gidx = torch.cat([gidx, torch.full((c * world - T, K), -1, dtype=torch.int32, device=idx.device)])
         val = torch.cat([val, torch.full((c * world - T, K), float('-inf'), dtype=torch.float64, device=idx.device)])
-    recv_i = torch.empty(world, c, K, dtype=torch.int32, device=idx.device)
-    recv_v = torch.empty(world, c, K, dtype=torch.float64, device=idx.device)
+    recv_i = torch.empty(world * c, K, dtype=torch.int32, device=idx.device)          # rank p's list of MY users at rows [p * c, (p + 1) * c)
+    recv_v = torch.empty(world * c, K, dtype=torch.float64, device=idx.device)
     dist.all_to_all_single(recv_i, gidx.contiguous(), group=group)
     dist.all_to_all_single(recv_v, val.contiguous(), group=group)
     out_i = torch.empty(c, K, dtype=torch.int32, device=idx.device)

@@ -342,3 +342,88 @@ def test_sharded_als_over_gloo(world):
         p.join(timeout=60)
     for rank, msg in res:
         assert msg == 'ok', 'rank %d: %s' % (rank, msg)
+
+
+def _topk_worker(rank, world, port, q):
+    """dist.distributed_topk (SURVEY 8e "Evaluation": local top-K over the rank's `item % P` shard -> exchange -> merge) over
+    gloo, both exchange forms: all-gather + merge of every user on every rank, and the one all-to-all that hands rank r the P
+    lists of ITS slice of the users.  The local top-K kernel and cf_topk_merge are replaced inside the test by numpy
+    stand-ins that follow the kernels' contract (score desc, item id asc; -1 / -inf padding), so what runs is the function's
+    own layout arithmetic: local -> global ids, the stacked gather, the padded slices, lo / n_mine."""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import ctypes
+        import types
+        import numpy as np
+        from collaborativefilteringusingtensorflow_b200 import _lib, dist as D
+        _lib.require_cuda = lambda: torch
+        torch.cuda.current_stream = lambda dev=None: types.SimpleNamespace(cuda_stream=0)
+
+        def view(ptr, n, ct, dt):
+            return np.frombuffer((ct * n).from_address(ptr), dtype=dt)
+
+        def cf_topk_merge(pi, pv, P, T, K, po, pov, stream):       # [P, T, K] lists -> [T, K]: score desc, id asc, -1 padded
+            ii = view(pi, P * T * K, ctypes.c_int32, np.int32).reshape(P, T, K)
+            vv = view(pv, P * T * K, ctypes.c_double, np.float64).reshape(P, T, K)
+            oi = view(po, T * K, ctypes.c_int32, np.int32).reshape(T, K)
+            ov = view(pov, T * K, ctypes.c_double, np.float64).reshape(T, K)
+            for t in range(T):
+                ids, vals = ii[:, t].reshape(-1), vv[:, t].reshape(-1)
+                keep = ids >= 0
+                ids, vals = ids[keep], vals[keep]
+                order = np.lexsort((ids, -vals))[:K]
+                oi[t], ov[t] = -1, -np.inf
+                oi[t, :len(order)], ov[t, :len(order)] = ids[order], vals[order]
+            return 0
+        _lib.lib = lambda: types.SimpleNamespace(cf_topk_merge=cf_topk_merge)
+        rng = np.random.default_rng(23)                      # the same problem on every rank
+        n_items, d, K = 41, 5, 6
+        for T in (11, 2):                                    # 2 users over 3 ranks: a rank's slice is empty
+            Vg = rng.standard_normal((n_items, d))
+            Q = rng.standard_normal((T, d))
+            Vg[7] = Vg[12]                                   # an exact tie across two shards: the lower item id first
+            shard = torch.from_numpy(Vg[rank::world].copy())
+            eng = types.SimpleNamespace(U=None, n_users=0, V=shard)
+
+            def topk(users, k, csr, return_values=True, method='auto', eng=eng):
+                s = eng.U.numpy() @ eng.V.numpy().T          # [T, local items], local ids
+                idx = np.full((s.shape[0], k), -1, np.int32)
+                val = np.full((s.shape[0], k), -np.inf)
+                for t in range(s.shape[0]):
+                    order = np.lexsort((np.arange(s.shape[1]), -s[t]))[:k]
+                    idx[t, :len(order)], val[t, :len(order)] = order, s[t, order]
+                return torch.from_numpy(idx), torch.from_numpy(val)
+            eng.topk = topk
+            full = Q @ Vg.T
+            want = np.stack([np.lexsort((np.arange(n_items), -full[t]))[:K] for t in range(T)]).astype(np.int32)
+            gi, gv = D.distributed_topk(eng, torch.from_numpy(Q), K, None, world, rank)
+            assert eng.U is None and eng.n_users == 0        # the engine's own user table is put back
+            assert np.array_equal(gi.numpy(), want), (gi, want)
+            assert np.allclose(gv.numpy(), np.take_along_axis(full, want.astype(np.int64), 1), rtol=0, atol=1e-12)
+            lo, si, sv = D.distributed_topk(eng, torch.from_numpy(Q), K, None, world, rank, gather=False)
+            c = (T + world - 1) // world
+            assert lo == rank * c and si.shape[0] == max(0, min(T, lo + c) - lo)
+            assert np.array_equal(si.numpy(), want[lo:lo + c]) and np.allclose(sv.numpy(), gv.numpy()[lo:lo + c], rtol=0, atol=0)
+        q.put((rank, 'ok'))
+    except Exception:
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_item_sharded_topk_exchange_over_gloo(world):
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_topk_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in res:
+        assert msg == 'ok', 'rank %d: %s' % (rank, msg)
