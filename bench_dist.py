@@ -241,9 +241,13 @@ def run_distributed(args, rank, world, device):
     clocks = clk.stop(r['t0'], r['t1']) if rank == 0 else None
     topk = None
     if args.topk_users > 0:
-        Tq = min(args.topk_users, wl['n_users'])
-        topk = user_sharded_topk_bench(B_, model, csr, n_items_global, wl, Tq, rank, world, device, pk)
-        topk['item_sharded'] = sharded_topk(B_, model, csr, n_items_global, wl, Tq, rank, world, device, pk)
+        # sub-objects must not cost the line (the same sizes on every rank: a failure lands on every rank alike)
+        try:
+            Tq = min(args.topk_users, wl['n_users'])
+            topk = user_sharded_topk_bench(B_, model, csr, n_items_global, wl, Tq, rank, world, device, pk)
+            topk['item_sharded'] = sharded_topk(B_, model, csr, n_items_global, wl, Tq, rank, world, device, pk)
+        except Exception as e:
+            topk = dict(topk or {}, **B_.sub_error(e))
     line = step_line(B_, wl, args, world, K, Wm, r, n_items_global, tr, pk)
     tr.close()
     del model, csr, tr
@@ -254,14 +258,22 @@ def run_distributed(args, rank, world, device):
     if args.workload == 'c2' and not args.no_c5:
         w5 = dict(B_.WORKLOADS['c5'])
         K5 = max(3, min(K, args.other_steps))
-        m5, csr5, tr5, r5 = sharded_training(B_, w5, args, rank, world, device, w5['n_items'], K5, 3, want_e2e=False)
-        c5 = step_line(B_, w5, args, world, K5, 3, r5, w5['n_items'], tr5, pk)
-        c5['workload'] = w5['desc'] + ' -- at %d GPUs: %d users, %d interactions in total' % (world, world * w5['n_users'], world * csr5.nnz)
-        if args.topk_users > 0:
-            c5['topk'] = user_sharded_topk_bench(B_, m5, csr5, w5['n_items'], w5, min(args.topk_users, w5['n_users']), rank, world, device, pk)
-            c5['topk']['item_sharded'] = sharded_topk(B_, m5, csr5, w5['n_items'], w5, min(args.topk_users, w5['n_users']), rank, world, device, pk)
-        tr5.close()
-        del m5, csr5, tr5
+        m5 = csr5 = tr5 = None
+        try:
+            m5, csr5, tr5, r5 = sharded_training(B_, w5, args, rank, world, device, w5['n_items'], K5, 3, want_e2e=False)
+            c5 = step_line(B_, w5, args, world, K5, 3, r5, w5['n_items'], tr5, pk)
+            c5['workload'] = w5['desc'] + ' -- at %d GPUs: %d users, %d interactions in total' % (world, world * w5['n_users'], world * csr5.nnz)
+            if args.topk_users > 0:
+                c5['topk'] = user_sharded_topk_bench(B_, m5, csr5, w5['n_items'], w5, min(args.topk_users, w5['n_users']), rank, world, device, pk)
+                c5['topk']['item_sharded'] = sharded_topk(B_, m5, csr5, w5['n_items'], w5, min(args.topk_users, w5['n_users']), rank, world, device, pk)
+        except Exception as e:
+            c5 = dict(c5 or {}, **B_.sub_error(e))
+        try:
+            if tr5 is not None:
+                tr5.close()
+        except Exception as e:
+            c5 = dict(c5 or {}, close_error=B_.sub_error(e)['error'])
+        m5 = csr5 = tr5 = None
         torch.cuda.empty_cache()
     als = None
     if args.workload == 'c2' and not args.no_other_configs:
